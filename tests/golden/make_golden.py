@@ -1,0 +1,197 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference modules from
+``/root/reference`` on seeded inputs (build container only: the reference tree does not exist on the GPU box).
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Import shims, created in a temp dir, never inside the reference tree:
+  * ``ot``                 -> ``emd2(a, b, M)`` backed by scipy's linear_sum_assignment (POT is not installed);
+                              only used for the *informational* exact-EMD fixture.
+  * ``normflows``          -> alias of the vendored ``losses/normflows_ishikawa`` package.
+  * ``matplotlib.pyplot``  -> empty stub (imported, never used, by max_spherical_sliced_w.py:4).
+The Sinkhorn files are loaded stand-alone by path.  Outputs: ``*.npz`` with inputs, outputs and autograd gradients.
+"""
+import importlib.util
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.dont_write_bytecode = True
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _install_shims():
+    shim = tempfile.mkdtemp(prefix="shwd_shim_")
+    os.symlink(os.path.join(REF, "Point_Cloud_Resistration/losses/normflows_ishikawa"), os.path.join(shim, "normflows"))
+    os.makedirs(os.path.join(shim, "matplotlib"))
+    open(os.path.join(shim, "matplotlib/__init__.py"), "w").close()
+    open(os.path.join(shim, "matplotlib/pyplot.py"), "w").close()
+    sys.path.insert(0, shim)
+    sys.path.insert(0, os.path.join(REF, "Point_Cloud_Resistration"))
+
+    ot = types.ModuleType("ot")
+
+    class _Emd2(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, a, b, M):
+            from scipy.optimize import linear_sum_assignment
+            Mn = M.detach().double().numpy()
+            r, c = linear_sum_assignment(Mn)
+            plan = np.zeros_like(Mn)
+            plan[r, c] = 1.0 / Mn.shape[0]
+            ctx.save_for_backward(torch.from_numpy(plan).to(M.dtype))
+            return torch.tensor((plan * Mn).sum(), dtype=M.dtype)
+
+        @staticmethod
+        def backward(ctx, g):
+            (plan,) = ctx.saved_tensors
+            return None, None, g * plan
+
+    ot.emd2 = lambda a, b, M: _Emd2.apply(a, b, M)
+    sys.modules["ot"] = ot
+
+
+def sphere_pair(B, N, M, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = F.normalize(torch.randn(B, N, 3, generator=g), dim=-1)
+    # a rotated + noisy copy when N == M, an independent cloud otherwise
+    if N == M:
+        ang = 0.4
+        R = torch.tensor([[1, 0, 0], [0, np.cos(ang), -np.sin(ang)], [0, np.sin(ang), np.cos(ang)]], dtype=torch.float32)
+        y = x @ R.T + 0.05 * torch.randn(B, M, 3, generator=g)
+    else:
+        y = torch.randn(B, M, 3, generator=g)
+    return x.contiguous(), y.contiguous()
+
+
+def grads(loss, *leaves):
+    gs = torch.autograd.grad(loss, leaves)
+    return [g.numpy() for g in gs]
+
+
+def main():
+    _install_shims()
+    torch.set_num_threads(8)
+    sk_cmp = _load(os.path.join(REF, "Comparison_Wasserstein_with_Chamfer_distance/losses/sinkhorn.py"), "ref_sinkhorn_cmp")
+    sk_fix = _load(os.path.join(REF, "Point_Cloud_Resistration/losses/Sinkhorn_fixed.py"), "ref_sinkhorn_fixed")
+    sk_plain = _load(os.path.join(REF, "Point_Cloud_Resistration/losses/Sinkhorn.py"), "ref_sinkhorn_plain")
+    ssw = _load(os.path.join(REF, "Point_Cloud_Resistration/losses/max_spherical_sliced_w.py"), "ref_ssw")
+    import losses as ref_losses  # Point_Cloud_Resistration/losses/__init__.py:27-32
+
+    out = {}
+
+    # ---- 1. the one deterministic smoke of the reference: Sinkhorn_fixed.py:97-110 ------------------------------
+    a = torch.tensor([[[i, 0, 0] for i in range(9)]] * 2)
+    b = torch.tensor([[[i, 8, 0] for i in range(12)]] * 2)
+    for norm in ("L1", "L2"):
+        crit = sk_fix.log_Sinkhorn_Distance_Loss(eps=0.1, max_iter=10, batch_reduction="mean", type_of_cost_norm=norm)
+        loss, P, C = crit(a, b, device="cpu")
+        out[f"smoke_fixed_{norm}"] = np.float64(loss.item())
+    np.savez(os.path.join(HERE, "sinkhorn_fixed_smoke.npz"), a=a.numpy(), b=b.numpy(), **out)
+    print("smoke:", out)
+
+    # ---- 2. log-Sinkhorn classes on random clouds, loss + autograd gradients ------------------------------------
+    def run_sink(tag, cls, kwargs, x, y, cost_override=None, extra=None):
+        x = x.clone().requires_grad_(True)
+        y = y.clone().requires_grad_(True)
+        crit = cls(**kwargs)
+        if cost_override is not None:
+            crit._cost_matrix = cost_override
+        loss, P, C = crit(x, y, "cpu")
+        total = loss if loss.dim() == 0 else loss.sum()
+        gx, gy = grads(total, x, y)
+        d = dict(x=x.detach().numpy(), y=y.detach().numpy(), loss=loss.detach().numpy(), gx=gx, gy=gy,
+                 P=P.detach().numpy() if P.numel() <= 70000 else np.zeros(0, np.float32),
+                 C=C.detach().numpy() if C.numel() <= 70000 else np.zeros(0, np.float32))
+        d.update({k: np.asarray(v) for k, v in kwargs.items() if not isinstance(v, str)})
+        d.update({k: np.asarray(v) for k, v in kwargs.items() if isinstance(v, str)})
+        if extra:
+            d.update(extra)
+        np.savez(os.path.join(HERE, tag + ".npz"), **d)
+        print(tag, "loss", loss.detach().numpy().ravel()[:4], "|gx|", np.linalg.norm(gx), "|gy|", np.linalg.norm(gy))
+
+    x, y = sphere_pair(2, 96, 80, 11)
+    run_sink("sinkhorn_cmp_L2", sk_cmp.log_Sinkhorn_Distance_Loss,
+             dict(eps=0.01, max_iter=100, batch_reduction="mean", type_of_cost_norm="L2"), x, y)
+    run_sink("sinkhorn_cmp_L1_sum", sk_cmp.log_Sinkhorn_Distance_Loss,
+             dict(eps=0.05, max_iter=40, batch_reduction="sum", type_of_cost_norm="L1"), x, y)
+    run_sink("sinkhorn_plain_L2_none", sk_plain.Sinkhorn_Distance_Loss,
+             dict(eps=0.02, max_iter=60, batch_reduction="none", type_of_cost_norm="L2"), x, y)
+    run_sink("sinkhorn_fixed_L2", sk_fix.log_Sinkhorn_Distance_Loss,
+             dict(eps=0.05, max_iter=50, batch_reduction="mean", type_of_cost_norm="L2"), x, y)
+    run_sink("sinkhorn_logN_2", sk_cmp.log_N_Sinkhorn_Distance_Loss,
+             dict(eps=0.05, max_iter=50, batch_reduction="mean", type_of_cost_norm="L2", type_of_Wasserstein_N="2"), x, y)
+    xs, ys = sphere_pair(1, 64, 64, 5)
+    run_sink("sinkhorn_cmp_unbatched", sk_cmp.log_Sinkhorn_Distance_Loss,
+             dict(eps=0.01, max_iter=30, batch_reduction="mean", type_of_cost_norm="L2"), xs[0], ys[0])
+
+    # ---- 3. the north-star composition: reference Sinkhorn recurrence on the reference geodesic cost ------------
+    geo = ref_losses.Geodesic_distance_W(device="cpu", p=2)
+    geo1 = ref_losses.Geodesic_distance_W(device="cpu", p=1)
+    x, y = sphere_pair(2, 128, 128, 1234)
+    x = x * (1.0 + 0.3 * torch.rand(2, 128, 1, generator=torch.Generator().manual_seed(3)))  # not unit-norm on entry
+    run_sink("geodesic_sinkhorn_p2", sk_plain.Sinkhorn_Distance_Loss,
+             dict(eps=0.01, max_iter=100, batch_reduction="mean", type_of_cost_norm="L2"), x, y,
+             cost_override=lambda x, y, p: geo.geodesic_cost_matrix(x, y, 2))
+    run_sink("geodesic_sinkhorn_p1", sk_plain.Sinkhorn_Distance_Loss,
+             dict(eps=0.05, max_iter=50, batch_reduction="none", type_of_cost_norm="L1"), x, y,
+             cost_override=lambda x, y, p: geo1.geodesic_cost_matrix(x, y, 1))
+    x3, y3 = sphere_pair(3, 200, 136, 77)
+    run_sink("geodesic_sinkhorn_p2_ragged", sk_plain.Sinkhorn_Distance_Loss,
+             dict(eps=0.02, max_iter=40, batch_reduction="sum", type_of_cost_norm="L2"), x3, y3,
+             cost_override=lambda x, y, p: geo.geodesic_cost_matrix(x, y, 2))
+
+    # ---- 4. cost matrices + exact-EMD wrappers (informational: needs the scipy-backed ``ot`` shim) ---------------
+    cosw = ref_losses.Cos_disimilarity_W(device="cpu", p=2)
+    x, y = sphere_pair(2, 64, 64, 21)
+    Cg = geo.geodesic_cost_matrix(x, y, 2)
+    Cg1 = geo1.geodesic_cost_matrix(x, y, 1)
+    Cs = cosw.cos_cost_matrix(x, y, 2)
+    np.savez(os.path.join(HERE, "cost_matrices.npz"), x=x.numpy(), y=y.numpy(), geodesic_p2=Cg.numpy(),
+             geodesic_p1=Cg1.numpy(), sqeuclid_p2=Cs.numpy(), sqeuclid_p1=cosw.cos_cost_matrix(x, y, 1).numpy(),
+             exact_emd_geodesic_p2=np.float64(geo(x, y).item()), exact_emd_sqeuclid_p2=np.float64(cosw(x, y).item()))
+
+    # ---- 5. regulariser (s2_wasserstein.py:224-232) --------------------------------------------------------------
+    crit = ref_losses.max_cos_disimilarity_wassersten_distance(phi=None, CSW=None, device="cpu", phi_op=None)
+    xr = torch.randn(3, 50, 3, generator=torch.Generator().manual_seed(9)).requires_grad_(True)
+    reg = crit.regularization_of_normalizing_flow(xr)
+    (gr,) = grads(reg, xr)
+    np.savez(os.path.join(HERE, "regularizer.npz"), x=xr.detach().numpy(), reg=reg.detach().numpy(), gx=gr)
+
+    # ---- 6. spherical sliced W (explicit frames U) --------------------------------------------------------------
+    g = torch.Generator().manual_seed(42)
+    Xs = F.normalize(torch.randn(150, 3, generator=g), dim=-1)
+    Xt = F.normalize(torch.randn(131, 3, generator=g) + torch.tensor([0.5, 0.0, 0.0]), dim=-1)
+    U, _ = torch.linalg.qr(torch.randn(24, 3, 2, generator=g))
+    for p in (1, 2):
+        xs = Xs.clone().requires_grad_(True)
+        xt = Xt.clone().requires_grad_(True)
+        loss = ssw.sliced_cost(xs, xt, U, p=p)
+        gx, gy = grads(loss, xs, xt)
+        np.savez(os.path.join(HERE, f"ssw_p{p}.npz"), Xs=Xs.numpy(), Xt=Xt.numpy(), U=U.numpy(), loss=loss.detach().numpy(),
+                 gx=gx, gy=gy)
+        print(f"ssw p={p}", loss.item())
+    # raw circular W1 on given circle coordinates
+    u = torch.rand(9, 70, generator=g).requires_grad_(True)
+    v = torch.rand(9, 55, generator=g).requires_grad_(True)
+    w = ssw.emd1D_circle(u, v, p=1)
+    gu, gv = grads(w.sum(), u, v)
+    np.savez(os.path.join(HERE, "emd1d_circle.npz"), u=u.detach().numpy(), v=v.detach().numpy(), w=w.detach().numpy(), gu=gu, gv=gv)
+    w2 = ssw.binary_search_circle(u.detach(), v.detach(), p=2)
+    np.savez(os.path.join(HERE, "binary_search_circle_p2.npz"), u=u.detach().numpy(), v=v.detach().numpy(), w=w2.numpy())
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,151 @@
+"""CPU: the oracle restatements reproduce the frozen outputs of the imported reference (tests/golden/*.npz,
+made by tests/golden/make_golden.py) and the reference's one deterministic known answer."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return dict(np.load(os.path.join(G, name + ".npz"), allow_pickle=False))
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def test_known_answer_sinkhorn_fixed_smoke():
+    # Point_Cloud_Resistration/losses/Sinkhorn_fixed.py:97-110
+    d = load("sinkhorn_fixed_smoke")
+    a, b = torch.from_numpy(d["a"]), torch.from_numpy(d["b"])
+    l1 = oracle.log_sinkhorn(a, b, "euclid", 1, 0.1, 10, 1e-9, "mean").item()
+    l2 = oracle.log_sinkhorn(a, b, "euclid", 2, 0.1, 10, 1e-9, "mean").item()
+    assert l1 == pytest.approx(8.621342658996582, rel=1e-7) and l1 == pytest.approx(float(d["smoke_fixed_L1"]), rel=0, abs=0)
+    assert l2 == pytest.approx(8.161666870117188, rel=1e-7) and l2 == pytest.approx(float(d["smoke_fixed_L2"]), rel=0, abs=0)
+
+
+CASES = [
+    # fixture, kind, p, thresh, n_power
+    ("sinkhorn_cmp_L2", "sqeuclid", 2, 1e-9, 1),
+    ("sinkhorn_cmp_L1_sum", "sqeuclid", 1, 1e-9, 1),
+    ("sinkhorn_plain_L2_none", "sqeuclid", 2, None, 1),
+    ("sinkhorn_fixed_L2", "euclid", 2, 1e-9, 1),
+    ("sinkhorn_logN_2", "sqeuclid", 2, 1e-9, 2),
+    ("sinkhorn_cmp_unbatched", "sqeuclid", 2, 1e-9, 1),
+    ("geodesic_sinkhorn_p2", "geodesic", 2, None, 1),
+    ("geodesic_sinkhorn_p1", "geodesic", 1, None, 1),
+    ("geodesic_sinkhorn_p2_ragged", "geodesic", 2, None, 1),
+]
+
+
+@pytest.mark.parametrize("name,kind,p,thresh,n_power", CASES)
+def test_oracle_sinkhorn_matches_reference(name, kind, p, thresh, n_power):
+    d = load(name)
+    x = torch.from_numpy(d["x"]).requires_grad_(True)
+    y = torch.from_numpy(d["y"]).requires_grad_(True)
+    loss = oracle.log_sinkhorn(x, y, kind, p, float(d["eps"]), int(d["max_iter"]), thresh, str(d["batch_reduction"]), n_power)
+    total = loss if loss.dim() == 0 else loss.sum()
+    gx, gy = torch.autograd.grad(total, (x, y))
+    # same torch ops in the same order -> bit-equal on the machine that made the fixture; allow ulp-level drift
+    # across CPU models / thread counts.
+    assert rel(loss.detach().numpy(), d["loss"]) < 2e-6
+    assert rel(gx.numpy(), d["gx"]) < 2e-5
+    assert rel(gy.numpy(), d["gy"]) < 2e-5
+
+
+def test_oracle_cost_matrices():
+    d = load("cost_matrices")
+    x, y = torch.from_numpy(d["x"]), torch.from_numpy(d["y"])
+    for key, kind, p in (("geodesic_p2", "geodesic", 2), ("geodesic_p1", "geodesic", 1), ("sqeuclid_p2", "sqeuclid", 2),
+                         ("sqeuclid_p1", "sqeuclid", 1)):
+        C = oracle.cost_matrix(x, y, kind, p).numpy()
+        assert np.array_equal(C, d[key]), key
+
+
+def test_oracle_exact_emd_standin_matches_reference_wrapper():
+    # informational row: Geodesic_distance_W / Cos_disimilarity_W through the scipy-backed ot shim
+    d = load("cost_matrices")
+    x, y = torch.from_numpy(d["x"]), torch.from_numpy(d["y"])
+    for key, kind in (("exact_emd_geodesic_p2", "geodesic"), ("exact_emd_sqeuclid_p2", "sqeuclid")):
+        C = oracle.cost_matrix(x, y, kind, 2)
+        vals = [oracle.exact_emd2(C[b])[0] ** 0.5 for b in range(C.shape[0])]
+        assert np.mean(vals) == pytest.approx(float(d[key]), rel=1e-5)
+
+
+def test_oracle_regularizer():
+    d = load("regularizer")
+    x = torch.from_numpy(d["x"]).requires_grad_(True)
+    r = oracle.flow_regularization(x)
+    (g,) = torch.autograd.grad(r, x)
+    assert r.item() == pytest.approx(float(d["reg"]), rel=1e-6)
+    assert rel(g.numpy(), d["gx"]) < 1e-6
+
+
+@pytest.mark.parametrize("p", [1, 2])
+def test_oracle_spherical_sliced(p):
+    d = load(f"ssw_p{p}")
+    xs = torch.from_numpy(d["Xs"]).requires_grad_(True)
+    xt = torch.from_numpy(d["Xt"]).requires_grad_(True)
+    U = torch.from_numpy(d["U"])
+    loss = oracle.sliced_wasserstein_sphere(xs, xt, U, p=p)
+    gx, gy = torch.autograd.grad(loss, (xs, xt))
+    assert loss.item() == pytest.approx(float(d["loss"]), rel=2e-6)
+    assert rel(gx.numpy(), d["gx"]) < 1e-5
+    assert rel(gy.numpy(), d["gy"]) < 1e-5
+
+
+def test_oracle_emd1d_circle_and_binary_search():
+    d = load("emd1d_circle")
+    u = torch.from_numpy(d["u"]).requires_grad_(True)
+    v = torch.from_numpy(d["v"]).requires_grad_(True)
+    w = oracle.emd1d_circle(u, v)
+    gu, gv = torch.autograd.grad(w.sum(), (u, v))
+    assert np.array_equal(w.detach().numpy(), d["w"])
+    assert np.array_equal(gu.numpy(), d["gu"]) and np.array_equal(gv.numpy(), d["gv"])
+    d2 = load("binary_search_circle_p2")
+    w2 = oracle.binary_search_circle(torch.from_numpy(d2["u"]), torch.from_numpy(d2["v"]), p=2)
+    assert rel(w2.numpy(), d2["w"]) < 1e-6
+
+
+def test_sphere_map_matches_cosine_similarity_normalisation():
+    # normalise-then-dot is what F.cosine_similarity computes (s2_wasserstein.py:122)
+    torch.manual_seed(0)
+    x = torch.randn(4, 64, 3) * 3
+    y = torch.randn(4, 48, 3)
+    xh = oracle.sphere_map(x, center=False)
+    yh = oracle.sphere_map(y, center=False)
+    dot = (xh.unsqueeze(-2) * yh.unsqueeze(-3)).sum(-1)
+    cs = torch.nn.functional.cosine_similarity(x.unsqueeze(-2), y.unsqueeze(-3), dim=-1)
+    assert torch.equal(dot, cs)
+
+
+def test_chamfer_oracle_manual_gradient():
+    # manual scatter backward equals autograd of the dense restatement
+    torch.manual_seed(1)
+    x = torch.randn(2, 40, 3, requires_grad=True)
+    y = torch.randn(2, 33, 3, requires_grad=True)
+    loss, none = oracle.chamfer_distance(x, y)
+    assert none is None
+    gx, gy = torch.autograd.grad(loss, (x, y))
+    with torch.no_grad():
+        d = ((x.unsqueeze(2) - y.unsqueeze(1)) ** 2).sum(-1)
+        jx = d.argmin(2)
+        iy = d.argmin(1)
+        B, N, M = 2, 40, 33
+        mgx = torch.zeros_like(x)
+        mgy = torch.zeros_like(y)
+        for b in range(B):
+            dx = 2 * (x[b] - y[b][jx[b]]) / N / B
+            mgx[b] += dx
+            mgy[b].index_add_(0, jx[b], -dx)
+            dy = 2 * (y[b] - x[b][iy[b]]) / M / B
+            mgy[b] += dy
+            mgx[b].index_add_(0, iy[b], -dy)
+    assert torch.allclose(gx, mgx, atol=1e-7) and torch.allclose(gy, mgy, atol=1e-7)
