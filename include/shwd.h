@@ -1,0 +1,131 @@
+/*
+ * shwd.h -- C ABI of libshwd_b200.so: the sphere-homeomorphic Wasserstein loss path on B200 (sm_100a).
+ *
+ * The reference (Satoshi0728/Sphere-Homeomorphic-Wasserstein-Distance-for-Point-Cloud-Registration) is pure
+ * Python/torch and has no FFI; its boundary for this path is the Python call signature of the loss objects
+ * (Point_Cloud_Resistration/losses/__init__.py:27-32, Comparison_Wasserstein_with_Chamfer_distance/losses/__init__.py:1-2).
+ * Each entry point below names the reference code it replaces.  The Python mirror of the reference interface lives in
+ * the package's losses/ directory and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors), float32 unless stated;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation, no hidden allocation:
+ *     scratch is passed in and sized by the *_workspace_bytes() helpers;
+ *   - return value: 0 on success, negative code otherwise (shwd_error_string); no exceptions cross the ABI;
+ *   - "packed points" are float4 records (x, y, z, w) -- 16-byte aligned -- produced by shwd_sphere_map_fwd.
+ */
+#ifndef SHWD_H_
+#define SHWD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHWD_OK 0
+#define SHWD_ERR_INVALID_ARGUMENT (-1)
+#define SHWD_ERR_CUDA (-2)
+#define SHWD_ERR_WORKSPACE (-3)
+#define SHWD_ERR_UNSUPPORTED (-4)
+
+/* cost kinds */
+#define SHWD_COST_GEODESIC 0      /* acos(<x^,y^>)^p            s2_wasserstein.py:112-123                       */
+#define SHWD_COST_SQEUCLID 1      /* sum_k |x_k-y_k|^p          s2_wasserstein.py:52-63, Sinkhorn.py:72-82       */
+#define SHWD_COST_EUCLID 2        /* (sum_k |x_k-y_k|^p)^(1/p)  Sinkhorn_fixed.py:79-89                          */
+#define SHWD_COST_ONE_MINUS_COS 3 /* (1-<x^,y^>)^p              max_spherical_w_cos_with_regulation.py:745       */
+
+/* sphere-map flags */
+#define SHWD_MAP_CENTER 1    /* x - mean_n(x)            train_W_COS.py:167-168                                   */
+#define SHWD_MAP_NORMALIZE 2 /* x / max(||x||, 1e-8)     inside F.cosine_similarity, s2_wasserstein.py:122         */
+
+int shwd_version(void);
+const char* shwd_error_string(int code);
+/* number of SMs / max co-resident CTAs the persistent kernels will use on the current device */
+int shwd_device_sm_count(void);
+
+/* ---- sphere map ------------------------------------------------------------------------------------------------
+ * x (B,N,3) contiguous -> xh4 (B,N,4): (x^_0, x^_1, x^_2, 1/max(||x_c||,1e-8)) [w = 1 when not normalising].
+ * Replaces train_W_COS.py:167-168 (centring) + the normalisation F.cosine_similarity applies at s2_wasserstein.py:122.
+ * reg_out (nullable, (B) floats): sum_n | ||x_bn|| - 1 |   (regularization_of_normalizing_flow, s2_wasserstein.py:224-232),
+ * computed on the un-centred, un-normalised input. */
+int shwd_sphere_map_fwd(const float* x, float* xh4, float* reg_out, int B, int N, int flags, void* stream);
+/* g4 (B,N,4) gradient w.r.t. the packed mapped points (w ignored) -> gx (B,N,3) gradient w.r.t. the raw points.
+ * x is the raw input of the forward; xh4 its output.  greg (nullable, (B)): upstream gradient of reg_out. */
+int shwd_sphere_map_bwd(const float* x, const float* xh4, const float* g4, const float* greg, float* gx, int B, int N,
+                        int flags, void* stream);
+
+/* ---- entropic OT on an on-the-fly cost (never materialises N x M) -----------------------------------------------
+ * Replaces the cost matrices (s2_wasserstein.py:52-63,112-123) + the log-domain Sinkhorn recurrence
+ * (Comparison_.../losses/sinkhorn.py:24-58; losses/Sinkhorn.py:25-60; losses/Sinkhorn_fixed.py:32-67).
+ *   x4 (B,N,4), y4 (B,M,4) packed points (unit vectors for the two cosine kinds, raw coordinates otherwise)
+ *   p            cost power; n_power: log_N_Sinkhorn's C^N (1 otherwise)
+ *   eps, iters   entropic regularisation and iteration count L
+ *   early_stop_thresh  <=0: run exactly L iterations (Sinkhorn.py); >0: use the iterate at which the batch-mean L1
+ *                change of u first drops below it (sinkhorn.py:42-44) -- decided on the device, no host sync
+ *   hist_levels  L+1 to keep every iterate (needed by the backward and by early stop) or 1 for forward-only
+ *   alpha_hist (B,hist_levels,N), beta_hist (B,hist_levels,M): log2-domain scaled duals k*u, k*v, k = log2(e)/eps
+ *   row_pc (B,N) = sum_j P_ij C_ij, col_pc (B,M) = sum_i P_ij C_ij, cost (B) = sum_ij P_ij C_ij
+ *   iters_run (1 int, device): the iterate index L* actually used
+ */
+size_t shwd_sinkhorn_workspace_bytes(int B, int N, int M, int iters);
+int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N, int M, int cost_kind, float p, float n_power,
+                      float eps, int iters, float early_stop_thresh, int hist_levels, float* alpha_hist,
+                      float* beta_hist, float* row_pc, float* col_pc, float* cost, int* iters_run, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* Reverse-mode through all L* unrolled iterations (what torch autograd does on the reference).
+ * grad_cost (B): upstream gradient of cost.  g4x (B,N,4), g4y (B,M,4): gradient w.r.t. the packed points. */
+int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N, int M, int cost_kind, float p, float n_power,
+                      float eps, int iters, const float* alpha_hist, const float* beta_hist, const float* row_pc,
+                      const float* col_pc, const int* iters_run, const float* grad_cost, float* g4x, float* g4y,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* status word of the last persistent launch that used `workspace` (0 ok, 1 = an inter-CTA wait timed out). */
+int shwd_sinkhorn_status_offset(void);
+/* Opt-in dense outputs for the reference's (cost, P, C) return (sinkhorn.py:60): P, C (B,N,M), either nullable. */
+int shwd_sinkhorn_plan_dense(const float* x4, const float* y4, int B, int N, int M, int cost_kind, float p,
+                             float n_power, float eps, const float* alpha, const float* beta, int level_stride_n,
+                             int level_stride_m, float* P, float* C, void* stream);
+
+/* ---- Chamfer distance (pytorch3d.loss.chamfer_distance semantics; call sites train_CD.py:123,161, main_rotation.py:203)
+ * x (B,N,3), y (B,M,3) raw contiguous.  d_xy (B,N) = min_j |x_i-y_j|^2, idx_xy (B,N) argmin; d_yx/idx_yx likewise. */
+int shwd_chamfer_fwd(const float* x, const float* y, int B, int N, int M, float* d_xy, int* idx_xy, float* d_yx,
+                     int* idx_yx, void* stream);
+/* gdx (B,N), gdy (B,M): upstream gradients of d_xy, d_yx.  gx (B,N,3), gy (B,M,3) are overwritten. */
+int shwd_chamfer_bwd(const float* x, const float* y, int B, int N, int M, const int* idx_xy, const int* idx_yx,
+                     const float* gdx, const float* gdy, float* gx, float* gy, void* stream);
+
+/* ---- sliced paths ------------------------------------------------------------------------------------------------
+ * Circle projection (sliced_cost, max_spherical_sliced_w.py:270-279): x (B,N,3), U (P,3,2) -> keys (B,P,N) in [0,1]. */
+int shwd_project_circle(const float* x, const float* U, int B, int N, int P, float* keys, void* stream);
+int shwd_project_circle_bwd(const float* x, const float* U, int B, int N, int P, const float* gkeys, float* gx,
+                            void* stream);
+/* Line projection (Flow_ellipsoid.ipynb:208-220): x (B,N,3), theta (P,3) -> keys (B,P,N). */
+int shwd_project_line(const float* x, const float* theta, int B, int N, int P, float* keys, void* stream);
+int shwd_project_line_bwd(const float* theta, int B, int N, int P, const float* gkeys, float* gx, void* stream);
+/* Stable segmented sort (torch.sort(stable=True) order, NaN last, -0 == +0): keys (segs,len) -> sorted (segs,len),
+ * perm (segs,len) int64.  Replaces torch.sort at max_spherical_sliced_w.py:163-164,224-225,232,235. */
+size_t shwd_segmented_sort_workspace_bytes(int segs, int len);
+int shwd_segmented_sort(const float* keys, int segs, int len, float* sorted, int64_t* perm, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* Circular W1 by level median on sorted circle coordinates (emd1D_circle, max_spherical_sliced_w.py:230-247):
+ * us (S,n), vs (S,m) sorted ascending -> w (S); gus/gvs (nullable) receive dW/d(sorted values). */
+size_t shwd_circular_w1_workspace_bytes(int S, int n, int m);
+int shwd_circular_w1(const float* us, const float* vs, int S, int n, int m, float* w, float* gus, float* gvs,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* Euclidean sliced W on sorted projections (Flow_ellipsoid.ipynb:217-219): xs, ys (S,n) sorted -> acc (S) =
+ * sum_n |xs-ys|^p ; gxs/gys (nullable) receive d acc / d(sorted values). */
+int shwd_euclid_sw(const float* xs, const float* ys, int S, int n, float p, float* acc, float* gxs, float* gys,
+                   void* stream);
+/* Scatter gradients of sorted values back through the permutation: gkeys[seg][perm[seg][k]] = gsorted[seg][k]. */
+int shwd_unsort(const float* gsorted, const int64_t* perm, int segs, int len, float* gkeys, void* stream);
+
+/* ---- measurement helpers (bench.py): FP32-FMA and MUFU issue-rate microbenchmarks -------------------------------
+ * out (grid*block floats) scratch; returns the number of lane-ops each launch performs in *ops. */
+int shwd_peak_fp32(float* out, int iters, double* ops, void* stream);
+int shwd_peak_mufu(float* out, int iters, double* ops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHWD_H_ */

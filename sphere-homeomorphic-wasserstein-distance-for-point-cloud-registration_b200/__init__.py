@@ -1,0 +1,15 @@
+"""B200-native sphere-homeomorphic Wasserstein loss path (sm_100a CUDA behind a C ABI, ctypes-bound).
+
+The directory name carries hyphens (it mirrors the upstream repository name), so import it through the ``shwd``
+alias module at the repository root, or put this directory on ``sys.path`` and ``import losses`` for the drop-in
+replacement of the reference's ``losses`` package.
+"""
+from . import _lib, ops
+from .ops import sphere_map, flow_regularization, entropic_ot
+
+__all__ = ["_lib", "ops", "sphere_map", "flow_regularization", "entropic_ot", "build_library"]
+
+
+def build_library(force=False):
+    from . import build as _build
+    return _build.build(force=force)

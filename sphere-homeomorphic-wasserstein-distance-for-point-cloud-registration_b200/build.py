@@ -1,0 +1,73 @@
+"""Build libshwd_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so must travel with the source tree).
+
+    python build.py [--force] [--exact-dot]
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libshwd_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-ftz=true", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
+
+
+def _nvcc():
+    n = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(n):
+        raise RuntimeError("nvcc not found: cannot build libshwd_b200.so")
+    return n
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest(extra):
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)) + ["../../include/shwd.h"]:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + extra).encode())
+    return h.hexdigest()
+
+
+def build(force=False, extra_flags=(), verbose=False):
+    extra = list(extra_flags)
+    os.makedirs(OBJ, exist_ok=True)
+    stamp = os.path.join(OBJ, "stamp")
+    dg = _digest(extra)
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dg:
+        return LIB
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, src[:-3] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        if verbose and (r.stdout or r.stderr):
+            print(r.stdout, r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    cmd = [nvcc, "-shared", "--cudart=static", "-o", LIB] + objs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    with open(stamp, "w") as fh:
+        fh.write(dg)
+    return LIB
+
+
+if __name__ == "__main__":
+    flags = ["-DSHWD_EXACT_DOT"] if "--exact-dot" in sys.argv else []
+    print(build(force="--force" in sys.argv, extra_flags=flags, verbose=True))

@@ -1,0 +1,167 @@
+// Chamfer distance: tiled nearest-neighbour min-reduction, both directions in one launch; deterministic backward.
+//
+// Replaces pytorch3d.loss.chamfer_distance as the reference calls it (Point_Cloud_Resistration/train_CD.py:123,161;
+// Comparison_Wasserstein_with_Chamfer_distance/main_rotation.py:203): squared L2, K = 1.
+//   d_xy[b,i] = min_j |x_i - y_j|^2 (first minimum wins), idx_xy[b,i] = argmin;  d_yx / idx_yx likewise.
+// The squared distance is formed as ((dx*dx + dy*dy) + dz*dz) with separately rounded products so it is bit-equal to
+// torch's ((x-y)**2).sum(-1) -- the argmin indices are then bit-exact against the oracle.
+//
+// One thread owns one query point; the other cloud is streamed through shared memory as float4 records (broadcast
+// LDS.128), 1024 points per tile.  HBM traffic is the algorithmic minimum (12 B/point in, 8 B/point out); the inner
+// loop is FP32-issue bound (8 FP32 + compare/select per pair of points).
+#include "common.cuh"
+
+namespace shwd {
+
+constexpr int CH_THREADS = 256;
+constexpr int CH_TILE = 1024;
+
+__device__ __forceinline__ float sqdist(float ax, float ay, float az, float4 s) {
+  float dx = ax - s.x, dy = ay - s.y, dz = az - s.z;
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// grid.x = query blocks of direction 0 (x queries) followed by direction 1 (y queries); grid.y = B
+__global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int N,
+                                                                 int M, int blocks_x, float* __restrict__ d_xy,
+                                                                 int* __restrict__ idx_xy, float* __restrict__ d_yx,
+                                                                 int* __restrict__ idx_yx) {
+  __shared__ float4 tile[CH_TILE];
+  const int b = blockIdx.y;
+  const bool dir = blockIdx.x >= blocks_x;  // false: x queries against y
+  const int qb = dir ? blockIdx.x - blocks_x : blockIdx.x;
+  const float* q = (dir ? y + (size_t)b * M * 3 : x + (size_t)b * N * 3);
+  const float* r = (dir ? x + (size_t)b * N * 3 : y + (size_t)b * M * 3);
+  const int nq = dir ? M : N, nr = dir ? N : M;
+  const int i = qb * CH_THREADS + threadIdx.x;
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  if (i < nq) {
+    ax = __ldg(q + 3 * i);
+    ay = __ldg(q + 3 * i + 1);
+    az = __ldg(q + 3 * i + 2);
+  }
+  float best = INFINITY;
+  int bi = 0;
+  for (int t0 = 0; t0 < nr; t0 += CH_TILE) {
+    const int cnt = min(CH_TILE, nr - t0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < CH_TILE; j += CH_THREADS) {
+      float4 v = make_float4(INFINITY, INFINITY, INFINITY, 0.f);  // padding never wins: distance = +inf (or NaN)
+      if (j < cnt) v = make_float4(__ldg(r + 3 * (t0 + j)), __ldg(r + 3 * (t0 + j) + 1), __ldg(r + 3 * (t0 + j) + 2), 0.f);
+      tile[j] = v;
+    }
+    __syncthreads();
+    const int lim = (cnt + 3) & ~3;
+#pragma unroll 2
+    for (int j = 0; j < lim; j += 4) {
+      float d0 = sqdist(ax, ay, az, tile[j]);
+      float d1 = sqdist(ax, ay, az, tile[j + 1]);
+      float d2 = sqdist(ax, ay, az, tile[j + 2]);
+      float d3 = sqdist(ax, ay, az, tile[j + 3]);
+      // strict '<' in index order keeps the first minimum
+      if (d0 < best) { best = d0; bi = t0 + j; }
+      if (d1 < best) { best = d1; bi = t0 + j + 1; }
+      if (d2 < best) { best = d2; bi = t0 + j + 2; }
+      if (d3 < best) { best = d3; bi = t0 + j + 3; }
+    }
+  }
+  if (i < nq) {
+    if (dir) {
+      d_yx[(size_t)b * M + i] = best;
+      idx_yx[(size_t)b * M + i] = bi;
+    } else {
+      d_xy[(size_t)b * N + i] = best;
+      idx_xy[(size_t)b * N + i] = bi;
+    }
+  }
+}
+
+// gq_i = 2 g_i (q_i - r_{nn(i)})  +  sum_{j : nn_r(j) == i} 2 h_j (q_i - r_j), the second sum gathered by scanning the
+// other cloud's argmin list in index order (deterministic; no float atomics).
+__global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int N,
+                                                                 int M, int blocks_x, const int* __restrict__ idx_xy,
+                                                                 const int* __restrict__ idx_yx, const float* __restrict__ gdx,
+                                                                 const float* __restrict__ gdy, float* __restrict__ gx,
+                                                                 float* __restrict__ gy) {
+  __shared__ float4 tile[CH_TILE];  // (r_j, h_j)
+  __shared__ int tidx[CH_TILE];
+  const int b = blockIdx.y;
+  const bool dir = blockIdx.x >= blocks_x;
+  const int qb = dir ? blockIdx.x - blocks_x : blockIdx.x;
+  const float* q = (dir ? y + (size_t)b * M * 3 : x + (size_t)b * N * 3);
+  const float* r = (dir ? x + (size_t)b * N * 3 : y + (size_t)b * M * 3);
+  const int nq = dir ? M : N, nr = dir ? N : M;
+  const int* q_nn = dir ? idx_yx + (size_t)b * M : idx_xy + (size_t)b * N;  // nn of each query in r
+  const int* r_nn = dir ? idx_xy + (size_t)b * N : idx_yx + (size_t)b * M;  // nn of each r point in q
+  const float* gq = dir ? gdy + (size_t)b * M : gdx + (size_t)b * N;
+  const float* gr = dir ? gdx + (size_t)b * N : gdy + (size_t)b * M;
+  float* out = dir ? gy + (size_t)b * M * 3 : gx + (size_t)b * N * 3;
+  const int i = qb * CH_THREADS + threadIdx.x;
+  float ax = 0.f, ay = 0.f, az = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+  if (i < nq) {
+    ax = __ldg(q + 3 * i);
+    ay = __ldg(q + 3 * i + 1);
+    az = __ldg(q + 3 * i + 2);
+    const int j = __ldg(q_nn + i);
+    const float g2 = 2.f * __ldg(gq + i);
+    ox = g2 * (ax - __ldg(r + 3 * j));
+    oy = g2 * (ay - __ldg(r + 3 * j + 1));
+    oz = g2 * (az - __ldg(r + 3 * j + 2));
+  }
+  for (int t0 = 0; t0 < nr; t0 += CH_TILE) {
+    const int cnt = min(CH_TILE, nr - t0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < CH_TILE; j += CH_THREADS) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      int k = -1;
+      if (j < cnt) {
+        v = make_float4(__ldg(r + 3 * (t0 + j)), __ldg(r + 3 * (t0 + j) + 1), __ldg(r + 3 * (t0 + j) + 2), 2.f * __ldg(gr + t0 + j));
+        k = __ldg(r_nn + t0 + j);
+      }
+      tile[j] = v;
+      tidx[j] = k;
+    }
+    __syncthreads();
+    for (int j = 0; j < cnt; ++j) {
+      if (tidx[j] == i) {
+        float4 s = tile[j];
+        ox = fmaf(s.w, ax - s.x, ox);
+        oy = fmaf(s.w, ay - s.y, oy);
+        oz = fmaf(s.w, az - s.z, oz);
+      }
+    }
+  }
+  if (i < nq) {
+    out[3 * i] = ox;
+    out[3 * i + 1] = oy;
+    out[3 * i + 2] = oz;
+  }
+}
+
+}  // namespace shwd
+
+using namespace shwd;
+
+extern "C" int shwd_chamfer_fwd(const float* x, const float* y, int B, int N, int M, float* d_xy, int* idx_xy, float* d_yx,
+                                int* idx_yx, void* stream) {
+  if (!x || !y || !d_xy || !idx_xy || !d_yx || !idx_yx || B < 0 || N <= 0 || M <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (B == 0) return SHWD_OK;
+  if (B > 65535) return SHWD_ERR_UNSUPPORTED;
+  const int bx = (N + CH_THREADS - 1) / CH_THREADS, by = (M + CH_THREADS - 1) / CH_THREADS;
+  chamfer_fwd_kernel<<<dim3(bx + by, B), CH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, y, N, M, bx, d_xy, idx_xy, d_yx,
+                                                                                           idx_yx);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+extern "C" int shwd_chamfer_bwd(const float* x, const float* y, int B, int N, int M, const int* idx_xy, const int* idx_yx,
+                                const float* gdx, const float* gdy, float* gx, float* gy, void* stream) {
+  if (!x || !y || !idx_xy || !idx_yx || !gdx || !gdy || !gx || !gy || B < 0 || N <= 0 || M <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (B == 0) return SHWD_OK;
+  if (B > 65535) return SHWD_ERR_UNSUPPORTED;
+  const int bx = (N + CH_THREADS - 1) / CH_THREADS, by = (M + CH_THREADS - 1) / CH_THREADS;
+  chamfer_bwd_kernel<<<dim3(bx + by, B), CH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, y, N, M, bx, idx_xy, idx_yx, gdx, gdy,
+                                                                                           gx, gy);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}

@@ -1,0 +1,195 @@
+// On-the-fly cost evaluation for the entropic OT sweeps (the N x M matrix is never formed).
+//
+// Everything is expressed in the scaled log2 domain: with k = log2(e)/eps the sweeps need k*C_ij, so the functors
+// return kC directly (and, for the backward, d(kC)/d(owner point)).  Kinds:
+//   GEODESIC       acos(<x^,y^>)^p          Point_Cloud_Resistration/losses/s2_wasserstein.py:112-123
+//   SQEUCLID       sum_k |x_k-y_k|^p        s2_wasserstein.py:52-63 (line 62), losses/Sinkhorn.py:72-82
+//   EUCLID         (sum_k |x_k-y_k|^p)^(1/p)  losses/Sinkhorn_fixed.py:79-89
+//   ONE_MINUS_COS  (1-<x^,y^>)^p            losses/max_spherical_w_cos_with_regulation.py:745
+//   n_power        C^N                      Comparison_.../losses/sinkhorn.py:165-176 (log_N_Sinkhorn)
+//
+// Two hand-tuned fast paths (geodesic p=2 -- the north-star configuration -- and squared-Euclidean p=2) plus one
+// generic path that covers every other (kind, p, n_power).
+#pragma once
+#include "common.cuh"
+
+namespace shwd {
+
+enum { FAST_GEO2 = 0, FAST_SQE2 = 1, GENERIC = 2 };
+
+struct CostParams {
+  int kind;
+  float p, npow;
+  float k;    // log2(e)/eps
+  float sk;   // sqrt(k)
+  float q[7]; // qs * Q_i, acos(a) ~= sqrt(1-a) * Q(a) on [0,1] (degree-6 minimax, rel err 1.0e-7);
+              // qs = sqrt(k) on the geodesic fast path (so th*th = k*theta^2 directly), 1 on the generic path
+  float hpi;  // qs * pi/2
+  float gscale;  // constant factor deferred out of the backward inner loop (fast paths)
+};
+
+// acos(a)/sqrt(1-a) on [0,1], degree 6, fitted by tools/fit_acos.py (max rel err 1.03e-7 before rounding).
+#define SHWD_ACOS_Q                                                                                              \
+  { 1.570796132e+00f, -2.145847082e-01f, 8.874903619e-02f, -4.877404124e-02f, 2.684460580e-02f, -1.109675225e-02f, \
+    2.279403852e-03f }
+
+// th = s * acos(c) with all constants pre-multiplied by s (s = sqrt(k) in the fast path, 1 in the generic path).
+// 11 FP32/ALU issue slots + 1 MUFU.  |w| keeps cos values a hair above 1 finite (the reference returns NaN there).
+__device__ __forceinline__ float scaled_acos(const float (&q)[7], float hpi, float c) {
+  float a = fabsf(c);
+  float w = 1.f - a;
+  float r = q[6];
+  r = fmaf(r, a, q[5]);
+  r = fmaf(r, a, q[4]);
+  r = fmaf(r, a, q[3]);
+  r = fmaf(r, a, q[2]);
+  r = fmaf(r, a, q[1]);
+  r = fmaf(r, a, q[0]);
+  float sq = sqrt_approx(fabsf(w));
+  float h = fmaf(-sq, r, hpi);  // s * asin(|c|)
+  float hs = copysignf(h, c);
+  return hpi - hs;
+}
+
+__device__ __forceinline__ float dot3(float ox, float oy, float oz, float sx, float sy, float sz) {
+#ifdef SHWD_EXACT_DOT
+  // ((x0*y0 + x1*y1) + x2*y2) with separately rounded products, as torch's cosine_similarity
+  return __fadd_rn(__fadd_rn(__fmul_rn(ox, sx), __fmul_rn(oy, sy)), __fmul_rn(oz, sz));
+#else
+  return fmaf(oz, sz, fmaf(oy, sy, ox * sx));
+#endif
+}
+
+template <int FAST>
+struct Cost {
+  // forward: k*C
+  static __device__ __forceinline__ float kc(const CostParams& cp, float ox, float oy, float oz, float sx, float sy,
+                                            float sz) {
+    if (FAST == FAST_GEO2) {
+      float th = scaled_acos(cp.q, cp.hpi, dot3(ox, oy, oz, sx, sy, sz));
+      return th * th;
+    } else if (FAST == FAST_SQE2) {
+      float dx = ox - sx, dy = oy - sy, dz = oz - sz;
+      return cp.k * fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    } else {
+      float C;
+      if (cp.kind == SHWD_COST_GEODESIC || cp.kind == SHWD_COST_ONE_MINUS_COS) {
+        float c = dot3(ox, oy, oz, sx, sy, sz);
+        float base = (cp.kind == SHWD_COST_GEODESIC) ? scaled_acos(cp.q, cp.hpi, c) : 1.f - c;
+        C = (cp.p == 1.f) ? base : ((cp.p == 2.f) ? base * base : powf(fmaxf(base, 0.f), cp.p));
+      } else {
+        float dx = fabsf(ox - sx), dy = fabsf(oy - sy), dz = fabsf(oz - sz);
+        float s;
+        if (cp.p == 2.f)
+          s = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        else if (cp.p == 1.f)
+          s = dx + dy + dz;
+        else
+          s = powf(dx, cp.p) + powf(dy, cp.p) + powf(dz, cp.p);
+        C = (cp.kind == SHWD_COST_EUCLID) ? ((cp.p == 2.f) ? sqrtf(s) : ((cp.p == 1.f) ? s : powf(s, 1.f / cp.p))) : s;
+      }
+      if (cp.npow != 1.f) C = powf(C, cp.npow);
+      return cp.k * C;
+    }
+  }
+
+  // backward: k*C and d(kC)/d(owner point) = gscale * gs * (gx, gy, gz)
+  static __device__ __forceinline__ float kc_grad(const CostParams& cp, float ox, float oy, float oz, float sx, float sy,
+                                                 float sz, float& gs, float& gx, float& gy, float& gz) {
+    if (FAST == FAST_GEO2) {
+      // C = theta^2, dC/dcos = -2 theta / sqrt(1 - cos^2) (torch: acos' = -(1 - x*x).rsqrt()).
+      // d(kC)/dx^ = (-2 sqrt(k)) * th * rsqrt(1-c^2) * y^ ; the constant is cp.gscale, applied once per owner.
+      float c = dot3(ox, oy, oz, sx, sy, sz);
+      float th = scaled_acos(cp.q, cp.hpi, c);
+      float rs = rsqrt_approx(fmaxf(fmaf(-c, c, 1.f), 1e-12f));
+      gs = th * rs;
+      gx = sx;
+      gy = sy;
+      gz = sz;
+      return th * th;
+    } else if (FAST == FAST_SQE2) {
+      float dx = ox - sx, dy = oy - sy, dz = oz - sz;  // gscale = 2k
+      gs = 1.f;
+      gx = dx;
+      gy = dy;
+      gz = dz;
+      return cp.k * fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    } else {
+      float C, dCx, dCy, dCz;  // gscale = k
+      if (cp.kind == SHWD_COST_GEODESIC || cp.kind == SHWD_COST_ONE_MINUS_COS) {
+        float c = dot3(ox, oy, oz, sx, sy, sz);
+        float base, dbase;  // base(c), d base / d c
+        if (cp.kind == SHWD_COST_GEODESIC) {
+          base = scaled_acos(cp.q, cp.hpi, c);
+          dbase = -rsqrtf(fmaxf(fmaf(-c, c, 1.f), 1e-12f));
+        } else {
+          base = 1.f - c;
+          dbase = -1.f;
+        }
+        float dC;
+        if (cp.p == 1.f) {
+          C = base;
+          dC = dbase;
+        } else if (cp.p == 2.f) {
+          C = base * base;
+          dC = 2.f * base * dbase;
+        } else {
+          base = fmaxf(base, 0.f);
+          C = powf(base, cp.p);
+          dC = cp.p * powf(base, cp.p - 1.f) * dbase;
+        }
+        dCx = dC * sx;
+        dCy = dC * sy;
+        dCz = dC * sz;
+      } else {
+        float ex = ox - sx, ey = oy - sy, ez = oz - sz;
+        float dx = fabsf(ex), dy = fabsf(ey), dz = fabsf(ez);
+        float s, tx, ty, tz;  // s = sum |d|^p, t = d s / d owner
+        if (cp.p == 2.f) {
+          s = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          tx = 2.f * ex;
+          ty = 2.f * ey;
+          tz = 2.f * ez;
+        } else if (cp.p == 1.f) {
+          s = dx + dy + dz;
+          tx = (ex > 0.f) - (ex < 0.f);
+          ty = (ey > 0.f) - (ey < 0.f);
+          tz = (ez > 0.f) - (ez < 0.f);
+        } else {
+          s = powf(dx, cp.p) + powf(dy, cp.p) + powf(dz, cp.p);
+          tx = copysignf(cp.p * powf(dx, cp.p - 1.f), ex);
+          ty = copysignf(cp.p * powf(dy, cp.p - 1.f), ey);
+          tz = copysignf(cp.p * powf(dz, cp.p - 1.f), ez);
+        }
+        if (cp.kind == SHWD_COST_EUCLID && cp.p != 1.f) {
+          C = (cp.p == 2.f) ? sqrtf(s) : powf(s, 1.f / cp.p);
+          // d s^(1/p) = (1/p) s^(1/p - 1) ds  = C / (p s) ds   (s == 0 -> sub-gradient 0, as torch's pow gives inf*0=nan;
+          // we return 0 there)
+          float f = (s > 0.f) ? C / (cp.p * s) : 0.f;
+          tx *= f;
+          ty *= f;
+          tz *= f;
+        } else {
+          C = s;
+        }
+        dCx = tx;
+        dCy = ty;
+        dCz = tz;
+      }
+      if (cp.npow != 1.f) {
+        float f = cp.npow * powf(C, cp.npow - 1.f);
+        C = powf(C, cp.npow);
+        dCx *= f;
+        dCy *= f;
+        dCz *= f;
+      }
+      gs = 1.f;
+      gx = dCx;
+      gy = dCy;
+      gz = dCz;
+      return cp.k * C;
+    }
+  }
+};
+
+}  // namespace shwd

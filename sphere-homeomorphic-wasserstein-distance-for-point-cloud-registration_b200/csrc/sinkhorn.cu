@@ -1,0 +1,793 @@
+// Entropic OT (log-domain Sinkhorn) on an on-the-fly cost: forward, and reverse-mode through every unrolled
+// iteration.  The N x M cost / kernel / plan matrices are never materialised.
+//
+// Replaces   cost matrices          Point_Cloud_Resistration/losses/s2_wasserstein.py:52-63, 112-123
+//            Sinkhorn recurrence    Comparison_Wasserstein_with_Chamfer_distance/losses/sinkhorn.py:24-58
+//                                   Point_Cloud_Resistration/losses/Sinkhorn.py:25-60, Sinkhorn_fixed.py:32-67
+//            its autograd           (torch reverse-mode over the unrolled loop)
+//
+// Formulation (scaled log2 domain, k = log2(e)/eps, alpha = k u, beta = k v, la2 = log2(1/N + 1e-8), lb2 likewise):
+//     alpha^l_i = la2 - log2 sum_j 2^(beta^{l-1}_j - k C_ij)          ("row" half-step, owners = x points)
+//     beta^l_j  = lb2 - log2 sum_i 2^(alpha^l_i   - k C_ij)           ("col" half-step, owners = y points)
+// which is the reference recurrence  u <- eps (log a - LSE_j M) + u  with the +u/-u pair cancelled analytically.
+// cost = sum_ij P_ij C_ij with P_ij = 2^(alpha^L_i + beta^L_j - k C_ij).
+//
+// Execution model: ONE persistent cooperative launch per direction.  Every half-step is a "sweep": each owner point
+// streams all points of the other cloud (staged in shared memory as float4 (x,y,z,potential) records, broadcast
+// LDS.128) and recomputes dot -> acos -> exp2 in registers on the FP32/SFU pipes (K = 3: tensor cores are useless here).
+// Owners are dealt to the CTAs in 32-owner groups over the flattened (pair, group) space, so the 148 SMs stay
+// balanced for any (B, N).  Inside a CTA the 16 warps split the streamed range; partial results are merged through
+// shared memory in a fixed order (bit-reproducible, no float atomics on the data path).  A half-step of pair b may
+// start once every group of its previous half-step is done: per-pair counters in global memory
+// (release: __syncthreads + __threadfence + atomicAdd; acquire: ld.acquire.gpu spin + __syncthreads).  Pairs never
+// wait on each other.  Iterates are kept in a write-once history (B, L+1, N): no WAR hazards, and the backward
+// replays them in reverse.
+//
+// Backward sweeps (derivation checked against torch autograd to 3e-8 in f64): with S^u,l_ij = 2^(alpha^l_i +
+// beta^{l-1}_j - kC_ij - la2) and S^v,l_ij = 2^(alpha^l_i + beta^l_j - kC_ij - lb2),
+//     row sweep(l):  abar^l_i      = [l=L: g ln2 r_i] - sum_j bbar^l_j S^v,l_ij
+//     col sweep(l):  bbar^{l-1}_j  =                  - sum_i abar^l_i S^u,l_ij
+// and each sweep also adds the cost-gradient terms it can form for its OWNER side without any cross-thread reduction:
+// its own term plus the adjacent other-type term that shares the streamed vector (row sweep(l): S^u,l+1; col sweep(l):
+// S^v,l), i.e. two exp2 per element instead of a 4-value cross-lane reduction per element.
+#include "common.cuh"
+#include "cost.cuh"
+#include <math.h>
+
+namespace shwd {
+
+constexpr int SK_THREADS = 512;
+constexpr int SK_WARPS = SK_THREADS / 32;
+constexpr int GMAX = 8;          // owner groups (of 32) per visit
+constexpr int CHUNK = 2048;      // streamed points staged per pass
+constexpr int CHUNK_PAD = CHUNK + 4 * SK_WARPS;
+constexpr long long WAIT_TIMEOUT_CYCLES = 6000000000LL;  // ~3 s: a lost signal ends the launch instead of hanging the GPU
+constexpr float LN2F = 0.6931471805599453f;
+constexpr float NEG_BIG = -3.0e38f;
+
+enum { MODE_LSE = 0, MODE_FINAL = 1, MODE_BWD = 2 };
+
+struct SinkParams {
+  const float4* X;
+  const float4* Y;
+  int B, N, M;
+  CostParams cp;
+  int iters;
+  int hist_levels;
+  float* alpha;  // (B, hist_levels, N)
+  float* beta;   // (B, hist_levels, M)
+  float* row_pc;
+  float* col_pc;
+  float* cost;
+  int* iters_run;
+  float la2, lb2, inv_k, bval;
+  float thresh;
+  // backward only
+  const float* grad_cost;
+  float4* g4x;
+  float4* g4y;
+  float* abar;  // (2, B, N)
+  float* bbar;  // (2, B, M)
+  // workspace
+  int* done;    // (B)
+  int* status;  // (1)
+  float* err;   // (iters, B)
+};
+
+// Per-(pair, half-step) description of one sweep.
+struct SweepIO {
+  const float4* own;
+  int n_own;
+  const float4* str;
+  int n_str;
+  const float* str_pot;  // nullptr -> 0
+  // MODE_LSE
+  float lconst;
+  float* out_pot;
+  const float* old_pot;  // for the early-stop statistic (nullptr -> 0)
+  float* err_out;        // nullptr -> not recorded
+  // MODE_FINAL
+  const float* own_pot;
+  float* out_pc;
+  float pc_scale;  // 1/k: the sweep accumulates P * (k C)
+  // MODE_BWD
+  const float* str_adj;  // nullptr -> 0
+  float str_adj_scale;
+  const float* own_pot1;  // nullptr -> primary term disabled
+  float c1;
+  const float* own_pot2;  // nullptr -> secondary term disabled
+  float c2;
+  const float* own_adj2;
+  float own_adj2_scale;
+  float fin1, fin2;
+  float* adj_out;  // nullptr -> not written
+  const float* adj_init;
+  float adj_init_scale;
+  float4* G;
+  int G_accumulate;
+};
+
+__device__ __forceinline__ void wait_done(const int* done_b, int target, int* status) {
+  if (threadIdx.x == 0 && target > 0) {
+    if (ld_acquire_gpu(done_b) < target) {
+      long long t0 = clock64();
+      while (ld_acquire_gpu(done_b) < target) {
+        if (*reinterpret_cast<volatile int*>(status) != 0) break;
+        if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
+          atomicExch(status, 1);
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void signal_done(int* done_b, int n) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(done_b, n);
+  }
+}
+
+// One visit-set: owners [lg0, lg1) (32-owner groups) of one pair against all streamed points.
+template <int FAST, int MODE, bool FINAL_TERM>
+__device__ void sweep(const CostParams& cp, const SweepIO& io, int lg0, int lg1, float4* sS, float* sAdj, float4* part) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int v0 = lg0; v0 < lg1; v0 += GMAX) {
+    const int ng = min(GMAX, lg1 - v0);
+    for (int c0 = 0; c0 < io.n_str; c0 += CHUNK) {
+      const int cnt = min(CHUNK, io.n_str - c0);
+      const int SL = (((cnt + SK_WARPS - 1) / SK_WARPS) + 3) & ~3;  // per-warp slice, multiple of 4
+      // ---- stage the streamed chunk: (x, y, z, potential); padding is neutral (potential = -inf, adjoint = 0)
+      for (int j = threadIdx.x; j < SL * SK_WARPS; j += SK_THREADS) {
+        float4 r = make_float4(0.f, 0.f, 0.f, -INFINITY);
+        float a = 0.f;
+        if (j < cnt) {
+          r = __ldg(io.str + c0 + j);
+          r.w = io.str_pot ? __ldcg(io.str_pot + c0 + j) : 0.f;
+          if (MODE == MODE_BWD) a = io.str_adj ? __ldcg(io.str_adj + c0 + j) * io.str_adj_scale : 0.f;
+        }
+        sS[j] = r;
+        if (MODE == MODE_BWD) sAdj[j] = a;
+      }
+      __syncthreads();
+      const int j0 = warp * SL, j1 = j0 + SL;
+      for (int g = 0; g < ng; ++g) {
+        const int o = (v0 + g) * 32 + lane;
+        const bool live = o < io.n_own;
+        float4 op = live ? __ldg(io.own + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* slot = part + (warp * GMAX + g) * 32 + lane;
+        if (MODE == MODE_LSE) {
+          float rm = NEG_BIG, rs = 0.f;
+          if (c0 > 0) {
+            float4 st = *slot;
+            rm = st.x;
+            rs = st.y;
+          }
+#pragma unroll 2
+          for (int j = j0; j < j1; j += 4) {
+            float4 s0 = sS[j], s1 = sS[j + 1], s2 = sS[j + 2], s3 = sS[j + 3];
+            float m0 = s0.w - Cost<FAST>::kc(cp, op.x, op.y, op.z, s0.x, s0.y, s0.z);
+            float m1 = s1.w - Cost<FAST>::kc(cp, op.x, op.y, op.z, s1.x, s1.y, s1.z);
+            float m2 = s2.w - Cost<FAST>::kc(cp, op.x, op.y, op.z, s2.x, s2.y, s2.z);
+            float m3 = s3.w - Cost<FAST>::kc(cp, op.x, op.y, op.z, s3.x, s3.y, s3.z);
+            float nm = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), rm);
+            rs *= ex2_approx(rm - nm);
+            rs += (ex2_approx(m0 - nm) + ex2_approx(m1 - nm)) + (ex2_approx(m2 - nm) + ex2_approx(m3 - nm));
+            rm = nm;
+          }
+          *slot = make_float4(rm, rs, 0.f, 0.f);
+        } else if (MODE == MODE_FINAL) {
+          float acc = (c0 > 0) ? slot->x : 0.f;
+          const float opot = live ? __ldcg(io.own_pot + o) : -INFINITY;
+#pragma unroll 2
+          for (int j = j0; j < j1; j += 4) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float4 s = sS[j + e];
+              float kc = Cost<FAST>::kc(cp, op.x, op.y, op.z, s.x, s.y, s.z);
+              float P = ex2_approx((s.w - kc) + opot);
+              acc = fmaf(P, kc, acc);
+            }
+          }
+          *slot = make_float4(acc, 0.f, 0.f, 0.f);
+        } else {
+          float4 acc = (c0 > 0) ? *slot : make_float4(0.f, 0.f, 0.f, 0.f);
+          float o1 = -INFINITY, o2 = -INFINITY, oadj = 0.f;
+          if (live) {
+            if (io.own_pot1) o1 = __ldcg(io.own_pot1 + o) - io.c1;
+            if (io.own_pot2) {
+              o2 = __ldcg(io.own_pot2 + o) - io.c2;
+              oadj = __ldcg(io.own_adj2 + o) * io.own_adj2_scale;
+            }
+          }
+#pragma unroll 2
+          for (int j = j0; j < j1; j += 2) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              float4 s = sS[j + e];
+              float adj = sAdj[j + e];
+              float gs, vx, vy, vz;
+              float kc = Cost<FAST>::kc_grad(cp, op.x, op.y, op.z, s.x, s.y, s.z, gs, vx, vy, vz);
+              float t = s.w - kc;
+              float S1 = ex2_approx(t + o1);
+              float S2 = ex2_approx(t + o2);
+              float w1 = adj * S1;
+              acc.w += w1;
+              float wt = fmaf(oadj, S2, w1);
+              if (FINAL_TERM) wt = fmaf(fmaf(io.fin1, S1, io.fin2 * S2), fmaf(-LN2F, kc, 1.f), wt);
+              float wg = wt * gs;
+              acc.x = fmaf(wg, vx, acc.x);
+              acc.y = fmaf(wg, vy, acc.y);
+              acc.z = fmaf(wg, vz, acc.z);
+            }
+          }
+          *slot = acc;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- merge the SK_WARPS partials of every owner in fixed order and finish the half-step for these owners
+    float errv = 0.f;
+    if (threadIdx.x < ng * 32) {
+      const int g = threadIdx.x >> 5;
+      const int o = (v0 + g) * 32 + lane;
+      if (o < io.n_own) {
+        if (MODE == MODE_LSE) {
+          float mx = NEG_BIG;
+#pragma unroll
+          for (int w = 0; w < SK_WARPS; ++w) mx = fmaxf(mx, part[(w * GMAX + g) * 32 + lane].x);
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < SK_WARPS; ++w) {
+            float4 st = part[(w * GMAX + g) * 32 + lane];
+            sum += st.y * ex2_approx(st.x - mx);
+          }
+          float np = io.lconst - (mx + log2f(sum));
+          if (io.err_out) errv = fabsf(np - (io.old_pot ? __ldcg(io.old_pot + o) : 0.f));
+          io.out_pot[o] = np;
+        } else if (MODE == MODE_FINAL) {
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < SK_WARPS; ++w) sum += part[(w * GMAX + g) * 32 + lane].x;
+          io.out_pc[o] = sum * io.pc_scale;
+        } else {
+          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int w = 0; w < SK_WARPS; ++w) {
+            float4 st = part[(w * GMAX + g) * 32 + lane];
+            sum.x += st.x;
+            sum.y += st.y;
+            sum.z += st.z;
+            sum.w += st.w;
+          }
+          if (io.adj_out) {
+            float a0 = io.adj_init ? __ldcg(io.adj_init + o) * io.adj_init_scale : 0.f;
+            io.adj_out[o] = a0 - sum.w;
+          }
+          float4 gv = make_float4(sum.x * cp.gscale, sum.y * cp.gscale, sum.z * cp.gscale, 0.f);
+          if (io.G_accumulate) {
+            float4 old = __ldcg(io.G + o);
+            gv.x += old.x;
+            gv.y += old.y;
+            gv.z += old.z;
+          }
+          __stcg(io.G + o, gv);
+        }
+      }
+    }
+    if (MODE == MODE_LSE && io.err_out) {
+      // early-stop statistic sum_i |u_new - u_old| (sinkhorn.py:42): CTA-reduce, one float atomic per visit
+      errv = warp_sum(errv);
+      __shared__ float serr[SK_WARPS];
+      if (lane == 0) serr[warp] = errv;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < SK_WARPS; ++w) t += serr[w];
+        atomicAdd(io.err_out, t);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void cta_range(long long total, int& g0, int& g1) {
+  g0 = (int)((total * blockIdx.x) / gridDim.x);
+  g1 = (int)((total * (blockIdx.x + 1)) / gridDim.x);
+}
+
+// ================================================================================================================
+// Forward: 2L half-steps, then [early stop: pick L*], then the two final sweeps (row/col sums of P*C) and the cost.
+// ================================================================================================================
+template <int FAST>
+__global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkParams prm) {
+  extern __shared__ float4 smem4[];
+  float4* sS = smem4;
+  float4* part = smem4 + CHUNK_PAD;
+  float* sAdj = nullptr;
+  __shared__ int s_ls;
+
+  const int gr = (prm.N + 31) / 32, gc = (prm.M + 31) / 32;  // groups per pair, row / col owners
+  const int HL = prm.hist_levels;
+  const int L = prm.iters;
+  auto slot = [&](int l) { return HL > 1 ? l : 0; };
+
+  // beta^0 = 0 (kept in the history so the backward can stream it)
+  if (HL > 1) {
+    for (long long i = (long long)blockIdx.x * SK_THREADS + threadIdx.x; i < (long long)prm.B * prm.M;
+         i += (long long)gridDim.x * SK_THREADS) {
+      int b = (int)(i / prm.M), j = (int)(i % prm.M);
+      prm.beta[((size_t)b * HL) * prm.M + j] = 0.f;
+    }
+  }
+
+  for (int h = 0; h < 2 * L; ++h) {
+    const int type = h & 1;            // 0: alpha (row owners), 1: beta (col owners)
+    const int l = (h >> 1) + 1;        // level being produced
+    const int gpp = type ? gc : gr;
+    int g0, g1;
+    cta_range((long long)prm.B * gpp, g0, g1);
+    const int target_unit_r = ((h + 1) >> 1), target_unit_c = (h >> 1);  // #row / #col half-steps before h
+    for (int g = g0; g < g1;) {
+      const int b = g / gpp, lg0 = g % gpp;
+      const int lg1 = min(gpp, lg0 + (g1 - g));
+      wait_done(prm.done + b, target_unit_r * gr + target_unit_c * gc, prm.status);
+      SweepIO io;
+      io.lconst = type ? prm.lb2 : prm.la2;
+      io.err_out = nullptr;
+      io.old_pot = nullptr;
+      if (type == 0) {
+        io.own = prm.X + (size_t)b * prm.N;
+        io.n_own = prm.N;
+        io.str = prm.Y + (size_t)b * prm.M;
+        io.n_str = prm.M;
+        io.str_pot = (l == 1) ? nullptr : prm.beta + ((size_t)b * HL + slot(l - 1)) * prm.M;
+        io.out_pot = prm.alpha + ((size_t)b * HL + slot(l)) * prm.N;
+        if (prm.thresh > 0.f) {
+          io.err_out = prm.err + (size_t)(l - 1) * prm.B + b;
+          io.old_pot = (l == 1) ? nullptr : prm.alpha + ((size_t)b * HL + slot(l - 1)) * prm.N;
+        }
+      } else {
+        io.own = prm.Y + (size_t)b * prm.M;
+        io.n_own = prm.M;
+        io.str = prm.X + (size_t)b * prm.N;
+        io.n_str = prm.N;
+        io.str_pot = prm.alpha + ((size_t)b * HL + slot(l)) * prm.N;
+        io.out_pot = prm.beta + ((size_t)b * HL + slot(l)) * prm.M;
+      }
+      sweep<FAST, MODE_LSE, false>(prm.cp, io, lg0, lg1, sS, sAdj, part);
+      signal_done(prm.done + b, lg1 - lg0);
+      g += lg1 - lg0;
+    }
+  }
+
+  // ---- which iterate is the result?  (sinkhorn.py:42-44: first l with mean_b sum_i |u^l - u^{l-1}| < thresh)
+  int Ls = L;
+  if (prm.thresh > 0.f) {
+    for (int b = 0; b < prm.B; ++b) wait_done(prm.done + b, L * (gr + gc), prm.status);
+    if (threadIdx.x == 0) {
+      int found = L;
+      for (int l = 0; l < L; ++l) {
+        float s = 0.f;
+        for (int b = 0; b < prm.B; ++b) s += __ldcg(prm.err + (size_t)l * prm.B + b);
+        // err is in alpha units (k u); the reference tests u
+        if (s * prm.inv_k / prm.B < prm.thresh) {
+          found = l + 1;
+          break;
+        }
+      }
+      s_ls = found;
+    }
+    __syncthreads();
+    Ls = s_ls;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *prm.iters_run = Ls;
+
+  // ---- final sweeps: r_i = sum_j P_ij C_ij (row owners), c_j = sum_i P_ij C_ij (col owners)
+  for (int type = 0; type < 2; ++type) {
+    const int gpp = type ? gc : gr;
+    int g0, g1;
+    cta_range((long long)prm.B * gpp, g0, g1);
+    for (int g = g0; g < g1;) {
+      const int b = g / gpp, lg0 = g % gpp;
+      const int lg1 = min(gpp, lg0 + (g1 - g));
+      wait_done(prm.done + b, L * (gr + gc), prm.status);
+      SweepIO io;
+      io.pc_scale = prm.inv_k;
+      const float* al = prm.alpha + ((size_t)b * HL + slot(Ls)) * prm.N;
+      const float* be = prm.beta + ((size_t)b * HL + slot(Ls)) * prm.M;
+      if (type == 0) {
+        io.own = prm.X + (size_t)b * prm.N;
+        io.n_own = prm.N;
+        io.str = prm.Y + (size_t)b * prm.M;
+        io.n_str = prm.M;
+        io.str_pot = be;
+        io.own_pot = al;
+        io.out_pc = prm.row_pc + (size_t)b * prm.N;
+      } else {
+        io.own = prm.Y + (size_t)b * prm.M;
+        io.n_own = prm.M;
+        io.str = prm.X + (size_t)b * prm.N;
+        io.n_str = prm.N;
+        io.str_pot = al;
+        io.own_pot = be;
+        io.out_pc = prm.col_pc + (size_t)b * prm.M;
+      }
+      sweep<FAST, MODE_FINAL, false>(prm.cp, io, lg0, lg1, sS, sAdj, part);
+      signal_done(prm.done + b, lg1 - lg0);
+      g += lg1 - lg0;
+    }
+  }
+
+  // ---- cost_b = sum_i r_i, summed in a fixed order by the CTA that owns the pair's first row group
+  {
+    int g0, g1;
+    cta_range((long long)prm.B * gr, g0, g1);
+    for (int b = (g0 + gr - 1) / gr; b * gr < g1 && b < prm.B; ++b) {
+      if (b * gr < g0) continue;
+      wait_done(prm.done + b, (L + 1) * (gr + gc), prm.status);
+      float s = 0.f;
+      for (int i = threadIdx.x; i < prm.N; i += SK_THREADS) s += __ldcg(prm.row_pc + (size_t)b * prm.N + i);
+      s = warp_sum(s);
+      __shared__ float sc[SK_WARPS];
+      if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = s;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < SK_WARPS; ++w) t += sc[w];
+        prm.cost[b] = t;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ================================================================================================================
+// Backward: 2L*+1 reverse sweeps.  phase ph < 2L*: l = L* - ph/2, type = ph & 1;  phase 2L*: row sweep(0).
+// ================================================================================================================
+template <int FAST>
+__global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_kernel(const SinkParams prm) {
+  extern __shared__ float4 smem4[];
+  float4* sS = smem4;
+  float4* part = smem4 + CHUNK_PAD;
+  float* sAdj = reinterpret_cast<float*>(part + SK_WARPS * GMAX * 32);
+
+  const int gr = (prm.N + 31) / 32, gc = (prm.M + 31) / 32;
+  const int HL = prm.hist_levels;
+  const int Ls = *prm.iters_run;
+  const size_t BN = (size_t)prm.B * prm.N, BM = (size_t)prm.B * prm.M;
+
+  for (int ph = 0; ph <= 2 * Ls; ++ph) {
+    const bool last = (ph == 2 * Ls);
+    const int type = last ? 0 : (ph & 1);
+    const int l = last ? 0 : Ls - (ph >> 1);
+    const int gpp = type ? gc : gr;
+    const int nrow_before = last ? Ls : ((ph + 1) >> 1), ncol_before = last ? Ls : (ph >> 1);
+    int g0, g1;
+    cta_range((long long)prm.B * gpp, g0, g1);
+    for (int g = g0; g < g1;) {
+      const int b = g / gpp, lg0 = g % gpp;
+      const int lg1 = min(gpp, lg0 + (g1 - g));
+      wait_done(prm.done + b, nrow_before * gr + ncol_before * gc, prm.status);
+      const float gb = __ldg(prm.grad_cost + b);
+      const float* al = prm.alpha + (size_t)b * HL * prm.N;  // level 0
+      const float* be = prm.beta + (size_t)b * HL * prm.M;
+      SweepIO io;
+      io.fin1 = io.fin2 = 0.f;
+      io.adj_init = nullptr;
+      io.adj_init_scale = 0.f;
+      io.G_accumulate = (l != Ls);
+      if (type == 0) {
+        io.own = prm.X + (size_t)b * prm.N;
+        io.n_own = prm.N;
+        io.str = prm.Y + (size_t)b * prm.M;
+        io.n_str = prm.M;
+        io.str_pot = be + (size_t)l * prm.M;
+        io.G = prm.g4x + (size_t)b * prm.N;
+        io.c1 = prm.lb2;
+        io.c2 = prm.la2;
+        if (last) {
+          io.str_adj = nullptr;
+          io.str_adj_scale = 0.f;
+          io.own_pot1 = nullptr;
+          io.adj_out = nullptr;
+        } else {
+          if (l == Ls) {
+            io.str_adj = prm.col_pc + (size_t)b * prm.M;
+            io.str_adj_scale = gb * LN2F;
+            io.adj_init = prm.row_pc + (size_t)b * prm.N;
+            io.adj_init_scale = gb * LN2F;
+            io.fin1 = gb * prm.bval * prm.inv_k;
+          } else {
+            io.str_adj = prm.bbar + (size_t)(l & 1) * BM + (size_t)b * prm.M;
+            io.str_adj_scale = 1.f;
+          }
+          io.own_pot1 = al + (size_t)l * prm.N;
+          io.adj_out = prm.abar + (size_t)(l & 1) * BN + (size_t)b * prm.N;
+        }
+        if (l < Ls) {
+          io.own_pot2 = al + (size_t)(l + 1) * prm.N;
+          io.own_adj2 = prm.abar + (size_t)((l + 1) & 1) * BN + (size_t)b * prm.N;
+          io.own_adj2_scale = 1.f;
+        } else {
+          io.own_pot2 = nullptr;
+          io.own_adj2 = nullptr;
+          io.own_adj2_scale = 0.f;
+        }
+      } else {
+        io.own = prm.Y + (size_t)b * prm.M;
+        io.n_own = prm.M;
+        io.str = prm.X + (size_t)b * prm.N;
+        io.n_str = prm.N;
+        io.str_pot = al + (size_t)l * prm.N;
+        io.str_adj = prm.abar + (size_t)(l & 1) * BN + (size_t)b * prm.N;
+        io.str_adj_scale = 1.f;
+        io.G = prm.g4y + (size_t)b * prm.M;
+        io.own_pot1 = be + (size_t)(l - 1) * prm.M;
+        io.c1 = prm.la2;
+        io.own_pot2 = be + (size_t)l * prm.M;
+        io.c2 = prm.lb2;
+        if (l == Ls) {
+          io.own_adj2 = prm.col_pc + (size_t)b * prm.M;
+          io.own_adj2_scale = gb * LN2F;
+          io.fin2 = gb * prm.bval * prm.inv_k;
+        } else {
+          io.own_adj2 = prm.bbar + (size_t)(l & 1) * BM + (size_t)b * prm.M;
+          io.own_adj2_scale = 1.f;
+        }
+        io.adj_out = prm.bbar + (size_t)((l - 1) & 1) * BM + (size_t)b * prm.M;
+      }
+      if (l == Ls)
+        sweep<FAST, MODE_BWD, true>(prm.cp, io, lg0, lg1, sS, sAdj, part);
+      else
+        sweep<FAST, MODE_BWD, false>(prm.cp, io, lg0, lg1, sS, sAdj, part);
+      signal_done(prm.done + b, lg1 - lg0);
+      g += lg1 - lg0;
+    }
+  }
+}
+
+// Dense plan / cost for the reference's (cost, P, C) return value (opt-in, small problems only).
+template <int FAST>
+__global__ void plan_dense_kernel(const float4* X, const float4* Y, int N, int M, CostParams cp, const float* alpha,
+                                  const float* beta, int sn, int sm, float inv_k, float* P, float* C) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= M) return;
+  float4 x = X[(size_t)b * N + i], y = Y[(size_t)b * M + j];
+  float kc = Cost<FAST>::kc(cp, x.x, x.y, x.z, y.x, y.y, y.z);
+  size_t o = ((size_t)b * N + i) * M + j;
+  if (C) C[o] = kc * inv_k;
+  if (P) P[o] = exp2f(alpha[(size_t)b * sn + i] + beta[(size_t)b * sm + j] - kc);
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  int* done;
+  int* status;
+  float* err;
+  float* abar;
+  float* bbar;
+  size_t head_bytes;  // counters + status + err (memset on every launch)
+  size_t total;
+};
+
+static Workspace carve(void* base, int B, int N, int M, int iters) {
+  Workspace w;
+  size_t off = 0;
+  char* p = static_cast<char*>(base);
+  w.status = reinterpret_cast<int*>(p + off);
+  off += 256;
+  w.done = reinterpret_cast<int*>(p + off);
+  off = align_up(off + sizeof(int) * (size_t)B, 256);
+  w.err = reinterpret_cast<float*>(p + off);
+  off = align_up(off + sizeof(float) * (size_t)B * (size_t)iters, 256);
+  w.head_bytes = off;
+  w.abar = reinterpret_cast<float*>(p + off);
+  off = align_up(off + sizeof(float) * 2 * (size_t)B * N, 256);
+  w.bbar = reinterpret_cast<float*>(p + off);
+  off = align_up(off + sizeof(float) * 2 * (size_t)B * M, 256);
+  w.total = off;
+  return w;
+}
+
+static int pick_fast(int kind, float p, float npow) {
+  if (kind == SHWD_COST_GEODESIC && p == 2.f && npow == 1.f) return FAST_GEO2;
+  if (kind == SHWD_COST_SQEUCLID && p == 2.f && npow == 1.f) return FAST_SQE2;
+  return GENERIC;
+}
+
+static CostParams make_cost(int kind, float p, float npow, float eps, int fast) {
+  CostParams cp;
+  cp.kind = kind;
+  cp.p = p;
+  cp.npow = npow;
+  const double k = 1.4426950408889634 / (double)eps;
+  cp.k = (float)k;
+  cp.sk = (float)sqrt(k);
+  const float q[7] = SHWD_ACOS_Q;
+  const double qs = (fast == FAST_GEO2) ? sqrt(k) : 1.0;
+  for (int i = 0; i < 7; ++i) cp.q[i] = (float)(qs * (double)q[i]);
+  cp.hpi = (float)(qs * 1.5707963267948966);
+  cp.gscale = (fast == FAST_GEO2) ? (float)(-2.0 * sqrt(k)) : ((fast == FAST_SQE2) ? (float)(2.0 * k) : (float)k);
+  return cp;
+}
+
+static void fill_marginals(SinkParams& prm, int N, int M, float eps) {
+  // log(fill_(1.0/n) + 1e-8) in float32, as the reference builds it (sinkhorn.py:25-26,39-40)
+  const float a = (float)(1.0 / (double)N) + 1e-8f, b = (float)(1.0 / (double)M) + 1e-8f;
+  prm.la2 = (float)log2((double)a);
+  prm.lb2 = (float)log2((double)b);
+  prm.bval = b;
+  prm.inv_k = (float)((double)eps / 1.4426950408889634);
+}
+
+template <typename K>
+static int launch_persistent(K kernel, const SinkParams& prm, size_t smem, int max_groups, cudaStream_t s) {
+  static thread_local int configured_dev = -1;
+  (void)configured_dev;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e);
+    return SHWD_ERR_CUDA;
+  }
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SK_THREADS, smem);
+  if (e != cudaSuccess || per_sm < 1) {
+    set_last_cuda_error(e == cudaSuccess ? cudaErrorLaunchOutOfResources : e);
+    return SHWD_ERR_CUDA;
+  }
+  int grid = sm_count();  // one persistent CTA per SM
+  if (grid > max_groups) grid = max_groups;
+  if (grid < 1) grid = 1;
+  void* args[] = {const_cast<SinkParams*>(&prm)};
+  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid), dim3(SK_THREADS), args, smem, s);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e);
+    return SHWD_ERR_CUDA;
+  }
+  return SHWD_OK;
+}
+
+}  // namespace shwd
+
+using namespace shwd;
+
+extern "C" size_t shwd_sinkhorn_workspace_bytes(int B, int N, int M, int iters) {
+  if (B <= 0 || N <= 0 || M <= 0 || iters <= 0) return 0;
+  return carve(nullptr, B, N, M, iters).total;
+}
+
+extern "C" int shwd_sinkhorn_status_offset(void) { return 0; }
+
+static int check_common(const void* x4, const void* y4, int B, int N, int M, float p, float eps, int iters) {
+  if (!x4 || !y4 || B <= 0 || N <= 0 || M <= 0 || iters <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (!(eps > 0.f) || !(p > 0.f)) return SHWD_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(x4) & 15) || (reinterpret_cast<uintptr_t>(y4) & 15)) return SHWD_ERR_INVALID_ARGUMENT;
+  return SHWD_OK;
+}
+
+extern "C" int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N, int M, int cost_kind, float p, float n_power,
+                                 float eps, int iters, float early_stop_thresh, int hist_levels, float* alpha_hist,
+                                 float* beta_hist, float* row_pc, float* col_pc, float* cost, int* iters_run,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(x4, y4, B, N, M, p, eps, iters);
+  if (rc) return rc;
+  if (cost_kind < 0 || cost_kind > 3 || !alpha_hist || !beta_hist || !row_pc || !col_pc || !cost || !iters_run)
+    return SHWD_ERR_INVALID_ARGUMENT;
+  if (hist_levels != 1 && hist_levels != iters + 1) return SHWD_ERR_INVALID_ARGUMENT;
+  if (early_stop_thresh > 0.f && hist_levels == 1) return SHWD_ERR_INVALID_ARGUMENT;
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return SHWD_ERR_WORKSPACE;
+  Workspace w = carve(workspace, B, N, M, iters);
+  if (workspace_bytes < w.total) return SHWD_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SHWD_CUDA_CHECK(cudaMemsetAsync(workspace, 0, w.head_bytes, s));
+
+  const int fast = pick_fast(cost_kind, p, n_power);
+  SinkParams prm = {};
+  prm.X = reinterpret_cast<const float4*>(x4);
+  prm.Y = reinterpret_cast<const float4*>(y4);
+  prm.B = B;
+  prm.N = N;
+  prm.M = M;
+  prm.cp = make_cost(cost_kind, p, n_power, eps, fast);
+  prm.iters = iters;
+  prm.hist_levels = hist_levels;
+  prm.alpha = alpha_hist;
+  prm.beta = beta_hist;
+  prm.row_pc = row_pc;
+  prm.col_pc = col_pc;
+  prm.cost = cost;
+  prm.iters_run = iters_run;
+  prm.thresh = early_stop_thresh;
+  fill_marginals(prm, N, M, eps);
+  prm.done = w.done;
+  prm.status = w.status;
+  prm.err = w.err;
+  const size_t smem = sizeof(float4) * (CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32);
+  const int maxg = B * (((N > M ? N : M) + 31) / 32);
+  switch (fast) {
+    case FAST_GEO2: return launch_persistent(sinkhorn_fwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
+    case FAST_SQE2: return launch_persistent(sinkhorn_fwd_kernel<FAST_SQE2>, prm, smem, maxg, s);
+    default: return launch_persistent(sinkhorn_fwd_kernel<GENERIC>, prm, smem, maxg, s);
+  }
+}
+
+extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N, int M, int cost_kind, float p, float n_power,
+                                 float eps, int iters, const float* alpha_hist, const float* beta_hist, const float* row_pc,
+                                 const float* col_pc, const int* iters_run, const float* grad_cost, float* g4x, float* g4y,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(x4, y4, B, N, M, p, eps, iters);
+  if (rc) return rc;
+  if (cost_kind < 0 || cost_kind > 3 || !alpha_hist || !beta_hist || !row_pc || !col_pc || !iters_run || !grad_cost || !g4x ||
+      !g4y)
+    return SHWD_ERR_INVALID_ARGUMENT;
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return SHWD_ERR_WORKSPACE;
+  Workspace w = carve(workspace, B, N, M, iters);
+  if (workspace_bytes < w.total) return SHWD_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SHWD_CUDA_CHECK(cudaMemsetAsync(workspace, 0, w.head_bytes, s));
+
+  const int fast = pick_fast(cost_kind, p, n_power);
+  SinkParams prm = {};
+  prm.X = reinterpret_cast<const float4*>(x4);
+  prm.Y = reinterpret_cast<const float4*>(y4);
+  prm.B = B;
+  prm.N = N;
+  prm.M = M;
+  prm.cp = make_cost(cost_kind, p, n_power, eps, fast);
+  prm.iters = iters;
+  prm.hist_levels = iters + 1;
+  prm.alpha = const_cast<float*>(alpha_hist);
+  prm.beta = const_cast<float*>(beta_hist);
+  prm.row_pc = const_cast<float*>(row_pc);
+  prm.col_pc = const_cast<float*>(col_pc);
+  prm.iters_run = const_cast<int*>(iters_run);
+  prm.grad_cost = grad_cost;
+  prm.g4x = reinterpret_cast<float4*>(g4x);
+  prm.g4y = reinterpret_cast<float4*>(g4y);
+  fill_marginals(prm, N, M, eps);
+  prm.done = w.done;
+  prm.status = w.status;
+  prm.err = w.err;
+  prm.abar = w.abar;
+  prm.bbar = w.bbar;
+  const size_t smem = sizeof(float4) * (CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32) + sizeof(float) * CHUNK_PAD;
+  const int maxg = B * (((N > M ? N : M) + 31) / 32);
+  switch (fast) {
+    case FAST_GEO2: return launch_persistent(sinkhorn_bwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
+    case FAST_SQE2: return launch_persistent(sinkhorn_bwd_kernel<FAST_SQE2>, prm, smem, maxg, s);
+    default: return launch_persistent(sinkhorn_bwd_kernel<GENERIC>, prm, smem, maxg, s);
+  }
+}
+
+extern "C" int shwd_sinkhorn_plan_dense(const float* x4, const float* y4, int B, int N, int M, int cost_kind, float p,
+                                        float n_power, float eps, const float* alpha, const float* beta, int level_stride_n,
+                                        int level_stride_m, float* P, float* C, void* stream) {
+  if (!x4 || !y4 || B <= 0 || N <= 0 || M <= 0 || !(eps > 0.f)) return SHWD_ERR_INVALID_ARGUMENT;
+  if (P && (!alpha || !beta)) return SHWD_ERR_INVALID_ARGUMENT;
+  if (N > 65535 || B > 65535) return SHWD_ERR_UNSUPPORTED;
+  const int fast = pick_fast(cost_kind, p, n_power);
+  CostParams cp = make_cost(cost_kind, p, n_power, eps, fast);
+  const float inv_k = (float)((double)eps / 1.4426950408889634);
+  dim3 grid((M + 127) / 128, N, B), block(128);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float4* X = reinterpret_cast<const float4*>(x4);
+  const float4* Y = reinterpret_cast<const float4*>(y4);
+  switch (fast) {
+    case FAST_GEO2:
+      plan_dense_kernel<FAST_GEO2><<<grid, block, 0, s>>>(X, Y, N, M, cp, alpha, beta, level_stride_n, level_stride_m, inv_k, P, C);
+      break;
+    case FAST_SQE2:
+      plan_dense_kernel<FAST_SQE2><<<grid, block, 0, s>>>(X, Y, N, M, cp, alpha, beta, level_stride_n, level_stride_m, inv_k, P, C);
+      break;
+    default:
+      plan_dense_kernel<GENERIC><<<grid, block, 0, s>>>(X, Y, N, M, cp, alpha, beta, level_stride_n, level_stride_m, inv_k, P, C);
+  }
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
