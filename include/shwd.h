@@ -65,7 +65,9 @@ int shwd_sphere_map_bwd(const float* x, const float* xh4, const float* g4, const
  *   early_stop_thresh  <=0: run exactly L iterations (Sinkhorn.py); >0: use the iterate at which the batch-mean L1
  *                change of u first drops below it (sinkhorn.py:42-44) -- decided on the device, no host sync
  *   hist_levels  L+1 to keep every iterate (needed by the backward and by early stop) or 1 for forward-only
- *   alpha_hist (B,hist_levels,N), beta_hist (B,hist_levels,M): log2-domain scaled duals k*u, k*v, k = log2(e)/eps
+ *   alpha_hist (2,B,hist_levels,N), beta_hist (2,B,hist_levels,M): plane 0 = log2-domain scaled duals k*u, k*v
+ *                (k = log2(e)/eps) of every iterate; plane 1 = the float32 rounding residual of each stored value
+ *                (the backward normalises its softmax factors with the unrounded log-sum-exp)
  *   row_pc (B,N) = sum_j P_ij C_ij, col_pc (B,M) = sum_i P_ij C_ij, cost (B) = sum_ij P_ij C_ij
  *   iters_run (1 int, device): the iterate index L* actually used
  */

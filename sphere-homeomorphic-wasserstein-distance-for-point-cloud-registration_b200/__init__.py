@@ -5,9 +5,11 @@ alias module at the repository root, or put this directory on ``sys.path`` and `
 replacement of the reference's ``losses`` package.
 """
 from . import _lib, ops
-from .ops import sphere_map, flow_regularization, entropic_ot
+from .ops import (sphere_map, flow_regularization, entropic_ot, chamfer_nn, segmented_sort_raw, spherical_sliced_w1,
+                  euclid_sliced_w)
 
-__all__ = ["_lib", "ops", "sphere_map", "flow_regularization", "entropic_ot", "build_library"]
+__all__ = ["_lib", "ops", "sphere_map", "flow_regularization", "entropic_ot", "chamfer_nn", "segmented_sort_raw",
+           "spherical_sliced_w1", "euclid_sliced_w", "build_library"]
 
 
 def build_library(force=False):

@@ -60,17 +60,37 @@ __device__ __forceinline__ float dot3(float ox, float oy, float oz, float sx, fl
 #endif
 }
 
+// Per-element cost evaluation.  `E` carries the one expensive intermediate; `m(e, pot)` is THE canonical
+// float32 evaluation of (pot - k*C): every sweep (forward and backward) that needs the exponent of a given forward
+// half-step calls it with that half-step's streamed potential, so the backward reproduces the forward's roundings
+// bit for bit and its softmax factors stay normalised to ~1e-7 (the gradient has a C/eps-fold cancellation between
+// the direct term and the adjoint terms, SURVEY.md B.6, which amplifies any inconsistency).
 template <int FAST>
 struct Cost {
-  // forward: k*C
-  static __device__ __forceinline__ float kc(const CostParams& cp, float ox, float oy, float oz, float sx, float sy,
-                                            float sz) {
+  struct E {
+    float a;  // FAST_GEO2: th = sqrt(k)*theta | FAST_SQE2: |x-y|^2 | GENERIC: k*C
+  };
+
+  static __device__ __forceinline__ float m(const CostParams& cp, E e, float pot) {
+    if (FAST == FAST_GEO2) return fmaf(-e.a, e.a, pot);
+    if (FAST == FAST_SQE2) return fmaf(-cp.k, e.a, pot);
+    return __fsub_rn(pot, e.a);
+  }
+  static __device__ __forceinline__ float kc(const CostParams& cp, E e) {
+    if (FAST == FAST_GEO2) return __fmul_rn(e.a, e.a);
+    if (FAST == FAST_SQE2) return __fmul_rn(cp.k, e.a);
+    return e.a;
+  }
+
+  // forward
+  static __device__ __forceinline__ E eval(const CostParams& cp, float ox, float oy, float oz, float sx, float sy,
+                                           float sz) {
+    E e;
     if (FAST == FAST_GEO2) {
-      float th = scaled_acos(cp.q, cp.hpi, dot3(ox, oy, oz, sx, sy, sz));
-      return th * th;
+      e.a = scaled_acos(cp.q, cp.hpi, dot3(ox, oy, oz, sx, sy, sz));
     } else if (FAST == FAST_SQE2) {
       float dx = ox - sx, dy = oy - sy, dz = oz - sz;
-      return cp.k * fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      e.a = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     } else {
       float C;
       if (cp.kind == SHWD_COST_GEODESIC || cp.kind == SHWD_COST_ONE_MINUS_COS) {
@@ -89,31 +109,32 @@ struct Cost {
         C = (cp.kind == SHWD_COST_EUCLID) ? ((cp.p == 2.f) ? sqrtf(s) : ((cp.p == 1.f) ? s : powf(s, 1.f / cp.p))) : s;
       }
       if (cp.npow != 1.f) C = powf(C, cp.npow);
-      return cp.k * C;
+      e.a = __fmul_rn(cp.k, C);
     }
+    return e;
   }
 
-  // backward: k*C and d(kC)/d(owner point) = gscale * gs * (gx, gy, gz)
-  static __device__ __forceinline__ float kc_grad(const CostParams& cp, float ox, float oy, float oz, float sx, float sy,
-                                                 float sz, float& gs, float& gx, float& gy, float& gz) {
+  // backward: the same E (bit-identical to eval) plus d(kC)/d(owner point) = gscale * gs * (gx, gy, gz)
+  static __device__ __forceinline__ E eval_grad(const CostParams& cp, float ox, float oy, float oz, float sx, float sy,
+                                                float sz, float& gs, float& gx, float& gy, float& gz) {
+    E e;
     if (FAST == FAST_GEO2) {
       // C = theta^2, dC/dcos = -2 theta / sqrt(1 - cos^2) (torch: acos' = -(1 - x*x).rsqrt()).
       // d(kC)/dx^ = (-2 sqrt(k)) * th * rsqrt(1-c^2) * y^ ; the constant is cp.gscale, applied once per owner.
       float c = dot3(ox, oy, oz, sx, sy, sz);
-      float th = scaled_acos(cp.q, cp.hpi, c);
+      e.a = scaled_acos(cp.q, cp.hpi, c);
       float rs = rsqrt_approx(fmaxf(fmaf(-c, c, 1.f), 1e-12f));
-      gs = th * rs;
+      gs = e.a * rs;
       gx = sx;
       gy = sy;
       gz = sz;
-      return th * th;
     } else if (FAST == FAST_SQE2) {
       float dx = ox - sx, dy = oy - sy, dz = oz - sz;  // gscale = 2k
       gs = 1.f;
       gx = dx;
       gy = dy;
       gz = dz;
-      return cp.k * fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      e.a = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     } else {
       float C, dCx, dCy, dCz;  // gscale = k
       if (cp.kind == SHWD_COST_GEODESIC || cp.kind == SHWD_COST_ONE_MINUS_COS) {
@@ -163,8 +184,7 @@ struct Cost {
         }
         if (cp.kind == SHWD_COST_EUCLID && cp.p != 1.f) {
           C = (cp.p == 2.f) ? sqrtf(s) : powf(s, 1.f / cp.p);
-          // d s^(1/p) = (1/p) s^(1/p - 1) ds  = C / (p s) ds   (s == 0 -> sub-gradient 0, as torch's pow gives inf*0=nan;
-          // we return 0 there)
+          // d s^(1/p) = C / (p s) ds   (s == 0: torch's pow backward gives inf*0 = nan; we return the sub-gradient 0)
           float f = (s > 0.f) ? C / (cp.p * s) : 0.f;
           tx *= f;
           ty *= f;
@@ -187,8 +207,9 @@ struct Cost {
       gx = dCx;
       gy = dCy;
       gz = dCz;
-      return cp.k * C;
+      e.a = __fmul_rn(cp.k, C);
     }
+    return e;
   }
 };
 

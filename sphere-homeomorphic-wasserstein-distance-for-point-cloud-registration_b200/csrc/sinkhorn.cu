@@ -54,8 +54,10 @@ struct SinkParams {
   CostParams cp;
   int iters;
   int hist_levels;
-  float* alpha;  // (B, hist_levels, N)
+  float* alpha;  // (B, hist_levels, N)   stored iterate (what the next half-step consumes)
   float* beta;   // (B, hist_levels, M)
+  float* alpha_lo;  // same shape: residual (la2 - lse2) - alpha of the float32 rounding, kept so the backward's
+  float* beta_lo;   // softmax factors are normalised by the UNROUNDED log-sum-exp (see sweep())
   float* row_pc;
   float* col_pc;
   float* cost;
@@ -84,25 +86,37 @@ struct SweepIO {
   // MODE_LSE
   float lconst;
   float* out_pot;
+  float* out_pot_lo;     // nullptr -> residual not kept
   const float* old_pot;  // for the early-stop statistic (nullptr -> 0)
   float* err_out;        // nullptr -> not recorded
-  // MODE_FINAL
+  // MODE_FINAL: the plan is evaluated in its column-normalised form P_ij = b * S^v,L_ij,
+  //   S^v,L_ij = 2^(fl(M(alpha^L_i) + fl(beta^L_j + lo_j - lb2))) * 2^res_j,
+  // i.e. with exactly the roundings of the last beta half-step, so P and the softmax factor it cancels against in the
+  // backward are the same float32 numbers.
   const float* own_pot;
+  const float* own_lo;   // residual plane of own_pot (column sweep)
+  int own_is_beta;       // 0: owners are x (row sums r_i); 1: owners are y (column sums c_j)
   float* out_pc;
-  float pc_scale;  // 1/k: the sweep accumulates P * (k C)
-  // MODE_BWD
+  float pc_scale;        // bval / k: the sweep accumulates S * (k C)
+  // MODE_BWD.  primary   S1 = 2^(fl(M(own_pot1) + sadd_j)) * 2^res_j,  sadd_j = fl(str_pot_j - c1), res folded into adj
+  //            secondary S2 = 2^(fl(M(str_pot_j) + o2))    * 2^res2,   o2 = fl(own_pot2 - c2),     res2 folded into oadj
   const float* str_adj;  // nullptr -> 0
   float str_adj_scale;
-  const float* own_pot1;  // nullptr -> primary term disabled
+  const float* str_lo;   // residual plane of the streamed potential (nullptr -> 0)
   float c1;
+  const float* own_pot1;  // nullptr -> primary term disabled
   const float* own_pot2;  // nullptr -> secondary term disabled
   float c2;
+  const float* own_lo2;
   const float* own_adj2;
   float own_adj2_scale;
-  float fin1, fin2;
+  // FINAL sweeps (l = L*): the direct term g P (1 - C/eps) and the first adjoint term share S^v,L and are combined
+  // analytically: weight = g (b/k) S' [1 + ln2 (k lambda_j - kC_ij)], lambda_j = c_j / b the column-mean cost; likewise
+  // abar^L_i = g ln2 (b/k) sum_j S'_ij (kC_ij - k lambda_j).  No difference of separately rounded large terms is formed.
+  const float* fin_cpc;   // col_pc of the pair (c_j)
+  float fin_A;            // g_b * bval / k
+  float fin_klam_scale;   // k / bval
   float* adj_out;  // nullptr -> not written
-  const float* adj_init;
-  float adj_init_scale;
   float4* G;
   int G_accumulate;
 };
@@ -133,7 +147,8 @@ __device__ __forceinline__ void signal_done(int* done_b, int n) {
 
 // One visit-set: owners [lg0, lg1) (32-owner groups) of one pair against all streamed points.
 template <int FAST, int MODE, bool FINAL_TERM>
-__device__ void sweep(const CostParams& cp, const SweepIO& io, int lg0, int lg1, float4* sS, float* sAdj, float4* part) {
+__device__ void sweep(const CostParams& cp, const SweepIO& io, int lg0, int lg1, float4* sS, float2* sAdj, float4* part) {
+  typedef Cost<FAST> CF;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int v0 = lg0; v0 < lg1; v0 += GMAX) {
     const int ng = min(GMAX, lg1 - v0);
@@ -143,14 +158,29 @@ __device__ void sweep(const CostParams& cp, const SweepIO& io, int lg0, int lg1,
       // ---- stage the streamed chunk: (x, y, z, potential); padding is neutral (potential = -inf, adjoint = 0)
       for (int j = threadIdx.x; j < SL * SK_WARPS; j += SK_THREADS) {
         float4 r = make_float4(0.f, 0.f, 0.f, -INFINITY);
-        float a = 0.f;
+        float2 a = make_float2(0.f, -INFINITY);
+        if (MODE == MODE_BWD && FINAL_TERM && !io.own_is_beta) r.w = 0.f;  // here .w carries k*lambda_j (0 * inf = NaN otherwise)
         if (j < cnt) {
           r = __ldg(io.str + c0 + j);
           r.w = io.str_pot ? __ldcg(io.str_pot + c0 + j) : 0.f;
-          if (MODE == MODE_BWD) a = io.str_adj ? __ldcg(io.str_adj + c0 + j) * io.str_adj_scale : 0.f;
+          if (MODE == MODE_BWD || (MODE == MODE_FINAL && !io.own_is_beta)) {
+            // the streamed potential normalises the primary softmax: apply (pot + lo - c1) as a float32 addend plus a
+            // multiplicative correction 2^res folded into the adjoint, so the normalisation is exact to ~1e-7
+            const double full = (double)r.w + (io.str_lo ? (double)__ldcg(io.str_lo + c0 + j) : 0.0) - (double)io.c1;
+            a.y = (float)full;
+            const float corr = exp2f((float)(full - (double)a.y));
+            if (MODE == MODE_FINAL) {
+              a.x = corr;
+            } else if (FINAL_TERM && !io.own_is_beta) {
+              a.x = io.fin_A * corr;
+              r.w = __ldcg(io.fin_cpc + c0 + j) * io.fin_klam_scale;  // k * lambda_j (the secondary term is off at l = L*)
+            } else {
+              a.x = io.str_adj ? __ldcg(io.str_adj + c0 + j) * io.str_adj_scale * corr : 0.f;
+            }
+          }
         }
         sS[j] = r;
-        if (MODE == MODE_BWD) sAdj[j] = a;
+        if (MODE != MODE_LSE) sAdj[j] = a;
       }
       __syncthreads();
       const int j0 = warp * SL, j1 = j0 + SL;
@@ -169,10 +199,10 @@ __device__ void sweep(const CostParams& cp, const SweepIO& io, int lg0, int lg1,
 #pragma unroll 2
           for (int j = j0; j < j1; j += 4) {
             float4 s0 = sS[j], s1 = sS[j + 1], s2 = sS[j + 2], s3 = sS[j + 3];
-            float m0 = s0.w - Cost<FAST>::kc(cp, op.x, op.y, op.z, s0.x, s0.y, s0.z);
-            float m1 = s1.w - Cost<FAST>::kc(cp, op.x, op.y, op.z, s1.x, s1.y, s1.z);
-            float m2 = s2.w - Cost<FAST>::kc(cp, op.x, op.y, op.z, s2.x, s2.y, s2.z);
-            float m3 = s3.w - Cost<FAST>::kc(cp, op.x, op.y, op.z, s3.x, s3.y, s3.z);
+            float m0 = CF::m(cp, CF::eval(cp, op.x, op.y, op.z, s0.x, s0.y, s0.z), s0.w);
+            float m1 = CF::m(cp, CF::eval(cp, op.x, op.y, op.z, s1.x, s1.y, s1.z), s1.w);
+            float m2 = CF::m(cp, CF::eval(cp, op.x, op.y, op.z, s2.x, s2.y, s2.z), s2.w);
+            float m3 = CF::m(cp, CF::eval(cp, op.x, op.y, op.z, s3.x, s3.y, s3.z), s3.w);
             float nm = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), rm);
             rs *= ex2_approx(rm - nm);
             rs += (ex2_approx(m0 - nm) + ex2_approx(m1 - nm)) + (ex2_approx(m2 - nm) + ex2_approx(m3 - nm));
@@ -181,26 +211,42 @@ __device__ void sweep(const CostParams& cp, const SweepIO& io, int lg0, int lg1,
           *slot = make_float4(rm, rs, 0.f, 0.f);
         } else if (MODE == MODE_FINAL) {
           float acc = (c0 > 0) ? slot->x : 0.f;
-          const float opot = live ? __ldcg(io.own_pot + o) : -INFINITY;
+          float opot = live ? __ldcg(io.own_pot + o) : -INFINITY;
+          const bool col = io.own_is_beta != 0;
+          if (col && live) opot = (float)((double)opot + (double)__ldcg(io.own_lo + o) - (double)io.c2);  // o2 of S^v,L
 #pragma unroll 2
           for (int j = j0; j < j1; j += 4) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float4 s = sS[j + e];
-              float kc = Cost<FAST>::kc(cp, op.x, op.y, op.z, s.x, s.y, s.z);
-              float P = ex2_approx((s.w - kc) + opot);
-              acc = fmaf(P, kc, acc);
+              typename CF::E ce = CF::eval(cp, op.x, op.y, op.z, s.x, s.y, s.z);
+              float S;
+              if (col) {
+                S = ex2_approx(__fadd_rn(CF::m(cp, ce, s.w), opot));
+              } else {
+                float2 ad = sAdj[j + e];
+                S = ex2_approx(__fadd_rn(CF::m(cp, ce, opot), ad.y)) * ad.x;
+              }
+              acc = fmaf(S, CF::kc(cp, ce), acc);
             }
           }
           *slot = make_float4(acc, 0.f, 0.f, 0.f);
         } else {
           float4 acc = (c0 > 0) ? *slot : make_float4(0.f, 0.f, 0.f, 0.f);
-          float o1 = -INFINITY, o2 = -INFINITY, oadj = 0.f;
+          float opot1 = -INFINITY, o2 = -INFINITY, oadj = 0.f, oklam = 0.f;
+          const bool col = io.own_is_beta != 0;
           if (live) {
-            if (io.own_pot1) o1 = __ldcg(io.own_pot1 + o) - io.c1;
+            if (io.own_pot1) opot1 = __ldcg(io.own_pot1 + o);
             if (io.own_pot2) {
-              o2 = __ldcg(io.own_pot2 + o) - io.c2;
-              oadj = __ldcg(io.own_adj2 + o) * io.own_adj2_scale;
+              const double full = (double)__ldcg(io.own_pot2 + o) + (io.own_lo2 ? (double)__ldcg(io.own_lo2 + o) : 0.0) - (double)io.c2;
+              o2 = (float)full;
+              const float corr = exp2f((float)(full - (double)o2));
+              if (FINAL_TERM && col) {
+                oadj = io.fin_A * corr;
+                oklam = __ldcg(io.fin_cpc + o) * io.fin_klam_scale;
+              } else {
+                oadj = __ldcg(io.own_adj2 + o) * io.own_adj2_scale * corr;
+              }
             }
           }
 #pragma unroll 2
@@ -208,16 +254,29 @@ __device__ void sweep(const CostParams& cp, const SweepIO& io, int lg0, int lg1,
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               float4 s = sS[j + e];
-              float adj = sAdj[j + e];
+              float2 ad = sAdj[j + e];
               float gs, vx, vy, vz;
-              float kc = Cost<FAST>::kc_grad(cp, op.x, op.y, op.z, s.x, s.y, s.z, gs, vx, vy, vz);
-              float t = s.w - kc;
-              float S1 = ex2_approx(t + o1);
-              float S2 = ex2_approx(t + o2);
-              float w1 = adj * S1;
-              acc.w += w1;
-              float wt = fmaf(oadj, S2, w1);
-              if (FINAL_TERM) wt = fmaf(fmaf(io.fin1, S1, io.fin2 * S2), fmaf(-LN2F, kc, 1.f), wt);
+              typename CF::E ce = CF::eval_grad(cp, op.x, op.y, op.z, s.x, s.y, s.z, gs, vx, vy, vz);
+              float S1 = ex2_approx(__fadd_rn(CF::m(cp, ce, opot1), ad.y));
+              float wt;
+              if (FINAL_TERM && !col) {
+                // row sweep(L*): u = g (b/k) S'_ij ; weight u [1 + ln2 (k lambda_j - kC)] ; abar accumulates u (kC - k lambda_j)
+                float u = ad.x * S1;
+                float d = __fsub_rn(s.w, CF::kc(cp, ce));
+                acc.w = fmaf(u, d, acc.w);
+                wt = fmaf(u * LN2F, d, u);
+              } else {
+                float S2 = ex2_approx(__fadd_rn(CF::m(cp, ce, s.w), o2));
+                float w1 = ad.x * S1;
+                acc.w += w1;
+                if (FINAL_TERM) {  // col sweep(L*): secondary + direct term combined the same way
+                  float u = oadj * S2;
+                  float d = __fsub_rn(oklam, CF::kc(cp, ce));
+                  wt = fmaf(u * LN2F, d, u) + w1;
+                } else {
+                  wt = fmaf(oadj, S2, w1);
+                }
+              }
               float wg = wt * gs;
               acc.x = fmaf(wg, vx, acc.x);
               acc.y = fmaf(wg, vy, acc.y);
@@ -245,13 +304,20 @@ __device__ void sweep(const CostParams& cp, const SweepIO& io, int lg0, int lg1,
             float4 st = part[(w * GMAX + g) * 32 + lane];
             sum += st.y * ex2_approx(st.x - mx);
           }
-          float np = io.lconst - (mx + log2f(sum));
+          // new potential = lconst - lse2 in double; keep the float32 rounding residual for the backward
+          const double npd = (double)io.lconst - ((double)mx + log2((double)sum));
+          const float np = (float)npd;
+          if (io.out_pot_lo) io.out_pot_lo[o] = (float)(npd - (double)np);
           if (io.err_out) errv = fabsf(np - (io.old_pot ? __ldcg(io.old_pot + o) : 0.f));
           io.out_pot[o] = np;
         } else if (MODE == MODE_FINAL) {
           float sum = 0.f;
 #pragma unroll
           for (int w = 0; w < SK_WARPS; ++w) sum += part[(w * GMAX + g) * 32 + lane].x;
+          if (io.own_is_beta) {
+            const double full = (double)__ldcg(io.own_pot + o) + (double)__ldcg(io.own_lo + o) - (double)io.c2;
+            sum *= exp2f((float)(full - (double)(float)full));
+          }
           io.out_pc[o] = sum * io.pc_scale;
         } else {
           float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -264,8 +330,8 @@ __device__ void sweep(const CostParams& cp, const SweepIO& io, int lg0, int lg1,
             sum.w += st.w;
           }
           if (io.adj_out) {
-            float a0 = io.adj_init ? __ldcg(io.adj_init + o) * io.adj_init_scale : 0.f;
-            io.adj_out[o] = a0 - sum.w;
+            // regular sweeps: -sum_j adj_j S_ij ; row sweep(L*): abar^L_i = -ln2 * sum_j u_ij (k lambda_j - kC_ij)
+            io.adj_out[o] = (FINAL_TERM && !io.own_is_beta) ? -LN2F * sum.w : -sum.w;
           }
           float4 gv = make_float4(sum.x * cp.gscale, sum.y * cp.gscale, sum.z * cp.gscale, 0.f);
           if (io.G_accumulate) {
@@ -307,7 +373,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkP
   extern __shared__ float4 smem4[];
   float4* sS = smem4;
   float4* part = smem4 + CHUNK_PAD;
-  float* sAdj = nullptr;
+  float2* sAdj = reinterpret_cast<float2*>(part + SK_WARPS * GMAX * 32);
   __shared__ int s_ls;
 
   const int gr = (prm.N + 31) / 32, gc = (prm.M + 31) / 32;  // groups per pair, row / col owners
@@ -346,6 +412,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkP
         io.n_str = prm.M;
         io.str_pot = (l == 1) ? nullptr : prm.beta + ((size_t)b * HL + slot(l - 1)) * prm.M;
         io.out_pot = prm.alpha + ((size_t)b * HL + slot(l)) * prm.N;
+        io.out_pot_lo = prm.alpha_lo + ((size_t)b * HL + slot(l)) * prm.N;
         if (prm.thresh > 0.f) {
           io.err_out = prm.err + (size_t)(l - 1) * prm.B + b;
           io.old_pot = (l == 1) ? nullptr : prm.alpha + ((size_t)b * HL + slot(l - 1)) * prm.N;
@@ -357,6 +424,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkP
         io.n_str = prm.N;
         io.str_pot = prm.alpha + ((size_t)b * HL + slot(l)) * prm.N;
         io.out_pot = prm.beta + ((size_t)b * HL + slot(l)) * prm.M;
+        io.out_pot_lo = prm.beta_lo + ((size_t)b * HL + slot(l)) * prm.M;
       }
       sweep<FAST, MODE_LSE, false>(prm.cp, io, lg0, lg1, sS, sAdj, part);
       signal_done(prm.done + b, lg1 - lg0);
@@ -396,16 +464,22 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkP
       const int lg1 = min(gpp, lg0 + (g1 - g));
       wait_done(prm.done + b, L * (gr + gc), prm.status);
       SweepIO io;
-      io.pc_scale = prm.inv_k;
+      io.pc_scale = prm.bval * prm.inv_k;
       const float* al = prm.alpha + ((size_t)b * HL + slot(Ls)) * prm.N;
       const float* be = prm.beta + ((size_t)b * HL + slot(Ls)) * prm.M;
+      const float* be_lo = prm.beta_lo + ((size_t)b * HL + slot(Ls)) * prm.M;
+      io.c1 = io.c2 = prm.lb2;
+      io.str_lo = nullptr;
+      io.own_lo = nullptr;
       if (type == 0) {
         io.own = prm.X + (size_t)b * prm.N;
         io.n_own = prm.N;
         io.str = prm.Y + (size_t)b * prm.M;
         io.n_str = prm.M;
         io.str_pot = be;
+        io.str_lo = be_lo;
         io.own_pot = al;
+        io.own_is_beta = 0;
         io.out_pc = prm.row_pc + (size_t)b * prm.N;
       } else {
         io.own = prm.Y + (size_t)b * prm.M;
@@ -414,6 +488,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkP
         io.n_str = prm.N;
         io.str_pot = al;
         io.own_pot = be;
+        io.own_lo = be_lo;
+        io.own_is_beta = 1;
         io.out_pc = prm.col_pc + (size_t)b * prm.M;
       }
       sweep<FAST, MODE_FINAL, false>(prm.cp, io, lg0, lg1, sS, sAdj, part);
@@ -453,7 +529,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_kernel(const SinkP
   extern __shared__ float4 smem4[];
   float4* sS = smem4;
   float4* part = smem4 + CHUNK_PAD;
-  float* sAdj = reinterpret_cast<float*>(part + SK_WARPS * GMAX * 32);
+  float2* sAdj = reinterpret_cast<float2*>(part + SK_WARPS * GMAX * 32);
 
   const int gr = (prm.N + 31) / 32, gc = (prm.M + 31) / 32;
   const int HL = prm.hist_levels;
@@ -475,10 +551,15 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_kernel(const SinkP
       const float gb = __ldg(prm.grad_cost + b);
       const float* al = prm.alpha + (size_t)b * HL * prm.N;  // level 0
       const float* be = prm.beta + (size_t)b * HL * prm.M;
+      const float* al_lo = prm.alpha_lo + (size_t)b * HL * prm.N;
+      const float* be_lo = prm.beta_lo + (size_t)b * HL * prm.M;
       SweepIO io;
-      io.fin1 = io.fin2 = 0.f;
-      io.adj_init = nullptr;
-      io.adj_init_scale = 0.f;
+      io.fin_A = gb * prm.bval * prm.inv_k;
+      io.fin_cpc = prm.col_pc + (size_t)b * prm.M;
+      io.fin_klam_scale = 1.f / (prm.bval * prm.inv_k);
+      io.own_is_beta = type;
+      io.str_lo = nullptr;
+      io.own_lo2 = nullptr;
       io.G_accumulate = (l != Ls);
       if (type == 0) {
         io.own = prm.X + (size_t)b * prm.N;
@@ -496,20 +577,19 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_kernel(const SinkP
           io.adj_out = nullptr;
         } else {
           if (l == Ls) {
-            io.str_adj = prm.col_pc + (size_t)b * prm.M;
-            io.str_adj_scale = gb * LN2F;
-            io.adj_init = prm.row_pc + (size_t)b * prm.N;
-            io.adj_init_scale = gb * LN2F;
-            io.fin1 = gb * prm.bval * prm.inv_k;
+            io.str_adj = nullptr;  // FINAL row sweep: the streamed scalars are g (b/k) 2^res_j and k lambda_j
+            io.str_adj_scale = 0.f;
           } else {
             io.str_adj = prm.bbar + (size_t)(l & 1) * BM + (size_t)b * prm.M;
             io.str_adj_scale = 1.f;
           }
           io.own_pot1 = al + (size_t)l * prm.N;
+          io.str_lo = be_lo + (size_t)l * prm.M;  // S^v,l is normalised by beta^l (streamed)
           io.adj_out = prm.abar + (size_t)(l & 1) * BN + (size_t)b * prm.N;
         }
         if (l < Ls) {
           io.own_pot2 = al + (size_t)(l + 1) * prm.N;
+          io.own_lo2 = al_lo + (size_t)(l + 1) * prm.N;  // S^u,l+1 is normalised by alpha^{l+1} (owner)
           io.own_adj2 = prm.abar + (size_t)((l + 1) & 1) * BN + (size_t)b * prm.N;
           io.own_adj2_scale = 1.f;
         } else {
@@ -525,15 +605,16 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_kernel(const SinkP
         io.str_pot = al + (size_t)l * prm.N;
         io.str_adj = prm.abar + (size_t)(l & 1) * BN + (size_t)b * prm.N;
         io.str_adj_scale = 1.f;
+        io.str_lo = al_lo + (size_t)l * prm.N;  // S^u,l is normalised by alpha^l (streamed)
         io.G = prm.g4y + (size_t)b * prm.M;
         io.own_pot1 = be + (size_t)(l - 1) * prm.M;
         io.c1 = prm.la2;
         io.own_pot2 = be + (size_t)l * prm.M;
+        io.own_lo2 = be_lo + (size_t)l * prm.M;  // S^v,l is normalised by beta^l (owner)
         io.c2 = prm.lb2;
         if (l == Ls) {
-          io.own_adj2 = prm.col_pc + (size_t)b * prm.M;
-          io.own_adj2_scale = gb * LN2F;
-          io.fin2 = gb * prm.bval * prm.inv_k;
+          io.own_adj2 = nullptr;  // FINAL col sweep: the owner scalars are g (b/k) 2^res_j and k lambda_j
+          io.own_adj2_scale = 0.f;
         } else {
           io.own_adj2 = prm.bbar + (size_t)(l & 1) * BM + (size_t)b * prm.M;
           io.own_adj2_scale = 1.f;
@@ -558,10 +639,11 @@ __global__ void plan_dense_kernel(const float4* X, const float4* Y, int N, int M
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
   if (j >= M) return;
   float4 x = X[(size_t)b * N + i], y = Y[(size_t)b * M + j];
-  float kc = Cost<FAST>::kc(cp, x.x, x.y, x.z, y.x, y.y, y.z);
+  typename Cost<FAST>::E ce = Cost<FAST>::eval(cp, x.x, x.y, x.z, y.x, y.y, y.z);
   size_t o = ((size_t)b * N + i) * M + j;
-  if (C) C[o] = kc * inv_k;
-  if (P) P[o] = exp2f(alpha[(size_t)b * sn + i] + beta[(size_t)b * sm + j] - kc);
+  if (C) C[o] = Cost<FAST>::kc(cp, ce) * inv_k;
+  // the plan exactly as the final-cost sweeps evaluate it: 2^(fl(M(beta_j) + alpha_i))
+  if (P) P[o] = ex2_approx(__fadd_rn(Cost<FAST>::m(cp, ce, beta[(size_t)b * sm + j]), alpha[(size_t)b * sn + i]));
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -699,6 +781,8 @@ extern "C" int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N,
   prm.hist_levels = hist_levels;
   prm.alpha = alpha_hist;
   prm.beta = beta_hist;
+  prm.alpha_lo = alpha_hist + (size_t)B * hist_levels * N;
+  prm.beta_lo = beta_hist + (size_t)B * hist_levels * M;
   prm.row_pc = row_pc;
   prm.col_pc = col_pc;
   prm.cost = cost;
@@ -708,7 +792,7 @@ extern "C" int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N,
   prm.done = w.done;
   prm.status = w.status;
   prm.err = w.err;
-  const size_t smem = sizeof(float4) * (CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32);
+  const size_t smem = sizeof(float4) * (CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32) + sizeof(float2) * CHUNK_PAD;
   const int maxg = B * (((N > M ? N : M) + 31) / 32);
   switch (fast) {
     case FAST_GEO2: return launch_persistent(sinkhorn_fwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
@@ -744,6 +828,8 @@ extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N,
   prm.hist_levels = iters + 1;
   prm.alpha = const_cast<float*>(alpha_hist);
   prm.beta = const_cast<float*>(beta_hist);
+  prm.alpha_lo = prm.alpha + (size_t)B * (iters + 1) * N;
+  prm.beta_lo = prm.beta + (size_t)B * (iters + 1) * M;
   prm.row_pc = const_cast<float*>(row_pc);
   prm.col_pc = const_cast<float*>(col_pc);
   prm.iters_run = const_cast<int*>(iters_run);
@@ -756,7 +842,7 @@ extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N,
   prm.err = w.err;
   prm.abar = w.abar;
   prm.bbar = w.bbar;
-  const size_t smem = sizeof(float4) * (CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32) + sizeof(float) * CHUNK_PAD;
+  const size_t smem = sizeof(float4) * (CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32) + sizeof(float2) * CHUNK_PAD;
   const int maxg = B * (((N > M ? N : M) + 31) / 32);
   switch (fast) {
     case FAST_GEO2: return launch_persistent(sinkhorn_bwd_kernel<FAST_GEO2>, prm, smem, maxg, s);

@@ -1,0 +1,522 @@
+// Sliced paths: projection -> per-slice stable radix sort in shared memory -> fused 1-D (circular) Wasserstein
+// reductions, with the gradients w.r.t. the sorted values and the scatter back through the sort permutation.
+//
+// Replaces   sliced_cost projection + normalise + atan2     Point_Cloud_Resistration/losses/max_spherical_sliced_w.py:270-279
+//            torch.sort calls                               max_spherical_sliced_w.py:163-164, 224-225, 232, 235
+//            emd1D_circle (p = 1, level median)             max_spherical_sliced_w.py:230-247
+//            Euclidean sliced W                             Wasserstein_flow_problem/Flow_ellipsoid.ipynb:208-220 (cell 5)
+//
+// Sort contract: the permutation equals torch.sort(keys, dim=-1, stable=True) bit for bit -- ascending, ties in input
+// order, -0.0 == +0.0, NaN last.  Keys go through the usual order-preserving float->uint32 map
+// (with -0 canonicalised and every NaN mapped to 0xFFFFFFFF) and a 4-pass LSD radix sort (8-bit digits) whose
+// ranking is warp-synchronous: each warp owns a contiguous item range, ranks 32 consecutive items per step with
+// __match_any_sync, and keeps warp-private digit offsets in shared memory, so there are no atomics and only three
+// block barriers per pass.  (key, index) records ping-pong between two shared-memory buffers for segments up to 8192
+// items and between two global scratch buffers beyond that.
+#include "common.cuh"
+
+namespace shwd {
+
+constexpr int PJ_THREADS = 256;
+constexpr float TWO_PI_F = 6.283185307179586f;
+constexpr float PI_F = 3.141592653589793f;
+
+// ------------------------------------------------------------------------------------------------ projections ----
+// keys[b,p,n] = (atan2(-q1, -q0) + pi) / (2 pi), q = normalize(U_p^T x_n)            (sliced_cost :270-279)
+__global__ void __launch_bounds__(PJ_THREADS) project_circle_kernel(const float* __restrict__ x, const float* __restrict__ U,
+                                                                    int N, int P, float* __restrict__ keys) {
+  extern __shared__ float sU[];  // P_TILE * 6
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.y * 32;
+  const int pc = min(32, P - p0);
+  for (int i = threadIdx.x; i < pc * 6; i += PJ_THREADS) sU[i] = __ldg(U + (size_t)p0 * 6 + i);
+  __syncthreads();
+  const int n = blockIdx.x * PJ_THREADS + threadIdx.x;
+  if (n >= N) return;
+  const float* xp = x + ((size_t)b * N + n) * 3;
+  const float x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
+  for (int p = 0; p < pc; ++p) {
+    const float* u = sU + p * 6;  // U[p][d][k] at d*2+k
+    float a = fmaf(u[4], x2, fmaf(u[2], x1, u[0] * x0));
+    float c = fmaf(u[5], x2, fmaf(u[3], x1, u[1] * x0));
+    float nr = fmaxf(sqrtf(fmaf(c, c, a * a)), 1e-12f);  // F.normalize eps
+    a = a / nr;
+    c = c / nr;
+    keys[((size_t)b * P + p0 + p) * N + n] = (atan2f(-c, -a) + PI_F) / TWO_PI_F;
+  }
+}
+
+// gx[b,n,:] = sum_p gk[b,p,n] * ( dt/da * U[p,:,0] + dt/dc * U[p,:,1] ),  dt/da = -c / (2 pi r^2), dt/dc = a / (2 pi r^2)
+__global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd_kernel(const float* __restrict__ x, const float* __restrict__ U,
+                                                                        int N, int P, const float* __restrict__ gk,
+                                                                        float* __restrict__ gx) {
+  extern __shared__ float sU[];  // P * 6 (tiled)
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * PJ_THREADS + threadIdx.x;
+  float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+  if (n < N) {
+    const float* xp = x + ((size_t)b * N + n) * 3;
+    x0 = __ldg(xp);
+    x1 = __ldg(xp + 1);
+    x2 = __ldg(xp + 2);
+  }
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  for (int p0 = 0; p0 < P; p0 += 256) {
+    const int pc = min(256, P - p0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < pc * 6; i += PJ_THREADS) sU[i] = __ldg(U + (size_t)p0 * 6 + i);
+    __syncthreads();
+    if (n < N) {
+      for (int p = 0; p < pc; ++p) {
+        const float* u = sU + p * 6;
+        float a = fmaf(u[4], x2, fmaf(u[2], x1, u[0] * x0));
+        float c = fmaf(u[5], x2, fmaf(u[3], x1, u[1] * x0));
+        float r2 = fmaxf(fmaf(c, c, a * a), 1e-24f);
+        float g = __ldg(gk + ((size_t)b * P + p0 + p) * N + n) / (TWO_PI_F * r2);
+        float ta = -c * g, tc = a * g;
+        g0 = fmaf(ta, u[0], fmaf(tc, u[1], g0));
+        g1 = fmaf(ta, u[2], fmaf(tc, u[3], g1));
+        g2 = fmaf(ta, u[4], fmaf(tc, u[5], g2));
+      }
+    }
+  }
+  if (n < N) {
+    float* o = gx + ((size_t)b * N + n) * 3;
+    o[0] = g0;
+    o[1] = g1;
+    o[2] = g2;
+  }
+}
+
+// keys[b,p,n] = <x_n, theta_p>                                              (Flow_ellipsoid.ipynb:214-216)
+__global__ void __launch_bounds__(PJ_THREADS) project_line_kernel(const float* __restrict__ x, const float* __restrict__ th, int N,
+                                                                  int P, float* __restrict__ keys) {
+  extern __shared__ float sT[];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.y * 32;
+  const int pc = min(32, P - p0);
+  for (int i = threadIdx.x; i < pc * 3; i += PJ_THREADS) sT[i] = __ldg(th + (size_t)p0 * 3 + i);
+  __syncthreads();
+  const int n = blockIdx.x * PJ_THREADS + threadIdx.x;
+  if (n >= N) return;
+  const float* xp = x + ((size_t)b * N + n) * 3;
+  const float x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
+  for (int p = 0; p < pc; ++p)
+    keys[((size_t)b * P + p0 + p) * N + n] = fmaf(sT[p * 3 + 2], x2, fmaf(sT[p * 3 + 1], x1, sT[p * 3] * x0));
+}
+
+__global__ void __launch_bounds__(PJ_THREADS) project_line_bwd_kernel(const float* __restrict__ th, int N, int P,
+                                                                      const float* __restrict__ gk, float* __restrict__ gx) {
+  extern __shared__ float sT[];
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * PJ_THREADS + threadIdx.x;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  for (int p0 = 0; p0 < P; p0 += 256) {
+    const int pc = min(256, P - p0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < pc * 3; i += PJ_THREADS) sT[i] = __ldg(th + (size_t)p0 * 3 + i);
+    __syncthreads();
+    if (n < N) {
+      for (int p = 0; p < pc; ++p) {
+        float g = __ldg(gk + ((size_t)b * P + p0 + p) * N + n);
+        g0 = fmaf(g, sT[p * 3], g0);
+        g1 = fmaf(g, sT[p * 3 + 1], g1);
+        g2 = fmaf(g, sT[p * 3 + 2], g2);
+      }
+    }
+  }
+  if (n < N) {
+    float* o = gx + ((size_t)b * N + n) * 3;
+    o[0] = g0;
+    o[1] = g1;
+    o[2] = g2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ radix sort -----
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_SMEM_MAX = 8192;  // items per segment whose ping-pong buffers fit in shared memory
+
+// Integer-only (immune to -ftz): every NaN -> 0xFFFFFFFF (last), -0.0 -> +0.0 (the two zeros tie), then the usual
+// order-preserving map.
+__device__ __forceinline__ uint32_t float_sort_key(float f) {
+  uint32_t u = __float_as_uint(f);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 0xFFFFFFFFu;
+  if ((u << 1) == 0u) u = 0u;
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_sort_key(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+// Block-wide exclusive scan of one unsigned value per thread (SORT_THREADS threads); returns the exclusive prefix.
+__device__ __forceinline__ uint32_t block_exscan_u32(uint32_t v, uint32_t* warp_tot /* SORT_WARPS */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int w = 0; w < warp; ++w) base += warp_tot[w];
+  __syncthreads();
+  return base + inc - v;
+}
+
+// Stable LSD radix sort of n (key, index) records: a -> ... -> result pointer returned (either a or b).
+// a, b may live in shared or global memory.  hist: SORT_WARPS*256 words of shared memory; wt: SORT_WARPS words.
+__device__ uint2* block_radix_sort(uint2* a, uint2* b, int n, uint32_t* hist, uint32_t* wt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunk = (((n + SORT_WARPS - 1) / SORT_WARPS) + 31) & ~31;
+  const int beg = min(n, warp * chunk), end = min(n, beg + chunk);
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int sh = pass * 8;
+    for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) hist[i] = 0;
+    __syncthreads();
+    uint32_t* wh = hist + warp * 256;
+    for (int i0 = beg; i0 < end; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < end;
+      const uint32_t d = valid ? ((a[i].x >> sh) & 255u) : 0xFFFFu;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      if (valid && (peers & lt) == 0) wh[d] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    {
+      // digit-major exclusive offsets: thread d owns digit d
+      const int d = threadIdx.x;
+      uint32_t tot = 0;
+#pragma unroll
+      for (int w = 0; w < SORT_WARPS; ++w) tot += hist[w * 256 + d];
+      uint32_t run = block_exscan_u32(tot, wt);
+#pragma unroll
+      for (int w = 0; w < SORT_WARPS; ++w) {
+        uint32_t t = hist[w * 256 + d];
+        hist[w * 256 + d] = run;
+        run += t;
+      }
+    }
+    __syncthreads();
+    for (int i0 = beg; i0 < end; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < end;
+      uint2 rec = valid ? a[i] : make_uint2(0u, 0u);
+      const uint32_t d = valid ? ((rec.x >> sh) & 255u) : 0xFFFFu;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      uint32_t pos = 0;
+      if (valid) pos = wh[d] + __popc(peers & lt);
+      __syncwarp();
+      if (valid) {
+        b[pos] = rec;
+        if ((peers & lt) == 0) wh[d] += __popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    uint2* t = a;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) segmented_sort_kernel(const float* __restrict__ keys, int len,
+                                                                      float* __restrict__ sorted, int64_t* __restrict__ perm,
+                                                                      uint2* __restrict__ gscratch) {
+  extern __shared__ uint2 sbuf[];
+  __shared__ uint32_t hist[SORT_WARPS * 256];
+  __shared__ uint32_t wt[SORT_WARPS];
+  const size_t seg = blockIdx.x;
+  const float* k = keys + seg * len;
+  uint2 *a, *b;
+  if (gscratch) {
+    a = gscratch + seg * 2 * (size_t)len;
+    b = a + len;
+  } else {
+    a = sbuf;
+    b = sbuf + len;
+  }
+  for (int i = threadIdx.x; i < len; i += SORT_THREADS) a[i] = make_uint2(float_sort_key(__ldg(k + i)), (uint32_t)i);
+  __syncthreads();
+  uint2* r = block_radix_sort(a, b, len, hist, wt);
+  for (int i = threadIdx.x; i < len; i += SORT_THREADS) {
+    const uint32_t j = r[i].y;
+    if (sorted) sorted[seg * len + i] = __ldg(k + j);
+    if (perm) perm[seg * len + i] = (int64_t)j;
+  }
+}
+
+// gkeys[seg][perm[seg][k]] = gsorted[seg][k]
+__global__ void unsort_kernel(const float* __restrict__ gs, const int64_t* __restrict__ perm, size_t total, int len,
+                              float* __restrict__ gk) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  size_t seg = i / len;
+  gk[seg * len + (size_t)perm[i]] = gs[i];
+}
+
+// ------------------------------------------------------------------------------------- circular W1 (level median) --
+// In-place inclusive scan of n floats in shared memory (thread-sequential chunks + block scan of the chunk totals).
+__device__ void block_inclusive_scan_f32(float* a, int n, float* wtot /* SORT_WARPS */) {
+  const int per = (n + SORT_THREADS - 1) / SORT_THREADS;
+  const int beg = min(n, (int)threadIdx.x * per), end = min(n, beg + per);
+  float s = 0.f;
+  for (int i = beg; i < end; ++i) s += a[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wtot[warp] = inc;
+  __syncthreads();
+  float base = 0.f;
+  for (int w = 0; w < warp; ++w) base += wtot[w];
+  float run = base + inc - s;
+  for (int i = beg; i < end; ++i) {
+    run += a[i];
+    a[i] = run;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float block_sum_f32(float v, float* wtot) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < SORT_WARPS; ++w) t += wtot[w];
+  return t;
+}
+
+// One CTA per slice.  us (n), vs (m) sorted ascending.  Follows emd1D_circle :230-247 step by step:
+//   merged = stable merge of (us, vs)  [== sort(cat(us, vs))],  w = +1/n for u entries, -1/m for v entries
+//   F = cumsum(w);  delta_k = merged_{k+1} - merged_k, last = 1 - merged_last   (the arc [0, first) is omitted)
+//   level median: sort F, cw = cumsum(delta[perm]) - 0.5, first k with cw >= 0 -> med = F_sorted[k]
+//   W = sum_k delta_k |F_k - med|;   dW/dmerged_k = |F_{k-1} - med| - |F_k - med|  (F_{-1} term = 0)
+__global__ void __launch_bounds__(SORT_THREADS) circular_w1_kernel(const float* __restrict__ us, const float* __restrict__ vs,
+                                                                   int n, int m, float* __restrict__ w_out,
+                                                                   float* __restrict__ gus, float* __restrict__ gvs) {
+  extern __shared__ uint2 sbuf[];
+  __shared__ uint32_t hist[SORT_WARPS * 256];
+  __shared__ uint32_t wt[SORT_WARPS];
+  __shared__ float wf[SORT_WARPS];
+  __shared__ int s_k;
+  const int nm = n + m;
+  uint2* a = sbuf;
+  uint2* b = sbuf + nm;
+  float* vals = reinterpret_cast<float*>(sbuf + 2 * (size_t)nm);
+  float* F = vals + nm;
+  const size_t s = blockIdx.x;
+  const float* u = us + s * n;
+  const float* v = vs + s * m;
+  const float wu = 1.f / n, wv = 1.f / m;
+
+  // stable merge by rank: u_i lands at i + #{v < u_i}; v_j at j + #{u <= v_j}
+  for (int i = threadIdx.x; i < nm; i += SORT_THREADS) {
+    const bool isu = i < n;
+    const float x = isu ? __ldg(u + i) : __ldg(v + i - n);
+    const float* o = isu ? v : u;
+    const int on = isu ? m : n;
+    int lo = 0, hi = on;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const float y = __ldg(o + mid);
+      const bool before = isu ? (y < x) : (y <= x);
+      if (before) lo = mid + 1; else hi = mid;
+    }
+    const int pos = (isu ? i : i - n) + lo;
+    vals[pos] = x;
+    F[pos] = isu ? wu : -wv;
+  }
+  __syncthreads();
+  block_inclusive_scan_f32(F, nm, wf);
+  // records (sort key of F_k, delta_k): the level-median sort carries delta as its payload
+  for (int k = threadIdx.x; k < nm; k += SORT_THREADS) {
+    const float d = ((k + 1 < nm) ? vals[k + 1] : 1.f) - vals[k];
+    a[k] = make_uint2(float_sort_key(F[k]), __float_as_uint(d));
+  }
+  __syncthreads();
+  uint2* r = block_radix_sort(a, b, nm, hist, wt);
+  // cw = cumsum(delta in sorted-F order) - 0.5; first k with cw >= 0 (merged values are dead: reuse `vals`)
+  for (int k = threadIdx.x; k < nm; k += SORT_THREADS) vals[k] = __uint_as_float(r[k].y);
+  if (threadIdx.x == 0) s_k = nm;
+  __syncthreads();
+  block_inclusive_scan_f32(vals, nm, wf);
+  for (int k = threadIdx.x; k < nm; k += SORT_THREADS)
+    if (vals[k] - 0.5f >= 0.f) atomicMin(&s_k, k);
+  __syncthreads();
+  const int kk = (s_k >= nm) ? 0 : s_k;
+  const float med = float_from_sort_key(r[kk].x);
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < nm; k += SORT_THREADS)
+    acc += __uint_as_float(r[k].y) * fabsf(float_from_sort_key(r[k].x) - med);
+  acc = block_sum_f32(acc, wf);
+  if (threadIdx.x == 0) w_out[s] = acc;
+  if (gus || gvs) {
+    // gradient w.r.t. merged values, routed back to u_i / v_j by recomputing each entry's merged position
+    for (int i = threadIdx.x; i < nm; i += SORT_THREADS) {
+      const bool isu = i < n;
+      const float x = isu ? __ldg(u + i) : __ldg(v + i - n);
+      const float* o = isu ? v : u;
+      const int on = isu ? m : n;
+      int lo = 0, hi = on;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float y = __ldg(o + mid);
+        const bool before = isu ? (y < x) : (y <= x);
+        if (before) lo = mid + 1; else hi = mid;
+      }
+      const int pos = (isu ? i : i - n) + lo;
+      const float g = ((pos > 0) ? fabsf(F[pos - 1] - med) : 0.f) - fabsf(F[pos] - med);
+      if (isu) {
+        if (gus) gus[s * n + i] = g;
+      } else {
+        if (gvs) gvs[s * m + i - n] = g;
+      }
+    }
+  }
+}
+
+// acc[s] = sum_k |xs_k - ys_k|^p on sorted projections; gradients w.r.t. the sorted values.
+__global__ void __launch_bounds__(SORT_THREADS) euclid_sw_kernel(const float* __restrict__ xs, const float* __restrict__ ys, int n,
+                                                                 float p, float* __restrict__ acc_out, float* __restrict__ gxs,
+                                                                 float* __restrict__ gys) {
+  __shared__ float wf[SORT_WARPS];
+  const size_t s = blockIdx.x;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < n; k += SORT_THREADS) {
+    const float d = xs[s * n + k] - ys[s * n + k];
+    const float ad = fabsf(d);
+    float t, g;
+    if (p == 2.f) {
+      t = d * d;
+      g = 2.f * d;
+    } else if (p == 1.f) {
+      t = ad;
+      g = (d > 0.f) - (d < 0.f);
+    } else {
+      t = powf(ad, p);
+      g = copysignf(p * powf(ad, p - 1.f), d);
+    }
+    acc += t;
+    if (gxs) gxs[s * n + k] = g;
+    if (gys) gys[s * n + k] = -g;
+  }
+  acc = block_sum_f32(acc, wf);
+  if (threadIdx.x == 0) acc_out[s] = acc;
+}
+
+}  // namespace shwd
+
+using namespace shwd;
+
+extern "C" int shwd_project_circle(const float* x, const float* U, int B, int N, int P, float* keys, void* stream) {
+  if (!x || !U || !keys || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (B > 65535 || (P + 31) / 32 > 65535) return SHWD_ERR_UNSUPPORTED;
+  dim3 grid((N + PJ_THREADS - 1) / PJ_THREADS, (P + 31) / 32, B);
+  project_circle_kernel<<<grid, PJ_THREADS, 32 * 6 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(x, U, N, P, keys);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+extern "C" int shwd_project_circle_bwd(const float* x, const float* U, int B, int N, int P, const float* gkeys, float* gx,
+                                       void* stream) {
+  if (!x || !U || !gkeys || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (B > 65535) return SHWD_ERR_UNSUPPORTED;
+  dim3 grid((N + PJ_THREADS - 1) / PJ_THREADS, B);
+  project_circle_bwd_kernel<<<grid, PJ_THREADS, 256 * 6 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(x, U, N, P, gkeys, gx);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+extern "C" int shwd_project_line(const float* x, const float* theta, int B, int N, int P, float* keys, void* stream) {
+  if (!x || !theta || !keys || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (B > 65535 || (P + 31) / 32 > 65535) return SHWD_ERR_UNSUPPORTED;
+  dim3 grid((N + PJ_THREADS - 1) / PJ_THREADS, (P + 31) / 32, B);
+  project_line_kernel<<<grid, PJ_THREADS, 32 * 3 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(x, theta, N, P, keys);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+extern "C" int shwd_project_line_bwd(const float* theta, int B, int N, int P, const float* gkeys, float* gx, void* stream) {
+  if (!theta || !gkeys || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (B > 65535) return SHWD_ERR_UNSUPPORTED;
+  dim3 grid((N + PJ_THREADS - 1) / PJ_THREADS, B);
+  project_line_bwd_kernel<<<grid, PJ_THREADS, 256 * 3 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(theta, N, P, gkeys, gx);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+extern "C" size_t shwd_segmented_sort_workspace_bytes(int segs, int len) {
+  if (segs <= 0 || len <= SORT_SMEM_MAX) return 0;
+  return (size_t)segs * 2 * (size_t)len * sizeof(uint2);
+}
+
+extern "C" int shwd_segmented_sort(const float* keys, int segs, int len, float* sorted, int64_t* perm, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (!keys || segs < 0 || len <= 0 || (!sorted && !perm)) return SHWD_ERR_INVALID_ARGUMENT;
+  if (segs == 0) return SHWD_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (len <= SORT_SMEM_MAX) {
+    const size_t smem = 2 * (size_t)len * sizeof(uint2);
+    if (smem > 48 * 1024)
+      SHWD_CUDA_CHECK(cudaFuncSetAttribute(segmented_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    segmented_sort_kernel<<<segs, SORT_THREADS, smem, s>>>(keys, len, sorted, perm, nullptr);
+  } else {
+    const size_t need = shwd_segmented_sort_workspace_bytes(segs, len);
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 7)) return SHWD_ERR_WORKSPACE;
+    segmented_sort_kernel<<<segs, SORT_THREADS, 0, s>>>(keys, len, sorted, perm, static_cast<uint2*>(workspace));
+  }
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+extern "C" size_t shwd_circular_w1_workspace_bytes(int S, int n, int m) {
+  (void)S;
+  (void)n;
+  (void)m;
+  return 0;  // everything lives in shared memory (n + m <= 8192)
+}
+
+extern "C" int shwd_circular_w1(const float* us, const float* vs, int S, int n, int m, float* w, float* gus, float* gvs,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  if (!us || !vs || !w || S < 0 || n <= 0 || m <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (S == 0) return SHWD_OK;
+  const size_t nm = (size_t)n + m;
+  const size_t smem = nm * (2 * sizeof(uint2) + 2 * sizeof(float));
+  if (smem > 216 * 1024) return SHWD_ERR_UNSUPPORTED;  // n + m <= 9216; larger slices: see DESIGN.md
+  if (smem > 48 * 1024)
+    SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_w1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  circular_w1_kernel<<<S, SORT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(us, vs, n, m, w, gus, gvs);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+extern "C" int shwd_euclid_sw(const float* xs, const float* ys, int S, int n, float p, float* acc, float* gxs, float* gys,
+                              void* stream) {
+  if (!xs || !ys || !acc || S < 0 || n <= 0 || !(p > 0.f)) return SHWD_ERR_INVALID_ARGUMENT;
+  if (S == 0) return SHWD_OK;
+  euclid_sw_kernel<<<S, SORT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(xs, ys, n, p, acc, gxs, gys);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+extern "C" int shwd_unsort(const float* gsorted, const int64_t* perm, int segs, int len, float* gkeys, void* stream) {
+  if (!gsorted || !perm || !gkeys || segs < 0 || len <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  const size_t total = (size_t)segs * len;
+  if (total == 0) return SHWD_OK;
+  unsort_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(gsorted, perm, total, len, gkeys);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}

@@ -1,0 +1,35 @@
+"""``chamfer_distance`` with pytorch3d's call signature as the reference uses it
+(Point_Cloud_Resistration/train_CD.py:123,161; Comparison_.../main_rotation.py:203): squared L2, K = 1."""
+from .. import ops
+
+
+def chamfer_distance(x, y, x_lengths=None, y_lengths=None, x_normals=None, y_normals=None, weights=None,
+                     batch_reduction="mean", point_reduction="mean", norm=2, single_directional=False,
+                     abs_cosine=True):
+    """Returns ``(loss, None)``.  Only what the reference exercises is supported: equal-length clouds, no normals,
+    no weights, ``norm == 2``; anything else raises (as pytorch3d raises on invalid arguments)."""
+    if x_lengths is not None or y_lengths is not None or x_normals is not None or y_normals is not None or weights is not None:
+        raise NotImplementedError("lengths / normals / weights are not used on the reference's path")
+    if norm != 2:
+        raise ValueError("Support for 1 or 2 norm.") if norm not in (1, 2) else NotImplementedError("norm=1 is not used on this path")
+    if batch_reduction is not None and batch_reduction not in ("mean", "sum"):
+        raise ValueError('batch_reduction must be one of ["mean", "sum"] or None')
+    if point_reduction not in ("mean", "sum"):
+        raise ValueError('point_reduction must be one of ["mean", "sum"]')
+    d_xy, d_yx, _, _ = ops.chamfer_nn(x, y)
+    B, N = d_xy.shape
+    M = d_yx.shape[1]
+    cham_x = d_xy.sum(1)
+    cham_y = d_yx.sum(1)
+    if point_reduction == "mean":
+        cham_x = cham_x / N
+        cham_y = cham_y / M
+    if batch_reduction is not None:
+        cham_x = cham_x.sum()
+        cham_y = cham_y.sum()
+        if batch_reduction == "mean":
+            cham_x = cham_x / max(B, 1)
+            cham_y = cham_y / max(B, 1)
+    if single_directional:
+        return cham_x, None
+    return cham_x + cham_y, None

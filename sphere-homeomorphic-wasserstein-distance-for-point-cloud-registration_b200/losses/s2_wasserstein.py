@@ -1,0 +1,210 @@
+"""Drop-in for ``Point_Cloud_Resistration/losses/s2_wasserstein.py`` on the B200 path.
+
+``Cos_disimilarity_W`` (:13-66) and ``Geodesic_distance_W`` (:73-126) keep their constructor and call signatures.
+The reference solves each pair with POT's exact CPU network simplex (``ot.emd2``, :41-43); here the same cost matrix is
+solved by on-the-fly log-domain Sinkhorn iterations in CUDA (BASELINE.json north_star), with the recurrence of
+``losses/Sinkhorn.py:35-50``: ``eps`` / ``max_iter`` are extra keyword arguments (defaults 0.01 / 100, the values the
+reference uses for its Sinkhorn runs, main_rotation.py:123-124).  The result is ``mean_b cost_b ** (1/p)`` exactly as
+:41-44 reduces it.  The wrappers (:211-344) are host-side orchestration and are restated unchanged in behaviour.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .flows import PlanarFlow, ResidualFlow
+
+
+class _EntropicW(nn.Module):
+    _kind = None
+
+    def __init__(self, device, p=1, eps=0.01, max_iter=100):
+        super().__init__()
+        self.device = device
+        self.p = p
+        self.eps = eps
+        self.max_iter = max_iter
+
+    def _w(self, x, y, device, p=1):
+        x = x.to(device)
+        y = y.to(device)
+        if x.dim() == 2:
+            batch_size = 1
+        else:
+            batch_size = x.shape[0]
+        if batch_size < 1:
+            raise ValueError("batch_size is not valid")
+        cost = ops.entropic_ot(x, y, self._kind, float(p), float(self.eps), int(self.max_iter)).cost
+        losses = torch.pow(cost, 1. / p)
+        if batch_size >= 2:
+            return losses.sum() / int(batch_size)
+        return losses.reshape(())
+
+    def forward(self, x, y):
+        return self._w(x, y, self.device, self.p)
+
+
+class Cos_disimilarity_W(_EntropicW):
+    """s2_wasserstein.py:13-66 -- cost ``sum_k |x_k - y_k|^p`` (the active line 62)."""
+    _kind = "sqeuclid"
+
+    def calcurate_cos_W(self, x, y, device, p=1):
+        return self._w(x, y, device, p)
+
+    def cos_cost_matrix(self, x, y, p=1):
+        """Dense (B,N,M) cost matrix, for inspection only (small problems)."""
+        return ops.entropic_ot(x, y, self._kind, float(p), 1.0, 1).dense(want_plan=False)[1].reshape(
+            x.shape[:-2] + (x.shape[-2], y.shape[-2]))
+
+
+class Geodesic_distance_W(_EntropicW):
+    """s2_wasserstein.py:73-126 -- cost ``acos(cosine_similarity(x, y)) ** p``."""
+    _kind = "geodesic"
+
+    def calcurate_geodesic_W(self, x, y, device, p=1):
+        return self._w(x, y, device, p)
+
+    def geodesic_cost_matrix(self, x, y, p=1):
+        """Dense (B,N,M) cost matrix, for inspection only (small problems)."""
+        return ops.entropic_ot(x, y, self._kind, float(p), 1.0, 1).dense(want_plan=False)[1].reshape(
+            x.shape[:-2] + (x.shape[-2], y.shape[-2]))
+
+
+class Norm_Flow_structure(nn.Module):
+    """s2_wasserstein.py:134-163 -- a stack of Planar or Residual (hidden 8, 7 layers, Lipschitz 0.95) flows."""
+
+    def __init__(self, input_dim=3, flow_name="Planar", n_flow_layer=3):
+        super().__init__()
+        self.net = nn.ModuleList(self.create__NF_structure(flow_name, input_dim, n_flow_layer))
+
+    def create__NF_structure(self, flow_name, input_dim, n_flow_layer):
+        if flow_name == "Planar":
+            return [PlanarFlow(input_dim) for _ in range(n_flow_layer)]
+        elif flow_name == "Residual":
+            return [ResidualFlow(input_dim, hidden_units=8, hidden_layers=7, lipschitz_const=0.95)
+                    for _ in range(n_flow_layer)]
+        else:
+            raise ValueError("Flow name is not valid")
+
+    def forward(self, x):
+        for flow in self.net:
+            x = flow(x)
+        return x
+
+
+class Norm_Flow_structure_optuna(nn.Module):
+    """s2_wasserstein.py:171-201 -- same with configurable Residual width / depth."""
+
+    def __init__(self, input_dim=3, flow_name="Planar", n_flow_layer=3, Residual_hidden_units=8, Residual_hidden_layers=3):
+        super().__init__()
+        self.Residual_hidden_units = Residual_hidden_units
+        self.Residual_hidden_layers = Residual_hidden_layers
+        self.net = nn.ModuleList(self.create__NF_structure(flow_name, input_dim, n_flow_layer))
+
+    def create__NF_structure(self, flow_name, input_dim, n_flow_layer):
+        if flow_name == "Planar":
+            return [PlanarFlow(input_dim) for _ in range(n_flow_layer)]
+        elif flow_name == "Residual":
+            return [ResidualFlow(input_dim, self.Residual_hidden_units, self.Residual_hidden_layers, 0.95)
+                    for _ in range(n_flow_layer)]
+        else:
+            raise ValueError("Flow name is not valid")
+
+    def forward(self, x):
+        for flow in self.net:
+            x = flow(x)
+        return x
+
+
+class max_cos_disimilarity_wassersten_distance(nn.Module):
+    """s2_wasserstein.py:211-262 -- inner gradient ascent on phi (detached inputs), then the outer distance."""
+
+    def __init__(self, phi, CSW, device, phi_op, max_iter=10, lam=0.1, psi_minibatch_size=5):
+        super().__init__()
+        self.phi = phi
+        self.CSW = CSW
+        self.phi_op = phi_op
+        self.max_iter = max_iter
+        self.device = device
+        self.reg_lam = lam
+
+    def regularization_of_normalizing_flow(self, x):
+        """sum_{b,n} | ||x_bn|| - 1 |  (:224-232) -- fused into the sphere-map reduction kernel on CUDA tensors."""
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        if x.is_cuda:
+            return ops.flow_regularization(x)
+        return torch.sum(torch.abs(torch.linalg.vector_norm(x, dim=-1) - 1))
+
+    def forward(self, first_samples, second_samples, train_or_test="train"):
+        first_samples_detach = first_samples.detach()
+        second_samples_detach = second_samples.detach()
+        if train_or_test == "train":
+            self.phi.train()
+            for _ in range(self.max_iter):
+                self.phi_op.zero_grad()
+                first_t = self.phi(first_samples_detach)
+                second_t = self.phi(second_samples_detach)
+                cswd = self.CSW(first_t, second_t)
+                reg_first = self.regularization_of_normalizing_flow(first_t) / (first_t.shape[0] * first_t.shape[1])
+                reg_second = self.regularization_of_normalizing_flow(second_t) / (second_t.shape[0] * second_t.shape[1])
+                regularization = self.reg_lam * (reg_first + reg_second)
+                loss = regularization - cswd
+                loss.backward(retain_graph=True)
+                self.phi_op.step()
+        elif train_or_test == "test":
+            self.phi.eval()
+        first_t = self.phi(first_samples)
+        second_t = self.phi(second_samples)
+        cswd = self.CSW(first_t, second_t)
+        return cswd, first_t, second_t
+
+
+class pseudo_max_cos_disimilarity_wassersten_distance(nn.Module):
+    """s2_wasserstein.py:272-344 -- max / mean of the distance over ``phi_num`` random untrained flows."""
+
+    def __init__(self, CSW, device, phi_num=10, lam=0.1, n_flow_layer=5, flow_name="Residual", mean_or_max_or_softmax="max"):
+        super().__init__()
+        self.CSW = CSW
+        self.phi_num = phi_num
+        self.n_flow_layer = n_flow_layer
+        self.device = device
+        self.flow_name = flow_name
+        self.reg_lam = lam
+        self.phi_list = self.norm_flow(self.phi_num, self.flow_name, self.n_flow_layer)
+        self.mean_or_max_or_softmax = mean_or_max_or_softmax
+
+    def norm_flow(self, phi_num=10, flow_name="Residual", n_flow_layer=3):
+        return [Norm_Flow_structure(flow_name=flow_name, n_flow_layer=n_flow_layer).to(self.device) for _ in range(phi_num)]
+
+    def forward(self, first_samples, second_samples):
+        first_samples_detach = first_samples.detach()
+        second_samples_detach = second_samples.detach()
+        if self.mean_or_max_or_softmax == "max":
+            max_cswd = -1
+            for phi in self.phi_list:
+                first_t = phi(first_samples_detach)
+                second_t = phi(second_samples_detach)
+                cswd = self.CSW(first_t, second_t)
+                if cswd > max_cswd:
+                    max_cswd = cswd
+            return max_cswd, first_t, second_t
+        elif self.mean_or_max_or_softmax == "mean":
+            mean_cswd = 0
+            for phi in self.phi_list:
+                first_t = phi(first_samples_detach)
+                second_t = phi(second_samples_detach)
+                mean_cswd = mean_cswd + self.CSW(first_t, second_t)
+            return mean_cswd / self.phi_num, first_t, second_t
+        elif self.mean_or_max_or_softmax == "softmax":
+            # the reference branch (:330-342) builds torch.tensor(list_of_modules) and cannot run; the evident intent
+            # (softmax-weighted mean of the per-flow distances) is what is computed here
+            vals = []
+            for phi in self.phi_list:
+                first_t = phi(first_samples_detach)
+                second_t = phi(second_samples_detach)
+                vals.append(self.CSW(first_t, second_t))
+            vals = torch.stack(vals)
+            return (F.softmax(vals, dim=0) * vals).sum(), first_t, second_t
+        else:
+            raise ValueError("mean_or_max_or_softmax is not valid")

@@ -1,0 +1,54 @@
+"""Sliced losses with the reference's function names and signatures.
+
+  sliced_wasserstein_sphere / sliced_cost / emd1D_circle   Point_Cloud_Resistration/losses/max_spherical_sliced_w.py:210-310
+  sliced_wasserstein_distance                               Wasserstein_flow_problem/Flow_ellipsoid.ipynb:203-220 (cell 5)
+
+The frames / directions are drawn with torch exactly as the reference draws them (``qr(randn(P,d,2))``,
+row-normalised ``randn(P,d)``); projection, sort and the 1-D reductions run in CUDA.
+"""
+import torch
+
+from .. import ops
+
+
+def emd1D_circle(u_values, v_values, u_weights=None, v_weights=None, p=1, require_sort=True):
+    """Circular W1 (level median) per row: (S,n),(S,m) -> (S,).  Uniform weights, p == 1 (max_spherical_sliced_w.py:210-247)."""
+    if u_weights is not None or v_weights is not None:
+        raise NotImplementedError("non-uniform weights are not used on the reference's path")
+    if p != 1:
+        raise NotImplementedError("emd1D_circle implements p == 1 only, like the reference (it returns None otherwise)")
+    if require_sort:
+        u_values, _ = ops.SegmentedSortFn.apply(u_values.contiguous().float())
+        v_values, _ = ops.SegmentedSortFn.apply(v_values.contiguous().float())
+    return ops.CircularW1Fn.apply(u_values.contiguous(), v_values.contiguous())
+
+
+def sliced_cost(Xs, Xt, Us, p=2, u_weights=None, v_weights=None):
+    """(n,3),(m,3) clouds and (P,3,2) frames -> mean over slices of the circular W (max_spherical_sliced_w.py:251-286)."""
+    if u_weights is not None or v_weights is not None:
+        raise NotImplementedError("non-uniform weights are not used on the reference's path")
+    if p != 1:
+        raise NotImplementedError("p != 1 (circular bisection, max_spherical_sliced_w.py:117-207) is not on the B200 path yet")
+    w = ops.spherical_sliced_w1(Xs, Xt, Us)
+    return w.reshape(()) if Xs.dim() == 2 else w
+
+
+def sliced_wasserstein_sphere(Xs, Xt, num_projections, device, u_weights=None, v_weights=None, p=2):
+    """max_spherical_sliced_w.py:289-310 -- draws ``U = qr(randn(P,d,2)).Q`` on ``device`` and calls sliced_cost."""
+    d = Xs.shape[-1]
+    Z = torch.randn((num_projections, d, 2), device=device)
+    U, _ = torch.linalg.qr(Z)
+    return sliced_cost(Xs, Xt, U, p=p, u_weights=u_weights, v_weights=v_weights)
+
+
+def rand_projections(dim, num_projections=100, device=None):
+    projections = torch.randn((num_projections, dim), device=device)
+    return projections / torch.sqrt(torch.sum(projections ** 2, dim=1, keepdim=True))
+
+
+def sliced_wasserstein_distance(first_samples, second_samples, num_projection=100, p=2, device="cuda", projections=None):
+    """Flow_ellipsoid.ipynb:208-220.  ``projections`` (P,3) may be supplied for reproducible tests."""
+    if projections is None:
+        projections = rand_projections(second_samples.size(-1), num_projection, device=device)
+    w = ops.euclid_sliced_w(first_samples.to(device), second_samples.to(device), projections, float(p))
+    return w.reshape(()) if first_samples.dim() == 2 else w

@@ -97,8 +97,8 @@ class EntropicOTFn(torch.autograd.Function):
         y4 = torch.empty(B, M, 4, **f32)
         keep = bool(need_grad) or thresh > 0
         HL = iters + 1 if keep else 1
-        alpha = torch.empty(B, HL, N, **f32)
-        beta = torch.empty(B, HL, M, **f32)
+        alpha = torch.empty(2, B, HL, N, **f32)  # plane 0: iterates k*u; plane 1: float32 rounding residuals
+        beta = torch.empty(2, B, HL, M, **f32)
         row_pc = torch.empty(B, N, **f32)
         col_pc = torch.empty(B, M, **f32)
         cost = torch.empty(B, **f32)
@@ -162,9 +162,9 @@ class EntropicOTResult:
     def duals(self):
         """(u, v) of the iterate used, in the reference's units (alpha / k)."""
         kind, p, n_power, eps, iters, center = self._cfg
-        lvl = self.iterations() if self._alpha.shape[1] > 1 else 0
+        lvl = self.iterations() if self._alpha.shape[2] > 1 else 0
         inv_k = eps / 1.4426950408889634
-        return self._alpha[:, lvl] * inv_k, self._beta[:, lvl] * inv_k
+        return self._alpha[0, :, lvl] * inv_k, self._beta[0, :, lvl] * inv_k
 
     def dense(self, want_plan=True, want_cost=True):
         """(P, C) as (B,N,M) tensors -- the reference's extra return values (sinkhorn.py:60).  Small problems only."""
@@ -179,10 +179,10 @@ class EntropicOTResult:
         y4 = torch.empty(B, M, 4, device=x.device, dtype=torch.float32)
         P = torch.empty(B, N, M, device=x.device, dtype=torch.float32) if want_plan else None
         C = torch.empty(B, N, M, device=x.device, dtype=torch.float32) if want_cost else None
-        HL = self._alpha.shape[1]
+        HL = self._alpha.shape[2]
         lvl = self.iterations() if HL > 1 else 0
-        a = self._alpha[:, lvl]
-        b = self._beta[:, lvl]
+        a = self._alpha[0, :, lvl]
+        b = self._beta[0, :, lvl]
         with torch.cuda.device(x.device):
             s = _stream()
             _lib.check(lib.shwd_sphere_map_fwd(_ptr(x), _ptr(x4), None, B, N, flags, s), "shwd_sphere_map_fwd")
@@ -210,3 +210,225 @@ def entropic_ot(x, y, kind="geodesic", p=2.0, eps=0.01, iters=100, n_power=1.0, 
                                                           float(early_stop_thresh), bool(center), need_grad)
     return EntropicOTResult(cost, alpha, beta, iters_run, ws, xc.detach(), yc.detach(),
                             (k, float(p), float(n_power), float(eps), int(iters), bool(center)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ChamferFn(torch.autograd.Function):
+    """(x (B,N,3), y (B,M,3)) -> (d_xy (B,N), d_yx (B,M)): nearest-neighbour squared distances, both directions."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        x = x.contiguous()
+        y = y.contiguous()
+        B, N, _ = x.shape
+        M = y.shape[1]
+        dev = x.device
+        d_xy = torch.empty(B, N, device=dev, dtype=torch.float32)
+        d_yx = torch.empty(B, M, device=dev, dtype=torch.float32)
+        i_xy = torch.empty(B, N, device=dev, dtype=torch.int32)
+        i_yx = torch.empty(B, M, device=dev, dtype=torch.int32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().shwd_chamfer_fwd(_ptr(x), _ptr(y), B, N, M, _ptr(d_xy), _ptr(i_xy), _ptr(d_yx), _ptr(i_yx), _stream()),
+                       "shwd_chamfer_fwd")
+        ctx.save_for_backward(x, y, i_xy, i_yx)
+        ctx.mark_non_differentiable(i_xy, i_yx)
+        return d_xy, d_yx, i_xy, i_yx
+
+    @staticmethod
+    def backward(ctx, gdx, gdy, _a, _b):
+        x, y, i_xy, i_yx = ctx.saved_tensors
+        B, N, _ = x.shape
+        M = y.shape[1]
+        gdx = torch.zeros(B, N, device=x.device) if gdx is None else gdx.contiguous().float()
+        gdy = torch.zeros(B, M, device=x.device) if gdy is None else gdy.contiguous().float()
+        gx = torch.empty_like(x)
+        gy = torch.empty_like(y)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().shwd_chamfer_bwd(_ptr(x), _ptr(y), B, N, M, _ptr(i_xy), _ptr(i_yx), _ptr(gdx), _ptr(gdy), _ptr(gx),
+                                                   _ptr(gy), _stream()), "shwd_chamfer_bwd")
+        return gx, gy
+
+
+def chamfer_nn(x, y):
+    """Nearest-neighbour squared distances and indices in both directions: (d_xy, d_yx, idx_xy, idx_yx)."""
+    xc, _ = _as_cloud(x, "x")
+    yc, _ = _as_cloud(y, "y")
+    if xc.shape[0] != yc.shape[0]:
+        raise ValueError("batch sizes differ: %d vs %d" % (xc.shape[0], yc.shape[0]))
+    return ChamferFn.apply(xc, yc)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ProjectCircleFn(torch.autograd.Function):
+    """x (B,N,3), U (P,3,2) -> circle coordinates (B,P,N) in [0,1]  (sliced_cost, max_spherical_sliced_w.py:270-279)."""
+
+    @staticmethod
+    def forward(ctx, x, U):
+        x = x.contiguous()
+        U = U.contiguous()  # torch.linalg.qr returns column-major batches
+        B, N, _ = x.shape
+        P = U.shape[0]
+        keys = torch.empty(B, P, N, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().shwd_project_circle(_ptr(x), _ptr(U), B, N, P, _ptr(keys), _stream()), "shwd_project_circle")
+        ctx.save_for_backward(x, U)
+        return keys
+
+    @staticmethod
+    def backward(ctx, gk):
+        x, U = ctx.saved_tensors
+        B, N, _ = x.shape
+        gx = torch.empty_like(x)
+        gk = gk.contiguous()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().shwd_project_circle_bwd(_ptr(x), _ptr(U), B, N, U.shape[0], _ptr(gk), _ptr(gx), _stream()),
+                       "shwd_project_circle_bwd")
+        return gx, None
+
+
+class ProjectLineFn(torch.autograd.Function):
+    """x (B,N,3), theta (P,3) -> projections (B,P,N)  (Flow_ellipsoid.ipynb:214-216)."""
+
+    @staticmethod
+    def forward(ctx, x, theta):
+        x = x.contiguous()
+        theta = theta.contiguous()
+        B, N, _ = x.shape
+        P = theta.shape[0]
+        keys = torch.empty(B, P, N, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().shwd_project_line(_ptr(x), _ptr(theta), B, N, P, _ptr(keys), _stream()), "shwd_project_line")
+        ctx.save_for_backward(theta)
+        ctx.shape = (B, N)
+        return keys
+
+    @staticmethod
+    def backward(ctx, gk):
+        (theta,) = ctx.saved_tensors
+        B, N = ctx.shape
+        gx = torch.empty(B, N, 3, device=gk.device, dtype=torch.float32)
+        gk = gk.contiguous()
+        with torch.cuda.device(gk.device):
+            _lib.check(_lib.lib().shwd_project_line_bwd(_ptr(theta), B, N, theta.shape[0], _ptr(gk), _ptr(gx), _stream()),
+                       "shwd_project_line_bwd")
+        return gx, None
+
+
+def segmented_sort_raw(keys):
+    """keys (..., len) float32 CUDA -> (sorted, perm int64), perm identical to torch.sort(keys, -1, stable=True)."""
+    lib = _lib.lib()
+    if not keys.is_cuda:
+        raise RuntimeError("keys must live on a CUDA device: no CPU fallback")
+    k = keys.contiguous().float()
+    length = k.shape[-1]
+    segs = k.numel() // max(length, 1)
+    out = torch.empty_like(k)
+    perm = torch.empty(k.shape, device=k.device, dtype=torch.int64)
+    wsb = lib.shwd_segmented_sort_workspace_bytes(segs, length)
+    ws = torch.empty(max(wsb, 8), device=k.device, dtype=torch.uint8)
+    with torch.cuda.device(k.device):
+        _lib.check(lib.shwd_segmented_sort(_ptr(k), segs, length, _ptr(out), _ptr(perm), _ptr(ws), wsb, _stream()), "shwd_segmented_sort")
+    return out, perm
+
+
+class SegmentedSortFn(torch.autograd.Function):
+    """Differentiable stable sort along the last dim: gradient of the sorted values scatters back through the
+    permutation (what autograd does for torch.sort's values output)."""
+
+    @staticmethod
+    def forward(ctx, keys):
+        out, perm = segmented_sort_raw(keys)
+        ctx.save_for_backward(perm)
+        ctx.mark_non_differentiable(perm)
+        return out, perm
+
+    @staticmethod
+    def backward(ctx, gs, _gp):
+        (perm,) = ctx.saved_tensors
+        gs = gs.contiguous().float()
+        length = perm.shape[-1]
+        segs = perm.numel() // max(length, 1)
+        gk = torch.empty_like(gs)
+        with torch.cuda.device(gs.device):
+            _lib.check(_lib.lib().shwd_unsort(_ptr(gs), _ptr(perm), segs, length, _ptr(gk), _stream()), "shwd_unsort")
+        return gk
+
+
+class CircularW1Fn(torch.autograd.Function):
+    """Sorted circle coordinates us (S,n), vs (S,m) -> W1 per slice (S)  (emd1D_circle, max_spherical_sliced_w.py:230-247)."""
+
+    @staticmethod
+    def forward(ctx, us, vs):
+        us = us.contiguous()
+        vs = vs.contiguous()
+        S, n = us.shape
+        m = vs.shape[1]
+        w = torch.empty(S, device=us.device, dtype=torch.float32)
+        gus = torch.empty_like(us)
+        gvs = torch.empty_like(vs)
+        with torch.cuda.device(us.device):
+            _lib.check(_lib.lib().shwd_circular_w1(_ptr(us), _ptr(vs), S, n, m, _ptr(w), _ptr(gus), _ptr(gvs), None, 0, _stream()),
+                       "shwd_circular_w1")
+        ctx.save_for_backward(gus, gvs)
+        return w
+
+    @staticmethod
+    def backward(ctx, gw):
+        gus, gvs = ctx.saved_tensors
+        g = gw.contiguous().unsqueeze(1)
+        return gus * g, gvs * g
+
+
+class EuclidSWFn(torch.autograd.Function):
+    """Sorted projections xs, ys (S,n) -> sum_n |xs-ys|^p per slice (S)  (Flow_ellipsoid.ipynb:217-219)."""
+
+    @staticmethod
+    def forward(ctx, xs, ys, p):
+        xs = xs.contiguous()
+        ys = ys.contiguous()
+        S, n = xs.shape
+        acc = torch.empty(S, device=xs.device, dtype=torch.float32)
+        gxs = torch.empty_like(xs)
+        gys = torch.empty_like(ys)
+        with torch.cuda.device(xs.device):
+            _lib.check(_lib.lib().shwd_euclid_sw(_ptr(xs), _ptr(ys), S, n, float(p), _ptr(acc), _ptr(gxs), _ptr(gys), _stream()),
+                       "shwd_euclid_sw")
+        ctx.save_for_backward(gxs, gys)
+        return acc
+
+    @staticmethod
+    def backward(ctx, ga):
+        gxs, gys = ctx.saved_tensors
+        g = ga.contiguous().unsqueeze(1)
+        return gxs * g, gys * g, None
+
+
+def spherical_sliced_w1(Xs, Xt, U):
+    """mean_P circular-W1 of the great-circle projections (sliced_cost with p == 1, explicit frames U (P,3,2))."""
+    xs, _ = _as_cloud(Xs, "Xs")
+    xt, _ = _as_cloud(Xt, "Xt")
+    U = U.to(device=xs.device, dtype=torch.float32).contiguous()
+    ks = ProjectCircleFn.apply(xs, U)  # (B,P,n)
+    kt = ProjectCircleFn.apply(xt, U)
+    B, P, n = ks.shape
+    m = kt.shape[2]
+    ss, _ = SegmentedSortFn.apply(ks.reshape(B * P, n))
+    st, _ = SegmentedSortFn.apply(kt.reshape(B * P, m))
+    w = CircularW1Fn.apply(ss, st).reshape(B, P)
+    return w.mean(dim=1)  # (B,)
+
+
+def euclid_sliced_w(x, y, theta, p=2.0):
+    """(mean_P sum_n |sort(x theta) - sort(y theta)|^p)^(1/p) per pair (Flow_ellipsoid.ipynb:208-220)."""
+    xc, _ = _as_cloud(x, "x")
+    yc, _ = _as_cloud(y, "y")
+    if xc.shape[1] != yc.shape[1]:
+        raise ValueError("Euclidean sliced W needs equally sized clouds")
+    theta = theta.to(device=xc.device, dtype=torch.float32).contiguous()
+    kx = ProjectLineFn.apply(xc, theta)
+    ky = ProjectLineFn.apply(yc, theta)
+    B, P, n = kx.shape
+    sx, _ = SegmentedSortFn.apply(kx.reshape(B * P, n))
+    sy, _ = SegmentedSortFn.apply(ky.reshape(B * P, n))
+    acc = EuclidSWFn.apply(sx, sy, float(p)).reshape(B, P)
+    return acc.mean(dim=1).pow(1.0 / p)

