@@ -1,0 +1,45 @@
+"""Multi-GPU plumbing: the loss path shards by independent units -- pairs of the batch, or slices of a
+single-pair sliced run -- one process per GPU, no collective on the data path.  The only collectives are the scalar
+loss all-reduce of a data-parallel step (``mean of equal-sized local means == the reference's emd / B``,
+s2_wasserstein.py:44) and, for slice sharding, the all-reduce of the per-rank partial sums / gradients.
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the transport.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_units, rank, world_size):
+    """Contiguous [begin, end) of ``n_units`` independent units owned by ``rank`` (sizes differ by at most one)."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("invalid rank/world_size %r/%r" % (rank, world_size))
+    base, rem = divmod(int(n_units), world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def global_mean(local_sum, local_count, group=None):
+    """Mean over all ranks of per-unit values given this rank's sum and count: one all-reduce of a 2-vector.
+    Differentiable w.r.t. ``local_sum`` (the gradient of the global mean w.r.t. a local unit is 1 / global_count)."""
+    count = torch.as_tensor(float(local_count), dtype=local_sum.dtype, device=local_sum.device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        tot = torch.stack([local_sum.detach(), count])
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+        # value: global; gradient: flows through the local contribution only
+        return (local_sum - local_sum.detach() + tot[0]) / tot[1]
+    return local_sum / count
+
+
+def sharded_pair_loss(loss_fn, x, y, rank=None, world_size=None, group=None):
+    """Evaluate ``loss_fn(x_shard, y_shard) -> per-pair losses (b,)`` on this rank's slice of the batch and return the
+    global batch mean (what the reference's single-process ``emd / B`` returns)."""
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world_size is None:
+        world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+    b0, b1 = shard_range(x.shape[0], rank, world_size)
+    if b1 > b0:
+        per_pair = loss_fn(x[b0:b1], y[b0:b1])
+        s = per_pair.sum()
+    else:
+        s = x.new_zeros(())
+    return global_mean(s, b1 - b0, group)

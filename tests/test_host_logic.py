@@ -1,0 +1,149 @@
+"""CPU: host-side mirror of the reference interface -- names, signatures, error behaviour, the phi flows, and the
+batch-sharding helper under a world_size-2 gloo group.  No CUDA compute happens here; the product path must refuse
+CPU tensors instead of falling back."""
+import inspect
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import shwd
+
+L = shwd.losses
+
+
+def test_exported_names_match_reference_packages():
+    # Point_Cloud_Resistration/losses/__init__.py:27-32 and Comparison_.../losses/__init__.py:1-2
+    for name in ("Cos_disimilarity_W", "Geodesic_distance_W", "Norm_Flow_structure", "Norm_Flow_structure_optuna",
+                 "max_cos_disimilarity_wassersten_distance", "pseudo_max_cos_disimilarity_wassersten_distance",
+                 "log_Sinkhorn_Distance_Loss", "log_N_Sinkhorn_Distance_Loss"):
+        assert hasattr(L, name), name
+
+
+def test_signatures_keep_the_reference_positional_arguments():
+    def params(fn):
+        return list(inspect.signature(fn).parameters)
+    assert params(L.Geodesic_distance_W.__init__)[:3] == ["self", "device", "p"]
+    assert params(L.Cos_disimilarity_W.__init__)[:3] == ["self", "device", "p"]
+    assert params(L.max_cos_disimilarity_wassersten_distance.__init__)[:8] == [
+        "self", "phi", "CSW", "device", "phi_op", "max_iter", "lam", "psi_minibatch_size"]
+    assert params(L.max_cos_disimilarity_wassersten_distance.forward) == ["self", "first_samples", "second_samples", "train_or_test"]
+    assert params(L.pseudo_max_cos_disimilarity_wassersten_distance.__init__)[:8] == [
+        "self", "CSW", "device", "phi_num", "lam", "n_flow_layer", "flow_name", "mean_or_max_or_softmax"]
+    assert params(L.log_Sinkhorn_Distance_Loss.__init__)[:5] == ["self", "eps", "max_iter", "batch_reduction", "type_of_cost_norm"]
+    assert params(L.log_Sinkhorn_Distance_Loss.forward) == ["self", "x", "y", "device"]
+    assert params(L.log_N_Sinkhorn_Distance_Loss.__init__)[:6] == ["self", "eps", "max_iter", "batch_reduction", "type_of_cost_norm",
+                                                                    "type_of_Wasserstein_N"]
+    assert params(L.sliced_wasserstein_sphere)[:7] == ["Xs", "Xt", "num_projections", "device", "u_weights", "v_weights", "p"]
+    assert params(L.Norm_Flow_structure.__init__) == ["self", "input_dim", "flow_name", "n_flow_layer"]
+    sig = inspect.signature(L.chamfer_distance)
+    assert sig.parameters["batch_reduction"].default == "mean" and sig.parameters["point_reduction"].default == "mean"
+
+
+def test_error_behaviour_matches_reference():
+    with pytest.raises(ValueError, match="Flow name is not valid"):  # s2_wasserstein.py:158
+        L.Norm_Flow_structure(flow_name="Nope")
+    with pytest.raises(ValueError, match="type_of_cost_norm must be 'L1' or 'L2'"):  # Sinkhorn.py:91
+        L.Sinkhorn_Distance_Loss(eps=0.1, max_iter=3, type_of_cost_norm="L7")
+    crit = L.pseudo_max_cos_disimilarity_wassersten_distance(None, "cpu", phi_num=1, n_flow_layer=1, flow_name="Planar",
+                                                             mean_or_max_or_softmax="bogus")
+    with pytest.raises(ValueError, match="mean_or_max_or_softmax is not valid"):  # s2_wasserstein.py:344
+        crit(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+
+
+def test_no_cpu_fallback():
+    x = torch.randn(2, 8, 3)
+    for call in (lambda: shwd.entropic_ot(x, x), lambda: shwd.sphere_map(x), lambda: shwd.chamfer_nn(x, x),
+                 lambda: L.Geodesic_distance_W("cpu", 2)(x, x), lambda: L.chamfer_distance(x, x)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+    with pytest.raises(ValueError):
+        shwd.ops._as_cloud(torch.zeros(2, 3, 4).cuda() if torch.cuda.is_available() else _FakeCuda((2, 3, 4)), "x")
+
+
+class _FakeCuda(torch.Tensor):
+    """A CPU tensor that claims to be CUDA, to reach the shape validation without a GPU."""
+    @staticmethod
+    def __new__(cls, shape):
+        return torch.Tensor._make_subclass(cls, torch.zeros(shape))
+
+    @property
+    def is_cuda(self):
+        return True
+
+
+def test_flows_forward_and_parameter_counts():
+    torch.manual_seed(0)
+    x = torch.randn(2, 16, 3)
+    res = L.Norm_Flow_structure(flow_name="Residual", n_flow_layer=3)
+    # 1284 parameters for Residual x3 in the reference = 1278 network parameters + 2 (geom_p, lamb) per block
+    assert sum(p.numel() for p in res.parameters()) == 1278
+    y = res(x)
+    assert y.shape == x.shape and torch.isfinite(y).all()
+    # Lipschitz < 1 residual branch: the map is a contraction-perturbed identity
+    a, b = torch.randn(64, 3), torch.randn(64, 3)
+    for flow in res.net:
+        ga, gb = flow.net(a), flow.net(b)
+        assert ((ga - gb).norm(dim=-1) <= 1.0 * (a - b).norm(dim=-1) + 1e-6).all()
+    pl = L.Norm_Flow_structure(flow_name="Planar", n_flow_layer=3)
+    assert sum(p.numel() for p in pl.parameters()) == 3 * 7
+    assert pl(x).shape == x.shape
+    opt = L.Norm_Flow_structure_optuna(flow_name="Residual", n_flow_layer=2, Residual_hidden_units=4, Residual_hidden_layers=3)
+    assert opt(x).shape == x.shape
+
+
+def test_regularizer_cpu_path_of_wrapper_matches_formula():
+    crit = L.max_cos_disimilarity_wassersten_distance(phi=None, CSW=None, device="cpu", phi_op=None)
+    x = torch.randn(3, 10, 3)
+    assert torch.allclose(crit.regularization_of_normalizing_flow(x), (x.norm(dim=-1) - 1).abs().sum())
+
+
+def test_shard_range_partitions_exactly():
+    from shwd_b200.dist import shard_range
+    for n in (0, 1, 7, 32, 33):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from shwd_b200.dist import sharded_pair_loss
+    torch.manual_seed(0)
+    x = torch.randn(5, 6, 3, requires_grad=True)  # identical on both ranks; 5 pairs -> shards of 3 and 2
+    y = torch.randn(5, 6, 3)
+
+    def per_pair(a, b):  # stand-in for the CUDA loss: any per-pair function
+        return ((a - b) ** 2).sum(dim=(1, 2))
+
+    loss = sharded_pair_loss(per_pair, x, y)
+    loss.backward()
+    g = x.grad.clone()
+    dist.all_reduce(g)  # DDP would sum the shards' gradients
+    ref = per_pair(x.detach(), y).mean()
+    ok = torch.allclose(loss.detach(), ref, rtol=1e-6) and torch.allclose(g, 2 * (x.detach() - y) / 5, rtol=1e-5, atol=1e-7)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_mean_equals_single_process_mean_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
