@@ -325,7 +325,7 @@ def main():
                  "mufu_peak_gops": mufu_peak / 1e9, "fp32_peak_tlaneops": fp32_peak / 1e12}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N=1 only (torchrun pins OMP_NUM_THREADS=1)
         v, threads, _ = cpu_reference_pairs_per_s(4)
         cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
                "sample": "4 pairs of the cfg2 workload (N=1024, L=100), one fwd+bwd by torch autograd on the host cores, float32"}

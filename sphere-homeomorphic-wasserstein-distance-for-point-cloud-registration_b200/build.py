@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libshwd_b200.so")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-ftz=true", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
 
@@ -70,4 +70,7 @@ def build(force=False, extra_flags=(), verbose=False):
 
 if __name__ == "__main__":
     flags = ["-DSHWD_EXACT_DOT"] if "--exact-dot" in sys.argv else []
+    if "--profile" in sys.argv:
+        flags.append("-DSHWD_PROFILE")
+    flags += [a for a in sys.argv[1:] if a.startswith("-D")]
     print(build(force="--force" in sys.argv, extra_flags=flags, verbose=True))

@@ -45,7 +45,7 @@ __device__ __forceinline__ float scaled_acos(const float (&q)[7], float hpi, flo
   r = fmaf(r, a, q[2]);
   r = fmaf(r, a, q[1]);
   r = fmaf(r, a, q[0]);
-  float sq = sqrt_approx(fabsf(w));
+  float sq = sqrt_approx(fabsf(w));  // MUFU.SQRT and MUFU.RSQ issue at the same rate on sm_100 (A/B measured)
   float h = fmaf(-sq, r, hpi);  // s * asin(|c|)
   float hs = copysignf(h, c);
   return hpi - hs;

@@ -32,12 +32,21 @@
 // S^v,l), i.e. two exp2 per element instead of a 4-value cross-lane reduction per element.
 #include "common.cuh"
 #include "cost.cuh"
+#include "f32x2.cuh"
 #include <math.h>
 
 namespace shwd {
 
-constexpr int SK_THREADS = 512;
+#ifndef SHWD_THREADS
+#define SHWD_THREADS 512
+#endif
+#ifndef SHWD_UNROLL
+#define SHWD_UNROLL 1
+#endif
+constexpr int SK_UNROLL = SHWD_UNROLL;
+constexpr int SK_THREADS = SHWD_THREADS;  // 256: two CTAs per SM (one CTA's inter-CTA wait / staging overlaps the other's compute)
 constexpr int SK_WARPS = SK_THREADS / 32;
+constexpr int SK_CTAS_PER_SM = 512 / SK_THREADS;
 constexpr int GMAX = 8;          // owner groups (of 32) per visit
 constexpr int CHUNK = 2048;      // streamed points staged per pass
 constexpr int CHUNK_PAD = CHUNK + 4 * SK_WARPS;
@@ -46,6 +55,28 @@ constexpr float LN2F = 0.6931471805599453f;
 constexpr float NEG_BIG = -3.0e38f;
 
 enum { MODE_LSE = 0, MODE_FINAL = 1, MODE_BWD = 2 };
+
+// Optional in-kernel phase timing (build with -DSHWD_PROFILE): thread 0 of every CTA accumulates clock64 deltas per
+// phase into the workspace's err area tail; read back by tools/phase_profile.py.  Off in the product build.
+#ifdef SHWD_PROFILE
+__device__ unsigned long long g_prof[8];
+__shared__ long long s_prof_t;
+#define PROF_INIT()                          \
+  do {                                       \
+    if (threadIdx.x == 0) s_prof_t = clock64(); \
+  } while (0)
+#define PROF_MARK(slot)                                                     \
+  do {                                                                      \
+    if (threadIdx.x == 0) {                                                 \
+      long long _n = clock64();                                             \
+      atomicAdd(&g_prof[slot], (unsigned long long)(_n - s_prof_t));        \
+      s_prof_t = _n;                                                        \
+    }                                                                       \
+  } while (0)
+#else
+#define PROF_INIT()
+#define PROF_MARK(slot)
+#endif
 
 struct SinkParams {
   const float4* X;
@@ -145,47 +176,353 @@ __device__ __forceinline__ void signal_done(int* done_b, int n) {
   }
 }
 
-// One visit-set: owners [lg0, lg1) (32-owner groups) of one pair against all streamed points.
+// ---- finish a visit: merge the SK_WARPS partials of every owner in fixed order, write the half-step's outputs.
+template <int MODE, bool FINAL_TERM>
+__device__ __forceinline__ void finalize_visit(const CostParams& cp, const SweepIO (&ios)[2], const int (&glo)[2], int n0, int c0v, int ng,
+                                               const float4* part) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // this thread's group (visit-local index = its warp index) and the segment it belongs to
+  const int cidx = c0v + (threadIdx.x >> 5);
+  const int seg = cidx >= n0;
+  const SweepIO& io = ios[seg];
+  const int gown = seg ? glo[1] + cidx - n0 : glo[0] + cidx;
+    // ---- merge the SK_WARPS partials of every owner in fixed order and finish the half-step for these owners
+    float errv = 0.f;
+    if (threadIdx.x < ng * 32) {
+      const int g = threadIdx.x >> 5;
+      const int o = gown * 32 + lane;
+      if (o < io.n_own) {
+        if (MODE == MODE_LSE) {
+          float mx = NEG_BIG;
+#pragma unroll
+          for (int w = 0; w < SK_WARPS; ++w) mx = fmaxf(mx, part[(w * GMAX + g) * 32 + lane].x);
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < SK_WARPS; ++w) {
+            float4 st = part[(w * GMAX + g) * 32 + lane];
+            sum += st.y * ex2_approx(st.x - mx);
+          }
+          // new potential = lconst - lse2 in double (a correctly rounded, monotone map lets the iteration settle on a
+          // bitwise fixed point like the reference does -- the early-stop rule of sinkhorn.py:42-44 needs that);
+          // keep the float32 rounding residual for the backward
+          const double npd = (double)io.lconst - ((double)mx + log2((double)sum));
+          const float np = (float)npd;
+          if (io.out_pot_lo) io.out_pot_lo[o] = (float)(npd - (double)np);
+          if (io.err_out) errv = fabsf(np - (io.old_pot ? __ldcg(io.old_pot + o) : 0.f));
+          io.out_pot[o] = np;
+        } else if (MODE == MODE_FINAL) {
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < SK_WARPS; ++w) sum += part[(w * GMAX + g) * 32 + lane].x;
+          if (io.own_is_beta) {
+            const double full = (double)__ldcg(io.own_pot + o) + (double)__ldcg(io.own_lo + o) - (double)io.c2;
+            sum *= exp2f((float)(full - (double)(float)full));
+          }
+          io.out_pc[o] = sum * io.pc_scale;
+        } else {
+          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int w = 0; w < SK_WARPS; ++w) {
+            float4 st = part[(w * GMAX + g) * 32 + lane];
+            sum.x += st.x;
+            sum.y += st.y;
+            sum.z += st.z;
+            sum.w += st.w;
+          }
+          if (io.adj_out) {
+            // regular sweeps: -sum_j adj_j S_ij ; row sweep(L*): abar^L_i = -ln2 * sum_j u_ij (k lambda_j - kC_ij)
+            io.adj_out[o] = (FINAL_TERM && !io.own_is_beta) ? -LN2F * sum.w : -sum.w;
+          }
+          float4 gv = make_float4(sum.x * cp.gscale, sum.y * cp.gscale, sum.z * cp.gscale, 0.f);
+          if (io.G_accumulate) {
+            float4 old = __ldcg(io.G + o);
+            gv.x += old.x;
+            gv.y += old.y;
+            gv.z += old.z;
+          }
+          __stcg(io.G + o, gv);
+        }
+      }
+    }
+    if (MODE == MODE_LSE && ios[0].err_out) {
+      // early-stop statistic sum_i |u_new - u_old| (sinkhorn.py:42): one float atomic per warp (= per owner group)
+      errv = warp_sum(errv);
+      if (lane == 0 && threadIdx.x < ng * 32) atomicAdd(io.err_out, errv);
+    }
+  __syncthreads();
+}
+
+// ---- streamed chunk staging, scalar layout: sS[j] = (x, y, z, potential), sAdj[j] = (adjoint', addend)
+template <int MODE, bool FINAL_TERM>
+__device__ __forceinline__ void stage_scalar(const SweepIO& io, int c0, int cnt, int total, float4* sS, float2* sAdj) {
+  for (int j = threadIdx.x; j < total; j += SK_THREADS) {
+    float4 r = make_float4(0.f, 0.f, 0.f, -INFINITY);
+    float2 a = make_float2(0.f, -INFINITY);
+    if (MODE == MODE_BWD && FINAL_TERM && !io.own_is_beta) r.w = 0.f;  // here .w carries k*lambda_j (0 * inf = NaN otherwise)
+    if (j < cnt) {
+      r = __ldg(io.str + c0 + j);
+      r.w = io.str_pot ? __ldcg(io.str_pot + c0 + j) : 0.f;
+      if (MODE == MODE_BWD || (MODE == MODE_FINAL && !io.own_is_beta)) {
+        // the streamed potential normalises the primary softmax: apply (pot + lo - c1) as a float32 addend plus a
+        // multiplicative correction 2^res folded into the adjoint, so the normalisation is exact to ~1e-7
+        const double full = (double)r.w + (io.str_lo ? (double)__ldcg(io.str_lo + c0 + j) : 0.0) - (double)io.c1;
+        a.y = (float)full;
+        const float corr = exp2f((float)(full - (double)a.y));
+        if (MODE == MODE_FINAL) {
+          a.x = corr;
+        } else if (FINAL_TERM && !io.own_is_beta) {
+          a.x = io.fin_A * corr;
+          r.w = __ldcg(io.fin_cpc + c0 + j) * io.fin_klam_scale;  // k * lambda_j (the secondary term is off at l = L*)
+        } else {
+          a.x = io.str_adj ? __ldcg(io.str_adj + c0 + j) * io.str_adj_scale * corr : 0.f;
+        }
+      }
+    }
+    sS[j] = r;
+    if (MODE != MODE_LSE) sAdj[j] = a;
+  }
+}
+
+// ---- packed layout (geodesic p=2 fast path, regular sweeps): record t holds streamed points j = t ("lo" half) and
+// j = t + T ("hi" half) as float2 pairs in six SoA arrays of T entries: X, Y, Z, POT (+ ADJ, ADD for the backward).
+struct PackedSmem {
+  float2 *X, *Y, *Z, *P, *A, *S;
+};
+__device__ __forceinline__ PackedSmem packed_view(float4* sS, float2* sAdj, int T) {
+  PackedSmem v;
+  float2* b = reinterpret_cast<float2*>(sS);
+  v.X = b;
+  v.Y = b + T;
+  v.Z = b + 2 * T;
+  v.P = b + 3 * T;
+  v.A = sAdj;
+  v.S = sAdj + T;
+  return v;
+}
+template <int MODE>
+__device__ __forceinline__ void stage_packed(const SweepIO& io, int c0, int cnt, int T, const PackedSmem& v) {
+  float* X = reinterpret_cast<float*>(v.X);
+  float* Y = reinterpret_cast<float*>(v.Y);
+  float* Z = reinterpret_cast<float*>(v.Z);
+  float* P = reinterpret_cast<float*>(v.P);
+  float* A = reinterpret_cast<float*>(v.A);
+  float* S = reinterpret_cast<float*>(v.S);
+  for (int q = threadIdx.x; q < 2 * T; q += SK_THREADS) {
+    const int half = q >= T, t = half ? q - T : q;
+    const int j = q;  // lo half: j = t; hi half: j = t + T
+    float4 r = make_float4(0.f, 0.f, 0.f, -INFINITY);
+    float2 a = make_float2(0.f, -INFINITY);
+    if (j < cnt) {
+      r = __ldg(io.str + c0 + j);
+      r.w = io.str_pot ? __ldcg(io.str_pot + c0 + j) : 0.f;
+      if (MODE == MODE_BWD) {
+        const double full = (double)r.w + (io.str_lo ? (double)__ldcg(io.str_lo + c0 + j) : 0.0) - (double)io.c1;
+        a.y = (float)full;
+        const float corr = exp2f((float)(full - (double)a.y));
+        a.x = io.str_adj ? __ldcg(io.str_adj + c0 + j) * io.str_adj_scale * corr : 0.f;
+      }
+    }
+    const int o = 2 * t + half;
+    X[o] = r.x;
+    Y[o] = r.y;
+    Z[o] = r.z;
+    P[o] = r.w;
+    if (MODE == MODE_BWD) {
+      A[o] = a.x;
+      S[o] = a.y;
+    }
+  }
+}
+
+// th = sqrt(k) * acos(c) on a packed pair -- operation for operation the scalar scaled_acos() (bit-identical results)
+__device__ __forceinline__ f2 scaled_acos2(const float (&q)[7], float hpi, f2 c) {
+  const f2 a = abs2(c);
+  const f2 w = sub2(bc2(1.f), a);
+  f2 r = bc2(q[6]);
+  r = fma2(r, a, bc2(q[5]));
+  r = fma2(r, a, bc2(q[4]));
+  r = fma2(r, a, bc2(q[3]));
+  r = fma2(r, a, bc2(q[2]));
+  r = fma2(r, a, bc2(q[1]));
+  r = fma2(r, a, bc2(q[0]));
+  const f2 sq = mk2(sqrt_approx(fabsf(lo2(w))), sqrt_approx(fabsf(hi2(w))));
+  const f2 h = fma2(neg2(sq), r, bc2(hpi));
+  const f2 hs = mk2(copysignf(lo2(h), lo2(c)), copysignf(hi2(h), hi2(c)));
+  return sub2(bc2(hpi), hs);
+}
+__device__ __forceinline__ f2 dot3_2(float ox, float oy, float oz, f2 X, f2 Y, f2 Z) {
+  return fma2(bc2(oz), Z, fma2(bc2(oy), Y, mul2(bc2(ox), X)));
+}
+
+// One (R owner groups, warp-slice) pass of a regular geodesic-p2 sweep in packed arithmetic: every lane owns R points
+// (one per group) and shares each streamed record between them, so one LDS.128 per array feeds 4R elements.
+// tb..te (multiple of 4) is the warp's range of packed records.  Results go to the warp's partial slots (slot[r*32]),
+// same format as the scalar path.
+template <int MODE, int R>
+__device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const SweepIO& io, const PackedSmem& v, int tb, int te,
+                                                    bool first_chunk, int o0, float4* slot) {
+  float4 op[R];
+  bool live[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    live[r] = (o0 + 32 * r) < io.n_own;
+    op[r] = live[r] ? __ldg(io.own + o0 + 32 * r) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (MODE == MODE_LSE) {
+    f2 rm[R], rs[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      rm[r] = bc2(NEG_BIG);
+      rs[r] = bc2(0.f);
+      if (!first_chunk) {
+        float4 st = slot[32 * r];  // (max, sum) merged so far: restart both halves from it, the sum in the lo half only
+        rm[r] = bc2(st.x);
+        rs[r] = mk2(st.y, 0.f);
+      }
+    }
+#pragma unroll SK_UNROLL
+    for (int t = tb; t < te; t += 4) {
+      f2 m[R][4];
+#pragma unroll
+      for (int e = 0; e < 4; e += 2) {
+        const float4 X = *reinterpret_cast<const float4*>(v.X + t + e), Y = *reinterpret_cast<const float4*>(v.Y + t + e);
+        const float4 Z = *reinterpret_cast<const float4*>(v.Z + t + e), P = *reinterpret_cast<const float4*>(v.P + t + e);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const f2 th0 = scaled_acos2(cp.q, cp.hpi, dot3_2(op[r].x, op[r].y, op[r].z, mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y)));
+          const f2 th1 = scaled_acos2(cp.q, cp.hpi, dot3_2(op[r].x, op[r].y, op[r].z, mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w)));
+          m[r][e] = fma2(neg2(th0), th0, mk2(P.x, P.y));
+          m[r][e + 1] = fma2(neg2(th1), th1, mk2(P.z, P.w));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const f2 nm = max2(max2(max2(m[r][0], m[r][1]), max2(m[r][2], m[r][3])), rm[r]);
+        rs[r] = mul2(rs[r], ex2_2(sub2(rm[r], nm)));
+        rs[r] = add2(rs[r], add2(add2(ex2_2(sub2(m[r][0], nm)), ex2_2(sub2(m[r][1], nm))),
+                                 add2(ex2_2(sub2(m[r][2], nm)), ex2_2(sub2(m[r][3], nm)))));
+        rm[r] = nm;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float M = fmaxf(lo2(rm[r]), hi2(rm[r]));
+      const float S = lo2(rs[r]) * ex2_approx(lo2(rm[r]) - M) + hi2(rs[r]) * ex2_approx(hi2(rm[r]) - M);
+      slot[32 * r] = make_float4(M, S, 0.f, 0.f);
+    }
+  } else {
+    float opot1[R], o2[R], oadj[R];
+    f2 ax[R], ay[R], az[R], aw[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      opot1[r] = -INFINITY;
+      o2[r] = -INFINITY;
+      oadj[r] = 0.f;
+      const int o = o0 + 32 * r;
+      if (live[r]) {
+        if (io.own_pot1) opot1[r] = __ldcg(io.own_pot1 + o);
+        if (io.own_pot2) {
+          const double full = (double)__ldcg(io.own_pot2 + o) + (io.own_lo2 ? (double)__ldcg(io.own_lo2 + o) : 0.0) - (double)io.c2;
+          o2[r] = (float)full;
+          oadj[r] = __ldcg(io.own_adj2 + o) * io.own_adj2_scale * exp2f((float)(full - (double)o2[r]));
+        }
+      }
+      ax[r] = ay[r] = az[r] = aw[r] = bc2(0.f);
+    }
+#pragma unroll SK_UNROLL
+    for (int t = tb; t < te; t += 2) {
+      const float4 X = *reinterpret_cast<const float4*>(v.X + t), Y = *reinterpret_cast<const float4*>(v.Y + t);
+      const float4 Z = *reinterpret_cast<const float4*>(v.Z + t), P = *reinterpret_cast<const float4*>(v.P + t);
+      const float4 A = *reinterpret_cast<const float4*>(v.A + t), S = *reinterpret_cast<const float4*>(v.S + t);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const f2 x2 = h ? mk2(X.z, X.w) : mk2(X.x, X.y), y2 = h ? mk2(Y.z, Y.w) : mk2(Y.x, Y.y);
+        const f2 z2 = h ? mk2(Z.z, Z.w) : mk2(Z.x, Z.y), p2 = h ? mk2(P.z, P.w) : mk2(P.x, P.y);
+        const f2 a2 = h ? mk2(A.z, A.w) : mk2(A.x, A.y), s2 = h ? mk2(S.z, S.w) : mk2(S.x, S.y);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const f2 c = dot3_2(op[r].x, op[r].y, op[r].z, x2, y2, z2);
+          const f2 th = scaled_acos2(cp.q, cp.hpi, c);
+          const f2 om = fma2(neg2(c), c, bc2(1.f));
+          const f2 rs = mk2(rsqrt_approx(fmaxf(lo2(om), 1e-12f)), rsqrt_approx(fmaxf(hi2(om), 1e-12f)));
+          const f2 gs = mul2(th, rs);
+          const f2 nth = neg2(th);
+          const f2 S1 = ex2_2(add2(fma2(nth, th, bc2(opot1[r])), s2));
+          const f2 S2 = ex2_2(add2(fma2(nth, th, p2), bc2(o2[r])));
+          const f2 w1 = mul2(a2, S1);
+          aw[r] = add2(aw[r], w1);
+          const f2 wg = mul2(fma2(bc2(oadj[r]), S2, w1), gs);
+          ax[r] = fma2(wg, x2, ax[r]);
+          ay[r] = fma2(wg, y2, ay[r]);
+          az[r] = fma2(wg, z2, az[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float4 acc = first_chunk ? make_float4(0.f, 0.f, 0.f, 0.f) : slot[32 * r];
+      acc.x += lo2(ax[r]) + hi2(ax[r]);
+      acc.y += lo2(ay[r]) + hi2(ay[r]);
+      acc.z += lo2(az[r]) + hi2(az[r]);
+      acc.w += lo2(aw[r]) + hi2(aw[r]);
+      slot[32 * r] = acc;
+    }
+  }
+}
+
+// One item of a half-step: up to two SEGMENTS -- owner-group ranges [glo[s], ghi[s]) of two different pairs (a CTA whose
+// share straddles a pair boundary) -- swept together: both pairs' streamed data are staged side by side, all groups are
+// computed in one pass and finalised together, so a straddling CTA pays the fixed per-item cost (staging, barriers,
+// finalise, signal) once instead of twice (every other CTA of both pairs waits for it each half-step).
 template <int FAST, int MODE, bool FINAL_TERM>
-__device__ void sweep(const CostParams& cp, const SweepIO& io, int lg0, int lg1, float4* sS, float2* sAdj, float4* part) {
+__device__ void sweep(const CostParams& cp, const SweepIO (&ios)[2], const int (&glo)[2], const int (&ghi)[2], int nseg, float4* sS0,
+                      float2* sAdj0, float4* part) {
   typedef Cost<FAST> CF;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int v0 = lg0; v0 < lg1; v0 += GMAX) {
-    const int ng = min(GMAX, lg1 - v0);
-    for (int c0 = 0; c0 < io.n_str; c0 += CHUNK) {
-      const int cnt = min(CHUNK, io.n_str - c0);
-      const int SL = (((cnt + SK_WARPS - 1) / SK_WARPS) + 3) & ~3;  // per-warp slice, multiple of 4
-      // ---- stage the streamed chunk: (x, y, z, potential); padding is neutral (potential = -inf, adjoint = 0)
-      for (int j = threadIdx.x; j < SL * SK_WARPS; j += SK_THREADS) {
-        float4 r = make_float4(0.f, 0.f, 0.f, -INFINITY);
-        float2 a = make_float2(0.f, -INFINITY);
-        if (MODE == MODE_BWD && FINAL_TERM && !io.own_is_beta) r.w = 0.f;  // here .w carries k*lambda_j (0 * inf = NaN otherwise)
-        if (j < cnt) {
-          r = __ldg(io.str + c0 + j);
-          r.w = io.str_pot ? __ldcg(io.str_pot + c0 + j) : 0.f;
-          if (MODE == MODE_BWD || (MODE == MODE_FINAL && !io.own_is_beta)) {
-            // the streamed potential normalises the primary softmax: apply (pot + lo - c1) as a float32 addend plus a
-            // multiplicative correction 2^res folded into the adjoint, so the normalisation is exact to ~1e-7
-            const double full = (double)r.w + (io.str_lo ? (double)__ldcg(io.str_lo + c0 + j) : 0.0) - (double)io.c1;
-            a.y = (float)full;
-            const float corr = exp2f((float)(full - (double)a.y));
-            if (MODE == MODE_FINAL) {
-              a.x = corr;
-            } else if (FINAL_TERM && !io.own_is_beta) {
-              a.x = io.fin_A * corr;
-              r.w = __ldcg(io.fin_cpc + c0 + j) * io.fin_klam_scale;  // k * lambda_j (the secondary term is off at l = L*)
-            } else {
-              a.x = io.str_adj ? __ldcg(io.str_adj + c0 + j) * io.str_adj_scale * corr : 0.f;
-            }
-          }
+  constexpr bool PACKED = (FAST == FAST_GEO2) && (MODE == MODE_LSE || (MODE == MODE_BWD && !FINAL_TERM));
+  const int n0 = ghi[0] - glo[0];
+  const int ntot = n0 + (nseg > 1 ? ghi[1] - glo[1] : 0);
+  float4* sSb[2] = {sS0, sS0 + CHUNK_PAD};
+  float2* sAdjb[2] = {sAdj0, sAdj0 + CHUNK_PAD};
+  const int n_str = ios[0].n_str;  // every pair of a launch has the same cloud sizes
+  for (int c0v = 0; c0v < ntot; c0v += GMAX) {
+    const int ng = min(GMAX, ntot - c0v);
+    const bool use0 = c0v < n0, use1 = (c0v + ng) > n0;  // which segments this visit touches
+    for (int c0 = 0; c0 < n_str; c0 += CHUNK) {
+      const int cnt = min(CHUNK, n_str - c0);
+      if (PACKED) {
+        // per-warp slice of packed records (two streamed points each), multiple of 4
+        const int SLt = ((((cnt + 1) / 2 + SK_WARPS - 1) / SK_WARPS) + 3) & ~3;
+        const int T = SLt * SK_WARPS;
+        const PackedSmem pv0 = packed_view(sSb[0], sAdjb[0], T), pv1 = packed_view(sSb[1], sAdjb[1], T);
+        if (use0) stage_packed<MODE>(ios[0], c0, cnt, T, pv0);
+        if (use1) stage_packed<MODE>(ios[1], c0, cnt, T, pv1);
+        __syncthreads();
+        PROF_MARK(1);
+        for (int g = 0; g < ng;) {  // two owner groups of the same pair per pass share every streamed record
+          const int seg = (c0v + g) >= n0;
+          const int gown = seg ? glo[1] + c0v + g - n0 : glo[0] + c0v + g;
+          const bool two = (g + 1 < ng) && (((c0v + g + 1) >= n0) == (seg != 0));
+          float4* slot = part + (warp * GMAX + g) * 32 + lane;
+          if (two)
+            compute_packed_geo2<MODE, 2>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, gown * 32 + lane, slot);
+          else
+            compute_packed_geo2<MODE, 1>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, gown * 32 + lane, slot);
+          g += two ? 2 : 1;
         }
-        sS[j] = r;
-        if (MODE != MODE_LSE) sAdj[j] = a;
-      }
+      } else {
+      const int SL = (((cnt + SK_WARPS - 1) / SK_WARPS) + 3) & ~3;  // per-warp slice, multiple of 4
+      if (use0) stage_scalar<MODE, FINAL_TERM>(ios[0], c0, cnt, SL * SK_WARPS, sSb[0], sAdjb[0]);
+      if (use1) stage_scalar<MODE, FINAL_TERM>(ios[1], c0, cnt, SL * SK_WARPS, sSb[1], sAdjb[1]);
       __syncthreads();
+      PROF_MARK(1);
       const int j0 = warp * SL, j1 = j0 + SL;
       for (int g = 0; g < ng; ++g) {
-        const int o = (v0 + g) * 32 + lane;
+        const int seg = (c0v + g) >= n0;
+        const SweepIO& io = ios[seg];
+        const float4* sS = sSb[seg];
+        const float2* sAdj = sAdjb[seg];
+        const int o = (seg ? glo[1] + c0v + g - n0 : glo[0] + c0v + g) * 32 + lane;
         const bool live = o < io.n_own;
         float4 op = live ? __ldg(io.own + o) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4* slot = part + (warp * GMAX + g) * 32 + lane;
@@ -286,77 +623,40 @@ __device__ void sweep(const CostParams& cp, const SweepIO& io, int lg0, int lg1,
           *slot = acc;
         }
       }
+      }
       __syncthreads();
+      PROF_MARK(2);
     }
-    // ---- merge the SK_WARPS partials of every owner in fixed order and finish the half-step for these owners
-    float errv = 0.f;
-    if (threadIdx.x < ng * 32) {
-      const int g = threadIdx.x >> 5;
-      const int o = (v0 + g) * 32 + lane;
-      if (o < io.n_own) {
-        if (MODE == MODE_LSE) {
-          float mx = NEG_BIG;
-#pragma unroll
-          for (int w = 0; w < SK_WARPS; ++w) mx = fmaxf(mx, part[(w * GMAX + g) * 32 + lane].x);
-          float sum = 0.f;
-#pragma unroll
-          for (int w = 0; w < SK_WARPS; ++w) {
-            float4 st = part[(w * GMAX + g) * 32 + lane];
-            sum += st.y * ex2_approx(st.x - mx);
+    finalize_visit<MODE, FINAL_TERM>(cp, ios, glo, n0, c0v, ng, part);
+    PROF_MARK(3);
+  }
+}
+
+// acquire: every segment's pair has finished the previous half-step
+__device__ __forceinline__ void wait_done2(const int* done, const int (&segb)[2], int nseg, int target, int* status) {
+  if (threadIdx.x == 0 && target > 0) {
+    for (int s = 0; s < nseg; ++s) {
+      const int* d = done + segb[s];
+      if (ld_acquire_gpu(d) < target) {
+        long long t0 = clock64();
+        while (ld_acquire_gpu(d) < target) {
+          if (*reinterpret_cast<volatile int*>(status) != 0) break;
+          if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
+            atomicExch(status, 1);
+            break;
           }
-          // new potential = lconst - lse2 in double; keep the float32 rounding residual for the backward
-          const double npd = (double)io.lconst - ((double)mx + log2((double)sum));
-          const float np = (float)npd;
-          if (io.out_pot_lo) io.out_pot_lo[o] = (float)(npd - (double)np);
-          if (io.err_out) errv = fabsf(np - (io.old_pot ? __ldcg(io.old_pot + o) : 0.f));
-          io.out_pot[o] = np;
-        } else if (MODE == MODE_FINAL) {
-          float sum = 0.f;
-#pragma unroll
-          for (int w = 0; w < SK_WARPS; ++w) sum += part[(w * GMAX + g) * 32 + lane].x;
-          if (io.own_is_beta) {
-            const double full = (double)__ldcg(io.own_pot + o) + (double)__ldcg(io.own_lo + o) - (double)io.c2;
-            sum *= exp2f((float)(full - (double)(float)full));
-          }
-          io.out_pc[o] = sum * io.pc_scale;
-        } else {
-          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int w = 0; w < SK_WARPS; ++w) {
-            float4 st = part[(w * GMAX + g) * 32 + lane];
-            sum.x += st.x;
-            sum.y += st.y;
-            sum.z += st.z;
-            sum.w += st.w;
-          }
-          if (io.adj_out) {
-            // regular sweeps: -sum_j adj_j S_ij ; row sweep(L*): abar^L_i = -ln2 * sum_j u_ij (k lambda_j - kC_ij)
-            io.adj_out[o] = (FINAL_TERM && !io.own_is_beta) ? -LN2F * sum.w : -sum.w;
-          }
-          float4 gv = make_float4(sum.x * cp.gscale, sum.y * cp.gscale, sum.z * cp.gscale, 0.f);
-          if (io.G_accumulate) {
-            float4 old = __ldcg(io.G + o);
-            gv.x += old.x;
-            gv.y += old.y;
-            gv.z += old.z;
-          }
-          __stcg(io.G + o, gv);
         }
       }
     }
-    if (MODE == MODE_LSE && io.err_out) {
-      // early-stop statistic sum_i |u_new - u_old| (sinkhorn.py:42): CTA-reduce, one float atomic per visit
-      errv = warp_sum(errv);
-      __shared__ float serr[SK_WARPS];
-      if (lane == 0) serr[warp] = errv;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < SK_WARPS; ++w) t += serr[w];
-        atomicAdd(io.err_out, t);
-      }
-    }
-    __syncthreads();
+  }
+  __syncthreads();
+}
+// release: this CTA's groups of every segment are done
+__device__ __forceinline__ void signal_done2(int* done, const int (&segb)[2], const int (&glo)[2], const int (&ghi)[2], int nseg) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    for (int s = 0; s < nseg; ++s) atomicAdd(done + segb[s], ghi[s] - glo[s]);
   }
 }
 
@@ -365,18 +665,42 @@ __device__ __forceinline__ void cta_range(long long total, int& g0, int& g1) {
   g1 = (int)((total * (blockIdx.x + 1)) / gridDim.x);
 }
 
+// Work split of one half-step: the pairs are divided into two sets (first / second half of the batch) and the flattened
+// (pair, group) list of each set is dealt to the CTAs in the interleaved order A0 B0 A1 B1 ..., so every CTA owns a
+// contiguous run of set A and a contiguous run of set B with |A|+|B| balanced to within one group.  A CTA works through
+// its A run, then its B run, every half-step: by the time it returns to set A the other CTAs have had a whole B run to
+// finish A's previous half-step, so the inter-CTA wait is (almost) never exposed.
+__device__ __forceinline__ void cta_ranges(int B, int gpp, int (&rs)[2], int (&re)[2], int (&poff)[2]) {
+#ifdef SHWD_TWO_SETS
+  const int BA = (B + 1) / 2;
+#else
+  const int BA = B;
+#endif
+  const long long GA = (long long)BA * gpp, GB = (long long)(B - BA) * gpp, G = GA + GB;
+  const long long f0 = (G * blockIdx.x) / gridDim.x, f1 = (G * (blockIdx.x + 1)) / gridDim.x;
+  auto cntA = [&](long long f) { return f < 2 * GB ? (f + 1) / 2 : f - GB; };
+  auto cntB = [&](long long f) { return f < 2 * GB ? f / 2 : GB; };
+  rs[0] = (int)cntA(f0);
+  re[0] = (int)cntA(f1);
+  rs[1] = (int)cntB(f0);
+  re[1] = (int)cntB(f1);
+  poff[0] = 0;
+  poff[1] = BA;
+}
+
 // ================================================================================================================
 // Forward: 2L half-steps, then [early stop: pick L*], then the two final sweeps (row/col sums of P*C) and the cost.
 // ================================================================================================================
 template <int FAST>
-__global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkParams prm) {
+__global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kernel(const SinkParams prm) {
   extern __shared__ float4 smem4[];
-  float4* sS = smem4;
-  float4* part = smem4 + CHUNK_PAD;
-  float2* sAdj = reinterpret_cast<float2*>(part + SK_WARPS * GMAX * 32);
+  float4* sS = smem4;                      // 2 x CHUNK_PAD staged records (one set per segment)
+  float4* part = smem4 + 2 * CHUNK_PAD;
+  float2* sAdj = reinterpret_cast<float2*>(part + SK_WARPS * GMAX * 32);  // 2 x CHUNK_PAD
   __shared__ int s_ls;
 
   const int gr = (prm.N + 31) / 32, gc = (prm.M + 31) / 32;  // groups per pair, row / col owners
+  PROF_INIT();
   const int HL = prm.hist_levels;
   const int L = prm.iters;
   auto slot = [&](int l) { return HL > 1 ? l : 0; };
@@ -394,14 +718,22 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkP
     const int type = h & 1;            // 0: alpha (row owners), 1: beta (col owners)
     const int l = (h >> 1) + 1;        // level being produced
     const int gpp = type ? gc : gr;
-    int g0, g1;
-    cta_range((long long)prm.B * gpp, g0, g1);
+    int rs[2], re[2], poff[2];
+    cta_ranges(prm.B, gpp, rs, re, poff);
     const int target_unit_r = ((h + 1) >> 1), target_unit_c = (h >> 1);  // #row / #col half-steps before h
-    for (int g = g0; g < g1;) {
-      const int b = g / gpp, lg0 = g % gpp;
-      const int lg1 = min(gpp, lg0 + (g1 - g));
-      wait_done(prm.done + b, target_unit_r * gr + target_unit_c * gc, prm.status);
-      SweepIO io;
+    for (int part_i = 0; part_i < 2; ++part_i)
+    for (int g = rs[part_i]; g < re[part_i];) {
+      // gather up to two segments (a CTA whose share straddles a pair boundary) into one item
+      SweepIO ios[2];
+      int segb[2] = {0, 0}, seg0[2] = {0, 0}, seg1[2] = {0, 0}, nseg = 0;
+      while (nseg < 2 && g < re[part_i]) {
+      const int b = poff[part_i] + g / gpp, lg0 = g % gpp;
+      const int lg1 = min(gpp, lg0 + (re[part_i] - g));
+      segb[nseg] = b;
+      seg0[nseg] = lg0;
+      seg1[nseg] = lg1;
+      g += lg1 - lg0;
+      SweepIO& io = ios[nseg];
       io.lconst = type ? prm.lb2 : prm.la2;
       io.err_out = nullptr;
       io.old_pot = nullptr;
@@ -426,9 +758,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkP
         io.out_pot = prm.beta + ((size_t)b * HL + slot(l)) * prm.M;
         io.out_pot_lo = prm.beta_lo + ((size_t)b * HL + slot(l)) * prm.M;
       }
-      sweep<FAST, MODE_LSE, false>(prm.cp, io, lg0, lg1, sS, sAdj, part);
-      signal_done(prm.done + b, lg1 - lg0);
-      g += lg1 - lg0;
+      ++nseg;
+      }
+      wait_done2(prm.done, segb, nseg, target_unit_r * gr + target_unit_c * gc, prm.status);
+      PROF_MARK(0);
+      sweep<FAST, MODE_LSE, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part);
+      signal_done2(prm.done, segb, seg0, seg1, nseg);
+      PROF_MARK(4);
     }
   }
 
@@ -457,13 +793,21 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkP
   // ---- final sweeps: r_i = sum_j P_ij C_ij (row owners), c_j = sum_i P_ij C_ij (col owners)
   for (int type = 0; type < 2; ++type) {
     const int gpp = type ? gc : gr;
-    int g0, g1;
-    cta_range((long long)prm.B * gpp, g0, g1);
-    for (int g = g0; g < g1;) {
-      const int b = g / gpp, lg0 = g % gpp;
-      const int lg1 = min(gpp, lg0 + (g1 - g));
-      wait_done(prm.done + b, L * (gr + gc), prm.status);
-      SweepIO io;
+    int rs[2], re[2], poff[2];
+    cta_ranges(prm.B, gpp, rs, re, poff);
+    for (int part_i = 0; part_i < 2; ++part_i)
+    for (int g = rs[part_i]; g < re[part_i];) {
+      // gather up to two segments (a CTA whose share straddles a pair boundary) into one item
+      SweepIO ios[2];
+      int segb[2] = {0, 0}, seg0[2] = {0, 0}, seg1[2] = {0, 0}, nseg = 0;
+      while (nseg < 2 && g < re[part_i]) {
+      const int b = poff[part_i] + g / gpp, lg0 = g % gpp;
+      const int lg1 = min(gpp, lg0 + (re[part_i] - g));
+      segb[nseg] = b;
+      seg0[nseg] = lg0;
+      seg1[nseg] = lg1;
+      g += lg1 - lg0;
+      SweepIO& io = ios[nseg];
       io.pc_scale = prm.bval * prm.inv_k;
       const float* al = prm.alpha + ((size_t)b * HL + slot(Ls)) * prm.N;
       const float* be = prm.beta + ((size_t)b * HL + slot(Ls)) * prm.M;
@@ -492,9 +836,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkP
         io.own_is_beta = 1;
         io.out_pc = prm.col_pc + (size_t)b * prm.M;
       }
-      sweep<FAST, MODE_FINAL, false>(prm.cp, io, lg0, lg1, sS, sAdj, part);
-      signal_done(prm.done + b, lg1 - lg0);
-      g += lg1 - lg0;
+      ++nseg;
+      }
+      wait_done2(prm.done, segb, nseg, L * (gr + gc), prm.status);
+      PROF_MARK(0);
+      sweep<FAST, MODE_FINAL, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part);
+      signal_done2(prm.done, segb, seg0, seg1, nseg);
+      PROF_MARK(4);
     }
   }
 
@@ -525,15 +873,16 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_kernel(const SinkP
 // Backward: 2L*+1 reverse sweeps.  phase ph < 2L*: l = L* - ph/2, type = ph & 1;  phase 2L*: row sweep(0).
 // ================================================================================================================
 template <int FAST>
-__global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_kernel(const SinkParams prm) {
+__global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kernel(const SinkParams prm) {
   extern __shared__ float4 smem4[];
-  float4* sS = smem4;
-  float4* part = smem4 + CHUNK_PAD;
-  float2* sAdj = reinterpret_cast<float2*>(part + SK_WARPS * GMAX * 32);
+  float4* sS = smem4;                      // 2 x CHUNK_PAD staged records (one set per segment)
+  float4* part = smem4 + 2 * CHUNK_PAD;
+  float2* sAdj = reinterpret_cast<float2*>(part + SK_WARPS * GMAX * 32);  // 2 x CHUNK_PAD
 
   const int gr = (prm.N + 31) / 32, gc = (prm.M + 31) / 32;
   const int HL = prm.hist_levels;
   const int Ls = *prm.iters_run;
+  PROF_INIT();
   const size_t BN = (size_t)prm.B * prm.N, BM = (size_t)prm.B * prm.M;
 
   for (int ph = 0; ph <= 2 * Ls; ++ph) {
@@ -542,18 +891,26 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_kernel(const SinkP
     const int l = last ? 0 : Ls - (ph >> 1);
     const int gpp = type ? gc : gr;
     const int nrow_before = last ? Ls : ((ph + 1) >> 1), ncol_before = last ? Ls : (ph >> 1);
-    int g0, g1;
-    cta_range((long long)prm.B * gpp, g0, g1);
-    for (int g = g0; g < g1;) {
-      const int b = g / gpp, lg0 = g % gpp;
-      const int lg1 = min(gpp, lg0 + (g1 - g));
-      wait_done(prm.done + b, nrow_before * gr + ncol_before * gc, prm.status);
+    int rs[2], re[2], poff[2];
+    cta_ranges(prm.B, gpp, rs, re, poff);
+    for (int part_i = 0; part_i < 2; ++part_i)
+    for (int g = rs[part_i]; g < re[part_i];) {
+      // gather up to two segments (a CTA whose share straddles a pair boundary) into one item
+      SweepIO ios[2];
+      int segb[2] = {0, 0}, seg0[2] = {0, 0}, seg1[2] = {0, 0}, nseg = 0;
+      while (nseg < 2 && g < re[part_i]) {
+      const int b = poff[part_i] + g / gpp, lg0 = g % gpp;
+      const int lg1 = min(gpp, lg0 + (re[part_i] - g));
+      segb[nseg] = b;
+      seg0[nseg] = lg0;
+      seg1[nseg] = lg1;
+      g += lg1 - lg0;
+      SweepIO& io = ios[nseg];
       const float gb = __ldg(prm.grad_cost + b);
       const float* al = prm.alpha + (size_t)b * HL * prm.N;  // level 0
       const float* be = prm.beta + (size_t)b * HL * prm.M;
       const float* al_lo = prm.alpha_lo + (size_t)b * HL * prm.N;
       const float* be_lo = prm.beta_lo + (size_t)b * HL * prm.M;
-      SweepIO io;
       io.fin_A = gb * prm.bval * prm.inv_k;
       io.fin_cpc = prm.col_pc + (size_t)b * prm.M;
       io.fin_klam_scale = 1.f / (prm.bval * prm.inv_k);
@@ -621,12 +978,16 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_kernel(const SinkP
         }
         io.adj_out = prm.bbar + (size_t)((l - 1) & 1) * BM + (size_t)b * prm.M;
       }
+      ++nseg;
+      }
+      wait_done2(prm.done, segb, nseg, nrow_before * gr + ncol_before * gc, prm.status);
+      PROF_MARK(0);
       if (l == Ls)
-        sweep<FAST, MODE_BWD, true>(prm.cp, io, lg0, lg1, sS, sAdj, part);
+        sweep<FAST, MODE_BWD, true>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part);
       else
-        sweep<FAST, MODE_BWD, false>(prm.cp, io, lg0, lg1, sS, sAdj, part);
-      signal_done(prm.done + b, lg1 - lg0);
-      g += lg1 - lg0;
+        sweep<FAST, MODE_BWD, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part);
+      signal_done2(prm.done, segb, seg0, seg1, nseg);
+      PROF_MARK(4);
     }
   }
 }
@@ -723,7 +1084,7 @@ static int launch_persistent(K kernel, const SinkParams& prm, size_t smem, int m
     set_last_cuda_error(e == cudaSuccess ? cudaErrorLaunchOutOfResources : e);
     return SHWD_ERR_CUDA;
   }
-  int grid = sm_count();  // one persistent CTA per SM
+  int grid = sm_count() * (per_sm < SK_CTAS_PER_SM ? per_sm : SK_CTAS_PER_SM);  // persistent CTAs, all co-resident
   if (grid > max_groups) grid = max_groups;
   if (grid < 1) grid = 1;
   void* args[] = {const_cast<SinkParams*>(&prm)};
@@ -792,7 +1153,7 @@ extern "C" int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N,
   prm.done = w.done;
   prm.status = w.status;
   prm.err = w.err;
-  const size_t smem = sizeof(float4) * (CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32) + sizeof(float2) * CHUNK_PAD;
+  const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD;
   const int maxg = B * (((N > M ? N : M) + 31) / 32);
   switch (fast) {
     case FAST_GEO2: return launch_persistent(sinkhorn_fwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
@@ -842,7 +1203,7 @@ extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N,
   prm.err = w.err;
   prm.abar = w.abar;
   prm.bbar = w.bbar;
-  const size_t smem = sizeof(float4) * (CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32) + sizeof(float2) * CHUNK_PAD;
+  const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD;
   const int maxg = B * (((N > M ? N : M) + 31) / 32);
   switch (fast) {
     case FAST_GEO2: return launch_persistent(sinkhorn_bwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
@@ -877,3 +1238,16 @@ extern "C" int shwd_sinkhorn_plan_dense(const float* x4, const float* y4, int B,
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }
+
+#ifdef SHWD_PROFILE
+extern "C" int shwd_prof_read(unsigned long long* out8, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out8, shwd::g_prof, sizeof(unsigned long long) * 8);
+  if (e != cudaSuccess) return SHWD_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[8] = {0};
+    e = cudaMemcpyToSymbol(shwd::g_prof, z, sizeof(z));
+    if (e != cudaSuccess) return SHWD_ERR_CUDA;
+  }
+  return SHWD_OK;
+}
+#endif

@@ -1,0 +1,25 @@
+"""Quick timing of the cfg2 forward / backward kernels (diagnostic)."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import shwd
+dev = torch.device("cuda:0")
+B, N, L = 32, 1024, 100
+torch.manual_seed(1234)
+x = torch.nn.functional.normalize(torch.randn(B, N, 3), dim=-1).to(dev).requires_grad_(True)
+y = torch.nn.functional.normalize(torch.randn(B, N, 3), dim=-1).to(dev).requires_grad_(True)
+fs, bs = [], []
+for it in range(6):
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    res = shwd.entropic_ot(x, y, "geodesic", 2.0, 0.01, L, center=True)
+    e1.record()
+    res.cost.sum().backward()
+    e2.record()
+    torch.cuda.synchronize()
+    if it >= 2:
+        fs.append(e0.elapsed_time(e1)); bs.append(e1.elapsed_time(e2))
+f, b = min(fs), min(bs)
+print("fwd %.2f ms  bwd %.2f ms  -> %.0f pairs/s   status %d" % (f, b, B / ((f + b) * 1e-3), res.status()))
