@@ -30,6 +30,10 @@ sys.path.insert(0, ROOT)
 
 B_PER_GPU, N_PTS, ITERS, EPS, P_COST = 32, 1024, 100, 0.01, 2.0
 FWD_OPS, BWD_OPS = 21.0, 33.0  # algorithmic FP32 lane-ops per element-eval
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the two sweep kernels at this exact workload, from the
+# `ncu --set full` capture summarised in profiles/ (bench.py cannot run under ncu while it is timing)
+NCU_DRAM_BYTES_FWD, NCU_DRAM_BYTES_BWD = 23.83e6, 61.67e6
+NCU_SOURCE = "profiles/r01b_ncu_sinkhorn_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
 METRIC = "SHWD loss fwd+bwd pairs/s (B=32,N=1024)"
 CONFIG = {"workload": "cfg2: synthetic registration pairs B=32/GPU N=M=1024, geodesic cost p=2, eps=0.01, L=100, sphere map "
                       "(centre+normalise) + loss + grads w.r.t. both clouds",
@@ -313,12 +317,18 @@ def main():
         ach_b, ach_f = BWD_OPS * E / (t_bwd * 1e-3), FWD_OPS * E / (t_fwd * 1e-3)
         nominal = 148 * 128 * 1.965e9
         roof = {"bound": "fp32", "kernel": "sinkhorn_bwd_kernel<FAST_GEO2>", "achieved": ach_b / 1e12, "peak": fp32_peak / 1e12,
-                "unit": "Tlane-op/s (FFMA = 1 lane-op)", "frac": ach_b / fp32_peak, "traffic": None,
+                "unit": "Tlane-op/s (FFMA = 1 lane-op)", "frac": ach_b / fp32_peak, "traffic": NCU_DRAM_BYTES_BWD,
+                "traffic_source": NCU_SOURCE,
                 "peak_source": "measured live: shwd_peak_fp32 FFMA chains (nominal 148x128x1.965 GHz = %.2f)" % (nominal / 1e12),
                 "ms_per_launch": t_bwd, "algorithmic_ops_per_launch": BWD_OPS * E}
         extra = {"roofline_fwd": {"bound": "fp32", "kernel": "sinkhorn_fwd_kernel<FAST_GEO2>", "achieved": ach_f / 1e12,
                                   "peak": fp32_peak / 1e12, "unit": "Tlane-op/s (FFMA = 1 lane-op)", "frac": ach_f / fp32_peak,
-                                  "ms_per_launch": t_fwd, "algorithmic_ops_per_launch": FWD_OPS * E},
+                                  "ms_per_launch": t_fwd, "algorithmic_ops_per_launch": FWD_OPS * E,
+                                  "traffic": NCU_DRAM_BYTES_FWD},
+                 "roofline_sfu": {"note": "SURVEY.md 8(d) MUFU figure: 2 (fwd) + 3 (bwd) MUFU per element-eval against the MUFU "
+                                          "issue rate measured live by shwd_peak_mufu; the backward executes 4 (sqrt, rsqrt, 2 ex2)",
+                                  "frac_fwd": 2.0 * E / (t_fwd * 1e-3) / mufu_peak, "frac_bwd": 3.0 * E / (t_bwd * 1e-3) / mufu_peak,
+                                  "frac_bwd_executed": 4.0 * E / (t_bwd * 1e-3) / mufu_peak},
                  "roofline_contract": {"note": "SURVEY.md 8(d): 54 lane-ops x E per pair (fwd+bwd) against the measured FP32 peak",
                                        "frac": (FWD_OPS + BWD_OPS) * E / ((t_fwd + t_bwd) * 1e-3) / fp32_peak,
                                        "frac_of_nominal": (FWD_OPS + BWD_OPS) * E / ((t_fwd + t_bwd) * 1e-3) / nominal},

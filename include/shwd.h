@@ -115,6 +115,15 @@ int shwd_segmented_sort(const float* keys, int segs, int len, float* sorted, int
 size_t shwd_circular_w1_workspace_bytes(int S, int n, int m);
 int shwd_circular_w1(const float* us, const float* vs, int S, int n, int m, float* w, float* gus, float* gvs,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Circular W_p^p, p != 1, by bisection on the rotation (binary_search_circle + dCost + Cost,
+ * max_spherical_sliced_w.py:25-207), all rounds and the final cost in one launch:
+ * us (S,n), vs (S,m) sorted ascending circle coordinates in [0,1] -> w (S) = Cost(theta*), theta (S, nullable) = the
+ * rotation found; gus/gvs (nullable) receive d w / d(sorted values) with theta detached (:207).  tm/tp: initial
+ * bracket (-1, 1 in the reference), tol: stopping width (eps / max(Lm, Lp) = 1e-7).  Workspace: the two uniform CDFs. */
+size_t shwd_circular_wp_workspace_bytes(int S, int n, int m);
+int shwd_circular_wp(const float* us, const float* vs, int S, int n, int m, float p, float tm, float tp, float tol,
+                     float* w, float* gus, float* gvs, float* theta, void* workspace, size_t workspace_bytes,
+                     void* stream);
 /* Euclidean sliced W on sorted projections (Flow_ellipsoid.ipynb:217-219): xs, ys (S,n) sorted -> acc (S) =
  * sum_n |xs-ys|^p ; gxs/gys (nullable) receive d acc / d(sorted values). */
 int shwd_euclid_sw(const float* xs, const float* ys, int S, int n, float p, float* acc, float* gxs, float* gys,

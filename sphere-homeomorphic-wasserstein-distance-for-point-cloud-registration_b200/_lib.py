@@ -37,6 +37,8 @@ SIGNATURES = {
     "shwd_segmented_sort": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "shwd_circular_w1_workspace_bytes": (_sz, [_i, _i, _i]),
     "shwd_circular_w1": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "shwd_circular_wp_workspace_bytes": (_sz, [_i, _i, _i]),
+    "shwd_circular_wp": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "shwd_euclid_sw": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "shwd_unsort": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "shwd_peak_fp32": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), _vp]),

@@ -1,0 +1,332 @@
+// Circular Wasserstein W_p^p, p != 1, on sorted circle coordinates: the Delon-Salomon-Sobolevski bisection on the
+// rotation theta, every round of it and the final cost + gradients in ONE launch, one CTA per slice.
+//
+// Replaces   binary_search_circle   Point_Cloud_Resistration/losses/max_spherical_sliced_w.py:117-207
+//            dCost                  max_spherical_sliced_w.py:25-65
+//            Cost                   max_spherical_sliced_w.py:68-113
+//            roll_by_gather         max_spherical_sliced_w.py:9-22
+// (the reference runs ~26 rounds of torch ops with a host sync per round; each round materialises rolled copies of the
+// value / CDF arrays, two searchsorted results and, for Cost, a sort of the concatenated CDFs).
+//
+// Nothing is materialised here.  With uniform weights the CDFs are the same for every slice
+// (u_cdf = cumsum(1/n), v_cdf = cumsum(1/m), accumulated in double and rounded per element like torch's CPU cumsum),
+// the "shifted + rolled" arrays of the reference are pure index arithmetic on them:
+//     frac = theta - floor(theta);  c_j = v_cdf_j - frac;  neg_j = c_j < 0   (a prefix: v_cdf is increasing)
+//     j0 = #neg (0 if all are negative -- argmin over an all-inf row)        (the roll)
+//     r_cdf[t] = c_{(t+j0)%m} (+1 if negative),  r_val[t] = v_{(t+j0)%m} + floor(theta) (+1 if negative),
+//     r_val[m] = r_val[0] + 1
+// and both searchsorted calls and the sort of cat(u_cdf, r_cdf) reduce to local probes around a closed-form guess,
+// because both CDFs are (nearly) arithmetic progressions.  The merged CDF axis of Cost is walked block-wise:
+//   * pass U: thread k owns the axis entries whose u-index is k (axis values in (u_cdf[k-1], u_cdf[k]]) -- cost and
+//     d cost / d u_sorted[k] with no cross-thread reduction;
+//   * pass V: thread t owns the entries whose v-index is t (axis values in (r_cdf[t-1], r_cdf[t]]) -- d cost / d v.
+// Sums are reduced in a fixed order (bit-reproducible run to run).
+//
+// Reference quirks kept: the arc bookkeeping of Cost (v_0 + 1 appended, index clips at n-1 / m), theta detached in
+// the final Cost (:207), the secant point only where |dCp(tm) - dCm(tp)| > 1e-3 (:196-197), `done` re-evaluated from
+// dCp * dCm <= 0 every round.  One batch-global quirk is NOT reproduced: "re-wrap negatives only if the whole batch
+// has both signs" (:41-42, :82-83) -- here negatives are always re-wrapped; the two differ only if every CDF entry of
+// every slice in the call is negative, which needs frac > v_cdf[m-1] ~ 1 in all slices at once.
+// The rounds of different slices are independent in the reference as well: every unfinished slice halves the same
+// dyadic bracket each round, so all of them reach the stopping width in the same round.
+#include "common.cuh"
+
+namespace shwd {
+
+constexpr int CW_THREADS = 256;
+constexpr int CW_WARPS = CW_THREADS / 32;
+constexpr int CW_MAX_ROUNDS = 96;  // the bracket [-1,1] reaches 1 ulp after ~25 halvings; a safety net, never hit
+
+struct Circle {
+  const float* u;     // sorted u values (n)            -- shared memory
+  const float* v;     // sorted v values (m)
+  const float* ucdf;  // cumsum(1/n) (n)
+  const float* vcdf;  // cumsum(1/m) (m)
+  int n, m;
+  float p;
+};
+
+struct Shift {
+  float fl, flp1, frac, r0;
+  int j0;
+};
+
+template <bool P2>
+__device__ __forceinline__ float powp(float d, float p) {
+  return P2 ? d * d : powf(fabsf(d), p);
+}
+// d/dd |d|^p
+template <bool P2>
+__device__ __forceinline__ float dpowp(float d, float p) {
+  if (P2) return 2.f * d;
+  const float a = fabsf(d);
+  if (a == 0.f) return 0.f;  // autograd: pow'(0) * sign(0) = 0
+  return copysignf(p * powf(a, p - 1.f), d);
+}
+
+__device__ __forceinline__ float r_cdf(const Circle& c, const Shift& s, int t) {
+  int j = t + s.j0;
+  if (j >= c.m) j -= c.m;
+  const float x = __fsub_rn(c.vcdf[j], s.frac);
+  return x < 0.f ? __fadd_rn(x, 1.f) : x;
+}
+__device__ __forceinline__ float r_val_in(const Circle& c, const Shift& s, int t) {
+  int j = t + s.j0;
+  if (j >= c.m) j -= c.m;
+  const float x = __fsub_rn(c.vcdf[j], s.frac);
+  return __fadd_rn(c.v[j], x < 0.f ? s.flp1 : s.fl);
+}
+// t in [0, m]: r_val[m] = r_val[0] + 1
+__device__ __forceinline__ float r_val(const Circle& c, const Shift& s, int t) {
+  return t >= c.m ? __fadd_rn(r_val_in(c, s, 0), 1.f) : r_val_in(c, s, t);
+}
+
+__device__ __forceinline__ Shift make_shift(const Circle& c, float theta) {
+  Shift s;
+  s.fl = floorf(theta);
+  s.flp1 = __fadd_rn(s.fl, 1.f);
+  s.frac = __fsub_rn(theta, s.fl);
+  int lo = 0, hi = c.m;  // first j with v_cdf_j - frac >= 0
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__fsub_rn(c.vcdf[mid], s.frac) < 0.f) lo = mid + 1; else hi = mid;
+  }
+  s.j0 = (lo == c.m) ? 0 : lo;
+  s.r0 = 0.f;
+  s.r0 = r_cdf(c, s, 0);
+  return s;
+}
+
+// #{i : u_cdf[i] < x}  (torch.searchsorted(u_cdf, x), left), in [0, n]
+__device__ __forceinline__ int u_count_lt(const Circle& c, float x) {
+  int i = min(max(__float2int_rd(x * (float)c.n), 0), c.n);
+  while (i < c.n && c.ucdf[i] < x) ++i;
+  while (i > 0 && c.ucdf[i - 1] >= x) --i;
+  return i;
+}
+// #{t : r_cdf[t] < x}, in [0, m]
+__device__ __forceinline__ int r_count_lt(const Circle& c, const Shift& s, float x) {
+  int t = min(max(__float2int_rd((x - s.r0) * (float)c.m) + 1, 0), c.m);
+  while (t < c.m && r_cdf(c, s, t) < x) ++t;
+  while (t > 0 && r_cdf(c, s, t - 1) >= x) --t;
+  return t;
+}
+
+// Fixed-order block sum of two values; result broadcast to every thread.
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* wtot) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = make_float2(a, b);
+  __syncthreads();
+  float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int w = 0; w < CW_WARPS; ++w) {
+    t.x += wtot[w].x;
+    t.y += wtot[w].y;
+  }
+  return t;
+}
+
+// dCost :25-65 -> (dCp, dCm): right / left derivative of the cost in theta
+template <bool P2>
+__device__ float2 dcost(const Circle& c, float theta, float2* wtot) {
+  const Shift s = make_shift(c, theta);
+  const float u_wrap = __fadd_rn(c.u[0], 1.f), ucdf_wrap = __fadd_rn(c.ucdf[0], 1.f);
+  float dcp = 0.f, dcm = 0.f;
+  for (int t = threadIdx.x; t < c.m; t += CW_THREADS) {
+    const float x = r_cdf(c, s, t);
+    const int iu = u_count_lt(c, x);                       // searchsorted(u_cdf, x)
+    const float ui = c.u[min(iu, c.n - 1)];
+    int ium = iu;                                          // searchsorted(cat(u_cdf, u_cdf_0 + 1), x, right=True)
+    while (ium < c.n && c.ucdf[ium] <= x) ++ium;
+    if (ium == c.n && ucdf_wrap <= x) ++ium;
+    const float uim = (ium < c.n) ? c.u[ium] : u_wrap;     // index clipped at n -> u_0 + 1
+    const float v0 = r_val_in(c, s, t), v1 = r_val(c, s, t + 1);
+    dcp += __fsub_rn(powp<P2>(__fsub_rn(ui, v1), c.p), powp<P2>(__fsub_rn(ui, v0), c.p));
+    dcm += __fsub_rn(powp<P2>(__fsub_rn(uim, v1), c.p), powp<P2>(__fsub_rn(uim, v0), c.p));
+  }
+  return block_sum2(dcp, dcm, wtot);
+}
+
+// Cost :68-113, pass U.  Returns the cost (broadcast); gu (nullable, global) receives d cost / d u_sorted.
+template <bool P2>
+__device__ float cost_pass_u(const Circle& c, float theta, float* __restrict__ gu, float2* wtot) {
+  const Shift s = make_shift(c, theta);
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < c.n; k += CW_THREADS) {
+    float prev = (k > 0) ? c.ucdf[k - 1] : 0.f;
+    const float xk = c.ucdf[k];
+    const float U = c.u[k];
+    int t = (k > 0) ? r_count_lt(c, s, prev) : 0;
+    float g = 0.f;
+    // v entries below u_cdf[k]: v-index t, u-index k
+    while (t < c.m) {
+      const float rt = r_cdf(c, s, t);
+      if (rt >= xk) break;
+      const float delta = __fsub_rn(rt, prev), d = __fsub_rn(U, r_val_in(c, s, t));
+      acc = fmaf(delta, powp<P2>(d, c.p), acc);
+      g = fmaf(delta, dpowp<P2>(d, c.p), g);
+      prev = rt;
+      ++t;
+    }
+    {  // the u entry itself: v-index = #{r < u_cdf[k]} = t (clipped at m)
+      const float delta = __fsub_rn(xk, prev), d = __fsub_rn(U, r_val(c, s, t));
+      acc = fmaf(delta, powp<P2>(d, c.p), acc);
+      g = fmaf(delta, dpowp<P2>(d, c.p), g);
+      prev = xk;
+    }
+    if (k == c.n - 1) {  // axis entries above u_cdf[n-1]: u-index clipped to n-1
+      while (t < c.m) {
+        const float rt = r_cdf(c, s, t);
+        const float delta = __fsub_rn(rt, prev), d = __fsub_rn(U, r_val_in(c, s, t));
+        acc = fmaf(delta, powp<P2>(d, c.p), acc);
+        g = fmaf(delta, dpowp<P2>(d, c.p), g);
+        prev = rt;
+        ++t;
+      }
+    }
+    if (gu) gu[k] = g;
+  }
+  return block_sum2(acc, 0.f, wtot).x;
+}
+
+// Cost, pass V: gv (global, indexed by sorted v position) receives d cost / d v_sorted.
+template <bool P2>
+__device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv) {
+  const Shift s = make_shift(c, theta);
+  for (int t = threadIdx.x; t < c.m; t += CW_THREADS) {
+    float prev = (t > 0) ? r_cdf(c, s, t - 1) : 0.f;
+    const float xt = r_cdf(c, s, t);
+    const float V = r_val_in(c, s, t);
+    int i = 0;
+    if (t > 0) {  // first u entry above r_cdf[t-1]
+      i = u_count_lt(c, prev);
+      while (i < c.n && c.ucdf[i] <= prev) ++i;
+    }
+    float g = 0.f;
+    while (i < c.n && c.ucdf[i] < xt) {  // u entries inside (r[t-1], r[t]): v-index t
+      const float a = c.ucdf[i];
+      g = fmaf(__fsub_rn(a, prev), dpowp<P2>(__fsub_rn(c.u[i], V), c.p), g);
+      prev = a;
+      ++i;
+    }
+    // the v entry itself: u-index = #{u_cdf < r[t]} = i (clipped at n-1)
+    g = fmaf(__fsub_rn(xt, prev), dpowp<P2>(__fsub_rn(c.u[min(i, c.n - 1)], V), c.p), g);
+    if (t == 0) {
+      // the wrap-around partner r_val[m] = r_val[0] + 1 serves the u entries above r_cdf[m-1]
+      const float Vw = __fadd_rn(V, 1.f);
+      float pw = r_cdf(c, s, c.m - 1);
+      int iw = u_count_lt(c, pw);
+      while (iw < c.n && c.ucdf[iw] <= pw) ++iw;
+      for (; iw < c.n; ++iw) {
+        const float a = c.ucdf[iw];
+        g = fmaf(__fsub_rn(a, pw), dpowp<P2>(__fsub_rn(c.u[iw], Vw), c.p), g);
+        pw = a;
+      }
+    }
+    int j = t + s.j0;
+    if (j >= c.m) j -= c.m;
+    gv[j] = -g;
+  }
+}
+
+template <bool P2>
+__global__ void __launch_bounds__(CW_THREADS) circular_wp_kernel(const float* __restrict__ us, const float* __restrict__ vs, int n,
+                                                                 int m, float p, float tm0, float tp0, float tol,
+                                                                 const float* __restrict__ cdfs, float* __restrict__ w_out,
+                                                                 float* __restrict__ gus, float* __restrict__ gvs,
+                                                                 float* __restrict__ theta_out) {
+  extern __shared__ float cw_smem[];
+  __shared__ float2 wtot[CW_WARPS];
+  float* su = cw_smem;
+  float* sv = su + n;
+  float* sucdf = sv + m;
+  float* svcdf = sucdf + n;
+  const size_t sl = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += CW_THREADS) {
+    su[i] = __ldg(us + sl * n + i);
+    sucdf[i] = __ldg(cdfs + i);
+  }
+  for (int j = threadIdx.x; j < m; j += CW_THREADS) {
+    sv[j] = __ldg(vs + sl * m + j);
+    svcdf[j] = __ldg(cdfs + n + j);
+  }
+  __syncthreads();
+  Circle c = {su, sv, sucdf, svcdf, n, m, p};
+
+  // binary_search_circle :172-205 (every quantity is uniform over the CTA: the sums are broadcast)
+  float tm = tm0, tp = tp0, tc = (tm0 + tp0) * 0.5f;
+  for (int round = 0; round < CW_MAX_ROUNDS; ++round) {
+    const float2 dc = dcost<P2>(c, tc, wtot);
+    if (dc.x * dc.y <= 0.f) break;  // done: the optimum is the kink at tc
+    if (__fsub_rn(tp, tm) < tol) {
+      const float2 dtp = dcost<P2>(c, tp, wtot);
+      const float2 dtm = dcost<P2>(c, tm, wtot);
+      const float ctm = cost_pass_u<P2>(c, tm, nullptr, wtot);
+      const float ctp = cost_pass_u<P2>(c, tp, nullptr, wtot);
+      const float den = __fsub_rn(dtm.x, dtp.y);  // dCptm - dCmtp
+      if (fabsf(den) > 0.001f)
+        tc = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(ctp, ctm), __fmul_rn(tm, dtm.x)), __fmul_rn(tp, dtp.y)), den);
+      break;
+    }
+    if (dc.x < 0.f) tm = tc; else tp = tc;
+    tc = __fmul_rn(__fadd_rn(tm, tp), 0.5f);
+  }
+  const float w = cost_pass_u<P2>(c, tc, gus ? gus + sl * n : nullptr, wtot);
+  if (gvs) cost_pass_v<P2>(c, tc, gvs + sl * m);
+  if (threadIdx.x == 0) {
+    w_out[sl] = w;
+    if (theta_out) theta_out[sl] = tc;
+  }
+}
+
+// cumsum(full(1/len)) the way torch's CPU kernel forms it: double accumulator, every prefix rounded to float32.
+__global__ void uniform_cdf_kernel(float* __restrict__ cdfs, int n, int m) {
+  const int which = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) != 0 || which > 1) return;
+  const int len = which ? m : n;
+  float* out = which ? cdfs + n : cdfs;
+  const double w = (double)(float)(1.0 / (double)len);  // torch.full((len,), 1/len, dtype=float32)
+  double s = 0.0;
+  for (int i = 0; i < len; ++i) {
+    s += w;
+    out[i] = (float)s;
+  }
+}
+
+}  // namespace shwd
+
+using namespace shwd;
+
+extern "C" size_t shwd_circular_wp_workspace_bytes(int S, int n, int m) {
+  (void)S;
+  if (n <= 0 || m <= 0) return 0;
+  return ((size_t)n + (size_t)m) * sizeof(float);
+}
+
+extern "C" int shwd_circular_wp(const float* us, const float* vs, int S, int n, int m, float p, float tm, float tp, float tol,
+                                float* w, float* gus, float* gvs, float* theta, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  if (!us || !vs || !w || S < 0 || n <= 0 || m <= 0 || !(p > 0.f) || !(tm < tp)) return SHWD_ERR_INVALID_ARGUMENT;
+  if (S == 0) return SHWD_OK;
+  const size_t need = shwd_circular_wp_workspace_bytes(S, n, m);
+  if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 3)) return SHWD_ERR_WORKSPACE;
+  const size_t smem = 2 * ((size_t)n + m) * sizeof(float);
+  if (smem > 220 * 1024) return SHWD_ERR_UNSUPPORTED;  // n + m <= 28160 per slice
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* cdfs = static_cast<float*>(workspace);
+  uniform_cdf_kernel<<<1, 64, 0, s>>>(cdfs, n, m);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  if (p == 2.f) {
+    if (smem > 48 * 1024)
+      SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    circular_wp_kernel<true><<<S, CW_THREADS, smem, s>>>(us, vs, n, m, p, tm, tp, tol, cdfs, w, gus, gvs, theta);
+  } else {
+    if (smem > 48 * 1024)
+      SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    circular_wp_kernel<false><<<S, CW_THREADS, smem, s>>>(us, vs, n, m, p, tm, tp, tol, cdfs, w, gus, gvs, theta);
+  }
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}

@@ -23,13 +23,25 @@ def emd1D_circle(u_values, v_values, u_weights=None, v_weights=None, p=1, requir
     return ops.CircularW1Fn.apply(u_values.contiguous(), v_values.contiguous())
 
 
+def binary_search_circle(u_values, v_values, u_weights=None, v_weights=None, p=1, Lm=10, Lp=10, tm=-1, tp=1, eps=1e-6,
+                         require_sort=True):
+    """Circular W_p^p per row by bisection on the rotation: (S,n),(S,m) -> (S,)  (max_spherical_sliced_w.py:117-207).
+    Uniform weights.  Every round of the reference's host-synchronised loop runs inside one kernel launch."""
+    if u_weights is not None or v_weights is not None:
+        raise NotImplementedError("non-uniform weights are not used on the reference's path")
+    if require_sort:
+        u_values, _ = ops.SegmentedSortFn.apply(u_values.contiguous().float())
+        v_values, _ = ops.SegmentedSortFn.apply(v_values.contiguous().float())
+    w, _ = ops.CircularWpFn.apply(u_values.contiguous(), v_values.contiguous(), float(p), float(tm), float(tp),
+                                  eps / max(Lm, Lp))
+    return w
+
+
 def sliced_cost(Xs, Xt, Us, p=2, u_weights=None, v_weights=None):
     """(n,3),(m,3) clouds and (P,3,2) frames -> mean over slices of the circular W (max_spherical_sliced_w.py:251-286)."""
     if u_weights is not None or v_weights is not None:
         raise NotImplementedError("non-uniform weights are not used on the reference's path")
-    if p != 1:
-        raise NotImplementedError("p != 1 (circular bisection, max_spherical_sliced_w.py:117-207) is not on the B200 path yet")
-    w = ops.spherical_sliced_w1(Xs, Xt, Us)
+    w = ops.spherical_sliced_w1(Xs, Xt, Us) if p == 1 else ops.spherical_sliced_wp(Xs, Xt, Us, float(p))
     return w.reshape(()) if Xs.dim() == 2 else w
 
 

@@ -379,6 +379,38 @@ class CircularW1Fn(torch.autograd.Function):
         return gus * g, gvs * g
 
 
+class CircularWpFn(torch.autograd.Function):
+    """Sorted circle coordinates us (S,n), vs (S,m) -> W_p^p per slice (S), p != 1: the whole bisection of
+    binary_search_circle (max_spherical_sliced_w.py:117-207) in one launch; gradients flow through the sorted values
+    only (theta is detached in the reference, :207)."""
+
+    @staticmethod
+    def forward(ctx, us, vs, p, tm, tp, tol):
+        us = us.contiguous()
+        vs = vs.contiguous()
+        S, n = us.shape
+        m = vs.shape[1]
+        lib = _lib.lib()
+        w = torch.empty(S, device=us.device, dtype=torch.float32)
+        theta = torch.empty(S, device=us.device, dtype=torch.float32)
+        gus = torch.empty_like(us)
+        gvs = torch.empty_like(vs)
+        wsb = lib.shwd_circular_wp_workspace_bytes(S, n, m)
+        ws = torch.empty(max(wsb, 8), device=us.device, dtype=torch.uint8)
+        with torch.cuda.device(us.device):
+            _lib.check(lib.shwd_circular_wp(_ptr(us), _ptr(vs), S, n, m, float(p), float(tm), float(tp), float(tol), _ptr(w),
+                                            _ptr(gus), _ptr(gvs), _ptr(theta), _ptr(ws), wsb, _stream()), "shwd_circular_wp")
+        ctx.save_for_backward(gus, gvs)
+        ctx.mark_non_differentiable(theta)
+        return w, theta
+
+    @staticmethod
+    def backward(ctx, gw, _gt):
+        gus, gvs = ctx.saved_tensors
+        g = gw.contiguous().unsqueeze(1)
+        return gus * g, gvs * g, None, None, None, None
+
+
 class EuclidSWFn(torch.autograd.Function):
     """Sorted projections xs, ys (S,n) -> sum_n |xs-ys|^p per slice (S)  (Flow_ellipsoid.ipynb:217-219)."""
 
@@ -416,6 +448,21 @@ def spherical_sliced_w1(Xs, Xt, U):
     st, _ = SegmentedSortFn.apply(kt.reshape(B * P, m))
     w = CircularW1Fn.apply(ss, st).reshape(B, P)
     return w.mean(dim=1)  # (B,)
+
+
+def spherical_sliced_wp(Xs, Xt, U, p=2.0, tm=-1.0, tp=1.0, tol=1e-7):
+    """mean_P circular-W_p^p (no root, max_spherical_sliced_w.py:284-286) of the great-circle projections, p != 1."""
+    xs, _ = _as_cloud(Xs, "Xs")
+    xt, _ = _as_cloud(Xt, "Xt")
+    U = U.to(device=xs.device, dtype=torch.float32).contiguous()
+    ks = ProjectCircleFn.apply(xs, U)  # (B,P,n)
+    kt = ProjectCircleFn.apply(xt, U)
+    B, P, n = ks.shape
+    m = kt.shape[2]
+    ss, _ = SegmentedSortFn.apply(ks.reshape(B * P, n))
+    st, _ = SegmentedSortFn.apply(kt.reshape(B * P, m))
+    w, _ = CircularWpFn.apply(ss, st, float(p), tm, tp, tol)
+    return w.reshape(B, P).mean(dim=1)  # (B,)
 
 
 def euclid_sliced_w(x, y, theta, p=2.0):
