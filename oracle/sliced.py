@@ -125,7 +125,7 @@ def _cost(theta, u_values, v_values, u_cdf, v_cdf, p):
     return torch.sum(delta * torch.abs(u_icdf - v_icdf) ** p, dim=-1)
 
 
-def binary_search_circle(u_values, v_values, p=2, Lm=10, Lp=10, tm=-1.0, tp=1.0, eps=1e-6):
+def binary_search_circle(u_values, v_values, p=2, Lm=10, Lp=10, tm=-1.0, tp=1.0, eps=1e-6, return_theta=False):
     """``binary_search_circle`` :117-207 with uniform weights and ``require_sort=True``.  (P,n),(P,m) -> (P,)."""
     n, m = u_values.shape[-1], v_values.shape[-1]
     dt = u_values.dtype
@@ -158,7 +158,8 @@ def binary_search_circle(u_values, v_values, p=2, Lm=10, Lp=10, tm=-1.0, tp=1.0,
             tp[hi] = tc[hi]
             go = ((1 - mask) * (1 - done)) > 0
             tc[go] = (tm[go] + tp[go]) / 2
-    return _cost(tc.detach(), u_values, v_values, u_cdf, v_cdf, p)
+    w = _cost(tc.detach(), u_values, v_values, u_cdf, v_cdf, p)
+    return (w, tc[:, 0].detach()) if return_theta else w
 
 
 def sliced_wasserstein_sphere(Xs, Xt, U, p=2):

@@ -375,6 +375,79 @@ def test_spherical_sliced_w1_matches_oracle(shwd, n, m, P):
     assert out.item() == pytest.approx(ref.item(), rel=2e-5)
 
 
+def _tie_free(S, n, seed, lo=0.0, width=1.0):
+    """Distinct float32 circle coordinates per row (torch.sort without stable=True orders ties arbitrarily): a
+    shuffled jittered grid, so distinctness does not rely on luck at n = 4096."""
+    g = torch.Generator().manual_seed(seed)
+    grid = (torch.arange(n, dtype=torch.float64) + 0.1 + 0.8 * torch.rand(S, n, generator=g, dtype=torch.float64)) / n
+    perm = torch.argsort(torch.rand(S, n, generator=g), dim=1)
+    x = ((torch.gather(grid, 1, perm) * width + lo) % 1.0).float()
+    assert all(torch.unique(r).numel() == n for r in x)
+    return x
+
+
+def test_binary_search_circle_matches_reference_fixture(shwd):
+    d = gold("binary_search_circle_p2")
+    w = shwd.losses.binary_search_circle(torch.from_numpy(d["u"]).to(dev()), torch.from_numpy(d["v"]).to(dev()), p=2)
+    assert rel(w, torch.from_numpy(d["w"])) < TOL
+
+
+def test_spherical_sliced_w2_matches_reference_fixture(shwd):
+    d = gold("ssw_p2")
+    xs = torch.from_numpy(d["Xs"]).to(dev()).requires_grad_(True)
+    xt = torch.from_numpy(d["Xt"]).to(dev()).requires_grad_(True)
+    loss = shwd.losses.sliced_cost(xs, xt, torch.from_numpy(d["U"]).to(dev()), p=2)
+    loss.backward()
+    assert loss.item() == pytest.approx(float(d["loss"]), rel=TOL)
+    assert rel(xs.grad, torch.from_numpy(d["gx"])) < TOL and rel(xt.grad, torch.from_numpy(d["gy"])) < TOL
+
+
+@pytest.mark.parametrize("S,n,m,p", [(9, 70, 55, 2), (5, 64, 64, 2), (6, 500, 333, 2), (4, 1024, 1024, 2), (3, 300, 300, 3),
+                                     (3, 200, 257, 1.5), (2, 4096, 4096, 2), (4, 1, 5, 2), (4, 7, 1, 2), (2, 3000, 9000, 2)])
+def test_circular_wp_matches_oracle(shwd, S, n, m, p):
+    """binary_search_circle (max_spherical_sliced_w.py:117-207): W_p^p, the rotation found, and the gradients w.r.t.
+    the unsorted coordinates.  The bisection's last sign decisions sit at the float32 noise level of a sum of m
+    cancelling terms, so the rotation may differ by the final bracket width (~1e-7); the gradient bound is
+    max(1e-5, 8 x the reference's own float32-vs-float64 distance), like the other non-north-star rows."""
+    u, v = _tie_free(S, n, 100 + n), _tie_free(S, m, 200 + m, lo=0.2, width=0.7)
+    ur, vr = u.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    wr, thr = oracle.sliced.binary_search_circle(ur, vr, p=p, return_theta=True)
+    wr.sum().backward()
+    u64, v64 = u.double().requires_grad_(True), v.double().requires_grad_(True)
+    oracle.sliced.binary_search_circle(u64, v64, p=p).sum().backward()
+    floor = max(rel(ur.grad, u64.grad), rel(vr.grad, v64.grad))
+    ug, vg = u.clone().to(dev()).requires_grad_(True), v.clone().to(dev()).requires_grad_(True)
+    us, _ = shwd.ops.SegmentedSortFn.apply(ug)
+    vs, _ = shwd.ops.SegmentedSortFn.apply(vg)
+    w, th = shwd.ops.CircularWpFn.apply(us, vs, float(p), -1.0, 1.0, 1e-7)
+    w.sum().backward()
+    assert rel(w, wr) < TOL
+    assert (th.cpu() - thr).abs().max().item() < 2e-6
+    bound = max(TOL, 8 * floor)
+    assert rel(ug.grad, ur.grad) < bound and rel(vg.grad, vr.grad) < bound, (rel(ug.grad, ur.grad), rel(vg.grad, vr.grad), floor)
+
+
+def test_circular_wp_full_size_properties(shwd):
+    """BASELINE config 3 (N=4096, 512 slices), p=2: properties that need no CPU reference.  (i) a common rotation of
+    both clouds on the circle leaves W unchanged; (ii) W(u,u) = 0; (iii) W(u,v) = W(v,u); (iv) the input order of the
+    points is irrelevant; (v) the optimal rotation can only improve on theta = 0 (the cut-at-0 line transport)."""
+    S, n = 512, 4096
+    u, v = _tie_free(S, n, 7).to(dev()), _tie_free(S, n, 8, lo=0.3, width=0.5).to(dev())
+    bsc = shwd.losses.binary_search_circle
+    w = bsc(u, v, p=2)
+    assert torch.isfinite(w).all() and (w >= 0).all()
+    shift = torch.rand(S, 1, device=dev())
+    w_rot = bsc((u + shift) % 1.0, (v + shift) % 1.0, p=2)
+    assert rel(w_rot, w) < 1e-4  # the rotated coordinates are re-rounded to float32 (1e-7 on values of ~1e-1 gaps)
+    assert bsc(u, u.clone(), p=2).abs().max().item() < 1e-10
+    assert rel(bsc(v, u, p=2), w) < TOL
+    perm = torch.randperm(n, device=dev())
+    assert torch.equal(bsc(u[:, perm], v, p=2), w)
+    us, vs = torch.sort(u, -1)[0], torch.sort(v, -1)[0]
+    line = ((us - vs) ** 2).mean(-1)
+    assert (w <= line * (1 + 1e-5) + 1e-9).all()
+
+
 def test_project_circle_keys(shwd):
     g = torch.Generator().manual_seed(9)
     X = torch.randn(2, 300, 3, generator=g)
