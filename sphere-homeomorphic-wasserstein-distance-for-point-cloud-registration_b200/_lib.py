@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libshwd_b200.so")
+# SHWD_B200_LIB: diagnostics only (A/B timing of differently built libraries); the product always loads the in-tree build
+LIB_PATH = os.environ.get("SHWD_B200_LIB") or os.path.join(_HERE, "libshwd_b200.so")
 
 COST_GEODESIC, COST_SQEUCLID, COST_EUCLID, COST_ONE_MINUS_COS = 0, 1, 2, 3
 COST_KINDS = {"geodesic": COST_GEODESIC, "sqeuclid": COST_SQEUCLID, "euclid": COST_EUCLID,

@@ -43,12 +43,22 @@ namespace shwd {
 #ifndef SHWD_UNROLL
 #define SHWD_UNROLL 1
 #endif
+#ifndef SHWD_OFF_UNROLL
+#define SHWD_OFF_UNROLL 2
+#endif
+#ifndef SHWD_OFFSET_LSE
+#define SHWD_OFFSET_LSE 1
+#endif
 constexpr int SK_UNROLL = SHWD_UNROLL;
+constexpr int OFF_UNROLL = SHWD_OFF_UNROLL;
 constexpr int SK_THREADS = SHWD_THREADS;  // 256: two CTAs per SM (one CTA's inter-CTA wait / staging overlaps the other's compute)
 constexpr int SK_WARPS = SK_THREADS / 32;
 constexpr int SK_CTAS_PER_SM = 512 / SK_THREADS;
 constexpr int GMAX = 8;          // owner groups (of 32) per visit
-constexpr int CHUNK = 2048;      // streamed points staged per pass
+#ifndef SHWD_CHUNK
+#define SHWD_CHUNK 2048
+#endif
+constexpr int CHUNK = SHWD_CHUNK;  // streamed points staged per pass
 constexpr int CHUNK_PAD = CHUNK + 4 * SK_WARPS;
 constexpr long long WAIT_TIMEOUT_CYCLES = 6000000000LL;  // ~3 s: a lost signal ends the launch instead of hanging the GPU
 constexpr float LN2F = 0.6931471805599453f;
@@ -105,6 +115,7 @@ struct SinkParams {
   int* done;    // (B)
   int* status;  // (1)
   float* err;   // (iters, B)
+  int* dmax;    // (2*iters, B) float bits: max_i |pot_new - pot_old| of every forward half-step (see compute_packed_geo2)
 };
 
 // Per-(pair, half-step) description of one sweep.
@@ -120,6 +131,8 @@ struct SweepIO {
   float* out_pot_lo;     // nullptr -> residual not kept
   const float* old_pot;  // for the early-stop statistic (nullptr -> 0)
   float* err_out;        // nullptr -> not recorded
+  int* dmax_out;         // nullptr -> not recorded: atomicMax of |new - old| (float bits; values are >= 0)
+  int use_off;           // LSE with a fixed per-owner offset instead of a running max (packed path, see below)
   // MODE_FINAL: the plan is evaluated in its column-normalised form P_ij = b * S^v,L_ij,
   //   S^v,L_ij = 2^(fl(M(alpha^L_i) + fl(beta^L_j + lo_j - lb2))) * 2^res_j,
   // i.e. with exactly the roundings of the last beta half-step, so P and the softmax factor it cancels against in the
@@ -179,7 +192,7 @@ __device__ __forceinline__ void signal_done(int* done_b, int n) {
 // ---- finish a visit: merge the SK_WARPS partials of every owner in fixed order, write the half-step's outputs.
 template <int MODE, bool FINAL_TERM>
 __device__ __forceinline__ void finalize_visit(const CostParams& cp, const SweepIO (&ios)[2], const int (&glo)[2], int n0, int c0v, int ng,
-                                               const float4* part) {
+                                               const float4* part, const float4* sOwn, const float4* sOwn2) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // this thread's group (visit-local index = its warp index) and the segment it belongs to
   const int cidx = c0v + (threadIdx.x >> 5);
@@ -208,7 +221,8 @@ __device__ __forceinline__ void finalize_visit(const CostParams& cp, const Sweep
           const double npd = (double)io.lconst - ((double)mx + log2((double)sum));
           const float np = (float)npd;
           if (io.out_pot_lo) io.out_pot_lo[o] = (float)(npd - (double)np);
-          if (io.err_out) errv = fabsf(np - (io.old_pot ? __ldcg(io.old_pot + o) : 0.f));
+          if (io.err_out || io.dmax_out)
+            errv = fabsf(np - (sOwn ? sOwn[threadIdx.x].w : (io.old_pot ? __ldcg(io.old_pot + o) : 0.f)));
           io.out_pot[o] = np;
         } else if (MODE == MODE_FINAL) {
           float sum = 0.f;
@@ -235,7 +249,7 @@ __device__ __forceinline__ void finalize_visit(const CostParams& cp, const Sweep
           }
           float4 gv = make_float4(sum.x * cp.gscale, sum.y * cp.gscale, sum.z * cp.gscale, 0.f);
           if (io.G_accumulate) {
-            float4 old = __ldcg(io.G + o);
+            const float4 old = sOwn2 ? sOwn2[threadIdx.x] : __ldcg(io.G + o);
             gv.x += old.x;
             gv.y += old.y;
             gv.z += old.z;
@@ -244,10 +258,15 @@ __device__ __forceinline__ void finalize_visit(const CostParams& cp, const Sweep
         }
       }
     }
-    if (MODE == MODE_LSE && ios[0].err_out) {
-      // early-stop statistic sum_i |u_new - u_old| (sinkhorn.py:42): one float atomic per warp (= per owner group)
+    if (MODE == MODE_LSE && (ios[0].err_out || ios[0].dmax_out)) {
+      // sup-norm change of this half-step (licenses the next half-step's fixed-offset LSE) and the early-stop
+      // statistic sum_i |u_new - u_old| (sinkhorn.py:42): one atomic each per warp (= per owner group)
+      const float dm = warp_max(errv);
       errv = warp_sum(errv);
-      if (lane == 0 && threadIdx.x < ng * 32) atomicAdd(io.err_out, errv);
+      if (lane == 0 && threadIdx.x < ng * 32) {
+        if (io.dmax_out) atomicMax(io.dmax_out, __float_as_int(dm == dm ? dm : INFINITY));
+        if (io.err_out) atomicAdd(io.err_out, errv);
+      }
     }
   __syncthreads();
 }
@@ -299,8 +318,12 @@ __device__ __forceinline__ PackedSmem packed_view(float4* sS, float2* sAdj, int 
   v.S = sAdj + T;
   return v;
 }
+// Staging is split around the inter-CTA wait.  PRE (before the wait): everything that does not depend on the previous
+// half-step -- the streamed coordinates, and for the backward the streamed potential (forward history), its float32 addend
+// and the 2^res correction.  POST (after the wait): the forward's streamed potential / the backward's streamed adjoint.
+// The same thread handles the same records in both parts, so no barrier is needed between them.
 template <int MODE>
-__device__ __forceinline__ void stage_packed(const SweepIO& io, int c0, int cnt, int T, const PackedSmem& v) {
+__device__ __forceinline__ void stage_packed_pre(const SweepIO& io, int c0, int cnt, int T, const PackedSmem& v) {
   float* X = reinterpret_cast<float*>(v.X);
   float* Y = reinterpret_cast<float*>(v.Y);
   float* Z = reinterpret_cast<float*>(v.Z);
@@ -313,24 +336,77 @@ __device__ __forceinline__ void stage_packed(const SweepIO& io, int c0, int cnt,
     float4 r = make_float4(0.f, 0.f, 0.f, -INFINITY);
     float2 a = make_float2(0.f, -INFINITY);
     if (j < cnt) {
-      r = __ldg(io.str + c0 + j);
-      r.w = io.str_pot ? __ldcg(io.str_pot + c0 + j) : 0.f;
+      const float4 c = __ldg(io.str + c0 + j);
+      r.x = c.x;
+      r.y = c.y;
+      r.z = c.z;
       if (MODE == MODE_BWD) {
+        r.w = io.str_pot ? __ldcg(io.str_pot + c0 + j) : 0.f;
         const double full = (double)r.w + (io.str_lo ? (double)__ldcg(io.str_lo + c0 + j) : 0.0) - (double)io.c1;
         a.y = (float)full;
-        const float corr = exp2f((float)(full - (double)a.y));
-        a.x = io.str_adj ? __ldcg(io.str_adj + c0 + j) * io.str_adj_scale * corr : 0.f;
+        a.x = exp2f((float)(full - (double)a.y));  // corr; multiplied by the adjoint in stage_packed_post
       }
     }
     const int o = 2 * t + half;
     X[o] = r.x;
     Y[o] = r.y;
     Z[o] = r.z;
-    P[o] = r.w;
     if (MODE == MODE_BWD) {
+      P[o] = r.w;
       A[o] = a.x;
       S[o] = a.y;
     }
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void stage_packed_post(const SweepIO& io, int c0, int cnt, int T, const PackedSmem& v) {
+  float* P = reinterpret_cast<float*>(v.P);
+  float* A = reinterpret_cast<float*>(v.A);
+  for (int q = threadIdx.x; q < 2 * T; q += SK_THREADS) {
+    const int half = q >= T, t = half ? q - T : q;
+    const int j = q;
+    const int o = 2 * t + half;
+    if (MODE == MODE_LSE) {
+      P[o] = (j < cnt) ? (io.str_pot ? __ldcg(io.str_pot + c0 + j) : 0.f) : -INFINITY;
+    } else {
+      A[o] = (j < cnt && io.str_adj) ? __ldcg(io.str_adj + c0 + j) * io.str_adj_scale * A[o] : 0.f;
+    }
+  }
+}
+
+// Owner records of a visit, staged once per CTA (PRE: none of it depends on the previous half-step): sOwn[g*32+lane] =
+// (x, y, z, old potential of the same kind [LSE]); the backward also stages sOwn2 = the owner's accumulated gradient
+// (read-modify-written by this very thread two half-steps ago) and sOwn3 = (own_pot1, o2, oadj).
+template <int MODE>
+__device__ __forceinline__ void stage_owners(const SweepIO (&ios)[2], const int (&glo)[2], int n0, int c0v, int ng, float4* sOwn,
+                                             float4* sOwn2, float4* sOwn3) {
+  if (threadIdx.x < ng * 32) {
+    const int lane = threadIdx.x & 31;
+    const int cidx = c0v + (threadIdx.x >> 5);
+    const int seg = cidx >= n0;
+    const SweepIO& io = ios[seg];
+    const int o = (seg ? glo[1] + cidx - n0 : glo[0] + cidx) * 32 + lane;
+    const bool live = o < io.n_own;
+    float4 rec = live ? __ldg(io.own + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rec.w = 0.f;
+    if (MODE == MODE_LSE) {
+      if (live && io.old_pot) rec.w = __ldcg(io.old_pot + o);
+    } else if (MODE == MODE_BWD) {
+      float4 e = make_float4(-INFINITY, -INFINITY, 0.f, 0.f);
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        if (io.own_pot1) e.x = __ldcg(io.own_pot1 + o);
+        if (io.own_pot2) {
+          const double full = (double)__ldcg(io.own_pot2 + o) + (io.own_lo2 ? (double)__ldcg(io.own_lo2 + o) : 0.0) - (double)io.c2;
+          e.y = (float)full;
+          e.z = __ldcg(io.own_adj2 + o) * io.own_adj2_scale * exp2f((float)(full - (double)e.y));
+        }
+        if (io.G_accumulate) g = __ldcg(io.G + o);
+      }
+      sOwn2[threadIdx.x] = g;
+      sOwn3[threadIdx.x] = e;
+    }
+    sOwn[threadIdx.x] = rec;
   }
 }
 
@@ -358,17 +434,53 @@ __device__ __forceinline__ f2 dot3_2(float ox, float oy, float oz, f2 X, f2 Y, f
 // (one per group) and shares each streamed record between them, so one LDS.128 per array feeds 4R elements.
 // tb..te (multiple of 4) is the warp's range of packed records.  Results go to the warp's partial slots (slot[r*32]),
 // same format as the scalar path.
-template <int MODE, int R>
+//
+// LSE sweeps come in two flavours.  The safe one keeps a running maximum (online log-sum-exp).  OFF = true replaces it by
+// a fixed per-owner offset: the owner's log-sum-exp of the PREVIOUS iterate, lse_old_i = lconst - pot_old_i.  The map
+// streamed potential -> log-sum-exp is 1-Lipschitz in the sup norm, so |lse_new_i - lse_old_i| <= d, d = the sup-norm change
+// of the streamed potential in its last half-step (recorded by finalize_visit); with d < 64 the sum of 2^(m - lse_old)
+// lies in [2^-64, 2^64] -- no overflow, no loss of the leading terms.  That removes the max / rescale work (0.25 MUFU and
+// ~2 FP32/ALU slots per element) and, more importantly, the dependency of every ex2 on the max of its batch, so the ex2
+// spread out between the FMA work instead of arriving as one burst on the XU pipe.
+template <int MODE, int R, bool OFF = false>
 __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const SweepIO& io, const PackedSmem& v, int tb, int te,
-                                                    bool first_chunk, int o0, float4* slot) {
-  float4 op[R];
-  bool live[R];
+                                                    bool first_chunk, const float4* own, const float4* own3, float4* slot) {
+  float4 op[R];  // staged owner records of this lane (stage_owners); entries of dead owners are zero / -inf
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    live[r] = (o0 + 32 * r) < io.n_own;
-    op[r] = live[r] ? __ldg(io.own + o0 + 32 * r) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  if (MODE == MODE_LSE) {
+  for (int r = 0; r < R; ++r) op[r] = own[32 * r];
+  if (MODE == MODE_LSE && OFF) {
+    float off[R];
+    f2 rs[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      off[r] = __fsub_rn(io.lconst, op[r].w);  // log-sum-exp of the previous iterate
+      rs[r] = first_chunk ? bc2(0.f) : mk2(slot[32 * r].y, 0.f);
+    }
+    // software-pipelined by hand: the ex2 of batch i are issued among the dot / acos FMAs of batch i+1, so every
+    // stretch of the instruction stream feeds the XU and the FMA pipe at their steady ratio
+    f2 mp[R][2];
+#pragma unroll
+    for (int r = 0; r < R; ++r) mp[r][0] = mp[r][1] = bc2(-INFINITY);
+#pragma unroll OFF_UNROLL
+    for (int t = tb; t < te; t += 2) {
+      const float4 X = *reinterpret_cast<const float4*>(v.X + t), Y = *reinterpret_cast<const float4*>(v.Y + t);
+      const float4 Z = *reinterpret_cast<const float4*>(v.Z + t), P = *reinterpret_cast<const float4*>(v.P + t);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const f2 e0 = ex2_2(sub2(mp[r][0], bc2(off[r]))), e1 = ex2_2(sub2(mp[r][1], bc2(off[r])));
+        const f2 th0 = scaled_acos2(cp.q, cp.hpi, dot3_2(op[r].x, op[r].y, op[r].z, mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y)));
+        const f2 th1 = scaled_acos2(cp.q, cp.hpi, dot3_2(op[r].x, op[r].y, op[r].z, mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w)));
+        mp[r][0] = fma2(neg2(th0), th0, mk2(P.x, P.y));  // the canonical exponent Cost::m, as in the safe path
+        mp[r][1] = fma2(neg2(th1), th1, mk2(P.z, P.w));
+        rs[r] = add2(rs[r], add2(e0, e1));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      rs[r] = add2(rs[r], add2(ex2_2(sub2(mp[r][0], bc2(off[r]))), ex2_2(sub2(mp[r][1], bc2(off[r])))));
+#pragma unroll
+    for (int r = 0; r < R; ++r) slot[32 * r] = make_float4(off[r], lo2(rs[r]) + hi2(rs[r]), 0.f, 0.f);
+  } else if (MODE == MODE_LSE) {
     f2 rm[R], rs[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -415,18 +527,10 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const 
     f2 ax[R], ay[R], az[R], aw[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      opot1[r] = -INFINITY;
-      o2[r] = -INFINITY;
-      oadj[r] = 0.f;
-      const int o = o0 + 32 * r;
-      if (live[r]) {
-        if (io.own_pot1) opot1[r] = __ldcg(io.own_pot1 + o);
-        if (io.own_pot2) {
-          const double full = (double)__ldcg(io.own_pot2 + o) + (io.own_lo2 ? (double)__ldcg(io.own_lo2 + o) : 0.0) - (double)io.c2;
-          o2[r] = (float)full;
-          oadj[r] = __ldcg(io.own_adj2 + o) * io.own_adj2_scale * exp2f((float)(full - (double)o2[r]));
-        }
-      }
+      const float4 e = own3[32 * r];
+      opot1[r] = e.x;
+      o2[r] = e.y;
+      oadj[r] = e.z;
       ax[r] = ay[r] = az[r] = aw[r] = bc2(0.f);
     }
 #pragma unroll SK_UNROLL
@@ -474,9 +578,38 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const 
 // share straddles a pair boundary) -- swept together: both pairs' streamed data are staged side by side, all groups are
 // computed in one pass and finalised together, so a straddling CTA pays the fixed per-item cost (staging, barriers,
 // finalise, signal) once instead of twice (every other CTA of both pairs waits for it each half-step).
+
+// acquire: every segment's pair has finished the previous half-step
+__device__ __forceinline__ void wait_done2(const int* done, const int (&segb)[2], int nseg, int target, int* status) {
+  if (threadIdx.x == 0 && target > 0) {
+    for (int s = 0; s < nseg; ++s) {
+      const int* d = done + segb[s];
+      if (ld_acquire_gpu(d) < target) {
+        long long t0 = clock64();
+        while (ld_acquire_gpu(d) < target) {
+          if (*reinterpret_cast<volatile int*>(status) != 0) break;
+          if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
+            atomicExch(status, 1);
+            break;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+struct WaitSpec {
+  const int* done;
+  int segb[2];
+  int target;
+  int* status;
+  const int* dmax_prev;  // fwd: sup-norm change of the streamed potential in its last half-step, per pair (nullptr: n/a)
+};
+
 template <int FAST, int MODE, bool FINAL_TERM>
-__device__ void sweep(const CostParams& cp, const SweepIO (&ios)[2], const int (&glo)[2], const int (&ghi)[2], int nseg, float4* sS0,
-                      float2* sAdj0, float4* part) {
+__device__ void sweep(const CostParams& cp, SweepIO (&ios)[2], const int (&glo)[2], const int (&ghi)[2], int nseg, float4* sS0,
+                      float2* sAdj0, float4* part, float4* sOwn, const WaitSpec& ws) {
   typedef Cost<FAST> CF;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr bool PACKED = (FAST == FAST_GEO2) && (MODE == MODE_LSE || (MODE == MODE_BWD && !FINAL_TERM));
@@ -485,6 +618,14 @@ __device__ void sweep(const CostParams& cp, const SweepIO (&ios)[2], const int (
   float4* sSb[2] = {sS0, sS0 + CHUNK_PAD};
   float2* sAdjb[2] = {sAdj0, sAdj0 + CHUNK_PAD};
   const int n_str = ios[0].n_str;  // every pair of a launch has the same cloud sizes
+  float4* sOwn2 = sOwn + GMAX * 32;
+  float4* sOwn3 = sOwn2 + GMAX * 32;
+  bool waited = false;
+  if (!PACKED) {
+    wait_done2(ws.done, ws.segb, nseg, ws.target, ws.status);
+    PROF_MARK(0);
+    waited = true;
+  }
   for (int c0v = 0; c0v < ntot; c0v += GMAX) {
     const int ng = min(GMAX, ntot - c0v);
     const bool use0 = c0v < n0, use1 = (c0v + ng) > n0;  // which segments this visit touches
@@ -495,8 +636,22 @@ __device__ void sweep(const CostParams& cp, const SweepIO (&ios)[2], const int (
         const int SLt = ((((cnt + 1) / 2 + SK_WARPS - 1) / SK_WARPS) + 3) & ~3;
         const int T = SLt * SK_WARPS;
         const PackedSmem pv0 = packed_view(sSb[0], sAdjb[0], T), pv1 = packed_view(sSb[1], sAdjb[1], T);
-        if (use0) stage_packed<MODE>(ios[0], c0, cnt, T, pv0);
-        if (use1) stage_packed<MODE>(ios[1], c0, cnt, T, pv1);
+        if (use0) stage_packed_pre<MODE>(ios[0], c0, cnt, T, pv0);
+        if (use1) stage_packed_pre<MODE>(ios[1], c0, cnt, T, pv1);
+        if (c0 == 0) stage_owners<MODE>(ios, glo, n0, c0v, ng, sOwn, sOwn2, sOwn3);
+        if (!waited) {
+          PROF_MARK(1);
+          wait_done2(ws.done, ws.segb, nseg, ws.target, ws.status);
+          PROF_MARK(0);
+          waited = true;
+          if (MODE == MODE_LSE && ws.dmax_prev) {
+            // fixed-offset LSE once the streamed potential moved by < 2^6 in its last half-step
+            for (int sgi = 0; sgi < nseg; ++sgi)
+              ios[sgi].use_off = SHWD_OFFSET_LSE && __int_as_float(__ldcg(ws.dmax_prev + ws.segb[sgi])) < 64.f;
+          }
+        }
+        if (use0) stage_packed_post<MODE>(ios[0], c0, cnt, T, pv0);
+        if (use1) stage_packed_post<MODE>(ios[1], c0, cnt, T, pv1);
         __syncthreads();
         PROF_MARK(1);
         for (int g = 0; g < ng;) {  // two owner groups of the same pair per pass share every streamed record
@@ -504,10 +659,15 @@ __device__ void sweep(const CostParams& cp, const SweepIO (&ios)[2], const int (
           const int gown = seg ? glo[1] + c0v + g - n0 : glo[0] + c0v + g;
           const bool two = (g + 1 < ng) && (((c0v + g + 1) >= n0) == (seg != 0));
           float4* slot = part + (warp * GMAX + g) * 32 + lane;
-          if (two)
-            compute_packed_geo2<MODE, 2>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, gown * 32 + lane, slot);
+          if (MODE == MODE_LSE && ios[seg].use_off) {
+            if (two)
+              compute_packed_geo2<MODE, 2, true>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
+            else
+              compute_packed_geo2<MODE, 1, true>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
+          } else if (two)
+            compute_packed_geo2<MODE, 2>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
           else
-            compute_packed_geo2<MODE, 1>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, gown * 32 + lane, slot);
+            compute_packed_geo2<MODE, 1>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
           g += two ? 2 : 1;
         }
       } else {
@@ -627,30 +787,11 @@ __device__ void sweep(const CostParams& cp, const SweepIO (&ios)[2], const int (
       __syncthreads();
       PROF_MARK(2);
     }
-    finalize_visit<MODE, FINAL_TERM>(cp, ios, glo, n0, c0v, ng, part);
+    finalize_visit<MODE, FINAL_TERM>(cp, ios, glo, n0, c0v, ng, part, PACKED ? sOwn : nullptr, PACKED ? sOwn2 : nullptr);
     PROF_MARK(3);
   }
 }
 
-// acquire: every segment's pair has finished the previous half-step
-__device__ __forceinline__ void wait_done2(const int* done, const int (&segb)[2], int nseg, int target, int* status) {
-  if (threadIdx.x == 0 && target > 0) {
-    for (int s = 0; s < nseg; ++s) {
-      const int* d = done + segb[s];
-      if (ld_acquire_gpu(d) < target) {
-        long long t0 = clock64();
-        while (ld_acquire_gpu(d) < target) {
-          if (*reinterpret_cast<volatile int*>(status) != 0) break;
-          if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
-            atomicExch(status, 1);
-            break;
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-}
 // release: this CTA's groups of every segment are done
 __device__ __forceinline__ void signal_done2(int* done, const int (&segb)[2], const int (&glo)[2], const int (&ghi)[2], int nseg) {
   __syncthreads();
@@ -697,6 +838,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
   float4* sS = smem4;                      // 2 x CHUNK_PAD staged records (one set per segment)
   float4* part = smem4 + 2 * CHUNK_PAD;
   float2* sAdj = reinterpret_cast<float2*>(part + SK_WARPS * GMAX * 32);  // 2 x CHUNK_PAD
+  float4* sOwn = reinterpret_cast<float4*>(sAdj + 2 * CHUNK_PAD);          // 3 x GMAX*32 staged owner records
   __shared__ int s_ls;
 
   const int gr = (prm.N + 31) / 32, gc = (prm.M + 31) / 32;  // groups per pair, row / col owners
@@ -737,6 +879,8 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
       io.lconst = type ? prm.lb2 : prm.la2;
       io.err_out = nullptr;
       io.old_pot = nullptr;
+      io.dmax_out = prm.dmax + (size_t)h * prm.B + b;
+      io.use_off = 0;
       if (type == 0) {
         io.own = prm.X + (size_t)b * prm.N;
         io.n_own = prm.N;
@@ -745,24 +889,23 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
         io.str_pot = (l == 1) ? nullptr : prm.beta + ((size_t)b * HL + slot(l - 1)) * prm.M;
         io.out_pot = prm.alpha + ((size_t)b * HL + slot(l)) * prm.N;
         io.out_pot_lo = prm.alpha_lo + ((size_t)b * HL + slot(l)) * prm.N;
-        if (prm.thresh > 0.f) {
-          io.err_out = prm.err + (size_t)(l - 1) * prm.B + b;
-          io.old_pot = (l == 1) ? nullptr : prm.alpha + ((size_t)b * HL + slot(l - 1)) * prm.N;
-        }
+        io.old_pot = (l == 1) ? nullptr : prm.alpha + ((size_t)b * HL + slot(l - 1)) * prm.N;
+        if (prm.thresh > 0.f) io.err_out = prm.err + (size_t)(l - 1) * prm.B + b;
       } else {
         io.own = prm.Y + (size_t)b * prm.M;
         io.n_own = prm.M;
         io.str = prm.X + (size_t)b * prm.N;
         io.n_str = prm.N;
         io.str_pot = prm.alpha + ((size_t)b * HL + slot(l)) * prm.N;
+        io.old_pot = (l == 1) ? nullptr : prm.beta + ((size_t)b * HL + slot(l - 1)) * prm.M;  // beta^0 = 0
         io.out_pot = prm.beta + ((size_t)b * HL + slot(l)) * prm.M;
         io.out_pot_lo = prm.beta_lo + ((size_t)b * HL + slot(l)) * prm.M;
       }
       ++nseg;
       }
-      wait_done2(prm.done, segb, nseg, target_unit_r * gr + target_unit_c * gc, prm.status);
-      PROF_MARK(0);
-      sweep<FAST, MODE_LSE, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part);
+      WaitSpec ws = {prm.done, {segb[0], segb[1]}, target_unit_r * gr + target_unit_c * gc, prm.status,
+                     (h >= 2 && FAST == FAST_GEO2) ? prm.dmax + (size_t)(h - 1) * prm.B : nullptr};
+      sweep<FAST, MODE_LSE, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws);
       signal_done2(prm.done, segb, seg0, seg1, nseg);
       PROF_MARK(4);
     }
@@ -838,9 +981,8 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
       }
       ++nseg;
       }
-      wait_done2(prm.done, segb, nseg, L * (gr + gc), prm.status);
-      PROF_MARK(0);
-      sweep<FAST, MODE_FINAL, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part);
+      WaitSpec ws = {prm.done, {segb[0], segb[1]}, L * (gr + gc), prm.status, nullptr};
+      sweep<FAST, MODE_FINAL, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws);
       signal_done2(prm.done, segb, seg0, seg1, nseg);
       PROF_MARK(4);
     }
@@ -878,6 +1020,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
   float4* sS = smem4;                      // 2 x CHUNK_PAD staged records (one set per segment)
   float4* part = smem4 + 2 * CHUNK_PAD;
   float2* sAdj = reinterpret_cast<float2*>(part + SK_WARPS * GMAX * 32);  // 2 x CHUNK_PAD
+  float4* sOwn = reinterpret_cast<float4*>(sAdj + 2 * CHUNK_PAD);          // 3 x GMAX*32 staged owner records
 
   const int gr = (prm.N + 31) / 32, gc = (prm.M + 31) / 32;
   const int HL = prm.hist_levels;
@@ -980,12 +1123,11 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
       }
       ++nseg;
       }
-      wait_done2(prm.done, segb, nseg, nrow_before * gr + ncol_before * gc, prm.status);
-      PROF_MARK(0);
+      WaitSpec ws = {prm.done, {segb[0], segb[1]}, nrow_before * gr + ncol_before * gc, prm.status, nullptr};
       if (l == Ls)
-        sweep<FAST, MODE_BWD, true>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part);
+        sweep<FAST, MODE_BWD, true>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws);
       else
-        sweep<FAST, MODE_BWD, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part);
+        sweep<FAST, MODE_BWD, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws);
       signal_done2(prm.done, segb, seg0, seg1, nseg);
       PROF_MARK(4);
     }
@@ -1013,6 +1155,7 @@ struct Workspace {
   int* done;
   int* status;
   float* err;
+  int* dmax;
   float* abar;
   float* bbar;
   size_t head_bytes;  // counters + status + err (memset on every launch)
@@ -1029,6 +1172,8 @@ static Workspace carve(void* base, int B, int N, int M, int iters) {
   off = align_up(off + sizeof(int) * (size_t)B, 256);
   w.err = reinterpret_cast<float*>(p + off);
   off = align_up(off + sizeof(float) * (size_t)B * (size_t)iters, 256);
+  w.dmax = reinterpret_cast<int*>(p + off);
+  off = align_up(off + sizeof(int) * 2 * (size_t)B * (size_t)iters, 256);
   w.head_bytes = off;
   w.abar = reinterpret_cast<float*>(p + off);
   off = align_up(off + sizeof(float) * 2 * (size_t)B * N, 256);
@@ -1153,7 +1298,8 @@ extern "C" int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N,
   prm.done = w.done;
   prm.status = w.status;
   prm.err = w.err;
-  const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD;
+  prm.dmax = w.dmax;
+  const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32 + 3 * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD;
   const int maxg = B * (((N > M ? N : M) + 31) / 32);
   switch (fast) {
     case FAST_GEO2: return launch_persistent(sinkhorn_fwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
@@ -1203,7 +1349,7 @@ extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N,
   prm.err = w.err;
   prm.abar = w.abar;
   prm.bbar = w.bbar;
-  const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD;
+  const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32 + 3 * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD;
   const int maxg = B * (((N > M ? N : M) + 31) / 32);
   switch (fast) {
     case FAST_GEO2: return launch_persistent(sinkhorn_bwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
