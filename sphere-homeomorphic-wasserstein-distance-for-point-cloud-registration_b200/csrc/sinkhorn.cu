@@ -46,6 +46,9 @@ namespace shwd {
 #ifndef SHWD_OFF_UNROLL
 #define SHWD_OFF_UNROLL 2
 #endif
+#ifndef SHWD_RESIDENT
+#define SHWD_RESIDENT 1
+#endif
 #ifndef SHWD_OFFSET_LSE
 #define SHWD_OFFSET_LSE 1
 #endif
@@ -115,7 +118,6 @@ struct SinkParams {
   int* done;    // (B)
   int* status;  // (1)
   float* err;   // (iters, B)
-  int* dmax;    // (2*iters, B) float bits: max_i |pot_new - pot_old| of every forward half-step (see compute_packed_geo2)
 };
 
 // Per-(pair, half-step) description of one sweep.
@@ -131,8 +133,6 @@ struct SweepIO {
   float* out_pot_lo;     // nullptr -> residual not kept
   const float* old_pot;  // for the early-stop statistic (nullptr -> 0)
   float* err_out;        // nullptr -> not recorded
-  int* dmax_out;         // nullptr -> not recorded: atomicMax of |new - old| (float bits; values are >= 0)
-  int use_off;           // LSE with a fixed per-owner offset instead of a running max (packed path, see below)
   // MODE_FINAL: the plan is evaluated in its column-normalised form P_ij = b * S^v,L_ij,
   //   S^v,L_ij = 2^(fl(M(alpha^L_i) + fl(beta^L_j + lo_j - lb2))) * 2^res_j,
   // i.e. with exactly the roundings of the last beta half-step, so P and the softmax factor it cancels against in the
@@ -190,9 +190,11 @@ __device__ __forceinline__ void signal_done(int* done_b, int n) {
 }
 
 // ---- finish a visit: merge the SK_WARPS partials of every owner in fixed order, write the half-step's outputs.
+// Returns true (CTA-uniform, nothing written) when a fixed-offset LSE visit has to be redone with the running maximum.
 template <int MODE, bool FINAL_TERM>
-__device__ __forceinline__ void finalize_visit(const CostParams& cp, const SweepIO (&ios)[2], const int (&glo)[2], int n0, int c0v, int ng,
-                                               const float4* part, const float4* sOwn, const float4* sOwn2) {
+__device__ __forceinline__ bool finalize_visit(const CostParams& cp, const SweepIO (&ios)[2], const int (&glo)[2], int n0, int c0v, int ng,
+                                               const float4* part, const float4* sOwn, const float4* sOwn2, float* oldp_out,
+                                               bool off_try) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // this thread's group (visit-local index = its warp index) and the segment it belongs to
   const int cidx = c0v + (threadIdx.x >> 5);
@@ -201,29 +203,37 @@ __device__ __forceinline__ void finalize_visit(const CostParams& cp, const Sweep
   const int gown = seg ? glo[1] + cidx - n0 : glo[0] + cidx;
     // ---- merge the SK_WARPS partials of every owner in fixed order and finish the half-step for these owners
     float errv = 0.f;
+    float mx = NEG_BIG, sum = 0.f;
+    if (MODE == MODE_LSE) {
+      bool bad = false;
+      if (threadIdx.x < ng * 32 && gown * 32 + lane < io.n_own) {
+        const int g = threadIdx.x >> 5;
+#pragma unroll
+        for (int w = 0; w < SK_WARPS; ++w) mx = fmaxf(mx, part[(w * GMAX + g) * 32 + lane].x);
+#pragma unroll
+        for (int w = 0; w < SK_WARPS; ++w) {
+          float4 st = part[(w * GMAX + g) * 32 + lane];
+          sum += st.y * ex2_approx(st.x - mx);
+        }
+        bad = !(sum >= 0x1p-60f && sum <= 0x1p60f);
+      }
+      if (off_try && __syncthreads_or(bad)) return true;
+    }
     if (threadIdx.x < ng * 32) {
       const int g = threadIdx.x >> 5;
       const int o = gown * 32 + lane;
       if (o < io.n_own) {
         if (MODE == MODE_LSE) {
-          float mx = NEG_BIG;
-#pragma unroll
-          for (int w = 0; w < SK_WARPS; ++w) mx = fmaxf(mx, part[(w * GMAX + g) * 32 + lane].x);
-          float sum = 0.f;
-#pragma unroll
-          for (int w = 0; w < SK_WARPS; ++w) {
-            float4 st = part[(w * GMAX + g) * 32 + lane];
-            sum += st.y * ex2_approx(st.x - mx);
-          }
           // new potential = lconst - lse2 in double (a correctly rounded, monotone map lets the iteration settle on a
           // bitwise fixed point like the reference does -- the early-stop rule of sinkhorn.py:42-44 needs that);
           // keep the float32 rounding residual for the backward
           const double npd = (double)io.lconst - ((double)mx + log2((double)sum));
           const float np = (float)npd;
           if (io.out_pot_lo) io.out_pot_lo[o] = (float)(npd - (double)np);
-          if (io.err_out || io.dmax_out)
+          if (io.err_out)
             errv = fabsf(np - (sOwn ? sOwn[threadIdx.x].w : (io.old_pot ? __ldcg(io.old_pot + o) : 0.f)));
           io.out_pot[o] = np;
+          if (oldp_out) oldp_out[threadIdx.x] = np;
         } else if (MODE == MODE_FINAL) {
           float sum = 0.f;
 #pragma unroll
@@ -258,17 +268,13 @@ __device__ __forceinline__ void finalize_visit(const CostParams& cp, const Sweep
         }
       }
     }
-    if (MODE == MODE_LSE && (ios[0].err_out || ios[0].dmax_out)) {
-      // sup-norm change of this half-step (licenses the next half-step's fixed-offset LSE) and the early-stop
-      // statistic sum_i |u_new - u_old| (sinkhorn.py:42): one atomic each per warp (= per owner group)
-      const float dm = warp_max(errv);
+    if (MODE == MODE_LSE && ios[0].err_out) {
+      // early-stop statistic sum_i |u_new - u_old| (sinkhorn.py:42): one float atomic per warp (= per owner group)
       errv = warp_sum(errv);
-      if (lane == 0 && threadIdx.x < ng * 32) {
-        if (io.dmax_out) atomicMax(io.dmax_out, __float_as_int(dm == dm ? dm : INFINITY));
-        if (io.err_out) atomicAdd(io.err_out, errv);
-      }
+      if (lane == 0 && threadIdx.x < ng * 32) atomicAdd(io.err_out, errv);
     }
   __syncthreads();
+  return false;
 }
 
 // ---- streamed chunk staging, scalar layout: sS[j] = (x, y, z, potential), sAdj[j] = (adjoint', addend)
@@ -322,8 +328,9 @@ __device__ __forceinline__ PackedSmem packed_view(float4* sS, float2* sAdj, int 
 // half-step -- the streamed coordinates, and for the backward the streamed potential (forward history), its float32 addend
 // and the 2^res correction.  POST (after the wait): the forward's streamed potential / the backward's streamed adjoint.
 // The same thread handles the same records in both parts, so no barrier is needed between them.
-template <int MODE>
+template <int MODE, bool COORDS>
 __device__ __forceinline__ void stage_packed_pre(const SweepIO& io, int c0, int cnt, int T, const PackedSmem& v) {
+  if (!COORDS && MODE != MODE_BWD) return;  // resident coordinates: nothing to do for the forward
   float* X = reinterpret_cast<float*>(v.X);
   float* Y = reinterpret_cast<float*>(v.Y);
   float* Z = reinterpret_cast<float*>(v.Z);
@@ -336,10 +343,12 @@ __device__ __forceinline__ void stage_packed_pre(const SweepIO& io, int c0, int 
     float4 r = make_float4(0.f, 0.f, 0.f, -INFINITY);
     float2 a = make_float2(0.f, -INFINITY);
     if (j < cnt) {
-      const float4 c = __ldg(io.str + c0 + j);
-      r.x = c.x;
-      r.y = c.y;
-      r.z = c.z;
+      if (COORDS) {
+        const float4 c = __ldg(io.str + c0 + j);
+        r.x = c.x;
+        r.y = c.y;
+        r.z = c.z;
+      }
       if (MODE == MODE_BWD) {
         r.w = io.str_pot ? __ldcg(io.str_pot + c0 + j) : 0.f;
         const double full = (double)r.w + (io.str_lo ? (double)__ldcg(io.str_lo + c0 + j) : 0.0) - (double)io.c1;
@@ -348,9 +357,11 @@ __device__ __forceinline__ void stage_packed_pre(const SweepIO& io, int c0, int 
       }
     }
     const int o = 2 * t + half;
-    X[o] = r.x;
-    Y[o] = r.y;
-    Z[o] = r.z;
+    if (COORDS) {
+      X[o] = r.x;
+      Y[o] = r.y;
+      Z[o] = r.z;
+    }
     if (MODE == MODE_BWD) {
       P[o] = r.w;
       A[o] = a.x;
@@ -374,12 +385,28 @@ __device__ __forceinline__ void stage_packed_post(const SweepIO& io, int c0, int
   }
 }
 
+// Resident mode.  A CTA's share of a half-step type (row / column owners) is the same in every half-step, so when that
+// share is one item (<= GMAX owner groups of <= 2 pairs) and the clouds fit, the packed coordinates of the streamed clouds
+// and the owner records are staged ONCE per launch and stay in shared memory; a half-step then only moves potentials
+// (and, in the backward, adjoints): the coordinate staging and its L2 round trip leave the critical path
+// wait -> stage -> sweep -> merge -> signal that every half-step of every pair is serialised on.
+struct ResidentType {
+  int ok;
+  int T;           // packed records per array
+  // offsets, not pointers: the struct lives in local memory, and a pointer loaded from there would be generic (LD
+  // instead of LDS in the sweeps); an offset added to the shared-memory base keeps the address space known
+  int xyz[2];      // per segment, float2 units from the sS base: X at xyz, Y at xyz + T, Z at xyz + 2T
+  int P[2];        // per segment: streamed potential
+  int own;         // GMAX*32-entry slot index (0 / 1) of the owner coordinate records and owner potentials
+};
+
 // Owner records of a visit, staged once per CTA (PRE: none of it depends on the previous half-step): sOwn[g*32+lane] =
 // (x, y, z, old potential of the same kind [LSE]); the backward also stages sOwn2 = the owner's accumulated gradient
 // (read-modify-written by this very thread two half-steps ago) and sOwn3 = (own_pot1, o2, oadj).
 template <int MODE>
 __device__ __forceinline__ void stage_owners(const SweepIO (&ios)[2], const int (&glo)[2], int n0, int c0v, int ng, float4* sOwn,
-                                             float4* sOwn2, float4* sOwn3) {
+                                             float4* sOwn2, float4* sOwn3, const float4* rt_ownc, const float* rt_oldp) {
+  const bool rt = rt_ownc != nullptr;
   if (threadIdx.x < ng * 32) {
     const int lane = threadIdx.x & 31;
     const int cidx = c0v + (threadIdx.x >> 5);
@@ -387,10 +414,13 @@ __device__ __forceinline__ void stage_owners(const SweepIO (&ios)[2], const int 
     const SweepIO& io = ios[seg];
     const int o = (seg ? glo[1] + cidx - n0 : glo[0] + cidx) * 32 + lane;
     const bool live = o < io.n_own;
-    float4 rec = live ? __ldg(io.own + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 rec = rt ? rt_ownc[threadIdx.x] : (live ? __ldg(io.own + o) : make_float4(0.f, 0.f, 0.f, 0.f));
     rec.w = 0.f;
     if (MODE == MODE_LSE) {
-      if (live && io.old_pot) rec.w = __ldcg(io.old_pot + o);
+      if (rt)
+        rec.w = rt_oldp[threadIdx.x];
+      else if (live && io.old_pot)
+        rec.w = __ldcg(io.old_pot + o);
     } else if (MODE == MODE_BWD) {
       float4 e = make_float4(-INFINITY, -INFINITY, 0.f, 0.f);
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -437,11 +467,11 @@ __device__ __forceinline__ f2 dot3_2(float ox, float oy, float oz, f2 X, f2 Y, f
 //
 // LSE sweeps come in two flavours.  The safe one keeps a running maximum (online log-sum-exp).  OFF = true replaces it by
 // a fixed per-owner offset: the owner's log-sum-exp of the PREVIOUS iterate, lse_old_i = lconst - pot_old_i.  The map
-// streamed potential -> log-sum-exp is 1-Lipschitz in the sup norm, so |lse_new_i - lse_old_i| <= d, d = the sup-norm change
-// of the streamed potential in its last half-step (recorded by finalize_visit); with d < 64 the sum of 2^(m - lse_old)
-// lies in [2^-64, 2^64] -- no overflow, no loss of the leading terms.  That removes the max / rescale work (0.25 MUFU and
-// ~2 FP32/ALU slots per element) and, more importantly, the dependency of every ex2 on the max of its batch, so the ex2
-// spread out between the FMA work instead of arriving as one burst on the XU pipe.
+// streamed potential -> log-sum-exp is 1-Lipschitz in the sup norm, so once the iteration has settled a little the sum of
+// 2^(m - lse_old) is close to 1.  The merge checks it: a total inside [2^-60, 2^60] is exact to float32 (terms flushed
+// below 2^-126 cannot matter, an overflow makes it inf); anything else -- only the first few, wildly moving iterations --
+// makes the CTA redo the visit with the running maximum.  The fixed offset removes the max / rescale work (0.25 MUFU
+// and ~2 FP32/ALU slots per element) and the dependency of every ex2 on the max of its batch.
 template <int MODE, int R, bool OFF = false>
 __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const SweepIO& io, const PackedSmem& v, int tb, int te,
                                                     bool first_chunk, const float4* own, const float4* own3, float4* slot) {
@@ -580,10 +610,10 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const 
 // finalise, signal) once instead of twice (every other CTA of both pairs waits for it each half-step).
 
 // acquire: every segment's pair has finished the previous half-step
-__device__ __forceinline__ void wait_done2(const int* done, const int (&segb)[2], int nseg, int target, int* status) {
+__device__ __forceinline__ void wait_done2(const int* done, int b0, int b1, int nseg, int target, int* status) {
   if (threadIdx.x == 0 && target > 0) {
     for (int s = 0; s < nseg; ++s) {
-      const int* d = done + segb[s];
+      const int* d = done + (s ? b1 : b0);
       if (ld_acquire_gpu(d) < target) {
         long long t0 = clock64();
         while (ld_acquire_gpu(d) < target) {
@@ -601,15 +631,15 @@ __device__ __forceinline__ void wait_done2(const int* done, const int (&segb)[2]
 
 struct WaitSpec {
   const int* done;
-  int segb[2];
+  int b0, b1;
   int target;
   int* status;
-  const int* dmax_prev;  // fwd: sup-norm change of the streamed potential in its last half-step, per pair (nullptr: n/a)
+  int try_off;  // forward LSE: attempt the fixed-offset sum (see compute_packed_geo2)
 };
 
 template <int FAST, int MODE, bool FINAL_TERM>
 __device__ void sweep(const CostParams& cp, SweepIO (&ios)[2], const int (&glo)[2], const int (&ghi)[2], int nseg, float4* sS0,
-                      float2* sAdj0, float4* part, float4* sOwn, const WaitSpec& ws) {
+                      float2* sAdj0, float4* part, float4* sOwn, const WaitSpec& ws, const ResidentType* rt) {
   typedef Cost<FAST> CF;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr bool PACKED = (FAST == FAST_GEO2) && (MODE == MODE_LSE || (MODE == MODE_BWD && !FINAL_TERM));
@@ -620,35 +650,49 @@ __device__ void sweep(const CostParams& cp, SweepIO (&ios)[2], const int (&glo)[
   const int n_str = ios[0].n_str;  // every pair of a launch has the same cloud sizes
   float4* sOwn2 = sOwn + GMAX * 32;
   float4* sOwn3 = sOwn2 + GMAX * 32;
+  // resident arrays (see resident_setup for the carve-up)
+  float2* sS2 = reinterpret_cast<float2*>(sS0);
+  const float4* rt_ownc = rt ? sOwn + (3 + rt->own) * GMAX * 32 : nullptr;
+  float* rt_oldp = rt ? reinterpret_cast<float*>(sOwn + 5 * GMAX * 32) + rt->own * GMAX * 32 : nullptr;
   bool waited = false;
   if (!PACKED) {
-    wait_done2(ws.done, ws.segb, nseg, ws.target, ws.status);
+    wait_done2(ws.done, ws.b0, ws.b1, nseg, ws.target, ws.status);
     PROF_MARK(0);
     waited = true;
   }
   for (int c0v = 0; c0v < ntot; c0v += GMAX) {
     const int ng = min(GMAX, ntot - c0v);
     const bool use0 = c0v < n0, use1 = (c0v + ng) > n0;  // which segments this visit touches
+    bool off_try = PACKED && MODE == MODE_LSE && ws.try_off;
+    for (;;) {  // (a fixed-offset LSE visit whose sums left the safe range is redone once with the running maximum)
     for (int c0 = 0; c0 < n_str; c0 += CHUNK) {
       const int cnt = min(CHUNK, n_str - c0);
       if (PACKED) {
         // per-warp slice of packed records (two streamed points each), multiple of 4
         const int SLt = ((((cnt + 1) / 2 + SK_WARPS - 1) / SK_WARPS) + 3) & ~3;
         const int T = SLt * SK_WARPS;
-        const PackedSmem pv0 = packed_view(sSb[0], sAdjb[0], T), pv1 = packed_view(sSb[1], sAdjb[1], T);
-        if (use0) stage_packed_pre<MODE>(ios[0], c0, cnt, T, pv0);
-        if (use1) stage_packed_pre<MODE>(ios[1], c0, cnt, T, pv1);
-        if (c0 == 0) stage_owners<MODE>(ios, glo, n0, c0v, ng, sOwn, sOwn2, sOwn3);
+        PackedSmem pv0 = packed_view(sSb[0], sAdjb[0], T), pv1 = packed_view(sSb[1], sAdjb[1], T);
+        if (rt) {
+          pv0.X = sS2 + rt->xyz[0];
+          pv0.Y = pv0.X + T;
+          pv0.Z = pv0.Y + T;
+          pv0.P = sS2 + rt->P[0];
+          pv1.X = sS2 + rt->xyz[1];
+          pv1.Y = pv1.X + T;
+          pv1.Z = pv1.Y + T;
+          pv1.P = sS2 + rt->P[1];
+          if (use0) stage_packed_pre<MODE, false>(ios[0], c0, cnt, T, pv0);
+          if (use1) stage_packed_pre<MODE, false>(ios[1], c0, cnt, T, pv1);
+        } else {
+          if (use0) stage_packed_pre<MODE, true>(ios[0], c0, cnt, T, pv0);
+          if (use1) stage_packed_pre<MODE, true>(ios[1], c0, cnt, T, pv1);
+        }
+        if (c0 == 0) stage_owners<MODE>(ios, glo, n0, c0v, ng, sOwn, sOwn2, sOwn3, rt_ownc, rt_oldp);
         if (!waited) {
           PROF_MARK(1);
-          wait_done2(ws.done, ws.segb, nseg, ws.target, ws.status);
+          wait_done2(ws.done, ws.b0, ws.b1, nseg, ws.target, ws.status);
           PROF_MARK(0);
           waited = true;
-          if (MODE == MODE_LSE && ws.dmax_prev) {
-            // fixed-offset LSE once the streamed potential moved by < 2^6 in its last half-step
-            for (int sgi = 0; sgi < nseg; ++sgi)
-              ios[sgi].use_off = SHWD_OFFSET_LSE && __int_as_float(__ldcg(ws.dmax_prev + ws.segb[sgi])) < 64.f;
-          }
         }
         if (use0) stage_packed_post<MODE>(ios[0], c0, cnt, T, pv0);
         if (use1) stage_packed_post<MODE>(ios[1], c0, cnt, T, pv1);
@@ -659,7 +703,7 @@ __device__ void sweep(const CostParams& cp, SweepIO (&ios)[2], const int (&glo)[
           const int gown = seg ? glo[1] + c0v + g - n0 : glo[0] + c0v + g;
           const bool two = (g + 1 < ng) && (((c0v + g + 1) >= n0) == (seg != 0));
           float4* slot = part + (warp * GMAX + g) * 32 + lane;
-          if (MODE == MODE_LSE && ios[seg].use_off) {
+          if (MODE == MODE_LSE && off_try) {
             if (two)
               compute_packed_geo2<MODE, 2, true>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
             else
@@ -680,8 +724,8 @@ __device__ void sweep(const CostParams& cp, SweepIO (&ios)[2], const int (&glo)[
       for (int g = 0; g < ng; ++g) {
         const int seg = (c0v + g) >= n0;
         const SweepIO& io = ios[seg];
-        const float4* sS = sSb[seg];
-        const float2* sAdj = sAdjb[seg];
+        const float4* sS = sS0 + seg * CHUNK_PAD;
+        const float2* sAdj = sAdj0 + seg * CHUNK_PAD;
         const int o = (seg ? glo[1] + c0v + g - n0 : glo[0] + c0v + g) * 32 + lane;
         const bool live = o < io.n_own;
         float4 op = live ? __ldg(io.own + o) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -787,8 +831,12 @@ __device__ void sweep(const CostParams& cp, SweepIO (&ios)[2], const int (&glo)[
       __syncthreads();
       PROF_MARK(2);
     }
-    finalize_visit<MODE, FINAL_TERM>(cp, ios, glo, n0, c0v, ng, part, PACKED ? sOwn : nullptr, PACKED ? sOwn2 : nullptr);
+    const bool redo = finalize_visit<MODE, FINAL_TERM>(cp, ios, glo, n0, c0v, ng, part, PACKED ? sOwn : nullptr,
+                                                       PACKED ? sOwn2 : nullptr, (PACKED && MODE == MODE_LSE) ? rt_oldp : nullptr, off_try);
     PROF_MARK(3);
+    if (!redo) break;
+    off_try = false;
+    }
   }
 }
 
@@ -797,7 +845,8 @@ __device__ __forceinline__ void signal_done2(int* done, const int (&segb)[2], co
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    for (int s = 0; s < nseg; ++s) atomicAdd(done + segb[s], ghi[s] - glo[s]);
+    atomicAdd(done + segb[0], ghi[0] - glo[0]);
+    if (nseg > 1) atomicAdd(done + segb[1], ghi[1] - glo[1]);
   }
 }
 
@@ -806,27 +855,94 @@ __device__ __forceinline__ void cta_range(long long total, int& g0, int& g1) {
   g1 = (int)((total * (blockIdx.x + 1)) / gridDim.x);
 }
 
-// Work split of one half-step: the pairs are divided into two sets (first / second half of the batch) and the flattened
-// (pair, group) list of each set is dealt to the CTAs in the interleaved order A0 B0 A1 B1 ..., so every CTA owns a
-// contiguous run of set A and a contiguous run of set B with |A|+|B| balanced to within one group.  A CTA works through
-// its A run, then its B run, every half-step: by the time it returns to set A the other CTAs have had a whole B run to
-// finish A's previous half-step, so the inter-CTA wait is (almost) never exposed.
-__device__ __forceinline__ void cta_ranges(int B, int gpp, int (&rs)[2], int (&re)[2], int (&poff)[2]) {
-#ifdef SHWD_TWO_SETS
-  const int BA = (B + 1) / 2;
-#else
-  const int BA = B;
-#endif
-  const long long GA = (long long)BA * gpp, GB = (long long)(B - BA) * gpp, G = GA + GB;
-  const long long f0 = (G * blockIdx.x) / gridDim.x, f1 = (G * (blockIdx.x + 1)) / gridDim.x;
-  auto cntA = [&](long long f) { return f < 2 * GB ? (f + 1) / 2 : f - GB; };
-  auto cntB = [&](long long f) { return f < 2 * GB ? f / 2 : GB; };
-  rs[0] = (int)cntA(f0);
-  re[0] = (int)cntA(f1);
-  rs[1] = (int)cntB(f0);
-  re[1] = (int)cntB(f1);
-  poff[0] = 0;
-  poff[1] = BA;
+// Work split of one half-step: the flattened (pair, owner group) list is dealt to the CTAs in contiguous, balanced runs
+// (cta_range).  (A two-set interleave that lets a CTA alternate between two halves of the batch to hide the inter-CTA
+// wait was tried and lost: it doubles the per-item fixed cost -- staging, merge, signal -- which outweighs the wait.)
+
+// One-time staging for the resident mode (see ResidentType).  sS (4*CHUNK_PAD float2 slots) is carved into the packed
+// coordinate arrays of both types' streamed clouds plus one potential array per segment.
+template <int FAST>
+__device__ void resident_setup(const SinkParams& prm, int gr, int gc, float4* sS, float4* sOwnC, float* sOldP, ResidentType (&R)[2]) {
+  int g0[2], g1[2], T[2], ok[2], xyz[2][2], Pof[2];
+  long long need = 0;
+  int Tmax = 0;
+#pragma unroll
+  for (int type = 0; type < 2; ++type) {
+    const int gpp = type ? gc : gr, n_str = type ? prm.N : prm.M;
+    cta_range((long long)prm.B * gpp, g0[type], g1[type]);
+    const int ntot = g1[type] - g0[type];
+    const int npairs = ntot > 0 ? (g1[type] - 1) / gpp - g0[type] / gpp + 1 : 0;
+    const int SLt = ((((n_str + 1) / 2 + SK_WARPS - 1) / SK_WARPS) + 3) & ~3;
+    T[type] = SLt * SK_WARPS;
+    ok[type] = (FAST == FAST_GEO2) && SHWD_RESIDENT && ntot >= 1 && ntot <= GMAX && npairs <= 2 && n_str <= CHUNK;
+    need += 2LL * 3 * T[type];
+    Tmax = max(Tmax, T[type]);
+  }
+  need += 2LL * Tmax;
+  if (need > 4LL * CHUNK_PAD) ok[0] = ok[1] = 0;
+  float2* sS2 = reinterpret_cast<float2*>(sS);
+  int base = 0;
+#pragma unroll
+  for (int type = 0; type < 2; ++type) {
+#pragma unroll
+    for (int sg = 0; sg < 2; ++sg) {
+      xyz[type][sg] = base;
+      base += 3 * T[type];
+    }
+  }
+  Pof[0] = base;
+  Pof[1] = base + Tmax;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int type = 0; type < 2; ++type) {
+      R[type].ok = ok[type];
+      R[type].T = T[type];
+      R[type].own = type;
+      R[type].xyz[0] = xyz[type][0];
+      R[type].xyz[1] = xyz[type][1];
+      R[type].P[0] = Pof[0];
+      R[type].P[1] = Pof[1];
+    }
+  }
+  __syncthreads();  // the previous users of sS are done
+#pragma unroll
+  for (int type = 0; type < 2; ++type) {
+    if (!ok[type]) continue;
+    const int gpp = type ? gc : gr, n_str = type ? prm.N : prm.M, n_own = type ? prm.M : prm.N;
+    const float4* str = type ? prm.X : prm.Y;
+    const float4* own = type ? prm.Y : prm.X;
+    const int b0 = g0[type] / gpp;
+    const int TT = T[type];
+#pragma unroll
+    for (int sg = 0; sg < 2; ++sg) {
+      const int b = b0 + sg;
+      if ((long long)b * gpp >= g1[type]) break;
+      float* X = reinterpret_cast<float*>(sS2 + xyz[type][sg]);
+      float* Y = X + 2 * TT;
+      float* Z = Y + 2 * TT;
+      for (int q = threadIdx.x; q < 2 * TT; q += SK_THREADS) {
+        const int half = q >= TT, t = half ? q - TT : q;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < n_str) c = __ldg(str + (size_t)b * n_str + q);
+        const int o = 2 * t + half;
+        X[o] = c.x;
+        Y[o] = c.y;
+        Z[o] = c.z;
+      }
+    }
+    if (threadIdx.x < GMAX * 32) {
+      const int g = g0[type] + (threadIdx.x >> 5);
+      float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < g1[type]) {
+        const int b = g / gpp, o = (g % gpp) * 32 + (threadIdx.x & 31);
+        if (o < n_own) rec = __ldg(own + (size_t)b * n_own + o);
+      }
+      rec.w = 0.f;
+      sOwnC[type * GMAX * 32 + threadIdx.x] = rec;
+      sOldP[type * GMAX * 32 + threadIdx.x] = 0.f;
+    }
+  }
+  __syncthreads();
 }
 
 // ================================================================================================================
@@ -839,7 +955,11 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
   float4* part = smem4 + 2 * CHUNK_PAD;
   float2* sAdj = reinterpret_cast<float2*>(part + SK_WARPS * GMAX * 32);  // 2 x CHUNK_PAD
   float4* sOwn = reinterpret_cast<float4*>(sAdj + 2 * CHUNK_PAD);          // 3 x GMAX*32 staged owner records
+  float4* sOwnC = sOwn + 3 * GMAX * 32;                                    // 2 x GMAX*32 resident owner coordinates
+  float* sOldP = reinterpret_cast<float*>(sOwnC + 2 * GMAX * 32);          // 2 x GMAX*32 resident owner potentials
   __shared__ int s_ls;
+  __shared__ SweepIO s_ios[2];      // item descriptors: shared, not local memory (every __threadfence of the signal
+  __shared__ ResidentType s_RT[2];  // path invalidates L1, and spilled descriptors would be re-fetched from L2 each time)
 
   const int gr = (prm.N + 31) / 32, gc = (prm.M + 31) / 32;  // groups per pair, row / col owners
   PROF_INIT();
@@ -856,31 +976,32 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
     }
   }
 
+  ResidentType (&RT)[2] = s_RT;
+  resident_setup<FAST>(prm, gr, gc, sS, sOwnC, sOldP, RT);
+
   for (int h = 0; h < 2 * L; ++h) {
     const int type = h & 1;            // 0: alpha (row owners), 1: beta (col owners)
     const int l = (h >> 1) + 1;        // level being produced
     const int gpp = type ? gc : gr;
-    int rs[2], re[2], poff[2];
-    cta_ranges(prm.B, gpp, rs, re, poff);
+    int gbeg, gend;
+    cta_range((long long)prm.B * gpp, gbeg, gend);
     const int target_unit_r = ((h + 1) >> 1), target_unit_c = (h >> 1);  // #row / #col half-steps before h
-    for (int part_i = 0; part_i < 2; ++part_i)
-    for (int g = rs[part_i]; g < re[part_i];) {
+    for (int g = gbeg; g < gend;) {
       // gather up to two segments (a CTA whose share straddles a pair boundary) into one item
-      SweepIO ios[2];
+      SweepIO (&ios)[2] = s_ios;
       int segb[2] = {0, 0}, seg0[2] = {0, 0}, seg1[2] = {0, 0}, nseg = 0;
-      while (nseg < 2 && g < re[part_i]) {
-      const int b = poff[part_i] + g / gpp, lg0 = g % gpp;
-      const int lg1 = min(gpp, lg0 + (re[part_i] - g));
+      while (nseg < 2 && g < gend) {
+      const int b = g / gpp, lg0 = g % gpp;
+      const int lg1 = min(gpp, lg0 + (gend - g));
       segb[nseg] = b;
       seg0[nseg] = lg0;
       seg1[nseg] = lg1;
       g += lg1 - lg0;
-      SweepIO& io = ios[nseg];
+      if (threadIdx.x == 0) {
+      SweepIO& io = s_ios[nseg];
       io.lconst = type ? prm.lb2 : prm.la2;
       io.err_out = nullptr;
       io.old_pot = nullptr;
-      io.dmax_out = prm.dmax + (size_t)h * prm.B + b;
-      io.use_off = 0;
       if (type == 0) {
         io.own = prm.X + (size_t)b * prm.N;
         io.n_own = prm.N;
@@ -901,11 +1022,13 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
         io.out_pot = prm.beta + ((size_t)b * HL + slot(l)) * prm.M;
         io.out_pot_lo = prm.beta_lo + ((size_t)b * HL + slot(l)) * prm.M;
       }
+      }
       ++nseg;
       }
-      WaitSpec ws = {prm.done, {segb[0], segb[1]}, target_unit_r * gr + target_unit_c * gc, prm.status,
-                     (h >= 2 && FAST == FAST_GEO2) ? prm.dmax + (size_t)(h - 1) * prm.B : nullptr};
-      sweep<FAST, MODE_LSE, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws);
+      __syncthreads();  // the item descriptors (written by thread 0) are visible to the CTA
+      WaitSpec ws = {prm.done, segb[0], segb[1], target_unit_r * gr + target_unit_c * gc, prm.status,
+                     (SHWD_OFFSET_LSE && h >= 2 && FAST == FAST_GEO2) ? 1 : 0};
+      sweep<FAST, MODE_LSE, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, RT[type].ok ? &RT[type] : nullptr);
       signal_done2(prm.done, segb, seg0, seg1, nseg);
       PROF_MARK(4);
     }
@@ -936,21 +1059,21 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
   // ---- final sweeps: r_i = sum_j P_ij C_ij (row owners), c_j = sum_i P_ij C_ij (col owners)
   for (int type = 0; type < 2; ++type) {
     const int gpp = type ? gc : gr;
-    int rs[2], re[2], poff[2];
-    cta_ranges(prm.B, gpp, rs, re, poff);
-    for (int part_i = 0; part_i < 2; ++part_i)
-    for (int g = rs[part_i]; g < re[part_i];) {
+    int gbeg, gend;
+    cta_range((long long)prm.B * gpp, gbeg, gend);
+    for (int g = gbeg; g < gend;) {
       // gather up to two segments (a CTA whose share straddles a pair boundary) into one item
-      SweepIO ios[2];
+      SweepIO (&ios)[2] = s_ios;
       int segb[2] = {0, 0}, seg0[2] = {0, 0}, seg1[2] = {0, 0}, nseg = 0;
-      while (nseg < 2 && g < re[part_i]) {
-      const int b = poff[part_i] + g / gpp, lg0 = g % gpp;
-      const int lg1 = min(gpp, lg0 + (re[part_i] - g));
+      while (nseg < 2 && g < gend) {
+      const int b = g / gpp, lg0 = g % gpp;
+      const int lg1 = min(gpp, lg0 + (gend - g));
       segb[nseg] = b;
       seg0[nseg] = lg0;
       seg1[nseg] = lg1;
       g += lg1 - lg0;
-      SweepIO& io = ios[nseg];
+      if (threadIdx.x == 0) {
+      SweepIO& io = s_ios[nseg];
       io.pc_scale = prm.bval * prm.inv_k;
       const float* al = prm.alpha + ((size_t)b * HL + slot(Ls)) * prm.N;
       const float* be = prm.beta + ((size_t)b * HL + slot(Ls)) * prm.M;
@@ -979,10 +1102,12 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
         io.own_is_beta = 1;
         io.out_pc = prm.col_pc + (size_t)b * prm.M;
       }
+      }
       ++nseg;
       }
-      WaitSpec ws = {prm.done, {segb[0], segb[1]}, L * (gr + gc), prm.status, nullptr};
-      sweep<FAST, MODE_FINAL, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws);
+      __syncthreads();  // the item descriptors (written by thread 0) are visible to the CTA
+      WaitSpec ws = {prm.done, segb[0], segb[1], L * (gr + gc), prm.status, 0};
+      sweep<FAST, MODE_FINAL, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, nullptr);
       signal_done2(prm.done, segb, seg0, seg1, nseg);
       PROF_MARK(4);
     }
@@ -1021,6 +1146,12 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
   float4* part = smem4 + 2 * CHUNK_PAD;
   float2* sAdj = reinterpret_cast<float2*>(part + SK_WARPS * GMAX * 32);  // 2 x CHUNK_PAD
   float4* sOwn = reinterpret_cast<float4*>(sAdj + 2 * CHUNK_PAD);          // 3 x GMAX*32 staged owner records
+  float4* sOwnC = sOwn + 3 * GMAX * 32;                                    // 2 x GMAX*32 resident owner coordinates
+  float* sOldP = reinterpret_cast<float*>(sOwnC + 2 * GMAX * 32);          // (unused by the backward)
+  __shared__ SweepIO s_ios[2];
+  __shared__ ResidentType s_RT[2];
+  ResidentType (&RT)[2] = s_RT;
+  if (threadIdx.x == 0) RT[0].ok = RT[1].ok = 0;
 
   const int gr = (prm.N + 31) / 32, gc = (prm.M + 31) / 32;
   const int HL = prm.hist_levels;
@@ -1029,26 +1160,27 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
   const size_t BN = (size_t)prm.B * prm.N, BM = (size_t)prm.B * prm.M;
 
   for (int ph = 0; ph <= 2 * Ls; ++ph) {
+    if (ph == 2) resident_setup<FAST>(prm, gr, gc, sS, sOwnC, sOldP, RT);  // the two FINAL sweeps (ph 0, 1) stage through sS
     const bool last = (ph == 2 * Ls);
     const int type = last ? 0 : (ph & 1);
     const int l = last ? 0 : Ls - (ph >> 1);
     const int gpp = type ? gc : gr;
     const int nrow_before = last ? Ls : ((ph + 1) >> 1), ncol_before = last ? Ls : (ph >> 1);
-    int rs[2], re[2], poff[2];
-    cta_ranges(prm.B, gpp, rs, re, poff);
-    for (int part_i = 0; part_i < 2; ++part_i)
-    for (int g = rs[part_i]; g < re[part_i];) {
+    int gbeg, gend;
+    cta_range((long long)prm.B * gpp, gbeg, gend);
+    for (int g = gbeg; g < gend;) {
       // gather up to two segments (a CTA whose share straddles a pair boundary) into one item
-      SweepIO ios[2];
+      SweepIO (&ios)[2] = s_ios;
       int segb[2] = {0, 0}, seg0[2] = {0, 0}, seg1[2] = {0, 0}, nseg = 0;
-      while (nseg < 2 && g < re[part_i]) {
-      const int b = poff[part_i] + g / gpp, lg0 = g % gpp;
-      const int lg1 = min(gpp, lg0 + (re[part_i] - g));
+      while (nseg < 2 && g < gend) {
+      const int b = g / gpp, lg0 = g % gpp;
+      const int lg1 = min(gpp, lg0 + (gend - g));
       segb[nseg] = b;
       seg0[nseg] = lg0;
       seg1[nseg] = lg1;
       g += lg1 - lg0;
-      SweepIO& io = ios[nseg];
+      if (threadIdx.x == 0) {
+      SweepIO& io = s_ios[nseg];
       const float gb = __ldg(prm.grad_cost + b);
       const float* al = prm.alpha + (size_t)b * HL * prm.N;  // level 0
       const float* be = prm.beta + (size_t)b * HL * prm.M;
@@ -1121,13 +1253,15 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
         }
         io.adj_out = prm.bbar + (size_t)((l - 1) & 1) * BM + (size_t)b * prm.M;
       }
+      }
       ++nseg;
       }
-      WaitSpec ws = {prm.done, {segb[0], segb[1]}, nrow_before * gr + ncol_before * gc, prm.status, nullptr};
+      __syncthreads();  // the item descriptors (written by thread 0) are visible to the CTA
+      WaitSpec ws = {prm.done, segb[0], segb[1], nrow_before * gr + ncol_before * gc, prm.status, 0};
       if (l == Ls)
-        sweep<FAST, MODE_BWD, true>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws);
+        sweep<FAST, MODE_BWD, true>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, nullptr);
       else
-        sweep<FAST, MODE_BWD, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws);
+        sweep<FAST, MODE_BWD, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, RT[type].ok ? &RT[type] : nullptr);
       signal_done2(prm.done, segb, seg0, seg1, nseg);
       PROF_MARK(4);
     }
@@ -1155,7 +1289,6 @@ struct Workspace {
   int* done;
   int* status;
   float* err;
-  int* dmax;
   float* abar;
   float* bbar;
   size_t head_bytes;  // counters + status + err (memset on every launch)
@@ -1172,8 +1305,6 @@ static Workspace carve(void* base, int B, int N, int M, int iters) {
   off = align_up(off + sizeof(int) * (size_t)B, 256);
   w.err = reinterpret_cast<float*>(p + off);
   off = align_up(off + sizeof(float) * (size_t)B * (size_t)iters, 256);
-  w.dmax = reinterpret_cast<int*>(p + off);
-  off = align_up(off + sizeof(int) * 2 * (size_t)B * (size_t)iters, 256);
   w.head_bytes = off;
   w.abar = reinterpret_cast<float*>(p + off);
   off = align_up(off + sizeof(float) * 2 * (size_t)B * N, 256);
@@ -1298,8 +1429,8 @@ extern "C" int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N,
   prm.done = w.done;
   prm.status = w.status;
   prm.err = w.err;
-  prm.dmax = w.dmax;
-  const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32 + 3 * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD;
+  const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32 + 5 * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD +
+                      sizeof(float) * 2 * GMAX * 32;
   const int maxg = B * (((N > M ? N : M) + 31) / 32);
   switch (fast) {
     case FAST_GEO2: return launch_persistent(sinkhorn_fwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
@@ -1349,7 +1480,8 @@ extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N,
   prm.err = w.err;
   prm.abar = w.abar;
   prm.bbar = w.bbar;
-  const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32 + 3 * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD;
+  const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32 + 5 * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD +
+                      sizeof(float) * 2 * GMAX * 32;
   const int maxg = B * (((N > M ? N : M) + 31) / 32);
   switch (fast) {
     case FAST_GEO2: return launch_persistent(sinkhorn_bwd_kernel<FAST_GEO2>, prm, smem, maxg, s);

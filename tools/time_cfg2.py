@@ -10,7 +10,7 @@ torch.manual_seed(1234)
 x = torch.nn.functional.normalize(torch.randn(B, N, 3), dim=-1).to(dev).requires_grad_(True)
 y = torch.nn.functional.normalize(torch.randn(B, N, 3), dim=-1).to(dev).requires_grad_(True)
 fs, bs = [], []
-for it in range(6):
+for it in range(12):
     torch.cuda.synchronize()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
@@ -21,5 +21,11 @@ for it in range(6):
     torch.cuda.synchronize()
     if it >= 2:
         fs.append(e0.elapsed_time(e1)); bs.append(e1.elapsed_time(e2))
+import statistics, subprocess
 f, b = min(fs), min(bs)
-print("fwd %.2f ms  bwd %.2f ms  -> %.0f pairs/s   status %d" % (f, b, B / ((f + b) * 1e-3), res.status()))
+try:
+    clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+except OSError:
+    clk = "?"
+print("fwd %.2f ms  bwd %.2f ms  -> %.0f pairs/s   (median fwd %.2f bwd %.2f; idle clock/power %s)  status %d" % (
+    f, b, B / ((f + b) * 1e-3), statistics.median(fs), statistics.median(bs), clk, res.status()))
