@@ -371,16 +371,28 @@ __device__ __forceinline__ void stage_packed_pre(const SweepIO& io, int c0, int 
 }
 template <int MODE>
 __device__ __forceinline__ void stage_packed_post(const SweepIO& io, int c0, int cnt, int T, const PackedSmem& v) {
-  float* P = reinterpret_cast<float*>(v.P);
-  float* A = reinterpret_cast<float*>(v.A);
-  for (int q = threadIdx.x; q < 2 * T; q += SK_THREADS) {
-    const int half = q >= T, t = half ? q - T : q;
-    const int j = q;
-    const int o = 2 * t + half;
-    if (MODE == MODE_LSE) {
-      P[o] = (j < cnt) ? (io.str_pot ? __ldcg(io.str_pot + c0 + j) : 0.f) : -INFINITY;
-    } else {
-      A[o] = (j < cnt && io.str_adj) ? __ldcg(io.str_adj + c0 + j) * io.str_adj_scale * A[o] : 0.f;
+  float* dst = reinterpret_cast<float*>(MODE == MODE_LSE ? v.P : v.A);
+  const float* src = (MODE == MODE_LSE) ? io.str_pot : io.str_adj;
+  const float scale = (MODE == MODE_LSE) ? 1.f : io.str_adj_scale;
+  // batches of 4 records per thread: the loads of a batch are all in flight before its first store
+  for (int q0 = threadIdx.x; q0 < 2 * T; q0 += 4 * SK_THREADS) {
+    float val[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * SK_THREADS;
+      val[u] = (src && q < cnt) ? __ldcg(src + c0 + q) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * SK_THREADS;
+      if (q < 2 * T) {
+        const int half = q >= T, t = half ? q - T : q;
+        const int o = 2 * t + half;
+        if (MODE == MODE_LSE)
+          dst[o] = (q < cnt) ? val[u] : -INFINITY;
+        else
+          dst[o] = (src && q < cnt) ? val[u] * scale * dst[o] : 0.f;
+      }
     }
   }
 }
@@ -697,7 +709,7 @@ __device__ void sweep(const CostParams& cp, SweepIO (&ios)[2], const int (&glo)[
         if (use0) stage_packed_post<MODE>(ios[0], c0, cnt, T, pv0);
         if (use1) stage_packed_post<MODE>(ios[1], c0, cnt, T, pv1);
         __syncthreads();
-        PROF_MARK(1);
+        PROF_MARK(6);
         for (int g = 0; g < ng;) {  // two owner groups of the same pair per pass share every streamed record
           const int seg = (c0v + g) >= n0;
           const int gown = seg ? glo[1] + c0v + g - n0 : glo[0] + c0v + g;
@@ -844,7 +856,8 @@ __device__ void sweep(const CostParams& cp, SweepIO (&ios)[2], const int (&glo)[
 __device__ __forceinline__ void signal_done2(int* done, const int (&segb)[2], const int (&glo)[2], const int (&ghi)[2], int nseg) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    // release at gpu scope (cumulative over the bar.sync above); __threadfence() would be the heavier fence.sc.gpu
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
     atomicAdd(done + segb[0], ghi[0] - glo[0]);
     if (nseg > 1) atomicAdd(done + segb[1], ghi[1] - glo[1]);
   }
@@ -997,7 +1010,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
       seg0[nseg] = lg0;
       seg1[nseg] = lg1;
       g += lg1 - lg0;
-      if (threadIdx.x == 0) {
+      if (threadIdx.x == 32 * nseg) {
       SweepIO& io = s_ios[nseg];
       io.lconst = type ? prm.lb2 : prm.la2;
       io.err_out = nullptr;
@@ -1026,6 +1039,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
       ++nseg;
       }
       __syncthreads();  // the item descriptors (written by thread 0) are visible to the CTA
+      PROF_MARK(5);
       WaitSpec ws = {prm.done, segb[0], segb[1], target_unit_r * gr + target_unit_c * gc, prm.status,
                      (SHWD_OFFSET_LSE && h >= 2 && FAST == FAST_GEO2) ? 1 : 0};
       sweep<FAST, MODE_LSE, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, RT[type].ok ? &RT[type] : nullptr);
@@ -1072,7 +1086,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
       seg0[nseg] = lg0;
       seg1[nseg] = lg1;
       g += lg1 - lg0;
-      if (threadIdx.x == 0) {
+      if (threadIdx.x == 32 * nseg) {
       SweepIO& io = s_ios[nseg];
       io.pc_scale = prm.bval * prm.inv_k;
       const float* al = prm.alpha + ((size_t)b * HL + slot(Ls)) * prm.N;
@@ -1106,6 +1120,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
       ++nseg;
       }
       __syncthreads();  // the item descriptors (written by thread 0) are visible to the CTA
+      PROF_MARK(5);
       WaitSpec ws = {prm.done, segb[0], segb[1], L * (gr + gc), prm.status, 0};
       sweep<FAST, MODE_FINAL, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, nullptr);
       signal_done2(prm.done, segb, seg0, seg1, nseg);
@@ -1179,7 +1194,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
       seg0[nseg] = lg0;
       seg1[nseg] = lg1;
       g += lg1 - lg0;
-      if (threadIdx.x == 0) {
+      if (threadIdx.x == 32 * nseg) {
       SweepIO& io = s_ios[nseg];
       const float gb = __ldg(prm.grad_cost + b);
       const float* al = prm.alpha + (size_t)b * HL * prm.N;  // level 0
@@ -1257,6 +1272,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
       ++nseg;
       }
       __syncthreads();  // the item descriptors (written by thread 0) are visible to the CTA
+      PROF_MARK(5);
       WaitSpec ws = {prm.done, segb[0], segb[1], nrow_before * gr + ncol_before * gc, prm.status, 0};
       if (l == Ls)
         sweep<FAST, MODE_BWD, true>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, nullptr);

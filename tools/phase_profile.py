@@ -20,16 +20,16 @@ torch.manual_seed(0)
 x = torch.nn.functional.normalize(torch.randn(B, N, 3), dim=-1).to(dev).requires_grad_(True)
 y = torch.nn.functional.normalize(torch.randn(B, N, 3), dim=-1).to(dev).requires_grad_(True)
 buf = (ctypes.c_ulonglong * 8)()
-names = ["wait", "stage", "compute", "finalize", "signal"]
+names = ["wait", "pre-stage", "compute", "finalize", "signal", "item-setup", "post-stage"]
 for it in range(2):
     res = shwd.entropic_ot(x, y, "geodesic", 2.0, 0.01, L, center=True)
     torch.cuda.synchronize()
     raw.shwd_prof_read(buf, 1)
-    f = list(buf)[:5]
+    f = list(buf)[:7]
     res.cost.sum().backward()
     torch.cuda.synchronize()
     raw.shwd_prof_read(buf, 1)
-    b = list(buf)[:5]
+    b = list(buf)[:7]
     for tag, v in (("fwd", f), ("bwd", b)):
         tot = sum(v)
         print(tag, "cycles/CTA %.2fM  " % (tot / 148 / 1e6) + "  ".join("%s %.1f%%" % (n, 100 * c / tot) for n, c in zip(names, v)))
