@@ -22,8 +22,8 @@ def log_sinkhorn(x, y, kind="sqeuclid", p=2, eps=0.01, max_iter=100, thresh=None
     batch = 1 if x.dim() == 2 else x.shape[0]
     dt = C.dtype
     # sinkhorn.py:25-26 -- float32 fill of 1.0/n, .squeeze()
-    a = torch.empty(batch, n, dtype=torch.float).fill_(1.0 / n).squeeze().to(dt)
-    b = torch.empty(batch, m, dtype=torch.float).fill_(1.0 / m).squeeze().to(dt)
+    a = torch.empty(batch, n, dtype=torch.float).fill_(1.0 / n).squeeze().to(dtype=dt, device=C.device)
+    b = torch.empty(batch, m, dtype=torch.float).fill_(1.0 / m).squeeze().to(dtype=dt, device=C.device)
     u = torch.zeros_like(a)
     v = torch.zeros_like(b)
 

@@ -509,3 +509,117 @@ def test_full_size_properties_b32_n1024(shwd):
     col = P.sum(dim=1)
     assert (col - (1.0 / N + 1e-8)).abs().max().item() < 2e-3 / N
     assert (P * C).sum().item() == pytest.approx(one.cost.item(), rel=1e-4)
+
+
+# ------------------------------------------------------------- full-size parity: the oracle evaluated ON the device ----
+# The oracle is device-agnostic torch code.  On the B200 (180 GB) it can hold the N x M tensors and the autograd tape
+# of the reference's unrolled loop at BASELINE.json's full sizes, in float64 -- so the full-size configurations get a
+# real parity check, not only size-independent properties.  (Pairs are independent: the kernel runs the whole batch,
+# the oracle a subset of it, to bound the tape at ~20 GB.)
+def _oracle_geodesic_on_device(x, y, eps, L, grad=True):
+    xr = x.double().clone().requires_grad_(grad)
+    yr = y.double().clone().requires_grad_(grad)
+    with torch.set_grad_enabled(grad):
+        cost = oracle.log_sinkhorn(oracle.sphere_map(xr), oracle.sphere_map(yr), "geodesic", 2, eps, L)
+        if grad:
+            cost.sum().backward()
+    return cost.detach(), xr.grad, yr.grad
+
+
+def test_cfg2_full_size_matches_oracle_on_device(shwd):
+    """BASELINE config 2: B=32, N=M=1024, L=100, eps=0.01, geodesic p=2 on synthetic registration pairs (the bench
+    workload).  Loss and both gradients w.r.t. the RAW clouds (through centring + normalisation) < 1e-5."""
+    import bench
+    B, N, L, eps, K = 32, 1024, 100, 0.01, 4
+    tmpl, src = bench.registration_pairs(B, N, 1234, dev())
+    xg, yg = tmpl.clone().requires_grad_(True), src.clone().requires_grad_(True)
+    res = shwd.entropic_ot(xg, yg, "geodesic", 2.0, eps, L, center=True)
+    res.cost.sum().backward()
+    assert res.status() == 0
+    cr, gxr, gyr = _oracle_geodesic_on_device(tmpl[:K], src[:K], eps, L)
+    assert rel(res.cost[:K], cr) < TOL
+    assert rel(xg.grad[:K], gxr) < TOL and rel(yg.grad[:K], gyr) < TOL, (rel(xg.grad[:K], gxr), rel(yg.grad[:K], gyr))
+    torch.cuda.empty_cache()
+
+
+def _ellipsoid(n, seed, biased=False):
+    """Flow_ellipsoid.ipynb:106-150 (cell 3): (a,b,c) = (2,1,1); uniform angles, or theta from acos(N(0,0.25)) clipped."""
+    g = torch.Generator().manual_seed(seed)
+    phi = torch.rand(n, generator=g) * 2 * np.pi
+    if biased:
+        t = torch.acos((0.25 * torch.randn(n, generator=g)).clamp(-1, 1))
+    else:
+        t = torch.acos(torch.rand(n, generator=g) * 2 - 1)
+    return torch.stack([2 * torch.sin(t) * torch.cos(phi), torch.sin(t) * torch.sin(phi), torch.cos(t)], -1)
+
+
+def test_cfg4_n16384_matches_oracle_on_device(shwd):
+    """BASELINE config 4: one ellipsoid pair, N=M=16384 (the N x M tensor is 2 GB in float64 -- never formed by the
+    kernel).  L=3 keeps the oracle's tape at ~40 GB."""
+    N, L, eps = 16384, 3, 0.01
+    x, y = _ellipsoid(N, 1).to(dev()).unsqueeze(0), _ellipsoid(N, 2, biased=True).to(dev()).unsqueeze(0)
+    xg, yg = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    res = shwd.entropic_ot(xg, yg, "geodesic", 2.0, eps, L, center=True)
+    res.cost.sum().backward()
+    assert res.status() == 0
+    cr, gxr, gyr = _oracle_geodesic_on_device(x, y, eps, L)
+    assert rel(res.cost, cr) < TOL
+    assert rel(xg.grad, gxr) < TOL and rel(yg.grad, gyr) < TOL, (rel(xg.grad, gxr), rel(yg.grad, gyr))
+    del cr, gxr, gyr
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("B,N,L", [(256, 256, 10), (1, 32768, 2), (3, 5000, 4)])
+def test_sweep_corners_match_oracle_on_device(shwd, B, N, L):
+    """BASELINE config 5 (loss-kernel sweep N=256..65536, B=1..256): corner shapes, forward value against the float64
+    oracle on the device (no tape: N=32768 alone is an 8.6 GB matrix), gradients where the tape fits."""
+    g = torch.Generator().manual_seed(B + N)
+    x = F.normalize(torch.randn(B, N, 3, generator=g), dim=-1).to(dev())
+    y = F.normalize(torch.randn(B, N, 3, generator=g) + 0.2, dim=-1).to(dev())
+    with_grad = B * N * N * L <= 256 * 256 * 256 * 10
+    xg = x.clone().requires_grad_(True)
+    res = shwd.entropic_ot(xg, y, "geodesic", 2.0, 0.02, L, center=True)
+    res.cost.sum().backward()
+    assert res.status() == 0 and torch.isfinite(xg.grad).all()
+    cr, gxr, _ = _oracle_geodesic_on_device(x, y, 0.02, L, grad=with_grad)
+    assert rel(res.cost, cr) < TOL
+    if with_grad:
+        assert rel(xg.grad, gxr) < TOL
+    del cr
+    torch.cuda.empty_cache()
+
+
+def test_n65536_single_pair_properties(shwd):
+    """The sweep's largest shape (N=M=65536, B=1): a 17 GB matrix in float32 that is never formed.  Finite, status 0,
+    bit-reproducible, and invariant (to rounding) under a permutation of the points."""
+    N, L = 65536, 2
+    g = torch.Generator().manual_seed(5)
+    x = F.normalize(torch.randn(1, N, 3, generator=g), dim=-1).to(dev())
+    y = F.normalize(torch.randn(1, N, 3, generator=g) + 0.3, dim=-1).to(dev())
+    xg = x.clone().requires_grad_(True)
+    r1 = shwd.entropic_ot(xg, y, "geodesic", 2.0, 0.01, L, center=True)
+    r1.cost.sum().backward()
+    assert r1.status() == 0 and torch.isfinite(r1.cost).all() and torch.isfinite(xg.grad).all()
+    xg2 = x.clone().requires_grad_(True)
+    r2 = shwd.entropic_ot(xg2, y, "geodesic", 2.0, 0.01, L, center=True)
+    r2.cost.sum().backward()
+    assert torch.equal(r1.cost, r2.cost) and torch.equal(xg.grad, xg2.grad)
+    perm = torch.randperm(N, device=dev())
+    xp = x[:, perm].clone().requires_grad_(True)
+    r3 = shwd.entropic_ot(xp, y, "geodesic", 2.0, 0.01, L, center=True)
+    r3.cost.sum().backward()
+    assert rel(r3.cost, r1.cost) < TOL and rel(xp.grad, xg.grad[:, perm]) < TOL
+
+
+def test_chamfer_n16384_matches_oracle_on_device(shwd):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 16384, 3, generator=g).to(dev())
+    y = (torch.randn(1, 12000, 3, generator=g) * 1.1 + 0.1).to(dev())
+    xg, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    out, _ = shwd.losses.chamfer_distance(xg, y)
+    out.backward()
+    ref, _ = oracle.chamfer_distance(xr, y)
+    ref.backward()
+    assert out.item() == pytest.approx(ref.item(), rel=TOL)
+    assert rel(xg.grad, xr.grad) < TOL
+    torch.cuda.empty_cache()
