@@ -46,6 +46,22 @@ namespace shwd {
 #ifndef SHWD_OFF_UNROLL
 #define SHWD_OFF_UNROLL 2
 #endif
+#ifndef SHWD_SPIN
+#define SHWD_SPIN 1
+#endif
+// The backward keeps the counter protocol: its adjoints live in two planes reused by level parity (hot in L2), and
+// making them write-once (level-indexed, as the spin protocol needs) costs more in fresh-line write traffic than the
+// protocol saves (A/B on B200 at B=32, N=1024: 8.62 ms vs 8.38 ms).
+#ifndef SHWD_SPIN_BWD
+#define SHWD_SPIN_BWD 0
+#endif
+#if SHWD_SPIN_BWD
+#define ADJ_PLANE(l) (l)
+#define ADJ_PLANES(iters) ((size_t)(iters) + 1)
+#else
+#define ADJ_PLANE(l) ((l) & 1)
+#define ADJ_PLANES(iters) ((size_t)2)
+#endif
 #ifndef SHWD_RESIDENT
 #define SHWD_RESIDENT 1
 #endif
@@ -112,12 +128,13 @@ struct SinkParams {
   const float* grad_cost;
   float4* g4x;
   float4* g4y;
-  float* abar;  // (2, B, N)
+  float* abar;  // (2, B, N) by level parity  [(iters+1, B, N) write-once when SHWD_SPIN_BWD]
   float* bbar;  // (2, B, M)
   // workspace
   int* done;    // (B)
   int* status;  // (1)
   float* err;   // (iters, B)
+  int spin_ready;  // the host pre-filled the write-once planes with SPIN_SENTINEL
 };
 
 // Per-(pair, half-step) description of one sweep.
@@ -324,6 +341,19 @@ __device__ __forceinline__ PackedSmem packed_view(float4* sS, float2* sAdj, int 
   v.S = sAdj + T;
   return v;
 }
+// Data-flow synchronisation ("spin" mode, geodesic-p2 kernels with a history).  Potentials (forward) and adjoints
+// (backward) are written ONCE per launch into level-indexed planes that the host pre-fills with the bit pattern
+// 0xFFFFFFFF (a NaN no computation produces).  A consumer simply re-loads an element until it differs from the
+// sentinel: the poll IS the data load, so the per-half-step chain  barrier -> fence -> atomic -> poll -> load  of the
+// counter protocol collapses to one store -> load hop, and producers need no fence at all (a 32-bit store is atomic and
+// becomes visible on its own; nothing else is communicated between CTAs inside these half-steps).
+constexpr unsigned SPIN_SENTINEL = 0xFFFFFFFFu;
+__device__ __forceinline__ unsigned ld_relaxed_u32(const float* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Staging is split around the inter-CTA wait.  PRE (before the wait): everything that does not depend on the previous
 // half-step -- the streamed coordinates, and for the backward the streamed potential (forward history), its float32 addend
 // and the 2^res correction.  POST (after the wait): the forward's streamed potential / the backward's streamed adjoint.
@@ -370,17 +400,42 @@ __device__ __forceinline__ void stage_packed_pre(const SweepIO& io, int c0, int 
   }
 }
 template <int MODE>
-__device__ __forceinline__ void stage_packed_post(const SweepIO& io, int c0, int cnt, int T, const PackedSmem& v) {
+__device__ __forceinline__ void stage_packed_post(const SweepIO& io, int c0, int cnt, int T, const PackedSmem& v, bool spin, int* status) {
   float* dst = reinterpret_cast<float*>(MODE == MODE_LSE ? v.P : v.A);
   const float* src = (MODE == MODE_LSE) ? io.str_pot : io.str_adj;
   const float scale = (MODE == MODE_LSE) ? 1.f : io.str_adj_scale;
   // batches of 4 records per thread: the loads of a batch are all in flight before its first store
   for (int q0 = threadIdx.x; q0 < 2 * T; q0 += 4 * SK_THREADS) {
     float val[4];
+    if (spin && src) {
+      unsigned raw[4];
+      long long t0 = 0;
+      for (unsigned tries = 0;; ++tries) {
+        bool all = true;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int q = q0 + u * SK_THREADS;
-      val[u] = (src && q < cnt) ? __ldcg(src + c0 + q) : 0.f;
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + u * SK_THREADS;
+          if (q < cnt && (tries == 0 || raw[u] == SPIN_SENTINEL)) raw[u] = ld_relaxed_u32(src + c0 + q);
+          if (q >= cnt) raw[u] = 0u;
+          all = all && (raw[u] != SPIN_SENTINEL);
+        }
+        if (all) break;
+        if ((tries & 255u) == 255u) {  // a lost producer ends the launch instead of hanging the GPU
+          if (t0 == 0) t0 = clock64();
+          if (*reinterpret_cast<volatile int*>(status) != 0 || clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
+            atomicExch(status, 1);
+            break;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) val[u] = __uint_as_float(raw[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + u * SK_THREADS;
+        val[u] = (src && q < cnt) ? __ldcg(src + c0 + q) : 0.f;
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -647,6 +702,7 @@ struct WaitSpec {
   int target;
   int* status;
   int try_off;  // forward LSE: attempt the fixed-offset sum (see compute_packed_geo2)
+  int spin;     // consumers poll the data itself (see above); done/target are not used by this item
 };
 
 template <int FAST, int MODE, bool FINAL_TERM>
@@ -702,12 +758,12 @@ __device__ void sweep(const CostParams& cp, SweepIO (&ios)[2], const int (&glo)[
         if (c0 == 0) stage_owners<MODE>(ios, glo, n0, c0v, ng, sOwn, sOwn2, sOwn3, rt_ownc, rt_oldp);
         if (!waited) {
           PROF_MARK(1);
-          wait_done2(ws.done, ws.b0, ws.b1, nseg, ws.target, ws.status);
+          if (!ws.spin) wait_done2(ws.done, ws.b0, ws.b1, nseg, ws.target, ws.status);
           PROF_MARK(0);
           waited = true;
         }
-        if (use0) stage_packed_post<MODE>(ios[0], c0, cnt, T, pv0);
-        if (use1) stage_packed_post<MODE>(ios[1], c0, cnt, T, pv1);
+        if (use0) stage_packed_post<MODE>(ios[0], c0, cnt, T, pv0, ws.spin != 0, ws.status);
+        if (use1) stage_packed_post<MODE>(ios[1], c0, cnt, T, pv1, ws.spin != 0, ws.status);
         __syncthreads();
         PROF_MARK(6);
         for (int g = 0; g < ng;) {  // two owner groups of the same pair per pass share every streamed record
@@ -992,6 +1048,10 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
   ResidentType (&RT)[2] = s_RT;
   resident_setup<FAST>(prm, gr, gc, sS, sOwnC, sOldP, RT);
 
+  // data-flow synchronisation of the LSE half-steps (see SPIN_SENTINEL); the counters then only see the last two of them
+  const bool spin = SHWD_SPIN && (FAST == FAST_GEO2) && HL > 1 && prm.spin_ready;
+  const int lse_done = spin ? (gr + gc) : L * (gr + gc);  // per-pair counter value once every LSE half-step is published
+
   for (int h = 0; h < 2 * L; ++h) {
     const int type = h & 1;            // 0: alpha (row owners), 1: beta (col owners)
     const int l = (h >> 1) + 1;        // level being produced
@@ -1041,9 +1101,10 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
       __syncthreads();  // the item descriptors (written by thread 0) are visible to the CTA
       PROF_MARK(5);
       WaitSpec ws = {prm.done, segb[0], segb[1], target_unit_r * gr + target_unit_c * gc, prm.status,
-                     (SHWD_OFFSET_LSE && h >= 2 && FAST == FAST_GEO2) ? 1 : 0};
+                     (SHWD_OFFSET_LSE && h >= 2 && FAST == FAST_GEO2) ? 1 : 0, spin ? 1 : 0};
       sweep<FAST, MODE_LSE, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, RT[type].ok ? &RT[type] : nullptr);
-      signal_done2(prm.done, segb, seg0, seg1, nseg);
+      // spin mode: only the last alpha / beta half-steps publish through the counters (for the final sweeps and the cost)
+      if (!spin || h >= 2 * L - 2) signal_done2(prm.done, segb, seg0, seg1, nseg);
       PROF_MARK(4);
     }
   }
@@ -1051,7 +1112,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
   // ---- which iterate is the result?  (sinkhorn.py:42-44: first l with mean_b sum_i |u^l - u^{l-1}| < thresh)
   int Ls = L;
   if (prm.thresh > 0.f) {
-    for (int b = 0; b < prm.B; ++b) wait_done(prm.done + b, L * (gr + gc), prm.status);
+    for (int b = 0; b < prm.B; ++b) wait_done(prm.done + b, lse_done, prm.status);
     if (threadIdx.x == 0) {
       int found = L;
       for (int l = 0; l < L; ++l) {
@@ -1121,7 +1182,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
       }
       __syncthreads();  // the item descriptors (written by thread 0) are visible to the CTA
       PROF_MARK(5);
-      WaitSpec ws = {prm.done, segb[0], segb[1], L * (gr + gc), prm.status, 0};
+      WaitSpec ws = {prm.done, segb[0], segb[1], lse_done, prm.status, 0, 0};
       sweep<FAST, MODE_FINAL, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, nullptr);
       signal_done2(prm.done, segb, seg0, seg1, nseg);
       PROF_MARK(4);
@@ -1134,7 +1195,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
     cta_range((long long)prm.B * gr, g0, g1);
     for (int b = (g0 + gr - 1) / gr; b * gr < g1 && b < prm.B; ++b) {
       if (b * gr < g0) continue;
-      wait_done(prm.done + b, (L + 1) * (gr + gc), prm.status);
+      wait_done(prm.done + b, lse_done + gr + gc, prm.status);
       float s = 0.f;
       for (int i = threadIdx.x; i < prm.N; i += SK_THREADS) s += __ldcg(prm.row_pc + (size_t)b * prm.N + i);
       s = warp_sum(s);
@@ -1174,6 +1235,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
   PROF_INIT();
   const size_t BN = (size_t)prm.B * prm.N, BM = (size_t)prm.B * prm.M;
 
+  const bool spin = SHWD_SPIN_BWD && (FAST == FAST_GEO2) && prm.spin_ready;
   for (int ph = 0; ph <= 2 * Ls; ++ph) {
     if (ph == 2) resident_setup<FAST>(prm, gr, gc, sS, sOwnC, sOldP, RT);  // the two FINAL sweeps (ph 0, 1) stage through sS
     const bool last = (ph == 2 * Ls);
@@ -1227,17 +1289,17 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
             io.str_adj = nullptr;  // FINAL row sweep: the streamed scalars are g (b/k) 2^res_j and k lambda_j
             io.str_adj_scale = 0.f;
           } else {
-            io.str_adj = prm.bbar + (size_t)(l & 1) * BM + (size_t)b * prm.M;
+            io.str_adj = prm.bbar + (size_t)ADJ_PLANE(l) * BM + (size_t)b * prm.M;
             io.str_adj_scale = 1.f;
           }
           io.own_pot1 = al + (size_t)l * prm.N;
           io.str_lo = be_lo + (size_t)l * prm.M;  // S^v,l is normalised by beta^l (streamed)
-          io.adj_out = prm.abar + (size_t)(l & 1) * BN + (size_t)b * prm.N;
+          io.adj_out = prm.abar + (size_t)ADJ_PLANE(l) * BN + (size_t)b * prm.N;
         }
         if (l < Ls) {
           io.own_pot2 = al + (size_t)(l + 1) * prm.N;
           io.own_lo2 = al_lo + (size_t)(l + 1) * prm.N;  // S^u,l+1 is normalised by alpha^{l+1} (owner)
-          io.own_adj2 = prm.abar + (size_t)((l + 1) & 1) * BN + (size_t)b * prm.N;
+          io.own_adj2 = prm.abar + (size_t)ADJ_PLANE(l + 1) * BN + (size_t)b * prm.N;
           io.own_adj2_scale = 1.f;
         } else {
           io.own_pot2 = nullptr;
@@ -1250,7 +1312,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
         io.str = prm.X + (size_t)b * prm.N;
         io.n_str = prm.N;
         io.str_pot = al + (size_t)l * prm.N;
-        io.str_adj = prm.abar + (size_t)(l & 1) * BN + (size_t)b * prm.N;
+        io.str_adj = prm.abar + (size_t)ADJ_PLANE(l) * BN + (size_t)b * prm.N;
         io.str_adj_scale = 1.f;
         io.str_lo = al_lo + (size_t)l * prm.N;  // S^u,l is normalised by alpha^l (streamed)
         io.G = prm.g4y + (size_t)b * prm.M;
@@ -1263,22 +1325,24 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
           io.own_adj2 = nullptr;  // FINAL col sweep: the owner scalars are g (b/k) 2^res_j and k lambda_j
           io.own_adj2_scale = 0.f;
         } else {
-          io.own_adj2 = prm.bbar + (size_t)(l & 1) * BM + (size_t)b * prm.M;
+          io.own_adj2 = prm.bbar + (size_t)ADJ_PLANE(l) * BM + (size_t)b * prm.M;
           io.own_adj2_scale = 1.f;
         }
-        io.adj_out = prm.bbar + (size_t)((l - 1) & 1) * BM + (size_t)b * prm.M;
+        io.adj_out = prm.bbar + (size_t)ADJ_PLANE(l - 1) * BM + (size_t)b * prm.M;
       }
       }
       ++nseg;
       }
       __syncthreads();  // the item descriptors (written by thread 0) are visible to the CTA
       PROF_MARK(5);
-      WaitSpec ws = {prm.done, segb[0], segb[1], nrow_before * gr + ncol_before * gc, prm.status, 0};
+      // spin mode: phase 0 publishes through the counters (phase 1 stages through the scalar path); from phase 2 on the
+      // consumers poll the adjoints themselves
+      WaitSpec ws = {prm.done, segb[0], segb[1], nrow_before * gr + ncol_before * gc, prm.status, 0, (spin && ph >= 2) ? 1 : 0};
       if (l == Ls)
         sweep<FAST, MODE_BWD, true>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, nullptr);
       else
         sweep<FAST, MODE_BWD, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, RT[type].ok ? &RT[type] : nullptr);
-      signal_done2(prm.done, segb, seg0, seg1, nseg);
+      if (!spin || ph == 0) signal_done2(prm.done, segb, seg0, seg1, nseg);
       PROF_MARK(4);
     }
   }
@@ -1323,9 +1387,9 @@ static Workspace carve(void* base, int B, int N, int M, int iters) {
   off = align_up(off + sizeof(float) * (size_t)B * (size_t)iters, 256);
   w.head_bytes = off;
   w.abar = reinterpret_cast<float*>(p + off);
-  off = align_up(off + sizeof(float) * 2 * (size_t)B * N, 256);
+  off = align_up(off + sizeof(float) * ADJ_PLANES(iters) * B * N, 256);
   w.bbar = reinterpret_cast<float*>(p + off);
-  off = align_up(off + sizeof(float) * 2 * (size_t)B * M, 256);
+  off = align_up(off + sizeof(float) * ADJ_PLANES(iters) * B * M, 256);
   w.total = off;
   return w;
 }
@@ -1445,6 +1509,13 @@ extern "C" int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N,
   prm.done = w.done;
   prm.status = w.status;
   prm.err = w.err;
+  prm.spin_ready = 0;
+  if (SHWD_SPIN && fast == FAST_GEO2 && hist_levels > 1) {
+    // write-once potential planes (not the residual planes): sentinel-filled, see SPIN_SENTINEL
+    SHWD_CUDA_CHECK(cudaMemsetAsync(alpha_hist, 0xFF, sizeof(float) * (size_t)B * hist_levels * N, s));
+    SHWD_CUDA_CHECK(cudaMemsetAsync(beta_hist, 0xFF, sizeof(float) * (size_t)B * hist_levels * M, s));
+    prm.spin_ready = 1;
+  }
   const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32 + 5 * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD +
                       sizeof(float) * 2 * GMAX * 32;
   const int maxg = B * (((N > M ? N : M) + 31) / 32);
@@ -1496,6 +1567,12 @@ extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N,
   prm.err = w.err;
   prm.abar = w.abar;
   prm.bbar = w.bbar;
+  prm.spin_ready = 0;
+  if (SHWD_SPIN_BWD && fast == FAST_GEO2) {
+    SHWD_CUDA_CHECK(cudaMemsetAsync(w.abar, 0xFF, sizeof(float) * ADJ_PLANES(iters) * B * N, s));
+    SHWD_CUDA_CHECK(cudaMemsetAsync(w.bbar, 0xFF, sizeof(float) * ADJ_PLANES(iters) * B * M, s));
+    prm.spin_ready = 1;
+  }
   const size_t smem = sizeof(float4) * (2 * CHUNK_PAD + (size_t)SK_WARPS * GMAX * 32 + 5 * GMAX * 32) + sizeof(float2) * 2 * CHUNK_PAD +
                       sizeof(float) * 2 * GMAX * 32;
   const int maxg = B * (((N > M ? N : M) + 31) / 32);
