@@ -131,6 +131,19 @@ int shwd_euclid_sw(const float* xs, const float* ys, int S, int n, float p, floa
 /* Scatter gradients of sorted values back through the permutation: gkeys[seg][perm[seg][k]] = gsorted[seg][k]. */
 int shwd_unsort(const float* gsorted, const int64_t* perm, int segs, int len, float* gkeys, void* stream);
 
+/* ---- the learned sphere map phi: a stack of Residual flows x <- x + LipschitzMLP(x), fused --------------------------
+ * Replaces Norm_Flow_structure.forward ("Residual", s2_wasserstein.py:144-163; normflows_ishikawa/flows/residual.py:63-68,
+ * nets/lipschitz.py:14-68,642-648) and its autograd.  x, y, gy, gx: (npts,3).  params: n_layers x
+ * shwd_resflow_params_per_layer() floats of EFFECTIVE parameters per flow layer, laid out
+ * [W0 8x3 | b0 8 | (W 8x8 | b 8) x5 | W6 3x8 | b6 3 | s0..s6], W_k already divided by max(1, sigma_k/0.95), s_k =
+ * softplus(beta_k) -- the caller keeps those two maps in its autograd graph.  gparams receives d/d(effective params),
+ * reduced in a fixed order (bit-reproducible).  n_layers <= 8. */
+int shwd_resflow_params_per_layer(void);
+size_t shwd_resflow_workspace_bytes(int npts, int n_layers);
+int shwd_resflow_fwd(const float* x, int npts, const float* params, int n_layers, float* y, void* stream);
+int shwd_resflow_bwd(const float* x, const float* gy, int npts, const float* params, int n_layers, float* gx,
+                     float* gparams, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement helpers (bench.py): FP32-FMA and MUFU issue-rate microbenchmarks -------------------------------
  * out (grid*block floats) scratch; returns the number of lane-ops each launch performs in *ops. */
 int shwd_peak_fp32(float* out, int iters, double* ops, void* stream);

@@ -42,6 +42,10 @@ SIGNATURES = {
     "shwd_circular_wp": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "shwd_euclid_sw": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "shwd_unsort": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "shwd_resflow_params_per_layer": (_i, []),
+    "shwd_resflow_workspace_bytes": (_sz, [_i, _i]),
+    "shwd_resflow_fwd": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "shwd_resflow_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "shwd_peak_fp32": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), _vp]),
     "shwd_peak_mufu": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), _vp]),
 }

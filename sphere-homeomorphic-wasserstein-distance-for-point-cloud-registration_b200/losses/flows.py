@@ -3,7 +3,10 @@ flows ``Norm_Flow_structure`` builds from the vendored normflows 1.7.2 copy
 (``Point_Cloud_Resistration/losses/normflows_ishikawa``): ``flows.Planar`` (flows/planar.py:8-64) and
 ``flows.Residual`` over ``nets.LipschitzMLP`` (flows/residual.py:12-124, nets/lipschitz.py:14-68,132-293,642-648).
 Only the forward map is kept -- the reference discards the log-determinant (``x, _ = flow(x)``,
-s2_wasserstein.py:160-163).  This stays PyTorch: it is a tiny per-point MLP upstream of the CUDA kernels.
+s2_wasserstein.py:160-163).  The modules below own the parameters and define the map; on CUDA inputs a stack of
+standard Residual flows (hidden 8, 7 layers -- what ``Norm_Flow_structure`` builds) runs as ONE fused kernel per direction
+(``csrc/resflow.cu``, ``fused_residual_stack``) instead of ~45 eager kernels per flow layer; anything else (Planar, other
+widths, CPU tensors) runs the eager modules.
 """
 import math
 
@@ -84,3 +87,36 @@ class ResidualFlow(nn.Module):
 
     def forward(self, x):
         return x + self.net(x)
+
+
+def _effective_params(flow):
+    """Flat effective parameters of one standard ResidualFlow in the layout of include/shwd.h:
+    [W0 | b0 | (W | b) x5 | W6 | b6 | s0..s6], W_k / max(1, sigma_k / coeff), s_k = softplus(beta_k)."""
+    mods = list(flow.net)
+    swish, lins = mods[0::2], mods[1::2]
+    parts = []
+    for lin in lins:
+        sigma = torch.dot(lin.u, torch.mv(lin.weight, lin.v))
+        factor = torch.clamp(sigma / lin.coeff, min=1.0)
+        parts += [(lin.weight / factor).reshape(-1), lin.bias]
+    parts += [F.softplus(sw.beta) for sw in swish]
+    return torch.cat(parts)
+
+
+def is_standard_residual_stack(flows):
+    """True when every flow is a ResidualFlow with channels [3, 8 x6, 3] -- the shape the fused kernel implements."""
+    for f in flows:
+        if not isinstance(f, ResidualFlow):
+            return False
+        lins = list(f.net)[1::2]
+        shapes = [tuple(l.weight.shape) for l in lins]
+        if shapes != [(8, 3)] + [(8, 8)] * 5 + [(3, 8)]:
+            return False
+    return 0 < len(flows) <= 8
+
+
+def fused_residual_stack(flows, x):
+    """phi(x) for a standard Residual stack through the fused CUDA kernel (x: (...,3) CUDA tensor)."""
+    from .. import ops
+    params = torch.cat([_effective_params(f) for f in flows])
+    return ops.ResidualFlowStackFn.apply(x, params, len(flows)).reshape(x.shape)

@@ -12,7 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .flows import PlanarFlow, ResidualFlow
+from .flows import PlanarFlow, ResidualFlow, fused_residual_stack, is_standard_residual_stack
 
 
 class _EntropicW(nn.Module):
@@ -87,6 +87,14 @@ class Norm_Flow_structure(nn.Module):
             raise ValueError("Flow name is not valid")
 
     def forward(self, x):
+        if x.is_cuda and x.shape[-1] == 3 and is_standard_residual_stack(self.net):
+            return fused_residual_stack(self.net, x)  # one kernel per direction (csrc/resflow.cu)
+        for flow in self.net:
+            x = flow(x)
+        return x
+
+    def forward_eager(self, x):
+        """The same map through the eager torch modules (reference for the fused kernel's parity tests)."""
         for flow in self.net:
             x = flow(x)
         return x

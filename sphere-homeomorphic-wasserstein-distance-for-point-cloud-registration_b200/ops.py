@@ -435,6 +435,41 @@ class EuclidSWFn(torch.autograd.Function):
         return gxs * g, gys * g, None
 
 
+class ResidualFlowStackFn(torch.autograd.Function):
+    """y = phi(x) for a stack of Residual flows, one fused launch per direction (csrc/resflow.cu).  ``params`` is the flat
+    tensor of effective parameters (see include/shwd.h); gradients w.r.t. x and params."""
+
+    @staticmethod
+    def forward(ctx, x, params, n_layers):
+        lib = _lib.lib()
+        if not x.is_cuda:
+            raise RuntimeError("phi inputs must live on a CUDA device: no CPU fallback")
+        xc = x.contiguous().float()
+        pc = params.contiguous().float()
+        npts = xc.numel() // 3
+        y = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            _lib.check(lib.shwd_resflow_fwd(_ptr(xc), npts, _ptr(pc), int(n_layers), _ptr(y), _stream()), "shwd_resflow_fwd")
+        ctx.save_for_backward(xc, pc)
+        ctx.n_layers = int(n_layers)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, pc = ctx.saved_tensors
+        lib = _lib.lib()
+        gy = gy.contiguous().float()
+        npts = xc.numel() // 3
+        gx = torch.empty_like(xc)
+        gp = torch.empty_like(pc)
+        wsb = lib.shwd_resflow_workspace_bytes(npts, ctx.n_layers)
+        ws = torch.empty(max(wsb, 8), device=xc.device, dtype=torch.uint8)
+        with torch.cuda.device(xc.device):
+            _lib.check(lib.shwd_resflow_bwd(_ptr(xc), _ptr(gy), npts, _ptr(pc), ctx.n_layers, _ptr(gx), _ptr(gp), _ptr(ws), wsb,
+                                            _stream()), "shwd_resflow_bwd")
+        return gx, gp, None
+
+
 def spherical_sliced_w1(Xs, Xt, U):
     """mean_P circular-W1 of the great-circle projections (sliced_cost with p == 1, explicit frames U (P,3,2))."""
     xs, _ = _as_cloud(Xs, "Xs")

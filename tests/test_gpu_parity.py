@@ -623,3 +623,55 @@ def test_chamfer_n16384_matches_oracle_on_device(shwd):
     assert out.item() == pytest.approx(ref.item(), rel=TOL)
     assert rel(xg.grad, xr.grad) < TOL
     torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------ phi: fused Residual-flow stack ----
+@pytest.mark.parametrize("n_flow_layer,shape", [(3, (4, 1024, 3)), (5, (1000, 3)), (1, (2, 77, 3)), (8, (3, 129, 3))])
+def test_fused_residual_flow_matches_eager_modules(shwd, n_flow_layer, shape):
+    """Norm_Flow_structure("Residual") (s2_wasserstein.py:144-163): the fused kernel against the eager torch modules of
+    the same object (plain PyTorch fp32 reference of the same op) -- output, d/dx and d/d(every parameter)."""
+    torch.manual_seed(n_flow_layer)
+    phi = shwd.losses.Norm_Flow_structure(flow_name="Residual", n_flow_layer=n_flow_layer).to(dev())
+    with torch.no_grad():  # move the near-zero last layers and the Swish scales off their initial values
+        for prm in phi.parameters():
+            prm.add_(0.05 * torch.randn_like(prm))
+    x = (torch.randn(*shape) * 0.8).to(dev())
+    w = torch.randn(*shape).to(dev())
+    xe = x.clone().requires_grad_(True)
+    ye = phi.forward_eager(xe)
+    (ye * w).sum().backward()
+    ge = [prm.grad.clone() for prm in phi.parameters()]
+    gxe = xe.grad.clone()
+    phi.zero_grad()
+    xf = x.clone().requires_grad_(True)
+    yf = phi(xf)
+    (yf * w).sum().backward()
+    assert yf.shape == ye.shape and rel(yf, ye) < TOL
+    assert rel(xf.grad, gxe) < TOL
+    for (name, prm), g in zip(phi.named_parameters(), ge):
+        assert prm.grad is not None, name
+        assert (prm.grad - g).norm().item() <= TOL * max(g.norm().item(), 1e-3), (name, prm.grad.norm().item(), g.norm().item())
+    # bit-reproducible parameter gradients (fixed-order reduction, no float atomics)
+    g1 = [prm.grad.clone() for prm in phi.parameters()]
+    phi.zero_grad()
+    xf2 = x.clone().requires_grad_(True)
+    (phi(xf2) * w).sum().backward()
+    assert all(torch.equal(a, prm.grad) for a, prm in zip(g1, phi.parameters()))
+
+
+def test_max_wrapper_with_fused_phi_runs_the_reference_step(shwd):
+    """One training step of max_cos_disimilarity_wassersten_distance (s2_wasserstein.py:234-262) with the fused phi:
+    the inner ascent changes phi's parameters, the outer loss back-propagates to the cloud."""
+    torch.manual_seed(0)
+    phi = shwd.losses.Norm_Flow_structure(flow_name="Residual", n_flow_layer=3).to(dev())
+    opt = torch.optim.Adam(phi.parameters(), lr=1e-2)
+    crit = shwd.losses.max_cos_disimilarity_wassersten_distance(phi, shwd.losses.Geodesic_distance_W(dev(), p=2, max_iter=20),
+                                                                dev(), opt, max_iter=1, lam=0.1)
+    a = F.normalize(torch.randn(4, 256, 3), dim=-1).to(dev())
+    b = (F.normalize(torch.randn(4, 256, 3), dim=-1) * 1.1).to(dev()).requires_grad_(True)
+    before = [p.detach().clone() for p in phi.parameters()]
+    loss, a_t, b_t = crit(a, b, "train")
+    loss.backward()
+    assert torch.isfinite(loss) and b.grad is not None and torch.isfinite(b.grad).all() and b.grad.abs().sum() > 0
+    assert any(not torch.equal(p0, p1) for p0, p1 in zip(before, phi.parameters()))
+    assert a_t.shape == a.shape and b_t.shape == b.shape
