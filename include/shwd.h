@@ -133,16 +133,19 @@ int shwd_unsort(const float* gsorted, const int64_t* perm, int segs, int len, fl
 
 /* ---- the learned sphere map phi: a stack of Residual flows x <- x + LipschitzMLP(x), fused --------------------------
  * Replaces Norm_Flow_structure.forward ("Residual", s2_wasserstein.py:144-163; normflows_ishikawa/flows/residual.py:63-68,
- * nets/lipschitz.py:14-68,642-648) and its autograd.  x, y, gy, gx: (npts,3).  params: n_layers x
- * shwd_resflow_params_per_layer() floats of EFFECTIVE parameters per flow layer, laid out
- * [W0 8x3 | b0 8 | (W 8x8 | b 8) x5 | W6 3x8 | b6 3 | s0..s6], W_k already divided by max(1, sigma_k/0.95), s_k =
- * softplus(beta_k) -- the caller keeps those two maps in its autograd graph.  gparams receives d/d(effective params),
- * reduced in a fixed order (bit-reproducible).  n_layers <= 8. */
+ * nets/lipschitz.py:14-68,223-274,642-648) and its autograd.  x, y, gy, gx: (npts,3).
+ * params: n_layers x shwd_resflow_params_per_layer() RAW parameters per flow layer, laid out
+ *   [W0 8x3 | b0 8 | (W 8x8 | b 8) x5 | W6 3x8 | b6 3 | beta0..beta6]      (row-major out x in; beta = Swish parameter)
+ * uv: n_layers x shwd_resflow_uv_per_layer() frozen power-iteration vectors [u0 8 | v0 3 | (u 8 | v 8) x5 | u6 3 | v6 8].
+ * The kernels form W_k / max(1, (u_k^T W_k v_k)/coeff) and softplus(beta_k) themselves; gparams receives the gradient
+ * w.r.t. the RAW parameters (same layout), reduced in a fixed order (bit-reproducible).  n_layers <= 8. */
 int shwd_resflow_params_per_layer(void);
+int shwd_resflow_uv_per_layer(void);
 size_t shwd_resflow_workspace_bytes(int npts, int n_layers);
-int shwd_resflow_fwd(const float* x, int npts, const float* params, int n_layers, float* y, void* stream);
-int shwd_resflow_bwd(const float* x, const float* gy, int npts, const float* params, int n_layers, float* gx,
-                     float* gparams, void* workspace, size_t workspace_bytes, void* stream);
+int shwd_resflow_fwd(const float* x, int npts, const float* params, const float* uv, int n_layers, float coeff, float* y,
+                     void* stream);
+int shwd_resflow_bwd(const float* x, const float* gy, int npts, const float* params, const float* uv, int n_layers,
+                     float coeff, float* gx, float* gparams, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- measurement helpers (bench.py): FP32-FMA and MUFU issue-rate microbenchmarks -------------------------------
  * out (grid*block floats) scratch; returns the number of lane-ops each launch performs in *ops. */

@@ -44,8 +44,9 @@ SIGNATURES = {
     "shwd_unsort": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "shwd_resflow_params_per_layer": (_i, []),
     "shwd_resflow_workspace_bytes": (_sz, [_i, _i]),
-    "shwd_resflow_fwd": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
-    "shwd_resflow_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "shwd_resflow_uv_per_layer": (_i, []),
+    "shwd_resflow_fwd": (_i, [_vp, _i, _vp, _vp, _i, _f, _vp, _vp]),
+    "shwd_resflow_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "shwd_peak_fp32": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), _vp]),
     "shwd_peak_mufu": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), _vp]),
 }

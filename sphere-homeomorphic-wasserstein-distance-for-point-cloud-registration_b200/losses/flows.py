@@ -89,18 +89,24 @@ class ResidualFlow(nn.Module):
         return x + self.net(x)
 
 
-def _effective_params(flow):
-    """Flat effective parameters of one standard ResidualFlow in the layout of include/shwd.h:
-    [W0 | b0 | (W | b) x5 | W6 | b6 | s0..s6], W_k / max(1, sigma_k / coeff), s_k = softplus(beta_k)."""
+def _raw_params(flow):
+    """Raw parameter tensors of one standard ResidualFlow in the layout order of include/shwd.h:
+    W0, b0, ..., W6, b6, beta0..beta6."""
     mods = list(flow.net)
     swish, lins = mods[0::2], mods[1::2]
-    parts = []
+    out = []
     for lin in lins:
-        sigma = torch.dot(lin.u, torch.mv(lin.weight, lin.v))
-        factor = torch.clamp(sigma / lin.coeff, min=1.0)
-        parts += [(lin.weight / factor).reshape(-1), lin.bias]
-    parts += [F.softplus(sw.beta) for sw in swish]
-    return torch.cat(parts)
+        out += [lin.weight, lin.bias]
+    return out + [sw.beta for sw in swish]
+
+
+def _uv_buffer(flows):
+    """The frozen power-iteration vectors of every linear layer, flat: per flow [u0 | v0 | ... | u6 | v6]."""
+    parts = []
+    for f in flows:
+        for lin in list(f.net)[1::2]:
+            parts += [lin.u, lin.v]
+    return torch.cat(parts).float().contiguous()
 
 
 def is_standard_residual_stack(flows):
@@ -115,8 +121,14 @@ def is_standard_residual_stack(flows):
     return 0 < len(flows) <= 8
 
 
-def fused_residual_stack(flows, x):
-    """phi(x) for a standard Residual stack through the fused CUDA kernel (x: (...,3) CUDA tensor)."""
+def fused_residual_stack(flows, x, uv=None):
+    """phi(x) for a standard Residual stack through the fused CUDA kernel (x: (...,3) CUDA tensor).  ``uv``: the cached
+    result of ``_uv_buffer`` (the vectors are buffers that never change after construction)."""
     from .. import ops
-    params = torch.cat([_effective_params(f) for f in flows])
-    return ops.ResidualFlowStackFn.apply(x, params, len(flows)).reshape(x.shape)
+    if uv is None:
+        uv = _uv_buffer(flows)
+    params = []
+    for f in flows:
+        params += _raw_params(f)
+    coeff = list(flows[0].net)[1].coeff
+    return ops.ResidualFlowStackFn.apply(x, uv.to(x.device), len(flows), coeff, *params).reshape(x.shape)

@@ -12,7 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .flows import PlanarFlow, ResidualFlow, fused_residual_stack, is_standard_residual_stack
+from .flows import PlanarFlow, ResidualFlow, fused_residual_stack, is_standard_residual_stack, _uv_buffer
 
 
 class _EntropicW(nn.Module):
@@ -88,7 +88,10 @@ class Norm_Flow_structure(nn.Module):
 
     def forward(self, x):
         if x.is_cuda and x.shape[-1] == 3 and is_standard_residual_stack(self.net):
-            return fused_residual_stack(self.net, x)  # one kernel per direction (csrc/resflow.cu)
+            uv = getattr(self, "_uv_cache", None)
+            if uv is None or uv.device != x.device:
+                uv = self._uv_cache = _uv_buffer(self.net).to(x.device)
+            return fused_residual_stack(self.net, x, uv)  # one kernel per direction (csrc/resflow.cu)
         for flow in self.net:
             x = flow(x)
         return x

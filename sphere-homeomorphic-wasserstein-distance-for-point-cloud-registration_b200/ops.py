@@ -436,38 +436,51 @@ class EuclidSWFn(torch.autograd.Function):
 
 
 class ResidualFlowStackFn(torch.autograd.Function):
-    """y = phi(x) for a stack of Residual flows, one fused launch per direction (csrc/resflow.cu).  ``params`` is the flat
-    tensor of effective parameters (see include/shwd.h); gradients w.r.t. x and params."""
+    """y = phi(x) for a stack of Residual flows, one fused launch per direction (csrc/resflow.cu).
+    ``apply(x, uv, n_layers, coeff, *params)``: ``params`` are the module's raw parameter tensors in the layout order of
+    include/shwd.h (per flow: W0, b0, ..., W6, b6, beta0..beta6); they are concatenated once, and the flat raw-parameter
+    gradient the kernel returns is handed back as views -- no eager parameter preparation on either side."""
 
     @staticmethod
-    def forward(ctx, x, params, n_layers):
+    def forward(ctx, x, uv, n_layers, coeff, *params):
         lib = _lib.lib()
         if not x.is_cuda:
             raise RuntimeError("phi inputs must live on a CUDA device: no CPU fallback")
         xc = x.contiguous().float()
-        pc = params.contiguous().float()
+        flat = torch.cat([p.reshape(-1) for p in params]).float()
+        if flat.numel() != n_layers * lib.shwd_resflow_params_per_layer():
+            raise ValueError("parameter list does not match the fused Residual-flow layout")
         npts = xc.numel() // 3
         y = torch.empty_like(xc)
         with torch.cuda.device(xc.device):
-            _lib.check(lib.shwd_resflow_fwd(_ptr(xc), npts, _ptr(pc), int(n_layers), _ptr(y), _stream()), "shwd_resflow_fwd")
-        ctx.save_for_backward(xc, pc)
-        ctx.n_layers = int(n_layers)
+            _lib.check(lib.shwd_resflow_fwd(_ptr(xc), npts, _ptr(flat), _ptr(uv), int(n_layers), float(coeff), _ptr(y), _stream()),
+                       "shwd_resflow_fwd")
+        ctx.save_for_backward(xc, flat, uv)
+        ctx.n_layers, ctx.coeff = int(n_layers), float(coeff)
+        ctx.shapes = [p.shape for p in params]
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        xc, pc = ctx.saved_tensors
+        xc, flat, uv = ctx.saved_tensors
         lib = _lib.lib()
         gy = gy.contiguous().float()
         npts = xc.numel() // 3
         gx = torch.empty_like(xc)
-        gp = torch.empty_like(pc)
+        gp = torch.empty_like(flat)
         wsb = lib.shwd_resflow_workspace_bytes(npts, ctx.n_layers)
         ws = torch.empty(max(wsb, 8), device=xc.device, dtype=torch.uint8)
         with torch.cuda.device(xc.device):
-            _lib.check(lib.shwd_resflow_bwd(_ptr(xc), _ptr(gy), npts, _ptr(pc), ctx.n_layers, _ptr(gx), _ptr(gp), _ptr(ws), wsb,
-                                            _stream()), "shwd_resflow_bwd")
-        return gx, gp, None
+            _lib.check(lib.shwd_resflow_bwd(_ptr(xc), _ptr(gy), npts, _ptr(flat), _ptr(uv), ctx.n_layers, ctx.coeff, _ptr(gx),
+                                            _ptr(gp), _ptr(ws), wsb, _stream()), "shwd_resflow_bwd")
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = 1
+            for d in shp:
+                n *= d
+            grads.append(gp[off:off + n].view(shp))
+            off += n
+        return (gx, None, None, None) + tuple(grads)
 
 
 def spherical_sliced_w1(Xs, Xt, U):
