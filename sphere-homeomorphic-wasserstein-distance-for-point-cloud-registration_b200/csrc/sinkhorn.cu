@@ -527,6 +527,21 @@ __device__ __forceinline__ f2 dot3_2(float ox, float oy, float oz, f2 X, f2 Y, f
   return fma2(bc2(oz), Z, fma2(bc2(oy), Y, mul2(bc2(ox), X)));
 }
 
+// The two fast costs in packed form.  pk_e: the per-element intermediate of Cost<FAST>::E on a packed pair (GEO2:
+// th = sqrt(k) theta; SQE2: |o - s|^2); pk_m: the canonical exponent Cost<FAST>::m(e, pot), bit-identical to the scalar one.
+template <int FAST>
+__device__ __forceinline__ f2 pk_e(const CostParams& cp, const float4& o, f2 X, f2 Y, f2 Z) {
+  if (FAST == FAST_GEO2) return scaled_acos2(cp.q, cp.hpi, dot3_2(o.x, o.y, o.z, X, Y, Z));
+  const f2 dx = sub2(bc2(o.x), X), dy = sub2(bc2(o.y), Y), dz = sub2(bc2(o.z), Z);
+  return fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+}
+template <int FAST>
+__device__ __forceinline__ f2 pk_m(const CostParams& cp, f2 e, f2 pot) {
+  if (FAST == FAST_GEO2) return fma2(neg2(e), e, pot);
+  return fma2(bc2(-cp.k), e, pot);
+}
+__host__ __device__ constexpr bool is_packed_cost(int fast) { return fast == FAST_GEO2 || fast == FAST_SQE2; }
+
 // One (R owner groups, warp-slice) pass of a regular geodesic-p2 sweep in packed arithmetic: every lane owns R points
 // (one per group) and shares each streamed record between them, so one LDS.128 per array feeds 4R elements.
 // tb..te (multiple of 4) is the warp's range of packed records.  Results go to the warp's partial slots (slot[r*32]),
@@ -539,7 +554,7 @@ __device__ __forceinline__ f2 dot3_2(float ox, float oy, float oz, f2 X, f2 Y, f
 // below 2^-126 cannot matter, an overflow makes it inf); anything else -- only the first few, wildly moving iterations --
 // makes the CTA redo the visit with the running maximum.  The fixed offset removes the max / rescale work (0.25 MUFU
 // and ~2 FP32/ALU slots per element) and the dependency of every ex2 on the max of its batch.
-template <int MODE, int R, bool OFF = false>
+template <int FAST, int MODE, int R, bool OFF = false>
 __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const SweepIO& io, const PackedSmem& v, int tb, int te,
                                                     bool first_chunk, const float4* own, const float4* own3, float4* slot) {
   float4 op[R];  // staged owner records of this lane (stage_owners); entries of dead owners are zero / -inf
@@ -565,10 +580,10 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const 
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const f2 e0 = ex2_2(sub2(mp[r][0], bc2(off[r]))), e1 = ex2_2(sub2(mp[r][1], bc2(off[r])));
-        const f2 th0 = scaled_acos2(cp.q, cp.hpi, dot3_2(op[r].x, op[r].y, op[r].z, mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y)));
-        const f2 th1 = scaled_acos2(cp.q, cp.hpi, dot3_2(op[r].x, op[r].y, op[r].z, mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w)));
-        mp[r][0] = fma2(neg2(th0), th0, mk2(P.x, P.y));  // the canonical exponent Cost::m, as in the safe path
-        mp[r][1] = fma2(neg2(th1), th1, mk2(P.z, P.w));
+        const f2 th0 = pk_e<FAST>(cp, op[r], mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y));
+        const f2 th1 = pk_e<FAST>(cp, op[r], mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w));
+        mp[r][0] = pk_m<FAST>(cp, th0, mk2(P.x, P.y));  // the canonical exponent Cost::m, as in the safe path
+        mp[r][1] = pk_m<FAST>(cp, th1, mk2(P.z, P.w));
         rs[r] = add2(rs[r], add2(e0, e1));
       }
     }
@@ -598,10 +613,10 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const 
         const float4 Z = *reinterpret_cast<const float4*>(v.Z + t + e), P = *reinterpret_cast<const float4*>(v.P + t + e);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const f2 th0 = scaled_acos2(cp.q, cp.hpi, dot3_2(op[r].x, op[r].y, op[r].z, mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y)));
-          const f2 th1 = scaled_acos2(cp.q, cp.hpi, dot3_2(op[r].x, op[r].y, op[r].z, mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w)));
-          m[r][e] = fma2(neg2(th0), th0, mk2(P.x, P.y));
-          m[r][e + 1] = fma2(neg2(th1), th1, mk2(P.z, P.w));
+          const f2 th0 = pk_e<FAST>(cp, op[r], mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y));
+          const f2 th1 = pk_e<FAST>(cp, op[r], mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w));
+          m[r][e] = pk_m<FAST>(cp, th0, mk2(P.x, P.y));
+          m[r][e + 1] = pk_m<FAST>(cp, th1, mk2(P.z, P.w));
         }
       }
 #pragma unroll
@@ -642,20 +657,34 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const 
         const f2 a2 = h ? mk2(A.z, A.w) : mk2(A.x, A.y), s2 = h ? mk2(S.z, S.w) : mk2(S.x, S.y);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const f2 c = dot3_2(op[r].x, op[r].y, op[r].z, x2, y2, z2);
-          const f2 th = scaled_acos2(cp.q, cp.hpi, c);
-          const f2 om = fma2(neg2(c), c, bc2(1.f));
-          const f2 rs = mk2(rsqrt_approx(fmaxf(lo2(om), 1e-12f)), rsqrt_approx(fmaxf(hi2(om), 1e-12f)));
-          const f2 gs = mul2(th, rs);
-          const f2 nth = neg2(th);
-          const f2 S1 = ex2_2(add2(fma2(nth, th, bc2(opot1[r])), s2));
-          const f2 S2 = ex2_2(add2(fma2(nth, th, p2), bc2(o2[r])));
-          const f2 w1 = mul2(a2, S1);
-          aw[r] = add2(aw[r], w1);
-          const f2 wg = mul2(fma2(bc2(oadj[r]), S2, w1), gs);
-          ax[r] = fma2(wg, x2, ax[r]);
-          ay[r] = fma2(wg, y2, ay[r]);
-          az[r] = fma2(wg, z2, az[r]);
+          if (FAST == FAST_GEO2) {
+            const f2 c = dot3_2(op[r].x, op[r].y, op[r].z, x2, y2, z2);
+            const f2 th = scaled_acos2(cp.q, cp.hpi, c);
+            const f2 om = fma2(neg2(c), c, bc2(1.f));
+            const f2 rs = mk2(rsqrt_approx(fmaxf(lo2(om), 1e-12f)), rsqrt_approx(fmaxf(hi2(om), 1e-12f)));
+            const f2 gs = mul2(th, rs);
+            const f2 nth = neg2(th);
+            const f2 S1 = ex2_2(add2(fma2(nth, th, bc2(opot1[r])), s2));
+            const f2 S2 = ex2_2(add2(fma2(nth, th, p2), bc2(o2[r])));
+            const f2 w1 = mul2(a2, S1);
+            aw[r] = add2(aw[r], w1);
+            const f2 wg = mul2(fma2(bc2(oadj[r]), S2, w1), gs);
+            ax[r] = fma2(wg, x2, ax[r]);
+            ay[r] = fma2(wg, y2, ay[r]);
+            az[r] = fma2(wg, z2, az[r]);
+          } else {  // squared Euclidean: kC = k |o - s|^2, d(kC)/d(owner) = 2k (o - s) (2k = cp.gscale, applied per owner)
+            const f2 dx = sub2(bc2(op[r].x), x2), dy = sub2(bc2(op[r].y), y2), dz = sub2(bc2(op[r].z), z2);
+            const f2 sq = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            const f2 nk = bc2(-cp.k);
+            const f2 S1 = ex2_2(add2(fma2(nk, sq, bc2(opot1[r])), s2));
+            const f2 S2 = ex2_2(add2(fma2(nk, sq, p2), bc2(o2[r])));
+            const f2 w1 = mul2(a2, S1);
+            aw[r] = add2(aw[r], w1);
+            const f2 wg = fma2(bc2(oadj[r]), S2, w1);
+            ax[r] = fma2(wg, dx, ax[r]);
+            ay[r] = fma2(wg, dy, ay[r]);
+            az[r] = fma2(wg, dz, az[r]);
+          }
         }
       }
     }
@@ -710,7 +739,8 @@ __device__ void sweep(const CostParams& cp, SweepIO (&ios)[2], const int (&glo)[
                       float2* sAdj0, float4* part, float4* sOwn, const WaitSpec& ws, const ResidentType* rt) {
   typedef Cost<FAST> CF;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr bool PACKED = (FAST == FAST_GEO2) && (MODE == MODE_LSE || (MODE == MODE_BWD && !FINAL_TERM));
+  constexpr bool PACKED = is_packed_cost(FAST) && (MODE == MODE_LSE || (MODE == MODE_BWD && !FINAL_TERM));
+  constexpr int PK = is_packed_cost(FAST) ? FAST : FAST_GEO2;  // (the packed branch is dead code for the generic kernel)
   const int n0 = ghi[0] - glo[0];
   const int ntot = n0 + (nseg > 1 ? ghi[1] - glo[1] : 0);
   float4* sSb[2] = {sS0, sS0 + CHUNK_PAD};
@@ -773,13 +803,13 @@ __device__ void sweep(const CostParams& cp, SweepIO (&ios)[2], const int (&glo)[
           float4* slot = part + (warp * GMAX + g) * 32 + lane;
           if (MODE == MODE_LSE && off_try) {
             if (two)
-              compute_packed_geo2<MODE, 2, true>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
+              compute_packed_geo2<PK, MODE, 2, true>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
             else
-              compute_packed_geo2<MODE, 1, true>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
+              compute_packed_geo2<PK, MODE, 1, true>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
           } else if (two)
-            compute_packed_geo2<MODE, 2>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
+            compute_packed_geo2<PK, MODE, 2>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
           else
-            compute_packed_geo2<MODE, 1>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
+            compute_packed_geo2<PK, MODE, 1>(cp, ios[seg], seg ? pv1 : pv0, warp * SLt, warp * SLt + SLt, c0 == 0, sOwn + g * 32 + lane, sOwn3 + g * 32 + lane, slot);
           g += two ? 2 : 1;
         }
       } else {
@@ -943,7 +973,7 @@ __device__ void resident_setup(const SinkParams& prm, int gr, int gc, float4* sS
     const int npairs = ntot > 0 ? (g1[type] - 1) / gpp - g0[type] / gpp + 1 : 0;
     const int SLt = ((((n_str + 1) / 2 + SK_WARPS - 1) / SK_WARPS) + 3) & ~3;
     T[type] = SLt * SK_WARPS;
-    ok[type] = (FAST == FAST_GEO2) && SHWD_RESIDENT && ntot >= 1 && ntot <= GMAX && npairs <= 2 && n_str <= CHUNK;
+    ok[type] = is_packed_cost(FAST) && SHWD_RESIDENT && ntot >= 1 && ntot <= GMAX && npairs <= 2 && n_str <= CHUNK;
     need += 2LL * 3 * T[type];
     Tmax = max(Tmax, T[type]);
   }
@@ -1049,7 +1079,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
   resident_setup<FAST>(prm, gr, gc, sS, sOwnC, sOldP, RT);
 
   // data-flow synchronisation of the LSE half-steps (see SPIN_SENTINEL); the counters then only see the last two of them
-  const bool spin = SHWD_SPIN && (FAST == FAST_GEO2) && HL > 1 && prm.spin_ready;
+  const bool spin = SHWD_SPIN && is_packed_cost(FAST) && HL > 1 && prm.spin_ready;
   const int lse_done = spin ? (gr + gc) : L * (gr + gc);  // per-pair counter value once every LSE half-step is published
 
   for (int h = 0; h < 2 * L; ++h) {
@@ -1100,8 +1130,10 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_fwd_kerne
       }
       __syncthreads();  // the item descriptors (written by thread 0) are visible to the CTA
       PROF_MARK(5);
+        // (with the early-stop rule the running-maximum LSE is kept: its result does not depend on the previous iterate, so
+      //  the iteration settles on a bitwise fixed point exactly where the reference's does -- sinkhorn.py:42-44)
       WaitSpec ws = {prm.done, segb[0], segb[1], target_unit_r * gr + target_unit_c * gc, prm.status,
-                     (SHWD_OFFSET_LSE && h >= 2 && FAST == FAST_GEO2) ? 1 : 0, spin ? 1 : 0};
+                     (SHWD_OFFSET_LSE && h >= 2 && is_packed_cost(FAST) && !(prm.thresh > 0.f)) ? 1 : 0, spin ? 1 : 0};
       sweep<FAST, MODE_LSE, false>(prm.cp, ios, seg0, seg1, nseg, sS, sAdj, part, sOwn, ws, RT[type].ok ? &RT[type] : nullptr);
       // spin mode: only the last alpha / beta half-steps publish through the counters (for the final sweeps and the cost)
       if (!spin || h >= 2 * L - 2) signal_done2(prm.done, segb, seg0, seg1, nseg);
@@ -1235,7 +1267,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
   PROF_INIT();
   const size_t BN = (size_t)prm.B * prm.N, BM = (size_t)prm.B * prm.M;
 
-  const bool spin = SHWD_SPIN_BWD && (FAST == FAST_GEO2) && prm.spin_ready;
+  const bool spin = SHWD_SPIN_BWD && is_packed_cost(FAST) && prm.spin_ready;
   for (int ph = 0; ph <= 2 * Ls; ++ph) {
     if (ph == 2) resident_setup<FAST>(prm, gr, gc, sS, sOwnC, sOldP, RT);  // the two FINAL sweeps (ph 0, 1) stage through sS
     const bool last = (ph == 2 * Ls);
@@ -1510,7 +1542,7 @@ extern "C" int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N,
   prm.status = w.status;
   prm.err = w.err;
   prm.spin_ready = 0;
-  if (SHWD_SPIN && fast == FAST_GEO2 && hist_levels > 1) {
+  if (SHWD_SPIN && is_packed_cost(fast) && hist_levels > 1) {
     // write-once potential planes (not the residual planes): sentinel-filled, see SPIN_SENTINEL
     SHWD_CUDA_CHECK(cudaMemsetAsync(alpha_hist, 0xFF, sizeof(float) * (size_t)B * hist_levels * N, s));
     SHWD_CUDA_CHECK(cudaMemsetAsync(beta_hist, 0xFF, sizeof(float) * (size_t)B * hist_levels * M, s));
@@ -1568,7 +1600,7 @@ extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N,
   prm.abar = w.abar;
   prm.bbar = w.bbar;
   prm.spin_ready = 0;
-  if (SHWD_SPIN_BWD && fast == FAST_GEO2) {
+  if (SHWD_SPIN_BWD && is_packed_cost(fast)) {
     SHWD_CUDA_CHECK(cudaMemsetAsync(w.abar, 0xFF, sizeof(float) * ADJ_PLANES(iters) * B * N, s));
     SHWD_CUDA_CHECK(cudaMemsetAsync(w.bbar, 0xFF, sizeof(float) * ADJ_PLANES(iters) * B * M, s));
     prm.spin_ready = 1;
