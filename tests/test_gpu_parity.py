@@ -675,3 +675,30 @@ def test_max_wrapper_with_fused_phi_runs_the_reference_step(shwd):
     assert torch.isfinite(loss) and b.grad is not None and torch.isfinite(b.grad).all() and b.grad.abs().sum() > 0
     assert any(not torch.equal(p0, p1) for p0, p1 in zip(before, phi.parameters()))
     assert a_t.shape == a.shape and b_t.shape == b.shape
+
+
+def test_cos_disimilarity_w_full_size_matches_oracle_on_device(shwd):
+    """What train_W_COS.py instantiates (:393): Cos_disimilarity_W(p=2), cost sum_k |x_k - y_k|^2, at B=32, N=1024,
+    L=100, eps=0.01 on phi-like (un-normalised) clouds.  Bound: max(1e-5, 8 x the reference's own f32-vs-f64 distance)."""
+    import bench
+    B, N, L, eps, K = 32, 1024, 100, 0.01, 2
+    tmpl, src = bench.registration_pairs(B, N, 99, dev())
+    tmpl = tmpl - tmpl.mean(1, keepdim=True)
+    src = src - src.mean(1, keepdim=True)
+    xg, yg = tmpl.clone().requires_grad_(True), src.clone().requires_grad_(True)
+    res = shwd.entropic_ot(xg, yg, "sqeuclid", 2.0, eps, L)
+    res.cost.sum().backward()
+    assert res.status() == 0
+    outs = {}
+    for dt in (torch.float64, torch.float32):
+        xr, yr = tmpl[:K].to(dt).requires_grad_(True), src[:K].to(dt).requires_grad_(True)
+        c = oracle.log_sinkhorn(xr, yr, "sqeuclid", 2, eps, L)
+        c.sum().backward()
+        outs[dt] = (c.detach(), xr.grad, yr.grad)
+        del c
+    floor = max(rel(a, b) for a, b in zip(outs[torch.float32], outs[torch.float64]))
+    bound = max(TOL, 8 * floor)
+    c64, gx64, gy64 = outs[torch.float64]
+    assert rel(res.cost[:K], c64) < bound
+    assert rel(xg.grad[:K], gx64) < bound and rel(yg.grad[:K], gy64) < bound, (rel(xg.grad[:K], gx64), rel(yg.grad[:K], gy64), floor)
+    torch.cuda.empty_cache()
