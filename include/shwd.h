@@ -147,6 +147,16 @@ int shwd_resflow_fwd(const float* x, int npts, const float* params, const float*
 int shwd_resflow_bwd(const float* x, const float* gy, int npts, const float* params, const float* uv, int n_layers,
                      float coeff, float* gx, float* gparams, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- exact optimal assignment (uniform weights, n == m): the exact solve behind ot.emd2 on the W_COS path ------------
+ * Replaces the per-pair CPU solve `ot.emd2(a_i, b_i, C_i)` (s2_wasserstein.py:39-50, 99-110; main_rotation.py:63-79) by a
+ * float64 forward auction with epsilon-scaling on the on-the-fly cost, one CTA per pair.  x4, y4: packed points (B,N,4)
+ * (normalised by shwd_sphere_map_fwd for the cosine cost kinds).  sigma (B,N) int32: sigma[i] = point of y matched to
+ * point i of x; emd2_b = (1/N) sum_i C(x_i, y_sigma[i]).  prices (B,N) float64 (nullable): the dual prices; rounds (B)
+ * (nullable): bidding rounds used; status (1): set to 1 if a pair hit the round limit.  N <= shwd_exact_assignment_max_points(). */
+int shwd_exact_assignment_max_points(void);
+int shwd_exact_assignment(const float* x4, const float* y4, int B, int N, int cost_kind, float p, float n_power, int* sigma,
+                          double* prices, int* rounds, int* status, void* stream);
+
 /* ---- measurement helpers (bench.py): FP32-FMA and MUFU issue-rate microbenchmarks -------------------------------
  * out (grid*block floats) scratch; returns the number of lane-ops each launch performs in *ops. */
 int shwd_peak_fp32(float* out, int iters, double* ops, void* stream);

@@ -6,10 +6,10 @@ replacement of the reference's ``losses`` package.
 """
 from . import _lib, ops
 from .ops import (sphere_map, flow_regularization, entropic_ot, chamfer_nn, segmented_sort_raw, spherical_sliced_w1,
-                  spherical_sliced_wp, euclid_sliced_w)
+                  spherical_sliced_wp, euclid_sliced_w, exact_assignment, exact_emd2)
 
 __all__ = ["_lib", "ops", "sphere_map", "flow_regularization", "entropic_ot", "chamfer_nn", "segmented_sort_raw",
-           "spherical_sliced_w1", "spherical_sliced_wp", "euclid_sliced_w", "build_library"]
+           "spherical_sliced_w1", "spherical_sliced_wp", "euclid_sliced_w", "exact_assignment", "exact_emd2", "build_library"]
 
 
 def build_library(force=False):

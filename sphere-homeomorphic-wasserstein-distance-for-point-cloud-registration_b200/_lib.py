@@ -47,6 +47,8 @@ SIGNATURES = {
     "shwd_resflow_uv_per_layer": (_i, []),
     "shwd_resflow_fwd": (_i, [_vp, _i, _vp, _vp, _i, _f, _vp, _vp]),
     "shwd_resflow_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "shwd_exact_assignment_max_points": (_i, []),
+    "shwd_exact_assignment": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "shwd_peak_fp32": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), _vp]),
     "shwd_peak_mufu": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), _vp]),
 }

@@ -12,6 +12,7 @@
 // generic path that covers every other (kind, p, n_power).
 #pragma once
 #include "common.cuh"
+#include <math.h>
 
 namespace shwd {
 
@@ -213,4 +214,42 @@ struct Cost {
   }
 };
 
+// Host side: which specialised kernel a (kind, p, n_power) runs on, and its constants.
+inline int pick_fast(int kind, float p, float npow) {
+  if (kind == SHWD_COST_GEODESIC && p == 2.f && npow == 1.f) return FAST_GEO2;
+  if (kind == SHWD_COST_SQEUCLID && p == 2.f && npow == 1.f) return FAST_SQE2;
+  return GENERIC;
+}
+
+inline CostParams make_cost(int kind, float p, float npow, float eps, int fast) {
+  CostParams cp;
+  cp.kind = kind;
+  cp.p = p;
+  cp.npow = npow;
+  const double k = 1.4426950408889634 / (double)eps;
+  cp.k = (float)k;
+  cp.sk = (float)sqrt(k);
+  const float q[7] = SHWD_ACOS_Q;
+  const double qs = (fast == FAST_GEO2) ? sqrt(k) : 1.0;
+  for (int i = 0; i < 7; ++i) cp.q[i] = (float)(qs * (double)q[i]);
+  cp.hpi = (float)(qs * 1.5707963267948966);
+  cp.gscale = (fast == FAST_GEO2) ? (float)(-2.0 * sqrt(k)) : ((fast == FAST_SQE2) ? (float)(2.0 * k) : (float)k);
+  return cp;
+}
+
+// k == 1 exactly: the functors then return the plain float32 cost C (no scaling rounding) -- the exact-assignment kernel
+// must order assignments by the very numbers the reference's cost matrix holds.
+inline CostParams make_cost_unit(int kind, float p, float npow) {
+  CostParams cp;
+  cp.kind = kind;
+  cp.p = p;
+  cp.npow = npow;
+  cp.k = 1.f;
+  cp.sk = 1.f;
+  const float q[7] = SHWD_ACOS_Q;
+  for (int i = 0; i < 7; ++i) cp.q[i] = q[i];
+  cp.hpi = 1.5707963267948966f;
+  cp.gscale = 1.f;
+  return cp;
+}
 }  // namespace shwd

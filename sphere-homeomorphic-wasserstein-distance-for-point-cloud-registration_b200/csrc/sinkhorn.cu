@@ -1426,28 +1426,6 @@ static Workspace carve(void* base, int B, int N, int M, int iters) {
   return w;
 }
 
-static int pick_fast(int kind, float p, float npow) {
-  if (kind == SHWD_COST_GEODESIC && p == 2.f && npow == 1.f) return FAST_GEO2;
-  if (kind == SHWD_COST_SQEUCLID && p == 2.f && npow == 1.f) return FAST_SQE2;
-  return GENERIC;
-}
-
-static CostParams make_cost(int kind, float p, float npow, float eps, int fast) {
-  CostParams cp;
-  cp.kind = kind;
-  cp.p = p;
-  cp.npow = npow;
-  const double k = 1.4426950408889634 / (double)eps;
-  cp.k = (float)k;
-  cp.sk = (float)sqrt(k);
-  const float q[7] = SHWD_ACOS_Q;
-  const double qs = (fast == FAST_GEO2) ? sqrt(k) : 1.0;
-  for (int i = 0; i < 7; ++i) cp.q[i] = (float)(qs * (double)q[i]);
-  cp.hpi = (float)(qs * 1.5707963267948966);
-  cp.gscale = (fast == FAST_GEO2) ? (float)(-2.0 * sqrt(k)) : ((fast == FAST_SQE2) ? (float)(2.0 * k) : (float)k);
-  return cp;
-}
-
 static void fill_marginals(SinkParams& prm, int N, int M, float eps) {
   // log(fill_(1.0/n) + 1e-8) in float32, as the reference builds it (sinkhorn.py:25-26,39-40)
   const float a = (float)(1.0 / (double)N) + 1e-8f, b = (float)(1.0 / (double)M) + 1e-8f;

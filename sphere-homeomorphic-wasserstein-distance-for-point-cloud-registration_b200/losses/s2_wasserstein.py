@@ -16,14 +16,20 @@ from .flows import PlanarFlow, ResidualFlow, fused_residual_stack, is_standard_r
 
 
 class _EntropicW(nn.Module):
+    """``solver="sinkhorn"`` (default; BASELINE.json north_star): on-the-fly entropic iterations.  ``solver="exact"``: the
+    exact LP optimum the reference itself computes with ``ot.emd2`` (:41-43), by the GPU auction kernel (equally sized
+    clouds); value and gradient are then the reference's up to float32 rounding."""
     _kind = None
 
-    def __init__(self, device, p=1, eps=0.01, max_iter=100):
+    def __init__(self, device, p=1, eps=0.01, max_iter=100, solver="sinkhorn"):
         super().__init__()
+        if solver not in ("sinkhorn", "exact"):
+            raise ValueError("solver must be 'sinkhorn' or 'exact'")
         self.device = device
         self.p = p
         self.eps = eps
         self.max_iter = max_iter
+        self.solver = solver
 
     def _w(self, x, y, device, p=1):
         x = x.to(device)
@@ -34,7 +40,10 @@ class _EntropicW(nn.Module):
             batch_size = x.shape[0]
         if batch_size < 1:
             raise ValueError("batch_size is not valid")
-        cost = ops.entropic_ot(x, y, self._kind, float(p), float(self.eps), int(self.max_iter)).cost
+        if self.solver == "exact":
+            cost = ops.exact_emd2(x, y, self._kind, float(p))
+        else:
+            cost = ops.entropic_ot(x, y, self._kind, float(p), float(self.eps), int(self.max_iter)).cost
         losses = torch.pow(cost, 1. / p)
         if batch_size >= 2:
             return losses.sum() / int(batch_size)

@@ -435,6 +435,68 @@ class EuclidSWFn(torch.autograd.Function):
         return gxs * g, gys * g, None
 
 
+def exact_assignment(x, y, kind="sqeuclid", p=2.0, n_power=1.0, return_info=False):
+    """Optimal assignment sigma (B,N) int64 between equally sized clouds under the cost ``kind`` (exact LP optimum for
+    uniform weights -- what ``ot.emd2`` solves at s2_wasserstein.py:41-43), by the float64 auction kernel."""
+    lib = _lib.lib()
+    xc, _ = _as_cloud(x, "x")
+    yc, _ = _as_cloud(y, "y")
+    if xc.shape != yc.shape:
+        raise ValueError("exact assignment needs equally sized clouds (uniform weights, n == m)")
+    B, N, _ = xc.shape
+    if N > lib.shwd_exact_assignment_max_points():
+        raise ValueError("exact assignment supports at most %d points per cloud" % lib.shwd_exact_assignment_max_points())
+    k = COST_KINDS[kind] if isinstance(kind, str) else int(kind)
+    cosine = k in (_lib.COST_GEODESIC, _lib.COST_ONE_MINUS_COS)
+    dev = xc.device
+    xd, yd = xc.detach(), yc.detach()
+    x4 = torch.empty(B, N, 4, device=dev, dtype=torch.float32)
+    y4 = torch.empty(B, N, 4, device=dev, dtype=torch.float32)
+    sigma = torch.empty(B, N, device=dev, dtype=torch.int32)
+    prices = torch.empty(B, N, device=dev, dtype=torch.float64)
+    rounds = torch.empty(B, device=dev, dtype=torch.int32)
+    status = torch.empty(1, device=dev, dtype=torch.int32)
+    flags = MAP_NORMALIZE if cosine else 0
+    with torch.cuda.device(dev):
+        s = _stream()
+        _lib.check(lib.shwd_sphere_map_fwd(_ptr(xd), _ptr(x4), None, B, N, flags, s), "shwd_sphere_map_fwd")
+        _lib.check(lib.shwd_sphere_map_fwd(_ptr(yd), _ptr(y4), None, B, N, flags, s), "shwd_sphere_map_fwd")
+        _lib.check(lib.shwd_exact_assignment(_ptr(x4), _ptr(y4), B, N, k, float(p), float(n_power), _ptr(sigma), _ptr(prices),
+                                             _ptr(rounds), _ptr(status), s), "shwd_exact_assignment")
+    sig = sigma.long()
+    if return_info:
+        return sig, prices, rounds, status
+    return sig
+
+
+def _pair_cost(x, ys, kind, p, n_power=1.0):
+    """C(x_i, ys_i) for matched points, with the reference's own torch formulas (s2_wasserstein.py:52-63,112-123;
+    max_spherical_w_cos_with_regulation.py:745) so the value and its autograd are the reference's on those n entries."""
+    if kind == "geodesic":
+        c = torch.acos(torch.nn.functional.cosine_similarity(x, ys, dim=-1)) ** p
+    elif kind == "one_minus_cos":
+        c = (1 - torch.nn.functional.cosine_similarity(x, ys, dim=-1)) ** p
+    elif kind == "sqeuclid":
+        c = torch.sum(torch.abs(x - ys) ** p, -1)
+    elif kind == "euclid":
+        c = torch.pow(torch.sum(torch.abs(x - ys) ** p, -1), 1.0 / p)
+    else:
+        raise ValueError(kind)
+    return c if n_power == 1.0 else torch.pow(c, n_power)
+
+
+def exact_emd2(x, y, kind="sqeuclid", p=2.0):
+    """Per-pair exact ``emd2`` (B,) with uniform weights: the optimal permutation from the auction kernel, the value
+    (1/n) sum_i C(x_i, y_sigma(i)) accumulated in float64 like POT does, and -- through autograd on the n matched
+    entries -- exactly the gradient POT attaches (d emd2 / dC = optimal plan)."""
+    xc, _ = _as_cloud(x, "x")
+    yc, _ = _as_cloud(y, "y")
+    sigma = exact_assignment(xc, yc, kind, p)
+    ys = torch.gather(yc, 1, sigma.unsqueeze(-1).expand(-1, -1, 3))
+    c = _pair_cost(xc, ys, kind, p)
+    return (c.double().sum(dim=1) / xc.shape[1]).to(c.dtype)
+
+
 class ResidualFlowStackFn(torch.autograd.Function):
     """y = phi(x) for a stack of Residual flows, one fused launch per direction (csrc/resflow.cu).
     ``apply(x, uv, n_layers, coeff, *params)``: ``params`` are the module's raw parameter tensors in the layout order of

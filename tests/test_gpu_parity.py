@@ -702,3 +702,93 @@ def test_cos_disimilarity_w_full_size_matches_oracle_on_device(shwd):
     assert rel(res.cost[:K], c64) < bound
     assert rel(xg.grad[:K], gx64) < bound and rel(yg.grad[:K], gy64) < bound, (rel(xg.grad[:K], gx64), rel(yg.grad[:K], gy64), floor)
     torch.cuda.empty_cache()
+
+
+# ------------------------------------------------ exact EMD (what the reference's W_COS path solves with ot.emd2, 8f #2) ----
+def _lsa(C):
+    from scipy.optimize import linear_sum_assignment
+    return linear_sum_assignment(C.double().numpy())[1]
+
+
+@pytest.mark.parametrize("B,N,kind,p", [(3, 7, "sqeuclid", 2), (2, 64, "geodesic", 2), (2, 257, "sqeuclid", 2), (2, 300, "geodesic", 1),
+                                        (1, 1024, "geodesic", 2), (2, 1, "sqeuclid", 2), (2, 200, "sqeuclid", 1), (1, 500, "one_minus_cos", 2)])
+def test_exact_assignment_is_the_lp_optimum(shwd, B, N, kind, p):
+    """The auction kernel returns an optimal permutation: identical to scipy's linear_sum_assignment on the reference's
+    own cost matrix, or -- for costs with exact ties between optimal assignments, which the L1 cost produces (swapping
+    two matches leaves sum |.| unchanged whenever the coordinate intervals nest) -- of exactly the same total cost."""
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    x = torch.randn(B, N, 3, generator=g)
+    y = torch.randn(B, N, 3, generator=g) * 0.9 + 0.1
+    if kind in ("geodesic", "one_minus_cos"):
+        x, y = F.normalize(x, dim=-1), F.normalize(y, dim=-1)
+    sig, prices, rounds, status = shwd.ops.exact_assignment(x.to(dev()), y.to(dev()), kind, float(p), return_info=True)
+    assert int(status.item()) == 0
+    C = oracle.cost_matrix(x, y, kind, p)
+    for b in range(B):
+        ours, ref = sig[b].cpu().numpy(), _lsa(C[b])
+        Cb = C[b].double().numpy()
+        excess = (Cb[np.arange(N), ours].sum() - Cb[np.arange(N), ref].sum()) / max(Cb[np.arange(N), ref].sum(), 1e-30)
+        assert sorted(ours.tolist()) == list(range(N))
+        assert np.array_equal(ours, ref) or abs(excess) <= 1e-13, (b, int(rounds[b]), "relative excess cost %.3e" % excess)
+
+
+@pytest.mark.parametrize("kind", ["sqeuclid", "geodesic"])
+def test_exact_solver_value_and_gradient_follow_pot_semantics(shwd, kind):
+    """Cos_disimilarity_W / Geodesic_distance_W with solver="exact": the value mean_b emd2_b^(1/p) and the gradient POT's
+    torch backend attaches (d emd2 / dC = optimal plan, s2_wasserstein.py:41-44), computed by the oracle on the dense
+    cost matrix with scipy's exact assignment."""
+    B, N, p = 3, 200, 2
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, N, 3, generator=g)
+    y = torch.randn(B, N, 3, generator=g) * 0.8 + 0.2
+    if kind == "geodesic":
+        x, y = F.normalize(x, dim=-1), F.normalize(y, dim=-1) * 1.3  # the cost normalises internally
+    xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    C = oracle.cost_matrix(xr, yr, kind, p)
+    ref = 0
+    for b in range(B):
+        _, plan = oracle.exact_emd2(C[b])
+        ref = ref + torch.pow((plan.float() * C[b]).sum(), 1.0 / p)
+    ref = ref / B
+    ref.backward()
+    cls = shwd.losses.Cos_disimilarity_W if kind == "sqeuclid" else shwd.losses.Geodesic_distance_W
+    xg, yg = x.clone().to(dev()).requires_grad_(True), y.clone().to(dev()).requires_grad_(True)
+    out = cls(dev(), p=p, solver="exact")(xg, yg)
+    out.backward()
+    assert out.item() == pytest.approx(ref.item(), rel=2e-6)
+    assert rel(xg.grad, xr.grad) < TOL and rel(yg.grad, yr.grad) < TOL
+
+
+def test_exact_solver_matches_reference_wrapper_fixture(shwd):
+    """The frozen outputs of the reference's own Geodesic_distance_W / Cos_disimilarity_W (run with a scipy-backed ``ot``
+    shim, tests/golden/make_golden.py) on the fixture clouds."""
+    d = gold("cost_matrices")
+    x, y = torch.from_numpy(d["x"]).to(dev()), torch.from_numpy(d["y"]).to(dev())
+    g = shwd.losses.Geodesic_distance_W(dev(), p=2, solver="exact")(x, y)
+    c = shwd.losses.Cos_disimilarity_W(dev(), p=2, solver="exact")(x, y)
+    assert g.item() == pytest.approx(float(d["exact_emd_geodesic_p2"]), rel=TOL)
+    assert c.item() == pytest.approx(float(d["exact_emd_sqeuclid_p2"]), rel=TOL)
+
+
+def test_exact_solver_training_shape_properties(shwd):
+    """B=32, N=1024 (the training shape): permutations, deterministic, no worse than the identity matching, and certified
+    optimal by LP duality (primal value == dual value of the returned prices)."""
+    import bench
+    tmpl, src = bench.registration_pairs(32, 1024, 7, dev())
+    s1, _, rounds, status = shwd.ops.exact_assignment(tmpl, src, "sqeuclid", 2.0, return_info=True)
+    assert int(status.item()) == 0
+    assert torch.equal(torch.sort(s1, dim=1)[0], torch.arange(1024, device=dev()).expand(32, -1))
+    s2 = shwd.ops.exact_assignment(tmpl, src, "sqeuclid", 2.0)
+    assert torch.equal(s1, s2)
+    emd = shwd.ops.exact_emd2(tmpl, src, "sqeuclid", 2.0)
+    ident = ((tmpl - src) ** 2).sum(-1).mean(1)
+    assert (emd <= ident * (1 + 1e-6)).all()
+    # optimality certificate from the returned duals: with profits pi_i = max_j (-C_ij - p_j), sum_i pi_i + sum_j p_j is
+    # an upper bound of -(min cost); it must meet the primal value to ~n * eps_final
+    sig, prices, _, _ = shwd.ops.exact_assignment(tmpl[:2], src[:2], "sqeuclid", 2.0, return_info=True)
+    C = ((tmpl[:2].unsqueeze(2) - src[:2].unsqueeze(1)).abs() ** 2).sum(-1).double()
+    profit = (-C - prices.unsqueeze(1)).max(dim=2).values
+    dual = -(profit.sum(1) + prices.sum(1))
+    primal = torch.gather(C, 2, sig.unsqueeze(-1)).sum((1, 2))
+    # (C here is torch's float32 evaluation; the kernel's differs by float32 rounding, ~1e-7 per entry)
+    assert ((primal - dual).abs() <= 1e-6 * primal.abs()).all(), (primal, dual)
