@@ -147,3 +147,37 @@ def test_sharded_mean_equals_single_process_mean_world2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_fused_phi_parameter_layout_matches_the_c_abi():
+    """The parameter tensors Norm_Flow_structure hands to the fused kernel, concatenated in order, must fill exactly the
+    layout include/shwd.h documents (426 raw parameters and 102 power-iteration entries per Residual flow)."""
+    from shwd_b200 import _lib
+    from shwd_b200.losses import flows
+    lib = _lib.lib()
+    per, uvper = lib.shwd_resflow_params_per_layer(), lib.shwd_resflow_uv_per_layer()
+    assert (per, uvper) == (8 * 3 + 8 + 5 * (64 + 8) + 3 * 8 + 3 + 7, (8 + 3) + 5 * 16 + (3 + 8))
+    phi = L.Norm_Flow_structure(flow_name="Residual", n_flow_layer=3)
+    assert flows.is_standard_residual_stack(phi.net)
+    raw = []
+    for f in phi.net:
+        raw += flows._raw_params(f)
+    assert sum(p.numel() for p in raw) == 3 * per
+    assert {id(p) for p in raw} == {id(p) for p in phi.parameters()}  # every parameter, once
+    assert flows._uv_buffer(phi.net).numel() == 3 * uvper
+    assert lib.shwd_resflow_workspace_bytes(1000, 3) == (8 + 1) * 3 * per * 4
+    # non-standard shapes and Planar stacks stay on the eager modules
+    assert not flows.is_standard_residual_stack(L.Norm_Flow_structure(flow_name="Planar").net)
+    assert not flows.is_standard_residual_stack(L.Norm_Flow_structure_optuna(flow_name="Residual", Residual_hidden_units=4).net)
+    x = torch.randn(5, 3)
+    assert torch.equal(phi(x), phi.forward_eager(x))  # CPU tensors: the eager path
+
+
+def test_exact_solver_option_and_limits():
+    with pytest.raises(ValueError, match="solver must be"):
+        L.Cos_disimilarity_W("cpu", p=2, solver="simplex")
+    assert L.Geodesic_distance_W("cpu", p=2, solver="exact").solver == "exact"
+    from shwd_b200 import _lib
+    assert _lib.lib().shwd_exact_assignment_max_points() >= 2048
+    assert list(inspect.signature(L.binary_search_circle).parameters) == [
+        "u_values", "v_values", "u_weights", "v_weights", "p", "Lm", "Lp", "tm", "tp", "eps", "require_sort"]
