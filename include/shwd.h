@@ -157,6 +157,14 @@ int shwd_exact_assignment_max_points(void);
 int shwd_exact_assignment(const float* x4, const float* y4, int B, int N, int cost_kind, float p, float n_power, int* sigma,
                           double* prices, int* rounds, int* status, void* stream);
 
+/* ---- data side: random rigid transform (+ optional sensor noise) of a device-resident batch ---------------------------
+ * Replaces Dataset_Transformation.__call__ / create_pose_7d / qrot (data_utils/Data_set_maker.py:40-52,173-230), run by the
+ * reference per item on the CPU.  src, out (B,N,3); pose7 (B,7) = (un-normalised quaternion w,x,y,z | translation);
+ * rotation (B,3,3), nullable = igt_rotation.  noise_std > 0 adds N(0, noise_std^2) to src first (add_noise, :13-22), from a
+ * counter-based generator keyed by (seed, element). */
+int shwd_rigid_transform(const float* src, const float* pose7, int B, int N, float noise_std, unsigned long long seed,
+                         float* out, float* rotation, void* stream);
+
 /* ---- measurement helpers (bench.py): FP32-FMA and MUFU issue-rate microbenchmarks -------------------------------
  * out (grid*block floats) scratch; returns the number of lane-ops each launch performs in *ops. */
 int shwd_peak_fp32(float* out, int iters, double* ops, void* stream);

@@ -22,9 +22,10 @@ from .sliced import (project_circle, emd1d_circle, sliced_wasserstein_sphere_p1,
                      binary_search_circle, sliced_wasserstein_sphere)
 from .chamfer import chamfer_distance
 from .emd import exact_emd2
+from . import data
 
 __all__ = [
     "sphere_map", "flow_regularization", "cost_matrix", "COST_KINDS", "log_sinkhorn", "entropic_w",
     "project_circle", "emd1d_circle", "sliced_wasserstein_sphere_p1", "euclid_sliced_wasserstein",
-    "binary_search_circle", "sliced_wasserstein_sphere", "chamfer_distance", "exact_emd2",
+    "binary_search_circle", "sliced_wasserstein_sphere", "chamfer_distance", "exact_emd2", "data",
 ]

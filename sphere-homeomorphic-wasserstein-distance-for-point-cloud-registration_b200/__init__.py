@@ -4,11 +4,11 @@ The directory name carries hyphens (it mirrors the upstream repository name), so
 alias module at the repository root, or put this directory on ``sys.path`` and ``import losses`` for the drop-in
 replacement of the reference's ``losses`` package.
 """
-from . import _lib, ops
+from . import _lib, ops, data
 from .ops import (sphere_map, flow_regularization, entropic_ot, chamfer_nn, segmented_sort_raw, spherical_sliced_w1,
                   spherical_sliced_wp, euclid_sliced_w, exact_assignment, exact_emd2)
 
-__all__ = ["_lib", "ops", "sphere_map", "flow_regularization", "entropic_ot", "chamfer_nn", "segmented_sort_raw",
+__all__ = ["_lib", "ops", "data", "sphere_map", "flow_regularization", "entropic_ot", "chamfer_nn", "segmented_sort_raw",
            "spherical_sliced_w1", "spherical_sliced_wp", "euclid_sliced_w", "exact_assignment", "exact_emd2", "build_library"]
 
 

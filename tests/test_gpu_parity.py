@@ -792,3 +792,29 @@ def test_exact_solver_training_shape_properties(shwd):
     primal = torch.gather(C, 2, sig.unsqueeze(-1)).sum((1, 2))
     # (C here is torch's float32 evaluation; the kernel's differs by float32 rounding, ~1e-7 per entry)
     assert ((primal - dual).abs() <= 1e-6 * primal.abs()).all(), (primal, dual)
+
+
+# ------------------------------------------------------------------------------- data side: rigid transform (8f #3) ----
+def test_rigid_transform_matches_reference_fixture_and_oracle(shwd):
+    d = gold("rigid_transform")
+    src, poses = torch.from_numpy(d["src"]), torch.from_numpy(d["poses"])
+    out, rot, trans = shwd.data.rigid_transform(src.to(dev()), poses.to(dev()))
+    assert (out.cpu() - torch.from_numpy(d["out"])).abs().max().item() < 1e-6
+    assert (rot.cpu() - torch.from_numpy(d["igt_rotation"])).abs().max().item() < 1e-6
+    assert torch.equal(trans.cpu(), torch.from_numpy(d["igt_translation"]))
+    # larger batch against the oracle; R reproduces the transform; noise has the requested moments and is reproducible
+    g = torch.Generator().manual_seed(3)
+    big = torch.randn(64, 1000, 3, generator=g)
+    P = shwd.data.random_poses(64, 45, 1, np.random.RandomState(7))
+    o2, r2, t2 = shwd.data.rigid_transform(big.to(dev()), P)
+    ro, rr, rt = oracle.data.rigid_transform(big, P)
+    assert rel(o2, ro) < 1e-6 and rel(r2, rr) < 1e-6
+    assert rel(torch.einsum("bij,bnj->bni", r2.cpu(), big) + t2.cpu(), ro) < 1e-6
+    n1, _, _ = shwd.data.rigid_transform(big.to(dev()), P, noise_std=0.02, seed=5)
+    n2, _, _ = shwd.data.rigid_transform(big.to(dev()), P, noise_std=0.02, seed=5)
+    assert torch.equal(n1, n2)
+    resid = torch.einsum("bji,bnj->bni", r2, n1 - o2)  # rotate the residual back: the noise that was added to the source
+    assert abs(resid.mean().item()) < 5e-4 and resid.std().item() == pytest.approx(0.02, rel=0.02)
+    ds = shwd.data.DeviceRegistrationPairs(big.to(dev()), big.to(dev()), seed=11)
+    tgt, srcs, R, T = ds.batch([3, 1, 4])
+    assert tgt.shape == (3, 1000, 3) and srcs.shape == (3, 1000, 3) and R.shape == (3, 3, 3) and T.shape == (3, 1, 3)

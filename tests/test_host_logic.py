@@ -181,3 +181,14 @@ def test_exact_solver_option_and_limits():
     assert _lib.lib().shwd_exact_assignment_max_points() >= 2048
     assert list(inspect.signature(L.binary_search_circle).parameters) == [
         "u_values", "v_values", "u_weights", "v_weights", "p", "Lm", "Lp", "tm", "tp", "eps", "require_sort"]
+
+
+def test_pose_generator_consumes_numpy_like_the_reference():
+    """shwd.data.random_poses against the frozen reference poses (numpy seed 1234, tests/golden/make_golden_data.py)."""
+    import numpy as np
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "rigid_transform.npz"))
+    poses = shwd.data.random_poses(d["poses"].shape[0], 45, 1, np.random.RandomState(1234))
+    assert np.array_equal(poses.numpy(), d["poses"])
+    assert np.allclose(shwd.data.euler_to_quaternion_xyz(d["euler_in"]), d["euler_quat"], rtol=0, atol=1e-15)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        shwd.data.rigid_transform(torch.zeros(1, 4, 3), poses[:1])
