@@ -297,90 +297,129 @@ __device__ __forceinline__ float block_sum_f32(float v, float* wtot) {
   return t;
 }
 
-// One CTA per slice.  us (n), vs (m) sorted ascending.  Follows emd1D_circle :230-247 step by step:
+// Fixed-order block sum (all threads get the result).
+__device__ __forceinline__ float block_sum_bcast(float v, float* wtot) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < SORT_WARPS; ++w) t += wtot[w];
+  return t;
+}
+
+constexpr int CW1_PER_THREAD = 40;  // merged entries per thread (n + m <= 256 * 40 = 10240)
+
+// One CTA per slice.  us (n), vs (m) sorted ascending.  Follows emd1D_circle :230-247:
 //   merged = stable merge of (us, vs)  [== sort(cat(us, vs))],  w = +1/n for u entries, -1/m for v entries
 //   F = cumsum(w);  delta_k = merged_{k+1} - merged_k, last = 1 - merged_last   (the arc [0, first) is omitted)
 //   level median: sort F, cw = cumsum(delta[perm]) - 0.5, first k with cw >= 0 -> med = F_sorted[k]
 //   W = sum_k delta_k |F_k - med|;   dW/dmerged_k = |F_{k-1} - med| - |F_k - med|  (F_{-1} term = 0)
+// Nothing is sorted here.  The merge is a merge-path: thread t owns the merged positions [t*c, (t+1)*c), finds its split
+// of (us, vs) with one binary search along the diagonal and merges sequentially.  The level median is a SELECTION: med is
+// the smallest F value f with  sum_{k: F_k <= f} delta_k >= 0.5  (the cumulative sum over the sorted order first reaches
+// 0.5 inside the run of entries equal to f), found by bisection on the 32-bit order-preserving key of F -- 32 rounds of a
+// register-resident partial sum + a fixed-order block reduction -- instead of a radix sort of n + m records.
 __global__ void __launch_bounds__(SORT_THREADS) circular_w1_kernel(const float* __restrict__ us, const float* __restrict__ vs,
                                                                    int n, int m, float* __restrict__ w_out,
                                                                    float* __restrict__ gus, float* __restrict__ gvs) {
-  extern __shared__ uint2 sbuf[];
-  __shared__ uint32_t hist[SORT_WARPS * 256];
-  __shared__ uint32_t wt[SORT_WARPS];
+  extern __shared__ float cw1_smem[];
   __shared__ float wf[SORT_WARPS];
-  __shared__ int s_k;
   const int nm = n + m;
-  uint2* a = sbuf;
-  uint2* b = sbuf + nm;
-  float* vals = reinterpret_cast<float*>(sbuf + 2 * (size_t)nm);
-  float* F = vals + nm;
+  float* su = cw1_smem;          // n
+  float* sv = su + n;            // m
+  float* vals = sv + m;          // nm   merged values
+  float* F = vals + nm;          // nm   +-w, then its inclusive scan
+  int* src = reinterpret_cast<int*>(F + nm);  // nm   origin of merged entry: i (u) or n + j (v)
   const size_t s = blockIdx.x;
-  const float* u = us + s * n;
-  const float* v = vs + s * m;
   const float wu = 1.f / n, wv = 1.f / m;
-
-  // stable merge by rank: u_i lands at i + #{v < u_i}; v_j at j + #{u <= v_j}
-  for (int i = threadIdx.x; i < nm; i += SORT_THREADS) {
-    const bool isu = i < n;
-    const float x = isu ? __ldg(u + i) : __ldg(v + i - n);
-    const float* o = isu ? v : u;
-    const int on = isu ? m : n;
-    int lo = 0, hi = on;
+  for (int i = threadIdx.x; i < n; i += SORT_THREADS) su[i] = __ldg(us + s * n + i);
+  for (int j = threadIdx.x; j < m; j += SORT_THREADS) sv[j] = __ldg(vs + s * m + j);
+  __syncthreads();
+  // ---- merge path: u goes first on ties (u_i lands at i + #{v < u_i}; v_j at j + #{u <= v_j})
+  const int c = (nm + SORT_THREADS - 1) / SORT_THREADS;
+  const int d0 = min(nm, (int)threadIdx.x * c), d1 = min(nm, d0 + c);
+  {
+    int lo = max(0, d0 - m), hi = min(d0, n);  // i = #u entries among the first d0 merged ones
     while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      const float y = __ldg(o + mid);
-      const bool before = isu ? (y < x) : (y <= x);
-      if (before) lo = mid + 1; else hi = mid;
+      const int i = (lo + hi) >> 1;  // take i u-entries, d0 - i v-entries: valid iff u[i] > v[d0 - i - 1] ... shrink
+      if (su[i] <= sv[d0 - i - 1]) lo = i + 1; else hi = i;
     }
-    const int pos = (isu ? i : i - n) + lo;
-    vals[pos] = x;
-    F[pos] = isu ? wu : -wv;
+    int i = lo, j = d0 - lo;
+    for (int k = d0; k < d1; ++k) {
+      const bool take_u = (j >= m) || (i < n && su[i] <= sv[j]);
+      if (take_u) {
+        vals[k] = su[i];
+        F[k] = wu;
+        src[k] = i++;
+      } else {
+        vals[k] = sv[j];
+        F[k] = -wv;
+        src[k] = n + j++;
+      }
+    }
   }
   __syncthreads();
   block_inclusive_scan_f32(F, nm, wf);
-  // records (sort key of F_k, delta_k): the level-median sort carries delta as its payload
-  for (int k = threadIdx.x; k < nm; k += SORT_THREADS) {
-    const float d = ((k + 1 < nm) ? vals[k + 1] : 1.f) - vals[k];
-    a[k] = make_uint2(float_sort_key(F[k]), __float_as_uint(d));
+  // ---- this thread's (key(F_k), delta_k) pairs, strided over the merged order, in registers
+  uint32_t key[CW1_PER_THREAD];
+  float dl[CW1_PER_THREAD];
+  float tot = 0.f;
+  uint32_t kmin = 0xFFFFFFFFu;
+#pragma unroll
+  for (int q = 0; q < CW1_PER_THREAD; ++q) {
+    const int k = threadIdx.x + q * SORT_THREADS;
+    key[q] = 0xFFFFFFFFu;
+    dl[q] = 0.f;
+    if (k < nm) {
+      key[q] = float_sort_key(F[k]);
+      dl[q] = ((k + 1 < nm) ? vals[k + 1] : 1.f) - vals[k];
+      kmin = min(kmin, key[q]);
+    }
+    tot += dl[q];
   }
-  __syncthreads();
-  uint2* r = block_radix_sort(a, b, nm, hist, wt);
-  // cw = cumsum(delta in sorted-F order) - 0.5; first k with cw >= 0 (merged values are dead: reuse `vals`)
-  for (int k = threadIdx.x; k < nm; k += SORT_THREADS) vals[k] = __uint_as_float(r[k].y);
-  if (threadIdx.x == 0) s_k = nm;
-  __syncthreads();
-  block_inclusive_scan_f32(vals, nm, wf);
-  for (int k = threadIdx.x; k < nm; k += SORT_THREADS)
-    if (vals[k] - 0.5f >= 0.f) atomicMin(&s_k, k);
-  __syncthreads();
-  const int kk = (s_k >= nm) ? 0 : s_k;
-  const float med = float_from_sort_key(r[kk].x);
+  tot = block_sum_bcast(tot, wf);
+  uint32_t kmed;
+  if (tot - 0.5f >= 0.f) {
+    // smallest key K with sum_{key <= K} delta - 0.5 >= 0
+    uint32_t lo = 0u, hi = 0xFFFFFFFFu;
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      float part = 0.f;
+#pragma unroll
+      for (int q = 0; q < CW1_PER_THREAD; ++q) part += (key[q] <= mid) ? dl[q] : 0.f;
+      part = block_sum_bcast(part, wf);
+      if (part - 0.5f >= 0.f) hi = mid; else lo = mid + 1u;
+    }
+    kmed = lo;
+  } else {
+    // the cumulative sum never reaches 0.5 (all cw < 0 -> all inf -> argmin = 0): the smallest F
+    for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    __shared__ uint32_t s_kmin[SORT_WARPS];
+    if ((threadIdx.x & 31) == 0) s_kmin[threadIdx.x >> 5] = kmin;
+    __syncthreads();
+    kmed = s_kmin[0];
+#pragma unroll
+    for (int w = 1; w < SORT_WARPS; ++w) kmed = min(kmed, s_kmin[w]);
+  }
+  const float med = float_from_sort_key(kmed);
   float acc = 0.f;
-  for (int k = threadIdx.x; k < nm; k += SORT_THREADS)
-    acc += __uint_as_float(r[k].y) * fabsf(float_from_sort_key(r[k].x) - med);
-  acc = block_sum_f32(acc, wf);
+#pragma unroll
+  for (int q = 0; q < CW1_PER_THREAD; ++q) {
+    const int k = threadIdx.x + q * SORT_THREADS;
+    if (k < nm) acc += dl[q] * fabsf(F[k] - med);
+  }
+  acc = block_sum_bcast(acc, wf);
   if (threadIdx.x == 0) w_out[s] = acc;
   if (gus || gvs) {
-    // gradient w.r.t. merged values, routed back to u_i / v_j by recomputing each entry's merged position
-    for (int i = threadIdx.x; i < nm; i += SORT_THREADS) {
-      const bool isu = i < n;
-      const float x = isu ? __ldg(u + i) : __ldg(v + i - n);
-      const float* o = isu ? v : u;
-      const int on = isu ? m : n;
-      int lo = 0, hi = on;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const float y = __ldg(o + mid);
-        const bool before = isu ? (y < x) : (y <= x);
-        if (before) lo = mid + 1; else hi = mid;
-      }
-      const int pos = (isu ? i : i - n) + lo;
-      const float g = ((pos > 0) ? fabsf(F[pos - 1] - med) : 0.f) - fabsf(F[pos] - med);
-      if (isu) {
-        if (gus) gus[s * n + i] = g;
-      } else {
-        if (gvs) gvs[s * m + i - n] = g;
+    for (int k = threadIdx.x; k < nm; k += SORT_THREADS) {
+      const float g = ((k > 0) ? fabsf(F[k - 1] - med) : 0.f) - fabsf(F[k] - med);
+      const int o = src[k];
+      if (o < n) {
+        if (gus) gus[s * n + o] = g;
+      } else if (gvs) {
+        gvs[s * m + o - n] = g;
       }
     }
   }
@@ -484,7 +523,7 @@ extern "C" size_t shwd_circular_w1_workspace_bytes(int S, int n, int m) {
   (void)S;
   (void)n;
   (void)m;
-  return 0;  // everything lives in shared memory (n + m <= 8192)
+  return 0;  // everything lives in shared memory / registers (n + m <= 10240)
 }
 
 extern "C" int shwd_circular_w1(const float* us, const float* vs, int S, int n, int m, float* w, float* gus, float* gvs,
@@ -494,8 +533,8 @@ extern "C" int shwd_circular_w1(const float* us, const float* vs, int S, int n, 
   if (!us || !vs || !w || S < 0 || n <= 0 || m <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (S == 0) return SHWD_OK;
   const size_t nm = (size_t)n + m;
-  const size_t smem = nm * (2 * sizeof(uint2) + 2 * sizeof(float));
-  if (smem > 216 * 1024) return SHWD_ERR_UNSUPPORTED;  // n + m <= 9216; larger slices: see DESIGN.md
+  const size_t smem = nm * (3 * sizeof(float) + sizeof(int));
+  if (nm > (size_t)SORT_THREADS * CW1_PER_THREAD) return SHWD_ERR_UNSUPPORTED;  // n + m <= 10240 (register-resident selection)
   if (smem > 48 * 1024)
     SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_w1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   circular_w1_kernel<<<S, SORT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(us, vs, n, m, w, gus, gvs);
