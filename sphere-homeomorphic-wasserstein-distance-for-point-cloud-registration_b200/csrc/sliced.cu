@@ -167,6 +167,27 @@ __device__ __forceinline__ uint32_t block_exscan_u32(uint32_t v, uint32_t* warp_
   return base + inc - v;
 }
 
+// Lanes holding the same 9-bit value (8-bit digit + "invalid" flag), from nine ballots.  __match_any_sync gives the same mask
+// but is microcoded on sm_100 (hundreds of cycles on the ADU pipe: it made this kernel ADU-bound, ncu 84 % busy).
+__device__ __forceinline__ uint32_t match_digit(uint32_t d9) {
+  uint32_t peers = 0xffffffffu;
+#pragma unroll
+  for (int bit = 0; bit < 9; ++bit) {
+    const bool on = (d9 >> bit) & 1u;
+    const uint32_t m = __ballot_sync(0xffffffffu, on);
+    peers &= on ? m : ~m;
+  }
+  return peers;
+}
+
+// shared-memory store under a predicate, without a branch
+__device__ __forceinline__ void st_shared_if(uint32_t* p, uint32_t v, bool pred) {
+  asm volatile(
+      "{ .reg .pred q; .reg .u64 sa; setp.ne.s32 q, %2, 0; cvta.to.shared.u64 sa, %0; @q st.shared.u32 [sa], %1; }" ::"l"(p), "r"(v),
+      "r"((int)pred)
+      : "memory");
+}
+
 // Stable LSD radix sort of n (key, index) records: a -> ... -> result pointer returned (either a or b).
 // a, b may live in shared or global memory.  hist: SORT_WARPS*256 words of shared memory; wt: SORT_WARPS words.
 __device__ uint2* block_radix_sort(uint2* a, uint2* b, int n, uint32_t* hist, uint32_t* wt) {
@@ -179,12 +200,16 @@ __device__ uint2* block_radix_sort(uint2* a, uint2* b, int n, uint32_t* hist, ui
     for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) hist[i] = 0;
     __syncthreads();
     uint32_t* wh = hist + warp * 256;
+    // The per-warp digit counters are read by every lane and advanced by the leader of each match group with a PREDICATED
+    // store: no divergent branch inside the batch loops (branch / reconvergence bookkeeping runs on the ADU pipe, which
+    // was the busiest unit of this kernel), one __syncwarp per batch orders the store against the next batch's reads.
     for (int i0 = beg; i0 < end; i0 += 32) {
       const int i = i0 + lane;
       const bool valid = i < end;
-      const uint32_t d = valid ? ((a[i].x >> sh) & 255u) : 0xFFFFu;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      if (valid && (peers & lt) == 0) wh[d] += __popc(peers);
+      const uint32_t d = valid ? ((a[i].x >> sh) & 255u) : 256u;
+      const uint32_t peers = match_digit(d);
+      const uint32_t cur = wh[d & 255u];
+      st_shared_if(wh + (d & 255u), cur + __popc(peers), valid && (peers & lt) == 0);
       __syncwarp();
     }
     __syncthreads();
@@ -206,16 +231,12 @@ __device__ uint2* block_radix_sort(uint2* a, uint2* b, int n, uint32_t* hist, ui
     for (int i0 = beg; i0 < end; i0 += 32) {
       const int i = i0 + lane;
       const bool valid = i < end;
-      uint2 rec = valid ? a[i] : make_uint2(0u, 0u);
-      const uint32_t d = valid ? ((rec.x >> sh) & 255u) : 0xFFFFu;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      uint32_t pos = 0;
-      if (valid) pos = wh[d] + __popc(peers & lt);
-      __syncwarp();
-      if (valid) {
-        b[pos] = rec;
-        if ((peers & lt) == 0) wh[d] += __popc(peers);
-      }
+      const uint2 rec = valid ? a[i] : make_uint2(0u, 0u);
+      const uint32_t d = valid ? ((rec.x >> sh) & 255u) : 256u;
+      const uint32_t peers = match_digit(d);
+      const uint32_t cur = wh[d & 255u];
+      if (valid) b[cur + __popc(peers & lt)] = rec;
+      st_shared_if(wh + (d & 255u), cur + __popc(peers), valid && (peers & lt) == 0);
       __syncwarp();
     }
     __syncthreads();
