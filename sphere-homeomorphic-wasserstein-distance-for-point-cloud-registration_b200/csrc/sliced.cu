@@ -169,13 +169,14 @@ __device__ __forceinline__ uint32_t block_exscan_u32(uint32_t v, uint32_t* warp_
 
 // Lanes holding the same 9-bit value (8-bit digit + "invalid" flag), from nine ballots.  __match_any_sync gives the same mask
 // but is microcoded on sm_100 (hundreds of cycles on the ADU pipe: it made this kernel ADU-bound, ncu 84 % busy).
-__device__ __forceinline__ uint32_t match_digit(uint32_t d9) {
+template <int BITS>
+__device__ __forceinline__ uint32_t match_digit(uint32_t d) {
   uint32_t peers = 0xffffffffu;
 #pragma unroll
-  for (int bit = 0; bit < 9; ++bit) {
-    const bool on = (d9 >> bit) & 1u;
-    const uint32_t m = __ballot_sync(0xffffffffu, on);
-    peers &= on ? m : ~m;
+  for (int bit = 0; bit < BITS; ++bit) {
+    const uint32_t on = (d >> bit) & 1u;
+    const uint32_t m = __ballot_sync(0xffffffffu, on != 0u);
+    peers &= m ^ (on - 1u);  // on ? m : ~m
   }
   return peers;
 }
@@ -203,15 +204,8 @@ __device__ uint2* block_radix_sort(uint2* a, uint2* b, int n, uint32_t* hist, ui
     // The per-warp digit counters are read by every lane and advanced by the leader of each match group with a PREDICATED
     // store: no divergent branch inside the batch loops (branch / reconvergence bookkeeping runs on the ADU pipe, which
     // was the busiest unit of this kernel), one __syncwarp per batch orders the store against the next batch's reads.
-    for (int i0 = beg; i0 < end; i0 += 32) {
-      const int i = i0 + lane;
-      const bool valid = i < end;
-      const uint32_t d = valid ? ((a[i].x >> sh) & 255u) : 256u;
-      const uint32_t peers = match_digit(d);
-      const uint32_t cur = wh[d & 255u];
-      st_shared_if(wh + (d & 255u), cur + __popc(peers), valid && (peers & lt) == 0);
-      __syncwarp();
-    }
+    // counting needs no order: shared-memory atomics on the warp's private histogram
+    for (int i = beg + lane; i < end; i += 32) atomicAdd(wh + ((a[i].x >> sh) & 255u), 1u);
     __syncthreads();
     {
       // digit-major exclusive offsets: thread d owns digit d
@@ -233,7 +227,7 @@ __device__ uint2* block_radix_sort(uint2* a, uint2* b, int n, uint32_t* hist, ui
       const bool valid = i < end;
       const uint2 rec = valid ? a[i] : make_uint2(0u, 0u);
       const uint32_t d = valid ? ((rec.x >> sh) & 255u) : 256u;
-      const uint32_t peers = match_digit(d);
+      const uint32_t peers = (i0 + 32 <= end) ? match_digit<8>(d) : match_digit<9>(d);  // full batches need no "invalid" bit
       const uint32_t cur = wh[d & 255u];
       if (valid) b[cur + __popc(peers & lt)] = rec;
       st_shared_if(wh + (d & 255u), cur + __popc(peers), valid && (peers & lt) == 0);
