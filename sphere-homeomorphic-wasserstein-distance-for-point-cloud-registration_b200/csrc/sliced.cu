@@ -47,44 +47,62 @@ __global__ void __launch_bounds__(PJ_THREADS) project_circle_kernel(const float*
 }
 
 // gx[b,n,:] = sum_p gk[b,p,n] * ( dt/da * U[p,:,0] + dt/dc * U[p,:,1] ),  dt/da = -c / (2 pi r^2), dt/dc = a / (2 pi r^2)
+// A CTA owns 32 consecutive points (lane = point); its 8 warps split the slices (warp w takes p = w, w + 8, ...), so a row
+// read is one 128-B line per warp and B * N / 32 CTAs x 8 independent load streams are in flight (the first version walked
+// all P slices sequentially in one thread per point: 128 CTAs, latency-bound, 250 us at cfg3).  The 8 partial sums are
+// added in warp order through shared memory (deterministic).
+constexpr int PB_WARPS = PJ_THREADS / 32;
+constexpr int PB_TILE = 256;  // slices staged per tile
+
 __global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd_kernel(const float* __restrict__ x, const float* __restrict__ U,
                                                                         int N, int P, const float* __restrict__ gk,
                                                                         float* __restrict__ gx) {
-  extern __shared__ float sU[];  // P * 6 (tiled)
+  __shared__ float sU[PB_TILE * 6];
+  __shared__ float red[PB_WARPS][3][32];
   const int b = blockIdx.y;
-  const int n = blockIdx.x * PJ_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const bool ok = n < N;
   float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-  if (n < N) {
+  if (ok) {
     const float* xp = x + ((size_t)b * N + n) * 3;
     x0 = __ldg(xp);
     x1 = __ldg(xp + 1);
     x2 = __ldg(xp + 2);
   }
+  const float* gkb = gk + (size_t)b * P * N + (ok ? n : 0);
   float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-  for (int p0 = 0; p0 < P; p0 += 256) {
-    const int pc = min(256, P - p0);
+  for (int p0 = 0; p0 < P; p0 += PB_TILE) {
+    const int pc = min(PB_TILE, P - p0);
     __syncthreads();
     for (int i = threadIdx.x; i < pc * 6; i += PJ_THREADS) sU[i] = __ldg(U + (size_t)p0 * 6 + i);
     __syncthreads();
-    if (n < N) {
-      for (int p = 0; p < pc; ++p) {
-        const float* u = sU + p * 6;
-        float a = fmaf(u[4], x2, fmaf(u[2], x1, u[0] * x0));
-        float c = fmaf(u[5], x2, fmaf(u[3], x1, u[1] * x0));
-        float r2 = fmaxf(fmaf(c, c, a * a), 1e-24f);
-        float g = __ldg(gk + ((size_t)b * P + p0 + p) * N + n) / (TWO_PI_F * r2);
-        float ta = -c * g, tc = a * g;
-        g0 = fmaf(ta, u[0], fmaf(tc, u[1], g0));
-        g1 = fmaf(ta, u[2], fmaf(tc, u[3], g1));
-        g2 = fmaf(ta, u[4], fmaf(tc, u[5], g2));
-      }
+#pragma unroll 4
+    for (int p = warp; p < pc; p += PB_WARPS) {
+      const float* u = sU + p * 6;
+      const float gkv = ok ? __ldg(gkb + (size_t)(p0 + p) * N) : 0.f;
+      float a = fmaf(u[4], x2, fmaf(u[2], x1, u[0] * x0));
+      float c = fmaf(u[5], x2, fmaf(u[3], x1, u[1] * x0));
+      float r2 = fmaxf(fmaf(c, c, a * a), 1e-24f);
+      float g = gkv / (TWO_PI_F * r2);
+      float ta = -c * g, tc = a * g;
+      g0 = fmaf(ta, u[0], fmaf(tc, u[1], g0));
+      g1 = fmaf(ta, u[2], fmaf(tc, u[3], g1));
+      g2 = fmaf(ta, u[4], fmaf(tc, u[5], g2));
     }
   }
-  if (n < N) {
-    float* o = gx + ((size_t)b * N + n) * 3;
-    o[0] = g0;
-    o[1] = g1;
-    o[2] = g2;
+  red[warp][0][lane] = g0;
+  red[warp][1][lane] = g1;
+  red[warp][2][lane] = g2;
+  __syncthreads();
+  if (threadIdx.x < 96) {  // output element (point pt, component k) of this CTA's contiguous 96-float span
+    const int pt = threadIdx.x / 3, k = threadIdx.x - pt * 3;
+    if (blockIdx.x * 32 + pt < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < PB_WARPS; ++w) t += red[w][k][pt];
+      gx[((size_t)b * N + blockIdx.x * 32) * 3 + threadIdx.x] = t;
+    }
   }
 }
 
@@ -107,29 +125,39 @@ __global__ void __launch_bounds__(PJ_THREADS) project_line_kernel(const float* _
 
 __global__ void __launch_bounds__(PJ_THREADS) project_line_bwd_kernel(const float* __restrict__ th, int N, int P,
                                                                       const float* __restrict__ gk, float* __restrict__ gx) {
-  extern __shared__ float sT[];
+  __shared__ float sT[PB_TILE * 3];
+  __shared__ float red[PB_WARPS][3][32];
   const int b = blockIdx.y;
-  const int n = blockIdx.x * PJ_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const bool ok = n < N;
+  const float* gkb = gk + (size_t)b * P * N + (ok ? n : 0);
   float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-  for (int p0 = 0; p0 < P; p0 += 256) {
-    const int pc = min(256, P - p0);
+  for (int p0 = 0; p0 < P; p0 += PB_TILE) {
+    const int pc = min(PB_TILE, P - p0);
     __syncthreads();
     for (int i = threadIdx.x; i < pc * 3; i += PJ_THREADS) sT[i] = __ldg(th + (size_t)p0 * 3 + i);
     __syncthreads();
-    if (n < N) {
-      for (int p = 0; p < pc; ++p) {
-        float g = __ldg(gk + ((size_t)b * P + p0 + p) * N + n);
-        g0 = fmaf(g, sT[p * 3], g0);
-        g1 = fmaf(g, sT[p * 3 + 1], g1);
-        g2 = fmaf(g, sT[p * 3 + 2], g2);
-      }
+#pragma unroll 4
+    for (int p = warp; p < pc; p += PB_WARPS) {
+      const float g = ok ? __ldg(gkb + (size_t)(p0 + p) * N) : 0.f;
+      g0 = fmaf(g, sT[p * 3], g0);
+      g1 = fmaf(g, sT[p * 3 + 1], g1);
+      g2 = fmaf(g, sT[p * 3 + 2], g2);
     }
   }
-  if (n < N) {
-    float* o = gx + ((size_t)b * N + n) * 3;
-    o[0] = g0;
-    o[1] = g1;
-    o[2] = g2;
+  red[warp][0][lane] = g0;
+  red[warp][1][lane] = g1;
+  red[warp][2][lane] = g2;
+  __syncthreads();
+  if (threadIdx.x < 96) {
+    const int pt = threadIdx.x / 3, k = threadIdx.x - pt * 3;
+    if (blockIdx.x * 32 + pt < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < PB_WARPS; ++w) t += red[w][k][pt];
+      gx[((size_t)b * N + blockIdx.x * 32) * 3 + threadIdx.x] = t;
+    }
   }
 }
 
@@ -326,75 +354,141 @@ __device__ __forceinline__ float block_sum_bcast(float v, float* wtot) {
 
 constexpr int CW1_PER_THREAD = 40;  // merged entries per thread (n + m <= 256 * 40 = 10240)
 
+// Fixed-order block sum with ONE barrier: the per-warp partials ping-pong between two shared-memory rows.
+__device__ __forceinline__ float block_sum_pp(float v, float (*wf)[SORT_WARPS], int& phase) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) wf[phase][threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < SORT_WARPS; ++w) t += wf[phase][w];
+  phase ^= 1;
+  return t;
+}
+
+// shared-memory index with one pad word per 32: the merge walks su / sv at a lane stride of ~c/2 words, which without the
+// pad lands every lane of a warp in one or two banks
+__host__ __device__ __forceinline__ int cw1_pad(int i) { return i + (i >> 5); }
+
 // One CTA per slice.  us (n), vs (m) sorted ascending.  Follows emd1D_circle :230-247:
 //   merged = stable merge of (us, vs)  [== sort(cat(us, vs))],  w = +1/n for u entries, -1/m for v entries
 //   F = cumsum(w);  delta_k = merged_{k+1} - merged_k, last = 1 - merged_last   (the arc [0, first) is omitted)
 //   level median: sort F, cw = cumsum(delta[perm]) - 0.5, first k with cw >= 0 -> med = F_sorted[k]
 //   W = sum_k delta_k |F_k - med|;   dW/dmerged_k = |F_{k-1} - med| - |F_k - med|  (F_{-1} term = 0)
 // Nothing is sorted here.  The merge is a merge-path: thread t owns the merged positions [t*c, (t+1)*c), finds its split
-// of (us, vs) with one binary search along the diagonal and merges sequentially.  The level median is a SELECTION: med is
-// the smallest F value f with  sum_{k: F_k <= f} delta_k >= 0.5  (the cumulative sum over the sorted order first reaches
-// 0.5 inside the run of entries equal to f), found by bisection on the 32-bit order-preserving key of F -- 32 rounds of a
+// of (us, vs) with one binary search along the diagonal and merges sequentially -- INTO REGISTERS: a thread keeps
+// (key(F_k), delta_k) of its own c entries plus a bit mask of which came from u, so the merged values, F and the origin
+// array never exist in shared memory (the first version wrote them at a lane stride of c words, a 32-way bank conflict,
+// and its 16 (n+m) bytes of shared memory allowed one CTA per SM; now 4 (n+m) bytes and two CTAs per SM).  F's scan uses
+// the same chunking (thread-sequential, block scan of the chunk totals).  The level median is a SELECTION: med is the
+// smallest F value f with  sum_{k: F_k <= f} delta_k >= 0.5  (the cumulative sum over the sorted order first reaches 0.5
+// inside the run of entries equal to f), found by bisection on the 32-bit order-preserving key of F -- 32 rounds of a
 // register-resident partial sum + a fixed-order block reduction -- instead of a radix sort of n + m records.
-__global__ void __launch_bounds__(SORT_THREADS) circular_w1_kernel(const float* __restrict__ us, const float* __restrict__ vs,
-                                                                   int n, int m, float* __restrict__ w_out,
-                                                                   float* __restrict__ gus, float* __restrict__ gvs) {
+template <int C>
+__global__ void __launch_bounds__(SORT_THREADS, (C <= 32 ? 2 : 1))
+    circular_w1_kernel(const float* __restrict__ us, const float* __restrict__ vs, int n, int m, float* __restrict__ w_out,
+                       float* __restrict__ gus, float* __restrict__ gvs) {
   extern __shared__ float cw1_smem[];
-  __shared__ float wf[SORT_WARPS];
+  __shared__ float wf[2][SORT_WARPS];
+  __shared__ float s_first[SORT_THREADS];  // first merged value of each thread's chunk
+  __shared__ float s_lastF[SORT_THREADS];  // F at the last entry of each thread's chunk
+  __shared__ uint32_t s_kmin[SORT_WARPS];
   const int nm = n + m;
-  float* su = cw1_smem;          // n
-  float* sv = su + n;            // m
-  float* vals = sv + m;          // nm   merged values
-  float* F = vals + nm;          // nm   +-w, then its inclusive scan
-  int* src = reinterpret_cast<int*>(F + nm);  // nm   origin of merged entry: i (u) or n + j (v)
+  float* su = cw1_smem;                 // n (padded)
+  float* sv = su + cw1_pad(n - 1) + 1;  // m (padded)
   const size_t s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float wu = 1.f / n, wv = 1.f / m;
-  for (int i = threadIdx.x; i < n; i += SORT_THREADS) su[i] = __ldg(us + s * n + i);
-  for (int j = threadIdx.x; j < m; j += SORT_THREADS) sv[j] = __ldg(vs + s * m + j);
+  for (int i = tid; i < n; i += SORT_THREADS) su[cw1_pad(i)] = __ldg(us + s * n + i);
+  for (int j = tid; j < m; j += SORT_THREADS) sv[cw1_pad(j)] = __ldg(vs + s * m + j);
   __syncthreads();
   // ---- merge path: u goes first on ties (u_i lands at i + #{v < u_i}; v_j at j + #{u <= v_j})
-  const int c = (nm + SORT_THREADS - 1) / SORT_THREADS;
-  const int d0 = min(nm, (int)threadIdx.x * c), d1 = min(nm, d0 + c);
+  const int c = (nm + SORT_THREADS - 1) / SORT_THREADS;  // <= C
+  const int d0 = min(nm, tid * c), d1 = min(nm, d0 + c);
+  const int cnt = d1 - d0;
+  int i0, j0;
   {
     int lo = max(0, d0 - m), hi = min(d0, n);  // i = #u entries among the first d0 merged ones
     while (lo < hi) {
-      const int i = (lo + hi) >> 1;  // take i u-entries, d0 - i v-entries: valid iff u[i] > v[d0 - i - 1] ... shrink
-      if (su[i] <= sv[d0 - i - 1]) lo = i + 1; else hi = i;
+      const int i = (lo + hi) >> 1;
+      if (su[cw1_pad(i)] <= sv[cw1_pad(d0 - i - 1)]) lo = i + 1; else hi = i;
     }
-    int i = lo, j = d0 - lo;
-    for (int k = d0; k < d1; ++k) {
-      const bool take_u = (j >= m) || (i < n && su[i] <= sv[j]);
-      if (take_u) {
-        vals[k] = su[i];
-        F[k] = wu;
-        src[k] = i++;
-      } else {
-        vals[k] = sv[j];
-        F[k] = -wv;
-        src[k] = n + j++;
+    i0 = lo;
+    j0 = d0 - lo;
+  }
+  uint32_t key[C];  // first the merged value bits, later key(F_k)
+  float dl[C];
+  uint64_t from_u = 0ull;
+  float wsum = 0.f;  // chunk total of +-w, summed in merged order
+  {
+    int i = i0, j = j0;
+    float cu = (i < n) ? su[cw1_pad(i)] : 0.f, cv = (j < m) ? sv[cw1_pad(j)] : 0.f;
+    float prev = 0.f;
+#pragma unroll
+    for (int q = 0; q < C; ++q) {
+      dl[q] = 0.f;
+      if (q < cnt) {
+        const bool take_u = (j >= m) || (i < n && cu <= cv);
+        const float v = take_u ? cu : cv;
+        if (take_u) {
+          from_u |= 1ull << q;
+          wsum += wu;
+          ++i;
+          if (i < n) cu = su[cw1_pad(i)];
+        } else {
+          wsum -= wv;
+          ++j;
+          if (j < m) cv = sv[cw1_pad(j)];
+        }
+        if (q == 0) s_first[tid] = v;
+        if (q > 0) dl[q - 1] = v - prev;
+        prev = v;
       }
     }
+    // the last delta of the chunk needs the next chunk's first value: parked in key[] until the exchange below
+    key[0] = __float_as_uint(prev);
   }
-  __syncthreads();
-  block_inclusive_scan_f32(F, nm, wf);
-  // ---- this thread's (key(F_k), delta_k) pairs, strided over the merged order, in registers
-  uint32_t key[CW1_PER_THREAD];
-  float dl[CW1_PER_THREAD];
+  // ---- exclusive block scan of the chunk totals (same association as a thread-sequential scan of F)
+  float base;
+  {
+    float inc = wsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wf[0][warp] = inc;
+    __syncthreads();  // also publishes s_first
+    float wb = 0.f;
+    for (int w = 0; w < warp; ++w) wb += wf[0][w];
+    base = wb + inc - wsum;
+  }
+  if (cnt > 0) {
+    const float last = __uint_as_float(key[0]);
+    const float nxt = (d1 < nm) ? s_first[tid + 1] : 1.f;
+#pragma unroll
+    for (int q = 0; q < C; ++q)
+      if (q == cnt - 1) dl[q] = nxt - last;
+  }
   float tot = 0.f;
   uint32_t kmin = 0xFFFFFFFFu;
+  {
+    float run = base;
 #pragma unroll
-  for (int q = 0; q < CW1_PER_THREAD; ++q) {
-    const int k = threadIdx.x + q * SORT_THREADS;
-    key[q] = 0xFFFFFFFFu;
-    dl[q] = 0.f;
-    if (k < nm) {
-      key[q] = float_sort_key(F[k]);
-      dl[q] = ((k + 1 < nm) ? vals[k + 1] : 1.f) - vals[k];
-      kmin = min(kmin, key[q]);
+    for (int q = 0; q < C; ++q) {
+      key[q] = 0xFFFFFFFFu;
+      if (q < cnt) {
+        run += ((from_u >> q) & 1ull) ? wu : -wv;
+        key[q] = float_sort_key(run);
+        kmin = min(kmin, key[q]);
+      }
+      tot += dl[q];
     }
-    tot += dl[q];
+    s_lastF[tid] = run;
   }
-  tot = block_sum_bcast(tot, wf);
+  __syncthreads();  // wf[0] read by everyone before block_sum_pp reuses it; publishes s_lastF
+  int phase = 1;
+  tot = block_sum_pp(tot, wf, phase);
   uint32_t kmed;
   if (tot - 0.5f >= 0.f) {
     // smallest key K with sum_{key <= K} delta - 0.5 >= 0
@@ -403,41 +497,56 @@ __global__ void __launch_bounds__(SORT_THREADS) circular_w1_kernel(const float* 
       const uint32_t mid = lo + ((hi - lo) >> 1);
       float part = 0.f;
 #pragma unroll
-      for (int q = 0; q < CW1_PER_THREAD; ++q) part += (key[q] <= mid) ? dl[q] : 0.f;
-      part = block_sum_bcast(part, wf);
+      for (int q = 0; q < C; ++q) part += (key[q] <= mid) ? dl[q] : 0.f;
+      part = block_sum_pp(part, wf, phase);
       if (part - 0.5f >= 0.f) hi = mid; else lo = mid + 1u;
     }
     kmed = lo;
   } else {
     // the cumulative sum never reaches 0.5 (all cw < 0 -> all inf -> argmin = 0): the smallest F
     for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-    __shared__ uint32_t s_kmin[SORT_WARPS];
-    if ((threadIdx.x & 31) == 0) s_kmin[threadIdx.x >> 5] = kmin;
+    if (lane == 0) s_kmin[warp] = kmin;
     __syncthreads();
     kmed = s_kmin[0];
 #pragma unroll
     for (int w = 1; w < SORT_WARPS; ++w) kmed = min(kmed, s_kmin[w]);
   }
   const float med = float_from_sort_key(kmed);
+  // ---- W and dW/d(merged value), the latter parked in su / sv (dead since the merge) for a coalesced write-out
+  const bool want_g = gus || gvs;
   float acc = 0.f;
+  {
+    float aprev = (tid > 0 && cnt > 0) ? fabsf(s_lastF[tid - 1] - med) : 0.f;  // |F_{k-1} - med|, 0 before the first entry
+    int i = i0, j = j0;
 #pragma unroll
-  for (int q = 0; q < CW1_PER_THREAD; ++q) {
-    const int k = threadIdx.x + q * SORT_THREADS;
-    if (k < nm) acc += dl[q] * fabsf(F[k] - med);
-  }
-  acc = block_sum_bcast(acc, wf);
-  if (threadIdx.x == 0) w_out[s] = acc;
-  if (gus || gvs) {
-    for (int k = threadIdx.x; k < nm; k += SORT_THREADS) {
-      const float g = ((k > 0) ? fabsf(F[k - 1] - med) : 0.f) - fabsf(F[k] - med);
-      const int o = src[k];
-      if (o < n) {
-        if (gus) gus[s * n + o] = g;
-      } else if (gvs) {
-        gvs[s * m + o - n] = g;
+    for (int q = 0; q < C; ++q) {
+      if (q < cnt) {
+        const float a = fabsf(float_from_sort_key(key[q]) - med);
+        acc += dl[q] * a;
+        if (want_g) {
+          if ((from_u >> q) & 1ull) su[cw1_pad(i++)] = aprev - a; else sv[cw1_pad(j++)] = aprev - a;
+        }
+        aprev = a;
       }
     }
   }
+  acc = block_sum_pp(acc, wf, phase);  // its barrier also orders the gradient stores above
+  if (tid == 0) w_out[s] = acc;
+  if (gus)
+    for (int i = tid; i < n; i += SORT_THREADS) gus[s * n + i] = su[cw1_pad(i)];
+  if (gvs)
+    for (int j = tid; j < m; j += SORT_THREADS) gvs[s * m + j] = sv[cw1_pad(j)];
+}
+
+template <int C>
+static int launch_circular_w1(const float* us, const float* vs, int S, int n, int m, float* w, float* gus, float* gvs,
+                              cudaStream_t stream) {
+  const size_t smem = (size_t)(cw1_pad(n - 1) + 1 + cw1_pad(m - 1) + 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_w1_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  circular_w1_kernel<C><<<S, SORT_THREADS, smem, stream>>>(us, vs, n, m, w, gus, gvs);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
 }
 
 // acc[s] = sum_k |xs_k - ys_k|^p on sorted projections; gradients w.r.t. the sorted values.
@@ -486,8 +595,8 @@ extern "C" int shwd_project_circle_bwd(const float* x, const float* U, int B, in
                                        void* stream) {
   if (!x || !U || !gkeys || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B > 65535) return SHWD_ERR_UNSUPPORTED;
-  dim3 grid((N + PJ_THREADS - 1) / PJ_THREADS, B);
-  project_circle_bwd_kernel<<<grid, PJ_THREADS, 256 * 6 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(x, U, N, P, gkeys, gx);
+  dim3 grid((N + 31) / 32, B);
+  project_circle_bwd_kernel<<<grid, PJ_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, U, N, P, gkeys, gx);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }
@@ -504,8 +613,8 @@ extern "C" int shwd_project_line(const float* x, const float* theta, int B, int 
 extern "C" int shwd_project_line_bwd(const float* theta, int B, int N, int P, const float* gkeys, float* gx, void* stream) {
   if (!theta || !gkeys || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B > 65535) return SHWD_ERR_UNSUPPORTED;
-  dim3 grid((N + PJ_THREADS - 1) / PJ_THREADS, B);
-  project_line_bwd_kernel<<<grid, PJ_THREADS, 256 * 3 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(theta, N, P, gkeys, gx);
+  dim3 grid((N + 31) / 32, B);
+  project_line_bwd_kernel<<<grid, PJ_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(theta, N, P, gkeys, gx);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }
@@ -548,13 +657,14 @@ extern "C" int shwd_circular_w1(const float* us, const float* vs, int S, int n, 
   if (!us || !vs || !w || S < 0 || n <= 0 || m <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (S == 0) return SHWD_OK;
   const size_t nm = (size_t)n + m;
-  const size_t smem = nm * (3 * sizeof(float) + sizeof(int));
-  if (nm > (size_t)SORT_THREADS * CW1_PER_THREAD) return SHWD_ERR_UNSUPPORTED;  // n + m <= 10240 (register-resident selection)
-  if (smem > 48 * 1024)
-    SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_w1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  circular_w1_kernel<<<S, SORT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(us, vs, n, m, w, gus, gvs);
-  SHWD_CUDA_CHECK(cudaGetLastError());
-  return SHWD_OK;
+  if (nm > (size_t)SORT_THREADS * CW1_PER_THREAD) return SHWD_ERR_UNSUPPORTED;  // n + m <= 10240 (register-resident entries)
+  const int c = (int)((nm + SORT_THREADS - 1) / SORT_THREADS);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c <= 8) return launch_circular_w1<8>(us, vs, S, n, m, w, gus, gvs, st);
+  if (c <= 16) return launch_circular_w1<16>(us, vs, S, n, m, w, gus, gvs, st);
+  if (c <= 24) return launch_circular_w1<24>(us, vs, S, n, m, w, gus, gvs, st);
+  if (c <= 32) return launch_circular_w1<32>(us, vs, S, n, m, w, gus, gvs, st);
+  return launch_circular_w1<CW1_PER_THREAD>(us, vs, S, n, m, w, gus, gvs, st);
 }
 
 extern "C" int shwd_euclid_sw(const float* xs, const float* ys, int S, int n, float p, float* acc, float* gxs, float* gys,

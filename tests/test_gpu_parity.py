@@ -352,6 +352,35 @@ def test_emd1d_circle_matches_reference_fixture(shwd):
     assert rel(u.grad, torch.from_numpy(d["gu"])) < TOL and rel(v.grad, torch.from_numpy(d["gv"])) < TOL
 
 
+@pytest.mark.parametrize("S,n,m", [(5, 1, 1), (5, 7, 3), (4, 1024, 1024), (3, 1500, 1500), (3, 3000, 2500), (3, 4096, 4096),
+                                   (2, 5000, 4800), (2, 5120, 5120)])
+def test_emd1d_circle_matches_oracle_every_bucket(shwd, S, n, m):
+    """circular_w1_kernel<C> keeps C merged entries per thread in registers (C = 8, 16, 24, 32, 40 by n + m): values and
+    the gradients w.r.t. the unsorted circle coordinates against emd1D_circle (oracle/sliced.py) in every bucket."""
+    uv = _tie_free(S, n + m, 100 + n)  # one shuffled tie-free row split in two: no u == v tie either (a tie's order in
+    u0, v0 = uv[:, :n].contiguous(), uv[:, n:].contiguous()  # the merged sort decides two gradient entries)
+    g = torch.Generator().manual_seed(S + n)
+    wgt = torch.rand(S, generator=g) + 0.5
+    ur, vr = u0.clone().requires_grad_(True), v0.clone().requires_grad_(True)
+    wr = oracle.emd1d_circle(ur, vr)
+    (wr * wgt).sum().backward()
+    u = u0.to(dev()).requires_grad_(True)
+    v = v0.to(dev()).requires_grad_(True)
+    w = shwd.losses.emd1D_circle(u, v)
+    (w * wgt.to(dev())).sum().backward()
+    assert rel(w, wr.detach()) < TOL
+    # n == m a power of two: the CDF difference F is a multiple of 1/n, every float32 prefix sum is exact (floor ~5e-7).
+    # Otherwise: wherever F_{k-1} and F_k straddle the level median the gradient entry is 2 med - F_{k-1} - F_k, which carries the
+    # ACCUMULATED rounding of two float32 prefix sums; torch's own float32 result sits `floor` from its float64 one
+    # (6e-6 .. 3e-5 here, and 1e-4 from a strictly sequential float32 cumsum), so the bound is max(1e-5, 8 x floor).
+    u64, v64 = u0.double().requires_grad_(True), v0.double().requires_grad_(True)
+    (oracle.emd1d_circle(u64, v64) * wgt.double()).sum().backward()
+    floor = max(rel(ur.grad, u64.grad), rel(vr.grad, v64.grad))
+    bound = max(TOL, 8 * floor)
+    assert rel(u.grad, ur.grad) < bound and rel(v.grad, vr.grad) < bound
+    assert rel(u.grad, u64.grad) < bound and rel(v.grad, v64.grad) < bound
+
+
 def test_spherical_sliced_w1_matches_reference_fixture(shwd):
     d = gold("ssw_p1")
     xs = torch.from_numpy(d["Xs"]).to(dev()).requires_grad_(True)
