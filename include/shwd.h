@@ -110,6 +110,9 @@ int shwd_project_line_bwd(const float* theta, int B, int N, int P, const float* 
 size_t shwd_segmented_sort_workspace_bytes(int segs, int len);
 int shwd_segmented_sort(const float* keys, int segs, int len, float* sorted, int64_t* perm, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* Same sort, permutation as int32 (the fused sliced losses keep it on the device only: half the bytes of torch's int64). */
+int shwd_segmented_sort_i32(const float* keys, int segs, int len, float* sorted, int32_t* perm, void* workspace,
+                            size_t workspace_bytes, void* stream);
 /* Circular W1 by level median on sorted circle coordinates (emd1D_circle, max_spherical_sliced_w.py:230-247):
  * us (S,n), vs (S,m) sorted ascending -> w (S); gus/gvs (nullable) receive dW/d(sorted values). */
 size_t shwd_circular_w1_workspace_bytes(int S, int n, int m);
@@ -119,7 +122,9 @@ int shwd_circular_w1(const float* us, const float* vs, int S, int n, int m, floa
  * max_spherical_sliced_w.py:25-207), all rounds and the final cost in one launch:
  * us (S,n), vs (S,m) sorted ascending circle coordinates in [0,1] -> w (S) = Cost(theta*), theta (S, nullable) = the
  * rotation found; gus/gvs (nullable) receive d w / d(sorted values) with theta detached (:207).  tm/tp: initial
- * bracket (-1, 1 in the reference), tol: stopping width (eps / max(Lm, Lp) = 1e-7).  Workspace: the two uniform CDFs. */
+ * bracket (-1, 1 in the reference), tol: stopping width (eps / max(Lm, Lp) = 1e-7).  n, m <= 32768, n + m <= 56320.
+ * No workspace is needed any more (the uniform CDFs are evaluated in registers): _workspace_bytes returns 0 and the
+ * workspace arguments are ignored; both are kept so that existing callers keep linking. */
 size_t shwd_circular_wp_workspace_bytes(int S, int n, int m);
 int shwd_circular_wp(const float* us, const float* vs, int S, int n, int m, float p, float tm, float tp, float tol,
                      float* w, float* gus, float* gvs, float* theta, void* workspace, size_t workspace_bytes,
@@ -128,6 +133,17 @@ int shwd_circular_wp(const float* us, const float* vs, int S, int n, int m, floa
  * sum_n |xs-ys|^p ; gxs/gys (nullable) receive d acc / d(sorted values). */
 int shwd_euclid_sw(const float* xs, const float* ys, int S, int n, float p, float* acc, float* gxs, float* gys,
                    void* stream);
+/* The three 1-D reductions with the sort's backward folded in: perm_u/perm_v (S,n)/(S,m) int32 from
+ * shwd_segmented_sort_i32; gku/gkv receive d w / d(UNSORTED keys), i.e. gku[s][perm_u[s][k]] = d w_s / d us[s][k] -- what
+ * autograd's scatter through torch.sort (max_spherical_sliced_w.py:163-164, 224-225; Flow_ellipsoid.ipynb:217) produces,
+ * without the sorted-order gradient ever reaching HBM. */
+int shwd_circular_w1_scatter(const float* us, const float* vs, const int32_t* perm_u, const int32_t* perm_v, int S, int n,
+                             int m, float* w, float* gku, float* gkv, void* stream);
+int shwd_circular_wp_scatter(const float* us, const float* vs, const int32_t* perm_u, const int32_t* perm_v, int S, int n,
+                             int m, float p, float tm, float tp, float tol, float* w, float* gku, float* gkv, float* theta,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int shwd_euclid_sw_scatter(const float* xs, const float* ys, const int32_t* perm_x, const int32_t* perm_y, int S, int n,
+                           float p, float* acc, float* gkx, float* gky, void* stream);
 /* Scatter gradients of sorted values back through the permutation: gkeys[seg][perm[seg][k]] = gsorted[seg][k]. */
 int shwd_unsort(const float* gsorted, const int64_t* perm, int segs, int len, float* gkeys, void* stream);
 

@@ -36,6 +36,10 @@ SIGNATURES = {
     "shwd_project_line_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "shwd_segmented_sort_workspace_bytes": (_sz, [_i, _i]),
     "shwd_segmented_sort": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "shwd_segmented_sort_i32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "shwd_circular_w1_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "shwd_circular_wp_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "shwd_euclid_sw_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "shwd_circular_w1_workspace_bytes": (_sz, [_i, _i, _i]),
     "shwd_circular_w1": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "shwd_circular_wp_workspace_bytes": (_sz, [_i, _i, _i]),

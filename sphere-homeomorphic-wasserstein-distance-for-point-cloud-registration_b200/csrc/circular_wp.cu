@@ -9,7 +9,8 @@
 // value / CDF arrays, two searchsorted results and, for Cost, a sort of the concatenated CDFs).
 //
 // Nothing is materialised here.  With uniform weights the CDFs are the same for every slice
-// (u_cdf = cumsum(1/n), v_cdf = cumsum(1/m), accumulated in double and rounded per element like torch's CPU cumsum),
+// (u_cdf = cumsum(1/n), v_cdf = cumsum(1/m), accumulated in double and rounded per element like torch's CPU cumsum --
+// evaluated in closed form in registers, see ucdf_at),
 // the "shifted + rolled" arrays of the reference are pure index arithmetic on them:
 //     frac = theta - floor(theta);  c_j = v_cdf_j - frac;  neg_j = c_j < 0   (a prefix: v_cdf is increasing)
 //     j0 = #neg (0 if all are negative -- argmin over an all-inf row)        (the roll)
@@ -40,11 +41,18 @@ constexpr int CW_MAX_ROUNDS = 96;  // the bracket [-1,1] reaches 1 ulp after ~25
 struct Circle {
   const float* u;     // sorted u values (n)            -- shared memory
   const float* v;     // sorted v values (m)
-  const float* ucdf;  // cumsum(1/n) (n)
-  const float* vcdf;  // cumsum(1/m) (m)
   int n, m;
   float p;
+  float wu, wv;  // float32(1/n), float32(1/m): torch.full((len,), 1/len, dtype=float32)
 };
+
+// u_cdf[i] = cumsum(full(1/n))[i] the way torch's CPU kernel forms it -- a double accumulator, every prefix rounded to
+// float32 -- WITHOUT a table: the weight is a float32 (24 significant bits) and at most 2^15 copies are added, so every
+// double partial sum is exact ((i+1) * w needs < 40 bits) and its float32 rounding is the single rounding of the exact
+// product, i.e. __fmul_rn(float(i+1), w).  Two ALU instructions instead of a shared-memory load on the hottest path of the
+// bisection (dcost was bound by shared-memory wavefronts: ~12 loads per CDF entry, 7 of them from the two CDF tables).
+__device__ __forceinline__ float ucdf_at(const Circle& c, int i) { return __fmul_rn(__int2float_rn(i + 1), c.wu); }
+__device__ __forceinline__ float vcdf_at(const Circle& c, int j) { return __fmul_rn(__int2float_rn(j + 1), c.wv); }
 
 struct Shift {
   float fl, flp1, frac, r0;
@@ -67,13 +75,13 @@ __device__ __forceinline__ float dpowp(float d, float p) {
 __device__ __forceinline__ float r_cdf(const Circle& c, const Shift& s, int t) {
   int j = t + s.j0;
   if (j >= c.m) j -= c.m;
-  const float x = __fsub_rn(c.vcdf[j], s.frac);
+  const float x = __fsub_rn(vcdf_at(c, j), s.frac);
   return x < 0.f ? __fadd_rn(x, 1.f) : x;
 }
 __device__ __forceinline__ float r_val_in(const Circle& c, const Shift& s, int t) {
   int j = t + s.j0;
   if (j >= c.m) j -= c.m;
-  const float x = __fsub_rn(c.vcdf[j], s.frac);
+  const float x = __fsub_rn(vcdf_at(c, j), s.frac);
   return __fadd_rn(c.v[j], x < 0.f ? s.flp1 : s.fl);
 }
 // t in [0, m]: r_val[m] = r_val[0] + 1
@@ -86,11 +94,10 @@ __device__ __forceinline__ Shift make_shift(const Circle& c, float theta) {
   s.fl = floorf(theta);
   s.flp1 = __fadd_rn(s.fl, 1.f);
   s.frac = __fsub_rn(theta, s.fl);
-  int lo = 0, hi = c.m;  // first j with v_cdf_j - frac >= 0
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__fsub_rn(c.vcdf[mid], s.frac) < 0.f) lo = mid + 1; else hi = mid;
-  }
+  // first j with v_cdf_j - frac >= 0 (v_cdf is increasing): closed-form guess, then a local walk
+  int lo = min(max(__float2int_rd(s.frac * (float)c.m), 0), c.m);
+  while (lo < c.m && __fsub_rn(vcdf_at(c, lo), s.frac) < 0.f) ++lo;
+  while (lo > 0 && !(__fsub_rn(vcdf_at(c, lo - 1), s.frac) < 0.f)) --lo;
   s.j0 = (lo == c.m) ? 0 : lo;
   s.r0 = 0.f;
   s.r0 = r_cdf(c, s, 0);
@@ -100,8 +107,8 @@ __device__ __forceinline__ Shift make_shift(const Circle& c, float theta) {
 // #{i : u_cdf[i] < x}  (torch.searchsorted(u_cdf, x), left), in [0, n]
 __device__ __forceinline__ int u_count_lt(const Circle& c, float x) {
   int i = min(max(__float2int_rd(x * (float)c.n), 0), c.n);
-  while (i < c.n && c.ucdf[i] < x) ++i;
-  while (i > 0 && c.ucdf[i - 1] >= x) --i;
+  while (i < c.n && ucdf_at(c, i) < x) ++i;
+  while (i > 0 && ucdf_at(c, i - 1) >= x) --i;
   return i;
 }
 // #{t : r_cdf[t] < x}, in [0, m]
@@ -132,14 +139,14 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* wtot) {
 template <bool P2>
 __device__ float2 dcost(const Circle& c, float theta, float2* wtot) {
   const Shift s = make_shift(c, theta);
-  const float u_wrap = __fadd_rn(c.u[0], 1.f), ucdf_wrap = __fadd_rn(c.ucdf[0], 1.f);
+  const float u_wrap = __fadd_rn(c.u[0], 1.f), ucdf_wrap = __fadd_rn(ucdf_at(c, 0), 1.f);
   float dcp = 0.f, dcm = 0.f;
   for (int t = threadIdx.x; t < c.m; t += CW_THREADS) {
     const float x = r_cdf(c, s, t);
     const int iu = u_count_lt(c, x);                       // searchsorted(u_cdf, x)
     const float ui = c.u[min(iu, c.n - 1)];
     int ium = iu;                                          // searchsorted(cat(u_cdf, u_cdf_0 + 1), x, right=True)
-    while (ium < c.n && c.ucdf[ium] <= x) ++ium;
+    while (ium < c.n && ucdf_at(c, ium) <= x) ++ium;
     if (ium == c.n && ucdf_wrap <= x) ++ium;
     const float uim = (ium < c.n) ? c.u[ium] : u_wrap;     // index clipped at n -> u_0 + 1
     const float v0 = r_val_in(c, s, t), v1 = r_val(c, s, t + 1);
@@ -151,12 +158,12 @@ __device__ float2 dcost(const Circle& c, float theta, float2* wtot) {
 
 // Cost :68-113, pass U.  Returns the cost (broadcast); gu (nullable, global) receives d cost / d u_sorted.
 template <bool P2>
-__device__ float cost_pass_u(const Circle& c, float theta, float* __restrict__ gu, float2* wtot) {
+__device__ float cost_pass_u(const Circle& c, float theta, float* __restrict__ gu, const int32_t* __restrict__ pu, float2* wtot) {
   const Shift s = make_shift(c, theta);
   float acc = 0.f;
   for (int k = threadIdx.x; k < c.n; k += CW_THREADS) {
-    float prev = (k > 0) ? c.ucdf[k - 1] : 0.f;
-    const float xk = c.ucdf[k];
+    float prev = (k > 0) ? ucdf_at(c, k - 1) : 0.f;
+    const float xk = ucdf_at(c, k);
     const float U = c.u[k];
     int t = (k > 0) ? r_count_lt(c, s, prev) : 0;
     float g = 0.f;
@@ -186,14 +193,14 @@ __device__ float cost_pass_u(const Circle& c, float theta, float* __restrict__ g
         ++t;
       }
     }
-    if (gu) gu[k] = g;
+    if (gu) gu[pu ? __ldg(pu + k) : k] = g;  // pu: straight to the unsorted key position
   }
   return block_sum2(acc, 0.f, wtot).x;
 }
 
 // Cost, pass V: gv (global, indexed by sorted v position) receives d cost / d v_sorted.
 template <bool P2>
-__device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv) {
+__device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv, const int32_t* __restrict__ pv) {
   const Shift s = make_shift(c, theta);
   for (int t = threadIdx.x; t < c.m; t += CW_THREADS) {
     float prev = (t > 0) ? r_cdf(c, s, t - 1) : 0.f;
@@ -202,11 +209,11 @@ __device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv
     int i = 0;
     if (t > 0) {  // first u entry above r_cdf[t-1]
       i = u_count_lt(c, prev);
-      while (i < c.n && c.ucdf[i] <= prev) ++i;
+      while (i < c.n && ucdf_at(c, i) <= prev) ++i;
     }
     float g = 0.f;
-    while (i < c.n && c.ucdf[i] < xt) {  // u entries inside (r[t-1], r[t]): v-index t
-      const float a = c.ucdf[i];
+    while (i < c.n && ucdf_at(c, i) < xt) {  // u entries inside (r[t-1], r[t]): v-index t
+      const float a = ucdf_at(c, i);
       g = fmaf(__fsub_rn(a, prev), dpowp<P2>(__fsub_rn(c.u[i], V), c.p), g);
       prev = a;
       ++i;
@@ -218,42 +225,39 @@ __device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv
       const float Vw = __fadd_rn(V, 1.f);
       float pw = r_cdf(c, s, c.m - 1);
       int iw = u_count_lt(c, pw);
-      while (iw < c.n && c.ucdf[iw] <= pw) ++iw;
+      while (iw < c.n && ucdf_at(c, iw) <= pw) ++iw;
       for (; iw < c.n; ++iw) {
-        const float a = c.ucdf[iw];
+        const float a = ucdf_at(c, iw);
         g = fmaf(__fsub_rn(a, pw), dpowp<P2>(__fsub_rn(c.u[iw], Vw), c.p), g);
         pw = a;
       }
     }
     int j = t + s.j0;
     if (j >= c.m) j -= c.m;
-    gv[j] = -g;
+    gv[pv ? __ldg(pv + j) : j] = -g;
   }
 }
 
 template <bool P2>
-__global__ void __launch_bounds__(CW_THREADS) circular_wp_kernel(const float* __restrict__ us, const float* __restrict__ vs, int n,
+__global__ void __launch_bounds__(CW_THREADS) circular_wp_kernel(const float* __restrict__ us, const float* __restrict__ vs,
+                                                                 const int32_t* __restrict__ pu, const int32_t* __restrict__ pv, int n,
                                                                  int m, float p, float tm0, float tp0, float tol,
-                                                                 const float* __restrict__ cdfs, float* __restrict__ w_out,
+                                                                 float* __restrict__ w_out,
                                                                  float* __restrict__ gus, float* __restrict__ gvs,
                                                                  float* __restrict__ theta_out) {
   extern __shared__ float cw_smem[];
   __shared__ float2 wtot[CW_WARPS];
   float* su = cw_smem;
   float* sv = su + n;
-  float* sucdf = sv + m;
-  float* svcdf = sucdf + n;
   const size_t sl = blockIdx.x;
   for (int i = threadIdx.x; i < n; i += CW_THREADS) {
     su[i] = __ldg(us + sl * n + i);
-    sucdf[i] = __ldg(cdfs + i);
   }
   for (int j = threadIdx.x; j < m; j += CW_THREADS) {
     sv[j] = __ldg(vs + sl * m + j);
-    svcdf[j] = __ldg(cdfs + n + j);
   }
   __syncthreads();
-  Circle c = {su, sv, sucdf, svcdf, n, m, p};
+  Circle c = {su, sv, n, m, p, (float)(1.0 / (double)n), (float)(1.0 / (double)m)};
 
   // binary_search_circle :172-205 (every quantity is uniform over the CTA: the sums are broadcast)
   float tm = tm0, tp = tp0, tc = (tm0 + tp0) * 0.5f;
@@ -263,8 +267,8 @@ __global__ void __launch_bounds__(CW_THREADS) circular_wp_kernel(const float* __
     if (__fsub_rn(tp, tm) < tol) {
       const float2 dtp = dcost<P2>(c, tp, wtot);
       const float2 dtm = dcost<P2>(c, tm, wtot);
-      const float ctm = cost_pass_u<P2>(c, tm, nullptr, wtot);
-      const float ctp = cost_pass_u<P2>(c, tp, nullptr, wtot);
+      const float ctm = cost_pass_u<P2>(c, tm, nullptr, nullptr, wtot);
+      const float ctp = cost_pass_u<P2>(c, tp, nullptr, nullptr, wtot);
       const float den = __fsub_rn(dtm.x, dtp.y);  // dCptm - dCmtp
       if (fabsf(den) > 0.001f)
         tc = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(ctp, ctm), __fmul_rn(tm, dtm.x)), __fmul_rn(tp, dtp.y)), den);
@@ -273,25 +277,11 @@ __global__ void __launch_bounds__(CW_THREADS) circular_wp_kernel(const float* __
     if (dc.x < 0.f) tm = tc; else tp = tc;
     tc = __fmul_rn(__fadd_rn(tm, tp), 0.5f);
   }
-  const float w = cost_pass_u<P2>(c, tc, gus ? gus + sl * n : nullptr, wtot);
-  if (gvs) cost_pass_v<P2>(c, tc, gvs + sl * m);
+  const float w = cost_pass_u<P2>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot);
+  if (gvs) cost_pass_v<P2>(c, tc, gvs + sl * m, pv ? pv + sl * m : nullptr);
   if (threadIdx.x == 0) {
     w_out[sl] = w;
     if (theta_out) theta_out[sl] = tc;
-  }
-}
-
-// cumsum(full(1/len)) the way torch's CPU kernel forms it: double accumulator, every prefix rounded to float32.
-__global__ void uniform_cdf_kernel(float* __restrict__ cdfs, int n, int m) {
-  const int which = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) != 0 || which > 1) return;
-  const int len = which ? m : n;
-  float* out = which ? cdfs + n : cdfs;
-  const double w = (double)(float)(1.0 / (double)len);  // torch.full((len,), 1/len, dtype=float32)
-  double s = 0.0;
-  for (int i = 0; i < len; ++i) {
-    s += w;
-    out[i] = (float)s;
   }
 }
 
@@ -301,32 +291,46 @@ using namespace shwd;
 
 extern "C" size_t shwd_circular_wp_workspace_bytes(int S, int n, int m) {
   (void)S;
-  if (n <= 0 || m <= 0) return 0;
-  return ((size_t)n + (size_t)m) * sizeof(float);
+  (void)n;
+  (void)m;
+  return 0;  // the uniform CDFs are evaluated in registers (ucdf_at / vcdf_at); kept for ABI stability
+}
+
+static int circular_wp_dispatch(const float* us, const float* vs, const int32_t* pu, const int32_t* pv, int S, int n, int m, float p,
+                                float tm, float tp, float tol, float* w, float* gus, float* gvs, float* theta, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (!us || !vs || !w || S < 0 || n <= 0 || m <= 0 || !(p > 0.f) || !(tm < tp)) return SHWD_ERR_INVALID_ARGUMENT;
+  if (S == 0) return SHWD_OK;
+  (void)workspace;
+  (void)workspace_bytes;
+  const size_t smem = ((size_t)n + m) * sizeof(float);
+  if (n > 32768 || m > 32768) return SHWD_ERR_UNSUPPORTED;  // exactness argument of ucdf_at: at most 2^15 weights per CDF
+  if (smem > 220 * 1024) return SHWD_ERR_UNSUPPORTED;        // n + m <= 56320 per slice
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p == 2.f) {
+    if (smem > 48 * 1024)
+      SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    circular_wp_kernel<true><<<S, CW_THREADS, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta);
+  } else {
+    if (smem > 48 * 1024)
+      SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    circular_wp_kernel<false><<<S, CW_THREADS, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta);
+  }
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
 }
 
 extern "C" int shwd_circular_wp(const float* us, const float* vs, int S, int n, int m, float p, float tm, float tp, float tol,
                                 float* w, float* gus, float* gvs, float* theta, void* workspace, size_t workspace_bytes,
                                 void* stream) {
-  if (!us || !vs || !w || S < 0 || n <= 0 || m <= 0 || !(p > 0.f) || !(tm < tp)) return SHWD_ERR_INVALID_ARGUMENT;
-  if (S == 0) return SHWD_OK;
-  const size_t need = shwd_circular_wp_workspace_bytes(S, n, m);
-  if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 3)) return SHWD_ERR_WORKSPACE;
-  const size_t smem = 2 * ((size_t)n + m) * sizeof(float);
-  if (smem > 220 * 1024) return SHWD_ERR_UNSUPPORTED;  // n + m <= 28160 per slice
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  float* cdfs = static_cast<float*>(workspace);
-  uniform_cdf_kernel<<<1, 64, 0, s>>>(cdfs, n, m);
-  SHWD_CUDA_CHECK(cudaGetLastError());
-  if (p == 2.f) {
-    if (smem > 48 * 1024)
-      SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    circular_wp_kernel<true><<<S, CW_THREADS, smem, s>>>(us, vs, n, m, p, tm, tp, tol, cdfs, w, gus, gvs, theta);
-  } else {
-    if (smem > 48 * 1024)
-      SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    circular_wp_kernel<false><<<S, CW_THREADS, smem, s>>>(us, vs, n, m, p, tm, tp, tol, cdfs, w, gus, gvs, theta);
-  }
-  SHWD_CUDA_CHECK(cudaGetLastError());
-  return SHWD_OK;
+  return circular_wp_dispatch(us, vs, nullptr, nullptr, S, n, m, p, tm, tp, tol, w, gus, gvs, theta, workspace, workspace_bytes,
+                              stream);
+}
+
+extern "C" int shwd_circular_wp_scatter(const float* us, const float* vs, const int32_t* perm_u, const int32_t* perm_v, int S, int n,
+                                        int m, float p, float tm, float tp, float tol, float* w, float* gku, float* gkv,
+                                        float* theta, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!perm_u || !perm_v || !gku || !gkv) return SHWD_ERR_INVALID_ARGUMENT;
+  return circular_wp_dispatch(us, vs, perm_u, perm_v, S, n, m, p, tm, tp, tol, w, gku, gkv, theta, workspace, workspace_bytes,
+                              stream);
 }

@@ -271,7 +271,7 @@ __device__ uint2* block_radix_sort(uint2* a, uint2* b, int n, uint32_t* hist, ui
 
 __global__ void __launch_bounds__(SORT_THREADS) segmented_sort_kernel(const float* __restrict__ keys, int len,
                                                                       float* __restrict__ sorted, int64_t* __restrict__ perm,
-                                                                      uint2* __restrict__ gscratch) {
+                                                                      int32_t* __restrict__ perm32, uint2* __restrict__ gscratch) {
   extern __shared__ uint2 sbuf[];
   __shared__ uint32_t hist[SORT_WARPS * 256];
   __shared__ uint32_t wt[SORT_WARPS];
@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(SORT_THREADS) segmented_sort_kernel(const floa
     const uint32_t j = r[i].y;
     if (sorted) sorted[seg * len + i] = __ldg(k + j);
     if (perm) perm[seg * len + i] = (int64_t)j;
+    if (perm32) perm32[seg * len + i] = (int32_t)j;
   }
 }
 
@@ -386,8 +387,9 @@ __host__ __device__ __forceinline__ int cw1_pad(int i) { return i + (i >> 5); }
 // register-resident partial sum + a fixed-order block reduction -- instead of a radix sort of n + m records.
 template <int C>
 __global__ void __launch_bounds__(SORT_THREADS, (C <= 32 ? 2 : 1))
-    circular_w1_kernel(const float* __restrict__ us, const float* __restrict__ vs, int n, int m, float* __restrict__ w_out,
-                       float* __restrict__ gus, float* __restrict__ gvs) {
+    circular_w1_kernel(const float* __restrict__ us, const float* __restrict__ vs, const int32_t* __restrict__ pu,
+                       const int32_t* __restrict__ pv, int n, int m, float* __restrict__ w_out, float* __restrict__ gus,
+                       float* __restrict__ gvs) {
   extern __shared__ float cw1_smem[];
   __shared__ float wf[2][SORT_WARPS];
   __shared__ float s_first[SORT_THREADS];  // first merged value of each thread's chunk
@@ -532,25 +534,27 @@ __global__ void __launch_bounds__(SORT_THREADS, (C <= 32 ? 2 : 1))
   }
   acc = block_sum_pp(acc, wf, phase);  // its barrier also orders the gradient stores above
   if (tid == 0) w_out[s] = acc;
+  // pu / pv given: the gradient goes straight to the UNSORTED key positions (the scatter torch.sort's backward would do)
   if (gus)
-    for (int i = tid; i < n; i += SORT_THREADS) gus[s * n + i] = su[cw1_pad(i)];
+    for (int i = tid; i < n; i += SORT_THREADS) gus[s * n + (pu ? __ldg(pu + s * n + i) : i)] = su[cw1_pad(i)];
   if (gvs)
-    for (int j = tid; j < m; j += SORT_THREADS) gvs[s * m + j] = sv[cw1_pad(j)];
+    for (int j = tid; j < m; j += SORT_THREADS) gvs[s * m + (pv ? __ldg(pv + s * m + j) : j)] = sv[cw1_pad(j)];
 }
 
 template <int C>
-static int launch_circular_w1(const float* us, const float* vs, int S, int n, int m, float* w, float* gus, float* gvs,
-                              cudaStream_t stream) {
+static int launch_circular_w1(const float* us, const float* vs, const int32_t* pu, const int32_t* pv, int S, int n, int m, float* w,
+                              float* gus, float* gvs, cudaStream_t stream) {
   const size_t smem = (size_t)(cw1_pad(n - 1) + 1 + cw1_pad(m - 1) + 1) * sizeof(float);
   if (smem > 48 * 1024)
     SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_w1_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  circular_w1_kernel<C><<<S, SORT_THREADS, smem, stream>>>(us, vs, n, m, w, gus, gvs);
+  circular_w1_kernel<C><<<S, SORT_THREADS, smem, stream>>>(us, vs, pu, pv, n, m, w, gus, gvs);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }
 
 // acc[s] = sum_k |xs_k - ys_k|^p on sorted projections; gradients w.r.t. the sorted values.
-__global__ void __launch_bounds__(SORT_THREADS) euclid_sw_kernel(const float* __restrict__ xs, const float* __restrict__ ys, int n,
+__global__ void __launch_bounds__(SORT_THREADS) euclid_sw_kernel(const float* __restrict__ xs, const float* __restrict__ ys,
+                                                                 const int32_t* __restrict__ px, const int32_t* __restrict__ py, int n,
                                                                  float p, float* __restrict__ acc_out, float* __restrict__ gxs,
                                                                  float* __restrict__ gys) {
   __shared__ float wf[SORT_WARPS];
@@ -571,8 +575,8 @@ __global__ void __launch_bounds__(SORT_THREADS) euclid_sw_kernel(const float* __
       g = copysignf(p * powf(ad, p - 1.f), d);
     }
     acc += t;
-    if (gxs) gxs[s * n + k] = g;
-    if (gys) gys[s * n + k] = -g;
+    if (gxs) gxs[s * n + (px ? __ldg(px + s * n + k) : k)] = g;
+    if (gys) gys[s * n + (py ? __ldg(py + s * n + k) : k)] = -g;
   }
   acc = block_sum_f32(acc, wf);
   if (threadIdx.x == 0) acc_out[s] = acc;
@@ -624,23 +628,33 @@ extern "C" size_t shwd_segmented_sort_workspace_bytes(int segs, int len) {
   return (size_t)segs * 2 * (size_t)len * sizeof(uint2);
 }
 
-extern "C" int shwd_segmented_sort(const float* keys, int segs, int len, float* sorted, int64_t* perm, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
-  if (!keys || segs < 0 || len <= 0 || (!sorted && !perm)) return SHWD_ERR_INVALID_ARGUMENT;
+static int launch_segmented_sort(const float* keys, int segs, int len, float* sorted, int64_t* perm, int32_t* perm32,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!keys || segs < 0 || len <= 0 || (!sorted && !perm && !perm32)) return SHWD_ERR_INVALID_ARGUMENT;
   if (segs == 0) return SHWD_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (len <= SORT_SMEM_MAX) {
     const size_t smem = 2 * (size_t)len * sizeof(uint2);
     if (smem > 48 * 1024)
       SHWD_CUDA_CHECK(cudaFuncSetAttribute(segmented_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    segmented_sort_kernel<<<segs, SORT_THREADS, smem, s>>>(keys, len, sorted, perm, nullptr);
+    segmented_sort_kernel<<<segs, SORT_THREADS, smem, s>>>(keys, len, sorted, perm, perm32, nullptr);
   } else {
     const size_t need = shwd_segmented_sort_workspace_bytes(segs, len);
     if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 7)) return SHWD_ERR_WORKSPACE;
-    segmented_sort_kernel<<<segs, SORT_THREADS, 0, s>>>(keys, len, sorted, perm, static_cast<uint2*>(workspace));
+    segmented_sort_kernel<<<segs, SORT_THREADS, 0, s>>>(keys, len, sorted, perm, perm32, static_cast<uint2*>(workspace));
   }
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
+}
+
+extern "C" int shwd_segmented_sort(const float* keys, int segs, int len, float* sorted, int64_t* perm, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  return launch_segmented_sort(keys, segs, len, sorted, perm, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int shwd_segmented_sort_i32(const float* keys, int segs, int len, float* sorted, int32_t* perm, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  return launch_segmented_sort(keys, segs, len, sorted, nullptr, perm, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t shwd_circular_w1_workspace_bytes(int S, int n, int m) {
@@ -650,28 +664,48 @@ extern "C" size_t shwd_circular_w1_workspace_bytes(int S, int n, int m) {
   return 0;  // everything lives in shared memory / registers (n + m <= 10240)
 }
 
-extern "C" int shwd_circular_w1(const float* us, const float* vs, int S, int n, int m, float* w, float* gus, float* gvs,
-                                void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace;
-  (void)workspace_bytes;
+static int circular_w1_dispatch(const float* us, const float* vs, const int32_t* pu, const int32_t* pv, int S, int n, int m, float* w,
+                                float* gus, float* gvs, void* stream) {
   if (!us || !vs || !w || S < 0 || n <= 0 || m <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (S == 0) return SHWD_OK;
   const size_t nm = (size_t)n + m;
   if (nm > (size_t)SORT_THREADS * CW1_PER_THREAD) return SHWD_ERR_UNSUPPORTED;  // n + m <= 10240 (register-resident entries)
   const int c = (int)((nm + SORT_THREADS - 1) / SORT_THREADS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (c <= 8) return launch_circular_w1<8>(us, vs, S, n, m, w, gus, gvs, st);
-  if (c <= 16) return launch_circular_w1<16>(us, vs, S, n, m, w, gus, gvs, st);
-  if (c <= 24) return launch_circular_w1<24>(us, vs, S, n, m, w, gus, gvs, st);
-  if (c <= 32) return launch_circular_w1<32>(us, vs, S, n, m, w, gus, gvs, st);
-  return launch_circular_w1<CW1_PER_THREAD>(us, vs, S, n, m, w, gus, gvs, st);
+  if (c <= 8) return launch_circular_w1<8>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
+  if (c <= 16) return launch_circular_w1<16>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
+  if (c <= 24) return launch_circular_w1<24>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
+  if (c <= 32) return launch_circular_w1<32>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
+  return launch_circular_w1<CW1_PER_THREAD>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
+}
+
+extern "C" int shwd_circular_w1(const float* us, const float* vs, int S, int n, int m, float* w, float* gus, float* gvs,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  return circular_w1_dispatch(us, vs, nullptr, nullptr, S, n, m, w, gus, gvs, stream);
+}
+
+extern "C" int shwd_circular_w1_scatter(const float* us, const float* vs, const int32_t* perm_u, const int32_t* perm_v, int S, int n,
+                                        int m, float* w, float* gku, float* gkv, void* stream) {
+  if (!perm_u || !perm_v || !gku || !gkv) return SHWD_ERR_INVALID_ARGUMENT;
+  return circular_w1_dispatch(us, vs, perm_u, perm_v, S, n, m, w, gku, gkv, stream);
 }
 
 extern "C" int shwd_euclid_sw(const float* xs, const float* ys, int S, int n, float p, float* acc, float* gxs, float* gys,
                               void* stream) {
   if (!xs || !ys || !acc || S < 0 || n <= 0 || !(p > 0.f)) return SHWD_ERR_INVALID_ARGUMENT;
   if (S == 0) return SHWD_OK;
-  euclid_sw_kernel<<<S, SORT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(xs, ys, n, p, acc, gxs, gys);
+  euclid_sw_kernel<<<S, SORT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(xs, ys, nullptr, nullptr, n, p, acc, gxs, gys);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+extern "C" int shwd_euclid_sw_scatter(const float* xs, const float* ys, const int32_t* perm_x, const int32_t* perm_y, int S, int n,
+                                      float p, float* acc, float* gkx, float* gky, void* stream) {
+  if (!xs || !ys || !perm_x || !perm_y || !acc || !gkx || !gky || S < 0 || n <= 0 || !(p > 0.f)) return SHWD_ERR_INVALID_ARGUMENT;
+  if (S == 0) return SHWD_OK;
+  euclid_sw_kernel<<<S, SORT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(xs, ys, perm_x, perm_y, n, p, acc, gkx, gky);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }

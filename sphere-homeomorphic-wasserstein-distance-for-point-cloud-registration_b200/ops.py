@@ -545,34 +545,115 @@ class ResidualFlowStackFn(torch.autograd.Function):
         return (gx, None, None, None) + tuple(grads)
 
 
+def _sort_i32(keys2d):
+    """(S,len) float32 keys -> (sorted values, int32 stable-sort permutation); device-side only."""
+    lib = _lib.lib()
+    S, length = keys2d.shape
+    out = torch.empty_like(keys2d)
+    perm = torch.empty(keys2d.shape, device=keys2d.device, dtype=torch.int32)
+    wsb = lib.shwd_segmented_sort_workspace_bytes(S, length)
+    ws = torch.empty(max(wsb, 8), device=keys2d.device, dtype=torch.uint8)
+    _lib.check(lib.shwd_segmented_sort_i32(_ptr(keys2d), S, length, _ptr(out), _ptr(perm), _ptr(ws), wsb, _stream()),
+               "shwd_segmented_sort_i32")
+    return out, perm
+
+
+class SlicedLossFn(torch.autograd.Function):
+    """The whole sliced path of one call in five launches forward and two backward:
+        project x, project y -> sort, sort (int32 permutations) -> one 1-D reduction kernel that also writes
+        d w_slice / d(unsorted keys) through the permutations;   backward: the two projection backward kernels.
+    mode "circle_w1":  sliced_cost p == 1  (max_spherical_sliced_w.py:251-286 with emd1D_circle :210-247)
+    mode "circle_wp":  sliced_cost p != 1  (binary_search_circle :117-207), mean of W_p^p
+    mode "line":       Euclidean sliced W  (Flow_ellipsoid.ipynb:208-220), returns mean_P sum_n |.|^p (root taken outside)
+    Returns the per-pair mean over the slices (B,).  Compared with chaining ProjectCircleFn / SegmentedSortFn /
+    CircularW1Fn it never writes the sorted-order gradients, needs no unsort launches, no gradient scaling passes and
+    no int64 permutations (cfg3: 2 x 8 B x P x N per pair)."""
+
+    @staticmethod
+    def forward(ctx, x, y, frames, mode, p, tm, tp, tol):
+        lib = _lib.lib()
+        x = x.contiguous()
+        y = y.contiguous()
+        frames = frames.contiguous()
+        B, n, _ = x.shape
+        m = y.shape[1]
+        P = frames.shape[0]
+        S = B * P
+        dev = x.device
+        ku = torch.empty(S, n, device=dev, dtype=torch.float32)
+        kv = torch.empty(S, m, device=dev, dtype=torch.float32)
+        w = torch.empty(S, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            st = _stream()
+            if mode == "line":
+                _lib.check(lib.shwd_project_line(_ptr(x), _ptr(frames), B, n, P, _ptr(ku), st), "shwd_project_line")
+                _lib.check(lib.shwd_project_line(_ptr(y), _ptr(frames), B, m, P, _ptr(kv), st), "shwd_project_line")
+            else:
+                _lib.check(lib.shwd_project_circle(_ptr(x), _ptr(frames), B, n, P, _ptr(ku), st), "shwd_project_circle")
+                _lib.check(lib.shwd_project_circle(_ptr(y), _ptr(frames), B, m, P, _ptr(kv), st), "shwd_project_circle")
+            su, pu = _sort_i32(ku)
+            sv, pv = _sort_i32(kv)
+            gku, gkv = ku, kv  # the keys are dead once sorted: their buffers receive d w / d keys
+            if mode == "circle_w1":
+                _lib.check(lib.shwd_circular_w1_scatter(_ptr(su), _ptr(sv), _ptr(pu), _ptr(pv), S, n, m, _ptr(w), _ptr(gku), _ptr(gkv),
+                                                        st), "shwd_circular_w1_scatter")
+            elif mode == "circle_wp":
+                wsb = lib.shwd_circular_wp_workspace_bytes(S, n, m)
+                ws = torch.empty(max(wsb, 8), device=dev, dtype=torch.uint8)
+                _lib.check(lib.shwd_circular_wp_scatter(_ptr(su), _ptr(sv), _ptr(pu), _ptr(pv), S, n, m, float(p), float(tm), float(tp),
+                                                        float(tol), _ptr(w), _ptr(gku), _ptr(gkv), None, _ptr(ws), wsb, st),
+                           "shwd_circular_wp_scatter")
+            elif mode == "line":
+                _lib.check(lib.shwd_euclid_sw_scatter(_ptr(su), _ptr(sv), _ptr(pu), _ptr(pv), S, n, float(p), _ptr(w), _ptr(gku),
+                                                      _ptr(gkv), st), "shwd_euclid_sw_scatter")
+            else:
+                raise ValueError("unknown sliced mode %r" % (mode,))
+        ctx.save_for_backward(x, y, frames, gku, gkv)
+        ctx.mode = mode
+        return w.view(B, P).mean(dim=1)
+
+    @staticmethod
+    def backward(ctx, gw):
+        x, y, frames, gku, gkv = ctx.saved_tensors
+        lib = _lib.lib()
+        B, n, _ = x.shape
+        m = y.shape[1]
+        P = frames.shape[0]
+        scale = (gw.reshape(B, 1, 1).float() / P)
+        gx = gy = None
+        with torch.cuda.device(x.device):
+            st = _stream()
+            for idx, (c, gk, cnt) in enumerate(((x, gku, n), (y, gkv, m))):
+                if not ctx.needs_input_grad[idx]:
+                    continue
+                g = torch.empty_like(c)
+                if ctx.mode == "line":
+                    _lib.check(lib.shwd_project_line_bwd(_ptr(frames), B, cnt, P, _ptr(gk), _ptr(g), st), "shwd_project_line_bwd")
+                else:
+                    _lib.check(lib.shwd_project_circle_bwd(_ptr(c), _ptr(frames), B, cnt, P, _ptr(gk), _ptr(g), st),
+                               "shwd_project_circle_bwd")
+                g = g * scale
+                if idx == 0:
+                    gx = g
+                else:
+                    gy = g
+        return gx, gy, None, None, None, None, None, None
+
+
 def spherical_sliced_w1(Xs, Xt, U):
     """mean_P circular-W1 of the great-circle projections (sliced_cost with p == 1, explicit frames U (P,3,2))."""
     xs, _ = _as_cloud(Xs, "Xs")
     xt, _ = _as_cloud(Xt, "Xt")
-    U = U.to(device=xs.device, dtype=torch.float32).contiguous()
-    ks = ProjectCircleFn.apply(xs, U)  # (B,P,n)
-    kt = ProjectCircleFn.apply(xt, U)
-    B, P, n = ks.shape
-    m = kt.shape[2]
-    ss, _ = SegmentedSortFn.apply(ks.reshape(B * P, n))
-    st, _ = SegmentedSortFn.apply(kt.reshape(B * P, m))
-    w = CircularW1Fn.apply(ss, st).reshape(B, P)
-    return w.mean(dim=1)  # (B,)
+    U = U.to(device=xs.device, dtype=torch.float32)
+    return SlicedLossFn.apply(xs, xt, U, "circle_w1", 1.0, 0.0, 0.0, 0.0)  # (B,)
 
 
 def spherical_sliced_wp(Xs, Xt, U, p=2.0, tm=-1.0, tp=1.0, tol=1e-7):
     """mean_P circular-W_p^p (no root, max_spherical_sliced_w.py:284-286) of the great-circle projections, p != 1."""
     xs, _ = _as_cloud(Xs, "Xs")
     xt, _ = _as_cloud(Xt, "Xt")
-    U = U.to(device=xs.device, dtype=torch.float32).contiguous()
-    ks = ProjectCircleFn.apply(xs, U)  # (B,P,n)
-    kt = ProjectCircleFn.apply(xt, U)
-    B, P, n = ks.shape
-    m = kt.shape[2]
-    ss, _ = SegmentedSortFn.apply(ks.reshape(B * P, n))
-    st, _ = SegmentedSortFn.apply(kt.reshape(B * P, m))
-    w, _ = CircularWpFn.apply(ss, st, float(p), tm, tp, tol)
-    return w.reshape(B, P).mean(dim=1)  # (B,)
+    U = U.to(device=xs.device, dtype=torch.float32)
+    return SlicedLossFn.apply(xs, xt, U, "circle_wp", float(p), tm, tp, tol)  # (B,)
 
 
 def euclid_sliced_w(x, y, theta, p=2.0):
@@ -581,11 +662,5 @@ def euclid_sliced_w(x, y, theta, p=2.0):
     yc, _ = _as_cloud(y, "y")
     if xc.shape[1] != yc.shape[1]:
         raise ValueError("Euclidean sliced W needs equally sized clouds")
-    theta = theta.to(device=xc.device, dtype=torch.float32).contiguous()
-    kx = ProjectLineFn.apply(xc, theta)
-    ky = ProjectLineFn.apply(yc, theta)
-    B, P, n = kx.shape
-    sx, _ = SegmentedSortFn.apply(kx.reshape(B * P, n))
-    sy, _ = SegmentedSortFn.apply(ky.reshape(B * P, n))
-    acc = EuclidSWFn.apply(sx, sy, float(p)).reshape(B, P)
-    return acc.mean(dim=1).pow(1.0 / p)
+    theta = theta.to(device=xc.device, dtype=torch.float32)
+    return SlicedLossFn.apply(xc, yc, theta, "line", float(p), 0.0, 0.0, 0.0).pow(1.0 / p)
