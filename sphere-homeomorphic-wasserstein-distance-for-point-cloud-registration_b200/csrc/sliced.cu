@@ -353,16 +353,18 @@ __device__ __forceinline__ float block_sum_bcast(float v, float* wtot) {
   return t;
 }
 
-constexpr int CW1_PER_THREAD = 40;  // merged entries per thread (n + m <= 256 * 40 = 10240)
+constexpr int CW1_THREADS = 512;     // 16 warps: with C <= 16 entries per thread (n + m <= 8192) 64 registers -> two CTAs, 32 warps per SM
+constexpr int CW1_WARPS = CW1_THREADS / 32;
+constexpr int CW1_PER_THREAD = 20;   // merged entries per thread (n + m <= 512 * 20 = 10240)
 
 // Fixed-order block sum with ONE barrier: the per-warp partials ping-pong between two shared-memory rows.
-__device__ __forceinline__ float block_sum_pp(float v, float (*wf)[SORT_WARPS], int& phase) {
+__device__ __forceinline__ float block_sum_pp(float v, float (*wf)[CW1_WARPS], int& phase) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) wf[phase][threadIdx.x >> 5] = v;
   __syncthreads();
   float t = 0.f;
 #pragma unroll
-  for (int w = 0; w < SORT_WARPS; ++w) t += wf[phase][w];
+  for (int w = 0; w < CW1_WARPS; ++w) t += wf[phase][w];
   phase ^= 1;
   return t;
 }
@@ -386,26 +388,26 @@ __host__ __device__ __forceinline__ int cw1_pad(int i) { return i + (i >> 5); }
 // inside the run of entries equal to f), found by bisection on the 32-bit order-preserving key of F -- 32 rounds of a
 // register-resident partial sum + a fixed-order block reduction -- instead of a radix sort of n + m records.
 template <int C>
-__global__ void __launch_bounds__(SORT_THREADS, (C <= 32 ? 2 : 1))
+__global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
     circular_w1_kernel(const float* __restrict__ us, const float* __restrict__ vs, const int32_t* __restrict__ pu,
                        const int32_t* __restrict__ pv, int n, int m, float* __restrict__ w_out, float* __restrict__ gus,
                        float* __restrict__ gvs) {
   extern __shared__ float cw1_smem[];
-  __shared__ float wf[2][SORT_WARPS];
-  __shared__ float s_first[SORT_THREADS];  // first merged value of each thread's chunk
-  __shared__ float s_lastF[SORT_THREADS];  // F at the last entry of each thread's chunk
-  __shared__ uint32_t s_kmin[SORT_WARPS];
+  __shared__ float wf[2][CW1_WARPS];
+  __shared__ float s_first[CW1_THREADS];  // first merged value of each thread's chunk
+  __shared__ float s_lastF[CW1_THREADS];  // F at the last entry of each thread's chunk
+  __shared__ uint32_t s_kmin[CW1_WARPS];
   const int nm = n + m;
   float* su = cw1_smem;                 // n (padded)
   float* sv = su + cw1_pad(n - 1) + 1;  // m (padded)
   const size_t s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float wu = 1.f / n, wv = 1.f / m;
-  for (int i = tid; i < n; i += SORT_THREADS) su[cw1_pad(i)] = __ldg(us + s * n + i);
-  for (int j = tid; j < m; j += SORT_THREADS) sv[cw1_pad(j)] = __ldg(vs + s * m + j);
+  for (int i = tid; i < n; i += CW1_THREADS) su[cw1_pad(i)] = __ldg(us + s * n + i);
+  for (int j = tid; j < m; j += CW1_THREADS) sv[cw1_pad(j)] = __ldg(vs + s * m + j);
   __syncthreads();
   // ---- merge path: u goes first on ties (u_i lands at i + #{v < u_i}; v_j at j + #{u <= v_j})
-  const int c = (nm + SORT_THREADS - 1) / SORT_THREADS;  // <= C
+  const int c = (nm + CW1_THREADS - 1) / CW1_THREADS;  // <= C
   const int d0 = min(nm, tid * c), d1 = min(nm, d0 + c);
   const int cnt = d1 - d0;
   int i0, j0;
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(SORT_THREADS, (C <= 32 ? 2 : 1))
   }
   uint32_t key[C];  // first the merged value bits, later key(F_k)
   float dl[C];
-  uint64_t from_u = 0ull;
+  uint32_t from_u = 0u;
   float wsum = 0.f;  // chunk total of +-w, summed in merged order
   {
     int i = i0, j = j0;
@@ -433,7 +435,7 @@ __global__ void __launch_bounds__(SORT_THREADS, (C <= 32 ? 2 : 1))
         const bool take_u = (j >= m) || (i < n && cu <= cv);
         const float v = take_u ? cu : cv;
         if (take_u) {
-          from_u |= 1ull << q;
+          from_u |= 1u << q;
           wsum += wu;
           ++i;
           if (i < n) cu = su[cw1_pad(i)];
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(SORT_THREADS, (C <= 32 ? 2 : 1))
     for (int q = 0; q < C; ++q) {
       key[q] = 0xFFFFFFFFu;
       if (q < cnt) {
-        run += ((from_u >> q) & 1ull) ? wu : -wv;
+        run += ((from_u >> q) & 1u) ? wu : -wv;
         key[q] = float_sort_key(run);
         kmin = min(kmin, key[q]);
       }
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(SORT_THREADS, (C <= 32 ? 2 : 1))
     __syncthreads();
     kmed = s_kmin[0];
 #pragma unroll
-    for (int w = 1; w < SORT_WARPS; ++w) kmed = min(kmed, s_kmin[w]);
+    for (int w = 1; w < CW1_WARPS; ++w) kmed = min(kmed, s_kmin[w]);
   }
   const float med = float_from_sort_key(kmed);
   // ---- W and dW/d(merged value), the latter parked in su / sv (dead since the merge) for a coalesced write-out
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(SORT_THREADS, (C <= 32 ? 2 : 1))
         const float a = fabsf(float_from_sort_key(key[q]) - med);
         acc += dl[q] * a;
         if (want_g) {
-          if ((from_u >> q) & 1ull) su[cw1_pad(i++)] = aprev - a; else sv[cw1_pad(j++)] = aprev - a;
+          if ((from_u >> q) & 1u) su[cw1_pad(i++)] = aprev - a; else sv[cw1_pad(j++)] = aprev - a;
         }
         aprev = a;
       }
@@ -536,9 +538,9 @@ __global__ void __launch_bounds__(SORT_THREADS, (C <= 32 ? 2 : 1))
   if (tid == 0) w_out[s] = acc;
   // pu / pv given: the gradient goes straight to the UNSORTED key positions (the scatter torch.sort's backward would do)
   if (gus)
-    for (int i = tid; i < n; i += SORT_THREADS) gus[s * n + (pu ? __ldg(pu + s * n + i) : i)] = su[cw1_pad(i)];
+    for (int i = tid; i < n; i += CW1_THREADS) gus[s * n + (pu ? __ldg(pu + s * n + i) : i)] = su[cw1_pad(i)];
   if (gvs)
-    for (int j = tid; j < m; j += SORT_THREADS) gvs[s * m + (pv ? __ldg(pv + s * m + j) : j)] = sv[cw1_pad(j)];
+    for (int j = tid; j < m; j += CW1_THREADS) gvs[s * m + (pv ? __ldg(pv + s * m + j) : j)] = sv[cw1_pad(j)];
 }
 
 template <int C>
@@ -547,7 +549,7 @@ static int launch_circular_w1(const float* us, const float* vs, const int32_t* p
   const size_t smem = (size_t)(cw1_pad(n - 1) + 1 + cw1_pad(m - 1) + 1) * sizeof(float);
   if (smem > 48 * 1024)
     SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_w1_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  circular_w1_kernel<C><<<S, SORT_THREADS, smem, stream>>>(us, vs, pu, pv, n, m, w, gus, gvs);
+  circular_w1_kernel<C><<<S, CW1_THREADS, smem, stream>>>(us, vs, pu, pv, n, m, w, gus, gvs);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }
@@ -669,13 +671,13 @@ static int circular_w1_dispatch(const float* us, const float* vs, const int32_t*
   if (!us || !vs || !w || S < 0 || n <= 0 || m <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (S == 0) return SHWD_OK;
   const size_t nm = (size_t)n + m;
-  if (nm > (size_t)SORT_THREADS * CW1_PER_THREAD) return SHWD_ERR_UNSUPPORTED;  // n + m <= 10240 (register-resident entries)
-  const int c = (int)((nm + SORT_THREADS - 1) / SORT_THREADS);
+  if (nm > (size_t)CW1_THREADS * CW1_PER_THREAD) return SHWD_ERR_UNSUPPORTED;  // n + m <= 10240 (register-resident entries)
+  const int c = (int)((nm + CW1_THREADS - 1) / CW1_THREADS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c <= 4) return launch_circular_w1<4>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
   if (c <= 8) return launch_circular_w1<8>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
+  if (c <= 12) return launch_circular_w1<12>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
   if (c <= 16) return launch_circular_w1<16>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
-  if (c <= 24) return launch_circular_w1<24>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
-  if (c <= 32) return launch_circular_w1<32>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
   return launch_circular_w1<CW1_PER_THREAD>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
 }
 

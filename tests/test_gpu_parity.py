@@ -355,7 +355,7 @@ def test_emd1d_circle_matches_reference_fixture(shwd):
 @pytest.mark.parametrize("S,n,m", [(5, 1, 1), (5, 7, 3), (4, 1024, 1024), (3, 1500, 1500), (3, 3000, 2500), (3, 4096, 4096),
                                    (2, 5000, 4800), (2, 5120, 5120)])
 def test_emd1d_circle_matches_oracle_every_bucket(shwd, S, n, m):
-    """circular_w1_kernel<C> keeps C merged entries per thread in registers (C = 8, 16, 24, 32, 40 by n + m): values and
+    """circular_w1_kernel<C> keeps C merged entries per thread in registers (C = 4, 8, 12, 16, 20 by n + m): values and
     the gradients w.r.t. the unsorted circle coordinates against emd1D_circle (oracle/sliced.py) in every bucket."""
     uv = _tie_free(S, n + m, 100 + n)  # one shuffled tie-free row split in two: no u == v tie either (a tie's order in
     u0, v0 = uv[:, :n].contiguous(), uv[:, n:].contiguous()  # the merged sort decides two gradient entries)
