@@ -6,19 +6,40 @@
 // The squared distance is formed as ((dx*dx + dy*dy) + dz*dz) with separately rounded products so it is bit-equal to
 // torch's ((x-y)**2).sum(-1) -- the argmin indices are then bit-exact against the oracle.
 //
-// One thread owns one query point; the other cloud is streamed through shared memory as float4 records (broadcast
-// LDS.128), 1024 points per tile.  HBM traffic is the algorithmic minimum (12 B/point in, 8 B/point out); the inner
-// loop is FP32-issue bound (8 FP32 + compare/select per pair of points).
+// Forward: one thread owns one query point; the other cloud is streamed through shared memory in SoA form (three
+// LDS.128 feed four candidates), 1024 points per tile.  The eight float32 operations of a squared distance run as
+// packed f32x2 instructions on two candidates at once (same roundings, half the issue slots), and the running argmin
+// is updated through a min tree: `min(d0..d3) < best` is false for almost every group of four (a query's best improves
+// O(log n) times), so the compare / select chain of the first version -- three ALU instructions per candidate on top of
+// the eight FP32 ones, which made the loop issue-bound -- only runs on those rare groups, in index order with a strict
+// '<' (the first minimum still wins).  HBM traffic is the algorithmic minimum (12 B/point in, 8 B/point out); the loop
+// is bound by the FMA pipe: 8 lane-ops per (query, candidate).
+// Backward: the gather  sum_{j : nn_r(j) == i}  is found per WARP: a warp owns 32 consecutive queries, its lanes test 32
+// candidates at a time for "nn_r(j) in my warp's range" (one subtract + compare + ballot per 32 candidates instead of a
+// compare per (query, candidate)), and the few hits are applied by the owning lane in ascending j -- the same order, and
+// the same bits, as a sequential scan.
 #include "common.cuh"
+#include "f32x2.cuh"
 
 namespace shwd {
 
 constexpr int CH_THREADS = 256;
 constexpr int CH_TILE = 1024;
 
-__device__ __forceinline__ float sqdist(float ax, float ay, float az, float4 s) {
-  float dx = ax - s.x, dy = ay - s.y, dz = az - s.z;
+__device__ __forceinline__ float sqdist(float ax, float ay, float az, float sx, float sy, float sz) {
+  float dx = ax - sx, dy = ay - sy, dz = az - sz;
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+// the same on two candidates: ((dx*dx + dy*dy) + dz*dz), every product and sum rounded separately
+__device__ __forceinline__ f2 sqdist2(f2 ax, f2 ay, f2 az, f2 sx, f2 sy, f2 sz) {
+  const f2 dx = sub2(ax, sx), dy = sub2(ay, sy), dz = sub2(az, sz);
+  // The products stay SCALAR (__fmul_rn): ptxas contracts mul.rn.f32x2 + add.rn.f32x2 (and fma(d, d, -0) + add) into
+  // FFMA2, which drops the product's rounding -- the last bit of the distance and, on near ties, the argmin would differ
+  // from torch.  Differences and sums are packed.
+  const f2 px = mk2(__fmul_rn(lo2(dx), lo2(dx)), __fmul_rn(hi2(dx), hi2(dx)));
+  const f2 py = mk2(__fmul_rn(lo2(dy), lo2(dy)), __fmul_rn(hi2(dy), hi2(dy)));
+  const f2 pz = mk2(__fmul_rn(lo2(dz), lo2(dz)), __fmul_rn(hi2(dz), hi2(dz)));
+  return add2(add2(px, py), pz);
 }
 
 // grid.x = query blocks of direction 0 (x queries) followed by direction 1 (y queries); grid.y = B
@@ -26,7 +47,9 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const float* __
                                                                  int M, int blocks_x, float* __restrict__ d_xy,
                                                                  int* __restrict__ idx_xy, float* __restrict__ d_yx,
                                                                  int* __restrict__ idx_yx) {
-  __shared__ float4 tile[CH_TILE];
+  __shared__ __align__(16) float tx[CH_TILE];
+  __shared__ __align__(16) float ty[CH_TILE];
+  __shared__ __align__(16) float tz[CH_TILE];
   const int b = blockIdx.y;
   const bool dir = blockIdx.x >= blocks_x;  // false: x queries against y
   const int qb = dir ? blockIdx.x - blocks_x : blockIdx.x;
@@ -40,29 +63,34 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const float* __
     ay = __ldg(q + 3 * i + 1);
     az = __ldg(q + 3 * i + 2);
   }
+  const f2 ax2 = bc2(ax), ay2 = bc2(ay), az2 = bc2(az);
   float best = INFINITY;
   int bi = 0;
   for (int t0 = 0; t0 < nr; t0 += CH_TILE) {
     const int cnt = min(CH_TILE, nr - t0);
     __syncthreads();
     for (int j = threadIdx.x; j < CH_TILE; j += CH_THREADS) {
-      float4 v = make_float4(INFINITY, INFINITY, INFINITY, 0.f);  // padding never wins: distance = +inf (or NaN)
-      if (j < cnt) v = make_float4(__ldg(r + 3 * (t0 + j)), __ldg(r + 3 * (t0 + j) + 1), __ldg(r + 3 * (t0 + j) + 2), 0.f);
-      tile[j] = v;
+      const bool in = j < cnt;  // padding never wins: distance = +inf (or NaN)
+      tx[j] = in ? __ldg(r + 3 * (t0 + j)) : INFINITY;
+      ty[j] = in ? __ldg(r + 3 * (t0 + j) + 1) : INFINITY;
+      tz[j] = in ? __ldg(r + 3 * (t0 + j) + 2) : INFINITY;
     }
     __syncthreads();
     const int lim = (cnt + 3) & ~3;
 #pragma unroll 2
     for (int j = 0; j < lim; j += 4) {
-      float d0 = sqdist(ax, ay, az, tile[j]);
-      float d1 = sqdist(ax, ay, az, tile[j + 1]);
-      float d2 = sqdist(ax, ay, az, tile[j + 2]);
-      float d3 = sqdist(ax, ay, az, tile[j + 3]);
-      // strict '<' in index order keeps the first minimum
-      if (d0 < best) { best = d0; bi = t0 + j; }
-      if (d1 < best) { best = d1; bi = t0 + j + 1; }
-      if (d2 < best) { best = d2; bi = t0 + j + 2; }
-      if (d3 < best) { best = d3; bi = t0 + j + 3; }
+      const float4 X = *reinterpret_cast<const float4*>(tx + j), Y = *reinterpret_cast<const float4*>(ty + j);
+      const float4 Z = *reinterpret_cast<const float4*>(tz + j);
+      const f2 d01 = sqdist2(ax2, ay2, az2, mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y));
+      const f2 d23 = sqdist2(ax2, ay2, az2, mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w));
+      const float d0 = lo2(d01), d1 = hi2(d01), d2 = lo2(d23), d3 = hi2(d23);
+      if (fminf(fminf(d0, d1), fminf(d2, d3)) < best) {
+        // strict '<' in index order keeps the first minimum
+        if (d0 < best) { best = d0; bi = t0 + j; }
+        if (d1 < best) { best = d1; bi = t0 + j + 1; }
+        if (d2 < best) { best = d2; bi = t0 + j + 2; }
+        if (d3 < best) { best = d3; bi = t0 + j + 3; }
+      }
     }
   }
   if (i < nq) {
@@ -76,14 +104,14 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const float* __
   }
 }
 
-// gq_i = 2 g_i (q_i - r_{nn(i)})  +  sum_{j : nn_r(j) == i} 2 h_j (q_i - r_j), the second sum gathered by scanning the
-// other cloud's argmin list in index order (deterministic; no float atomics).
+// gq_i = 2 g_i (q_i - r_{nn(i)})  +  sum_{j : nn_r(j) == i} 2 h_j (q_i - r_j), the second sum in ascending j
+// (deterministic; no float atomics).
 __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int N,
                                                                  int M, int blocks_x, const int* __restrict__ idx_xy,
                                                                  const int* __restrict__ idx_yx, const float* __restrict__ gdx,
                                                                  const float* __restrict__ gdy, float* __restrict__ gx,
                                                                  float* __restrict__ gy) {
-  __shared__ float4 tile[CH_TILE];  // (r_j, h_j)
+  __shared__ float4 tile[CH_TILE];  // (r_j, 2 h_j)
   __shared__ int tidx[CH_TILE];
   const int b = blockIdx.y;
   const bool dir = blockIdx.x >= blocks_x;
@@ -97,6 +125,8 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const float* __
   const float* gr = dir ? gdx + (size_t)b * N : gdy + (size_t)b * M;
   float* out = dir ? gy + (size_t)b * M * 3 : gx + (size_t)b * N * 3;
   const int i = qb * CH_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int wbase = i - lane;  // first query of this warp
   float ax = 0.f, ay = 0.f, az = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
   if (i < nq) {
     ax = __ldg(q + 3 * i);
@@ -122,12 +152,18 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const float* __
       tidx[j] = k;
     }
     __syncthreads();
-    for (int j = 0; j < cnt; ++j) {
-      if (tidx[j] == i) {
-        float4 s = tile[j];
-        ox = fmaf(s.w, ax - s.x, ox);
-        oy = fmaf(s.w, ay - s.y, oy);
-        oz = fmaf(s.w, az - s.z, oz);
+    for (int j0 = 0; j0 < cnt; j0 += 32) {  // padding entries hold -1: never inside [wbase, wbase + 32)
+      const int own = tidx[j0 + lane] - wbase;  // which lane of this warp candidate j0 + lane belongs to, if any
+      unsigned hits = __ballot_sync(0xffffffffu, (unsigned)own < 32u);
+      while (hits) {
+        const int l = __ffs(hits) - 1;
+        hits &= hits - 1;
+        if (__shfl_sync(0xffffffffu, own, l) == lane) {
+          const float4 s = tile[j0 + l];
+          ox = fmaf(s.w, ax - s.x, ox);
+          oy = fmaf(s.w, ay - s.y, oy);
+          oz = fmaf(s.w, az - s.z, oz);
+        }
       }
     }
   }
