@@ -8,15 +8,19 @@
 //   ONE_MINUS_COS  (1-<x^,y^>)^p            losses/max_spherical_w_cos_with_regulation.py:745
 //   n_power        C^N                      Comparison_.../losses/sinkhorn.py:165-176 (log_N_Sinkhorn)
 //
-// Two hand-tuned fast paths (geodesic p=2 -- the north-star configuration -- and squared-Euclidean p=2) plus one
-// generic path that covers every other (kind, p, n_power).
+// Four hand-tuned fast paths -- geodesic p=2 (the north-star configuration), squared-Euclidean p=2 (what train_W_COS.py:393
+// instantiates), and their p=1 siblings: geodesic p=1 (the default p of Geodesic_distance_W, s2_wasserstein.py:74) and
+// the L1 cost sum_k |x_k-y_k| (Cos_disimilarity_W(p=1), Optimize_hyperparameters/train_W1_COS.py:393; type_of_cost_norm
+// 'L1') -- plus one generic path that covers every other (kind, p, n_power).
 #pragma once
 #include "common.cuh"
 #include <math.h>
 
 namespace shwd {
 
-enum { FAST_GEO2 = 0, FAST_SQE2 = 1, GENERIC = 2 };
+enum { FAST_GEO2 = 0, FAST_SQE2 = 1, GENERIC = 2, FAST_GEO1 = 3, FAST_SQE1 = 4 };
+__host__ __device__ constexpr bool fast_is_geo(int f) { return f == FAST_GEO2 || f == FAST_GEO1; }
+__host__ __device__ constexpr bool fast_is_sqe(int f) { return f == FAST_SQE2 || f == FAST_SQE1; }
 
 struct CostParams {
   int kind;
@@ -69,17 +73,19 @@ __device__ __forceinline__ float dot3(float ox, float oy, float oz, float sx, fl
 template <int FAST>
 struct Cost {
   struct E {
-    float a;  // FAST_GEO2: th = sqrt(k)*theta | FAST_SQE2: |x-y|^2 | GENERIC: k*C
+    float a;  // FAST_GEO2 / FAST_GEO1: th = sqrt(k)*theta | FAST_SQE2: |x-y|^2 | FAST_SQE1: |x-y|_1 | GENERIC: k*C
   };
 
   static __device__ __forceinline__ float m(const CostParams& cp, E e, float pot) {
     if (FAST == FAST_GEO2) return fmaf(-e.a, e.a, pot);
-    if (FAST == FAST_SQE2) return fmaf(-cp.k, e.a, pot);
+    if (FAST == FAST_GEO1) return fmaf(-cp.sk, e.a, pot);
+    if (fast_is_sqe(FAST)) return fmaf(-cp.k, e.a, pot);
     return __fsub_rn(pot, e.a);
   }
   static __device__ __forceinline__ float kc(const CostParams& cp, E e) {
     if (FAST == FAST_GEO2) return __fmul_rn(e.a, e.a);
-    if (FAST == FAST_SQE2) return __fmul_rn(cp.k, e.a);
+    if (FAST == FAST_GEO1) return __fmul_rn(cp.sk, e.a);
+    if (fast_is_sqe(FAST)) return __fmul_rn(cp.k, e.a);
     return e.a;
   }
 
@@ -87,11 +93,13 @@ struct Cost {
   static __device__ __forceinline__ E eval(const CostParams& cp, float ox, float oy, float oz, float sx, float sy,
                                            float sz) {
     E e;
-    if (FAST == FAST_GEO2) {
+    if (fast_is_geo(FAST)) {
       e.a = scaled_acos(cp.q, cp.hpi, dot3(ox, oy, oz, sx, sy, sz));
     } else if (FAST == FAST_SQE2) {
       float dx = ox - sx, dy = oy - sy, dz = oz - sz;
       e.a = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    } else if (FAST == FAST_SQE1) {
+      e.a = (fabsf(ox - sx) + fabsf(oy - sy)) + fabsf(oz - sz);
     } else {
       float C;
       if (cp.kind == SHWD_COST_GEODESIC || cp.kind == SHWD_COST_ONE_MINUS_COS) {
@@ -129,6 +137,14 @@ struct Cost {
       gx = sx;
       gy = sy;
       gz = sz;
+    } else if (FAST == FAST_GEO1) {
+      // C = theta, d(kC)/dx^ = -k rsqrt(1-c^2) y^ = (-sqrt(k)) * [sqrt(k) rs] ... the constant -k is cp.gscale
+      float c = dot3(ox, oy, oz, sx, sy, sz);
+      e.a = scaled_acos(cp.q, cp.hpi, c);
+      gs = rsqrt_approx(fmaxf(fmaf(-c, c, 1.f), 1e-12f));
+      gx = sx;
+      gy = sy;
+      gz = sz;
     } else if (FAST == FAST_SQE2) {
       float dx = ox - sx, dy = oy - sy, dz = oz - sz;  // gscale = 2k
       gs = 1.f;
@@ -136,6 +152,13 @@ struct Cost {
       gy = dy;
       gz = dz;
       e.a = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    } else if (FAST == FAST_SQE1) {
+      float dx = ox - sx, dy = oy - sy, dz = oz - sz;  // gscale = k; d|d|/dd = sign(d), 0 at 0 (torch.abs backward)
+      gs = 1.f;
+      gx = (dx > 0.f) - (dx < 0.f);
+      gy = (dy > 0.f) - (dy < 0.f);
+      gz = (dz > 0.f) - (dz < 0.f);
+      e.a = (fabsf(dx) + fabsf(dy)) + fabsf(dz);
     } else {
       float C, dCx, dCy, dCz;  // gscale = k
       if (cp.kind == SHWD_COST_GEODESIC || cp.kind == SHWD_COST_ONE_MINUS_COS) {
@@ -218,6 +241,8 @@ struct Cost {
 inline int pick_fast(int kind, float p, float npow) {
   if (kind == SHWD_COST_GEODESIC && p == 2.f && npow == 1.f) return FAST_GEO2;
   if (kind == SHWD_COST_SQEUCLID && p == 2.f && npow == 1.f) return FAST_SQE2;
+  if (kind == SHWD_COST_GEODESIC && p == 1.f && npow == 1.f) return FAST_GEO1;
+  if ((kind == SHWD_COST_SQEUCLID || kind == SHWD_COST_EUCLID) && p == 1.f && npow == 1.f) return FAST_SQE1;  // (s)^(1/1) = s
   return GENERIC;
 }
 
@@ -230,10 +255,10 @@ inline CostParams make_cost(int kind, float p, float npow, float eps, int fast) 
   cp.k = (float)k;
   cp.sk = (float)sqrt(k);
   const float q[7] = SHWD_ACOS_Q;
-  const double qs = (fast == FAST_GEO2) ? sqrt(k) : 1.0;
+  const double qs = fast_is_geo(fast) ? sqrt(k) : 1.0;
   for (int i = 0; i < 7; ++i) cp.q[i] = (float)(qs * (double)q[i]);
   cp.hpi = (float)(qs * 1.5707963267948966);
-  cp.gscale = (fast == FAST_GEO2) ? (float)(-2.0 * sqrt(k)) : ((fast == FAST_SQE2) ? (float)(2.0 * k) : (float)k);
+  cp.gscale = (fast == FAST_GEO2) ? (float)(-2.0 * sqrt(k)) : (fast == FAST_GEO1) ? (float)(-k) : (fast == FAST_SQE2) ? (float)(2.0 * k) : (float)k;
   return cp;
 }
 

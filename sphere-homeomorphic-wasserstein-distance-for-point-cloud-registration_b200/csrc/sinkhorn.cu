@@ -531,16 +531,23 @@ __device__ __forceinline__ f2 dot3_2(float ox, float oy, float oz, f2 X, f2 Y, f
 // th = sqrt(k) theta; SQE2: |o - s|^2); pk_m: the canonical exponent Cost<FAST>::m(e, pot), bit-identical to the scalar one.
 template <int FAST>
 __device__ __forceinline__ f2 pk_e(const CostParams& cp, const float4& o, f2 X, f2 Y, f2 Z) {
-  if (FAST == FAST_GEO2) return scaled_acos2(cp.q, cp.hpi, dot3_2(o.x, o.y, o.z, X, Y, Z));
+  if (fast_is_geo(FAST)) return scaled_acos2(cp.q, cp.hpi, dot3_2(o.x, o.y, o.z, X, Y, Z));
   const f2 dx = sub2(bc2(o.x), X), dy = sub2(bc2(o.y), Y), dz = sub2(bc2(o.z), Z);
+  if (FAST == FAST_SQE1) return add2(add2(abs2(dx), abs2(dy)), abs2(dz));
   return fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
 }
 template <int FAST>
 __device__ __forceinline__ f2 pk_m(const CostParams& cp, f2 e, f2 pot) {
   if (FAST == FAST_GEO2) return fma2(neg2(e), e, pot);
+  if (FAST == FAST_GEO1) return fma2(bc2(-cp.sk), e, pot);
   return fma2(bc2(-cp.k), e, pot);
 }
-__host__ __device__ constexpr bool is_packed_cost(int fast) { return fast == FAST_GEO2 || fast == FAST_SQE2; }
+__host__ __device__ constexpr bool is_packed_cost(int fast) { return fast_is_geo(fast) || fast_is_sqe(fast); }
+// sign(d) per half, 0 at 0 (torch.abs backward)
+__device__ __forceinline__ f2 sign2(f2 d) {
+  const float a = lo2(d), b = hi2(d);  // FSET (1.0 / 0.0) + LOP3 (sign copy) per half
+  return mk2(copysignf(a != 0.f ? 1.f : 0.f, a), copysignf(b != 0.f ? 1.f : 0.f, b));
+}
 
 // One (R owner groups, warp-slice) pass of a regular geodesic-p2 sweep in packed arithmetic: every lane owns R points
 // (one per group) and shares each streamed record between them, so one LDS.128 per array feeds 4R elements.
@@ -657,13 +664,13 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const 
         const f2 a2 = h ? mk2(A.z, A.w) : mk2(A.x, A.y), s2 = h ? mk2(S.z, S.w) : mk2(S.x, S.y);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (FAST == FAST_GEO2) {
+          if (fast_is_geo(FAST)) {
             const f2 c = dot3_2(op[r].x, op[r].y, op[r].z, x2, y2, z2);
             const f2 th = scaled_acos2(cp.q, cp.hpi, c);
             const f2 om = fma2(neg2(c), c, bc2(1.f));
             const f2 rs = mk2(rsqrt_approx(fmaxf(lo2(om), 1e-12f)), rsqrt_approx(fmaxf(hi2(om), 1e-12f)));
-            const f2 gs = mul2(th, rs);
-            const f2 nth = neg2(th);
+            const f2 gs = (FAST == FAST_GEO2) ? mul2(th, rs) : rs;             // p = 1: d(k theta)/dc = -k rs (constant in gscale)
+            const f2 nth = (FAST == FAST_GEO2) ? neg2(th) : bc2(-cp.sk);      // -kC = nth * th in both cases
             const f2 S1 = ex2_2(add2(fma2(nth, th, bc2(opot1[r])), s2));
             const f2 S2 = ex2_2(add2(fma2(nth, th, p2), bc2(o2[r])));
             const f2 w1 = mul2(a2, S1);
@@ -672,18 +679,19 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const 
             ax[r] = fma2(wg, x2, ax[r]);
             ay[r] = fma2(wg, y2, ay[r]);
             az[r] = fma2(wg, z2, az[r]);
-          } else {  // squared Euclidean: kC = k |o - s|^2, d(kC)/d(owner) = 2k (o - s) (2k = cp.gscale, applied per owner)
+          } else {  // squared Euclidean: kC = k |o - s|^2, d(kC)/d(owner) = 2k (o - s) (2k = cp.gscale, applied per owner);
+                    // L1: kC = k |o - s|_1, d(kC)/d(owner) = k sign(o - s)
             const f2 dx = sub2(bc2(op[r].x), x2), dy = sub2(bc2(op[r].y), y2), dz = sub2(bc2(op[r].z), z2);
-            const f2 sq = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            const f2 sq = (FAST == FAST_SQE1) ? add2(add2(abs2(dx), abs2(dy)), abs2(dz)) : fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
             const f2 nk = bc2(-cp.k);
             const f2 S1 = ex2_2(add2(fma2(nk, sq, bc2(opot1[r])), s2));
             const f2 S2 = ex2_2(add2(fma2(nk, sq, p2), bc2(o2[r])));
             const f2 w1 = mul2(a2, S1);
             aw[r] = add2(aw[r], w1);
             const f2 wg = fma2(bc2(oadj[r]), S2, w1);
-            ax[r] = fma2(wg, dx, ax[r]);
-            ay[r] = fma2(wg, dy, ay[r]);
-            az[r] = fma2(wg, dz, az[r]);
+            ax[r] = fma2(wg, (FAST == FAST_SQE1) ? sign2(dx) : dx, ax[r]);
+            ay[r] = fma2(wg, (FAST == FAST_SQE1) ? sign2(dy) : dy, ay[r]);
+            az[r] = fma2(wg, (FAST == FAST_SQE1) ? sign2(dz) : dz, az[r]);
           }
         }
       }
@@ -1532,6 +1540,8 @@ extern "C" int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N,
   switch (fast) {
     case FAST_GEO2: return launch_persistent(sinkhorn_fwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
     case FAST_SQE2: return launch_persistent(sinkhorn_fwd_kernel<FAST_SQE2>, prm, smem, maxg, s);
+    case FAST_GEO1: return launch_persistent(sinkhorn_fwd_kernel<FAST_GEO1>, prm, smem, maxg, s);
+    case FAST_SQE1: return launch_persistent(sinkhorn_fwd_kernel<FAST_SQE1>, prm, smem, maxg, s);
     default: return launch_persistent(sinkhorn_fwd_kernel<GENERIC>, prm, smem, maxg, s);
   }
 }
@@ -1589,6 +1599,8 @@ extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N,
   switch (fast) {
     case FAST_GEO2: return launch_persistent(sinkhorn_bwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
     case FAST_SQE2: return launch_persistent(sinkhorn_bwd_kernel<FAST_SQE2>, prm, smem, maxg, s);
+    case FAST_GEO1: return launch_persistent(sinkhorn_bwd_kernel<FAST_GEO1>, prm, smem, maxg, s);
+    case FAST_SQE1: return launch_persistent(sinkhorn_bwd_kernel<FAST_SQE1>, prm, smem, maxg, s);
     default: return launch_persistent(sinkhorn_bwd_kernel<GENERIC>, prm, smem, maxg, s);
   }
 }
@@ -1612,6 +1624,12 @@ extern "C" int shwd_sinkhorn_plan_dense(const float* x4, const float* y4, int B,
       break;
     case FAST_SQE2:
       plan_dense_kernel<FAST_SQE2><<<grid, block, 0, s>>>(X, Y, N, M, cp, alpha, beta, level_stride_n, level_stride_m, inv_k, P, C);
+      break;
+    case FAST_GEO1:
+      plan_dense_kernel<FAST_GEO1><<<grid, block, 0, s>>>(X, Y, N, M, cp, alpha, beta, level_stride_n, level_stride_m, inv_k, P, C);
+      break;
+    case FAST_SQE1:
+      plan_dense_kernel<FAST_SQE1><<<grid, block, 0, s>>>(X, Y, N, M, cp, alpha, beta, level_stride_n, level_stride_m, inv_k, P, C);
       break;
     default:
       plan_dense_kernel<GENERIC><<<grid, block, 0, s>>>(X, Y, N, M, cp, alpha, beta, level_stride_n, level_stride_m, inv_k, P, C);

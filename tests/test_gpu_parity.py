@@ -184,6 +184,30 @@ def test_generic_cost_path(shwd, kind, p, eps):
     assert rel(gy, gy32) < max(TOL, 8 * rel(gy32, gy64))
 
 
+@pytest.mark.parametrize("kind,p,B,N,M,L,eps", [("geodesic", 1, 3, 300, 260, 30, 0.02), ("geodesic", 1, 2, 1024, 1024, 50, 0.01),
+                                                ("sqeuclid", 1, 3, 300, 260, 30, 0.02), ("euclid", 1, 2, 1024, 1024, 50, 0.02),
+                                                ("sqeuclid", 1, 2, 700, 2300, 10, 0.05)])
+def test_p1_fast_costs_match_oracle(shwd, kind, p, B, N, M, L, eps):
+    """The packed fast paths for geodesic p = 1 (default p of Geodesic_distance_W, s2_wasserstein.py:74) and the L1 cost
+    (Cos_disimilarity_W(p=1), train_W1_COS.py:393; 'L1' of the Sinkhorn classes) on resident / chunked / ragged shapes.
+    Some points of y coincide with points of x: |d| has the sub-gradient sign(0) = 0 there (torch.abs backward)."""
+    torch.manual_seed(B * 13 + N)
+    x = F.normalize(torch.randn(B, N, 3), dim=-1)
+    y = F.normalize(torch.randn(B, M, 3) + 0.3, dim=-1)
+    if kind != "geodesic":  # exact coincidences (for the geodesic cost the reference returns NaN there, SURVEY.md B.1)
+        y[:, :16] = x[:, :16]
+        y[:, 20:24, 0] = x[:, 20:24, 0]
+    cost, gx, gy, _ = _run_cuda(shwd, x, y, kind, float(p), eps, L)
+    c32, gx32, gy32 = _run_oracle(x, y, kind, p, eps, L)
+    c64, gx64, gy64 = _run_oracle(x, y, kind, p, eps, L, dtype=torch.float64)
+    ok = torch.isfinite(c32) & torch.isfinite(gx32).flatten(1).all(1) & torch.isfinite(gy32).flatten(1).all(1)
+    assert ok.all() or kind == "geodesic"
+    assert ok.any() and torch.isfinite(cost).all() and torch.isfinite(gx).all() and torch.isfinite(gy).all()
+    assert rel(cost[ok], c32[ok]) < max(TOL, 8 * rel(c32[ok], c64[ok]))
+    assert rel(gx[ok], gx32[ok]) < max(TOL, 8 * rel(gx32[ok], gx64[ok]))
+    assert rel(gy[ok], gy32[ok]) < max(TOL, 8 * rel(gy32[ok], gy64[ok]))
+
+
 def test_known_answer_sinkhorn_fixed_smoke(shwd):
     """Point_Cloud_Resistration/losses/Sinkhorn_fixed.py:97-110: integer grids, eps 0.1, 10 iterations."""
     d = gold("sinkhorn_fixed_smoke")
@@ -847,3 +871,29 @@ def test_rigid_transform_matches_reference_fixture_and_oracle(shwd):
     ds = shwd.data.DeviceRegistrationPairs(big.to(dev()), big.to(dev()), seed=11)
     tgt, srcs, R, T = ds.batch([3, 1, 4])
     assert tgt.shape == (3, 1000, 3) and srcs.shape == (3, 1000, 3) and R.shape == (3, 3, 3) and T.shape == (3, 1, 3)
+
+
+# ------------------------------------------------------------------------------------- run-to-run reproducibility ----
+def test_sliced_and_chamfer_are_bit_reproducible(shwd):
+    """No float atomics and fixed-order reductions on these paths: two runs on the same inputs give the same bits (this
+    is also the race check for the shared-memory exchanges of circular_w1 / circular_wp / the projection backward --
+    compute-sanitizer is not available on the GPU pool)."""
+    g = torch.Generator().manual_seed(77)
+    x = F.normalize(torch.randn(2, 3000, 3, generator=g), dim=-1).to(dev())
+    y = F.normalize(torch.randn(2, 2500, 3, generator=g) + 0.2, dim=-1).to(dev())
+    U, _ = torch.linalg.qr(torch.randn(24, 3, 2, generator=g))
+    U = U.to(dev())
+
+    def run(fn):
+        xs, ys = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+        out = fn(xs, ys)
+        out.sum().backward()
+        return out.detach().clone(), xs.grad.clone(), ys.grad.clone()
+
+    fns = [lambda a, b: shwd.ops.spherical_sliced_w1(a, b, U), lambda a, b: shwd.ops.spherical_sliced_wp(a, b, U, 2.0),
+           lambda a, b: shwd.ops.spherical_sliced_wp(a, b, U, 3.0), lambda a, b: shwd.losses.chamfer_distance(a, b)[0]]
+    for fn in fns:
+        first = run(fn)
+        for _ in range(3):
+            again = run(fn)
+            assert all(torch.equal(p, q) for p, q in zip(first, again))
