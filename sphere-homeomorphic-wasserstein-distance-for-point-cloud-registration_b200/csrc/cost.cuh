@@ -11,16 +11,19 @@
 // Four hand-tuned fast paths -- geodesic p=2 (the north-star configuration), squared-Euclidean p=2 (what train_W_COS.py:393
 // instantiates), and their p=1 siblings: geodesic p=1 (the default p of Geodesic_distance_W, s2_wasserstein.py:74) and
 // the L1 cost sum_k |x_k-y_k| (Cos_disimilarity_W(p=1), Optimize_hyperparameters/train_W1_COS.py:393; type_of_cost_norm
-// 'L1') -- plus one generic path that covers every other (kind, p, n_power).
+// 'L1'), the Euclidean norm |x-y|_2 (log_Sinkhorn_Distance_Loss of Sinkhorn_fixed.py:79-89, 'L2') and (1-cos)^2
+// (max_spherical_w_cos_with_regulation.py:745) -- plus one generic path that covers every other (kind, p, n_power).
 #pragma once
 #include "common.cuh"
 #include <math.h>
 
 namespace shwd {
 
-enum { FAST_GEO2 = 0, FAST_SQE2 = 1, GENERIC = 2, FAST_GEO1 = 3, FAST_SQE1 = 4 };
-__host__ __device__ constexpr bool fast_is_geo(int f) { return f == FAST_GEO2 || f == FAST_GEO1; }
-__host__ __device__ constexpr bool fast_is_sqe(int f) { return f == FAST_SQE2 || f == FAST_SQE1; }
+enum { FAST_GEO2 = 0, FAST_SQE2 = 1, GENERIC = 2, FAST_GEO1 = 3, FAST_SQE1 = 4, FAST_EUC2 = 5, FAST_OMC2 = 6 };
+// "geo" family: the owner's gradient direction is the streamed point (cost is a function of the dot product);
+// "sqe" family: it is a function of the difference o - s and the exponent is pot - k * e
+__host__ __device__ constexpr bool fast_is_geo(int f) { return f == FAST_GEO2 || f == FAST_GEO1 || f == FAST_OMC2; }
+__host__ __device__ constexpr bool fast_is_sqe(int f) { return f == FAST_SQE2 || f == FAST_SQE1 || f == FAST_EUC2; }
 
 struct CostParams {
   int kind;
@@ -73,17 +76,18 @@ __device__ __forceinline__ float dot3(float ox, float oy, float oz, float sx, fl
 template <int FAST>
 struct Cost {
   struct E {
-    float a;  // FAST_GEO2 / FAST_GEO1: th = sqrt(k)*theta | FAST_SQE2: |x-y|^2 | FAST_SQE1: |x-y|_1 | GENERIC: k*C
+    float a;  // FAST_GEO2 / FAST_GEO1: th = sqrt(k)*theta | FAST_OMC2: sqrt(k)*(1-cos) | FAST_SQE2: |x-y|^2 | FAST_SQE1: |x-y|_1
+              // FAST_EUC2: |x-y|_2 | GENERIC: k*C
   };
 
   static __device__ __forceinline__ float m(const CostParams& cp, E e, float pot) {
-    if (FAST == FAST_GEO2) return fmaf(-e.a, e.a, pot);
+    if (FAST == FAST_GEO2 || FAST == FAST_OMC2) return fmaf(-e.a, e.a, pot);
     if (FAST == FAST_GEO1) return fmaf(-cp.sk, e.a, pot);
     if (fast_is_sqe(FAST)) return fmaf(-cp.k, e.a, pot);
     return __fsub_rn(pot, e.a);
   }
   static __device__ __forceinline__ float kc(const CostParams& cp, E e) {
-    if (FAST == FAST_GEO2) return __fmul_rn(e.a, e.a);
+    if (FAST == FAST_GEO2 || FAST == FAST_OMC2) return __fmul_rn(e.a, e.a);
     if (FAST == FAST_GEO1) return __fmul_rn(cp.sk, e.a);
     if (fast_is_sqe(FAST)) return __fmul_rn(cp.k, e.a);
     return e.a;
@@ -93,11 +97,14 @@ struct Cost {
   static __device__ __forceinline__ E eval(const CostParams& cp, float ox, float oy, float oz, float sx, float sy,
                                            float sz) {
     E e;
-    if (fast_is_geo(FAST)) {
+    if (FAST == FAST_OMC2) {
+      e.a = fmaf(-cp.sk, dot3(ox, oy, oz, sx, sy, sz), cp.sk);
+    } else if (fast_is_geo(FAST)) {
       e.a = scaled_acos(cp.q, cp.hpi, dot3(ox, oy, oz, sx, sy, sz));
-    } else if (FAST == FAST_SQE2) {
+    } else if (FAST == FAST_SQE2 || FAST == FAST_EUC2) {
       float dx = ox - sx, dy = oy - sy, dz = oz - sz;
       e.a = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      if (FAST == FAST_EUC2) e.a = sqrt_approx(e.a);
     } else if (FAST == FAST_SQE1) {
       e.a = (fabsf(ox - sx) + fabsf(oy - sy)) + fabsf(oz - sz);
     } else {
@@ -137,6 +144,22 @@ struct Cost {
       gx = sx;
       gy = sy;
       gz = sz;
+    } else if (FAST == FAST_OMC2) {
+      // C = (1-c)^2, d(kC)/dx^ = -2k (1-c) y^ = (-2 sqrt(k)) * th * y^ ; the constant is cp.gscale
+      e.a = fmaf(-cp.sk, dot3(ox, oy, oz, sx, sy, sz), cp.sk);
+      gs = e.a;
+      gx = sx;
+      gy = sy;
+      gz = sz;
+    } else if (FAST == FAST_EUC2) {
+      // C = |d|, d(kC)/d(owner) = k d / |d| (0 at d = 0: the sub-gradient the generic path returns as well); gscale = k
+      float dx = ox - sx, dy = oy - sy, dz = oz - sz;
+      float sq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      e.a = sqrt_approx(sq);
+      gs = (sq > 0.f) ? rsqrt_approx(sq) : 0.f;
+      gx = dx;
+      gy = dy;
+      gz = dz;
     } else if (FAST == FAST_GEO1) {
       // C = theta, d(kC)/dx^ = -k rsqrt(1-c^2) y^ = (-sqrt(k)) * [sqrt(k) rs] ... the constant -k is cp.gscale
       float c = dot3(ox, oy, oz, sx, sy, sz);
@@ -243,6 +266,8 @@ inline int pick_fast(int kind, float p, float npow) {
   if (kind == SHWD_COST_SQEUCLID && p == 2.f && npow == 1.f) return FAST_SQE2;
   if (kind == SHWD_COST_GEODESIC && p == 1.f && npow == 1.f) return FAST_GEO1;
   if ((kind == SHWD_COST_SQEUCLID || kind == SHWD_COST_EUCLID) && p == 1.f && npow == 1.f) return FAST_SQE1;  // (s)^(1/1) = s
+  if (kind == SHWD_COST_EUCLID && p == 2.f && npow == 1.f) return FAST_EUC2;
+  if (kind == SHWD_COST_ONE_MINUS_COS && p == 2.f && npow == 1.f) return FAST_OMC2;
   return GENERIC;
 }
 
@@ -255,10 +280,11 @@ inline CostParams make_cost(int kind, float p, float npow, float eps, int fast) 
   cp.k = (float)k;
   cp.sk = (float)sqrt(k);
   const float q[7] = SHWD_ACOS_Q;
-  const double qs = fast_is_geo(fast) ? sqrt(k) : 1.0;
+  const double qs = (fast == FAST_GEO2 || fast == FAST_GEO1) ? sqrt(k) : 1.0;
   for (int i = 0; i < 7; ++i) cp.q[i] = (float)(qs * (double)q[i]);
   cp.hpi = (float)(qs * 1.5707963267948966);
-  cp.gscale = (fast == FAST_GEO2) ? (float)(-2.0 * sqrt(k)) : (fast == FAST_GEO1) ? (float)(-k) : (fast == FAST_SQE2) ? (float)(2.0 * k) : (float)k;
+  cp.gscale = (fast == FAST_GEO2 || fast == FAST_OMC2) ? (float)(-2.0 * sqrt(k))
+              : (fast == FAST_GEO1) ? (float)(-k) : (fast == FAST_SQE2) ? (float)(2.0 * k) : (float)k;
   return cp;
 }
 

@@ -531,14 +531,17 @@ __device__ __forceinline__ f2 dot3_2(float ox, float oy, float oz, f2 X, f2 Y, f
 // th = sqrt(k) theta; SQE2: |o - s|^2); pk_m: the canonical exponent Cost<FAST>::m(e, pot), bit-identical to the scalar one.
 template <int FAST>
 __device__ __forceinline__ f2 pk_e(const CostParams& cp, const float4& o, f2 X, f2 Y, f2 Z) {
+  if (FAST == FAST_OMC2) return fma2(bc2(-cp.sk), dot3_2(o.x, o.y, o.z, X, Y, Z), bc2(cp.sk));
   if (fast_is_geo(FAST)) return scaled_acos2(cp.q, cp.hpi, dot3_2(o.x, o.y, o.z, X, Y, Z));
   const f2 dx = sub2(bc2(o.x), X), dy = sub2(bc2(o.y), Y), dz = sub2(bc2(o.z), Z);
   if (FAST == FAST_SQE1) return add2(add2(abs2(dx), abs2(dy)), abs2(dz));
-  return fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+  const f2 sq = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+  if (FAST == FAST_EUC2) return mk2(sqrt_approx(lo2(sq)), sqrt_approx(hi2(sq)));
+  return sq;
 }
 template <int FAST>
 __device__ __forceinline__ f2 pk_m(const CostParams& cp, f2 e, f2 pot) {
-  if (FAST == FAST_GEO2) return fma2(neg2(e), e, pot);
+  if (FAST == FAST_GEO2 || FAST == FAST_OMC2) return fma2(neg2(e), e, pot);
   if (FAST == FAST_GEO1) return fma2(bc2(-cp.sk), e, pot);
   return fma2(bc2(-cp.k), e, pot);
 }
@@ -666,11 +669,17 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const 
         for (int r = 0; r < R; ++r) {
           if (fast_is_geo(FAST)) {
             const f2 c = dot3_2(op[r].x, op[r].y, op[r].z, x2, y2, z2);
-            const f2 th = scaled_acos2(cp.q, cp.hpi, c);
-            const f2 om = fma2(neg2(c), c, bc2(1.f));
-            const f2 rs = mk2(rsqrt_approx(fmaxf(lo2(om), 1e-12f)), rsqrt_approx(fmaxf(hi2(om), 1e-12f)));
-            const f2 gs = (FAST == FAST_GEO2) ? mul2(th, rs) : rs;             // p = 1: d(k theta)/dc = -k rs (constant in gscale)
-            const f2 nth = (FAST == FAST_GEO2) ? neg2(th) : bc2(-cp.sk);      // -kC = nth * th in both cases
+            f2 th, gs;
+            if (FAST == FAST_OMC2) {
+              th = fma2(bc2(-cp.sk), c, bc2(cp.sk));  // sqrt(k) (1 - c); d(kC)/dc = -2 sqrt(k) th
+              gs = th;
+            } else {
+              th = scaled_acos2(cp.q, cp.hpi, c);
+              const f2 om = fma2(neg2(c), c, bc2(1.f));
+              const f2 rs = mk2(rsqrt_approx(fmaxf(lo2(om), 1e-12f)), rsqrt_approx(fmaxf(hi2(om), 1e-12f)));
+              gs = (FAST == FAST_GEO2) ? mul2(th, rs) : rs;                   // p = 1: d(k theta)/dc = -k rs (constant in gscale)
+            }
+            const f2 nth = (FAST == FAST_GEO1) ? bc2(-cp.sk) : neg2(th);      // -kC = nth * th in every case
             const f2 S1 = ex2_2(add2(fma2(nth, th, bc2(opot1[r])), s2));
             const f2 S2 = ex2_2(add2(fma2(nth, th, p2), bc2(o2[r])));
             const f2 w1 = mul2(a2, S1);
@@ -682,13 +691,19 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, const 
           } else {  // squared Euclidean: kC = k |o - s|^2, d(kC)/d(owner) = 2k (o - s) (2k = cp.gscale, applied per owner);
                     // L1: kC = k |o - s|_1, d(kC)/d(owner) = k sign(o - s)
             const f2 dx = sub2(bc2(op[r].x), x2), dy = sub2(bc2(op[r].y), y2), dz = sub2(bc2(op[r].z), z2);
-            const f2 sq = (FAST == FAST_SQE1) ? add2(add2(abs2(dx), abs2(dy)), abs2(dz)) : fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            f2 sq = (FAST == FAST_SQE1) ? add2(add2(abs2(dx), abs2(dy)), abs2(dz)) : fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            f2 ri = bc2(1.f);
+            if (FAST == FAST_EUC2) {  // kC = k |d|, d(kC)/d(owner) = k d / |d| (0 at d = 0); |d| = sqrt.approx as in the forward
+              ri = mk2(lo2(sq) > 0.f ? rsqrt_approx(lo2(sq)) : 0.f, hi2(sq) > 0.f ? rsqrt_approx(hi2(sq)) : 0.f);
+              sq = mk2(sqrt_approx(lo2(sq)), sqrt_approx(hi2(sq)));
+            }
             const f2 nk = bc2(-cp.k);
             const f2 S1 = ex2_2(add2(fma2(nk, sq, bc2(opot1[r])), s2));
             const f2 S2 = ex2_2(add2(fma2(nk, sq, p2), bc2(o2[r])));
             const f2 w1 = mul2(a2, S1);
             aw[r] = add2(aw[r], w1);
-            const f2 wg = fma2(bc2(oadj[r]), S2, w1);
+            f2 wg = fma2(bc2(oadj[r]), S2, w1);
+            if (FAST == FAST_EUC2) wg = mul2(wg, ri);
             ax[r] = fma2(wg, (FAST == FAST_SQE1) ? sign2(dx) : dx, ax[r]);
             ay[r] = fma2(wg, (FAST == FAST_SQE1) ? sign2(dy) : dy, ay[r]);
             az[r] = fma2(wg, (FAST == FAST_SQE1) ? sign2(dz) : dz, az[r]);
@@ -1542,6 +1557,8 @@ extern "C" int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N,
     case FAST_SQE2: return launch_persistent(sinkhorn_fwd_kernel<FAST_SQE2>, prm, smem, maxg, s);
     case FAST_GEO1: return launch_persistent(sinkhorn_fwd_kernel<FAST_GEO1>, prm, smem, maxg, s);
     case FAST_SQE1: return launch_persistent(sinkhorn_fwd_kernel<FAST_SQE1>, prm, smem, maxg, s);
+    case FAST_EUC2: return launch_persistent(sinkhorn_fwd_kernel<FAST_EUC2>, prm, smem, maxg, s);
+    case FAST_OMC2: return launch_persistent(sinkhorn_fwd_kernel<FAST_OMC2>, prm, smem, maxg, s);
     default: return launch_persistent(sinkhorn_fwd_kernel<GENERIC>, prm, smem, maxg, s);
   }
 }
@@ -1601,6 +1618,8 @@ extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N,
     case FAST_SQE2: return launch_persistent(sinkhorn_bwd_kernel<FAST_SQE2>, prm, smem, maxg, s);
     case FAST_GEO1: return launch_persistent(sinkhorn_bwd_kernel<FAST_GEO1>, prm, smem, maxg, s);
     case FAST_SQE1: return launch_persistent(sinkhorn_bwd_kernel<FAST_SQE1>, prm, smem, maxg, s);
+    case FAST_EUC2: return launch_persistent(sinkhorn_bwd_kernel<FAST_EUC2>, prm, smem, maxg, s);
+    case FAST_OMC2: return launch_persistent(sinkhorn_bwd_kernel<FAST_OMC2>, prm, smem, maxg, s);
     default: return launch_persistent(sinkhorn_bwd_kernel<GENERIC>, prm, smem, maxg, s);
   }
 }
@@ -1630,6 +1649,12 @@ extern "C" int shwd_sinkhorn_plan_dense(const float* x4, const float* y4, int B,
       break;
     case FAST_SQE1:
       plan_dense_kernel<FAST_SQE1><<<grid, block, 0, s>>>(X, Y, N, M, cp, alpha, beta, level_stride_n, level_stride_m, inv_k, P, C);
+      break;
+    case FAST_EUC2:
+      plan_dense_kernel<FAST_EUC2><<<grid, block, 0, s>>>(X, Y, N, M, cp, alpha, beta, level_stride_n, level_stride_m, inv_k, P, C);
+      break;
+    case FAST_OMC2:
+      plan_dense_kernel<FAST_OMC2><<<grid, block, 0, s>>>(X, Y, N, M, cp, alpha, beta, level_stride_n, level_stride_m, inv_k, P, C);
       break;
     default:
       plan_dense_kernel<GENERIC><<<grid, block, 0, s>>>(X, Y, N, M, cp, alpha, beta, level_stride_n, level_stride_m, inv_k, P, C);

@@ -186,15 +186,19 @@ def test_generic_cost_path(shwd, kind, p, eps):
 
 @pytest.mark.parametrize("kind,p,B,N,M,L,eps", [("geodesic", 1, 3, 300, 260, 30, 0.02), ("geodesic", 1, 2, 1024, 1024, 50, 0.01),
                                                 ("sqeuclid", 1, 3, 300, 260, 30, 0.02), ("euclid", 1, 2, 1024, 1024, 50, 0.02),
-                                                ("sqeuclid", 1, 2, 700, 2300, 10, 0.05)])
-def test_p1_fast_costs_match_oracle(shwd, kind, p, B, N, M, L, eps):
-    """The packed fast paths for geodesic p = 1 (default p of Geodesic_distance_W, s2_wasserstein.py:74) and the L1 cost
-    (Cos_disimilarity_W(p=1), train_W1_COS.py:393; 'L1' of the Sinkhorn classes) on resident / chunked / ragged shapes.
+                                                ("sqeuclid", 1, 2, 700, 2300, 10, 0.05),
+                                                ("euclid", 2, 3, 300, 260, 30, 0.05), ("euclid", 2, 2, 1024, 1024, 50, 0.02),
+                                                ("one_minus_cos", 2, 3, 300, 260, 30, 0.02),
+                                                ("one_minus_cos", 2, 2, 1024, 1024, 50, 0.01)])
+def test_other_fast_costs_match_oracle(shwd, kind, p, B, N, M, L, eps):
+    """The packed fast paths for geodesic p = 1 (default p of Geodesic_distance_W, s2_wasserstein.py:74), the L1 cost
+    (Cos_disimilarity_W(p=1), train_W1_COS.py:393; 'L1' of the Sinkhorn classes), |x-y|_2 (Sinkhorn_fixed.py:79-89) and
+    (1-cos)^2 (max_spherical_w_cos_with_regulation.py:745) on resident / chunked / ragged shapes.
     Some points of y coincide with points of x: |d| has the sub-gradient sign(0) = 0 there (torch.abs backward)."""
     torch.manual_seed(B * 13 + N)
     x = F.normalize(torch.randn(B, N, 3), dim=-1)
     y = F.normalize(torch.randn(B, M, 3) + 0.3, dim=-1)
-    if kind != "geodesic":  # exact coincidences (for the geodesic cost the reference returns NaN there, SURVEY.md B.1)
+    if kind != "geodesic" and p == 1:  # exact coincidences (geodesic / |d|_2: the reference returns NaN there, SURVEY.md B.1)
         y[:, :16] = x[:, :16]
         y[:, 20:24, 0] = x[:, 20:24, 0]
     cost, gx, gy, _ = _run_cuda(shwd, x, y, kind, float(p), eps, L)
