@@ -250,7 +250,7 @@ extern "C" int shwd_exact_assignment(const float* x4, const float* y4, int B, in
   const float4* Y = reinterpret_cast<const float4*>(y4);
 #define SHWD_LAUNCH_AUCTION(F)                                                                                              \
   do {                                                                                                                      \
-    if (smem > 48 * 1024)                                                                                                   \
+    if (smem > 32 * 1024) /* static + dynamic beyond 48 KB needs the opt-in */                                              \
       SHWD_CUDA_CHECK(cudaFuncSetAttribute(auction_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     auction_kernel<F><<<B, AU_THREADS, smem, s>>>(X, Y, N, cp, sigma, prices, rounds, status);                              \
   } while (0)

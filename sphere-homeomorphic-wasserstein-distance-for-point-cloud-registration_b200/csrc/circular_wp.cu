@@ -308,11 +308,11 @@ static int circular_wp_dispatch(const float* us, const float* vs, const int32_t*
   if (smem > 220 * 1024) return SHWD_ERR_UNSUPPORTED;        // n + m <= 56320 per slice
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (p == 2.f) {
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)  // static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here)
       SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     circular_wp_kernel<true><<<S, CW_THREADS, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta);
   } else {
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)  // static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here)
       SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     circular_wp_kernel<false><<<S, CW_THREADS, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta);
   }

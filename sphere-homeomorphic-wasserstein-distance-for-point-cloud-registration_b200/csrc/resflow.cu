@@ -421,7 +421,7 @@ extern "C" int shwd_resflow_bwd(const float* x, const float* gy, int npts, const
   float* partial = static_cast<float*>(workspace);
   float* geff = partial + (size_t)blocks * np;
   const size_t smem = (size_t)(1 + RF_WARPS) * np * sizeof(float);
-  if (smem > 48 * 1024)
+  if (smem > 32 * 1024)  // static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here)
     SHWD_CUDA_CHECK(cudaFuncSetAttribute(resflow_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   resflow_bwd_kernel<<<blocks, RF_THREADS, smem, s>>>(x, gy, npts, params, uv, n_layers, coeff, gx, partial);
   SHWD_CUDA_CHECK(cudaGetLastError());

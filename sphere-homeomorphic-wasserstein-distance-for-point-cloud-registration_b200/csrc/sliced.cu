@@ -547,7 +547,7 @@ template <int C>
 static int launch_circular_w1(const float* us, const float* vs, const int32_t* pu, const int32_t* pv, int S, int n, int m, float* w,
                               float* gus, float* gvs, cudaStream_t stream) {
   const size_t smem = (size_t)(cw1_pad(n - 1) + 1 + cw1_pad(m - 1) + 1) * sizeof(float);
-  if (smem > 48 * 1024)
+  if (smem > 32 * 1024)  // static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here)
     SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_w1_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   circular_w1_kernel<C><<<S, CW1_THREADS, smem, stream>>>(us, vs, pu, pv, n, m, w, gus, gvs);
   SHWD_CUDA_CHECK(cudaGetLastError());
@@ -637,7 +637,7 @@ static int launch_segmented_sort(const float* keys, int segs, int len, float* so
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (len <= SORT_SMEM_MAX) {
     const size_t smem = 2 * (size_t)len * sizeof(uint2);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)  // static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here)
       SHWD_CUDA_CHECK(cudaFuncSetAttribute(segmented_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     segmented_sort_kernel<<<segs, SORT_THREADS, smem, s>>>(keys, len, sorted, perm, perm32, nullptr);
   } else {

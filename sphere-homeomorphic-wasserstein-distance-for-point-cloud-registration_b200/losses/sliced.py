@@ -20,6 +20,8 @@ def emd1D_circle(u_values, v_values, u_weights=None, v_weights=None, p=1, requir
     if require_sort:
         u_values, _ = ops.SegmentedSortFn.apply(u_values.contiguous().float())
         v_values, _ = ops.SegmentedSortFn.apply(v_values.contiguous().float())
+    if u_values.shape[-1] + v_values.shape[-1] > ops.CIRCULAR_W1_MAX:
+        return ops.circular_w1_large(u_values.contiguous(), v_values.contiguous())
     return ops.CircularW1Fn.apply(u_values.contiguous(), v_values.contiguous())
 
 

@@ -640,12 +640,41 @@ class SlicedLossFn(torch.autograd.Function):
         return gx, gy, None, None, None, None, None, None
 
 
+CIRCULAR_W1_MAX = 10240  # n + m the register-resident circular_w1 kernel takes per slice (512 threads x 20 entries)
+
+
+def circular_w1_large(us, vs):
+    """emd1D_circle (max_spherical_sliced_w.py:230-247) on sorted rows us (S,n), vs (S,m) of ANY length, for slices
+    beyond CIRCULAR_W1_MAX: the reference's own four-sort formulation, with every sort done by the segmented radix sort
+    kernel (global-scratch path above 8192 keys) and the scans / gathers by torch device ops.  Differentiable w.r.t.
+    us / vs through the merged sort's permutation, like autograd through torch.sort."""
+    S, n = us.shape
+    m = vs.shape[1]
+    merged, mperm = SegmentedSortFn.apply(torch.cat((us, vs), -1))  # stable: a u entry precedes an equal v entry
+    wts = torch.cat((torch.full((n,), 1 / n, dtype=torch.float32, device=us.device),
+                     -torch.full((m,), 1 / m, dtype=torch.float32, device=us.device)))
+    cdf_diff = torch.cumsum(wts[mperm], -1)
+    cdf_sorted, cperm = segmented_sort_raw(cdf_diff)
+    delta = torch.cat((merged[:, 1:], torch.ones_like(merged[:, :1])), -1) - merged  # the arc [0, first) is omitted (:238-239)
+    cw = torch.cumsum(torch.gather(delta.detach(), -1, cperm), -1) - 0.5
+    k = torch.argmin(torch.where(cw < 0, torch.full_like(cw, float("inf")), cw), dim=-1, keepdim=True)
+    lev_med = torch.gather(cdf_sorted, -1, k)
+    return torch.sum(delta * torch.abs(cdf_diff - lev_med), dim=-1)
+
+
 def spherical_sliced_w1(Xs, Xt, U):
     """mean_P circular-W1 of the great-circle projections (sliced_cost with p == 1, explicit frames U (P,3,2))."""
     xs, _ = _as_cloud(Xs, "Xs")
     xt, _ = _as_cloud(Xt, "Xt")
     U = U.to(device=xs.device, dtype=torch.float32)
-    return SlicedLossFn.apply(xs, xt, U, "circle_w1", 1.0, 0.0, 0.0, 0.0)  # (B,)
+    if xs.shape[1] + xt.shape[1] <= CIRCULAR_W1_MAX:
+        return SlicedLossFn.apply(xs, xt, U, "circle_w1", 1.0, 0.0, 0.0, 0.0)  # (B,)
+    ks = ProjectCircleFn.apply(xs, U)  # (B,P,n)
+    kt = ProjectCircleFn.apply(xt, U)
+    B, P, n = ks.shape
+    ss, _ = SegmentedSortFn.apply(ks.reshape(B * P, n))
+    st, _ = SegmentedSortFn.apply(kt.reshape(B * P, kt.shape[2]))
+    return circular_w1_large(ss, st).reshape(B, P).mean(dim=1)
 
 
 def spherical_sliced_wp(Xs, Xt, U, p=2.0, tm=-1.0, tp=1.0, tol=1e-7):

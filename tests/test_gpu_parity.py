@@ -381,10 +381,11 @@ def test_emd1d_circle_matches_reference_fixture(shwd):
 
 
 @pytest.mark.parametrize("S,n,m", [(5, 1, 1), (5, 7, 3), (4, 1024, 1024), (3, 1500, 1500), (3, 3000, 2500), (3, 4096, 4096),
-                                   (2, 5000, 4800), (2, 5120, 5120)])
+                                   (2, 5000, 4800), (2, 5120, 5120), (2, 6000, 5000), (1, 16384, 16384)])
 def test_emd1d_circle_matches_oracle_every_bucket(shwd, S, n, m):
     """circular_w1_kernel<C> keeps C merged entries per thread in registers (C = 4, 8, 12, 16, 20 by n + m): values and
-    the gradients w.r.t. the unsorted circle coordinates against emd1D_circle (oracle/sliced.py) in every bucket."""
+    the gradients w.r.t. the unsorted circle coordinates against emd1D_circle (oracle/sliced.py) in every bucket; beyond
+    n + m = 10240 the four-sort composition circular_w1_large (sort kernel with global scratch) takes over."""
     uv = _tie_free(S, n + m, 100 + n)  # one shuffled tie-free row split in two: no u == v tie either (a tie's order in
     u0, v0 = uv[:, :n].contiguous(), uv[:, n:].contiguous()  # the merged sort decides two gradient entries)
     g = torch.Generator().manual_seed(S + n)
@@ -421,7 +422,7 @@ def test_spherical_sliced_w1_matches_reference_fixture(shwd):
     assert rel(xt.grad, torch.from_numpy(d["gy"])) < 5e-5
 
 
-@pytest.mark.parametrize("n,m,P", [(64, 64, 8), (500, 333, 16), (4096, 4096, 4)])
+@pytest.mark.parametrize("n,m,P", [(64, 64, 8), (500, 333, 16), (4096, 4096, 4), (16384, 16384, 3), (9000, 7000, 2)])
 def test_spherical_sliced_w1_matches_oracle(shwd, n, m, P):
     g = torch.Generator().manual_seed(n + m)
     Xs = F.normalize(torch.randn(n, 3, generator=g), dim=-1)
@@ -901,3 +902,21 @@ def test_sliced_and_chamfer_are_bit_reproducible(shwd):
         for _ in range(3):
             again = run(fn)
             assert all(torch.equal(p, q) for p, q in zip(first, again))
+
+
+@pytest.mark.parametrize("length", [2560, 2900, 3000, 3072, 5600, 6100])
+def test_kernels_just_below_the_48k_dynamic_smem_mark(length):
+    """Dynamic shared memory just under 48 KB plus the kernels' static arrays exceeds the default limit: the launchers
+    must opt in (a fresh process is used so that no earlier launch has raised the function attribute already)."""
+    import subprocess
+    import sys
+    code = ("import sys, torch; sys.path.insert(0, %r); import shwd; "
+            "g = torch.Generator().manual_seed(0); k = torch.rand(3, %d, generator=g).cuda(); "
+            "s, p = shwd.ops.segmented_sort_raw(k); r, q = torch.sort(k, dim=-1, stable=True); "
+            "assert torch.equal(p, q) and torch.equal(s, r); "
+            "w = shwd.losses.emd1D_circle(k, torch.rand(3, %d, generator=g).cuda()); "
+            "w2 = shwd.losses.binary_search_circle(k, torch.rand(3, %d, generator=g).cuda(), p=2); "
+            "torch.cuda.synchronize(); assert torch.isfinite(w).all() and torch.isfinite(w2).all()"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), length, length, length))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
