@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(PJ_THREADS) project_circle_kernel(const float*
   if (n >= N) return;
   const float* xp = x + ((size_t)b * N + n) * 3;
   const float x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
+#pragma unroll 4
   for (int p = 0; p < pc; ++p) {
     const float* u = sU + p * 6;  // U[p][d][k] at d*2+k
     float a = fmaf(u[4], x2, fmaf(u[2], x1, u[0] * x0));
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd_kernel(const fl
     __syncthreads();
     for (int i = threadIdx.x; i < pc * 6; i += PJ_THREADS) sU[i] = __ldg(U + (size_t)p0 * 6 + i);
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 8
     for (int p = warp; p < pc; p += PB_WARPS) {
       const float* u = sU + p * 6;
       const float gkv = ok ? __ldg(gkb + (size_t)(p0 + p) * N) : 0.f;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(PJ_THREADS) project_line_bwd_kernel(const floa
     __syncthreads();
     for (int i = threadIdx.x; i < pc * 3; i += PJ_THREADS) sT[i] = __ldg(th + (size_t)p0 * 3 + i);
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 8
     for (int p = warp; p < pc; p += PB_WARPS) {
       const float g = ok ? __ldg(gkb + (size_t)(p0 + p) * N) : 0.f;
       g0 = fmaf(g, sT[p * 3], g0);
