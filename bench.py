@@ -32,8 +32,8 @@ B_PER_GPU, N_PTS, ITERS, EPS, P_COST = 32, 1024, 100, 0.01, 2.0
 FWD_OPS, BWD_OPS = 21.0, 33.0  # algorithmic FP32 lane-ops per element-eval
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two sweep kernels at this exact workload, from the
 # `ncu --set full` capture summarised in profiles/ (bench.py cannot run under ncu while it is timing)
-NCU_DRAM_BYTES_FWD, NCU_DRAM_BYTES_BWD = 4.35e6, 54.05e6
-NCU_SOURCE = "profiles/r01c_ncu_sinkhorn_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+NCU_DRAM_BYTES_FWD, NCU_DRAM_BYTES_BWD = 11.97e6, 53.95e6
+NCU_SOURCE = "profiles/r01e_ncu_sinkhorn_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
 METRIC = "SHWD loss fwd+bwd pairs/s (B=32,N=1024)"
 CONFIG = {"workload": "cfg2: synthetic registration pairs B=32/GPU N=M=1024, geodesic cost p=2, eps=0.01, L=100, sphere map "
                       "(centre+normalise) + loss + grads w.r.t. both clouds",
