@@ -43,3 +43,22 @@ def sharded_pair_loss(loss_fn, x, y, rank=None, world_size=None, group=None):
     else:
         s = x.new_zeros(())
     return global_mean(s, b1 - b0, group)
+
+
+def sharded_slice_loss(slice_loss_fn, Xs, Xt, frames, rank=None, world_size=None, group=None):
+    """Slice sharding of one sliced-loss call (cfg3 / cfg4 style single-pair runs): every rank holds the same
+    clouds and the same frames ``(P, ...)``, evaluates ``slice_loss_fn(Xs, Xt, frames[p0:p1]) -> mean over its slices``
+    (e.g. ``lambda a, b, U: losses.sliced_cost(a, b, U, p=2)``) and the global mean over all P slices is returned (the
+    reference's ``torch.mean`` over slices, max_spherical_sliced_w.py:284-286).  The value is global on every rank; the
+    gradient w.r.t. the clouds flows through the local slices only, so a caller that differentiates w.r.t. the clouds sums
+    the ranks' gradients (``dist.all_reduce(x.grad)`` -- what DDP does for parameters)."""
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world_size is None:
+        world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+    p0, p1 = shard_range(frames.shape[0], rank, world_size)
+    if p1 > p0:
+        s = slice_loss_fn(Xs, Xt, frames[p0:p1]) * float(p1 - p0)  # local mean -> local sum
+    else:
+        s = Xs.new_zeros(())
+    return global_mean(s.reshape(()) if s.dim() == 0 else s, p1 - p0, group)

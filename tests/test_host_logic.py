@@ -149,6 +149,39 @@ def test_sharded_mean_equals_single_process_mean_world2_gloo():
     assert dict(out) == {0: True, 1: True}
 
 
+def _slice_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from shwd_b200.dist import sharded_slice_loss
+    torch.manual_seed(0)
+    x = torch.randn(40, 3, requires_grad=True)  # the same clouds and frames on both ranks; 7 slices -> shards of 4 and 3
+    y = torch.randn(40, 3)
+    th = torch.nn.functional.normalize(torch.randn(7, 3), dim=-1)
+
+    def slice_mean(a, b, frames):  # stand-in for the CUDA sliced loss: mean over the given slices of a per-slice value
+        pa, pb = torch.sort(a @ frames.T, dim=0)[0], torch.sort(b @ frames.T, dim=0)[0]
+        return ((pa - pb) ** 2).sum(0).mean()
+
+    loss = sharded_slice_loss(slice_mean, x, y, th)
+    loss.backward()
+    g = x.grad.clone()
+    dist.all_reduce(g)
+    xr = x.detach().clone().requires_grad_(True)
+    ref = slice_mean(xr, y, th)
+    ref.backward()
+    out[rank] = bool(torch.allclose(loss.detach(), ref.detach(), rtol=1e-6) and torch.allclose(g, xr.grad, rtol=1e-5, atol=1e-7))
+    dist.destroy_process_group()
+
+
+def test_slice_sharded_mean_equals_single_process_mean_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_slice_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
+
+
 def test_fused_phi_parameter_layout_matches_the_c_abi():
     """The parameter tensors Norm_Flow_structure hands to the fused kernel, concatenated in order, must fill exactly the
     layout include/shwd.h documents (426 raw parameters and 102 power-iteration entries per Residual flow)."""
