@@ -9,10 +9,10 @@
 // Sort contract: the permutation equals torch.sort(keys, dim=-1, stable=True) bit for bit -- ascending, ties in input
 // order, -0.0 == +0.0, NaN last.  Keys go through the usual order-preserving float->uint32 map
 // (with -0 canonicalised and every NaN mapped to 0xFFFFFFFF) and a 4-pass LSD radix sort (8-bit digits) whose
-// ranking is warp-synchronous: each warp owns a contiguous item range, ranks 32 consecutive items per step with
-// __match_any_sync, and keeps warp-private digit offsets in shared memory, so there are no atomics and only three
-// block barriers per pass.  (key, index) records ping-pong between two shared-memory buffers for segments up to 8192
-// items and between two global scratch buffers beyond that.
+// ranking is warp-synchronous: each warp owns a contiguous item range, counts its digits with shared-memory atomics on a
+// warp-private histogram, then ranks 32 consecutive items per step by grouping equal digits with eight ballots, so the
+// scatter needs no atomics and a pass has only three block barriers.  (key, index) records ping-pong between two
+// shared-memory buffers for segments up to 8192 items and between two global scratch buffers beyond that.
 #include "common.cuh"
 
 namespace shwd {
@@ -307,49 +307,12 @@ __global__ void unsort_kernel(const float* __restrict__ gs, const int64_t* __res
 }
 
 // ------------------------------------------------------------------------------------- circular W1 (level median) --
-// In-place inclusive scan of n floats in shared memory (thread-sequential chunks + block scan of the chunk totals).
-__device__ void block_inclusive_scan_f32(float* a, int n, float* wtot /* SORT_WARPS */) {
-  const int per = (n + SORT_THREADS - 1) / SORT_THREADS;
-  const int beg = min(n, (int)threadIdx.x * per), end = min(n, beg + per);
-  float s = 0.f;
-  for (int i = beg; i < end; ++i) s += a[i];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float inc = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    float t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) wtot[warp] = inc;
-  __syncthreads();
-  float base = 0.f;
-  for (int w = 0; w < warp; ++w) base += wtot[w];
-  float run = base + inc - s;
-  for (int i = beg; i < end; ++i) {
-    run += a[i];
-    a[i] = run;
-  }
-  __syncthreads();
-}
-
 __device__ __forceinline__ float block_sum_f32(float v, float* wtot) {
   v = warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = v;
   __syncthreads();
   float t = 0.f;
-  for (int w = 0; w < SORT_WARPS; ++w) t += wtot[w];
-  return t;
-}
-
-// Fixed-order block sum (all threads get the result).
-__device__ __forceinline__ float block_sum_bcast(float v, float* wtot) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float t = 0.f;
-#pragma unroll
   for (int w = 0; w < SORT_WARPS; ++w) t += wtot[w];
   return t;
 }
