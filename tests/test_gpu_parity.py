@@ -920,3 +920,49 @@ def test_kernels_just_below_the_48k_dynamic_smem_mark(length):
             % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), length, length, length))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("case", ["constant", "duplicates", "one_vs_many", "endpoints", "identical"])
+def test_emd1d_circle_degenerate_rows(shwd, case):
+    """Ties and degenerate rows of the level-median kernel against emd1D_circle with stable sorts (ties: input order, a u
+    entry before an equal v entry): all-equal coordinates (the cumulative gap sum never reaches 0.5 -> the smallest CDF
+    difference is the median, the reference's argmin over an all-inf row), heavy duplicates, n = 1, coordinates exactly
+    0 and 1, and identical clouds (W = 0)."""
+    g = torch.Generator().manual_seed(len(case))
+    S = 4
+    if case == "constant":
+        u, v = torch.full((S, 300), 0.7), torch.full((S, 200), 0.7)
+    elif case == "duplicates":
+        u = torch.randint(0, 12, (S, 1000), generator=g).float() / 12
+        v = torch.randint(0, 12, (S, 900), generator=g).float() / 12
+    elif case == "one_vs_many":
+        u, v = torch.rand(S, 1, generator=g), torch.rand(S, 4096, generator=g)
+    elif case == "endpoints":
+        u = torch.cat([torch.zeros(S, 5), torch.ones(S, 5), torch.rand(S, 502, generator=g)], 1)
+        v = torch.cat([torch.ones(S, 7), torch.zeros(S, 3), torch.rand(S, 246, generator=g)], 1)
+    else:
+        u = torch.rand(S, 2048, generator=g)
+        v = u.clone()
+    ur, vr = u.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    wr = oracle.emd1d_circle(ur, vr, stable=True)
+    wr.sum().backward()
+    ug, vg = u.to(dev()).requires_grad_(True), v.to(dev()).requires_grad_(True)
+    w = shwd.losses.emd1D_circle(ug, vg)
+    w.sum().backward()
+    assert torch.isfinite(w).all() and torch.isfinite(ug.grad).all() and torch.isfinite(vg.grad).all()
+    assert (w.cpu() - wr.detach()).abs().max().item() <= 1e-5 * max(wr.abs().max().item(), 1e-3)
+    if case in ("constant", "endpoints", "one_vs_many"):  # tie-free in F, or F ties that do not move the median
+        assert rel(ug.grad, ur.grad) < 1e-4 and rel(vg.grad, vr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("p", [2.0, 3.0])
+def test_circular_wp_degenerate_rows(shwd, p):
+    """binary_search_circle on identical clouds (cost 0 at rotation 0) and on a pure rotation of the same cloud."""
+    g = torch.Generator().manual_seed(int(p))
+    u = torch.rand(3, 1024, generator=g)
+    for shift in (0.0, 0.25):
+        v = (u + shift) % 1.0
+        w = shwd.losses.binary_search_circle(u.to(dev()), v.to(dev()), p=p)
+        wr = oracle.binary_search_circle(u, v, p=p)
+        assert torch.isfinite(w).all()
+        assert (w.cpu() - wr).abs().max().item() <= 1e-5 * max(wr.abs().max().item(), 1e-3) + 1e-9
