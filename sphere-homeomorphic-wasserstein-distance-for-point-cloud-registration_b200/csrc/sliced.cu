@@ -203,38 +203,82 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
   uint32_t peers = 0xffffffffu;
 #pragma unroll
   for (int bit = 0; bit < BITS; ++bit) {
-    const uint32_t on = (d >> bit) & 1u;
-    const uint32_t m = __ballot_sync(0xffffffffu, on != 0u);
-    peers &= m ^ (on - 1u);  // on ? m : ~m
+    // peers &= (bit set) ? ballot : ~ballot -- spelled in PTX so that it stays four instructions per bit (test, vote,
+    // predicated complement, and); the compiler's own lowering of the C++ form takes six
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b32 t, m;\n and.b32 t, %1, %2;\n setp.ne.u32 p, t, 0;\n"
+        " vote.sync.ballot.b32 m, p, 0xffffffff;\n @!p not.b32 m, m;\n and.b32 %0, %0, m;\n}"
+        : "+r"(peers)
+        : "r"(d), "r"(1u << bit));
   }
   return peers;
 }
 
-// shared-memory store under a predicate, without a branch
-__device__ __forceinline__ void st_shared_if(uint32_t* p, uint32_t v, bool pred) {
-  asm volatile(
-      "{ .reg .pred q; .reg .u64 sa; setp.ne.s32 q, %2, 0; cvta.to.shared.u64 sa, %0; @q st.shared.u32 [sa], %1; }" ::"l"(p), "r"(v),
-      "r"((int)pred)
-      : "memory");
+// Record buffers of the sort live in shared memory (segments up to 8192 keys) or in global scratch.  In the shared case
+// they are addressed through 32-bit shared-window addresses with explicit ld.shared / st.shared: through generic pointers
+// the compiler emitted LD.E.64 / ST.E.64 plus, for every predicated counter store, an S2R SR_SWINHI / SR_CgaCtaId pair to
+// rebuild the window base inside the batch loop (the kernel is ALU / issue bound, so those instructions were not free).
+template <bool SMEM>
+struct RecBuf {
+  uint2* g;     // global (or generic) pointer
+  uint32_t sa;  // shared-window byte address (SMEM only)
+};
+template <bool SMEM>
+__device__ __forceinline__ RecBuf<SMEM> make_recbuf(uint2* p) {
+  RecBuf<SMEM> r;
+  r.g = p;
+  r.sa = SMEM ? (uint32_t)__cvta_generic_to_shared(p) : 0u;
+  return r;
+}
+template <bool SMEM>
+__device__ __forceinline__ uint2 rec_ld(const RecBuf<SMEM>& b, int i) {
+  if (SMEM) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(b.sa + 8u * (uint32_t)i));
+    return v;
+  }
+  return b.g[i];
+}
+template <bool SMEM>
+__device__ __forceinline__ uint32_t rec_ld_key(const RecBuf<SMEM>& b, int i) {
+  if (SMEM) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(b.sa + 8u * (uint32_t)i));
+    return v;
+  }
+  return b.g[i].x;
+}
+template <bool SMEM>
+__device__ __forceinline__ void rec_st(const RecBuf<SMEM>& b, int i, uint2 v) {
+  if (SMEM)
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(b.sa + 8u * (uint32_t)i), "r"(v.x), "r"(v.y) : "memory");
+  else
+    b.g[i] = v;
+}
+// shared-memory store under a predicate, without a branch (32-bit shared-window address)
+__device__ __forceinline__ void st_shared_if(uint32_t saddr, uint32_t v, bool pred) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.u32 [%0], %1; }" ::"r"(saddr), "r"(v), "r"((int)pred) : "memory");
 }
 
-// Stable LSD radix sort of n (key, index) records: a -> ... -> result pointer returned (either a or b).
-// a, b may live in shared or global memory.  hist: SORT_WARPS*256 words of shared memory; wt: SORT_WARPS words.
-__device__ uint2* block_radix_sort(uint2* a, uint2* b, int n, uint32_t* hist, uint32_t* wt) {
+// Stable LSD radix sort of n (key, index) records: a -> ... -> result buffer returned (either a or b).
+// hist: SORT_WARPS*256 words of shared memory; wt: SORT_WARPS words.
+template <bool SMEM>
+__device__ RecBuf<SMEM> block_radix_sort(RecBuf<SMEM> a, RecBuf<SMEM> b, int n, uint32_t* hist, uint32_t* wt) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunk = (((n + SORT_WARPS - 1) / SORT_WARPS) + 31) & ~31;
   const int beg = min(n, warp * chunk), end = min(n, beg + chunk);
   const uint32_t lt = (1u << lane) - 1u;
+  uint32_t* wh = hist + warp * 256;
+  const uint32_t wh_s = (uint32_t)__cvta_generic_to_shared(wh);
   for (int pass = 0; pass < 4; ++pass) {
     const int sh = pass * 8;
     for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) hist[i] = 0;
     __syncthreads();
-    uint32_t* wh = hist + warp * 256;
     // The per-warp digit counters are read by every lane and advanced by the leader of each match group with a PREDICATED
     // store: no divergent branch inside the batch loops (branch / reconvergence bookkeeping runs on the ADU pipe, which
     // was the busiest unit of this kernel), one __syncwarp per batch orders the store against the next batch's reads.
     // counting needs no order: shared-memory atomics on the warp's private histogram
-    for (int i = beg + lane; i < end; i += 32) atomicAdd(wh + ((a[i].x >> sh) & 255u), 1u);
+    for (int i = beg + lane; i < end; i += 32) atomicAdd(wh + ((rec_ld_key<SMEM>(a, i) >> sh) & 255u), 1u);
     __syncthreads();
     {
       // digit-major exclusive offsets: thread d owns digit d
@@ -254,22 +298,23 @@ __device__ uint2* block_radix_sort(uint2* a, uint2* b, int n, uint32_t* hist, ui
     for (int i0 = beg; i0 < end; i0 += 32) {
       const int i = i0 + lane;
       const bool valid = i < end;
-      const uint2 rec = valid ? a[i] : make_uint2(0u, 0u);
+      const uint2 rec = valid ? rec_ld<SMEM>(a, i) : make_uint2(0u, 0u);
       const uint32_t d = valid ? ((rec.x >> sh) & 255u) : 256u;
       const uint32_t peers = (i0 + 32 <= end) ? match_digit<8>(d) : match_digit<9>(d);  // full batches need no "invalid" bit
       const uint32_t cur = wh[d & 255u];
-      if (valid) b[cur + __popc(peers & lt)] = rec;
-      st_shared_if(wh + (d & 255u), cur + __popc(peers), valid && (peers & lt) == 0);
+      if (valid) rec_st<SMEM>(b, cur + __popc(peers & lt), rec);
+      st_shared_if(wh_s + 4u * (d & 255u), cur + __popc(peers), valid && (peers & lt) == 0);
       __syncwarp();
     }
     __syncthreads();
-    uint2* t = a;
+    RecBuf<SMEM> t = a;
     a = b;
     b = t;
   }
   return a;
 }
 
+template <bool SMEM>
 __global__ void __launch_bounds__(SORT_THREADS) segmented_sort_kernel(const float* __restrict__ keys, int len,
                                                                       float* __restrict__ sorted, int64_t* __restrict__ perm,
                                                                       int32_t* __restrict__ perm32, uint2* __restrict__ gscratch) {
@@ -278,19 +323,19 @@ __global__ void __launch_bounds__(SORT_THREADS) segmented_sort_kernel(const floa
   __shared__ uint32_t wt[SORT_WARPS];
   const size_t seg = blockIdx.x;
   const float* k = keys + seg * len;
-  uint2 *a, *b;
-  if (gscratch) {
-    a = gscratch + seg * 2 * (size_t)len;
-    b = a + len;
+  RecBuf<SMEM> a, b;
+  if (SMEM) {
+    a = make_recbuf<SMEM>(sbuf);
+    b = make_recbuf<SMEM>(sbuf + len);
   } else {
-    a = sbuf;
-    b = sbuf + len;
+    a = make_recbuf<SMEM>(gscratch + seg * 2 * (size_t)len);
+    b = make_recbuf<SMEM>(gscratch + seg * 2 * (size_t)len + len);
   }
-  for (int i = threadIdx.x; i < len; i += SORT_THREADS) a[i] = make_uint2(float_sort_key(__ldg(k + i)), (uint32_t)i);
+  for (int i = threadIdx.x; i < len; i += SORT_THREADS) rec_st<SMEM>(a, i, make_uint2(float_sort_key(__ldg(k + i)), (uint32_t)i));
   __syncthreads();
-  uint2* r = block_radix_sort(a, b, len, hist, wt);
+  const RecBuf<SMEM> r = block_radix_sort<SMEM>(a, b, len, hist, wt);
   for (int i = threadIdx.x; i < len; i += SORT_THREADS) {
-    const uint32_t j = r[i].y;
+    const uint32_t j = rec_ld<SMEM>(r, i).y;
     if (sorted) sorted[seg * len + i] = __ldg(k + j);
     if (perm) perm[seg * len + i] = (int64_t)j;
     if (perm32) perm32[seg * len + i] = (int32_t)j;
@@ -602,12 +647,12 @@ static int launch_segmented_sort(const float* keys, int segs, int len, float* so
   if (len <= SORT_SMEM_MAX) {
     const size_t smem = 2 * (size_t)len * sizeof(uint2);
     if (smem > 32 * 1024)  // static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here)
-      SHWD_CUDA_CHECK(cudaFuncSetAttribute(segmented_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    segmented_sort_kernel<<<segs, SORT_THREADS, smem, s>>>(keys, len, sorted, perm, perm32, nullptr);
+      SHWD_CUDA_CHECK(cudaFuncSetAttribute(segmented_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    segmented_sort_kernel<true><<<segs, SORT_THREADS, smem, s>>>(keys, len, sorted, perm, perm32, nullptr);
   } else {
     const size_t need = shwd_segmented_sort_workspace_bytes(segs, len);
     if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 7)) return SHWD_ERR_WORKSPACE;
-    segmented_sort_kernel<<<segs, SORT_THREADS, 0, s>>>(keys, len, sorted, perm, perm32, static_cast<uint2*>(workspace));
+    segmented_sort_kernel<false><<<segs, SORT_THREADS, 0, s>>>(keys, len, sorted, perm, perm32, static_cast<uint2*>(workspace));
   }
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
