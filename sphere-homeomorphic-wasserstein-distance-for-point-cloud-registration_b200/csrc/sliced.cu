@@ -201,15 +201,22 @@ __device__ __forceinline__ uint32_t block_exscan_u32(uint32_t v, uint32_t* warp_
 template <int BITS>
 __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
   uint32_t peers = 0xffffffffu;
+  // peers &= (bit set) ? ballot : ~ballot -- spelled in PTX so that it stays ~3 instructions per bit (R2P sets the
+  // predicates of four bits at once, then vote, predicated complement, and); the compiler's own lowering of the C++
+  // form takes six.  The bits are fed four at a time from separately shifted copies so that ptxas does not try to keep
+  // all eight predicates alive at once (it has seven).
 #pragma unroll
-  for (int bit = 0; bit < BITS; ++bit) {
-    // peers &= (bit set) ? ballot : ~ballot -- spelled in PTX so that it stays four instructions per bit (test, vote,
-    // predicated complement, and); the compiler's own lowering of the C++ form takes six
-    asm volatile(
-        "{\n .reg .pred p;\n .reg .b32 t, m;\n and.b32 t, %1, %2;\n setp.ne.u32 p, t, 0;\n"
-        " vote.sync.ballot.b32 m, p, 0xffffffff;\n @!p not.b32 m, m;\n and.b32 %0, %0, m;\n}"
-        : "+r"(peers)
-        : "r"(d), "r"(1u << bit));
+  for (int base = 0; base < BITS; base += 4) {
+    uint32_t dd;
+    asm volatile("shr.u32 %0, %1, %2;" : "=r"(dd) : "r"(d), "r"(base));
+#pragma unroll
+    for (int bit = 0; bit < 4 && base + bit < BITS; ++bit) {
+      asm volatile(
+          "{\n .reg .pred p;\n .reg .b32 t, m;\n and.b32 t, %1, %2;\n setp.ne.u32 p, t, 0;\n"
+          " vote.sync.ballot.b32 m, p, 0xffffffff;\n @!p not.b32 m, m;\n and.b32 %0, %0, m;\n}"
+          : "+r"(peers)
+          : "r"(dd), "r"(1u << bit));
+    }
   }
   return peers;
 }
@@ -295,12 +302,23 @@ __device__ RecBuf<SMEM> block_radix_sort(RecBuf<SMEM> a, RecBuf<SMEM> b, int n, 
       }
     }
     __syncthreads();
-    for (int i0 = beg; i0 < end; i0 += 32) {
+    int i0 = beg;
+#pragma unroll 1
+    for (; i0 + 32 <= end; i0 += 32) {  // full batches: every lane holds a record, eight ballots
+      const uint2 rec = rec_ld<SMEM>(a, i0 + lane);
+      const uint32_t d = (rec.x >> sh) & 255u;
+      const uint32_t peers = match_digit<8>(d);
+      const uint32_t cur = wh[d];
+      rec_st<SMEM>(b, cur + __popc(peers & lt), rec);
+      st_shared_if(wh_s + 4u * d, cur + __popc(peers), (peers & lt) == 0);
+      __syncwarp();
+    }
+    if (i0 < end) {  // the ragged tail of the warp's range: a ninth "invalid" bit keeps the empty lanes apart
       const int i = i0 + lane;
       const bool valid = i < end;
       const uint2 rec = valid ? rec_ld<SMEM>(a, i) : make_uint2(0u, 0u);
       const uint32_t d = valid ? ((rec.x >> sh) & 255u) : 256u;
-      const uint32_t peers = (i0 + 32 <= end) ? match_digit<8>(d) : match_digit<9>(d);  // full batches need no "invalid" bit
+      const uint32_t peers = match_digit<9>(d);
       const uint32_t cur = wh[d & 255u];
       if (valid) rec_st<SMEM>(b, cur + __popc(peers & lt), rec);
       st_shared_if(wh_s + 4u * (d & 255u), cur + __popc(peers), valid && (peers & lt) == 0);
