@@ -5,11 +5,12 @@ alias module at the repository root, or put this directory on ``sys.path`` and `
 replacement of the reference's ``losses`` package.
 """
 from . import _lib, ops, data
+from .graphs import graphed_loss, GraphedLoss
 from .ops import (sphere_map, flow_regularization, entropic_ot, chamfer_nn, segmented_sort_raw, spherical_sliced_w1,
                   spherical_sliced_wp, euclid_sliced_w, exact_assignment, exact_emd2)
 
 __all__ = ["_lib", "ops", "data", "sphere_map", "flow_regularization", "entropic_ot", "chamfer_nn", "segmented_sort_raw",
-           "spherical_sliced_w1", "spherical_sliced_wp", "euclid_sliced_w", "exact_assignment", "exact_emd2", "build_library"]
+           "spherical_sliced_w1", "spherical_sliced_wp", "euclid_sliced_w", "exact_assignment", "exact_emd2", "build_library", "graphed_loss", "GraphedLoss"]
 
 
 def build_library(force=False):

@@ -966,3 +966,65 @@ def test_circular_wp_degenerate_rows(shwd, p):
         wr = oracle.binary_search_circle(u, v, p=p)
         assert torch.isfinite(w).all()
         assert (w.cpu() - wr).abs().max().item() <= 1e-5 * max(wr.abs().max().item(), 1e-3) + 1e-9
+
+
+# ------------------------------------------------------------------------------------------------- CUDA graphs ----
+def _graph_cases(shwd):
+    g = torch.Generator().manual_seed(5)
+    U, _ = torch.linalg.qr(torch.randn(16, 3, 2, generator=g))
+    U = U.to(dev())
+    th = F.normalize(torch.randn(16, 3, generator=g), dim=-1).to(dev())
+    geo = shwd.losses.Geodesic_distance_W(device=dev(), p=2, eps=0.02, max_iter=20)
+    return {
+        "chamfer": (lambda a, b: shwd.losses.chamfer_distance(a, b)[0], (4, 300, 3), (4, 260, 3)),
+        "ssw1": (lambda a, b: shwd.losses.sliced_cost(a, b, U, p=1), (500, 3), (450, 3)),
+        "ssw2": (lambda a, b: shwd.losses.sliced_cost(a, b, U, p=2), (500, 3), (450, 3)),
+        "euclid_sw": (lambda a, b: shwd.losses.sliced_wasserstein_distance(a, b, p=2, device=dev(), projections=th), (400, 3), (400, 3)),
+        "geodesic_w": (lambda a, b: geo(a, b), (3, 200, 3), (3, 160, 3)),  # the persistent cooperative sweeps
+    }
+
+
+@pytest.mark.parametrize("which", ["chamfer", "ssw1", "ssw2", "euclid_sw", "geodesic_w"])
+def test_graphed_loss_replays_forward_and_backward_bit_exactly(shwd, which):
+    """graphs.graphed_loss: forward + backward captured once, replayed on NEW inputs -> the same bits as the eager call
+    (the same kernels run on the same data; only the launch mechanism differs)."""
+    fn, sx, sy = _graph_cases(shwd)[which]
+    gfn = shwd.graphed_loss(fn)
+    g = torch.Generator().manual_seed(11)
+    for trial in range(3):  # trial 0 captures, 1 and 2 replay with different data
+        x = F.normalize(torch.randn(*sx, generator=g), dim=-1).to(dev())
+        y = F.normalize(torch.randn(*sy, generator=g) + 0.3, dim=-1).to(dev())
+        xe, ye = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+        le = fn(xe, ye)
+        (2.0 * le).backward()
+        xg, yg = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+        lg = gfn(xg, yg)
+        (2.0 * lg).backward()
+        assert torch.equal(lg.detach(), le.detach()), (which, trial)
+        assert torch.equal(xg.grad, xe.grad) and torch.equal(yg.grad, ye.grad), (which, trial)
+    assert len(gfn._captures) == 1
+    # zero-copy form used by gradient-flow loops
+    loss, (gx, gy) = gfn.value_and_grad(xg, yg)
+    assert torch.equal(loss, le.detach()) and torch.equal(2.0 * gx, xe.grad) and torch.equal(2.0 * gy, ye.grad)
+
+
+def test_graphed_loss_signatures_and_one_sided_gradients(shwd):
+    fn = lambda a, b: shwd.losses.chamfer_distance(a, b, batch_reduction="sum")[0]  # noqa: E731
+    gfn = shwd.graphed_loss(fn)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 128, 3, generator=g).to(dev())
+    y = torch.randn(2, 96, 3, generator=g).to(dev())
+    xg = x.clone().requires_grad_(True)
+    out = gfn(xg, y)  # only x requires grad (the registration setting: y is the fixed template)
+    out.backward()
+    xe = x.clone().requires_grad_(True)
+    fn(xe, y).backward()
+    assert torch.equal(xg.grad, xe.grad)
+    with torch.no_grad():
+        assert torch.equal(gfn(x, y), fn(x, y))
+    gfn(torch.randn(1, 50, 3, device=dev()), torch.randn(1, 70, 3, device=dev()))  # a new shape -> a new capture
+    assert len(gfn._captures) == 3
+    with pytest.raises(RuntimeError):
+        gfn(x.cpu(), y.cpu())
+    with pytest.raises(ValueError):
+        shwd.graphed_loss(lambda a, b: shwd.chamfer_nn(a, b)[0])(x, y)  # not a scalar

@@ -225,3 +225,10 @@ def test_pose_generator_consumes_numpy_like_the_reference():
     assert np.allclose(shwd.data.euler_to_quaternion_xyz(d["euler_in"]), d["euler_quat"], rtol=0, atol=1e-15)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         shwd.data.rigid_transform(torch.zeros(1, 4, 3), poses[:1])
+
+
+def test_graphed_loss_refuses_cpu_tensors():
+    gfn = shwd.graphed_loss(lambda a, b: (a - b).pow(2).sum())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gfn(torch.randn(4, 3), torch.randn(4, 3))
+    assert len(gfn._captures) == 0
