@@ -106,7 +106,8 @@ int shwd_project_circle_bwd(const float* x, const float* U, int B, int N, int P,
 int shwd_project_line(const float* x, const float* theta, int B, int N, int P, float* keys, void* stream);
 int shwd_project_line_bwd(const float* theta, int B, int N, int P, const float* gkeys, float* gx, void* stream);
 /* Stable segmented sort (torch.sort(stable=True) order, NaN last, -0 == +0): keys (segs,len) -> sorted (segs,len),
- * perm (segs,len) int64.  Replaces torch.sort at max_spherical_sliced_w.py:163-164,224-225,232,235. */
+ * perm (segs,len) int64.  Replaces torch.sort at max_spherical_sliced_w.py:163-164,224-225,232,235.
+ * Rows of up to 16384 keys are sorted in shared memory (workspace 0 bytes); longer rows need the global scratch. */
 size_t shwd_segmented_sort_workspace_bytes(int segs, int len);
 int shwd_segmented_sort(const float* keys, int segs, int len, float* sorted, int64_t* perm, void* workspace,
                         size_t workspace_bytes, void* stream);

@@ -11,8 +11,12 @@
 // (with -0 canonicalised and every NaN mapped to 0xFFFFFFFF) and a 4-pass LSD radix sort (8-bit digits) whose
 // ranking is warp-synchronous: each warp owns a contiguous item range, counts its digits with shared-memory atomics on a
 // warp-private histogram, then ranks 32 consecutive items per step by grouping equal digits with eight ballots, so the
-// scatter needs no atomics and a pass has only three block barriers.  (key, index) records ping-pong between two
-// shared-memory buffers for segments up to 8192 items and between two global scratch buffers beyond that.
+// scatter needs no atomics and a pass has only three block barriers.  Records ping-pong between two shared-memory buffers:
+// (key, index) uint2 pairs for rows up to 4224 keys, separate 4-byte key / 2-byte index arrays up to 16384 keys
+// (segmented_sort_compact_kernel), and between two global scratch buffers beyond that.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace shwd {
@@ -360,6 +364,140 @@ __global__ void __launch_bounds__(SORT_THREADS) segmented_sort_kernel(const floa
   }
 }
 
+// ---- compact shared-memory layout ------------------------------------------------------------------------------------
+// The same stable LSD radix sort with 4-byte keys and 2-byte indices in SEPARATE ping-pong arrays (12 B per item instead of
+// the 16 B of two uint2 buffers) and the per-warp digit counters as 16-bit halves (offsets < 65536): rows of up to
+// SORT_COMPACT_MAX = 16384 keys stay in shared memory (the uint2 layout ends at 8192 and falls back to global scratch), a
+// row of 8192 keys leaves room for two CTAs per SM instead of one, a row of 4096 keys for four instead of three.
+constexpr int SORT_COMPACT_MAX = 16384;
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ void sts_u16_if(uint32_t a, uint32_t v, bool pred) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.u16 [%0], %1; }" ::"r"(a), "h"((uint16_t)v), "r"((int)pred) : "memory");
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) segmented_sort_compact_kernel(const float* __restrict__ keys, int len,
+                                                                            float* __restrict__ sorted, int64_t* __restrict__ perm,
+                                                                            int32_t* __restrict__ perm32) {
+  constexpr int THREADS = WARPS * 32;
+  static_assert(THREADS >= 256, "one thread per digit in the offset scan");
+  extern __shared__ __align__(16) unsigned char csm[];
+  __shared__ uint32_t wt[WARPS];
+  // keyA[len] keyB[len] (u32) | idxA[len] idxB[len] (u16) | hist[WARPS][256] (u16)
+  uint32_t ka = (uint32_t)__cvta_generic_to_shared(csm), kb = ka + 4u * len;
+  uint32_t ia = kb + 4u * len, ib = ia + 2u * len;
+  const uint32_t hs = ib + 2u * len;  // 4-byte aligned: 12 * len
+  uint32_t* hist32 = reinterpret_cast<uint32_t*>(csm + 12 * (size_t)len);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t seg = blockIdx.x;
+  const float* k = keys + seg * len;
+  for (int i = tid; i < len; i += THREADS) {
+    sts_u32(ka + 4u * i, float_sort_key(__ldg(k + i)));
+    sts_u16(ia + 2u * i, (uint32_t)i);
+  }
+  const int chunk = (((len + WARPS - 1) / WARPS) + 31) & ~31;
+  const int beg = min(len, warp * chunk), end = min(len, beg + chunk);
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t wh = hs + 512u * warp;  // this warp's 256 16-bit counters
+  for (int pass = 0; pass < 4; ++pass) {
+    const int sh = pass * 8;
+    for (int i = tid; i < WARPS * 128; i += THREADS) hist32[i] = 0u;
+    __syncthreads();  // (first pass: also the record stores above)
+    // counting needs no order: one shared-memory atomic per key on the 32-bit word that holds the digit's 16-bit half
+    for (int i = beg + lane; i < end; i += 32) {
+      const uint32_t d = (lds_u32(ka + 4u * i) >> sh) & 255u;
+      atomicAdd(hist32 + warp * 128 + (d >> 1), 1u << ((d & 1u) << 4));
+    }
+    __syncthreads();
+    {
+      // digit-major exclusive offsets: thread d < 256 owns digit d
+      const bool own = tid < 256;
+      uint32_t tot = 0;
+      if (own) {
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) tot += lds_u16(hs + 512u * w + 2u * tid);
+      }
+      uint32_t inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) wt[warp] = inc;
+      __syncthreads();
+      uint32_t run = inc - tot;
+      for (int w = 0; w < warp; ++w) run += wt[w];
+      if (own) {
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+          const uint32_t a = hs + 512u * w + 2u * tid;
+          const uint32_t t = lds_u16(a);
+          sts_u16(a, run);
+          run += t;
+        }
+      }
+    }
+    __syncthreads();
+    int i0 = beg;
+#pragma unroll 1
+    for (; i0 + 32 <= end; i0 += 32) {  // full batches
+      const uint32_t key = lds_u32(ka + 4u * (i0 + lane));
+      const uint32_t idx = lds_u16(ia + 2u * (i0 + lane));
+      const uint32_t d = (key >> sh) & 255u;
+      const uint32_t peers = match_digit<8>(d);
+      const uint32_t cur = lds_u16(wh + 2u * d);
+      const uint32_t dst = cur + __popc(peers & lt);
+      sts_u32(kb + 4u * dst, key);
+      sts_u16(ib + 2u * dst, idx);
+      sts_u16_if(wh + 2u * d, cur + __popc(peers), (peers & lt) == 0);
+      __syncwarp();
+    }
+    if (i0 < end) {  // ragged tail of the warp's range
+      const int i = i0 + lane;
+      const bool valid = i < end;
+      const uint32_t key = valid ? lds_u32(ka + 4u * i) : 0u;
+      const uint32_t idx = valid ? lds_u16(ia + 2u * i) : 0u;
+      const uint32_t d = valid ? ((key >> sh) & 255u) : 256u;
+      const uint32_t peers = match_digit<9>(d);
+      const uint32_t cur = lds_u16(wh + 2u * (d & 255u));
+      const uint32_t dst = cur + __popc(peers & lt);
+      if (valid) {
+        sts_u32(kb + 4u * dst, key);
+        sts_u16(ib + 2u * dst, idx);
+      }
+      sts_u16_if(wh + 2u * (d & 255u), cur + __popc(peers), valid && (peers & lt) == 0);
+      __syncwarp();
+    }
+    __syncthreads();
+    uint32_t t = ka;
+    ka = kb;
+    kb = t;
+    t = ia;
+    ia = ib;
+    ib = t;
+  }
+  for (int i = tid; i < len; i += THREADS) {
+    const uint32_t j = lds_u16(ia + 2u * i);
+    if (sorted) sorted[seg * len + i] = __ldg(k + j);  // the original value (keeps -0.0 and NaN payloads)
+    if (perm) perm[seg * len + i] = (int64_t)j;
+    if (perm32) perm32[seg * len + i] = (int32_t)j;
+  }
+}
+
 // gkeys[seg][perm[seg][k]] = gsorted[seg][k]
 __global__ void unsort_kernel(const float* __restrict__ gs, const int64_t* __restrict__ perm, size_t total, int len,
                               float* __restrict__ gk) {
@@ -652,9 +790,41 @@ extern "C" int shwd_project_line_bwd(const float* theta, int B, int N, int P, co
   return SHWD_OK;
 }
 
+// Which layout sorts a row of `len` keys.  Measured on B200 (tools/time_sort.py, Gkeys/s, wide / compact-8 warps / compact-16):
+//   len 1024: 52.9 / 45.5 / 34.7    2048: 66.5 / 56.1 / 47.5    4096: 62.7 / 56.7 / 53.3    8192: 32.8 / 42.7 / 47.5
+//   10240: 24.6 / 29.0 / 36.8       16384: 18.0 / 27.0 / 34.0 (1024 rows: 11.2 / 30.3 / 38.7)
+// -> the uint2 records win while three of their CTAs fit on an SM (one 64-bit access per record and pass instead of two
+// narrower ones), the compact layout with 16 warps wins from there on.  SHWD_SORT_LAYOUT=wide|compact and
+// SHWD_SORT_WARPS=8|16 override the choice for A/B timing (read once).
+constexpr int SORT_WIDE_BEST_MAX = 4224;
+static int sort_env(const char* name, const char* a, int va, const char* b, int vb, int dflt) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  if (!strcmp(v, a)) return va;
+  if (!strcmp(v, b)) return vb;
+  return dflt;
+}
+static bool sort_use_compact(int len) {
+  static const int forced = sort_env("SHWD_SORT_LAYOUT", "wide", 1, "compact", 2, 0);
+  if (len > SORT_COMPACT_MAX) return false;
+  if (forced == 1) return false;
+  if (forced == 2) return true;
+  return len > SORT_WIDE_BEST_MAX;
+}
+
 extern "C" size_t shwd_segmented_sort_workspace_bytes(int segs, int len) {
-  if (segs <= 0 || len <= SORT_SMEM_MAX) return 0;
+  if (segs <= 0 || len <= SORT_SMEM_MAX || sort_use_compact(len)) return 0;
   return (size_t)segs * 2 * (size_t)len * sizeof(uint2);
+}
+
+template <int WARPS>
+static int launch_sort_compact(const float* keys, int segs, int len, float* sorted, int64_t* perm, int32_t* perm32, cudaStream_t s) {
+  const size_t smem = 12 * (size_t)len + (size_t)WARPS * 512;
+  if (smem > 32 * 1024)
+    SHWD_CUDA_CHECK(cudaFuncSetAttribute(segmented_sort_compact_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  segmented_sort_compact_kernel<WARPS><<<segs, WARPS * 32, smem, s>>>(keys, len, sorted, perm, perm32);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
 }
 
 static int launch_segmented_sort(const float* keys, int segs, int len, float* sorted, int64_t* perm, int32_t* perm32,
@@ -662,6 +832,12 @@ static int launch_segmented_sort(const float* keys, int segs, int len, float* so
   if (!keys || segs < 0 || len <= 0 || (!sorted && !perm && !perm32)) return SHWD_ERR_INVALID_ARGUMENT;
   if (segs == 0) return SHWD_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (sort_use_compact(len)) {
+    static const int warps_env = sort_env("SHWD_SORT_WARPS", "8", 8, "16", 16, 0);
+    const int warps = warps_env ? warps_env : 16;
+    return warps == 16 ? launch_sort_compact<16>(keys, segs, len, sorted, perm, perm32, s)
+                       : launch_sort_compact<8>(keys, segs, len, sorted, perm, perm32, s);
+  }
   if (len <= SORT_SMEM_MAX) {
     const size_t smem = 2 * (size_t)len * sizeof(uint2);
     if (smem > 32 * 1024)  // static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here)

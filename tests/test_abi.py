@@ -42,7 +42,8 @@ def test_library_builds_and_exports_every_symbol():
     assert h.shwd_sinkhorn_workspace_bytes(0, 1024, 1024, 100) == 0
     assert h.shwd_segmented_sort_workspace_bytes(8, 4096) == 0
     h.shwd_segmented_sort_workspace_bytes.restype = ctypes.c_size_t
-    assert h.shwd_segmented_sort_workspace_bytes(2, 10000) == 2 * 2 * 10000 * 8
+    assert h.shwd_segmented_sort_workspace_bytes(2, 10000) == 0  # rows up to 16384 keys are sorted in shared memory
+    assert h.shwd_segmented_sort_workspace_bytes(2, 20000) == 2 * 2 * 20000 * 8  # global scratch beyond
 
 
 def test_no_product_code_imports_the_oracle():
