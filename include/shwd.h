@@ -115,7 +115,7 @@ int shwd_segmented_sort(const float* keys, int segs, int len, float* sorted, int
 int shwd_segmented_sort_i32(const float* keys, int segs, int len, float* sorted, int32_t* perm, void* workspace,
                             size_t workspace_bytes, void* stream);
 /* Circular W1 by level median on sorted circle coordinates (emd1D_circle, max_spherical_sliced_w.py:230-247):
- * us (S,n), vs (S,m) sorted ascending -> w (S); gus/gvs (nullable) receive dW/d(sorted values). */
+ * us (S,n), vs (S,m) sorted ascending, n + m <= 32768 -> w (S); gus/gvs (nullable) receive dW/d(sorted values). */
 size_t shwd_circular_w1_workspace_bytes(int S, int n, int m);
 int shwd_circular_w1(const float* us, const float* vs, int S, int n, int m, float* w, float* gus, float* gvs,
                      void* workspace, size_t workspace_bytes, void* stream);

@@ -17,6 +17,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace shwd {
@@ -520,7 +522,8 @@ __device__ __forceinline__ float block_sum_f32(float v, float* wtot) {
 
 constexpr int CW1_THREADS = 512;     // 16 warps: with C <= 16 entries per thread (n + m <= 8192) 64 registers -> two CTAs, 32 warps per SM
 constexpr int CW1_WARPS = CW1_THREADS / 32;
-constexpr int CW1_PER_THREAD = 20;   // merged entries per thread (n + m <= 512 * 20 = 10240)
+constexpr int CW1_PER_THREAD = 20;   // merged entries per thread with register-resident F keys (n + m <= 512 * 20 = 10240)
+constexpr int CW1_PER_THREAD_MAX = 64;  // ... with recomputed F keys (n + m <= 32768: cfg4's two clouds of 16384 points)
 
 // Fixed-order block sum with ONE barrier: the per-warp partials ping-pong between two shared-memory rows.
 __device__ __forceinline__ float block_sum_pp(float v, float (*wf)[CW1_WARPS], int& phase) {
@@ -552,6 +555,10 @@ __host__ __device__ __forceinline__ int cw1_pad(int i) { return i + (i >> 5); }
 // smallest F value f with  sum_{k: F_k <= f} delta_k >= 0.5  (the cumulative sum over the sorted order first reaches 0.5
 // inside the run of entries equal to f), found by bisection on the 32-bit order-preserving key of F -- 32 rounds of a
 // register-resident partial sum + a fixed-order block reduction -- instead of a radix sort of n + m records.
+// C > CW1_PER_THREAD (slices of up to 32768 merged entries): 2 C words per thread no longer fit in the register file next
+// to the 4 (n+m) bytes of rows in shared memory, so only delta_k stays in registers and key(F_k) is RECOMPUTED wherever it is
+// needed -- F is a running sum of +-w from the chunk's base in merged order, i.e. one select + add + key map per entry,
+// bit-identical every time; this replaces the reference's four-sort composition on global scratch that such slices used to take.
 template <int C>
 __global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
     circular_w1_kernel(const float* __restrict__ us, const float* __restrict__ vs, const int32_t* __restrict__ pu,
@@ -585,9 +592,11 @@ __global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
     i0 = lo;
     j0 = d0 - lo;
   }
-  uint32_t key[C];  // first the merged value bits, later key(F_k)
+  constexpr bool RECOMPUTE = C > CW1_PER_THREAD;
+  typedef typename std::conditional<(C > 32), unsigned long long, uint32_t>::type mask_t;
+  uint32_t key[RECOMPUTE ? 1 : C];  // first the merged value bits, later key(F_k)
   float dl[C];
-  uint32_t from_u = 0u;
+  mask_t from_u = 0;
   float wsum = 0.f;  // chunk total of +-w, summed in merged order
   {
     int i = i0, j = j0;
@@ -600,7 +609,7 @@ __global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
         const bool take_u = (j >= m) || (i < n && cu <= cv);
         const float v = take_u ? cu : cv;
         if (take_u) {
-          from_u |= 1u << q;
+          from_u |= (mask_t)1 << q;
           wsum += wu;
           ++i;
           if (i < n) cu = su[cw1_pad(i)];
@@ -645,11 +654,12 @@ __global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
     float run = base;
 #pragma unroll
     for (int q = 0; q < C; ++q) {
-      key[q] = 0xFFFFFFFFu;
+      if (!RECOMPUTE) key[q] = 0xFFFFFFFFu;
       if (q < cnt) {
         run += ((from_u >> q) & 1u) ? wu : -wv;
-        key[q] = float_sort_key(run);
-        kmin = min(kmin, key[q]);
+        const uint32_t kq = float_sort_key(run);
+        if (!RECOMPUTE) key[q] = kq;
+        kmin = min(kmin, kq);
       }
       tot += dl[q];
     }
@@ -665,8 +675,17 @@ __global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
     while (lo < hi) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
       float part = 0.f;
+      if (RECOMPUTE) {
+        float run = base;  // dl[q] == 0 beyond cnt, so the surplus entries add nothing whatever their recomputed key
 #pragma unroll
-      for (int q = 0; q < C; ++q) part += (key[q] <= mid) ? dl[q] : 0.f;
+        for (int q = 0; q < C; ++q) {
+          run += ((from_u >> q) & 1u) ? wu : -wv;
+          part += (float_sort_key(run) <= mid) ? dl[q] : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < C; ++q) part += (key[q] <= mid) ? dl[q] : 0.f;
+      }
       part = block_sum_pp(part, wf, phase);
       if (part - 0.5f >= 0.f) hi = mid; else lo = mid + 1u;
     }
@@ -687,10 +706,12 @@ __global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
   {
     float aprev = (tid > 0 && cnt > 0) ? fabsf(s_lastF[tid - 1] - med) : 0.f;  // |F_{k-1} - med|, 0 before the first entry
     int i = i0, j = j0;
+    float run = base;
 #pragma unroll
     for (int q = 0; q < C; ++q) {
       if (q < cnt) {
-        const float a = fabsf(float_from_sort_key(key[q]) - med);
+        run += ((from_u >> q) & 1u) ? wu : -wv;
+        const float a = fabsf(float_from_sort_key(RECOMPUTE ? float_sort_key(run) : key[RECOMPUTE ? 0 : q]) - med);
         acc += dl[q] * a;
         if (want_g) {
           if ((from_u >> q) & 1u) su[cw1_pad(i++)] = aprev - a; else sv[cw1_pad(j++)] = aprev - a;
@@ -874,14 +895,16 @@ static int circular_w1_dispatch(const float* us, const float* vs, const int32_t*
   if (!us || !vs || !w || S < 0 || n <= 0 || m <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (S == 0) return SHWD_OK;
   const size_t nm = (size_t)n + m;
-  if (nm > (size_t)CW1_THREADS * CW1_PER_THREAD) return SHWD_ERR_UNSUPPORTED;  // n + m <= 10240 (register-resident entries)
+  if (nm > (size_t)CW1_THREADS * CW1_PER_THREAD_MAX) return SHWD_ERR_UNSUPPORTED;  // n + m <= 32768
   const int c = (int)((nm + CW1_THREADS - 1) / CW1_THREADS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (c <= 4) return launch_circular_w1<4>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
   if (c <= 8) return launch_circular_w1<8>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
   if (c <= 12) return launch_circular_w1<12>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
   if (c <= 16) return launch_circular_w1<16>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
-  return launch_circular_w1<CW1_PER_THREAD>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
+  if (c <= CW1_PER_THREAD) return launch_circular_w1<CW1_PER_THREAD>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
+  if (c <= 32) return launch_circular_w1<32>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
+  return launch_circular_w1<CW1_PER_THREAD_MAX>(us, vs, pu, pv, S, n, m, w, gus, gvs, st);
 }
 
 extern "C" int shwd_circular_w1(const float* us, const float* vs, int S, int n, int m, float* w, float* gus, float* gvs,

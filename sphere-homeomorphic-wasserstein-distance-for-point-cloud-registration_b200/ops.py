@@ -640,13 +640,13 @@ class SlicedLossFn(torch.autograd.Function):
         return gx, gy, None, None, None, None, None, None
 
 
-CIRCULAR_W1_MAX = 10240  # n + m the register-resident circular_w1 kernel takes per slice (512 threads x 20 entries)
+CIRCULAR_W1_MAX = 32768  # n + m the circular_w1 kernel takes per slice (512 threads x up to 64 merged entries each)
 
 
 def circular_w1_large(us, vs):
     """emd1D_circle (max_spherical_sliced_w.py:230-247) on sorted rows us (S,n), vs (S,m) of ANY length, for slices
     beyond CIRCULAR_W1_MAX: the reference's own four-sort formulation, with every sort done by the segmented radix sort
-    kernel (global-scratch path above 8192 keys) and the scans / gathers by torch device ops.  Differentiable w.r.t.
+    kernel (global-scratch path above 16384 keys) and the scans / gathers by torch device ops.  Differentiable w.r.t.
     us / vs through the merged sort's permutation, like autograd through torch.sort."""
     S, n = us.shape
     m = vs.shape[1]

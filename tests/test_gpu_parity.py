@@ -381,11 +381,13 @@ def test_emd1d_circle_matches_reference_fixture(shwd):
 
 
 @pytest.mark.parametrize("S,n,m", [(5, 1, 1), (5, 7, 3), (4, 1024, 1024), (3, 1500, 1500), (3, 3000, 2500), (3, 4096, 4096),
-                                   (2, 5000, 4800), (2, 5120, 5120), (2, 6000, 5000), (1, 16384, 16384)])
+                                   (2, 5000, 4800), (2, 5120, 5120), (2, 6000, 5000), (2, 8000, 8100), (2, 16000, 16500),
+                                   (1, 16384, 16384), (1, 20000, 17000)])
 def test_emd1d_circle_matches_oracle_every_bucket(shwd, S, n, m):
-    """circular_w1_kernel<C> keeps C merged entries per thread in registers (C = 4, 8, 12, 16, 20 by n + m): values and
-    the gradients w.r.t. the unsorted circle coordinates against emd1D_circle (oracle/sliced.py) in every bucket; beyond
-    n + m = 10240 the four-sort composition circular_w1_large (sort kernel with global scratch) takes over."""
+    """circular_w1_kernel<C> keeps C merged entries per thread in registers (C = 4, 8, 12, 16, 20 by n + m; C = 32, 64 with
+    recomputed CDF keys up to n + m = 32768): values and the gradients w.r.t. the unsorted circle coordinates against
+    emd1D_circle (oracle/sliced.py) in every bucket; beyond that the four-sort composition circular_w1_large (sort kernel
+    with global scratch) takes over."""
     uv = _tie_free(S, n + m, 100 + n)  # one shuffled tie-free row split in two: no u == v tie either (a tie's order in
     u0, v0 = uv[:, :n].contiguous(), uv[:, n:].contiguous()  # the merged sort decides two gradient entries)
     g = torch.Generator().manual_seed(S + n)

@@ -12,7 +12,7 @@ y = F.normalize(torch.randn(1, N, 3, generator=g) + 0.2, dim=-1).to(dev).require
 U, _ = torch.linalg.qr(torch.randn(P, 3, 2, generator=g)); U = U.to(dev)
 th = F.normalize(torch.randn(P, 3, generator=g), dim=-1).to(dev)
 cases = {
-    "SSW p=1 (level median; four-sort composition above 10240 merged entries)": lambda: shwd.ops.spherical_sliced_w1(x, y, U),
+    "SSW p=1 (level median)": lambda: shwd.ops.spherical_sliced_w1(x, y, U),
     "SSW p=2 (bisection)": lambda: shwd.ops.spherical_sliced_wp(x, y, U, 2.0),
     "Euclid SW p=2": lambda: shwd.ops.euclid_sliced_w(x, y, th, 2.0),
     "Chamfer": lambda: shwd.losses.chamfer_distance(x, y)[0],
