@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import shwd
 dev = torch.device("cuda:0")
-for segs, length in ((4096, 4096), (2048, 5000), (2048, 6500), (1024, 8192), (512, 8192), (512, 10240), (512, 16384), (1024, 16384), (512, 32768), (128, 65536)):
+for segs, length in ((2048, 6500), (1024, 8192), (512, 8192), (512, 10240), (512, 16384), (1024, 16384), (512, 32768), (128, 65536)):
     k = torch.rand(segs, length, device=dev)
     for _ in range(3):
         shwd.ops._sort_i32(k)
