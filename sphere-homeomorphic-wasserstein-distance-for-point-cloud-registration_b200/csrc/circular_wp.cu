@@ -120,6 +120,7 @@ __device__ __forceinline__ int r_count_lt(const Circle& c, const Shift& s, float
 }
 
 // Fixed-order block sum of two values; result broadcast to every thread.
+template <int T>
 __device__ __forceinline__ float2 block_sum2(float a, float b, float2* wtot) {
   a = warp_sum(a);
   b = warp_sum(b);
@@ -128,7 +129,7 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* wtot) {
   __syncthreads();
   float2 t = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int w = 0; w < CW_WARPS; ++w) {
+  for (int w = 0; w < T / 32; ++w) {
     t.x += wtot[w].x;
     t.y += wtot[w].y;
   }
@@ -136,12 +137,12 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* wtot) {
 }
 
 // dCost :25-65 -> (dCp, dCm): right / left derivative of the cost in theta
-template <bool P2>
+template <bool P2, int T>
 __device__ float2 dcost(const Circle& c, float theta, float2* wtot) {
   const Shift s = make_shift(c, theta);
   const float u_wrap = __fadd_rn(c.u[0], 1.f), ucdf_wrap = __fadd_rn(ucdf_at(c, 0), 1.f);
   float dcp = 0.f, dcm = 0.f;
-  for (int t = threadIdx.x; t < c.m; t += CW_THREADS) {
+  for (int t = threadIdx.x; t < c.m; t += T) {
     const float x = r_cdf(c, s, t);
     const int iu = u_count_lt(c, x);                       // searchsorted(u_cdf, x)
     const float ui = c.u[min(iu, c.n - 1)];
@@ -153,15 +154,15 @@ __device__ float2 dcost(const Circle& c, float theta, float2* wtot) {
     dcp += __fsub_rn(powp<P2>(__fsub_rn(ui, v1), c.p), powp<P2>(__fsub_rn(ui, v0), c.p));
     dcm += __fsub_rn(powp<P2>(__fsub_rn(uim, v1), c.p), powp<P2>(__fsub_rn(uim, v0), c.p));
   }
-  return block_sum2(dcp, dcm, wtot);
+  return block_sum2<T>(dcp, dcm, wtot);
 }
 
 // Cost :68-113, pass U.  Returns the cost (broadcast); gu (nullable, global) receives d cost / d u_sorted.
-template <bool P2>
+template <bool P2, int T>
 __device__ float cost_pass_u(const Circle& c, float theta, float* __restrict__ gu, const int32_t* __restrict__ pu, float2* wtot) {
   const Shift s = make_shift(c, theta);
   float acc = 0.f;
-  for (int k = threadIdx.x; k < c.n; k += CW_THREADS) {
+  for (int k = threadIdx.x; k < c.n; k += T) {
     float prev = (k > 0) ? ucdf_at(c, k - 1) : 0.f;
     const float xk = ucdf_at(c, k);
     const float U = c.u[k];
@@ -195,14 +196,14 @@ __device__ float cost_pass_u(const Circle& c, float theta, float* __restrict__ g
     }
     if (gu) gu[pu ? __ldg(pu + k) : k] = g;  // pu: straight to the unsorted key position
   }
-  return block_sum2(acc, 0.f, wtot).x;
+  return block_sum2<T>(acc, 0.f, wtot).x;
 }
 
 // Cost, pass V: gv (global, indexed by sorted v position) receives d cost / d v_sorted.
-template <bool P2>
+template <bool P2, int T>
 __device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv, const int32_t* __restrict__ pv) {
   const Shift s = make_shift(c, theta);
-  for (int t = threadIdx.x; t < c.m; t += CW_THREADS) {
+  for (int t = threadIdx.x; t < c.m; t += T) {
     float prev = (t > 0) ? r_cdf(c, s, t - 1) : 0.f;
     const float xt = r_cdf(c, s, t);
     const float V = r_val_in(c, s, t);
@@ -238,22 +239,22 @@ __device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv
   }
 }
 
-template <bool P2>
-__global__ void __launch_bounds__(CW_THREADS) circular_wp_kernel(const float* __restrict__ us, const float* __restrict__ vs,
+template <bool P2, int T>
+__global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict__ us, const float* __restrict__ vs,
                                                                  const int32_t* __restrict__ pu, const int32_t* __restrict__ pv, int n,
                                                                  int m, float p, float tm0, float tp0, float tol,
                                                                  float* __restrict__ w_out,
                                                                  float* __restrict__ gus, float* __restrict__ gvs,
                                                                  float* __restrict__ theta_out) {
   extern __shared__ float cw_smem[];
-  __shared__ float2 wtot[CW_WARPS];
+  __shared__ float2 wtot[T / 32];
   float* su = cw_smem;
   float* sv = su + n;
   const size_t sl = blockIdx.x;
-  for (int i = threadIdx.x; i < n; i += CW_THREADS) {
+  for (int i = threadIdx.x; i < n; i += T) {
     su[i] = __ldg(us + sl * n + i);
   }
-  for (int j = threadIdx.x; j < m; j += CW_THREADS) {
+  for (int j = threadIdx.x; j < m; j += T) {
     sv[j] = __ldg(vs + sl * m + j);
   }
   __syncthreads();
@@ -262,13 +263,13 @@ __global__ void __launch_bounds__(CW_THREADS) circular_wp_kernel(const float* __
   // binary_search_circle :172-205 (every quantity is uniform over the CTA: the sums are broadcast)
   float tm = tm0, tp = tp0, tc = (tm0 + tp0) * 0.5f;
   for (int round = 0; round < CW_MAX_ROUNDS; ++round) {
-    const float2 dc = dcost<P2>(c, tc, wtot);
+    const float2 dc = dcost<P2, T>(c, tc, wtot);
     if (dc.x * dc.y <= 0.f) break;  // done: the optimum is the kink at tc
     if (__fsub_rn(tp, tm) < tol) {
-      const float2 dtp = dcost<P2>(c, tp, wtot);
-      const float2 dtm = dcost<P2>(c, tm, wtot);
-      const float ctm = cost_pass_u<P2>(c, tm, nullptr, nullptr, wtot);
-      const float ctp = cost_pass_u<P2>(c, tp, nullptr, nullptr, wtot);
+      const float2 dtp = dcost<P2, T>(c, tp, wtot);
+      const float2 dtm = dcost<P2, T>(c, tm, wtot);
+      const float ctm = cost_pass_u<P2, T>(c, tm, nullptr, nullptr, wtot);
+      const float ctp = cost_pass_u<P2, T>(c, tp, nullptr, nullptr, wtot);
       const float den = __fsub_rn(dtm.x, dtp.y);  // dCptm - dCmtp
       if (fabsf(den) > 0.001f)
         tc = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(ctp, ctm), __fmul_rn(tm, dtm.x)), __fmul_rn(tp, dtp.y)), den);
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(CW_THREADS) circular_wp_kernel(const float* __
     if (dc.x < 0.f) tm = tc; else tp = tc;
     tc = __fmul_rn(__fadd_rn(tm, tp), 0.5f);
   }
-  const float w = cost_pass_u<P2>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot);
-  if (gvs) cost_pass_v<P2>(c, tc, gvs + sl * m, pv ? pv + sl * m : nullptr);
+  const float w = cost_pass_u<P2, T>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot);
+  if (gvs) cost_pass_v<P2, T>(c, tc, gvs + sl * m, pv ? pv + sl * m : nullptr);
   if (threadIdx.x == 0) {
     w_out[sl] = w;
     if (theta_out) theta_out[sl] = tc;
@@ -307,15 +308,22 @@ static int circular_wp_dispatch(const float* us, const float* vs, const int32_t*
   if (n > 32768 || m > 32768) return SHWD_ERR_UNSUPPORTED;  // exactness argument of ucdf_at: at most 2^15 weights per CDF
   if (smem > 220 * 1024) return SHWD_ERR_UNSUPPORTED;        // n + m <= 56320 per slice
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // Rows beyond 14336 merged entries leave room for at most three 256-thread CTAs per SM (one at cfg4's 32768): those
+  // slices run 1024 threads per CTA instead (cfg4 SSW p=2: see DESIGN.md 4.4); shorter rows keep the 256-thread CTAs
+  // (and their summation order).
+  const bool big = smem > 56 * 1024;
+#define SHWD_LAUNCH_WP(P2, T)                                                                                                      \
+  do {                                                                                                                             \
+    if (smem > 32 * 1024) /* static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here) */                            \
+      SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<P2, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    circular_wp_kernel<P2, T><<<S, T, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta);                        \
+  } while (0)
   if (p == 2.f) {
-    if (smem > 32 * 1024)  // static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here)
-      SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    circular_wp_kernel<true><<<S, CW_THREADS, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta);
+    if (big) SHWD_LAUNCH_WP(true, 1024); else SHWD_LAUNCH_WP(true, CW_THREADS);
   } else {
-    if (smem > 32 * 1024)  // static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here)
-      SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    circular_wp_kernel<false><<<S, CW_THREADS, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta);
+    if (big) SHWD_LAUNCH_WP(false, 1024); else SHWD_LAUNCH_WP(false, CW_THREADS);
   }
+#undef SHWD_LAUNCH_WP
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }

@@ -463,7 +463,8 @@ def test_spherical_sliced_w2_matches_reference_fixture(shwd):
 
 
 @pytest.mark.parametrize("S,n,m,p", [(9, 70, 55, 2), (5, 64, 64, 2), (6, 500, 333, 2), (4, 1024, 1024, 2), (3, 300, 300, 3),
-                                     (3, 200, 257, 1.5), (2, 4096, 4096, 2), (4, 1, 5, 2), (4, 7, 1, 2), (2, 3000, 9000, 2)])
+                                     (3, 200, 257, 1.5), (2, 4096, 4096, 2), (4, 1, 5, 2), (4, 7, 1, 2), (2, 3000, 9000, 2),
+                                     (2, 9000, 8000, 2), (1, 16384, 16384, 2), (1, 15000, 16000, 3)])  # 1024-thread CTAs beyond 14336
 def test_circular_wp_matches_oracle(shwd, S, n, m, p):
     """binary_search_circle (max_spherical_sliced_w.py:117-207): W_p^p, the rotation found, and the gradients w.r.t.
     the unsorted coordinates.  The bisection's last sign decisions sit at the float32 noise level of a sum of m
