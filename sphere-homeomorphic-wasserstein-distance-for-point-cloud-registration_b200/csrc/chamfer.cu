@@ -43,6 +43,12 @@ __device__ __forceinline__ f2 sqdist2(f2 ax, f2 ay, f2 az, f2 sx, f2 sy, f2 sz) 
 }
 
 // grid.x = query blocks of direction 0 (x queries) followed by direction 1 (y queries); grid.y = B
+// SPLIT > 1 (small grids: one pair, or few short clouds): a CTA owns CH_THREADS / SPLIT queries and SPLIT threads share a
+// query, thread `sub` scanning the sub-th slice of every tile -- SPLIT times as many CTAs for the same work, so a single pair
+// of 16384-point clouds fills the GPU (1024 CTAs instead of 128; a warp still reads one candidate address: broadcast).
+// The SPLIT partial (distance, index) pairs of a query are combined by smallest distance, then smallest index -- each partial
+// is already the first minimum of its slice set, so this is exactly the first minimum of the sequential scan.
+template <int SPLIT>
 __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int N,
                                                                  int M, int blocks_x, float* __restrict__ d_xy,
                                                                  int* __restrict__ idx_xy, float* __restrict__ d_yx,
@@ -56,7 +62,10 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const float* __
   const float* q = (dir ? y + (size_t)b * M * 3 : x + (size_t)b * N * 3);
   const float* r = (dir ? x + (size_t)b * N * 3 : y + (size_t)b * M * 3);
   const int nq = dir ? M : N, nr = dir ? N : M;
-  const int i = qb * CH_THREADS + threadIdx.x;
+  constexpr int QPB = CH_THREADS / SPLIT;  // queries per CTA
+  constexpr int SLICE = CH_TILE / SPLIT;   // candidates of a tile one thread scans
+  const int sub = threadIdx.x / QPB;
+  const int i = qb * QPB + (threadIdx.x - sub * QPB);
   float ax = 0.f, ay = 0.f, az = 0.f;
   if (i < nq) {
     ax = __ldg(q + 3 * i);
@@ -76,9 +85,9 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const float* __
       tz[j] = in ? __ldg(r + 3 * (t0 + j) + 2) : INFINITY;
     }
     __syncthreads();
-    const int lim = (cnt + 3) & ~3;
+    const int lim = min((cnt + 3) & ~3, (sub + 1) * SLICE);
 #pragma unroll 2
-    for (int j = 0; j < lim; j += 4) {
+    for (int j = sub * SLICE; j < lim; j += 4) {
       const float4 X = *reinterpret_cast<const float4*>(tx + j), Y = *reinterpret_cast<const float4*>(ty + j);
       const float4 Z = *reinterpret_cast<const float4*>(tz + j);
       const f2 d01 = sqdist2(ax2, ay2, az2, mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y));
@@ -90,6 +99,23 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const float* __
         if (d1 < best) { best = d1; bi = t0 + j + 1; }
         if (d2 < best) { best = d2; bi = t0 + j + 2; }
         if (d3 < best) { best = d3; bi = t0 + j + 3; }
+      }
+    }
+  }
+  if (SPLIT > 1) {
+    __shared__ float pbest[CH_THREADS];
+    __shared__ int pbi[CH_THREADS];
+    pbest[threadIdx.x] = best;
+    pbi[threadIdx.x] = bi;
+    __syncthreads();
+    if (sub != 0) return;
+#pragma unroll
+    for (int r = 1; r < SPLIT; ++r) {
+      const float ob = pbest[r * QPB + threadIdx.x];
+      const int oi = pbi[r * QPB + threadIdx.x];
+      if (ob < best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
       }
     }
   }
@@ -184,8 +210,14 @@ extern "C" int shwd_chamfer_fwd(const float* x, const float* y, int B, int N, in
   if (B == 0) return SHWD_OK;
   if (B > 65535) return SHWD_ERR_UNSUPPORTED;
   const int bx = (N + CH_THREADS - 1) / CH_THREADS, by = (M + CH_THREADS - 1) / CH_THREADS;
-  chamfer_fwd_kernel<<<dim3(bx + by, B), CH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, y, N, M, bx, d_xy, idx_xy, d_yx,
-                                                                                           idx_yx);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((long long)(bx + by) * B >= 592) {  // at least four 256-thread CTAs per SM: one thread per query fills the GPU
+    chamfer_fwd_kernel<1><<<dim3(bx + by, B), CH_THREADS, 0, s>>>(x, y, N, M, bx, d_xy, idx_xy, d_yx, idx_yx);
+  } else {
+    constexpr int SPLIT = 8, QPB = CH_THREADS / SPLIT;
+    const int sx = (N + QPB - 1) / QPB, sy = (M + QPB - 1) / QPB;
+    chamfer_fwd_kernel<SPLIT><<<dim3(sx + sy, B), CH_THREADS, 0, s>>>(x, y, N, M, sx, d_xy, idx_xy, d_yx, idx_yx);
+  }
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }

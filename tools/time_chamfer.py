@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import shwd
 dev = torch.device("cuda:0")
-for B, N in ((32, 1024), (256, 1024), (32, 4096), (32, 16384), (4, 65536)):
+for B, N in ((1, 1024), (1, 4096), (1, 16384), (2, 16384), (1, 65536), (32, 1024), (256, 1024), (32, 4096), (32, 16384), (4, 65536)):
     g = torch.Generator().manual_seed(N)
     x = torch.randn(B, N, 3, generator=g).to(dev).requires_grad_(True)
     y = (torch.randn(B, N, 3, generator=g) * 1.1 + 0.1).to(dev).requires_grad_(True)
