@@ -722,17 +722,38 @@ __global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
   }
   acc = block_sum_pp(acc, wf, phase);  // its barrier also orders the gradient stores above
   if (tid == 0) w_out[s] = acc;
-  // pu / pv given: the gradient goes straight to the UNSORTED key positions (the scatter torch.sort's backward would do)
-  if (gus)
-    for (int i = tid; i < n; i += CW1_THREADS) gus[s * n + (pu ? __ldg(pu + s * n + i) : i)] = su[cw1_pad(i)];
-  if (gvs)
-    for (int j = tid; j < m; j += CW1_THREADS) gvs[s * m + (pv ? __ldg(pv + s * m + j) : j)] = sv[cw1_pad(j)];
+  // pu / pv given: the gradient goes to the UNSORTED key positions (the scatter torch.sort's backward would do).  With two
+  // CTAs per SM (C <= 16) the row is first permuted in shared memory (stage: max(n, m) floats behind the rows) and written
+  // out coalesced: circular_w1_kernel<16> at cfg3 490 -> 431 us.  The one-CTA-per-SM variants lose (C = 64 at cfg4: 370 ->
+  // 439 us, the extra barriers are not hidden by a second CTA) and keep the direct scatter; so does euclid_sw_kernel
+  // (157 -> 236 us when staged).
+  constexpr bool STAGE = C <= 16;
+  float* stage = sv + cw1_pad(m - 1) + 1;
+  if (gus) {
+    if (pu && STAGE) {
+      for (int i = tid; i < n; i += CW1_THREADS) stage[__ldg(pu + s * n + i)] = su[cw1_pad(i)];
+      __syncthreads();
+      for (int i = tid; i < n; i += CW1_THREADS) gus[s * n + i] = stage[i];
+      __syncthreads();
+    } else {
+      for (int i = tid; i < n; i += CW1_THREADS) gus[s * n + (pu ? __ldg(pu + s * n + i) : i)] = su[cw1_pad(i)];
+    }
+  }
+  if (gvs) {
+    if (pv && STAGE) {
+      for (int j = tid; j < m; j += CW1_THREADS) stage[__ldg(pv + s * m + j)] = sv[cw1_pad(j)];
+      __syncthreads();
+      for (int j = tid; j < m; j += CW1_THREADS) gvs[s * m + j] = stage[j];
+    } else {
+      for (int j = tid; j < m; j += CW1_THREADS) gvs[s * m + (pv ? __ldg(pv + s * m + j) : j)] = sv[cw1_pad(j)];
+    }
+  }
 }
 
 template <int C>
 static int launch_circular_w1(const float* us, const float* vs, const int32_t* pu, const int32_t* pv, int S, int n, int m, float* w,
                               float* gus, float* gvs, cudaStream_t stream) {
-  const size_t smem = (size_t)(cw1_pad(n - 1) + 1 + cw1_pad(m - 1) + 1) * sizeof(float);
+  const size_t smem = (size_t)(cw1_pad(n - 1) + 1 + cw1_pad(m - 1) + 1 + ((C <= 16 && (pu || pv)) ? (n > m ? n : m) : 0)) * sizeof(float);
   if (smem > 32 * 1024)  // static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here)
     SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_w1_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   circular_w1_kernel<C><<<S, CW1_THREADS, smem, stream>>>(us, vs, pu, pv, n, m, w, gus, gvs);
