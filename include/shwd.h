@@ -173,6 +173,11 @@ int shwd_resflow_bwd(const float* x, const float* gy, int npts, const float* par
 int shwd_exact_assignment_max_points(void);
 int shwd_exact_assignment(const float* x4, const float* y4, int B, int N, int cost_kind, float p, float n_power, int* sigma,
                           double* prices, int* rounds, int* status, void* stream);
+/* The same exact solve on an explicit cost matrix C (B,N,N) float32, costs >= 0: the drop-in for ot.emd2(a, b, M) with
+ * uniform weights as called at Comparison_Wasserstein_with_Chamfer_distance/main_rotation.py:63-79 (POT_loss) and in the
+ * notebooks' W2 metric (Flow_ellipsoid.ipynb cell 8). */
+int shwd_exact_assignment_dense(const float* C, int B, int N, int* sigma, double* prices, int* rounds, int* status,
+                                void* stream);
 
 /* ---- data side: random rigid transform (+ optional sensor noise) of a device-resident batch ---------------------------
  * Replaces Dataset_Transformation.__call__ / create_pose_7d / qrot (data_utils/Data_set_maker.py:40-52,173-230), run by the

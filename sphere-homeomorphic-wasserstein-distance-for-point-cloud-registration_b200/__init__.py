@@ -7,10 +7,10 @@ replacement of the reference's ``losses`` package.
 from . import _lib, ops, data
 from .graphs import graphed_loss, GraphedLoss
 from .ops import (sphere_map, flow_regularization, entropic_ot, chamfer_nn, segmented_sort_raw, spherical_sliced_w1,
-                  spherical_sliced_wp, euclid_sliced_w, exact_assignment, exact_emd2)
+                  spherical_sliced_wp, euclid_sliced_w, exact_assignment, exact_emd2, exact_assignment_dense, exact_emd2_dense)
 
 __all__ = ["_lib", "ops", "data", "sphere_map", "flow_regularization", "entropic_ot", "chamfer_nn", "segmented_sort_raw",
-           "spherical_sliced_w1", "spherical_sliced_wp", "euclid_sliced_w", "exact_assignment", "exact_emd2", "build_library", "graphed_loss", "GraphedLoss"]
+           "spherical_sliced_w1", "spherical_sliced_wp", "euclid_sliced_w", "exact_assignment", "exact_emd2", "exact_assignment_dense", "exact_emd2_dense", "build_library", "graphed_loss", "GraphedLoss"]
 
 
 def build_library(force=False):

@@ -53,6 +53,7 @@ SIGNATURES = {
     "shwd_resflow_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "shwd_exact_assignment_max_points": (_i, []),
     "shwd_exact_assignment": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "shwd_exact_assignment_dense": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "shwd_rigid_transform": (_i, [_vp, _vp, _i, _i, _f, ctypes.c_ulonglong, _vp, _vp, _vp]),
     "shwd_peak_fp32": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), _vp]),
     "shwd_peak_mufu": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), _vp]),

@@ -30,6 +30,9 @@ constexpr int AU_WARPS = AU_THREADS / 32;
 #endif
 constexpr double AU_EPS_FACTOR = SHWD_AU_EPS_FACTOR;  // epsilon is multiplied by this between phases
 constexpr int AU_MAX_ROUNDS = 4000000;  // safety net (a phase needs O(n) rounds in practice)
+// FAST value of the dense variant: the cost is READ from a caller-supplied (B, N, N) matrix instead of being evaluated from
+// points -- the drop-in for ot.emd2(a, b, M) called on an explicit cost matrix (main_rotation.py:63-79 POT_loss; notebooks).
+constexpr int AU_DENSE = 1000;
 
 __device__ __forceinline__ unsigned long long au_key(double v) { return (unsigned long long)__double_as_longlong(v); }
 
@@ -54,13 +57,21 @@ __device__ __forceinline__ AuBest au_merge(const AuBest& a, const AuBest& b) {
 
 // One warp's scan of the objects j0, j0 + step, ... for a bidder at `o`: best and second-best value -C - price.
 template <int FAST>
-__device__ __forceinline__ AuBest au_scan(const CostParams& cp, const float4 o, const float4* sY, const double* price, int N, int j0,
-                                          int step) {
-  typedef Cost<FAST> CF;
+__device__ __forceinline__ float au_cost(const CostParams& cp, const float4 o, const float4* sY, const float* crow, int j) {
+  if constexpr (FAST == AU_DENSE) {
+    return __ldg(crow + j);
+  } else {
+    typedef Cost<FAST> CF;
+    const float4 t = sY[j];
+    return CF::kc(cp, CF::eval(cp, o.x, o.y, o.z, t.x, t.y, t.z));
+  }
+}
+template <int FAST>
+__device__ __forceinline__ AuBest au_scan(const CostParams& cp, const float4 o, const float4* sY, const float* crow,
+                                          const double* price, int N, int j0, int step) {
   AuBest best = {-INFINITY, -INFINITY, INT_MAX};
   for (int j = j0; j < N; j += step) {
-    const float4 t = sY[j];
-    const double v = -(double)CF::kc(cp, CF::eval(cp, o.x, o.y, o.z, t.x, t.y, t.z)) - price[j];
+    const double v = -(double)au_cost<FAST>(cp, o, sY, crow, j) - price[j];
     if (v > best.v1) {
       best.v2 = best.v1;
       best.v1 = v;
@@ -90,10 +101,11 @@ __device__ __forceinline__ void au_bid(AuBest best, double eps, const double* pr
 }
 
 template <int FAST>
-__global__ void __launch_bounds__(AU_THREADS) auction_kernel(const float4* __restrict__ X, const float4* __restrict__ Y, int N,
-                                                             CostParams cp, int* __restrict__ sigma, double* __restrict__ price_out,
+__global__ void __launch_bounds__(AU_THREADS) auction_kernel(const float4* __restrict__ X, const float4* __restrict__ Y,
+                                                             const float* __restrict__ Cd, int N, CostParams cp,
+                                                             int* __restrict__ sigma, double* __restrict__ price_out,
                                                              int* __restrict__ rounds_out, int* __restrict__ status) {
-  typedef Cost<FAST> CF;
+  constexpr bool DENSE = FAST == AU_DENSE;
   extern __shared__ float4 au_smem[];  // carved in decreasing alignment: float4, 8-byte, 4-byte arrays
   float4* sX = au_smem;                                               // N
   float4* sY = sX + N;                                                // N
@@ -111,9 +123,10 @@ __global__ void __launch_bounds__(AU_THREADS) auction_kernel(const float4* __res
   __shared__ double s_red[AU_WARPS];
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* Cb = DENSE ? Cd + (size_t)b * N * N : nullptr;  // row i of this pair's matrix: Cb + i * N
   for (int i = threadIdx.x; i < N; i += AU_THREADS) {
-    sX[i] = __ldg(X + (size_t)b * N + i);
-    sY[i] = __ldg(Y + (size_t)b * N + i);
+    sX[i] = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(X + (size_t)b * N + i);
+    sY[i] = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(Y + (size_t)b * N + i);
     price[i] = 0.0;
     bidval[i] = 0ull;
     bidder[i] = INT_MAX;
@@ -123,10 +136,7 @@ __global__ void __launch_bounds__(AU_THREADS) auction_kernel(const float4* __res
   float cm = 0.f;
   for (int i = warp; i < N; i += AU_WARPS) {
     const float4 o = sX[i];
-    for (int j = lane; j < N; j += 32) {
-      const float4 t = sY[j];
-      cm = fmaxf(cm, CF::kc(cp, CF::eval(cp, o.x, o.y, o.z, t.x, t.y, t.z)));
-    }
+    for (int j = lane; j < N; j += 32) cm = fmaxf(cm, au_cost<FAST>(cp, o, sY, DENSE ? Cb + (size_t)i * N : nullptr, j));
   }
   cm = warp_max(cm);
   if (lane == 0) s_red[warp] = (double)cm;
@@ -162,13 +172,13 @@ __global__ void __launch_bounds__(AU_THREADS) auction_kernel(const float4* __res
       while (wpb * 2 * U <= AU_WARPS) wpb *= 2;
       if (wpb == 1) {
         for (int idx = warp; idx < U; idx += AU_WARPS) {
-          const AuBest best = au_scan<FAST>(cp, sX[cur[idx]], sY, price, N, lane, 32);
+          const AuBest best = au_scan<FAST>(cp, sX[cur[idx]], sY, DENSE ? Cb + (size_t)cur[idx] * N : nullptr, price, N, lane, 32);
           if (lane == 0) au_bid(best, eps, price, idx, lobj, lbid, bidval);
         }
       } else {
         const int idx = warp / wpb, sub = warp % wpb;
         if (idx < U) {
-          const AuBest best = au_scan<FAST>(cp, sX[cur[idx]], sY, price, N, sub * 32 + lane, 32 * wpb);
+          const AuBest best = au_scan<FAST>(cp, sX[cur[idx]], sY, DENSE ? Cb + (size_t)cur[idx] * N : nullptr, price, N, sub * 32 + lane, 32 * wpb);
           if (lane == 0) s_part[warp] = best;
         }
         __syncthreads();
@@ -252,7 +262,7 @@ extern "C" int shwd_exact_assignment(const float* x4, const float* y4, int B, in
   do {                                                                                                                      \
     if (smem > 32 * 1024) /* static + dynamic beyond 48 KB needs the opt-in */                                              \
       SHWD_CUDA_CHECK(cudaFuncSetAttribute(auction_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    auction_kernel<F><<<B, AU_THREADS, smem, s>>>(X, Y, N, cp, sigma, prices, rounds, status);                              \
+    auction_kernel<F><<<B, AU_THREADS, smem, s>>>(X, Y, nullptr, N, cp, sigma, prices, rounds, status);                     \
   } while (0)
   switch (fast) {
     case FAST_GEO2: SHWD_LAUNCH_AUCTION(FAST_GEO2); break;
@@ -260,6 +270,24 @@ extern "C" int shwd_exact_assignment(const float* x4, const float* y4, int B, in
     default: SHWD_LAUNCH_AUCTION(GENERIC);
   }
 #undef SHWD_LAUNCH_AUCTION
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+// The same solve on an explicit cost matrix C (B, N, N) float32 (costs >= 0, as every cost of this path is): what
+// ot.emd2(a, b, M) receives at main_rotation.py:63-79 (POT_loss) and in the notebooks' W2 metric.  Uniform weights, square.
+extern "C" int shwd_exact_assignment_dense(const float* C, int B, int N, int* sigma, double* prices, int* rounds, int* status,
+                                           void* stream) {
+  if (!C || !sigma || !status || B < 0 || N <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (B == 0) return SHWD_OK;
+  const size_t smem = auction_smem(N);
+  if (smem > 220 * 1024) return SHWD_ERR_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SHWD_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), s));
+  const CostParams cp = make_cost_unit(SHWD_COST_SQEUCLID, 2.f, 1.f);  // unused by the dense functor
+  if (smem > 32 * 1024)
+    SHWD_CUDA_CHECK(cudaFuncSetAttribute(auction_kernel<AU_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auction_kernel<AU_DENSE><<<B, AU_THREADS, smem, s>>>(nullptr, nullptr, C, N, cp, sigma, prices, rounds, status);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }

@@ -469,6 +469,46 @@ def exact_assignment(x, y, kind="sqeuclid", p=2.0, n_power=1.0, return_info=Fals
     return sig
 
 
+def exact_assignment_dense(C, return_info=False):
+    """Optimal assignment sigma (B,N) int64 for explicit square cost matrices C (B,N,N) [or (N,N)] float32 with uniform
+    weights -- the LP ``ot.emd2(a, b, M)`` solves when called on a cost matrix (main_rotation.py:63-79)."""
+    lib = _lib.lib()
+    if not isinstance(C, torch.Tensor) or not C.is_cuda:
+        raise RuntimeError("the cost matrix must live on a CUDA device: the B200 loss path has no CPU fallback")
+    Cb = C.detach()
+    if Cb.dim() == 2:
+        Cb = Cb.unsqueeze(0)
+    if Cb.dim() != 3 or Cb.shape[1] != Cb.shape[2]:
+        raise ValueError("exact assignment needs square cost matrices (uniform weights, n == m), got %s" % (tuple(C.shape),))
+    Cb = Cb.float().contiguous()
+    B, N, _ = Cb.shape
+    if N > lib.shwd_exact_assignment_max_points():
+        raise ValueError("exact assignment supports at most %d points per cloud" % lib.shwd_exact_assignment_max_points())
+    dev = Cb.device
+    sigma = torch.empty(B, N, device=dev, dtype=torch.int32)
+    prices = torch.empty(B, N, device=dev, dtype=torch.float64)
+    rounds = torch.empty(B, device=dev, dtype=torch.int32)
+    status = torch.empty(1, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.shwd_exact_assignment_dense(_ptr(Cb), B, N, _ptr(sigma), _ptr(prices), _ptr(rounds), _ptr(status), _stream()),
+                   "shwd_exact_assignment_dense")
+    sig = sigma.long()
+    if return_info:
+        return sig, prices, rounds, status
+    return sig
+
+
+def exact_emd2_dense(M):
+    """``ot.emd2(a, b, M)`` for uniform ``a``, ``b`` and a square cost matrix M (N,N) [or (B,N,N) -> (B,)]: the value
+    (1/n) sum_i M[i, sigma(i)] accumulated in float64 like POT, returned in M's dtype; through autograd on the n matched
+    entries the gradient w.r.t. M is the optimal plan -- what POT's torch backend attaches."""
+    sigma = exact_assignment_dense(M)
+    Mb = M if M.dim() == 3 else M.unsqueeze(0)
+    c = torch.gather(Mb, 2, sigma.unsqueeze(-1)).squeeze(-1)  # (B,N): M[b, i, sigma(i)]
+    v = (c.double().sum(dim=1) / Mb.shape[1]).to(M.dtype)
+    return v if M.dim() == 3 else v.reshape(())
+
+
 def _pair_cost(x, ys, kind, p, n_power=1.0):
     """C(x_i, ys_i) for matched points, with the reference's own torch formulas (s2_wasserstein.py:52-63,112-123;
     max_spherical_w_cos_with_regulation.py:745) so the value and its autograd are the reference's on those n entries."""

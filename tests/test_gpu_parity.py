@@ -1031,3 +1031,47 @@ def test_graphed_loss_signatures_and_one_sided_gradients(shwd):
         gfn(x.cpu(), y.cpu())
     with pytest.raises(ValueError):
         shwd.graphed_loss(lambda a, b: shwd.chamfer_nn(a, b)[0])(x, y)  # not a scalar
+
+
+# ------------------------------------------------------------------------------------- ot.emd2 on a cost matrix ----
+@pytest.mark.parametrize("N,kind", [(1, "rand"), (7, "rand"), (64, "rand"), (300, "euclid"), (1024, "euclid"), (256, "ties")])
+def test_dense_emd2_dropin_is_the_lp_optimum(shwd, N, kind):
+    """dropin_ot/ot.emd2(a, b, M) (auction kernel on an explicit cost matrix) against scipy's exact assignment on the same
+    float32 matrix: optimal value, the permutation (where it is unique) and d emd2 / dM = plan -- POT's semantics."""
+    import sys
+    from scipy.optimize import linear_sum_assignment
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dropin_ot"))
+    import ot
+    g = torch.Generator().manual_seed(N)
+    if kind == "euclid":  # main_rotation.py:82-92 cost_matrix, p = 2
+        x = F.normalize(torch.randn(N, 3, generator=g), dim=-1)
+        y = F.normalize(torch.randn(N, 3, generator=g) + 0.2, dim=-1)
+        M = torch.pow(torch.sum(torch.abs(x.unsqueeze(-2) - y.unsqueeze(-3)) ** 2, -1), 0.5)
+    elif kind == "ties":
+        M = torch.randint(0, 4, (N, N), generator=g).float()
+    else:
+        M = torch.rand(N, N, generator=g)
+    r, c = linear_sum_assignment(M.double().numpy())
+    ref = M.double()[r, c].sum().item() / N
+    Mg = M.to(dev()).requires_grad_(True)
+    w = torch.full((N,), 1.0 / N, device=dev())
+    val = ot.emd2(w, w, Mg)
+    assert val.shape == () and val.dtype == torch.float32
+    assert abs(val.item() - ref) <= 2e-6 * max(abs(ref), 1e-30) + 1e-12
+    val.backward()
+    plan = Mg.grad.cpu()
+    assert torch.equal(plan.sum(0), torch.full((N,), 1.0 / N)) and torch.equal(plan.sum(1), torch.full((N,), 1.0 / N))
+    assert (plan > 0).sum().item() == N
+    if kind != "ties":
+        assert torch.equal(plan.argmax(1), torch.from_numpy(c).long())
+    # batched form + the reference's POT_loss pattern (main_rotation.py:63-79): sum_b emd2_b^(1/p)
+    Mb = torch.stack([M, M.t().contiguous()]).to(dev())
+    vb = shwd.exact_emd2_dense(Mb)
+    assert vb.shape == (2,) and abs(vb[0].item() - val.item()) < 1e-7 and abs(vb[1].item() - ref) <= 2e-6 * max(abs(ref), 1e-30) + 1e-12
+    with pytest.raises(NotImplementedError):
+        ot.emd2(w, w, torch.rand(N, N + 1, device=dev()))
+    if N > 1:
+        w2 = w.clone()
+        w2[0] *= 1.5
+        with pytest.raises(NotImplementedError):
+            ot.emd2(w2, w, Mg)

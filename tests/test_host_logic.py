@@ -232,3 +232,15 @@ def test_graphed_loss_refuses_cpu_tensors():
     with pytest.raises(RuntimeError, match="CUDA"):
         gfn(torch.randn(4, 3), torch.randn(4, 3))
     assert len(gfn._captures) == 0
+
+
+def test_ot_dropin_exports_emd2_and_refuses_cpu_matrices():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dropin_ot"))
+    import ot
+    assert ot.__all__ == ["emd2"]
+    w = torch.full((4,), 0.25)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ot.emd2(w, w, torch.rand(4, 4))
+    with pytest.raises(NotImplementedError):
+        ot.emd2(w, w, torch.rand(4, 5))
