@@ -17,8 +17,12 @@ import torch
 __all__ = ["graphed_loss", "GraphedLoss"]
 
 
+def _needs_grad(t):
+    return bool(isinstance(t, torch.Tensor) and t.requires_grad and torch.is_grad_enabled())
+
+
 def _signature(tensors):
-    return tuple((tuple(t.shape), t.dtype, t.device.index, bool(t.requires_grad)) for t in tensors)
+    return tuple((tuple(t.shape), t.dtype, t.device.index, _needs_grad(t)) if isinstance(t, torch.Tensor) else ("?",) for t in tensors)
 
 
 class _Capture:
@@ -28,9 +32,10 @@ class _Capture:
         for t in tensors:
             if not (isinstance(t, torch.Tensor) and t.is_cuda):
                 raise RuntimeError("graphed_loss: every argument must be a CUDA tensor (no CPU fallback)")
-        self.needs = [bool(t.requires_grad) for t in tensors]
+        self.needs = [_needs_grad(t) for t in tensors]
         self.static_in = [t.detach().clone().contiguous() for t in tensors]
 
+        @torch.enable_grad()
         def run():
             ins = [s.detach().requires_grad_(n) for s, n in zip(self.static_in, self.needs)]
             loss = fn(*ins)

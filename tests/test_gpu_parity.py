@@ -1025,6 +1025,7 @@ def test_graphed_loss_signatures_and_one_sided_gradients(shwd):
     assert torch.equal(xg.grad, xe.grad)
     with torch.no_grad():
         assert torch.equal(gfn(x, y), fn(x, y))
+        assert torch.equal(gfn(xg, y), fn(x, y))  # requires_grad input under no_grad: the gradient-free capture is used
     gfn(torch.randn(1, 50, 3, device=dev()), torch.randn(1, 70, 3, device=dev()))  # a new shape -> a new capture
     assert len(gfn._captures) == 3
     with pytest.raises(RuntimeError):
