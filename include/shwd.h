@@ -84,6 +84,17 @@ int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N, int M, int
                       void* workspace, size_t workspace_bytes, void* stream);
 /* status word of the last persistent launch that used `workspace` (0 ok, 1 = an inter-CTA wait timed out). */
 int shwd_sinkhorn_status_offset(void);
+/* Two kernel families serve shwd_sinkhorn_fwd / _bwd with identical arithmetic and history format: the flattened-deal
+ * persistent kernels (any size; the benchmark shape B=32, N=1024) and the dedicated-CTA "lean" kernels for small
+ * problems -- the reference's B=32, N=128..256 runs (train_RUNNER.py:124-127), single pairs of N~1000
+ * (Flow_ellipsoid.ipynb cell 8), a strong-scaled batch's 4 pairs per GPU.  The lean forward needs the history
+ * (hist_levels = iters+1) and no early stop.
+ *   shwd_sinkhorn_lean_regime: 1 if a (B,N,M) problem would take the lean kernels -- callers then keep the history
+ *                              even for forward-only calls;
+ *   shwd_sinkhorn_set_path:    0 automatic (default), 1 always flattened-deal, 2 lean whenever eligible (A/B timing,
+ *                              tests).  Process-wide; not thread-safe against concurrent launches. */
+int shwd_sinkhorn_lean_regime(int B, int N, int M);
+int shwd_sinkhorn_set_path(int mode);
 /* Opt-in dense outputs for the reference's (cost, P, C) return (sinkhorn.py:60): P, C (B,N,M), either nullable. */
 int shwd_sinkhorn_plan_dense(const float* x4, const float* y4, int B, int N, int M, int cost_kind, float p,
                              float n_power, float eps, const float* alpha, const float* beta, int level_stride_n,

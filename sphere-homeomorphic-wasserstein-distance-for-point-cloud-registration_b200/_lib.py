@@ -27,6 +27,8 @@ SIGNATURES = {
     "shwd_sinkhorn_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "shwd_sinkhorn_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "shwd_sinkhorn_status_offset": (_i, []),
+    "shwd_sinkhorn_lean_regime": (_i, [_i, _i, _i]),
+    "shwd_sinkhorn_set_path": (_i, [_i]),
     "shwd_sinkhorn_plan_dense": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "shwd_chamfer_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "shwd_chamfer_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

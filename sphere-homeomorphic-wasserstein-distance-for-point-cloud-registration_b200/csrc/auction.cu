@@ -134,13 +134,30 @@ __global__ void __launch_bounds__(AU_THREADS) auction_kernel(const float4* __res
   __syncthreads();
   // Cmax = max_ij kC_ij (sets the epsilon schedule)
   float cm = 0.f;
+  bool nonfinite = false;
   for (int i = warp; i < N; i += AU_WARPS) {
     const float4 o = sX[i];
-    for (int j = lane; j < N; j += 32) cm = fmaxf(cm, au_cost<FAST>(cp, o, sY, DENSE ? Cb + (size_t)i * N : nullptr, j));
+    for (int j = lane; j < N; j += 32) {
+      const float cij = au_cost<FAST>(cp, o, sY, DENSE ? Cb + (size_t)i * N : nullptr, j);
+      nonfinite = nonfinite || !(fabsf(cij) <= 3.0e38f);
+      cm = fmaxf(cm, cij);
+    }
   }
   cm = warp_max(cm);
   if (lane == 0) s_red[warp] = (double)cm;
-  __syncthreads();
+  if (__syncthreads_or(nonfinite)) {
+    // a NaN / infinite cost (a diverged model upstream): no assignment is meaningful and the bidding would run to
+    // AU_MAX_ROUNDS.  Report failure at once; sigma = identity keeps every downstream gather in range.
+    for (int i = threadIdx.x; i < N; i += AU_THREADS) {
+      sigma[(size_t)b * N + i] = i;
+      if (price_out) price_out[(size_t)b * N + i] = 0.0;
+    }
+    if (threadIdx.x == 0) {
+      if (rounds_out) rounds_out[b] = 0;
+      atomicExch(status, 1);
+    }
+    return;
+  }
   double cmax = 0.0;
   for (int w = 0; w < AU_WARPS; ++w) cmax = fmax(cmax, s_red[w]);
   if (!(cmax > 0.0)) cmax = 1.0;  // all costs zero (or NaN): any assignment is optimal; run one trivial phase
@@ -221,7 +238,7 @@ __global__ void __launch_bounds__(AU_THREADS) auction_kernel(const float4* __res
   }
   __syncthreads();
   for (int i = threadIdx.x; i < N; i += AU_THREADS) {
-    sigma[(size_t)b * N + i] = objof[i];
+    sigma[(size_t)b * N + i] = failed ? i : objof[i];  // (a failed solve leaves persons unassigned: keep indices in range)
     if (price_out) price_out[(size_t)b * N + i] = price[i];
   }
   if (threadIdx.x == 0) {

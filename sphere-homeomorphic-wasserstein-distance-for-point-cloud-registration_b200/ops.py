@@ -78,6 +78,13 @@ def flow_regularization(x):
     return reg.sum()
 
 
+def _poison(t, ws):
+    """NaN out ``t`` when the status word at the head of the persistent kernels' workspace is non-zero (include/shwd.h:
+    shwd_sinkhorn_status_offset) -- decided on the device, so a failed launch can never pass for a result."""
+    failed = ws[:4].view(torch.int32) != 0
+    return torch.where(failed.view((1,) * t.dim()), torch.full((), float("nan"), device=t.device, dtype=t.dtype), t)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 class EntropicOTFn(torch.autograd.Function):
     """cost_b = sum_ij P_ij C_ij after L log-domain Sinkhorn iterations on an on-the-fly cost; reverse mode through all
@@ -95,7 +102,8 @@ class EntropicOTFn(torch.autograd.Function):
         f32 = dict(device=dev, dtype=torch.float32)
         x4 = torch.empty(B, N, 4, **f32)
         y4 = torch.empty(B, M, 4, **f32)
-        keep = bool(need_grad) or thresh > 0
+        # the lean kernels for small problems exchange potentials through the write-once history planes: keep them
+        keep = bool(need_grad) or thresh > 0 or bool(lib.shwd_sinkhorn_lean_regime(B, N, M))
         HL = iters + 1 if keep else 1
         alpha = torch.empty(2, B, HL, N, **f32)  # plane 0: iterates k*u; plane 1: float32 rounding residuals
         beta = torch.empty(2, B, HL, M, **f32)
@@ -112,6 +120,8 @@ class EntropicOTFn(torch.autograd.Function):
             _lib.check(lib.shwd_sinkhorn_fwd(_ptr(x4), _ptr(y4), B, N, M, kind, p, n_power, eps, iters, thresh, HL, _ptr(alpha),
                                              _ptr(beta), _ptr(row_pc), _ptr(col_pc), _ptr(cost), _ptr(iters_run), _ptr(ws), wsb, s),
                        "shwd_sinkhorn_fwd")
+        # a timed-out inter-CTA wait leaves garbage potentials behind: poison the result on the device (no host sync)
+        cost = _poison(cost, ws)
         ctx.save_for_backward(x, y, x4, y4, alpha, beta, row_pc, col_pc, iters_run)
         ctx.cfg = (kind, p, n_power, eps, iters, flags, keep)
         ctx.mark_non_differentiable(alpha, beta, iters_run, ws)
@@ -141,8 +151,7 @@ class EntropicOTFn(torch.autograd.Function):
                                              wsb, s), "shwd_sinkhorn_bwd")
             _lib.check(lib.shwd_sphere_map_bwd(_ptr(x), _ptr(x4), _ptr(g4x), None, _ptr(gx), B, N, flags, s), "shwd_sphere_map_bwd")
             _lib.check(lib.shwd_sphere_map_bwd(_ptr(y), _ptr(y4), _ptr(g4y), None, _ptr(gy), B, M, flags, s), "shwd_sphere_map_bwd")
-        ctx.last_ws = ws
-        return gx, gy, None, None, None, None, None, None, None, None
+        return _poison(gx, ws), _poison(gy, ws), None, None, None, None, None, None, None, None
 
 
 class EntropicOTResult:
@@ -502,10 +511,11 @@ def exact_emd2_dense(M):
     """``ot.emd2(a, b, M)`` for uniform ``a``, ``b`` and a square cost matrix M (N,N) [or (B,N,N) -> (B,)]: the value
     (1/n) sum_i M[i, sigma(i)] accumulated in float64 like POT, returned in M's dtype; through autograd on the n matched
     entries the gradient w.r.t. M is the optimal plan -- what POT's torch backend attaches."""
-    sigma = exact_assignment_dense(M)
+    sigma, _, _, status = exact_assignment_dense(M, return_info=True)
     Mb = M if M.dim() == 3 else M.unsqueeze(0)
     c = torch.gather(Mb, 2, sigma.unsqueeze(-1)).squeeze(-1)  # (B,N): M[b, i, sigma(i)]
     v = (c.double().sum(dim=1) / Mb.shape[1]).to(M.dtype)
+    v = torch.where(status != 0, torch.full_like(v, float("nan")), v)  # failed solve (non-finite costs): never a number
     return v if M.dim() == 3 else v.reshape(())
 
 
@@ -531,10 +541,11 @@ def exact_emd2(x, y, kind="sqeuclid", p=2.0):
     entries -- exactly the gradient POT attaches (d emd2 / dC = optimal plan)."""
     xc, _ = _as_cloud(x, "x")
     yc, _ = _as_cloud(y, "y")
-    sigma = exact_assignment(xc, yc, kind, p)
+    sigma, _, _, status = exact_assignment(xc, yc, kind, p, return_info=True)
     ys = torch.gather(yc, 1, sigma.unsqueeze(-1).expand(-1, -1, 3))
     c = _pair_cost(xc, ys, kind, p)
-    return (c.double().sum(dim=1) / xc.shape[1]).to(c.dtype)
+    v = (c.double().sum(dim=1) / xc.shape[1]).to(c.dtype)
+    return torch.where(status != 0, torch.full_like(v, float("nan")), v)  # failed solve (non-finite costs): never a number
 
 
 class ResidualFlowStackFn(torch.autograd.Function):

@@ -139,6 +139,102 @@ def test_geodesic_sinkhorn_matches_oracle(shwd, B, N, M, L, eps):
     assert rel(gy[ok], gy_ref[ok]) < TOL
 
 
+# ---- the two kernel families behind shwd_sinkhorn_fwd / _bwd (include/shwd.h: shwd_sinkhorn_set_path) -----------------
+PATHS = {"auto": 0, "flat": 1, "lean": 2}
+
+
+class _path:
+    """Force the flattened-deal (1) or the lean small-problem (2) kernels for the enclosed calls."""
+
+    def __init__(self, shwd, name):
+        self.lib, self.mode = shwd._lib.lib(), PATHS[name]
+
+    def __enter__(self):
+        assert self.lib.shwd_sinkhorn_set_path(self.mode) == 0
+
+    def __exit__(self, *a):
+        self.lib.shwd_sinkhorn_set_path(0)
+
+
+LEAN_SHAPES = [
+    # B, N, M, L, eps                 what the mapping looks like on 148 SMs
+    (1, 1024, 1024, 100, 0.01),     # one pair over 128 CTAs, 8 owners per warp row (4 sub-slices per warp)
+    (1, 256, 256, 40, 0.01),        # 32 CTAs, heavy padding of the packed records
+    (4, 1024, 1024, 100, 0.01),     # the 4 pairs per GPU of an 8-way strong-scaled B=32: 32 CTAs per pair, 32 owners each
+    (32, 256, 256, 100, 0.01),      # train_RUNNER.py's small runs: 4 CTAs per pair, two owner groups each
+    (200, 256, 200, 12, 0.02),      # B > #SMs: whole pairs per CTA, 8 + 7 owner groups, 4 group pairs x 4 slices
+    (3, 40, 700, 15, 0.05),         # ragged: most CTAs have no row owners at all
+    (2, 2048, 1500, 8, 0.05),       # the largest resident clouds
+    (9, 600, 600, 20, 0.02),        # 16 CTAs per pair, 38 owners -> two groups of 32 with a ragged tail
+    (16, 1000, 1024, 10, 0.02),     # 9 CTAs per pair, four groups
+]
+
+
+@pytest.mark.parametrize("B,N,M,L,eps", LEAN_SHAPES)
+def test_lean_kernels_match_oracle_and_flat_kernels(shwd, B, N, M, L, eps):
+    """The dedicated-CTA kernels for small problems (csrc/sinkhorn_lean.cu) against the float32 oracle (1e-5), and
+    against the flattened-deal kernels they replace there (same arithmetic, different summation grouping)."""
+    assert shwd._lib.lib().shwd_sinkhorn_lean_regime(B, N, M) == 1 or B * max(N, M) > 32 * 4 * 148
+    torch.manual_seed(B * 31 + N + M)
+    x = F.normalize(torch.randn(B, N, 3), dim=-1) * (1 + 0.2 * torch.rand(B, N, 1))
+    y = F.normalize(torch.randn(B, M, 3) + 0.3, dim=-1)
+    with _path(shwd, "lean"):
+        cost, gx, gy, _ = _run_cuda(shwd, x, y, "geodesic", 2.0, eps, L)
+    with _path(shwd, "flat"):
+        cost_f, gx_f, gy_f, _ = _run_cuda(shwd, x, y, "geodesic", 2.0, eps, L)
+    assert torch.isfinite(cost).all() and torch.isfinite(gx).all() and torch.isfinite(gy).all()
+    print("lean vs flat: cost %.2e gx %.2e gy %.2e" % (rel(cost, cost_f), rel(gx, gx_f), rel(gy, gy_f)))
+    assert rel(cost, cost_f) < 2e-6 and rel(gx, gx_f) < TOL and rel(gy, gy_f) < TOL
+    if B * N * M * L > 6e8:  # the CPU oracle's autograd tape: keep it to a few pairs
+        keep = slice(0, max(1, int(6e8 // (N * M * L))))
+        x, y, cost, gx, gy = x[keep], y[keep], cost[keep], gx[keep], gy[keep]
+    c_ref, gx_ref, gy_ref = _run_oracle(x, y, "geodesic", 2, eps, L)
+    ok = torch.isfinite(c_ref) & torch.isfinite(gx_ref).flatten(1).all(1) & torch.isfinite(gy_ref).flatten(1).all(1)
+    assert ok.any()
+    errs = (rel(cost[ok], c_ref[ok]), rel(gx[ok], gx_ref[ok]), rel(gy[ok], gy_ref[ok]))
+    print("lean vs oracle: cost %.2e gx %.2e gy %.2e" % errs)
+    assert max(errs) < TOL
+
+
+@pytest.mark.parametrize("kind,p", [("geodesic", 1), ("sqeuclid", 2), ("sqeuclid", 1), ("euclid", 2), ("one_minus_cos", 2)])
+@pytest.mark.parametrize("B,N,M", [(1, 700, 512), (12, 256, 300)])
+def test_lean_kernels_other_packed_costs(shwd, kind, p, B, N, M):
+    """Every packed cost kind through the lean kernels, against the reference's float32 / float64 evaluations."""
+    torch.manual_seed(B + N)
+    x = F.normalize(torch.randn(B, N, 3), dim=-1)
+    y = F.normalize(torch.randn(B, M, 3) + 0.3, dim=-1)
+    with _path(shwd, "lean"):
+        cost, gx, gy, _ = _run_cuda(shwd, x, y, kind, float(p), 0.02, 30)
+    c32, gx32, gy32 = _run_oracle(x, y, kind, p, 0.02, 30)
+    c64, gx64, gy64 = _run_oracle(x, y, kind, p, 0.02, 30, dtype=torch.float64)
+    ok = torch.isfinite(c32) & torch.isfinite(gx32).flatten(1).all(1) & torch.isfinite(gy32).flatten(1).all(1)
+    assert ok.any() and torch.isfinite(cost).all() and torch.isfinite(gx).all() and torch.isfinite(gy).all()
+    for a, r32, r64 in ((cost, c32, c64), (gx, gx32, gx64), (gy, gy32, gy64)):
+        floor = rel(r32[ok], r64[ok])
+        print("%s p=%s: err %.2e (float32 reference's own floor %.2e)" % (kind, p, rel(a[ok], r32[ok]), floor))
+        assert rel(a[ok], r32[ok]) < max(TOL, 8 * floor)
+
+
+def test_lean_forward_without_grad_and_reproducibility(shwd):
+    """Forward-only calls keep the history in the lean regime (the exchange planes); two runs are bit-identical."""
+    torch.manual_seed(12)
+    x = F.normalize(torch.randn(4, 512, 3), dim=-1).to(dev())
+    y = F.normalize(torch.randn(4, 512, 3) + 0.2, dim=-1).to(dev())
+    with torch.no_grad():
+        a = shwd.entropic_ot(x, y, "geodesic", 2.0, 0.01, 60)
+        b = shwd.entropic_ot(x, y, "geodesic", 2.0, 0.01, 60)
+    assert a.status() == 0 and torch.equal(a.cost, b.cost)
+    ref = oracle.log_sinkhorn(x.cpu(), y.cpu(), "geodesic", 2, 0.01, 60)
+    assert rel(a.cost, ref) < TOL
+    xg, yg = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    g = []
+    for _ in range(2):
+        xg.grad = yg.grad = None
+        shwd.entropic_ot(xg, yg, "geodesic", 2.0, 0.01, 60).cost.sum().backward()
+        g.append((xg.grad.clone(), yg.grad.clone()))
+    assert torch.equal(g[0][0], g[1][0]) and torch.equal(g[0][1], g[1][1])
+
+
 OTHER = [
     # fixture, kind, p, n_power, thresh
     ("geodesic_sinkhorn_p1", "geodesic", 1, 1, 0.0),
