@@ -30,7 +30,6 @@
 // and each sweep also adds the cost-gradient terms it can form for its OWNER side without any cross-thread reduction:
 // its own term plus the adjacent other-type term that shares the streamed vector (row sweep(l): S^u,l+1; col sweep(l):
 // S^v,l), i.e. two exp2 per element instead of a 4-value cross-lane reduction per element.
-#define SHWD_PROF_OWNER
 #include "sinkhorn_core.cuh"
 #include "sinkhorn_lean.h"
 

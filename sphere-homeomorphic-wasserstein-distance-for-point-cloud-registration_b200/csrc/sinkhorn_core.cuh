@@ -52,11 +52,10 @@ enum { MODE_LSE = 0, MODE_FINAL = 1, MODE_BWD = 2 };
 // Optional in-kernel phase timing (build with -DSHWD_PROFILE): thread 0 of every CTA accumulates clock64 deltas per
 // phase into the workspace's err area tail; read back by tools/phase_profile.py.  Off in the product build.
 #ifdef SHWD_PROFILE
-#ifdef SHWD_PROF_OWNER
-__device__ unsigned long long g_prof[8];
-#else
-extern __device__ unsigned long long g_prof[8];
+#ifndef SHWD_PROF_SYM
+#define SHWD_PROF_SYM g_prof
 #endif
+__device__ unsigned long long SHWD_PROF_SYM[8];  // one array per translation unit (no relocatable device code)
 __shared__ long long s_prof_t;
 #define PROF_INIT()                          \
   do {                                       \
@@ -66,7 +65,7 @@ __shared__ long long s_prof_t;
   do {                                                                      \
     if (threadIdx.x == 0) {                                                 \
       long long _n = clock64();                                             \
-      atomicAdd(&g_prof[slot], (unsigned long long)(_n - s_prof_t));        \
+      atomicAdd(&SHWD_PROF_SYM[slot], (unsigned long long)(_n - s_prof_t));        \
       s_prof_t = _n;                                                        \
     }                                                                       \
   } while (0)

@@ -25,6 +25,7 @@
 //
 // The two FINAL sweeps of either direction (4 of 404 sweeps) run through the general kernel's code (fwd_tail /
 // bwd_phase in sinkhorn_core.cuh) on the flattened deal; the hand-over is one counter per pair.
+#define SHWD_PROF_SYM g_prof_lean
 #include "sinkhorn_core.cuh"
 #include "sinkhorn_lean.h"
 
@@ -68,6 +69,34 @@ __device__ __forceinline__ LeanView lean_view(float4* smem4, const LeanGeom& gm,
 }
 __device__ __forceinline__ float4* lean_part(float4* smem4, const LeanGeom& gm, bool bwd) {
   return reinterpret_cast<float4*>(reinterpret_cast<float2*>(smem4) + (bwd ? 6 : 4) * (gm.T[0] + gm.T[1]));
+}
+
+// log2 of a positive, normal float32 as a double, accurate to ~1e-12 -- far inside what the float32 sum it is applied to
+// carries.  The library's double log2 is ~150 dependent instructions on the one warp every other CTA of the pair is
+// waiting for; this is ~20: exponent split, s = (f-1)/(f+1) with a float reciprocal seed and one Newton step,
+// 2 atanh(s) by its odd series through s^13 (|s| <= 0.172).
+__device__ __forceinline__ double lean_log2(float x) {
+  const int bits = __float_as_int(x);
+  int e = ((bits >> 23) & 0xff) - 127;
+  float f = __int_as_float((bits & 0x007fffff) | 0x3f800000);  // [1, 2)
+  if (f > 1.41421356f) {
+    f *= 0.5f;
+    e += 1;
+  }
+  const double fd = (double)f;
+  const double den = fd + 1.0;
+  double r = (double)__frcp_rn((float)den);
+  r = r * (2.0 - den * r);
+  const double t = (fd - 1.0) * r;
+  const double t2 = t * t;
+  double p = 1.0 / 13.0;
+  p = fma(p, t2, 1.0 / 11.0);
+  p = fma(p, t2, 1.0 / 9.0);
+  p = fma(p, t2, 1.0 / 7.0);
+  p = fma(p, t2, 1.0 / 5.0);
+  p = fma(p, t2, 1.0 / 3.0);
+  p = fma(p, t2, 1.0);
+  return fma(t * p, 2.8853900817779268, (double)e);  // 2 / ln 2
 }
 
 // packed position of streamed point q: record t = q mod T, half = q / T
@@ -133,18 +162,45 @@ __device__ __forceinline__ void lean_poll(const float* src, int cnt, int T, floa
   }
 }
 
-// One warp's pass of a half-step: its (group pair, streamed slice), then the combination of the sub-slices of a warp row.
-template <int PK, int MODE, bool OFF>
-__device__ __forceinline__ void lean_compute(const CostParams& cp, float lconst, const LeanView& v, float4* part, int rw_shift) {
+// What a thread does in every half-step of one type -- fixed for the whole pair, so computed once (the runtime divisions
+// and the address arithmetic otherwise cost ~150 instructions per warp and half-step, on the critical path).
+struct LeanThread {
+  int tb, te;      // packed records of this lane's sub-slice; te < 0: the warp has no group pair
+  int slot;        // float4 index of the lane's partial in `part`
+  int own;         // float4 index of the lane's first owner record (relative to LeanView::own / own3)
+  int two;         // the warp sweeps two owner groups
+  int pp;          // merge: float4 index of this owner's slice-0 partial; < 0: not an owner thread
+  int pp_stride;   // float4 stride between the slice partials of one owner
+  int NS;
+};
+__device__ __forceinline__ LeanThread lean_thread(const LeanView& v, int rw_shift) {
+  LeanThread t;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slice = warp / v.NGP, gpi = warp % v.NGP;
   const int g = 2 * gpi;
-  if (g >= v.ng) return;
-  const bool two = g + 1 < v.ng;
-  const int NS = SK_WARPS / v.NGP;
-  const int SLr = v.T / NS;               // records per slice
+  t.NS = SK_WARPS / v.NGP;
+  const int SLr = v.T / t.NS;             // records per slice
   const int SLs = SLr >> (5 - rw_shift);  // records per sub-slice (multiple of 4)
-  const int tb = slice * SLr + (lane >> rw_shift) * SLs, te = tb + SLs;
+  t.tb = slice * SLr + (lane >> rw_shift) * SLs;
+  t.te = g < v.ng ? t.tb + SLs : -1;
+  t.two = g + 1 < v.ng;
+  t.slot = ((slice * 2 * v.NGP + g) << 5) + lane;
+  t.own = g * 32 + lane;
+  const int og = threadIdx.x >> rw_shift, oin = threadIdx.x & ((1 << rw_shift) - 1);
+  const bool owner = (int)threadIdx.x < (v.ng << rw_shift) && v.r0 + (int)threadIdx.x < v.r1;
+  t.pp = owner ? (og << 5) + oin : -1;
+  t.pp_stride = (2 * v.NGP) << 5;
+  return t;
+}
+
+// One warp's pass of a half-step: its (group pair, streamed slice), then the combination of the sub-slices of a warp row.
+template <int PK, int MODE, bool OFF>
+__device__ __forceinline__ void lean_compute(const CostParams& cp, float lconst, const LeanView& v, const LeanThread& lt, float4* part,
+                                             int rw_shift) {
+  if (lt.te < 0) return;
+  const int lane = threadIdx.x & 31;
+  const bool two = lt.two != 0;
+  const int tb = lt.tb, te = lt.te;
   PackedSmem pv;
   pv.X = v.X;
   pv.Y = v.X + v.T;
@@ -152,9 +208,9 @@ __device__ __forceinline__ void lean_compute(const CostParams& cp, float lconst,
   pv.P = v.P;
   pv.A = v.A;
   pv.S = v.S;
-  float4* slot = part + ((slice * 2 * v.NGP + g) << 5) + lane;
-  const float4* own = v.own + g * 32 + lane;
-  const float4* own3 = v.own3 + g * 32 + lane;
+  float4* slot = part + lt.slot;
+  const float4* own = v.own + lt.own;
+  const float4* own3 = v.own3 + lt.own;
   if (two)
     compute_packed_geo2<PK, MODE, 2, OFF>(cp, lconst, pv, tb, te, true, own, own3, slot);
   else
@@ -223,6 +279,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_lean_kernel(const 
 
   int b0, bstep, c;
   lean_pairs(prm, gm, b0, bstep, c);
+  PROF_INIT();
   for (int b = b0; b < prm.B; b += bstep) {
     const LeanView V0 = lean_view<false>(smem4, gm, 0, c, prm.N, prm.M), V1 = lean_view<false>(smem4, gm, 1, c, prm.M, prm.N);
     __syncthreads();  // the previous pair's readers are done
@@ -237,46 +294,51 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_lean_kernel(const 
     // beta^0 = 0 (kept in the history so the backward can stream it)
     for (int j = V1.r0 + threadIdx.x; j < V1.r1; j += SK_THREADS) prm.beta[((size_t)b * HL) * prm.M + j] = 0.f;
 
+    const LeanThread LT0 = lean_thread(V0, rw_shift), LT1 = lean_thread(V1, rw_shift);
     for (int h = 0; h < 2 * L; ++h) {
       const int type = h & 1;
       const int l = (h >> 1) + 1;
       const LeanView v = type ? V1 : V0;
+      const LeanThread lt = type ? LT1 : LT0;
       if (v.r1 <= v.r0) continue;  // (CTA-uniform) no owners of this kind in the band
       const float lconst = type ? prm.lb2 : prm.la2;
       float* P = reinterpret_cast<float*>(v.P);
+      PROF_MARK(5);
       if (type == 0 && l == 1) {
         for (int q = threadIdx.x; q < v.n_str; q += SK_THREADS) P[packed_pos(q, v.T)] = 0.f;
       } else {
         const float* src = type ? prm.alpha + ((size_t)b * HL + l) * prm.N : prm.beta + ((size_t)b * HL + (l - 1)) * prm.M;
         lean_poll<false>(src, v.n_str, v.T, P, prm.status);
       }
+      PROF_MARK(0);
       __syncthreads();
+      PROF_MARK(1);
       float* out_pot = type ? prm.beta + ((size_t)b * HL + l) * prm.M : prm.alpha + ((size_t)b * HL + l) * prm.N;
       float* out_lo = type ? prm.beta_lo + ((size_t)b * HL + l) * prm.M : prm.alpha_lo + ((size_t)b * HL + l) * prm.N;
       bool off_try = SHWD_OFFSET_LSE && h >= 2;
       for (;;) {
         if (off_try)
-          lean_compute<PK, MODE_LSE, true>(prm.cp, lconst, v, part, rw_shift);
+          lean_compute<PK, MODE_LSE, true>(prm.cp, lconst, v, lt, part, rw_shift);
         else
-          lean_compute<PK, MODE_LSE, false>(prm.cp, lconst, v, part, rw_shift);
+          lean_compute<PK, MODE_LSE, false>(prm.cp, lconst, v, lt, part, rw_shift);
+        PROF_MARK(2);
         __syncthreads();
+        PROF_MARK(6);
         // merge the NS slice partials of every owner in fixed order
-        const int NS = SK_WARPS / v.NGP;
-        const int g = threadIdx.x >> rw_shift, oin = threadIdx.x & (RW - 1);
         const int o = v.r0 + threadIdx.x;
-        const bool owner = threadIdx.x < (v.ng << rw_shift) && o < v.r1;
+        const bool owner = lt.pp >= 0;
         float mx = NEG_BIG, sum = 0.f;
         bool bad = false;
         if (owner) {
-          const float4* pp = part + (g << 5) + oin;
+          const float4* pp = part + lt.pp;
           if (off_try) {
             mx = pp[0].x;  // the common offset
-            for (int s = 0; s < NS; ++s) sum += pp[(s * 2 * v.NGP) << 5].y;
+            for (int s = 0; s < lt.NS; ++s) sum += pp[s * lt.pp_stride].y;
             bad = !(sum >= 0x1p-60f && sum <= 0x1p60f);
           } else {
-            for (int s = 0; s < NS; ++s) mx = fmaxf(mx, pp[(s * 2 * v.NGP) << 5].x);
-            for (int s = 0; s < NS; ++s) {
-              const float4 st = pp[(s * 2 * v.NGP) << 5];
+            for (int s = 0; s < lt.NS; ++s) mx = fmaxf(mx, pp[s * lt.pp_stride].x);
+            for (int s = 0; s < lt.NS; ++s) {
+              const float4 st = pp[s * lt.pp_stride];
               sum += st.y * ex2_approx(st.x - mx);
             }
           }
@@ -285,15 +347,17 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_lean_kernel(const 
           off_try = false;
           continue;
         }
+        PROF_MARK(3);
         if (owner) {
           // new potential in double, float32 rounding residual kept for the backward (see finalize_visit)
-          const double npd = (double)lconst - ((double)mx + log2((double)sum));
+          const double npd = (double)lconst - ((double)mx + lean_log2(sum));
           const float np = (float)npd;
           out_lo[o] = (float)(npd - (double)np);
           out_pot[o] = np;
-          float4* ow = v.own + (g << 5) + oin;
+          float4* ow = v.own + lt.pp;
           for (int s = 0; s < nsub; ++s) ow[s << rw_shift].w = np;
         }
+        PROF_MARK(4);
         break;
       }
     }
@@ -318,6 +382,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_lean_kernel(const 
   __shared__ ResidentType s_RT[2];
   constexpr int PK = is_packed_cost(FAST) ? FAST : FAST_GEO2;
   if (threadIdx.x == 0) s_RT[0].ok = s_RT[1].ok = 0;
+  PROF_INIT();
   const int HL = prm.hist_levels;
   const int Ls = *prm.iters_run;
   const int rw_shift = gm.rw_shift, RW = 1 << rw_shift, nsub = 32 >> rw_shift;
@@ -338,6 +403,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_lean_kernel(const 
 
   int b0, bstep, c;
   lean_pairs(prm, gm, b0, bstep, c);
+  PROF_INIT();
   for (int b = b0; b < prm.B; b += bstep) {
     const LeanView V0 = lean_view<true>(smem4, gm, 0, c, prm.N, prm.M), V1 = lean_view<true>(smem4, gm, 1, c, prm.M, prm.N);
     wait_done(prm.done + b, gr + gc, prm.status);  // (ends with a barrier: the previous users of the shared arrays are done)
@@ -375,15 +441,18 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_lean_kernel(const 
       V1.ownadj[threadIdx.x] = __ldcg(bbar_b + (size_t)(Ls - 1) * BM + oy);
     }
 
+    const LeanThread LT0 = lean_thread(V0, rw_shift), LT1 = lean_thread(V1, rw_shift);
     for (int ph = 2; ph <= 2 * Ls; ++ph) {
       const bool last = (ph == 2 * Ls);
       const int type = last ? 0 : (ph & 1);
       const int l = last ? 0 : Ls - (ph >> 1);
       const LeanView v = type ? V1 : V0;
+      const LeanThread lt = type ? LT1 : LT0;
       if (v.r1 <= v.r0) continue;  // (CTA-uniform)
       float* P = reinterpret_cast<float*>(v.P);
       float* A = reinterpret_cast<float*>(v.A);
       float* S = reinterpret_cast<float*>(v.S);
+      PROF_MARK(5);
       // ---- PRE (independent of the previous phase): streamed potential of the forward history, its float32 addend and
       // the 2^res correction (parked in A until the adjoint arrives); the owners' exponents
       {
@@ -417,23 +486,26 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_lean_kernel(const 
           for (int s = 0; s < nsub; ++s) ow[s << rw_shift] = e;
         }
       }
+      PROF_MARK(1);
       // ---- POST: the streamed adjoint of the previous phase (same thread -> same records as PRE: no barrier needed)
       if (!last) {
         const float* sadj = type ? abar_b + (size_t)l * BN : bbar_b + (size_t)l * BM;
         lean_poll<true>(sadj, v.n_str, v.T, A, prm.status);
       }
+      PROF_MARK(0);
       __syncthreads();
-      lean_compute<PK, MODE_BWD, false>(prm.cp, 0.f, v, part, rw_shift);
+      PROF_MARK(6);
+      lean_compute<PK, MODE_BWD, false>(prm.cp, 0.f, v, lt, part, rw_shift);
+      PROF_MARK(2);
       __syncthreads();
+      PROF_MARK(3);
       // ---- merge + publish
-      if (threadIdx.x < (v.ng << rw_shift) && v.r0 + (int)threadIdx.x < v.r1) {
-        const int NS = SK_WARPS / v.NGP;
-        const int g = threadIdx.x >> rw_shift, oin = threadIdx.x & (RW - 1);
+      if (lt.pp >= 0) {
         const int o = v.r0 + threadIdx.x;
-        const float4* pp = part + (g << 5) + oin;
+        const float4* pp = part + lt.pp;
         float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < NS; ++s) {
-          const float4 st = pp[(s * 2 * v.NGP) << 5];
+        for (int s = 0; s < lt.NS; ++s) {
+          const float4 st = pp[s * lt.pp_stride];
           sum.x += st.x;
           sum.y += st.y;
           sum.z += st.z;
@@ -456,6 +528,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_lean_kernel(const 
           Gx.z += gzs;
         }
       }
+      PROF_MARK(4);
     }
     if (own_x) __stcg(prm.g4x + (size_t)b * prm.N + ox, make_float4(Gx.x, Gx.y, Gx.z, 0.f));
     if (own_y) __stcg(prm.g4y + (size_t)b * prm.M + oy, make_float4(Gy.x, Gy.y, Gy.z, 0.f));
@@ -505,16 +578,28 @@ bool lean_plan(int B, int N, int M, LeanGeom* out) {
   return true;
 }
 
+// Automatic choice (measured on B200, profiles/r02a_ot_kernels.md).  The lean skeleton saves ~3 us of bookkeeping per
+// half-step; what it can lose is SMs: Q is an integer, so B = 32, N = 1024 runs on 4 x 32 = 128 of 148 SMs.  It wins
+// wherever a CTA's share of a half-step is small next to that saving (B = 16, N = 1024: 7.2 vs 7.8 ms) or no SM is left
+// idle anyway; at the benchmark shape (8 owner groups x 1024 streamed points per CTA, ~24 us per half-step) the
+// flattened deal's 148 balanced CTAs win (12.96 vs 13.46 ms).
+static bool lean_auto(int B, int N, int M, const LeanGeom& gm) {
+  const int G = sm_count();
+  if (gm.whole_pairs) {  // whole pairs in rounds: worth it unless the last round is mostly empty
+    const int rounds = (B + G - 1) / G;
+    return 10LL * B >= 8LL * rounds * G;
+  }
+  if (100LL * gm.grid >= 98LL * G) return true;
+  const long long per_cta = (long long)(gm.R[0] > gm.R[1] ? gm.R[0] : gm.R[1]) * (N > M ? N : M);  // element-evals per half-step
+  return per_cta <= 160000;
+}
+
 bool lean_selected(int B, int N, int M, int fast, int hist_levels, float thresh) {
   if (g_path_mode == 1) return false;
   if (!is_packed_cost(fast) || hist_levels <= 1 || thresh > 0.f) return false;
   LeanGeom gm;
   if (!lean_plan(B, N, M, &gm)) return false;
-  if (g_path_mode == 2) return true;
-  // automatic: where a CTA of the flattened deal would hold little work per half-step.  (At the benchmark shape,
-  // B = 32, N = 1024, the lean mapping would leave 20 of 148 SMs idle -- Q must be an integer -- and loses.)
-  const long long groups = (long long)B * (((N > M ? N : M) + 31) / 32);
-  return groups <= 4LL * sm_count() || gm.whole_pairs;
+  return g_path_mode == 2 || lean_auto(B, N, M, gm);
 }
 
 template <typename K>
@@ -571,7 +656,18 @@ extern "C" int shwd_sinkhorn_lean_regime(int B, int N, int M) {
   if (shwd::g_path_mode == 1) return 0;
   shwd::LeanGeom gm;
   if (!shwd::lean_plan(B, N, M, &gm)) return 0;
-  if (shwd::g_path_mode == 2) return 1;
-  const long long groups = (long long)B * (((N > M ? N : M) + 31) / 32);
-  return (groups <= 4LL * shwd::sm_count() || gm.whole_pairs) ? 1 : 0;
+  return (shwd::g_path_mode == 2 || shwd::lean_auto(B, N, M, gm)) ? 1 : 0;
 }
+
+#ifdef SHWD_PROFILE
+extern "C" int shwd_prof_read_lean(unsigned long long* out8, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out8, shwd::g_prof_lean, sizeof(unsigned long long) * 8);
+  if (e != cudaSuccess) return SHWD_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[8] = {0};
+    e = cudaMemcpyToSymbol(shwd::g_prof_lean, z, sizeof(z));
+    if (e != cudaSuccess) return SHWD_ERR_CUDA;
+  }
+  return SHWD_OK;
+}
+#endif

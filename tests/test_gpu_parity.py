@@ -174,11 +174,11 @@ LEAN_SHAPES = [
 def test_lean_kernels_match_oracle_and_flat_kernels(shwd, B, N, M, L, eps):
     """The dedicated-CTA kernels for small problems (csrc/sinkhorn_lean.cu) against the float32 oracle (1e-5), and
     against the flattened-deal kernels they replace there (same arithmetic, different summation grouping)."""
-    assert shwd._lib.lib().shwd_sinkhorn_lean_regime(B, N, M) == 1 or B * max(N, M) > 32 * 4 * 148
     torch.manual_seed(B * 31 + N + M)
     x = F.normalize(torch.randn(B, N, 3), dim=-1) * (1 + 0.2 * torch.rand(B, N, 1))
     y = F.normalize(torch.randn(B, M, 3) + 0.3, dim=-1)
     with _path(shwd, "lean"):
+        assert shwd._lib.lib().shwd_sinkhorn_lean_regime(B, N, M) == 1
         cost, gx, gy, _ = _run_cuda(shwd, x, y, "geodesic", 2.0, eps, L)
     with _path(shwd, "flat"):
         cost_f, gx_f, gy_f, _ = _run_cuda(shwd, x, y, "geodesic", 2.0, eps, L)
@@ -190,6 +190,9 @@ def test_lean_kernels_match_oracle_and_flat_kernels(shwd, B, N, M, L, eps):
         x, y, cost, gx, gy = x[keep], y[keep], cost[keep], gx[keep], gy[keep]
     c_ref, gx_ref, gy_ref = _run_oracle(x, y, "geodesic", 2, eps, L)
     ok = torch.isfinite(c_ref) & torch.isfinite(gx_ref).flatten(1).all(1) & torch.isfinite(gy_ref).flatten(1).all(1)
+    if not ok.any():  # float32 reference NaN on every pair kept (a cosine rounded to >= 1): use its float64 run
+        c_ref, gx_ref, gy_ref = _run_oracle(x, y, "geodesic", 2, eps, L, dtype=torch.float64)
+        ok = torch.isfinite(c_ref) & torch.isfinite(gx_ref).flatten(1).all(1) & torch.isfinite(gy_ref).flatten(1).all(1)
     assert ok.any()
     errs = (rel(cost[ok], c_ref[ok]), rel(gx[ok], gx_ref[ok]), rel(gy[ok], gy_ref[ok]))
     print("lean vs oracle: cost %.2e gx %.2e gy %.2e" % errs)
