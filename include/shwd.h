@@ -82,7 +82,8 @@ int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N, int M, int
                       float eps, int iters, const float* alpha_hist, const float* beta_hist, const float* row_pc,
                       const float* col_pc, const int* iters_run, const float* grad_cost, float* g4x, float* g4y,
                       void* workspace, size_t workspace_bytes, void* stream);
-/* status word of the last persistent launch that used `workspace` (0 ok, 1 = an inter-CTA wait timed out). */
+/* status word of the last persistent launch that used `workspace` (0 ok, 1 = an inter-CTA wait timed out).  A failed
+ * launch also overwrites its outputs (cost; g4x, g4y) with NaN on the device, so it can never pass for a result. */
 int shwd_sinkhorn_status_offset(void);
 /* Two kernel families serve shwd_sinkhorn_fwd / _bwd with identical arithmetic and history format: the flattened-deal
  * persistent kernels (any size; the benchmark shape B=32, N=1024) and the dedicated-CTA "lean" kernels for small

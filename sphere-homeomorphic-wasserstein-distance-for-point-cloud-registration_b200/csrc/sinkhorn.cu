@@ -163,6 +163,16 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM) sinkhorn_bwd_kerne
   }
 }
 
+// A persistent launch whose inter-CTA wait timed out sets the workspace's status word and carries on with garbage.  Every
+// launcher ends with this kernel: one word read when all is well, NaN over the launch's outputs otherwise -- decided on
+// the device, so a failed launch can never pass for a result (and the NaN propagates through shwd_sphere_map_bwd).
+__global__ void poison_on_failure_kernel(const int* status, float* a, size_t na, float* b, size_t nb) {
+  if (*status == 0) return;
+  const float nan = __int_as_float(0x7fc00000);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += (size_t)gridDim.x * blockDim.x) a[i] = nan;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += (size_t)gridDim.x * blockDim.x) b[i] = nan;
+}
+
 // Dense plan / cost for the reference's (cost, P, C) return value (opt-in, small problems only).
 template <int FAST>
 __global__ void plan_dense_kernel(const float4* X, const float4* Y, int N, int M, CostParams cp, const float* alpha,
@@ -245,19 +255,25 @@ extern "C" int shwd_sinkhorn_fwd(const float* x4, const float* y4, int B, int N,
     prm.spin_ready = 1;
   }
   LeanGeom gm;
-  if (prm.spin_ready && lean_selected(B, N, M, fast, hist_levels, early_stop_thresh) && lean_plan(B, N, M, &gm))
-    return launch_lean_fwd(fast, prm, gm, s);
   const size_t smem = sinkhorn_smem_bytes();
   const int maxg = B * (((N > M ? N : M) + 31) / 32);
-  switch (fast) {
-    case FAST_GEO2: return launch_persistent(sinkhorn_fwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
-    case FAST_SQE2: return launch_persistent(sinkhorn_fwd_kernel<FAST_SQE2>, prm, smem, maxg, s);
-    case FAST_GEO1: return launch_persistent(sinkhorn_fwd_kernel<FAST_GEO1>, prm, smem, maxg, s);
-    case FAST_SQE1: return launch_persistent(sinkhorn_fwd_kernel<FAST_SQE1>, prm, smem, maxg, s);
-    case FAST_EUC2: return launch_persistent(sinkhorn_fwd_kernel<FAST_EUC2>, prm, smem, maxg, s);
-    case FAST_OMC2: return launch_persistent(sinkhorn_fwd_kernel<FAST_OMC2>, prm, smem, maxg, s);
-    default: return launch_persistent(sinkhorn_fwd_kernel<GENERIC>, prm, smem, maxg, s);
+  if (prm.spin_ready && lean_selected(B, N, M, fast, hist_levels, early_stop_thresh) && lean_plan(B, N, M, &gm)) {
+    rc = launch_lean_fwd(fast, prm, gm, s);
+  } else {
+    switch (fast) {
+      case FAST_GEO2: rc = launch_persistent(sinkhorn_fwd_kernel<FAST_GEO2>, prm, smem, maxg, s); break;
+      case FAST_SQE2: rc = launch_persistent(sinkhorn_fwd_kernel<FAST_SQE2>, prm, smem, maxg, s); break;
+      case FAST_GEO1: rc = launch_persistent(sinkhorn_fwd_kernel<FAST_GEO1>, prm, smem, maxg, s); break;
+      case FAST_SQE1: rc = launch_persistent(sinkhorn_fwd_kernel<FAST_SQE1>, prm, smem, maxg, s); break;
+      case FAST_EUC2: rc = launch_persistent(sinkhorn_fwd_kernel<FAST_EUC2>, prm, smem, maxg, s); break;
+      case FAST_OMC2: rc = launch_persistent(sinkhorn_fwd_kernel<FAST_OMC2>, prm, smem, maxg, s); break;
+      default: rc = launch_persistent(sinkhorn_fwd_kernel<GENERIC>, prm, smem, maxg, s);
+    }
   }
+  if (rc) return rc;
+  poison_on_failure_kernel<<<1, 256, 0, s>>>(w.status, cost, (size_t)B, nullptr, 0);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
 }
 
 extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N, int M, int cost_kind, float p, float n_power,
@@ -314,19 +330,24 @@ extern "C" int shwd_sinkhorn_bwd(const float* x4, const float* y4, int B, int N,
     SHWD_CUDA_CHECK(cudaMemsetAsync(w.abar, 0xFF, sizeof(float) * (size_t)(iters + 1) * B * N, s));
     SHWD_CUDA_CHECK(cudaMemsetAsync(w.bbar, 0xFF, sizeof(float) * (size_t)(iters + 1) * B * M, s));
     prm.spin_ready = 1;
-    return launch_lean_bwd(fast, prm, gm, s);
+    rc = launch_lean_bwd(fast, prm, gm, s);
+  } else {
+    const size_t smem = sinkhorn_smem_bytes();
+    const int maxg = B * (((N > M ? N : M) + 31) / 32);
+    switch (fast) {
+      case FAST_GEO2: rc = launch_persistent(sinkhorn_bwd_kernel<FAST_GEO2>, prm, smem, maxg, s); break;
+      case FAST_SQE2: rc = launch_persistent(sinkhorn_bwd_kernel<FAST_SQE2>, prm, smem, maxg, s); break;
+      case FAST_GEO1: rc = launch_persistent(sinkhorn_bwd_kernel<FAST_GEO1>, prm, smem, maxg, s); break;
+      case FAST_SQE1: rc = launch_persistent(sinkhorn_bwd_kernel<FAST_SQE1>, prm, smem, maxg, s); break;
+      case FAST_EUC2: rc = launch_persistent(sinkhorn_bwd_kernel<FAST_EUC2>, prm, smem, maxg, s); break;
+      case FAST_OMC2: rc = launch_persistent(sinkhorn_bwd_kernel<FAST_OMC2>, prm, smem, maxg, s); break;
+      default: rc = launch_persistent(sinkhorn_bwd_kernel<GENERIC>, prm, smem, maxg, s);
+    }
   }
-  const size_t smem = sinkhorn_smem_bytes();
-  const int maxg = B * (((N > M ? N : M) + 31) / 32);
-  switch (fast) {
-    case FAST_GEO2: return launch_persistent(sinkhorn_bwd_kernel<FAST_GEO2>, prm, smem, maxg, s);
-    case FAST_SQE2: return launch_persistent(sinkhorn_bwd_kernel<FAST_SQE2>, prm, smem, maxg, s);
-    case FAST_GEO1: return launch_persistent(sinkhorn_bwd_kernel<FAST_GEO1>, prm, smem, maxg, s);
-    case FAST_SQE1: return launch_persistent(sinkhorn_bwd_kernel<FAST_SQE1>, prm, smem, maxg, s);
-    case FAST_EUC2: return launch_persistent(sinkhorn_bwd_kernel<FAST_EUC2>, prm, smem, maxg, s);
-    case FAST_OMC2: return launch_persistent(sinkhorn_bwd_kernel<FAST_OMC2>, prm, smem, maxg, s);
-    default: return launch_persistent(sinkhorn_bwd_kernel<GENERIC>, prm, smem, maxg, s);
-  }
+  if (rc) return rc;
+  poison_on_failure_kernel<<<64, 256, 0, s>>>(w.status, g4x, (size_t)B * N * 4, g4y, (size_t)B * M * 4);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
 }
 
 extern "C" int shwd_sinkhorn_plan_dense(const float* x4, const float* y4, int B, int N, int M, int cost_kind, float p,

@@ -47,11 +47,30 @@ def sliced_cost(Xs, Xt, Us, p=2, u_weights=None, v_weights=None):
     return w.reshape(()) if Xs.dim() == 2 else w
 
 
+def stiefel_frames(Z):
+    """The Q factor of ``torch.linalg.qr(Z)`` for a batch of (d,2) matrices, as a dozen elementwise device ops.
+
+    ``sliced_wasserstein_sphere`` (max_spherical_sliced_w.py:307-308) draws ``randn(P,d,2)`` and runs a batched QR inside
+    every loss call; on the GPU that is a cuSOLVER batched factorisation of P tiny matrices -- 15 ms at P = 512, eight
+    times the whole cfg3 loss.  For two columns Q is Gram-Schmidt up to LAPACK's Householder signs
+    (R11 = -sign(a11)|a1|, R22 = -sign((H1 a2)_2)|w|), reproduced here, so the frames equal torch's to rounding."""
+    a1, a2 = Z[..., 0], Z[..., 1]
+    n1 = torch.linalg.vector_norm(a1, dim=-1, keepdim=True)
+    s1 = torch.where(a1[..., :1] >= 0, 1.0, -1.0)
+    q1 = -s1 * a1 / n1
+    w = a2 - (q1 * a2).sum(-1, keepdim=True) * q1
+    beta = -s1 * n1
+    h2 = a2[..., 1:2] - a1[..., 1:2] * ((a1 * a2).sum(-1, keepdim=True) - beta * a2[..., :1]) / (n1 * (n1 + a1[..., :1].abs()))
+    s2 = torch.where(h2 >= 0, 1.0, -1.0)
+    q2 = -s2 * w / torch.linalg.vector_norm(w, dim=-1, keepdim=True)
+    return torch.stack((q1, q2), dim=-1)
+
+
 def sliced_wasserstein_sphere(Xs, Xt, num_projections, device, u_weights=None, v_weights=None, p=2):
     """max_spherical_sliced_w.py:289-310 -- draws ``U = qr(randn(P,d,2)).Q`` on ``device`` and calls sliced_cost."""
     d = Xs.shape[-1]
     Z = torch.randn((num_projections, d, 2), device=device)
-    U, _ = torch.linalg.qr(Z)
+    U = stiefel_frames(Z)
     return sliced_cost(Xs, Xt, U, p=p, u_weights=u_weights, v_weights=v_weights)
 
 

@@ -78,13 +78,6 @@ def flow_regularization(x):
     return reg.sum()
 
 
-def _poison(t, ws):
-    """NaN out ``t`` when the status word at the head of the persistent kernels' workspace is non-zero (include/shwd.h:
-    shwd_sinkhorn_status_offset) -- decided on the device, so a failed launch can never pass for a result."""
-    failed = ws[:4].view(torch.int32) != 0
-    return torch.where(failed.view((1,) * t.dim()), torch.full((), float("nan"), device=t.device, dtype=t.dtype), t)
-
-
 # ---------------------------------------------------------------------------------------------------------------------
 class EntropicOTFn(torch.autograd.Function):
     """cost_b = sum_ij P_ij C_ij after L log-domain Sinkhorn iterations on an on-the-fly cost; reverse mode through all
@@ -120,8 +113,7 @@ class EntropicOTFn(torch.autograd.Function):
             _lib.check(lib.shwd_sinkhorn_fwd(_ptr(x4), _ptr(y4), B, N, M, kind, p, n_power, eps, iters, thresh, HL, _ptr(alpha),
                                              _ptr(beta), _ptr(row_pc), _ptr(col_pc), _ptr(cost), _ptr(iters_run), _ptr(ws), wsb, s),
                        "shwd_sinkhorn_fwd")
-        # a timed-out inter-CTA wait leaves garbage potentials behind: poison the result on the device (no host sync)
-        cost = _poison(cost, ws)
+        # (a launch whose inter-CTA wait timed out NaNs `cost` itself, on the device: csrc/sinkhorn.cu poison_on_failure_kernel)
         ctx.save_for_backward(x, y, x4, y4, alpha, beta, row_pc, col_pc, iters_run)
         ctx.cfg = (kind, p, n_power, eps, iters, flags, keep)
         ctx.mark_non_differentiable(alpha, beta, iters_run, ws)
@@ -151,7 +143,7 @@ class EntropicOTFn(torch.autograd.Function):
                                              wsb, s), "shwd_sinkhorn_bwd")
             _lib.check(lib.shwd_sphere_map_bwd(_ptr(x), _ptr(x4), _ptr(g4x), None, _ptr(gx), B, N, flags, s), "shwd_sphere_map_bwd")
             _lib.check(lib.shwd_sphere_map_bwd(_ptr(y), _ptr(y4), _ptr(g4y), None, _ptr(gy), B, M, flags, s), "shwd_sphere_map_bwd")
-        return _poison(gx, ws), _poison(gy, ws), None, None, None, None, None, None, None, None
+        return gx, gy, None, None, None, None, None, None, None, None  # (NaN on a failed launch, see above)
 
 
 class EntropicOTResult:

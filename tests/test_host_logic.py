@@ -244,3 +244,30 @@ def test_ot_dropin_exports_emd2_and_refuses_cpu_matrices():
         ot.emd2(w, w, torch.rand(4, 4))
     with pytest.raises(NotImplementedError):
         ot.emd2(w, w, torch.rand(4, 5))
+
+
+def test_stiefel_frames_equal_torch_qr():
+    """sliced_wasserstein_sphere draws qr(randn(P,d,2)).Q (max_spherical_sliced_w.py:307-308); the elementwise restatement
+    reproduces LAPACK's Householder signs, so the frames equal torch.linalg.qr's to rounding."""
+    from shwd_b200.losses.sliced import stiefel_frames
+    torch.manual_seed(0)
+    for d in (3, 4):
+        Z = torch.randn(2000, d, 2)
+        Q, _ = torch.linalg.qr(Z)
+        U = stiefel_frames(Z)
+        assert (U - Q).abs().max().item() < 2e-5
+        assert (U.transpose(1, 2) @ U - torch.eye(2)).abs().max().item() < 2e-5
+
+
+def test_bench_reference_arm_and_meta_describe_the_same_workload():
+    """The driver compares the two arms' `config`: both must come from workload_meta, for every --config."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for cfg in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5"):
+        m = bench.workload_meta(cfg, "weak", 1)
+        assert set(m) == {"metric", "unit", "config"} and "workload" in m["config"]
+        assert cfg in bench.CPU_SAMPLE
+    assert bench.workload_meta("cfg2", "strong", 8)["config"]["global_batch"] == 32
+    assert bench.workload_meta("cfg2", "weak", 8)["config"]["global_batch"] == 256
