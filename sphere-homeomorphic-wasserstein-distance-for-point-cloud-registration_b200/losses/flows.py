@@ -16,7 +16,12 @@ from torch import nn
 
 
 class PlanarFlow(nn.Module):
-    """f(z) = z + u^ tanh(<w, z> + b), u^ = u + (softplus(<w,u>) - 1 - <w,u>) w / |w|^2  (flows/planar.py:49-60)."""
+    """f(z) = z + u^ tanh(lin + b), u^ = u + (softplus(<w,u>) - 1 - <w,u>) w / |w|^2  (flows/planar.py:49-60).
+
+    ``lin`` is the reference's expression verbatim in behaviour: ``sum(w * z, dims 1 .. w.dim()-1, keepdim=True)`` with
+    ``w`` of shape (1, dim) -- i.e. a sum over dim 1 of the input.  For (N, dim) inputs that is <w, z_n>; for the batched
+    (B, N, dim) clouds the loss wrappers feed it (s2_wasserstein.py:243-246) it sums over the N points per coordinate.
+    That is what the reference computes, so it is what is computed here."""
 
     def __init__(self, dim=3):
         super().__init__()
@@ -26,7 +31,7 @@ class PlanarFlow(nn.Module):
         self.b = nn.Parameter(torch.zeros(1))
 
     def forward(self, z):
-        lin = torch.sum(self.w * z, dim=-1, keepdim=True) + self.b
+        lin = torch.sum(self.w * z, list(range(1, self.w.dim())), keepdim=True) + self.b
         inner = torch.sum(self.w * self.u)
         u = self.u + (torch.log(1 + torch.exp(inner)) - 1 - inner) * self.w / torch.sum(self.w ** 2)
         return z + u * torch.tanh(lin)
@@ -46,7 +51,8 @@ class Swish(nn.Module):
 class SpectralLinear(nn.Module):
     """Linear layer softly normalised to spectral norm <= coeff: W / max(1, (u^T W v)/coeff) with u, v frozen after 200
     power iterations at construction (InducedNormLinear with domain = codomain = 2, nets/lipschitz.py:132-274;
-    the reference never calls update_lipschitz, so u and v stay fixed)."""
+    the reference never calls update_lipschitz, so u and v stay fixed).  Parameters and buffers carry the reference's
+    names (weight, bias; scale, u, v), so a reference checkpoint's entries load unchanged."""
 
     def __init__(self, in_features, out_features, coeff=0.95, zero_init=False):
         super().__init__()
@@ -64,29 +70,68 @@ class SpectralLinear(nn.Module):
             for _ in range(200):
                 u = F.normalize(torch.mv(self.weight, v), dim=0)
                 v = F.normalize(torch.mv(self.weight.t(), u), dim=0)
+            sigma = torch.dot(u, torch.mv(self.weight, v))
+        self.register_buffer("scale", sigma.detach().clone())  # the last u^T W v seen (nets/lipschitz.py:266-268)
         self.register_buffer("u", u)
         self.register_buffer("v", v)
 
     def forward(self, x):
         sigma = torch.dot(self.u, torch.mv(self.weight, self.v))
+        with torch.no_grad():
+            self.scale.copy_(sigma)
         factor = torch.clamp(sigma / self.coeff, min=1.0)
         return F.linear(x, self.weight / factor, self.bias)
 
 
+class LipschitzMLP(nn.Module):
+    """[Swish, SpectralLinear] per layer, last layer initialised near zero (nets/lipschitz.py:14-68)."""
+
+    def __init__(self, channels, lipschitz_const=0.95):
+        super().__init__()
+        layers = []
+        for i in range(len(channels) - 1):
+            layers += [Swish(), SpectralLinear(channels[i], channels[i + 1], lipschitz_const, zero_init=(i == len(channels) - 2))]
+        self.net = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class _IResBlock(nn.Module):
+    """Container with the reference's iResBlock state (flows/residual.py:82-124): the Lipschitz net under ``nnet`` plus
+    the parameters / buffers of the log-determinant estimator.  The loss path discards the log-determinant
+    (``x, _ = flow(x)``, s2_wasserstein.py:160-163), so ``geom_p``, ``lamb`` and the moment buffers are carried only to
+    keep ``state_dict()`` / ``parameters()`` identical in names, shapes and order to the reference's -- what
+    train_W_COS.py:204-205,260-263 saves and restores for phi and its optimiser."""
+
+    def __init__(self, nnet, geom_p=0.5, lamb=2.0, n_samples=1):
+        super().__init__()
+        self.nnet = nnet
+        self.geom_p = nn.Parameter(torch.tensor(math.log(geom_p) - math.log(1.0 - geom_p), dtype=torch.float64))
+        self.lamb = nn.Parameter(torch.tensor(lamb))
+        self.register_buffer("last_n_samples", torch.zeros(n_samples))
+        self.register_buffer("last_firmom", torch.zeros(1))
+        self.register_buffer("last_secmom", torch.zeros(1))
+
+    def forward(self, x):
+        return x + self.nnet(x)
+
+
 class ResidualFlow(nn.Module):
-    """x + LipschitzMLP(x): [Swish, SpectralLinear] per layer, last layer initialised near zero (nets/lipschitz.py:47-63)."""
+    """x + LipschitzMLP(x) (flows/residual.py:12-68 with reverse=False); module tree as in the reference:
+    ``iresblock.nnet.net.{2i}`` = Swish, ``.{2i+1}`` = the spectrally normalised linear layer."""
 
     def __init__(self, dim=3, hidden_units=8, hidden_layers=7, lipschitz_const=0.95):
         super().__init__()
         channels = [dim] + [hidden_units] * (hidden_layers - 1) + [dim]
-        layers = []
-        for i in range(len(channels) - 1):
-            layers += [Swish(), SpectralLinear(channels[i], channels[i + 1], lipschitz_const,
-                                               zero_init=(i == len(channels) - 2))]
-        self.net = nn.Sequential(*layers)
+        self.iresblock = _IResBlock(LipschitzMLP(channels, lipschitz_const))
+
+    @property
+    def net(self):
+        return self.iresblock.nnet.net
 
     def forward(self, x):
-        return x + self.net(x)
+        return self.iresblock(x)
 
 
 def _raw_params(flow):

@@ -1,11 +1,11 @@
 """Drop-in for ``Point_Cloud_Resistration/losses/s2_wasserstein.py`` on the B200 path.
 
 ``Cos_disimilarity_W`` (:13-66) and ``Geodesic_distance_W`` (:73-126) keep their constructor and call signatures.
-The reference solves each pair with POT's exact CPU network simplex (``ot.emd2``, :41-43); here the same cost matrix is
-solved by on-the-fly log-domain Sinkhorn iterations in CUDA (BASELINE.json north_star), with the recurrence of
-``losses/Sinkhorn.py:35-50``: ``eps`` / ``max_iter`` are extra keyword arguments (defaults 0.01 / 100, the values the
-reference uses for its Sinkhorn runs, main_rotation.py:123-124).  The result is ``mean_b cost_b ** (1/p)`` exactly as
-:41-44 reduces it.  The wrappers (:211-344) are host-side orchestration and are restated unchanged in behaviour.
+The reference solves each pair with POT's exact CPU network simplex (``ot.emd2``, :41-43).  Called the reference's way
+(``Cos_disimilarity_W(device, p)``) the drop-in solves the same LP exactly on the GPU (auction kernel); given ``eps`` /
+``max_iter`` (or ``solver="sinkhorn"``) the same cost matrix is solved by on-the-fly log-domain Sinkhorn iterations
+(BASELINE.json north_star; recurrence of ``losses/Sinkhorn.py:35-50``; 0.01 / 100 are the values the reference uses for
+its Sinkhorn runs, main_rotation.py:123-124).  The result is ``mean_b cost_b ** (1/p)`` exactly as :41-44 reduces it.  The wrappers (:211-344) are host-side orchestration and are restated unchanged in behaviour.
 """
 import torch
 import torch.nn as nn
@@ -15,21 +15,47 @@ from .. import ops
 from .flows import PlanarFlow, ResidualFlow, fused_residual_stack, is_standard_residual_stack, _uv_buffer
 
 
+_warned_fallback = [False]
+
+
 class _EntropicW(nn.Module):
-    """``solver="sinkhorn"`` (default; BASELINE.json north_star): on-the-fly entropic iterations.  ``solver="exact"``: the
-    exact LP optimum the reference itself computes with ``ot.emd2`` (:41-43), by the GPU auction kernel (equally sized
-    clouds); value and gradient are then the reference's up to float32 rounding."""
+    """The per-pair solve of ``calcurate_cos_W`` / ``calcurate_geodesic_W`` (:25-50, :85-110).
+
+    ``solver="exact"``: the LP optimum the reference computes with ``ot.emd2`` (:41-43), by the GPU auction kernel; value
+    and gradient are the reference's up to float32 rounding.  ``solver="sinkhorn"``: on-the-fly entropic iterations
+    (BASELINE.json north_star; the recurrence of losses/Sinkhorn.py:35-50 with ``eps`` / ``max_iter``).
+    Default (``solver=None``): what the reference call means -- ``Cos_disimilarity_W(device, p)`` with nothing else is
+    the exact solve whenever the auction kernel takes the shape (equally sized clouds up to
+    ``shwd_exact_assignment_max_points()``), so train_W_COS.py:393 run through the drop-in optimises the reference's
+    loss, not an entropic surrogate; passing ``eps`` or ``max_iter`` asks for the entropic solver.  Shapes the exact
+    kernel does not take fall back to the entropic solver with a one-time warning."""
     _kind = None
 
-    def __init__(self, device, p=1, eps=0.01, max_iter=100, solver="sinkhorn"):
+    def __init__(self, device, p=1, eps=None, max_iter=None, solver=None):
         super().__init__()
-        if solver not in ("sinkhorn", "exact"):
+        if solver not in (None, "sinkhorn", "exact"):
             raise ValueError("solver must be 'sinkhorn' or 'exact'")
+        if solver is None:
+            solver = "sinkhorn" if (eps is not None or max_iter is not None) else "auto"
         self.device = device
         self.p = p
-        self.eps = eps
-        self.max_iter = max_iter
+        self.eps = 0.01 if eps is None else eps            # main_rotation.py:123-124
+        self.max_iter = 100 if max_iter is None else max_iter
         self.solver = solver
+
+    def _use_exact(self, x, y):
+        if self.solver != "auto":
+            return self.solver == "exact"
+        from .. import _lib
+        ok = x.shape[-2] == y.shape[-2] and x.shape[-2] <= _lib.lib().shwd_exact_assignment_max_points()
+        if not ok and not _warned_fallback[0]:
+            import warnings
+            _warned_fallback[0] = True
+            warnings.warn("%s: clouds of %d and %d points are outside the exact assignment kernel (equal sizes up to %d); "
+                          "using the entropic solver (eps=%g, %d iterations) instead of the reference's ot.emd2"
+                          % (type(self).__name__, x.shape[-2], y.shape[-2], _lib.lib().shwd_exact_assignment_max_points(),
+                             self.eps, self.max_iter))
+        return ok
 
     def _w(self, x, y, device, p=1):
         x = x.to(device)
@@ -40,7 +66,7 @@ class _EntropicW(nn.Module):
             batch_size = x.shape[0]
         if batch_size < 1:
             raise ValueError("batch_size is not valid")
-        if self.solver == "exact":
+        if self._use_exact(x, y):
             cost = ops.exact_emd2(x, y, self._kind, float(p))
         else:
             cost = ops.entropic_ot(x, y, self._kind, float(p), float(self.eps), int(self.max_iter)).cost
@@ -85,6 +111,17 @@ class Norm_Flow_structure(nn.Module):
     def __init__(self, input_dim=3, flow_name="Planar", n_flow_layer=3):
         super().__init__()
         self.net = nn.ModuleList(self.create__NF_structure(flow_name, input_dim, n_flow_layer))
+        # ``state_dict()`` keys, shapes and parameter order equal the reference's (net.i.iresblock.nnet.net.j.*, geom_p,
+        # lamb, ...), so the phi / phi_op entries of a reference ``.t7`` snapshot load unchanged (train_W_COS.py:252-276)
+        self._uv_cache = None
+        self.register_load_state_dict_pre_hook(self._drop_uv_cache)
+
+    def _drop_uv_cache(self, *args, **kwargs):
+        self._uv_cache = None  # the frozen power-iteration vectors are about to be overwritten
+
+    def _apply(self, fn, *args, **kwargs):
+        self._uv_cache = None  # .to() / .cuda() / .float() replace the buffers
+        return super()._apply(fn, *args, **kwargs)
 
     def create__NF_structure(self, flow_name, input_dim, n_flow_layer):
         if flow_name == "Planar":
@@ -97,7 +134,7 @@ class Norm_Flow_structure(nn.Module):
 
     def forward(self, x):
         if x.is_cuda and x.shape[-1] == 3 and is_standard_residual_stack(self.net):
-            uv = getattr(self, "_uv_cache", None)
+            uv = self._uv_cache
             if uv is None or uv.device != x.device:
                 uv = self._uv_cache = _uv_buffer(self.net).to(x.device)
             return fused_residual_stack(self.net, x, uv)  # one kernel per direction (csrc/resflow.cu)

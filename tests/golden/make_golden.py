@@ -192,6 +192,109 @@ def main():
     w2 = ssw.binary_search_circle(u.detach(), v.detach(), p=2)
     np.savez(os.path.join(HERE, "binary_search_circle_p2.npz"), u=u.detach().numpy(), v=v.detach().numpy(), w=w2.numpy())
 
+    make_wrapper_fixtures(ref_losses)
+    make_notebook_fixture()
+
+
+def _flat_state(prefix, sd):
+    return {prefix + k.replace(".", "__"): v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def make_wrapper_fixtures(ref_losses):
+    """Rows a14 / f1: the learned sphere map and the max-over-phi wrapper, from the UNMODIFIED
+    reference modules (vendored normflows 1.7.2 + s2_wasserstein.py:134-163, 211-262), with every weight saved so the
+    fixtures replay through ``load_state_dict`` -- the state_dict keys are the reference's own."""
+    # ---- 7. Norm_Flow_structure forward + gradients (Residual x3 as train_W_COS.py:390 builds it; Planar x3) -----
+    for name in ("Residual", "Planar"):
+        torch.manual_seed(101 if name == "Residual" else 202)
+        np.random.seed(5)
+        phi = ref_losses.Norm_Flow_structure(flow_name=name, n_flow_layer=3)
+        with torch.no_grad():  # move the weights off their init so every term of the chain rule is exercised
+            for prm in phi.parameters():
+                if prm.dim() > 0 and prm.dtype == torch.float32:
+                    prm.add_(0.3 * torch.randn_like(prm))
+        phi.train()
+        sd0 = {k: v.clone() for k, v in phi.state_dict().items()}
+        g = torch.Generator().manual_seed(7)
+        out = {}
+        for tag, shape in (("b", (3, 64, 3)), ("u", (50, 3))):  # batched clouds and the un-batched (N,3) branch
+            x = (torch.randn(*shape, generator=g) * 0.8).requires_grad_(True)
+            w = torch.randn(*shape, generator=g)
+            y = phi(x)
+            params = [q for q in phi.parameters() if q.dtype == torch.float32 and q.dim() > 0]
+            names = [n for n, q in phi.named_parameters() if q.dtype == torch.float32 and q.dim() > 0]
+            gs = torch.autograd.grad((y * w).sum(), [x] + params, allow_unused=True)
+            out.update({f"x_{tag}": x.detach().numpy(), f"w_{tag}": w.numpy(), f"y_{tag}": y.detach().numpy(),
+                        f"gx_{tag}": gs[0].numpy()})
+            for n, gq, q in zip(names, gs[1:], params):
+                out[f"gp_{tag}__" + n.replace(".", "__")] = (torch.zeros_like(q) if gq is None else gq).numpy()
+        out.update(_flat_state("sd__", sd0))
+        np.savez(os.path.join(HERE, f"flow_{name.lower()}.npz"), **out)
+        print("flow", name, "|y|", float(np.linalg.norm(out["y_b"])), "|gx|", float(np.linalg.norm(out["gx_b"])))
+
+    # ---- 8. one training step of max_cos_disimilarity_wassersten_distance (s2_wasserstein.py:234-262) -------------
+    # phi ascent (max_iter=2, SGD so the update is a plain function of the gradient) on detached inputs, then the outer
+    # distance; CSW = Cos_disimilarity_W(p=2) as train_W_COS.py:393 (exact EMD through the scipy-backed ``ot`` shim)
+    for name, layers in (("Residual", 2), ("Planar", 3)):
+        torch.manual_seed(303 if name == "Residual" else 404)
+        np.random.seed(6)
+        phi = ref_losses.Norm_Flow_structure(flow_name=name, n_flow_layer=layers)
+        phi_op = torch.optim.SGD([q for q in phi.parameters()], lr=0.05)
+        csw = ref_losses.Cos_disimilarity_W(device="cpu", p=2)
+        crit = ref_losses.max_cos_disimilarity_wassersten_distance(phi=phi, CSW=csw, device="cpu", phi_op=phi_op, max_iter=2, lam=0.1)
+        sd0 = {k: v.clone() for k, v in phi.state_dict().items()}
+        g = torch.Generator().manual_seed(8)
+        first = torch.randn(2, 48, 3, generator=g)
+        first = first - first.mean(1, keepdim=True)
+        second = (first[:, torch.randperm(48, generator=g)] * 0.9 + 0.05 * torch.randn(2, 48, 3, generator=g)).requires_grad_(True)
+        cswd, first_t, second_t = crit(first, second, "train")
+        (g_second,) = torch.autograd.grad(cswd, second)
+        sd1 = phi.state_dict()
+        cswd_test, ft_test, st_test = crit(first, second.detach(), "test")
+        out = dict(first=first.detach().numpy(), second=second.detach().numpy(), cswd=np.float64(cswd.item()), first_t=first_t.detach().numpy(),
+                   second_t=second_t.detach().numpy(), g_second=g_second.numpy(), cswd_test=np.float64(cswd_test.item()),
+                   lr=np.float64(0.05), lam=np.float64(0.1), max_iter=np.int64(2), n_flow_layer=np.int64(layers))
+        out.update(_flat_state("sd0__", sd0))
+        out.update(_flat_state("sd1__", sd1))
+        np.savez(os.path.join(HERE, f"max_wrapper_{name.lower()}.npz"), **out)
+        print("max wrapper", name, "cswd", cswd.item(), "test", cswd_test.item())
+
+
+def make_notebook_fixture():
+    """Row a11: the Euclidean sliced Wasserstein distance of the flow notebooks, by executing the SOURCE of cell 5 of
+    Wasserstein_flow_problem/Flow_ellipsoid.ipynb (``rand_projections`` / ``sliced_wasserstein_distance``, raw JSON lines
+    203-220) unmodified; only the random directions are pinned by seeding torch right before the call."""
+    import json
+    with open(os.path.join(REF, "Wasserstein_flow_problem/Flow_ellipsoid.ipynb")) as fh:
+        nb = json.load(fh)
+    src = "".join(nb["cells"][5]["source"])
+    assert "def sliced_wasserstein_distance" in src
+    ns = {"torch": torch, "np": np, "optim": torch.optim, "nn": torch.nn}
+    exec(compile(src, "Flow_ellipsoid.ipynb#cell5", "exec"), ns)
+    g = torch.Generator().manual_seed(55)
+    out = {}
+    for p in (1, 2, 3):
+        P = 40
+        ns["num_projections"] = P  # the cell reads this global inside rand_projections(dim, num_projections) (:214)
+        x = (torch.randn(300, 3, generator=g) * torch.tensor([2.0, 1.0, 1.0])).requires_grad_(True)
+        y = (torch.randn(300, 3, generator=g) + 0.3).requires_grad_(True)
+        torch.manual_seed(1000 + p)
+        theta = ns["rand_projections"](3, P)        # the directions the call below will draw (same seed)
+        torch.manual_seed(1000 + p)
+        loss = ns["sliced_wasserstein_distance"](x, y, num_projection=P, p=p, device="cpu")
+        gx, gy = torch.autograd.grad(loss, (x, y))
+        out.update({f"x_p{p}": x.detach().numpy(), f"y_p{p}": y.detach().numpy(), f"theta_p{p}": theta.numpy(),
+                    f"loss_p{p}": np.float64(loss.item()), f"gx_p{p}": gx.numpy(), f"gy_p{p}": gy.numpy()})
+        print("notebook SWD p=%d" % p, loss.item())
+    np.savez(os.path.join(HERE, "notebook_sliced_wasserstein.npz"), **out)
+
 
 if __name__ == "__main__":
-    main()
+    if "--wrappers-only" in sys.argv:  # regenerate only the fixtures added in round 2 (the older ones are unchanged)
+        _install_shims()
+        torch.set_num_threads(8)
+        import losses as _ref_losses
+        make_wrapper_fixtures(_ref_losses)
+        make_notebook_fixture()
+    else:
+        main()

@@ -534,6 +534,57 @@ def test_spherical_sliced_w1_matches_oracle(shwd, n, m, P):
     assert out.item() == pytest.approx(ref.item(), rel=2e-5)
 
 
+SLICED_FULL = [
+    # n, m, P        merged-entry bucket of circular_w1 (C per thread) / circular_wp CTA size
+    (4096, 4096, 8),     # cfg3: C = 16, gradient rows staged and permuted in shared memory; 256-thread circular_wp
+    (5000, 5000, 4),     # C = 20
+    (7000, 8000, 3),     # C = 32 (register-light variant: F recomputed), 1024-thread circular_wp (> 14336 merged entries)
+    (16384, 16384, 2),   # cfg4: C = 64, direct scatter; compact sort layout
+    (300, 1500, 5),      # ragged, C = 4
+]
+
+
+@pytest.mark.parametrize("n,m,P", SLICED_FULL)
+@pytest.mark.parametrize("mode", ["circle_w1", "circle_wp", "line"])
+def test_fused_sliced_loss_gradients_match_oracle_at_full_sizes(shwd, mode, n, m, P):
+    """The path users call -- sliced_cost / sliced_wasserstein_distance -> ops.SlicedLossFn -> shwd_*_scatter (gradients
+    written through the int32 permutations) -- value AND both cloud gradients against the reference's autograd
+    (oracle.sliced_wasserstein_sphere / euclid_sliced_wasserstein, max_spherical_sliced_w.py:251-286,
+    Flow_ellipsoid.ipynb cell 5) at BASELINE cfg3 / cfg4 sizes and in every register bucket.  The reference's own
+    float32-vs-float64 distance (`floor`) is printed beside the achieved error; bound max(1e-5, 8 x floor)."""
+    if mode == "line" and n != m:
+        pytest.skip("the notebook's Euclidean sliced W needs equally sized clouds")
+    g = torch.Generator().manual_seed(n + 3 * m + P)
+    Xs = F.normalize(torch.randn(n, 3, generator=g), dim=-1) * (1 + 0.1 * torch.rand(n, 1, generator=g))
+    Xt = F.normalize(torch.randn(m, 3, generator=g) + torch.tensor([0.4, 0.0, 0.1]), dim=-1)
+    if mode == "line":
+        fr = F.normalize(torch.randn(P, 3, generator=g), dim=-1)
+        ofn = lambda a, b: oracle.euclid_sliced_wasserstein(a, b, fr.to(a.dtype), 2)
+        cfn = lambda a, b: shwd.losses.sliced_wasserstein_distance(a, b, p=2, device=dev(), projections=fr.to(dev()))
+    else:
+        fr, _ = torch.linalg.qr(torch.randn(P, 3, 2, generator=g))
+        p = 1 if mode == "circle_w1" else 2
+        ofn = lambda a, b: (oracle.sliced_wasserstein_sphere_p1(a, b, fr.to(a.dtype)) if p == 1
+                            else oracle.sliced_wasserstein_sphere(a, b, fr.to(a.dtype), p=2))
+        cfn = lambda a, b: shwd.losses.sliced_cost(a, b, fr.to(dev()), p=p)
+    outs = {}
+    for dt in (torch.float32, torch.float64):
+        a, b = Xs.to(dt).requires_grad_(True), Xt.to(dt).requires_grad_(True)
+        v = ofn(a, b)
+        v.backward()
+        outs[dt] = (v.detach(), a.grad, b.grad)
+    a, b = Xs.to(dev()).requires_grad_(True), Xt.to(dev()).requires_grad_(True)
+    v = cfn(a, b)
+    v.backward()
+    floor = [rel(x32, x64) for x32, x64 in zip(outs[torch.float32], outs[torch.float64])]
+    err = [rel(x, x32) for x, x32 in zip((v, a.grad, b.grad), outs[torch.float32])]
+    err64 = [rel(x, x64) for x, x64 in zip((v, a.grad, b.grad), outs[torch.float64])]
+    print("%s n=%d m=%d: value %.2e / gx %.2e / gy %.2e vs float32 reference (its own floor %.2e / %.2e / %.2e); vs float64 %.2e / %.2e / %.2e"
+          % ((mode, n, m) + tuple(err) + tuple(floor) + tuple(err64)))
+    for e, e64, f in zip(err, err64, floor):
+        assert min(e, e64) < max(TOL, 8 * f)
+
+
 def _tie_free(S, n, seed, lo=0.0, width=1.0):
     """Distinct float32 circle coordinates per row (torch.sort without stable=True orders ties arbitrarily): a
     shuffled jittered grid, so distinctness does not rely on luck at n = 4096."""
@@ -792,15 +843,17 @@ def test_fused_residual_flow_matches_eager_modules(shwd, n_flow_layer, shape):
     the same object (plain PyTorch fp32 reference of the same op) -- output, d/dx and d/d(every parameter)."""
     torch.manual_seed(n_flow_layer)
     phi = shwd.losses.Norm_Flow_structure(flow_name="Residual", n_flow_layer=n_flow_layer).to(dev())
+    # (geom_p / lamb belong to the discarded log-determinant estimator: they mirror the reference's state and get no gradient)
+    live = [(n, q) for n, q in phi.named_parameters() if not n.endswith(("geom_p", "lamb"))]
     with torch.no_grad():  # move the near-zero last layers and the Swish scales off their initial values
-        for prm in phi.parameters():
+        for _, prm in live:
             prm.add_(0.05 * torch.randn_like(prm))
     x = (torch.randn(*shape) * 0.8).to(dev())
     w = torch.randn(*shape).to(dev())
     xe = x.clone().requires_grad_(True)
     ye = phi.forward_eager(xe)
     (ye * w).sum().backward()
-    ge = [prm.grad.clone() for prm in phi.parameters()]
+    ge = [prm.grad.clone() for _, prm in live]
     gxe = xe.grad.clone()
     phi.zero_grad()
     xf = x.clone().requires_grad_(True)
@@ -808,15 +861,100 @@ def test_fused_residual_flow_matches_eager_modules(shwd, n_flow_layer, shape):
     (yf * w).sum().backward()
     assert yf.shape == ye.shape and rel(yf, ye) < TOL
     assert rel(xf.grad, gxe) < TOL
-    for (name, prm), g in zip(phi.named_parameters(), ge):
+    for (name, prm), g in zip(live, ge):
         assert prm.grad is not None, name
         assert (prm.grad - g).norm().item() <= TOL * max(g.norm().item(), 1e-3), (name, prm.grad.norm().item(), g.norm().item())
     # bit-reproducible parameter gradients (fixed-order reduction, no float atomics)
-    g1 = [prm.grad.clone() for prm in phi.parameters()]
+    g1 = [prm.grad.clone() for _, prm in live]
     phi.zero_grad()
     xf2 = x.clone().requires_grad_(True)
     (phi(xf2) * w).sum().backward()
-    assert all(torch.equal(a, prm.grad) for a, prm in zip(g1, phi.parameters()))
+    assert all(torch.equal(a, prm.grad) for a, (_, prm) in zip(g1, live))
+
+
+def _state(d, prefix):
+    return {k[len(prefix):].replace("__", "."): torch.from_numpy(v) for k, v in d.items() if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("name", ["Residual", "Planar"])
+def test_phi_matches_vendored_normflows_fixture(shwd, name):
+    """Norm_Flow_structure on the GPU (Residual: the fused resflow kernels; Planar: eager) loaded with the REFERENCE's
+    state_dict -- same keys, shapes and order as train_W_COS.py:204 saves -- against outputs and autograd gradients frozen
+    from the vendored normflows 1.7.2 (tests/golden/make_golden.py section 7): batched clouds and the (N,3) branch."""
+    d = gold("flow_" + name.lower())
+    phi = shwd.losses.Norm_Flow_structure(flow_name=name, n_flow_layer=3)
+    res = phi.load_state_dict(_state(d, "sd__"), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    phi = phi.to(dev()).train()
+    for tag in ("b", "u"):
+        x = torch.from_numpy(d["x_" + tag]).to(dev()).requires_grad_(True)
+        y = phi(x)
+        named = [(n, q) for n, q in phi.named_parameters() if q.dtype == torch.float32 and q.dim() > 0]
+        gs = torch.autograd.grad((y * torch.from_numpy(d["w_" + tag]).to(dev())).sum(), [x] + [q for _, q in named], allow_unused=True)
+        ey, egx = rel(y, torch.from_numpy(d["y_" + tag])), rel(gs[0], torch.from_numpy(d["gx_" + tag]))
+        worst = 0.0
+        for (n, q), g in zip(named, gs[1:]):
+            want = torch.from_numpy(d["gp_%s__%s" % (tag, n.replace(".", "__"))])
+            got = torch.zeros_like(want) if g is None else g.cpu()
+            worst = max(worst, (got - want).norm().item() / max(want.norm().item(), 1e-3))
+        print("phi %s (%s): y %.2e  d/dx %.2e  worst d/dparam %.2e" % (name, tag, ey, egx, worst))
+        assert ey < TOL and egx < TOL and worst < 2e-5
+    # a buffer copy after a forward must not leave the fused kernel on stale power-iteration vectors
+    if name == "Residual":
+        sd = _state(d, "sd__")
+        key = "net.0.iresblock.nnet.net.1.u"
+        sd[key] = -sd[key]  # u -> -u flips the sign of u^T W v: the normalisation factor becomes max(1, negative) = 1
+        phi.load_state_dict(sd)
+        x = torch.from_numpy(d["x_b"]).to(dev())
+        assert rel(phi(x), phi.forward_eager(x)) < TOL
+
+
+def test_euclid_sliced_w_matches_notebook_fixture(shwd):
+    """The notebooks' `sliced_wasserstein_distance`, frozen by executing cell 5 of Flow_ellipsoid.ipynb from its own source."""
+    d = gold("notebook_sliced_wasserstein")
+    for p in (1, 2, 3):
+        x = torch.from_numpy(d["x_p%d" % p]).to(dev()).requires_grad_(True)
+        y = torch.from_numpy(d["y_p%d" % p]).to(dev()).requires_grad_(True)
+        out = shwd.losses.sliced_wasserstein_distance(x, y, num_projection=40, p=p, device=dev(),
+                                                      projections=torch.from_numpy(d["theta_p%d" % p]).to(dev()))
+        out.backward()
+        e = (abs(out.item() - float(d["loss_p%d" % p])) / float(d["loss_p%d" % p]), rel(x.grad, torch.from_numpy(d["gx_p%d" % p])),
+             rel(y.grad, torch.from_numpy(d["gy_p%d" % p])))
+        print("notebook SWD p=%d: loss %.2e gx %.2e gy %.2e" % ((p,) + e))
+        assert e[0] < TOL and e[1] < 2e-5 and e[2] < 2e-5
+
+
+@pytest.mark.parametrize("name", ["Residual", "Planar"])
+def test_max_wrapper_step_matches_reference_fixture(shwd, name):
+    """One training call of max_cos_disimilarity_wassersten_distance exactly as train_W_COS.py:404 builds it -- phi,
+    Cos_disimilarity_W(device, p=2) with NO other argument (-> the exact solve the reference runs through ot.emd2), an
+    optimiser on phi -- against the frozen run of the unmodified reference wrapper (two SGD ascent steps, then the outer
+    distance): value, both transformed clouds, the gradient reaching the second cloud, phi after the ascent, and the
+    'test' branch."""
+    d = gold("max_wrapper_" + name.lower())
+    L = shwd.losses
+    phi = L.Norm_Flow_structure(flow_name=name, n_flow_layer=int(d["n_flow_layer"]))
+    phi.load_state_dict(_state(d, "sd0__"))
+    phi = phi.to(dev())
+    op = torch.optim.SGD(list(phi.parameters()), lr=float(d["lr"]))
+    csw = L.Cos_disimilarity_W(dev(), p=2)
+    assert csw.solver == "auto"
+    crit = L.max_cos_disimilarity_wassersten_distance(phi=phi, CSW=csw, device=dev(), phi_op=op, max_iter=int(d["max_iter"]),
+                                                       lam=float(d["lam"]))
+    second = torch.from_numpy(d["second"]).to(dev()).requires_grad_(True)
+    first = torch.from_numpy(d["first"]).to(dev())
+    cswd, ft, st = crit(first, second, "train")
+    (g2,) = torch.autograd.grad(cswd, second)
+    e = (abs(cswd.item() - float(d["cswd"])) / float(d["cswd"]), rel(ft, torch.from_numpy(d["first_t"])),
+         rel(st, torch.from_numpy(d["second_t"])), rel(g2, torch.from_numpy(d["g_second"])))
+    print("max wrapper %s: cswd %.2e first_t %.2e second_t %.2e d/dsecond %.2e" % ((name,) + e))
+    assert e[0] < TOL and e[1] < TOL and e[2] < TOL and e[3] < 5e-5
+    for k, v in _state(d, "sd1__").items():
+        if v.dtype == torch.float32 and v.dim() > 0 and "last_" not in k and not k.endswith("scale"):
+            got = phi.state_dict()[k].cpu()
+            assert torch.allclose(got, v, rtol=2e-4, atol=2e-6), (k, (got - v).abs().max().item())
+    ctest, _, _ = crit(first, second.detach(), "test")
+    assert ctest.item() == pytest.approx(float(d["cswd_test"]), rel=TOL)
 
 
 def test_max_wrapper_with_fused_phi_runs_the_reference_step(shwd):

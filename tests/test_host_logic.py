@@ -79,8 +79,11 @@ def test_flows_forward_and_parameter_counts():
     torch.manual_seed(0)
     x = torch.randn(2, 16, 3)
     res = L.Norm_Flow_structure(flow_name="Residual", n_flow_layer=3)
-    # 1284 parameters for Residual x3 in the reference = 1278 network parameters + 2 (geom_p, lamb) per block
-    assert sum(p.numel() for p in res.parameters()) == 1278
+    # 1284 parameters for Residual x3 in the reference = 1278 network parameters + 2 (geom_p, lamb) per block;
+    # the module tree mirrors the reference's, so parameters() / state_dict() have its names, shapes and order
+    assert sum(p.numel() for p in res.parameters()) == 1284
+    assert [n for n, _ in res.named_parameters()][:4] == ["net.0.iresblock.geom_p", "net.0.iresblock.lamb",
+                                                          "net.0.iresblock.nnet.net.0.beta", "net.0.iresblock.nnet.net.1.weight"]
     y = res(x)
     assert y.shape == x.shape and torch.isfinite(y).all()
     # Lipschitz < 1 residual branch: the map is a contraction-perturbed identity
@@ -196,7 +199,8 @@ def test_fused_phi_parameter_layout_matches_the_c_abi():
     for f in phi.net:
         raw += flows._raw_params(f)
     assert sum(p.numel() for p in raw) == 3 * per
-    assert {id(p) for p in raw} == {id(p) for p in phi.parameters()}  # every parameter, once
+    # every network parameter, once (geom_p / lamb of the discarded log-determinant estimator never reach the kernel)
+    assert {id(p) for p in raw} == {id(p) for n, p in phi.named_parameters() if not n.endswith(("geom_p", "lamb"))}
     assert flows._uv_buffer(phi.net).numel() == 3 * uvper
     assert lib.shwd_resflow_workspace_bytes(1000, 3) == (8 + 1) * 3 * per * 4
     # non-standard shapes and Planar stacks stay on the eager modules

@@ -163,3 +163,79 @@ def test_oracle_rigid_transform_matches_reference():
     rng = np.random.RandomState(1234)
     poses = torch.cat([oracle.data.create_random_transform(rng) for _ in range(d["poses"].shape[0])], 0)
     assert np.array_equal(poses.numpy(), d["poses"])
+
+
+# ---- rows a11 / a14 / f1: notebook sliced W, the learned sphere map, the max-over-phi wrapper ---------------------------
+def _state(d, prefix):
+    return {k[len(prefix):].replace("__", "."): torch.from_numpy(v) for k, v in d.items() if k.startswith(prefix)}
+
+
+def test_oracle_euclid_sliced_w_matches_notebook_cell():
+    """Flow_ellipsoid.ipynb cell 5 `sliced_wasserstein_distance`, executed from the notebook's own source by make_golden.py."""
+    d = load("notebook_sliced_wasserstein")
+    for p in (1, 2, 3):
+        x = torch.from_numpy(d["x_p%d" % p]).requires_grad_(True)
+        y = torch.from_numpy(d["y_p%d" % p]).requires_grad_(True)
+        loss = oracle.euclid_sliced_wasserstein(x, y, torch.from_numpy(d["theta_p%d" % p]), p)
+        gx, gy = torch.autograd.grad(loss, (x, y))
+        assert loss.item() == pytest.approx(float(d["loss_p%d" % p]), rel=2e-6)
+        assert rel(gx.numpy(), d["gx_p%d" % p]) < 2e-5 and rel(gy.numpy(), d["gy_p%d" % p]) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["Residual", "Planar"])
+def test_flow_modules_replay_the_vendored_normflows(name):
+    """losses/flows.py (the eager definition of phi the fused kernel is tested against) loaded with the reference's own
+    state_dict -- same keys -- reproduces the vendored normflows' outputs and gradients (batched and un-batched inputs)."""
+    import shwd
+    d = load("flow_" + name.lower())
+    phi = shwd.losses.Norm_Flow_structure(flow_name=name, n_flow_layer=3)
+    missing = phi.load_state_dict(_state(d, "sd__"), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    phi.train()
+    for tag in ("b", "u"):
+        x = torch.from_numpy(d["x_" + tag]).requires_grad_(True)
+        y = phi(x)
+        named = [(n, q) for n, q in phi.named_parameters() if q.dtype == torch.float32 and q.dim() > 0]
+        gs = torch.autograd.grad((y * torch.from_numpy(d["w_" + tag])).sum(), [x] + [q for _, q in named], allow_unused=True)
+        assert rel(y.detach().numpy(), d["y_" + tag]) < 1e-6
+        assert rel(gs[0].numpy(), d["gx_" + tag]) < 1e-5
+        for (n, q), g in zip(named, gs[1:]):
+            want = d["gp_%s__%s" % (tag, n.replace(".", "__"))]
+            got = np.zeros_like(want) if g is None else g.numpy()
+            assert np.linalg.norm(got - want) <= 2e-5 * max(np.linalg.norm(want), 1e-3), n
+
+
+class _CpuExactCSW(torch.nn.Module):
+    """Cos_disimilarity_W (s2_wasserstein.py:25-50) on the CPU from oracle pieces: cost matrix + exact plan per pair."""
+
+    def forward(self, x, y):
+        C = oracle.cost_matrix(x, y, "sqeuclid", 2)
+        tot = 0
+        for b in range(C.shape[0]):
+            _, plan = oracle.exact_emd2(C[b])
+            tot = tot + torch.pow((plan.to(C.dtype) * C[b]).sum(), 1.0 / 2)
+        return tot / C.shape[0]
+
+
+@pytest.mark.parametrize("name", ["Residual", "Planar"])
+def test_max_wrapper_step_matches_reference_on_cpu(name):
+    """The host orchestration of max_cos_disimilarity_wassersten_distance (s2_wasserstein.py:234-262: two SGD ascent steps
+    on phi, then the outer distance) against one frozen step of the unmodified reference wrapper."""
+    import shwd
+    d = load("max_wrapper_" + name.lower())
+    L = shwd.losses
+    phi = L.Norm_Flow_structure(flow_name=name, n_flow_layer=int(d["n_flow_layer"]))
+    phi.load_state_dict(_state(d, "sd0__"))
+    op = torch.optim.SGD(list(phi.parameters()), lr=float(d["lr"]))
+    crit = L.max_cos_disimilarity_wassersten_distance(phi=phi, CSW=_CpuExactCSW(), device="cpu", phi_op=op,
+                                                       max_iter=int(d["max_iter"]), lam=float(d["lam"]))
+    second = torch.from_numpy(d["second"]).requires_grad_(True)
+    cswd, ft, st = crit(torch.from_numpy(d["first"]), second, "train")
+    (g2,) = torch.autograd.grad(cswd, second)
+    assert cswd.item() == pytest.approx(float(d["cswd"]), rel=2e-6)
+    assert rel(ft.detach().numpy(), d["first_t"]) < 1e-5 and rel(st.detach().numpy(), d["second_t"]) < 1e-5
+    assert rel(g2.numpy(), d["g_second"]) < 5e-5
+    for k, v in _state(d, "sd1__").items():  # phi after the two ascent steps
+        got = phi.state_dict()[k]
+        if v.dtype == torch.float32 and v.dim() > 0 and "last_" not in k and not k.endswith("scale"):
+            assert torch.allclose(got, v, rtol=2e-4, atol=2e-6), (k, (got - v).abs().max().item())

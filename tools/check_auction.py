@@ -44,4 +44,4 @@ torch.cuda.synchronize(); t0 = time.time()
 loss = crit(tmpl, xg); loss.backward()
 torch.cuda.synchronize(); t1 = time.time()
 print("Cos_disimilarity_W(solver=exact) loss %.6f fwd+bwd %.1f ms; entropic (eps=0.01, L=100): %.6f" % (
-    loss.item(), (t1 - t0) * 1e3, shwd.losses.Cos_disimilarity_W(dev, p=2)(tmpl, src).item()))
+    loss.item(), (t1 - t0) * 1e3, shwd.losses.Cos_disimilarity_W(dev, p=2, solver="sinkhorn")(tmpl, src).item()))

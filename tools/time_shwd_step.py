@@ -19,7 +19,7 @@ for mode in ("fused", "eager"):
     if mode == "eager":
         phi.forward = phi.forward_eager
     opt = torch.optim.Adam(phi.parameters(), lr=1e-3)
-    crit = shwd.losses.max_cos_disimilarity_wassersten_distance(phi, shwd.losses.Geodesic_distance_W(dev, p=2), dev, opt,
+    crit = shwd.losses.max_cos_disimilarity_wassersten_distance(phi, shwd.losses.Geodesic_distance_W(dev, p=2, solver="sinkhorn"), dev, opt,
                                                                 max_iter=1, lam=0.1)
     ts, pts = [], []
     for it in range(8):
