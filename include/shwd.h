@@ -126,6 +126,14 @@ int shwd_segmented_sort(const float* keys, int segs, int len, float* sorted, int
 /* Same sort, permutation as int32 (the fused sliced losses keep it on the device only: half the bytes of torch's int64). */
 int shwd_segmented_sort_i32(const float* keys, int segs, int len, float* sorted, int32_t* perm, void* workspace,
                             size_t workspace_bytes, void* stream);
+/* The sliced losses' own sort: the sort CTA of slice (b, p) computes its keys from the cloud x (B,N,3) and frame p itself
+ * (mode 1: circle coordinates through frames (P,3,2), max_spherical_sliced_w.py:270-279; mode 2: line projections through
+ * directions (P,3), Flow_ellipsoid.ipynb:214-216) -- no (B,P,N) key array is written or read -- and emits the sorted
+ * values (B*P,N) (rebuilt from the sort keys: -0.0 comes back as +0.0) and the int32 stable-sort permutation.  Same keys,
+ * same permutation as shwd_project_* followed by shwd_segmented_sort_i32.  N <= shwd_sort_projected_max_points(). */
+int shwd_sort_projected_max_points(void);
+int shwd_sort_projected(const float* x, const float* frames, int B, int N, int P, int mode, float* sorted, int32_t* perm,
+                        void* stream);
 /* Circular W1 by level median on sorted circle coordinates (emd1D_circle, max_spherical_sliced_w.py:230-247):
  * us (S,n), vs (S,m) sorted ascending, n + m <= 32768 -> w (S); gus/gvs (nullable) receive dW/d(sorted values). */
 size_t shwd_circular_w1_workspace_bytes(int S, int n, int m);

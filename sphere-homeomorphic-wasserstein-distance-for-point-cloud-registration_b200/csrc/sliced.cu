@@ -28,6 +28,20 @@ constexpr float TWO_PI_F = 6.283185307179586f;
 constexpr float PI_F = 3.141592653589793f;
 
 // ------------------------------------------------------------------------------------------------ projections ----
+// One key: the stand-alone projection kernels and the sort kernels that compute their own keys (segmented_sort_project_*)
+// call the same functions, so both produce the same bits.
+__device__ __forceinline__ float circle_key(const float* u /* U[p][d][k] at d*2+k */, float x0, float x1, float x2) {
+  float a = fmaf(u[4], x2, fmaf(u[2], x1, u[0] * x0));
+  float c = fmaf(u[5], x2, fmaf(u[3], x1, u[1] * x0));
+  float nr = fmaxf(sqrtf(fmaf(c, c, a * a)), 1e-12f);  // F.normalize eps
+  a = a / nr;
+  c = c / nr;
+  return (atan2f(-c, -a) + PI_F) / TWO_PI_F;
+}
+__device__ __forceinline__ float line_key(const float* t /* theta[p][d] */, float x0, float x1, float x2) {
+  return fmaf(t[2], x2, fmaf(t[1], x1, t[0] * x0));
+}
+
 // keys[b,p,n] = (atan2(-q1, -q0) + pi) / (2 pi), q = normalize(U_p^T x_n)            (sliced_cost :270-279)
 __global__ void __launch_bounds__(PJ_THREADS) project_circle_kernel(const float* __restrict__ x, const float* __restrict__ U,
                                                                     int N, int P, float* __restrict__ keys) {
@@ -42,15 +56,7 @@ __global__ void __launch_bounds__(PJ_THREADS) project_circle_kernel(const float*
   const float* xp = x + ((size_t)b * N + n) * 3;
   const float x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
 #pragma unroll 4
-  for (int p = 0; p < pc; ++p) {
-    const float* u = sU + p * 6;  // U[p][d][k] at d*2+k
-    float a = fmaf(u[4], x2, fmaf(u[2], x1, u[0] * x0));
-    float c = fmaf(u[5], x2, fmaf(u[3], x1, u[1] * x0));
-    float nr = fmaxf(sqrtf(fmaf(c, c, a * a)), 1e-12f);  // F.normalize eps
-    a = a / nr;
-    c = c / nr;
-    keys[((size_t)b * P + p0 + p) * N + n] = (atan2f(-c, -a) + PI_F) / TWO_PI_F;
-  }
+  for (int p = 0; p < pc; ++p) keys[((size_t)b * P + p0 + p) * N + n] = circle_key(sU + p * 6, x0, x1, x2);
 }
 
 // gx[b,n,:] = sum_p gk[b,p,n] * ( dt/da * U[p,:,0] + dt/dc * U[p,:,1] ),  dt/da = -c / (2 pi r^2), dt/dc = a / (2 pi r^2)
@@ -126,8 +132,7 @@ __global__ void __launch_bounds__(PJ_THREADS) project_line_kernel(const float* _
   if (n >= N) return;
   const float* xp = x + ((size_t)b * N + n) * 3;
   const float x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
-  for (int p = 0; p < pc; ++p)
-    keys[((size_t)b * P + p0 + p) * N + n] = fmaf(sT[p * 3 + 2], x2, fmaf(sT[p * 3 + 1], x1, sT[p * 3] * x0));
+  for (int p = 0; p < pc; ++p) keys[((size_t)b * P + p0 + p) * N + n] = line_key(sT + p * 3, x0, x1, x2);
 }
 
 __global__ void __launch_bounds__(PJ_THREADS) project_line_bwd_kernel(const float* __restrict__ th, int N, int P,
@@ -363,6 +368,170 @@ __global__ void __launch_bounds__(SORT_THREADS) segmented_sort_kernel(const floa
     if (sorted) sorted[seg * len + i] = __ldg(k + j);
     if (perm) perm[seg * len + i] = (int64_t)j;
     if (perm32) perm32[seg * len + i] = (int32_t)j;
+  }
+}
+
+// ---- digit trimming + fused projection (the sliced losses' own sort) ---------------------------------------------------
+// An LSD radix sort only has to look at the bits in which the keys of a row differ.  Circle coordinates lie in [0, 1): sign
+// and the top exponent bits are the same for every key of a row, and a row of 4096 coordinates almost always differs in 27
+// bits -- three passes of 9-bit digits instead of four of 8 (the bits are found per row from the OR / AND of its keys, so
+// any input is still sorted exactly; signed Euclidean projections keep four passes).  A pass is the same warp-synchronous
+// ranking as block_radix_sort, with per-warp digit counters as 16-bit halves (512 bins x 8 warps = the same 8 KB).
+// The kernel can also COMPUTE its keys: a slice's keys are a function of the (N,3) cloud and one frame, so the sort CTA of
+// slice (b, p) projects the cloud itself instead of reading a (B,P,N) key array that a projection kernel wrote -- two
+// launches and 8 B per key of HBM traffic less per cloud -- and rebuilds the sorted values from the sorted keys (the key map
+// is invertible; -0.0 comes back as +0.0, which no consumer of the sorted values can tell apart) instead of gathering them.
+constexpr int SORT_TRIM_MAXW = 9;
+
+template <int W>
+__device__ __forceinline__ void radix_pass_trim(const RecBuf<true>& a, const RecBuf<true>& b, int beg, int end, int sh, uint32_t dmask,
+                                                uint32_t* hist32, uint32_t* wt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int BINS = 1 << SORT_TRIM_MAXW;          // counters are laid out for the widest digit
+  constexpr int WORDS = BINS / 2;                    // 16-bit counters, two per word
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t* wh = hist32 + warp * WORDS;
+  const uint32_t wh_s = (uint32_t)__cvta_generic_to_shared(wh);
+  for (int i = threadIdx.x; i < SORT_WARPS * WORDS; i += SORT_THREADS) hist32[i] = 0;
+  __syncthreads();
+  for (int i = beg + lane; i < end; i += 32) {
+    const uint32_t d = (rec_ld_key<true>(a, i) >> sh) & dmask;
+    atomicAdd(wh + (d >> 1), 1u << ((d & 1u) * 16u));
+  }
+  __syncthreads();
+  {
+    // digit-major exclusive offsets: thread t owns digits 2t and 2t+1 (one counter word per warp)
+    const int t = threadIdx.x;
+    uint32_t c[SORT_WARPS];
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      c[w] = hist32[w * WORDS + t];
+      tot += (c[w] & 0xffffu) + (c[w] >> 16);
+    }
+    uint32_t run = block_exscan_u32(tot, wt);
+    uint32_t lo[SORT_WARPS];
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      lo[w] = run;
+      run += c[w] & 0xffffu;
+    }
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      hist32[w * WORDS + t] = lo[w] | (run << 16);
+      run += c[w] >> 16;
+    }
+  }
+  __syncthreads();
+  int i0 = beg;
+#pragma unroll 1
+  for (; i0 + 32 <= end; i0 += 32) {
+    const uint2 rec = rec_ld<true>(a, i0 + lane);
+    const uint32_t d = (rec.x >> sh) & dmask;
+    const uint32_t peers = match_digit<W>(d);
+    uint32_t cur;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(cur) : "r"(wh_s + 2u * d));
+    rec_st<true>(b, cur + __popc(peers & lt), rec);
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.u16 [%0], %1; }" ::"r"(wh_s + 2u * d), "r"(cur + __popc(peers)),
+                 "r"((int)((peers & lt) == 0))
+                 : "memory");
+    __syncwarp();
+  }
+  if (i0 < end) {  // ragged tail: an extra "invalid" bit keeps the empty lanes apart
+    const int i = i0 + lane;
+    const bool valid = i < end;
+    const uint2 rec = valid ? rec_ld<true>(a, i) : make_uint2(0u, 0u);
+    const uint32_t d = valid ? ((rec.x >> sh) & dmask) : (1u << W);
+    const uint32_t peers = match_digit<W + 1>(d);
+    const uint32_t dd = d & dmask;
+    uint32_t cur;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(cur) : "r"(wh_s + 2u * dd));
+    if (valid) rec_st<true>(b, cur + __popc(peers & lt), rec);
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.u16 [%0], %1; }" ::"r"(wh_s + 2u * dd), "r"(cur + __popc(peers)),
+                 "r"((int)(valid && (peers & lt) == 0))
+                 : "memory");
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
+// KEYS: 0 = keys read from `keys` (B*P rows of len), 1 = circle keys of cloud x through frames fr (P,3,2), 2 = line keys
+// through directions fr (P,3).  seg = b * P + p.
+template <int KEYS>
+__global__ void __launch_bounds__(SORT_THREADS) segmented_sort_trim_kernel(const float* __restrict__ keys, const float* __restrict__ x,
+                                                                           const float* __restrict__ fr, int P, int len,
+                                                                           float* __restrict__ sorted, int32_t* __restrict__ perm32) {
+  extern __shared__ uint2 sbuf[];
+  __shared__ uint32_t hist32[SORT_WARPS * (1 << SORT_TRIM_MAXW) / 2];
+  __shared__ uint32_t wt[SORT_WARPS];
+  __shared__ uint32_t s_or[SORT_WARPS], s_and[SORT_WARPS];
+  __shared__ float s_fr[6];
+  const size_t seg = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  RecBuf<true> a = make_recbuf<true>(sbuf), b = make_recbuf<true>(sbuf + len);
+  if (KEYS != 0) {
+    const int p = (int)(seg % P);
+    const int nf = KEYS == 1 ? 6 : 3;
+    if (threadIdx.x < nf) s_fr[threadIdx.x] = __ldg(fr + (size_t)p * nf + threadIdx.x);
+    __syncthreads();
+  }
+  uint32_t vor = 0u, vand = 0xffffffffu;
+  for (int i = threadIdx.x; i < len; i += SORT_THREADS) {
+    float kf;
+    if (KEYS == 0) {
+      kf = __ldg(keys + seg * len + i);
+    } else {
+      const float* xp = x + ((seg / P) * (size_t)len + i) * 3;
+      const float x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
+      kf = KEYS == 1 ? circle_key(s_fr, x0, x1, x2) : line_key(s_fr, x0, x1, x2);
+    }
+    const uint32_t k = float_sort_key(kf);
+    vor |= k;
+    vand &= k;
+    rec_st<true>(a, i, make_uint2(k, (uint32_t)i));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+    vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+  }
+  if (lane == 0) {
+    s_or[warp] = vor;
+    s_and[warp] = vand;
+  }
+  __syncthreads();
+  vor = 0u;
+  vand = 0xffffffffu;
+#pragma unroll
+  for (int w = 0; w < SORT_WARPS; ++w) {
+    vor |= s_or[w];
+    vand &= s_and[w];
+  }
+  const uint32_t varying = vor ^ vand;  // (CTA-uniform) bits in which the row's keys differ
+  if (varying != 0u) {
+    const int lo = __ffs(varying) - 1, nbits = 32 - __clz(varying) - lo;
+    const int passes = (nbits + SORT_TRIM_MAXW - 1) / SORT_TRIM_MAXW;
+    const int w = (nbits + passes - 1) / passes;  // 1 .. 9 bits per pass
+    const uint32_t dmask = (1u << w) - 1u;
+    const int chunk = (((len + SORT_WARPS - 1) / SORT_WARPS) + 31) & ~31;
+    const int beg = min(len, warp * chunk), end = min(len, beg + chunk);
+    for (int pass = 0; pass < passes; ++pass) {
+      const int sh = lo + pass * w;
+      if (w <= 7)
+        radix_pass_trim<7>(a, b, beg, end, sh, dmask, hist32, wt);
+      else if (w == 8)
+        radix_pass_trim<8>(a, b, beg, end, sh, dmask, hist32, wt);
+      else
+        radix_pass_trim<9>(a, b, beg, end, sh, dmask, hist32, wt);
+      const RecBuf<true> t = a;
+      a = b;
+      b = t;
+    }
+  }
+  for (int i = threadIdx.x; i < len; i += SORT_THREADS) {
+    const uint2 r = rec_ld<true>(a, i);
+    if (sorted) sorted[seg * len + i] = float_from_sort_key(r.x);
+    if (perm32) perm32[seg * len + i] = (int32_t)r.y;
   }
 }
 
@@ -869,11 +1038,44 @@ static int launch_sort_compact(const float* keys, int segs, int len, float* sort
   return SHWD_OK;
 }
 
+// the trimmed-digit kernel (int32 permutation, values rebuilt from the keys): rows the uint2 layout is best for
+template <int KEYS>
+static int launch_sort_trim(const float* keys, const float* x, const float* fr, int P, int segs, int len, float* sorted, int32_t* perm32,
+                            cudaStream_t s) {
+  const size_t smem = 2 * (size_t)len * sizeof(uint2);
+  if (smem > 32 * 1024)
+    SHWD_CUDA_CHECK(cudaFuncSetAttribute(segmented_sort_trim_kernel<KEYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  segmented_sort_trim_kernel<KEYS><<<segs, SORT_THREADS, smem, s>>>(keys, x, fr, P, len, sorted, perm32);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+static bool sort_use_trim(int len) {
+  static const int forced = sort_env("SHWD_SORT_TRIM", "0", 1, "1", 2, 0);
+  if (forced == 1) return false;
+  return len <= SORT_WIDE_BEST_MAX && !sort_use_compact(len);
+}
+
+extern "C" int shwd_sort_projected_max_points(void) {
+  static const int forced = sort_env("SHWD_SORT_TRIM", "0", 1, "1", 2, 0);
+  return forced == 1 ? 0 : SORT_WIDE_BEST_MAX;
+}
+
+extern "C" int shwd_sort_projected(const float* x, const float* frames, int B, int N, int P, int mode, float* sorted, int32_t* perm,
+                                   void* stream) {
+  if (!x || !frames || B < 0 || N <= 0 || P <= 0 || (mode != 1 && mode != 2) || (!sorted && !perm)) return SHWD_ERR_INVALID_ARGUMENT;
+  if (N > shwd_sort_projected_max_points()) return SHWD_ERR_UNSUPPORTED;
+  if (B == 0) return SHWD_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return mode == 1 ? launch_sort_trim<1>(nullptr, x, frames, P, B * P, N, sorted, perm, s)
+                   : launch_sort_trim<2>(nullptr, x, frames, P, B * P, N, sorted, perm, s);
+}
+
 static int launch_segmented_sort(const float* keys, int segs, int len, float* sorted, int64_t* perm, int32_t* perm32,
                                  void* workspace, size_t workspace_bytes, void* stream) {
   if (!keys || segs < 0 || len <= 0 || (!sorted && !perm && !perm32)) return SHWD_ERR_INVALID_ARGUMENT;
   if (segs == 0) return SHWD_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!perm && sort_use_trim(len)) return launch_sort_trim<0>(keys, nullptr, nullptr, 1, segs, len, sorted, perm32, s);
   if (sort_use_compact(len)) {
     static const int warps_env = sort_env("SHWD_SORT_WARPS", "8", 8, "16", 16, 0);
     const int warps = warps_env ? warps_env : 16;  // (32 warps for the one-CTA-per-SM rows: 34.1 vs 33.7 Gkeys/s at 16384, slower below)

@@ -626,17 +626,25 @@ class SlicedLossFn(torch.autograd.Function):
         ku = torch.empty(S, n, device=dev, dtype=torch.float32)
         kv = torch.empty(S, m, device=dev, dtype=torch.float32)
         w = torch.empty(S, device=dev, dtype=torch.float32)
+        fused_max = lib.shwd_sort_projected_max_points()
         with torch.cuda.device(dev):
             st = _stream()
-            if mode == "line":
-                _lib.check(lib.shwd_project_line(_ptr(x), _ptr(frames), B, n, P, _ptr(ku), st), "shwd_project_line")
-                _lib.check(lib.shwd_project_line(_ptr(y), _ptr(frames), B, m, P, _ptr(kv), st), "shwd_project_line")
-            else:
-                _lib.check(lib.shwd_project_circle(_ptr(x), _ptr(frames), B, n, P, _ptr(ku), st), "shwd_project_circle")
-                _lib.check(lib.shwd_project_circle(_ptr(y), _ptr(frames), B, m, P, _ptr(kv), st), "shwd_project_circle")
-            su, pu = _sort_i32(ku)
-            sv, pv = _sort_i32(kv)
-            gku, gkv = ku, kv  # the keys are dead once sorted: their buffers receive d w / d keys
+            sorted_perm = []
+            for c, cnt, kbuf in ((x, n, ku), (y, m, kv)):
+                if cnt <= fused_max:  # the sort CTAs compute their own keys: no key array, no projection launch
+                    so = torch.empty(S, cnt, device=dev, dtype=torch.float32)
+                    pe = torch.empty(S, cnt, device=dev, dtype=torch.int32)
+                    _lib.check(lib.shwd_sort_projected(_ptr(c), _ptr(frames), B, cnt, P, 2 if mode == "line" else 1, _ptr(so), _ptr(pe), st),
+                               "shwd_sort_projected")
+                    sorted_perm.append((so, pe))
+                else:
+                    if mode == "line":
+                        _lib.check(lib.shwd_project_line(_ptr(c), _ptr(frames), B, cnt, P, _ptr(kbuf), st), "shwd_project_line")
+                    else:
+                        _lib.check(lib.shwd_project_circle(_ptr(c), _ptr(frames), B, cnt, P, _ptr(kbuf), st), "shwd_project_circle")
+                    sorted_perm.append(_sort_i32(kbuf))
+            (su, pu), (sv, pv) = sorted_perm
+            gku, gkv = ku, kv  # (dead once sorted / never filled): these buffers receive d w / d keys
             if mode == "circle_w1":
                 _lib.check(lib.shwd_circular_w1_scatter(_ptr(su), _ptr(sv), _ptr(pu), _ptr(pv), S, n, m, _ptr(w), _ptr(gku), _ptr(gkv),
                                                         st), "shwd_circular_w1_scatter")

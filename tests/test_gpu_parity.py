@@ -456,6 +456,63 @@ def test_segmented_sort_is_bit_exact_stable(shwd, segs, length):
     assert torch.equal(v.cpu().view(torch.int32), ref_v.view(torch.int32))  # same bits, incl. signed zeros / NaN payloads
 
 
+@pytest.mark.parametrize("kind", ["circle", "signed", "ties", "constant", "tiny_range", "specials", "denormal_span"])
+@pytest.mark.parametrize("segs,length", [(5, 1), (7, 33), (3, 1000), (4, 4096), (2, 4224)])
+def test_trimmed_digit_sort_is_bit_exact_stable(shwd, kind, segs, length):
+    """The sliced losses' own sort (digits trimmed to the bits in which a row's keys differ, csrc/sliced.cu): the int32
+    permutation equals torch.sort(stable=True) bit for bit on rows that differ in 27 bits (circle coordinates: 3 passes),
+    32 bits (signed), a handful of bits, none at all, with NaN / +-inf / +-0, and across the denormal boundary."""
+    g = torch.Generator().manual_seed(segs * 100 + length)
+    if kind == "circle":
+        k = torch.rand(segs, length, generator=g)
+    elif kind == "signed":
+        k = torch.randn(segs, length, generator=g) * 3
+    elif kind == "ties":
+        k = torch.randint(0, 7, (segs, length), generator=g).float() / 7
+    elif kind == "constant":
+        k = torch.full((segs, length), 0.375)
+    elif kind == "tiny_range":
+        k = 0.5 + torch.randint(0, 40, (segs, length), generator=g).float() * 2.0 ** -24
+    elif kind == "specials":
+        k = torch.randn(segs, length, generator=g)
+        k[:, ::5] = float("nan")
+        k[:, 1::7] = float("inf")
+        k[:, 2::11] = -float("inf")
+        k[:, 3::13] = 0.0
+        k[:, 4::17] = -0.0
+    else:
+        k = torch.rand(segs, length, generator=g) * 1e-37 * torch.randint(0, 3, (segs, length), generator=g).float() * 1e-3
+    kd = k.to(dev())
+    so, pe = shwd.ops._sort_i32(kd)
+    ref_v, ref_p = torch.sort(kd, dim=-1, stable=True)
+    assert torch.equal(pe.long(), ref_p)
+    assert torch.equal(so.isnan(), ref_v.isnan()) and torch.equal(so[~so.isnan()], ref_v[~ref_v.isnan()])  # (-0.0 == +0.0)
+
+
+@pytest.mark.parametrize("mode", ["circle", "line"])
+@pytest.mark.parametrize("B,N,P", [(1, 1, 3), (2, 700, 9), (3, 4096, 5), (1, 4224, 2)])
+def test_projected_sort_equals_projection_then_sort(shwd, mode, B, N, P):
+    """shwd_sort_projected (sort CTAs that compute their own keys) against the stand-alone projection kernel followed by
+    the sort: same keys, same permutation, same sorted values."""
+    g = torch.Generator().manual_seed(B + N + P)
+    x = (torch.randn(B, N, 3, generator=g) * torch.tensor([1.0, 0.6, 1.7])).to(dev())
+    lib = shwd._lib.lib()
+    if mode == "circle":
+        fr, _ = torch.linalg.qr(torch.randn(P, 3, 2, generator=g))
+        fr = fr.contiguous().to(dev())
+        keys = shwd.ops.ProjectCircleFn.apply(x, fr)
+    else:
+        fr = F.normalize(torch.randn(P, 3, generator=g), dim=-1).to(dev())
+        keys = shwd.ops.ProjectLineFn.apply(x, fr)
+    so = torch.empty(B * P, N, device=dev())
+    pe = torch.empty(B * P, N, device=dev(), dtype=torch.int32)
+    assert N <= lib.shwd_sort_projected_max_points()
+    shwd._lib.check(lib.shwd_sort_projected(x.data_ptr(), fr.data_ptr(), B, N, P, 1 if mode == "circle" else 2, so.data_ptr(),
+                                            pe.data_ptr(), torch.cuda.current_stream().cuda_stream), "shwd_sort_projected")
+    ref_v, ref_p = torch.sort(keys.reshape(B * P, N), dim=-1, stable=True)
+    assert torch.equal(pe.long(), ref_p) and torch.equal(so, ref_v)
+
+
 def test_sort_gradient_scatters_through_permutation(shwd):
     torch.manual_seed(0)
     k = torch.randn(6, 300)
@@ -569,11 +626,11 @@ def test_fused_sliced_loss_gradients_match_oracle_at_full_sizes(shwd, mode, n, m
         cfn = lambda a, b: shwd.losses.sliced_cost(a, b, fr.to(dev()), p=p)
     outs = {}
     for dt in (torch.float32, torch.float64):
-        a, b = Xs.to(dt).requires_grad_(True), Xt.to(dt).requires_grad_(True)
+        a, b = Xs.detach().clone().to(dt).requires_grad_(True), Xt.detach().clone().to(dt).requires_grad_(True)
         v = ofn(a, b)
         v.backward()
         outs[dt] = (v.detach(), a.grad, b.grad)
-    a, b = Xs.to(dev()).requires_grad_(True), Xt.to(dev()).requires_grad_(True)
+    a, b = Xs.detach().clone().to(dev()).requires_grad_(True), Xt.detach().clone().to(dev()).requires_grad_(True)
     v = cfn(a, b)
     v.backward()
     floor = [rel(x32, x64) for x32, x64 in zip(outs[torch.float32], outs[torch.float64])]
