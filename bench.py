@@ -45,16 +45,15 @@ CPU_CHUNK = 4                  # the CPU reference holds 
 NCU_BYTES_FILE = os.path.join(ROOT, "profiles", "ncu_dram_bytes.json")  # written by tools/ncu_summary.py --bytes
 
 
-def ncu_bytes(kernel, default):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the latest `ncu --set full` capture
-    (bench.py cannot run under ncu while it is timing); regenerated by tools/ncu_summary.py --bytes."""
+def ncu_bytes(cfg, kernel, default):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` (base name) at workload `cfg`, from the latest
+    `ncu --set full` capture (bench.py cannot run under ncu while it is timing); written by tools/ncu_summary.py --bytes."""
     try:
         with open(NCU_BYTES_FILE) as fh:
-            d = json.load(fh)
-        e = d[kernel]
-        return float(e["bytes"]), "%s (%s)" % (os.path.relpath(NCU_BYTES_FILE, ROOT), e.get("source", "?"))
+            e = json.load(fh)[cfg][kernel]
+        return float(e["bytes"]), "%s[%s][%s] (%s)" % (os.path.relpath(NCU_BYTES_FILE, ROOT), cfg, kernel, e.get("source", "?"))
     except Exception:
-        return default, "profiles/r01e_ncu_sinkhorn_full_summary.txt (constant; profiles/ncu_dram_bytes.json absent)"
+        return default, "profiles/r01e_ncu_sinkhorn_full_summary.txt (constant; no entry in profiles/ncu_dram_bytes.json)"
 
 
 def measured_hbm_peak():
@@ -571,8 +570,9 @@ def main():
             kname = "sinkhorn_bwd_lean_kernel<FAST_GEO2>" if lean else "sinkhorn_bwd_kernel<FAST_GEO2>"
             E = (2 * ITERS + 1) * Nk * Nk * Bk
             ach_b, ach_f = BWD_OPS * E / (t_bwd * 1e-3), FWD_OPS * E / (t_fwd * 1e-3)
-            tb_bytes, tb_src = ncu_bytes(kname + "@%s" % cfg, 53.95e6 if cfg == "cfg2" and not lean else None)
-            tf_bytes, _ = ncu_bytes(kname.replace("bwd", "fwd") + "@%s" % cfg, 11.97e6 if cfg == "cfg2" and not lean else None)
+            kbase = "sinkhorn_bwd_lean_kernel" if lean else "sinkhorn_bwd_kernel"
+            tb_bytes, tb_src = ncu_bytes(cfg, kbase, 53.95e6 if cfg == "cfg2" and not lean else None)
+            tf_bytes, _ = ncu_bytes(cfg, kbase.replace("bwd", "fwd"), 11.97e6 if cfg == "cfg2" and not lean else None)
             roof = {"bound": "fp32", "kernel": kname, "achieved": ach_b / 1e12, "peak": fp32_peak / 1e12,
                     "unit": "Tlane-op/s (FFMA = 1 lane-op)", "frac": ach_b / fp32_peak, "traffic": tb_bytes, "traffic_source": tb_src,
                     "peak_source": psrc, "ms_per_launch": t_bwd, "algorithmic_ops_per_launch": BWD_OPS * E}
@@ -609,8 +609,9 @@ def main():
             t_sort = ktime(k_sort)
             hbm, hsrc = measured_hbm_peak()
             bytes_alg = 12.0 * B * P * n
-            tr_bytes, tr_src = ncu_bytes("segmented_sort_kernel@cfg3", None)
-            roof = {"bound": "hbm", "kernel": "segmented_sort_kernel<int32 perm> (one launch per cloud: 4096 slices x 4096 keys)",
+            tr_bytes, tr_src = ncu_bytes("cfg3", "segmented_sort_trim_kernel", None)
+            roof = {"bound": "hbm", "kernel": "segmented_sort_trim_kernel (one launch per cloud: 4096 slices x 4096 keys; in the loss the "
+                                              "sort CTAs also compute the keys, shwd_sort_projected)",
                     "achieved": bytes_alg / (t_sort * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": bytes_alg / (t_sort * 1e-3) / 1e9 / hbm,
                     "traffic": tr_bytes, "traffic_source": tr_src, "peak_source": hsrc, "ms_per_launch": t_sort,
                     "algorithmic_bytes_per_launch": bytes_alg, "gkeys_per_s": B * P * n / (t_sort * 1e-3) / 1e9,
