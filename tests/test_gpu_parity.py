@@ -157,15 +157,17 @@ class _path:
 
 
 LEAN_SHAPES = [
-    # B, N, M, L, eps                 what the mapping looks like on 148 SMs
+    # B, N, M, L, eps                 what the dedicated-CTA mapping of csrc/sinkhorn_lean.cu looks like on 148 SMs
     (1, 1024, 1024, 100, 0.01),     # one pair over 128 CTAs, 8 owners per warp row (4 sub-slices per warp)
     (1, 256, 256, 40, 0.01),        # 32 CTAs, heavy padding of the packed records
     (4, 1024, 1024, 100, 0.01),     # the 4 pairs per GPU of an 8-way strong-scaled B=32: 32 CTAs per pair, 32 owners each
     (32, 256, 256, 100, 0.01),      # train_RUNNER.py's small runs: 4 CTAs per pair, two owner groups each
+    (32, 1024, 1024, 12, 0.02),     # the benchmark shape forced onto the lean kernels: 4 CTAs per pair, eight groups each
     (200, 256, 200, 12, 0.02),      # B > #SMs: whole pairs per CTA, 8 + 7 owner groups, 4 group pairs x 4 slices
     (3, 40, 700, 15, 0.05),         # ragged: most CTAs have no row owners at all
     (2, 2048, 1500, 8, 0.05),       # the largest resident clouds
     (9, 600, 600, 20, 0.02),        # 16 CTAs per pair, 38 owners -> two groups of 32 with a ragged tail
+    (7, 1000, 777, 10, 0.02),       # N != M: bands of 64 row owners and 64 column owners, the last ones ragged
     (16, 1000, 1024, 10, 0.02),     # 9 CTAs per pair, four groups
 ]
 
