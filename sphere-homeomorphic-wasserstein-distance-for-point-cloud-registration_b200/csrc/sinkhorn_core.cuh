@@ -532,9 +532,14 @@ __device__ __forceinline__ f2 sign2(f2 d) {
 // below 2^-126 cannot matter, an overflow makes it inf); anything else -- only the first few, wildly moving iterations --
 // makes the CTA redo the visit with the running maximum.  The fixed offset removes the max / rescale work (0.25 MUFU
 // and ~2 FP32/ALU slots per element) and the dependency of every ex2 on the max of its batch.
-template <int FAST, int MODE, int R, bool OFF = false>
+// CACHED (sinkhorn_lean.cu): the per-element intermediate pk_e -- the expensive, potential-independent part of an element
+// (dot product, acos) -- of records t, t+1 against owner r comes from cth[(((t - tb) / 2) * R + r) * SK_THREADS] (the
+// thread's own column of a shared-memory table filled once per launch by lean_fill_cache with the same pk_e calls, so
+// the values are the ones the uncached loop would compute, bit for bit) instead of being recomputed.
+template <int FAST, int MODE, int R, bool OFF = false, bool CACHED = false>
 __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, float lconst, const PackedSmem& v, int tb, int te,
-                                                    bool first_chunk, const float4* own, const float4* own3, float4* slot) {
+                                                    bool first_chunk, const float4* own, const float4* own3, float4* slot,
+                                                    const float4* cth = nullptr) {
   float4 op[R];  // staged owner records of this lane (stage_owners); entries of dead owners are zero / -inf
 #pragma unroll
   for (int r = 0; r < R; ++r) op[r] = own[32 * r];
@@ -558,8 +563,15 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, float 
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const f2 e0 = ex2_2(sub2(mp[r][0], bc2(off[r]))), e1 = ex2_2(sub2(mp[r][1], bc2(off[r])));
-        const f2 th0 = pk_e<FAST>(cp, op[r], mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y));
-        const f2 th1 = pk_e<FAST>(cp, op[r], mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w));
+        f2 th0, th1;
+        if (CACHED) {
+          const float4 c = cth[(((t - tb) >> 1) * R + r) * SK_THREADS];
+          th0 = mk2(c.x, c.y);
+          th1 = mk2(c.z, c.w);
+        } else {
+          th0 = pk_e<FAST>(cp, op[r], mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y));
+          th1 = pk_e<FAST>(cp, op[r], mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w));
+        }
         mp[r][0] = pk_m<FAST>(cp, th0, mk2(P.x, P.y));  // the canonical exponent Cost::m, as in the safe path
         mp[r][1] = pk_m<FAST>(cp, th1, mk2(P.z, P.w));
         rs[r] = add2(rs[r], add2(e0, e1));
@@ -591,8 +603,15 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, float 
         const float4 Z = *reinterpret_cast<const float4*>(v.Z + t + e), P = *reinterpret_cast<const float4*>(v.P + t + e);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const f2 th0 = pk_e<FAST>(cp, op[r], mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y));
-          const f2 th1 = pk_e<FAST>(cp, op[r], mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w));
+          f2 th0, th1;
+          if (CACHED) {
+            const float4 c = cth[(((t + e - tb) >> 1) * R + r) * SK_THREADS];
+            th0 = mk2(c.x, c.y);
+            th1 = mk2(c.z, c.w);
+          } else {
+            th0 = pk_e<FAST>(cp, op[r], mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y));
+            th1 = pk_e<FAST>(cp, op[r], mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w));
+          }
           m[r][e] = pk_m<FAST>(cp, th0, mk2(P.x, P.y));
           m[r][e + 1] = pk_m<FAST>(cp, th1, mk2(P.z, P.w));
         }
@@ -642,7 +661,12 @@ __device__ __forceinline__ void compute_packed_geo2(const CostParams& cp, float 
               th = fma2(bc2(-cp.sk), c, bc2(cp.sk));  // sqrt(k) (1 - c); d(kC)/dc = -2 sqrt(k) th
               gs = th;
             } else {
-              th = scaled_acos2(cp.q, cp.hpi, c);
+              if (CACHED) {
+                const float4 cc = cth[(((t - tb) >> 1) * R + r) * SK_THREADS];
+                th = h ? mk2(cc.z, cc.w) : mk2(cc.x, cc.y);
+              } else {
+                th = scaled_acos2(cp.q, cp.hpi, c);
+              }
               const f2 om = fma2(neg2(c), c, bc2(1.f));
               const f2 rs = mk2(rsqrt_approx(fmaxf(lo2(om), 1e-12f)), rsqrt_approx(fmaxf(hi2(om), 1e-12f)));
               gs = (FAST == FAST_GEO2) ? mul2(th, rs) : rs;                   // p = 1: d(k theta)/dc = -k rs (constant in gscale)

@@ -28,6 +28,7 @@
 #define SHWD_PROF_SYM g_prof_lean
 #include "sinkhorn_core.cuh"
 #include "sinkhorn_lean.h"
+#include <stdlib.h>
 
 namespace shwd {
 
@@ -38,6 +39,8 @@ struct LeanView {
   float4* own;            // (x, y, z, previous potential) per (group, lane), owners replicated over the sub-slices
   float4* own3;           // backward: (own_pot1, o2, oadj)
   float* ownadj;          // backward: the owners' latest adjoint
+  const float4* cth;      // this thread's column of the cached-intermediate table of the type (see lean_fill_cache)
+  int nc;                 // record pairs per lane the table holds
   int T, ng, NGP, r0, r1, n_str;
 };
 
@@ -58,6 +61,11 @@ __device__ __forceinline__ LeanView lean_view(float4* smem4, const LeanGeom& gm,
   v.own = own + type * GMAX * 32;
   v.own3 = own + (2 + type) * GMAX * 32;
   v.ownadj = reinterpret_cast<float*>(own + 4 * GMAX * 32) + type * GMAX * 32;
+  // cached intermediates: after the owners' adjoints (2 * GMAX * 32 floats), one float4 per (record pair, owner group) and
+  // thread, thread-major inside an entry (conflict-free: lane i reads word 4 i of a 512-B line)
+  const float4* cache = own + 4 * GMAX * 32 + (2 * GMAX * 32) / 4;
+  v.cth = cache + (type ? (size_t)gm.nc[0] * gm.cr[0] * SK_THREADS : 0) + threadIdx.x;
+  v.nc = gm.nc[type];
   v.T = T;
   v.ng = gm.R[type] >> gm.rw_shift;
   const int ngp = (v.ng + 1) >> 1;
@@ -193,6 +201,31 @@ __device__ __forceinline__ LeanThread lean_thread(const LeanView& v, int rw_shif
   return t;
 }
 
+// The potential-independent part of an element -- dot product and acos (pk_e) -- is the same in all 2L+1 sweeps of a
+// launch, and in this regime a lane's elements are few: fill a thread-private shared-memory table with them once per pair
+// and let the sweeps read it back (compute_packed_geo2<..., CACHED>).  The sweeps are XU-bound (sqrt + ex2 per forward
+// element, sqrt + rsqrt + 2 ex2 backward); a cached element needs no sqrt and no dot / acos arithmetic.  The table holds
+// the first v.nc record pairs of every lane's sub-slice (all of them when shared memory allows -- LeanGeom::nc); the
+// rest of the sub-slice is swept by the recomputing loop, which continues from the partial result of the cached part.
+template <int PK>
+__device__ __forceinline__ void lean_fill_cache(const CostParams& cp, const LeanView& v, const LeanThread& lt) {
+  if (lt.te < 0 || v.nc == 0) return;
+  const int R = lt.two ? 2 : 1;
+  float4* dst = const_cast<float4*>(v.cth);
+  const float2 *Xa = v.X, *Ya = v.X + v.T, *Za = v.X + 2 * v.T;
+  for (int r = 0; r < R; ++r) {
+    const float4 op = v.own[lt.own + 32 * r];
+    for (int it = 0; it < v.nc && lt.tb + 2 * it < lt.te; ++it) {
+      const int t = lt.tb + 2 * it;
+      const float4 X = *reinterpret_cast<const float4*>(Xa + t), Y = *reinterpret_cast<const float4*>(Ya + t);
+      const float4 Z = *reinterpret_cast<const float4*>(Za + t);
+      const f2 th0 = pk_e<PK>(cp, op, mk2(X.x, X.y), mk2(Y.x, Y.y), mk2(Z.x, Z.y));
+      const f2 th1 = pk_e<PK>(cp, op, mk2(X.z, X.w), mk2(Y.z, Y.w), mk2(Z.z, Z.w));
+      dst[(it * R + r) * SK_THREADS] = make_float4(lo2(th0), hi2(th0), lo2(th1), hi2(th1));
+    }
+  }
+}
+
 // One warp's pass of a half-step: its (group pair, streamed slice), then the combination of the sub-slices of a warp row.
 template <int PK, int MODE, bool OFF>
 __device__ __forceinline__ void lean_compute(const CostParams& cp, float lconst, const LeanView& v, const LeanThread& lt, float4* part,
@@ -211,10 +244,21 @@ __device__ __forceinline__ void lean_compute(const CostParams& cp, float lconst,
   float4* slot = part + lt.slot;
   const float4* own = v.own + lt.own;
   const float4* own3 = v.own3 + lt.own;
-  if (two)
-    compute_packed_geo2<PK, MODE, 2, OFF>(cp, lconst, pv, tb, te, true, own, own3, slot);
-  else
-    compute_packed_geo2<PK, MODE, 1, OFF>(cp, lconst, pv, tb, te, true, own, own3, slot);
+  // the backward reads the table only for the acos-based costs (the others' intermediates are by-products of the gradient)
+  constexpr bool USE = MODE == MODE_LSE || PK == FAST_GEO2 || PK == FAST_GEO1;
+  const int tc = USE ? min(te, tb + 2 * v.nc) : tb;  // [tb, tc): cached record pairs; [tc, te): recomputed
+  if (tc > tb) {
+    if (two)
+      compute_packed_geo2<PK, MODE, 2, OFF, true>(cp, lconst, pv, tb, tc, true, own, own3, slot, v.cth);
+    else
+      compute_packed_geo2<PK, MODE, 1, OFF, true>(cp, lconst, pv, tb, tc, true, own, own3, slot, v.cth);
+  }
+  if (tc < te) {
+    if (two)
+      compute_packed_geo2<PK, MODE, 2, OFF>(cp, lconst, pv, tc, te, tc == tb, own, own3, slot);
+    else
+      compute_packed_geo2<PK, MODE, 1, OFF>(cp, lconst, pv, tc, te, tc == tb, own, own3, slot);
+  }
   if (rw_shift < 5) {
     const int RW = 1 << rw_shift;
     __syncwarp();
@@ -295,6 +339,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_lean_kernel(const 
     for (int j = V1.r0 + threadIdx.x; j < V1.r1; j += SK_THREADS) prm.beta[((size_t)b * HL) * prm.M + j] = 0.f;
 
     const LeanThread LT0 = lean_thread(V0, rw_shift), LT1 = lean_thread(V1, rw_shift);
+    __syncthreads();  // the resident coordinates and owner records are in place
+    lean_fill_cache<PK>(prm.cp, V0, LT0);
+    lean_fill_cache<PK>(prm.cp, V1, LT1);
     for (int h = 0; h < 2 * L; ++h) {
       const int type = h & 1;
       const int l = (h >> 1) + 1;
@@ -442,6 +489,11 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_bwd_lean_kernel(const 
     }
 
     const LeanThread LT0 = lean_thread(V0, rw_shift), LT1 = lean_thread(V1, rw_shift);
+    __syncthreads();  // the resident coordinates and owner records are in place
+    if (PK == FAST_GEO2 || PK == FAST_GEO1) {
+      lean_fill_cache<PK>(prm.cp, V0, LT0);
+      lean_fill_cache<PK>(prm.cp, V1, LT1);
+    }
     for (int ph = 2; ph <= 2 * Ls; ++ph) {
       const bool last = (ph == 2 * Ls);
       const int type = last ? 0 : (ph & 1);
@@ -570,10 +622,27 @@ bool lean_plan(int B, int N, int M, LeanGeom* out) {
     gm.T[type] = ((n_str + 1) / 2 + unit - 1) / unit * unit;
   }
   gm.grid = gm.whole_pairs ? G : B * gm.Q;
-  // shared memory: the lean carve-up must fit inside the general kernel's allocation (the FINAL sweeps use that one)
+  // shared memory: the lean carve-up, then as much of the cached-intermediate table (lean_fill_cache) as fits in the SM's
+  // 227 KB; the FINAL sweeps use the general kernel's carve-up over the same allocation
   const size_t lean_bytes = sizeof(float2) * 6 * (size_t)(gm.T[0] + gm.T[1]) + sizeof(float4) * (LEAN_PART_ROWS * 32 + 4 * GMAX * 32) +
                             sizeof(float) * 2 * GMAX * 32;
   if (lean_bytes > sinkhorn_smem_bytes()) return false;
+  static const bool cache_on = !(getenv("SHWD_LEAN_CACHE") && getenv("SHWD_LEAN_CACHE")[0] == '0');
+  long long slots = cache_on ? (long long)(226 * 1024 - lean_bytes) / (long long)(sizeof(float4) * SK_THREADS) : 0;  // float4 per thread
+  for (int type = 0; type < 2; ++type) {
+    const int ng = gm.R[type] >> gm.rw_shift;
+    const int ngp = (ng + 1) >> 1;
+    const int NGP = ngp <= 1 ? 1 : (ngp <= 2 ? 2 : 4);
+    const int sls = (gm.T[type] / (SK_WARPS / NGP)) >> (5 - gm.rw_shift);  // records per lane sub-slice
+    gm.cr[type] = ng >= 2 ? 2 : 1;
+    long long nc = slots / gm.cr[type];
+    if (nc > sls / 2) nc = sls / 2;
+    nc &= ~1LL;  // the running-maximum loop advances two record pairs at a time
+    gm.nc[type] = (int)nc;
+    slots -= nc * gm.cr[type];
+  }
+  const size_t total = lean_bytes + sizeof(float4) * SK_THREADS * ((size_t)gm.nc[0] * gm.cr[0] + (size_t)gm.nc[1] * gm.cr[1]);
+  gm.smem = (int)(total > sinkhorn_smem_bytes() ? total : sinkhorn_smem_bytes());
   if (out) *out = gm;
   return true;
 }
@@ -604,7 +673,7 @@ bool lean_selected(int B, int N, int M, int fast, int hist_levels, float thresh)
 
 template <typename K>
 static int launch_lean(K kernel, const SinkParams& prm, const LeanGeom& gm, cudaStream_t s) {
-  const size_t smem = sinkhorn_smem_bytes();
+  const size_t smem = (size_t)gm.smem;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_last_cuda_error(e);

@@ -12,6 +12,9 @@ struct LeanGeom {
   int rw_shift;     // log2(owners per warp row): 3, 4 or 5
   int R[2];         // owners per CTA band (row / col owners), multiples of the warp row
   int T[2];         // packed records of the streamed cloud per half-step type (type 0 streams y, type 1 streams x)
+  int nc[2];        // cached intermediates: record pairs per lane and type held in shared memory (sinkhorn_lean.cu)
+  int cr[2];        // ... owner groups per warp the table is laid out for (1 or 2)
+  int smem;         // dynamic shared memory of the launch
 };
 
 bool lean_plan(int B, int N, int M, LeanGeom* out);
