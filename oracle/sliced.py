@@ -18,8 +18,9 @@ def project_circle(X, U):
     return (torch.atan2(-Xp[:, :, 1], -Xp[:, :, 0]) + math.pi) / (2 * math.pi)
 
 
-def emd1d_circle(u_values, v_values, stable=False):
-    """Circular W1 by the level-median formula, uniform weights -- ``emd1D_circle`` :210-247 (p == 1 branch).
+def emd1d_circle(u_values, v_values, stable=False, u_weights=None, v_weights=None):
+    """Circular W1 by the level-median formula -- ``emd1D_circle`` :210-247 (p == 1 branch); uniform weights unless
+    ``u_weights`` (n,) / (P,n) and ``v_weights`` are given (:217-228: gathered through the sort permutations).
 
     (P,n),(P,m) -> (P,).  Quirk kept: ``delta`` pads the sorted merged values with 1 at the END only, so the arc
     from 0 to the first point is omitted (:238-239).
@@ -27,8 +28,8 @@ def emd1d_circle(u_values, v_values, stable=False):
     """
     n, m = u_values.shape[-1], v_values.shape[-1]
     dt = u_values.dtype
-    uw = torch.full((n,), 1 / n, dtype=dt)
-    vw = torch.full((m,), 1 / m, dtype=dt)
+    uw = torch.full((n,), 1 / n, dtype=dt) if u_weights is None else u_weights
+    vw = torch.full((m,), 1 / m, dtype=dt) if v_weights is None else v_weights
     u_sorted, u_perm = torch.sort(u_values, dim=-1, stable=stable)
     v_sorted, v_perm = torch.sort(v_values, dim=-1, stable=stable)
     uw = uw[..., u_perm]

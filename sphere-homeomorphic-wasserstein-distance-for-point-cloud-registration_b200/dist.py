@@ -17,21 +17,29 @@ def shard_range(n_units, rank, world_size):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def global_mean(local_sum, local_count, group=None):
+def global_mean(local_sum, local_count, group=None, grad_reduction="sum"):
     """Mean over all ranks of per-unit values given this rank's sum and count: one all-reduce of a 2-vector.
-    Differentiable w.r.t. ``local_sum`` (the gradient of the global mean w.r.t. a local unit is 1 / global_count)."""
+    Differentiable w.r.t. ``local_sum``: the gradient w.r.t. a local unit is 1 / global_count, so the gradient of the
+    global mean w.r.t. shared parameters is the SUM of the ranks' gradients -- ``grad_reduction="sum"`` (default): the
+    caller all-reduces parameter gradients with ReduceOp.SUM.  ``torch.nn.parallel.DistributedDataParallel`` AVERAGES
+    them instead: pass ``grad_reduction="mean"`` there, which scales this rank's differentiable part by the world size so
+    that DDP's average is the single-process gradient (the returned value is the global mean either way)."""
+    if grad_reduction not in ("sum", "mean"):
+        raise ValueError("grad_reduction must be 'sum' or 'mean'")
     count = torch.as_tensor(float(local_count), dtype=local_sum.dtype, device=local_sum.device)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         tot = torch.stack([local_sum.detach(), count])
         dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+        scale = float(dist.get_world_size(group)) if grad_reduction == "mean" else 1.0
         # value: global; gradient: flows through the local contribution only
-        return (local_sum - local_sum.detach() + tot[0]) / tot[1]
+        return ((local_sum - local_sum.detach()) * scale + tot[0]) / tot[1]
     return local_sum / count
 
 
-def sharded_pair_loss(loss_fn, x, y, rank=None, world_size=None, group=None):
+def sharded_pair_loss(loss_fn, x, y, rank=None, world_size=None, group=None, grad_reduction="sum"):
     """Evaluate ``loss_fn(x_shard, y_shard) -> per-pair losses (b,)`` on this rank's slice of the batch and return the
-    global batch mean (what the reference's single-process ``emd / B`` returns)."""
+    global batch mean (what the reference's single-process ``emd / B`` returns).  ``grad_reduction``: see global_mean
+    ("mean" inside a DistributedDataParallel training loop, whose gradient all-reduce averages)."""
     if rank is None:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
     if world_size is None:
@@ -42,7 +50,7 @@ def sharded_pair_loss(loss_fn, x, y, rank=None, world_size=None, group=None):
         s = per_pair.sum()
     else:
         s = x.new_zeros(())
-    return global_mean(s, b1 - b0, group)
+    return global_mean(s, b1 - b0, group, grad_reduction)
 
 
 def sharded_slice_loss(slice_loss_fn, Xs, Xt, frames, rank=None, world_size=None, group=None):

@@ -12,14 +12,23 @@ from .. import ops
 
 
 def emd1D_circle(u_values, v_values, u_weights=None, v_weights=None, p=1, require_sort=True):
-    """Circular W1 (level median) per row: (S,n),(S,m) -> (S,).  Uniform weights, p == 1 (max_spherical_sliced_w.py:210-247)."""
-    if u_weights is not None or v_weights is not None:
-        raise NotImplementedError("non-uniform weights are not used on the reference's path")
+    """Circular W1 (level median) per row: (S,n),(S,m) -> (S,), p == 1 (max_spherical_sliced_w.py:210-247).  With
+    ``u_weights`` / ``v_weights`` ((n,) or (S,n); the reference gathers them through the sort permutations, :224-228) the
+    level median runs as the reference's four-sort composition on the device sort instead of the fused uniform kernel."""
     if p != 1:
         raise NotImplementedError("emd1D_circle implements p == 1 only, like the reference (it returns None otherwise)")
+    weighted = u_weights is not None or v_weights is not None
+    pu = pv = None
     if require_sort:
-        u_values, _ = ops.SegmentedSortFn.apply(u_values.contiguous().float())
-        v_values, _ = ops.SegmentedSortFn.apply(v_values.contiguous().float())
+        u_values, pu = ops.SegmentedSortFn.apply(u_values.contiguous().float())
+        v_values, pv = ops.SegmentedSortFn.apply(v_values.contiguous().float())
+    if weighted:
+        def sorted_w(w, perm):
+            if w is None:
+                return None
+            w = w.to(u_values.device)
+            return w[..., perm] if perm is not None else w  # (:227-228)
+        return ops.circular_w1_large(u_values.contiguous(), v_values.contiguous(), sorted_w(u_weights, pu), sorted_w(v_weights, pv))
     if u_values.shape[-1] + v_values.shape[-1] > ops.CIRCULAR_W1_MAX:
         return ops.circular_w1_large(u_values.contiguous(), v_values.contiguous())
     return ops.CircularW1Fn.apply(u_values.contiguous(), v_values.contiguous())
@@ -30,7 +39,9 @@ def binary_search_circle(u_values, v_values, u_weights=None, v_weights=None, p=1
     """Circular W_p^p per row by bisection on the rotation: (S,n),(S,m) -> (S,)  (max_spherical_sliced_w.py:117-207).
     Uniform weights.  Every round of the reference's host-synchronised loop runs inside one kernel launch."""
     if u_weights is not None or v_weights is not None:
-        raise NotImplementedError("non-uniform weights are not used on the reference's path")
+        raise NotImplementedError("binary_search_circle with non-uniform weights: the bisection kernel evaluates the uniform "
+                                  "CDFs in closed form; no caller in the reference passes weights (sliced_cost is always "
+                                  "called with u_weights=v_weights=None, max_spherical_sliced_w.py:518-533)")
     if require_sort:
         u_values, _ = ops.SegmentedSortFn.apply(u_values.contiguous().float())
         v_values, _ = ops.SegmentedSortFn.apply(v_values.contiguous().float())
@@ -42,7 +53,15 @@ def binary_search_circle(u_values, v_values, u_weights=None, v_weights=None, p=1
 def sliced_cost(Xs, Xt, Us, p=2, u_weights=None, v_weights=None):
     """(n,3),(m,3) clouds and (P,3,2) frames -> mean over slices of the circular W (max_spherical_sliced_w.py:251-286)."""
     if u_weights is not None or v_weights is not None:
-        raise NotImplementedError("non-uniform weights are not used on the reference's path")
+        if p != 1:
+            raise NotImplementedError("sliced_cost with non-uniform weights is supported for p == 1 (see binary_search_circle)")
+        xs, unb = ops._as_cloud(Xs, "Xs")
+        xt, _ = ops._as_cloud(Xt, "Xt")
+        ks = ops.ProjectCircleFn.apply(xs, Us.to(device=xs.device, dtype=torch.float32))  # (B,P,n)
+        kt = ops.ProjectCircleFn.apply(xt, Us.to(device=xs.device, dtype=torch.float32))
+        B, P, n = ks.shape
+        w = emd1D_circle(ks.reshape(B * P, n), kt.reshape(B * P, -1), u_weights, v_weights, p=1).reshape(B, P).mean(1)
+        return w.reshape(()) if unb else w
     w = ops.spherical_sliced_w1(Xs, Xt, Us) if p == 1 else ops.spherical_sliced_wp(Xs, Xt, Us, float(p))
     return w.reshape(()) if Xs.dim() == 2 else w
 

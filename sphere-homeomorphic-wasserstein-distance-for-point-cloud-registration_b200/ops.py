@@ -694,17 +694,24 @@ class SlicedLossFn(torch.autograd.Function):
 CIRCULAR_W1_MAX = 32768  # n + m the circular_w1 kernel takes per slice (512 threads x up to 64 merged entries each)
 
 
-def circular_w1_large(us, vs):
-    """emd1D_circle (max_spherical_sliced_w.py:230-247) on sorted rows us (S,n), vs (S,m) of ANY length, for slices
-    beyond CIRCULAR_W1_MAX: the reference's own four-sort formulation, with every sort done by the segmented radix sort
-    kernel (global-scratch path above 16384 keys) and the scans / gathers by torch device ops.  Differentiable w.r.t.
-    us / vs through the merged sort's permutation, like autograd through torch.sort."""
+def circular_w1_large(us, vs, uw=None, vw=None):
+    """emd1D_circle (max_spherical_sliced_w.py:230-247) on sorted rows us (S,n), vs (S,m) of ANY length and with ANY
+    weights: the reference's own four-sort formulation, with every sort done by the segmented radix sort kernel and the
+    scans / gathers by torch device ops.  Used for slices beyond CIRCULAR_W1_MAX and whenever weights are given (uw (S,n),
+    vw (S,m): the weights of the SORTED entries, :224-228; the fused level-median kernel evaluates uniform CDFs in closed
+    form).  Differentiable w.r.t. us / vs through the merged sort's permutation, like autograd through torch.sort, and
+    w.r.t. the weights through the cumulative sum."""
     S, n = us.shape
     m = vs.shape[1]
     merged, mperm = SegmentedSortFn.apply(torch.cat((us, vs), -1))  # stable: a u entry precedes an equal v entry
-    wts = torch.cat((torch.full((n,), 1 / n, dtype=torch.float32, device=us.device),
-                     -torch.full((m,), 1 / m, dtype=torch.float32, device=us.device)))
-    cdf_diff = torch.cumsum(wts[mperm], -1)
+    if uw is None and vw is None:
+        wts = torch.cat((torch.full((n,), 1 / n, dtype=torch.float32, device=us.device),
+                         -torch.full((m,), 1 / m, dtype=torch.float32, device=us.device)))
+        cdf_diff = torch.cumsum(wts[mperm], -1)
+    else:
+        uw = torch.full((S, n), 1 / n, dtype=torch.float32, device=us.device) if uw is None else uw.to(us.dtype).expand(S, n)
+        vw = torch.full((S, m), 1 / m, dtype=torch.float32, device=us.device) if vw is None else vw.to(us.dtype).expand(S, m)
+        cdf_diff = torch.cumsum(torch.gather(torch.cat((uw, -vw), -1), -1, mperm), -1)
     cdf_sorted, cperm = segmented_sort_raw(cdf_diff)
     delta = torch.cat((merged[:, 1:], torch.ones_like(merged[:, :1])), -1) - merged  # the arc [0, first) is omitted (:238-239)
     cw = torch.cumsum(torch.gather(delta.detach(), -1, cperm), -1) - 0.5

@@ -194,6 +194,7 @@ def main():
 
     make_wrapper_fixtures(ref_losses)
     make_notebook_fixture()
+    make_weighted_circle_fixture()
 
 
 def _flat_state(prefix, sd):
@@ -260,6 +261,23 @@ def make_wrapper_fixtures(ref_losses):
         print("max wrapper", name, "cswd", cswd.item(), "test", cswd_test.item())
 
 
+def make_weighted_circle_fixture():
+    """emd1D_circle with non-uniform weights (max_spherical_sliced_w.py:210-247, weights gathered through the sorts :224-228)."""
+    ssw = _load(os.path.join(REF, "Point_Cloud_Resistration/losses/max_spherical_sliced_w.py"), "ref_ssw_w")
+    g = torch.Generator().manual_seed(77)
+    u = torch.rand(6, 90, generator=g).requires_grad_(True)
+    v = torch.rand(6, 64, generator=g).requires_grad_(True)
+    uw = torch.rand(90, generator=g) + 0.1
+    uw = (uw / uw.sum()).requires_grad_(True)
+    vw = torch.rand(64, generator=g) + 0.1
+    vw = (vw / vw.sum()).requires_grad_(True)
+    w = ssw.emd1D_circle(u, v, u_weights=uw, v_weights=vw, p=1)
+    gu, gv, guw, gvw = torch.autograd.grad(w.sum(), (u, v, uw, vw))
+    np.savez(os.path.join(HERE, "emd1d_circle_weighted.npz"), u=u.detach().numpy(), v=v.detach().numpy(), uw=uw.detach().numpy(),
+             vw=vw.detach().numpy(), w=w.detach().numpy(), gu=gu.numpy(), gv=gv.numpy(), guw=guw.numpy(), gvw=gvw.numpy())
+    print("weighted emd1D_circle", w.detach().numpy()[:3])
+
+
 def make_notebook_fixture():
     """Row a11: the Euclidean sliced Wasserstein distance of the flow notebooks, by executing the SOURCE of cell 5 of
     Wasserstein_flow_problem/Flow_ellipsoid.ipynb (``rand_projections`` / ``sliced_wasserstein_distance``, raw JSON lines
@@ -296,5 +314,6 @@ if __name__ == "__main__":
         import losses as _ref_losses
         make_wrapper_fixtures(_ref_losses)
         make_notebook_fixture()
+        make_weighted_circle_fixture()
     else:
         main()

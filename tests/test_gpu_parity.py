@@ -538,6 +538,30 @@ def test_emd1d_circle_matches_reference_fixture(shwd):
     assert rel(u.grad, torch.from_numpy(d["gu"])) < TOL and rel(v.grad, torch.from_numpy(d["gv"])) < TOL
 
 
+def test_weighted_emd1d_circle_matches_reference_fixture(shwd):
+    """emd1D_circle with u_weights / v_weights (max_spherical_sliced_w.py:217-228): value and the gradients w.r.t. the
+    coordinates AND the weights against the unmodified reference; and sliced_cost(p=1, weights) through the same path."""
+    d = gold("emd1d_circle_weighted")
+    t = {k: torch.from_numpy(d[k]).to(dev()).requires_grad_(True) for k in ("u", "v", "uw", "vw")}
+    w = shwd.losses.emd1D_circle(t["u"], t["v"], u_weights=t["uw"], v_weights=t["vw"], p=1)
+    w.sum().backward()
+    errs = [rel(w, torch.from_numpy(d["w"]))] + [rel(t[k].grad, torch.from_numpy(d["g" + k])) for k in ("u", "v", "uw", "vw")]
+    print("weighted emd1D_circle: w %.2e gu %.2e gv %.2e guw %.2e gvw %.2e" % tuple(errs))
+    assert errs[0] < TOL and max(errs[1:]) < 2e-5
+    # uniform weights given explicitly == the fused uniform kernel
+    g = torch.Generator().manual_seed(3)
+    Xs = F.normalize(torch.randn(120, 3, generator=g), dim=-1).to(dev())
+    Xt = F.normalize(torch.randn(90, 3, generator=g) + 0.3, dim=-1).to(dev())
+    U, _ = torch.linalg.qr(torch.randn(7, 3, 2, generator=g))
+    U = U.to(dev())
+    a = shwd.losses.sliced_cost(Xs, Xt, U, p=1)
+    b = shwd.losses.sliced_cost(Xs, Xt, U, p=1, u_weights=torch.full((120,), 1 / 120, device=dev()),
+                                v_weights=torch.full((90,), 1 / 90, device=dev()))
+    assert rel(b, a) < TOL
+    with pytest.raises(NotImplementedError):
+        shwd.losses.sliced_cost(Xs, Xt, U, p=2, u_weights=torch.full((120,), 1 / 120, device=dev()))
+
+
 @pytest.mark.parametrize("S,n,m", [(5, 1, 1), (5, 7, 3), (4, 1024, 1024), (3, 1500, 1500), (3, 3000, 2500), (3, 4096, 4096),
                                    (2, 5000, 4800), (2, 5120, 5120), (2, 6000, 5000), (2, 8000, 8100), (2, 16000, 16500),
                                    (1, 16384, 16384), (1, 20000, 17000)])

@@ -152,6 +152,42 @@ def test_sharded_mean_equals_single_process_mean_world2_gloo():
     assert dict(out) == {0: True, 1: True}
 
 
+def _ddp_worker(rank, world, port, out):
+    """sharded_pair_loss inside a real DistributedDataParallel step: DDP AVERAGES parameter gradients over the ranks, so the
+    loss is built with grad_reduction="mean"; the averaged gradient must be the single-process gradient of the batch mean."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from shwd_b200.dist import sharded_pair_loss
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(3, 3)
+    ref = torch.nn.Linear(3, 3)
+    ref.load_state_dict(lin.state_dict())
+    model = torch.nn.parallel.DistributedDataParallel(lin)
+    x = torch.randn(5, 6, 3)
+    y = torch.randn(5, 6, 3)
+
+    def per_pair(a, b):
+        return ((a - b) ** 2).sum(dim=(1, 2))
+
+    loss = sharded_pair_loss(per_pair, model(x), y, grad_reduction="mean")
+    loss.backward()
+    want = per_pair(ref(x), y).mean()
+    want.backward()
+    ok = torch.allclose(loss.detach(), want.detach(), rtol=1e-6)
+    ok = ok and all(torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-7) for a, b in zip(lin.parameters(), ref.parameters()))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_loss_inside_ddp_averaging_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ddp_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
+
+
 def _slice_worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

@@ -239,3 +239,16 @@ def test_max_wrapper_step_matches_reference_on_cpu(name):
         got = phi.state_dict()[k]
         if v.dtype == torch.float32 and v.dim() > 0 and "last_" not in k and not k.endswith("scale"):
             assert torch.allclose(got, v, rtol=2e-4, atol=2e-6), (k, (got - v).abs().max().item())
+
+
+def test_oracle_weighted_emd1d_circle_matches_reference():
+    d = load("emd1d_circle_weighted")
+    u = torch.from_numpy(d["u"]).requires_grad_(True)
+    v = torch.from_numpy(d["v"]).requires_grad_(True)
+    uw = torch.from_numpy(d["uw"]).requires_grad_(True)
+    vw = torch.from_numpy(d["vw"]).requires_grad_(True)
+    w = oracle.emd1d_circle(u, v, u_weights=uw, v_weights=vw)
+    gu, gv, guw, gvw = torch.autograd.grad(w.sum(), (u, v, uw, vw))
+    assert rel(w.detach().numpy(), d["w"]) < 2e-6
+    for got, want in ((gu, "gu"), (gv, "gv"), (guw, "guw"), (gvw, "gvw")):
+        assert rel(got.numpy(), d[want]) < 2e-5
