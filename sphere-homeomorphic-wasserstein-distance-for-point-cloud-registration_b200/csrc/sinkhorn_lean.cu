@@ -79,34 +79,6 @@ __device__ __forceinline__ float4* lean_part(float4* smem4, const LeanGeom& gm, 
   return reinterpret_cast<float4*>(reinterpret_cast<float2*>(smem4) + (bwd ? 6 : 4) * (gm.T[0] + gm.T[1]));
 }
 
-// log2 of a positive, normal float32 as a double, accurate to ~1e-12 -- far inside what the float32 sum it is applied to
-// carries.  The library's double log2 is ~150 dependent instructions on the one warp every other CTA of the pair is
-// waiting for; this is ~20: exponent split, s = (f-1)/(f+1) with a float reciprocal seed and one Newton step,
-// 2 atanh(s) by its odd series through s^13 (|s| <= 0.172).
-__device__ __forceinline__ double lean_log2(float x) {
-  const int bits = __float_as_int(x);
-  int e = ((bits >> 23) & 0xff) - 127;
-  float f = __int_as_float((bits & 0x007fffff) | 0x3f800000);  // [1, 2)
-  if (f > 1.41421356f) {
-    f *= 0.5f;
-    e += 1;
-  }
-  const double fd = (double)f;
-  const double den = fd + 1.0;
-  double r = (double)__frcp_rn((float)den);
-  r = r * (2.0 - den * r);
-  const double t = (fd - 1.0) * r;
-  const double t2 = t * t;
-  double p = 1.0 / 13.0;
-  p = fma(p, t2, 1.0 / 11.0);
-  p = fma(p, t2, 1.0 / 9.0);
-  p = fma(p, t2, 1.0 / 7.0);
-  p = fma(p, t2, 1.0 / 5.0);
-  p = fma(p, t2, 1.0 / 3.0);
-  p = fma(p, t2, 1.0);
-  return fma(t * p, 2.8853900817779268, (double)e);  // 2 / ln 2
-}
-
 // packed position of streamed point q: record t = q mod T, half = q / T
 __device__ __forceinline__ int packed_pos(int q, int T) { return q >= T ? 2 * (q - T) + 1 : 2 * q; }
 
@@ -397,7 +369,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fwd_lean_kernel(const 
         PROF_MARK(3);
         if (owner) {
           // new potential in double, float32 rounding residual kept for the backward (see finalize_visit)
-          const double npd = (double)lconst - ((double)mx + lean_log2(sum));
+          const double npd = (double)lconst - ((double)mx + fast_log2d(sum));
           const float np = (float)npd;
           out_lo[o] = (float)(npd - (double)np);
           out_pot[o] = np;
