@@ -716,7 +716,7 @@ def circular_w1_large(us, vs, uw=None, vw=None):
     delta = torch.cat((merged[:, 1:], torch.ones_like(merged[:, :1])), -1) - merged  # the arc [0, first) is omitted (:238-239)
     cw = torch.cumsum(torch.gather(delta.detach(), -1, cperm), -1) - 0.5
     k = torch.argmin(torch.where(cw < 0, torch.full_like(cw, float("inf")), cw), dim=-1, keepdim=True)
-    lev_med = torch.gather(cdf_sorted, -1, k)
+    lev_med = torch.gather(cdf_diff, -1, torch.gather(cperm.long(), -1, k))  # = cdf_sorted[k], differentiable (weights)
     return torch.sum(delta * torch.abs(cdf_diff - lev_med), dim=-1)
 
 
