@@ -108,6 +108,17 @@ int shwd_chamfer_fwd(const float* x, const float* y, int B, int N, int M, float*
 /* gdx (B,N), gdy (B,M): upstream gradients of d_xy, d_yx.  gx (B,N,3), gy (B,M,3) are overwritten. */
 int shwd_chamfer_bwd(const float* x, const float* y, int B, int N, int M, const int* idx_xy, const int* idx_yx,
                      const float* gdx, const float* gdy, float* gx, float* gy, void* stream);
+/* The reductions of chamfer_distance (point_reduction / batch_reduction / single_directional of the call sites above) on
+ * the distances of shwd_chamfer_fwd, one launch, fixed summation order:  loss_b = sx * sum_i d_xy[b,i] + sy * sum_j d_yx[b,j];
+ * reduce_batch != 0: loss[0] = sb * sum_b loss_b, else loss[b] = loss_b.  ws: shwd_chamfer_reduce_workspace_bytes(B) bytes,
+ * zeroed once by the caller (the kernel re-arms it). */
+size_t shwd_chamfer_reduce_workspace_bytes(int B);
+int shwd_chamfer_reduce(const float* d_xy, const float* d_yx, int B, int N, int M, float sx, float sy, float sb,
+                        int reduce_batch, void* ws, float* loss, void* stream);
+/* Backward of that loss without per-point gradient tensors: d loss / d d_xy[b,:] = g[b * g_stride] * cx and
+ * d loss / d d_yx[b,:] = g[b * g_stride] * cy, g on the device (g_stride 0: one scalar, 1: one per pair). */
+int shwd_chamfer_bwd_uniform(const float* x, const float* y, int B, int N, int M, const int* idx_xy, const int* idx_yx,
+                             const float* g, int g_stride, float cx, float cy, float* gx, float* gy, void* stream);
 
 /* ---- sliced paths ------------------------------------------------------------------------------------------------
  * Circle projection (sliced_cost, max_spherical_sliced_w.py:270-279): x (B,N,3), U (P,3,2) -> keys (B,P,N) in [0,1]. */

@@ -32,6 +32,9 @@ SIGNATURES = {
     "shwd_sinkhorn_plan_dense": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "shwd_chamfer_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "shwd_chamfer_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "shwd_chamfer_reduce_workspace_bytes": (_sz, [_i]),
+    "shwd_chamfer_reduce": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp]),
+    "shwd_chamfer_bwd_uniform": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp]),
     "shwd_project_circle": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "shwd_project_circle_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "shwd_project_line": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),

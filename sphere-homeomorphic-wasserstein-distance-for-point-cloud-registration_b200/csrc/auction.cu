@@ -6,15 +6,32 @@
 // For uniform weights and n == m the LP optimum is attained at a permutation, so emd2 = (1/n) * min-assignment cost.
 // POT is a third-party dependency that is not vendored (version un-pinned): this solves the same LP by a different exact
 // method, Bertsekas' forward auction with epsilon-scaling, in float64 on the float32 cost values:
-//   * an unassigned person i bids for its best object j1 = argmax_j (-C_ij - price_j) the price
-//     price_j1 + (best - second best) + eps; every object goes to its highest bidder (ties: lowest person index), the
-//     previous owner becomes unassigned;  a phase ends when everybody is assigned;
+//   * an unassigned person i bids for its best object j1 = argmin_j w_ij, w_ij = C_ij + price_j, the price
+//     price_j1 + (second best w - best w) + eps; the previous owner becomes unassigned; a phase ends when everybody is
+//     assigned;
 //   * eps starts at Cmax/4 and is divided by 5 per phase down to Cmax * 2^-40, prices are kept between phases.  At the
 //     end the assignment is within n*eps of optimal -- far below one float32 ulp of the cost sum -- i.e. it is the
 //     optimum unless two assignments tie to ~1e-9 relative.
-// One CTA per pair; points, prices and the assignment live in shared memory; a warp serves one bidder at a time and
-// scans the objects with the same cost functor the Sinkhorn sweeps use (the N x N matrix is never formed).  Everything
-// is deterministic (no order-dependent atomics: bids are resolved by atomicMax on the price, then atomicMin on the index).
+//
+// What the first version of this kernel measured (one CTA per pair, every bidder scanning all N objects every round): a
+// 1024-point pair needs ~9 k rounds, nearly all of them "price wars" with one or two bidders, ~5 us each (five barriers, a
+// full scan) -> 46 ms per pair, latency-bound.  This version removes the scan and the barriers from those bids:
+//   * CANDIDATE LISTS.  Prices only rise (within and across phases), so w_ij only grows.  A full scan of person i stores
+//     the K objects with the smallest w (index + float32 cost, in shared memory) and Tw_i = the smallest w it did NOT
+//     store.  Later, as long as the second-smallest CURRENT w among the K listed objects is <= Tw_i, the list provably
+//     contains the person's best and second-best object overall, and a bid needs K shared-memory loads instead of N
+//     cost evaluations.  Lists are selected by a window [w1, max(w1 + delta_i, w2)] with a per-person adaptive delta_i.
+//   * GAUSS-SEIDEL BIDS IN ONE WARP.  Warp 0 pops unassigned persons from a ring buffer and serves them from their lists
+//     with warp-wide integer min-reductions (redux.sync on the bit patterns of the non-negative doubles w) -- no
+//     __syncthreads, ~0.15 us per bid.  A person whose list is exhausted is deferred to a rescan list R.
+//   * BATCHED RESCANS + ONE JACOBI ROUND.  When the queue is empty all 16 warps rescan the persons in R in parallel (one
+//     warp each: best / second best, new list, new Tw) against the same price vector, and those persons bid at once
+//     (a Jacobi round: one atomicMax per bid on (bid bits | slot), the winner takes the object).  Phases also start with
+//     one such parallel round served from the lists.  Large-eps phases (every bid moves a price by more than a list's
+//     window) therefore run as parallel rounds, small-eps price wars as barrier-free list bids.
+// Any unassigned person may bid in any order and any bidder may win an object (only eps-complementary slackness of the
+// assigned pairs and monotone prices are needed), so the result is exact in the same sense as before; everything is
+// deterministic (fixed orders, the only atomics are max on keys that embed the slot index).
 // Output: sigma (B, N) int32 with sigma[i] = object of person i.  The loss value and its gradient are assembled by the
 // caller from the n matched pairs (the plan has n non-zeros, d emd2 / dC = plan -- what POT attaches for autograd).
 #include "common.cuh"
@@ -29,33 +46,27 @@ constexpr int AU_WARPS = AU_THREADS / 32;
 #define SHWD_AU_EPS_FACTOR 0.2
 #endif
 constexpr double AU_EPS_FACTOR = SHWD_AU_EPS_FACTOR;  // epsilon is multiplied by this between phases
-constexpr int AU_MAX_ROUNDS = 4000000;  // safety net (a phase needs O(n) rounds in practice)
+constexpr long long AU_MAX_BIDS = 64ll << 20;  // safety net (a solve needs ~50 n bids in practice)
+constexpr int AU_RC = 512;        // rescanned persons per Jacobi round (their slot index rides in the low 9 bits of the bid key)
+constexpr int AU_MAX_N = 2048;    // person index rides in the low 11 bits of the phase-start bid key
+constexpr int AU_PP = AU_MAX_N / AU_THREADS;  // persons per thread in the phase-start round
+#ifndef SHWD_AU_LIST_EPS
+#define SHWD_AU_LIST_EPS 2.5e-3  // candidate lists are built once eps <= this fraction of Cmax
+#endif
+#ifndef SHWD_AU_DELTA0
+#define SHWD_AU_DELTA0 8.0
+#endif
 // FAST value of the dense variant: the cost is READ from a caller-supplied (B, N, N) matrix instead of being evaluated from
 // points -- the drop-in for ot.emd2(a, b, M) called on an explicit cost matrix (main_rotation.py:63-79 POT_loss; notebooks).
 constexpr int AU_DENSE = 1000;
+#ifdef SHWD_AU_PROFILE  // diagnostics build (tools/build_variant.sh): cycle counts per stage land in price_out[0..7]
+#define AU_PROF_T(v) const long long v = clock64()
+#define AU_PROF_ADD(acc, t0) acc += clock64() - t0
+#else
+#define AU_PROF_T(v)
+#define AU_PROF_ADD(acc, t0)
+#endif
 
-__device__ __forceinline__ unsigned long long au_key(double v) { return (unsigned long long)__double_as_longlong(v); }
-
-struct AuBest {
-  double v1, v2;
-  int j1;
-};
-__device__ __forceinline__ AuBest au_merge(const AuBest& a, const AuBest& b) {
-  AuBest r;
-  const bool takea = (a.v1 > b.v1) || (a.v1 == b.v1 && a.j1 <= b.j1);
-  if (takea) {
-    r.v1 = a.v1;
-    r.j1 = a.j1;
-    r.v2 = fmax(a.v2, b.v1);
-  } else {
-    r.v1 = b.v1;
-    r.j1 = b.j1;
-    r.v2 = fmax(b.v2, a.v1);
-  }
-  return r;
-}
-
-// One warp's scan of the objects j0, j0 + step, ... for a bidder at `o`: best and second-best value -C - price.
 template <int FAST>
 __device__ __forceinline__ float au_cost(const CostParams& cp, const float4 o, const float4* sY, const float* crow, int j) {
   if constexpr (FAST == AU_DENSE) {
@@ -66,184 +77,514 @@ __device__ __forceinline__ float au_cost(const CostParams& cp, const float4 o, c
     return CF::kc(cp, CF::eval(cp, o.x, o.y, o.z, t.x, t.y, t.z));
   }
 }
-template <int FAST>
-__device__ __forceinline__ AuBest au_scan(const CostParams& cp, const float4 o, const float4* sY, const float* crow,
-                                          const double* price, int N, int j0, int step) {
-  AuBest best = {-INFINITY, -INFINITY, INT_MAX};
-  for (int j = j0; j < N; j += step) {
-    const double v = -(double)au_cost<FAST>(cp, o, sY, crow, j) - price[j];
-    if (v > best.v1) {
-      best.v2 = best.v1;
-      best.v1 = v;
-      best.j1 = j;
-    } else if (v > best.v2) {
-      best.v2 = v;
-    }
+
+struct AuBest {  // smallest and second-smallest w of a scan, the object and plain cost of the smallest
+  double w1, w2;
+  int j1;
+  float c1;
+};
+__device__ __forceinline__ AuBest au_merge(const AuBest& a, const AuBest& b) {
+  AuBest r;
+  const bool takea = (a.w1 < b.w1) || (a.w1 == b.w1 && a.j1 <= b.j1);
+  if (takea) {
+    r.w1 = a.w1;
+    r.j1 = a.j1;
+    r.c1 = a.c1;
+    r.w2 = fmin(a.w2, b.w1);
+  } else {
+    r.w1 = b.w1;
+    r.j1 = b.j1;
+    r.c1 = b.c1;
+    r.w2 = fmin(b.w2, a.w1);
   }
+  return r;
+}
+
+struct AuShared {
+  float4* sY;                  // N   packed points of the object cloud (unused by the dense variant)
+  double* price;               // N
+  unsigned long long* bidval;  // N   highest (bid bits | slot) per object in a Jacobi round (0: none)
+  double* Tw;                  // N   smallest w the person's last scan did NOT list (-inf: no list yet)
+  float* delta;                // N   the person's list window
+  int* owner;                  // N   person holding object j (-1: free)
+  int* queue;                  // N   ring buffer of unassigned persons with a (possibly) usable list
+  int* R;                      // N   persons whose list is exhausted: to be rescanned
+  unsigned short* lidx;        // N*K listed objects (0xFFFF: empty slot)
+  float* lcost;                // N*K their plain costs
+  double* rbid;                // AU_RC  bid of a rescanned person
+  int* rj;                     // AU_RC  its object
+};
+
+// ---- full scans of person i by one warp against the current prices (four objects per lane in flight, branch-free) ----
+__device__ __forceinline__ AuBest au_warp_merge(AuBest best) {
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
     AuBest other;
-    other.v1 = __shfl_xor_sync(0xffffffffu, best.v1, s);
-    other.v2 = __shfl_xor_sync(0xffffffffu, best.v2, s);
+    other.w1 = __shfl_xor_sync(0xffffffffu, best.w1, s);
+    other.w2 = __shfl_xor_sync(0xffffffffu, best.w2, s);
     other.j1 = __shfl_xor_sync(0xffffffffu, best.j1, s);
+    other.c1 = __shfl_xor_sync(0xffffffffu, best.c1, s);
     best = au_merge(best, other);
+  }
+  if (best.j1 == INT_MAX) best.j1 = 0;  // (cannot happen for finite costs; keeps indices in range)
+  return best;
+}
+__device__ __forceinline__ void au_top2_update(AuBest& best, double w, int j, float c) {
+  const bool lt = w < best.w1;
+  best.w2 = fmin(best.w2, lt ? best.w1 : w);
+  best.j1 = lt ? j : best.j1;
+  best.c1 = lt ? c : best.c1;
+  best.w1 = lt ? w : best.w1;
+}
+// best and second best only (the large-eps phases: every bid moves a price by more than a list window, lists are useless)
+template <int FAST>
+__device__ __forceinline__ AuBest au_scan_top2(const CostParams& cp, const AuShared& S, const float4 o, const float* crow,
+                                               double cshift, int N, int lane) {
+  AuBest best = {INFINITY, INFINITY, INT_MAX, 0.f};
+  for (int j0 = lane; j0 < N; j0 += 128) {
+    float c[4];
+    double p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u;
+      const bool ok = j < N;
+      c[u] = ok ? au_cost<FAST>(cp, o, S.sY, crow, ok ? j : 0) : 0.f;
+      p[u] = ok ? S.price[j] : (double)INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) au_top2_update(best, ((double)c[u] - cshift) + p[u], j0 + 32 * u, c[u]);
+  }
+  return au_warp_merge(best);
+}
+// One collecting pass: every object with w <= cut goes into the person's list in index order (at most K; j1k >= 0: that
+// object is known to be the best, it is skipped here and owns slot 0), tmin = smallest w NOT stored, cnt = how many
+// qualified; TRACK: also the exact best / second best over all objects (valid whenever cut >= the true second best).
+template <int FAST, bool TRACK>
+__device__ __forceinline__ void au_scan_collect(const CostParams& cp, const AuShared& S, const float4 o, const float* crow,
+                                                double cshift, int N, int K, int i, int lane, double cut, int j1k, int& cnt,
+                                                double& tmin, AuBest& best) {
+  unsigned short* li = S.lidx + (size_t)i * K;
+  float* lc = S.lcost + (size_t)i * K;
+  const unsigned lt = (1u << lane) - 1u;
+  cnt = j1k >= 0 ? 1 : 0;
+  tmin = INFINITY;
+  for (int j0 = lane; j0 < N + lane; j0 += 128) {  // (+ lane: every lane runs the same number of ballots)
+    float c[4];
+    double p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u;
+      const bool ok = j < N;
+      c[u] = ok ? au_cost<FAST>(cp, o, S.sY, crow, ok ? j : 0) : 0.f;
+      p[u] = ok ? S.price[j] : (double)INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u;
+      const double w = ((double)c[u] - cshift) + p[u];
+      if (TRACK) au_top2_update(best, w, j, c[u]);
+      const bool other = j < N && j != j1k;
+      const bool take = other && w <= cut;
+      const unsigned b = __ballot_sync(0xffffffffu, take);
+      const int pos = cnt + __popc(b & lt);
+      const bool st = take && pos < K;
+      if (st) {
+        li[pos] = (unsigned short)j;
+        lc[pos] = c[u];
+      }
+      tmin = (other && !st) ? fmin(tmin, w) : tmin;
+      cnt += __popc(b);
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, s));
+}
+// A rescan that also rebuilds the candidate list.  guess: an upper bound of the person's true second-best w (the second
+// best of its exhausted list), or non-finite when there is none: with a guess the list is cut at guess + delta_i and ONE
+// pass finds the exact best / second best and the list; otherwise (or when more than K objects qualify) the cut comes from
+// the exact values: max(w1 + delta_i, w2), then w2 itself.
+template <int FAST>
+__device__ __forceinline__ AuBest au_rescan(const CostParams& cp, const AuShared& S, const float4 o, const float* crow,
+                                            double cshift, int N, int K, int i, int lane) {
+  float dl = S.delta[i];
+  const double guess = S.Tw[i];
+  AuBest best = {INFINITY, INFINITY, INT_MAX, 0.f};
+  int cnt = 0;
+  double tmin = INFINITY;
+  bool done = false;
+  if (guess > -INFINITY && guess < INFINITY) {
+    const double cut = guess + (double)dl;
+    au_scan_collect<FAST, true>(cp, S, o, crow, cshift, N, K, i, lane, cut, -1, cnt, tmin, best);
+    best = au_warp_merge(best);
+    done = cnt <= K && best.w2 <= cut;  // (prices may have risen past the guess since it was taken)
+    if (!done) dl *= 0.125f;
+  } else {
+    best = au_scan_top2<FAST>(cp, S, o, crow, cshift, N, lane);
+  }
+  unsigned short* li = S.lidx + (size_t)i * K;
+  if (!done) {
+    AuBest dummy = best;
+    au_scan_collect<FAST, false>(cp, S, o, crow, cshift, N, K, i, lane, fmax(best.w1 + (double)dl, best.w2), best.j1, cnt, tmin, dummy);
+    if (cnt > K) {
+      dl *= 0.125f;
+      au_scan_collect<FAST, false>(cp, S, o, crow, cshift, N, K, i, lane, best.w2, best.j1, cnt, tmin, dummy);
+    }
+    if (lane == 0) {
+      li[0] = (unsigned short)best.j1;
+      S.lcost[(size_t)i * K] = best.c1;
+    }
+  }
+  if (cnt <= K / 2) dl *= 2.f;
+  for (int k = cnt + lane; k < K; k += 32) li[k] = 0xFFFFu;
+  if (lane == 0) {
+    S.Tw[i] = tmin;
+    S.delta[i] = dl;
   }
   return best;
 }
-__device__ __forceinline__ void au_bid(AuBest best, double eps, const double* price, int idx, int* lobj, double* lbid,
-                                       unsigned long long* bidval) {
-  if (best.j1 == INT_MAX) best.j1 = 0;  // every value NaN (non-finite input): keep the indices in range
-  const double gap = (best.v2 == -INFINITY) ? 0.0 : best.v1 - best.v2;  // N == 1: no second best
-  const double bid = price[best.j1] + gap + eps;
-  lobj[idx] = best.j1;
-  lbid[idx] = bid;
-  atomicMax(bidval + best.j1, au_key(bid));  // prices are >= 0 and only rise: the bit pattern orders like the value
+
+// Smallest and second-smallest of one non-negative double per lane (+inf: no entry), by integer min-reductions on the bit
+// patterns (non-negative doubles order like their bits).  l1 = lowest lane holding the smallest.
+__device__ __forceinline__ void au_top2(double w, int lane, double& w1, double& w2, int& l1) {
+  const unsigned long long kb = (unsigned long long)__double_as_longlong(w);
+  unsigned hi = (unsigned)(kb >> 32), lo = (unsigned)kb;
+  const unsigned m1h = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned m1l = __reduce_min_sync(0xffffffffu, hi == m1h ? lo : 0xffffffffu);
+  l1 = __ffs(__ballot_sync(0xffffffffu, hi == m1h && lo == m1l)) - 1;
+  if (lane == l1) {
+    hi = 0xffffffffu;
+    lo = 0xffffffffu;
+  }
+  const unsigned m2h = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned m2l = __reduce_min_sync(0xffffffffu, hi == m2h ? lo : 0xffffffffu);
+  w1 = __longlong_as_double((long long)(((unsigned long long)m1h << 32) | m1l));
+  w2 = (m2h == 0xffffffffu) ? (double)INFINITY : __longlong_as_double((long long)(((unsigned long long)m2h << 32) | m2l));
 }
 
 template <int FAST>
-__global__ void __launch_bounds__(AU_THREADS) auction_kernel(const float4* __restrict__ X, const float4* __restrict__ Y,
-                                                             const float* __restrict__ Cd, int N, CostParams cp,
+__global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __restrict__ X, const float4* __restrict__ Y,
+                                                             const float* __restrict__ Cd, int N, int K, CostParams cp,
                                                              int* __restrict__ sigma, double* __restrict__ price_out,
                                                              int* __restrict__ rounds_out, int* __restrict__ status) {
   constexpr bool DENSE = FAST == AU_DENSE;
-  extern __shared__ float4 au_smem[];  // carved in decreasing alignment: float4, 8-byte, 4-byte arrays
-  float4* sX = au_smem;                                               // N
-  float4* sY = sX + N;                                                // N
-  double* price = reinterpret_cast<double*>(sY + N);                  // N
-  double* lbid = price + N;                                           // N   bid of list entry
-  unsigned long long* bidval = reinterpret_cast<unsigned long long*>(lbid + N);  // N   highest bid per object (0: none)
-  int* owner = reinterpret_cast<int*>(bidval + N);                        // N   person holding object j (-1: free)
-  int* objof = owner + N;                                             // N   object of person i (-1: unassigned)
-  int* bidder = objof + N;                                            // N   winning person per object this round
-  int* list = bidder + N;                                             // N   unassigned persons
-  int* lobj = list + N;                                               // N   best object of list entry
-  int* list2 = lobj + N;                                              // N   next round's unassigned persons
-  __shared__ int s_count;
-  __shared__ AuBest s_part[AU_WARPS];
-  __shared__ double s_red[AU_WARPS];
+  extern __shared__ float4 au_smem[];  // carved in decreasing alignment: float4, 8-byte, 4-byte, 2-byte arrays
+  AuShared S;
+  S.sY = au_smem;
+  S.price = reinterpret_cast<double*>(S.sY + (DENSE ? 0 : N));
+  S.bidval = reinterpret_cast<unsigned long long*>(S.price + N);
+  S.Tw = reinterpret_cast<double*>(S.bidval + N);
+  S.rbid = S.Tw + N;
+  S.delta = reinterpret_cast<float*>(S.rbid + AU_RC);
+  S.lcost = S.delta + N;
+  S.owner = reinterpret_cast<int*>(S.lcost + (size_t)N * K);
+  S.queue = S.owner + N;
+  S.R = S.queue + N;
+  S.rj = S.R + N;
+  S.lidx = reinterpret_cast<unsigned short*>(S.rj + AU_RC);
+  __shared__ double s_red[AU_WARPS], s_red2[AU_WARPS];
+  __shared__ int s_ctl[4];  // nR, queue head, queue count, failed
   const int b = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4* Xb = DENSE ? nullptr : X + (size_t)b * N;
   const float* Cb = DENSE ? Cd + (size_t)b * N * N : nullptr;  // row i of this pair's matrix: Cb + i * N
-  for (int i = threadIdx.x; i < N; i += AU_THREADS) {
-    sX[i] = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(X + (size_t)b * N + i);
-    sY[i] = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(Y + (size_t)b * N + i);
-    price[i] = 0.0;
-    bidval[i] = 0ull;
-    bidder[i] = INT_MAX;
+  for (int i = tid; i < N; i += AU_THREADS) {
+    if (!DENSE) S.sY[i] = __ldg(Y + (size_t)b * N + i);
+    S.price[i] = 0.0;
+    S.bidval[i] = 0ull;
+    S.Tw[i] = -INFINITY;
+    S.owner[i] = -1;
   }
   __syncthreads();
-  // Cmax = max_ij kC_ij (sets the epsilon schedule)
-  float cm = 0.f;
+  // Cmax = max_ij C_ij sets the epsilon schedule; Cmin < 0 (possible for a caller-supplied matrix only) is shifted away so
+  // that every w = C - shift + price is a non-negative double
+  float cm = 0.f, cn = 0.f;
   bool nonfinite = false;
   for (int i = warp; i < N; i += AU_WARPS) {
-    const float4 o = sX[i];
+    const float4 o = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(Xb + i);
     for (int j = lane; j < N; j += 32) {
-      const float cij = au_cost<FAST>(cp, o, sY, DENSE ? Cb + (size_t)i * N : nullptr, j);
+      const float cij = au_cost<FAST>(cp, o, S.sY, DENSE ? Cb + (size_t)i * N : nullptr, j);
       nonfinite = nonfinite || !(fabsf(cij) <= 3.0e38f);
       cm = fmaxf(cm, cij);
+      cn = fminf(cn, cij);
     }
   }
   cm = warp_max(cm);
-  if (lane == 0) s_red[warp] = (double)cm;
+  cn = -warp_max(-cn);
+  if (lane == 0) {
+    s_red[warp] = (double)cm;
+    s_red2[warp] = (double)cn;
+  }
   if (__syncthreads_or(nonfinite)) {
-    // a NaN / infinite cost (a diverged model upstream): no assignment is meaningful and the bidding would run to
-    // AU_MAX_ROUNDS.  Report failure at once; sigma = identity keeps every downstream gather in range.
-    for (int i = threadIdx.x; i < N; i += AU_THREADS) {
+    // a NaN / infinite cost (a diverged model upstream): no assignment is meaningful.  Report failure at once;
+    // sigma = identity keeps every downstream gather in range.
+    for (int i = tid; i < N; i += AU_THREADS) {
       sigma[(size_t)b * N + i] = i;
       if (price_out) price_out[(size_t)b * N + i] = 0.0;
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       if (rounds_out) rounds_out[b] = 0;
       atomicExch(status, 1);
     }
     return;
   }
-  double cmax = 0.0;
-  for (int w = 0; w < AU_WARPS; ++w) cmax = fmax(cmax, s_red[w]);
-  if (!(cmax > 0.0)) cmax = 1.0;  // all costs zero (or NaN): any assignment is optimal; run one trivial phase
-  const double eps_final = cmax * 9.094947017729282e-13;  // 2^-40
-  int rounds = 0;
-  bool failed = false;
-  int* cur = list;    // unassigned persons of this round
-  int* nxt = list2;   // ... of the next round (built incrementally from the losers and the displaced owners)
-  for (double eps = cmax * 0.25;; eps = fmax(eps * AU_EPS_FACTOR, eps_final)) {
-    // ---- a phase: everybody unassigned, prices kept
-    __syncthreads();
-    for (int i = threadIdx.x; i < N; i += AU_THREADS) {
-      owner[i] = -1;
-      objof[i] = -1;
-      cur[i] = i;
+  double cmax = 0.0, cshift = 0.0;
+  for (int w = 0; w < AU_WARPS; ++w) {
+    cmax = fmax(cmax, s_red[w]);
+    cshift = fmin(cshift, s_red2[w]);
+  }
+  cmax -= cshift;
+  if (!(cmax > 0.0)) cmax = 1.0;  // all costs equal: any assignment is optimal; run one trivial phase
+  if (N == 1) {
+    if (tid == 0) {
+      sigma[(size_t)b] = 0;
+      if (price_out) price_out[(size_t)b] = 0.0;
+      if (rounds_out) rounds_out[b] = 0;
     }
-    int U = N;
-    for (;;) {
-      __syncthreads();
-      if (U == 0) break;
-      if (++rounds > AU_MAX_ROUNDS) {
-        failed = true;
-        break;
-      }
-      if (threadIdx.x == 0) s_count = 0;
-      // ---- bidding.  Many bidders: one warp each.  Few bidders (the long tail of a phase): wpb warps share a bidder's
-      // scan and their partial (best, second best) are merged through shared memory.
-      int wpb = 1;
-      while (wpb * 2 * U <= AU_WARPS) wpb *= 2;
-      if (wpb == 1) {
-        for (int idx = warp; idx < U; idx += AU_WARPS) {
-          const AuBest best = au_scan<FAST>(cp, sX[cur[idx]], sY, DENSE ? Cb + (size_t)cur[idx] * N : nullptr, price, N, lane, 32);
-          if (lane == 0) au_bid(best, eps, price, idx, lobj, lbid, bidval);
+    return;
+  }
+  for (int i = tid; i < N; i += AU_THREADS) S.delta[i] = (float)(SHWD_AU_DELTA0 * cmax / N);
+  const double eps_final = cmax * 9.094947017729282e-13;  // 2^-40
+#ifdef SHWD_AU_PROFILE
+  long long pf_start = 0, pf_gs = 0, pf_rescan = 0, pf_apply = 0, pf_nresc = 0, pf_nlist = 0, pf_rounds = 0;
+#endif
+  long long bids = 0;  // (warp 0's count of list bids + every thread's view of the parallel rounds is not needed: info only)
+  int failed = 0;
+  for (double eps = cmax * 0.25;; eps = fmax(eps * AU_EPS_FACTOR, eps_final)) {
+    const bool lists = eps <= cmax * SHWD_AU_LIST_EPS;  // larger eps: plain parallel rounds of full scans
+    // ================= phase start: everybody unassigned, prices and lists kept; one parallel round from the lists
+    __syncthreads();
+    AU_PROF_T(t_start);
+    for (int i = tid; i < N; i += AU_THREADS) S.owner[i] = -1;
+    int pj[AU_PP];
+    double pbid[AU_PP];
+#pragma unroll
+    for (int q = 0; q < AU_PP; ++q) {
+      const int i = tid + q * AU_THREADS;
+      pj[q] = -1;
+      if (i < N) {
+        const unsigned short* li = S.lidx + (size_t)i * K;
+        const float* lc = S.lcost + (size_t)i * K;
+        const double tw = S.Tw[i];
+        if (tw > -INFINITY) {
+          double w1 = INFINITY, w2 = INFINITY, p1 = 0.0;
+          int j1 = -1;
+          for (int k = 0; k < K; ++k) {
+            const int j = li[k];
+            if (j == 0xFFFF) break;
+            const double p = S.price[j];
+            const double w = ((double)lc[k] - cshift) + p;
+            if (w < w1) {
+              w2 = w1;
+              w1 = w;
+              j1 = j;
+              p1 = p;
+            } else if (w < w2) {
+              w2 = w;
+            }
+          }
+          if (w2 <= tw) {
+            pj[q] = j1;
+            pbid[q] = p1 + (w2 - w1) + eps;
+          } else {
+            S.Tw[i] = w2;  // cut guess for the rescan
+          }
         }
-      } else {
-        const int idx = warp / wpb, sub = warp % wpb;
-        if (idx < U) {
-          const AuBest best = au_scan<FAST>(cp, sX[cur[idx]], sY, DENSE ? Cb + (size_t)cur[idx] * N : nullptr, price, N, sub * 32 + lane, 32 * wpb);
-          if (lane == 0) s_part[warp] = best;
+      }
+    }
+    __syncthreads();  // (owner reset above is complete; bids go in)
+#pragma unroll
+    for (int q = 0; q < AU_PP; ++q) {
+      const int i = tid + q * AU_THREADS;
+      if (pj[q] >= 0)
+        atomicMax(S.bidval + pj[q], ((unsigned long long)__double_as_longlong(pbid[q]) & ~0x7FFull) | (unsigned long long)(AU_MAX_N - 1 - i));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < AU_PP; ++q) {
+      const int i = tid + q * AU_THREADS;
+      if (i < N) {
+        int flag = 2;  // no usable list: rescan
+        if (pj[q] >= 0) {
+          if ((int)(S.bidval[pj[q]] & 0x7FFull) == AU_MAX_N - 1 - i) {
+            S.owner[pj[q]] = i;
+            S.price[pj[q]] = pbid[q];
+            flag = 0;
+          } else {
+            flag = 1;  // lost: bids again from its list
+          }
+        }
+        S.R[i] = flag;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < AU_PP; ++q)
+      if (pj[q] >= 0) S.bidval[pj[q]] = 0ull;
+    int qhead = 0, qcount = 0, nR = 0;  // warp 0's registers
+    if (warp == 0) {
+      // ordered compaction of the flags (read from R in batches before R is overwritten below the read position)
+      for (int base = 0; base < N; base += 32) {
+        const int i = base + lane;
+        const int flag = i < N ? S.R[i] : 0;
+        const unsigned b1 = __ballot_sync(0xffffffffu, flag == 1), b2 = __ballot_sync(0xffffffffu, flag == 2);
+        const unsigned lt = (1u << lane) - 1u;
+        __syncwarp();
+        if (flag == 1) S.queue[qcount + __popc(b1 & lt)] = i;
+        if (flag == 2) S.R[nR + __popc(b2 & lt)] = i;
+        qcount += __popc(b1);
+        nR += __popc(b2);
+        __syncwarp();
+      }
+    }
+    AU_PROF_ADD(pf_start, t_start);
+    // ================= the phase: list bids by warp 0, batched rescans + a Jacobi round by everybody
+    for (;;) {
+      AU_PROF_T(t_gs);
+      if (warp == 0) {
+        __syncwarp();
+        while (qcount > 0) {
+          const int i = S.queue[qhead];
+          qhead = (qhead + 1 == N) ? 0 : qhead + 1;
+          --qcount;
+          if (!lists) {  // no lists in the large-eps phases: straight to the next parallel round
+            if (lane == 0) S.R[nR] = i;
+            ++nR;
+            continue;
+          }
+          int j = 0xFFFF;
+          float c = 0.f;
+          if (lane < K) {
+            j = S.lidx[(size_t)i * K + lane];
+            c = S.lcost[(size_t)i * K + lane];
+          }
+          double p = 0.0, w = INFINITY;
+          int own = -1;
+          if (j != 0xFFFF) {
+            p = S.price[j];
+            own = S.owner[j];
+            w = ((double)c - cshift) + p;
+          }
+          const double tw = S.Tw[i];
+          double w1, w2;
+          int l1;
+          au_top2(w, lane, w1, w2, l1);
+          if (!(w2 <= tw)) {  // list exhausted: the best or second best may be an unlisted object
+            if (lane == 0) {
+              S.R[nR] = i;
+              S.Tw[i] = w2;  // the rescan's cut guess: the true second best is <= the listed one (+inf: none)
+            }
+            ++nR;
+            continue;
+          }
+          if (lane == l1) {
+            S.price[j] = p + (w2 - w1) + eps;
+            S.owner[j] = i;
+          }
+          const int old = __shfl_sync(0xffffffffu, own, l1);
+          if (old >= 0) {
+            int qt = qhead + qcount;
+            if (qt >= N) qt -= N;
+            if (lane == 0) S.queue[qt] = old;
+            ++qcount;
+          }
+          __syncwarp();
+#ifdef SHWD_AU_PROFILE
+          ++pf_nlist;
+#endif
+          if (++bids > AU_MAX_BIDS) {
+            failed = 1;
+            break;
+          }
+        }
+        if (lane == 0) {
+          s_ctl[0] = nR;
+          s_ctl[3] = failed;
+        }
+      }
+      __syncthreads();
+      AU_PROF_ADD(pf_gs, t_gs);
+#ifdef SHWD_AU_PROFILE
+      ++pf_rounds;
+#endif
+      const int nRall = s_ctl[0];
+      failed = s_ctl[3];
+      if (nRall == 0 || failed) break;
+      for (int c0 = 0; c0 < nRall; c0 += AU_RC) {
+        const int nC = min(AU_RC, nRall - c0);
+        AU_PROF_T(t_rs);
+        for (int r = warp; r < nC; r += AU_WARPS) {
+          const int i = S.R[c0 + r];
+          const float4 o = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(Xb + i);
+          const float* crow = DENSE ? Cb + (size_t)i * N : nullptr;
+          const AuBest best = lists ? au_rescan<FAST>(cp, S, o, crow, cshift, N, K, i, lane)
+                                    : au_scan_top2<FAST>(cp, S, o, crow, cshift, N, lane);
+          if (lane == 0) {
+            const double bid = S.price[best.j1] + (best.w2 - best.w1) + eps;
+            S.rj[r] = best.j1;
+            S.rbid[r] = bid;
+            atomicMax(S.bidval + best.j1, ((unsigned long long)__double_as_longlong(bid) & ~0x1FFull) | (unsigned long long)(AU_RC - 1 - r));
+          }
         }
         __syncthreads();
-        if (threadIdx.x < U) {
-          AuBest best = s_part[threadIdx.x * wpb];
-          for (int q = 1; q < wpb; ++q) best = au_merge(best, s_part[threadIdx.x * wpb + q]);
-          au_bid(best, eps, price, threadIdx.x, lobj, lbid, bidval);
-        }
-      }
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < U; idx += AU_THREADS)
-        if (au_key(lbid[idx]) == bidval[lobj[idx]]) atomicMin(bidder + lobj[idx], cur[idx]);
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < U; idx += AU_THREADS) {
-        const int j = lobj[idx], i = cur[idx];
-        if (bidder[j] == i) {
-          const int old = owner[j];
-          if (old >= 0) {
-            objof[old] = -1;
-            nxt[atomicAdd(&s_count, 1)] = old;
+        AU_PROF_ADD(pf_rescan, t_rs);
+        AU_PROF_T(t_ap);
+        if (warp == 0) {
+          for (int base = 0; base < nC; base += 32) {
+            const int r = base + lane;
+            const bool valid = r < nC;
+            int i = -1, j = 0, old = -1;
+            bool win = false;
+            if (valid) {
+              i = S.R[c0 + r];
+              j = S.rj[r];
+              win = (int)(S.bidval[j] & 0x1FFull) == AU_RC - 1 - r;
+              if (win) {
+                old = S.owner[j];
+                S.owner[j] = i;
+                S.price[j] = S.rbid[r];
+              }
+            }
+            const bool app = valid && (!win || old >= 0);  // losers bid again from their fresh lists; displaced owners too
+            const unsigned ba = __ballot_sync(0xffffffffu, app);
+            if (app) {
+              int qt = qhead + qcount + __popc(ba & ((1u << lane) - 1u));
+              if (qt >= N) qt -= N;
+              S.queue[qt] = win ? old : i;
+            }
+            qcount += __popc(ba);
           }
-          owner[j] = i;
-          objof[i] = j;
-          price[j] = lbid[idx];
-        } else {
-          nxt[atomicAdd(&s_count, 1)] = i;
+          __syncwarp();
+          for (int r = lane; r < nC; r += 32) S.bidval[S.rj[r]] = 0ull;
+          bids += nC;
         }
+        __syncthreads();
+        AU_PROF_ADD(pf_apply, t_ap);
+#ifdef SHWD_AU_PROFILE
+        pf_nresc += nC;
+#endif
       }
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < U; idx += AU_THREADS) {
-        bidval[lobj[idx]] = 0ull;
-        bidder[lobj[idx]] = INT_MAX;
-      }
-      U = s_count;
-      int* t = cur;
-      cur = nxt;
-      nxt = t;
+      nR = 0;
     }
     if (failed || eps <= eps_final) break;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < N; i += AU_THREADS) {
-    sigma[(size_t)b * N + i] = failed ? i : objof[i];  // (a failed solve leaves persons unassigned: keep indices in range)
-    if (price_out) price_out[(size_t)b * N + i] = price[i];
+  if (failed) {
+    for (int i = tid; i < N; i += AU_THREADS) sigma[(size_t)b * N + i] = i;  // (keep indices in range)
+  } else {
+    for (int j = tid; j < N; j += AU_THREADS) sigma[(size_t)b * N + S.owner[j]] = j;
   }
-  if (threadIdx.x == 0) {
-    if (rounds_out) rounds_out[b] = rounds;
+  for (int i = tid; i < N; i += AU_THREADS)
+    if (price_out) price_out[(size_t)b * N + i] = S.price[i];
+  if (tid == 0) {
+    if (rounds_out) rounds_out[b] = (int)(bids > INT_MAX ? INT_MAX : bids);
     if (failed) atomicExch(status, 1);
+#ifdef SHWD_AU_PROFILE
+    if (price_out && N >= 8) {
+      double* po = price_out + (size_t)b * N;
+      po[0] = (double)pf_start; po[1] = (double)pf_gs; po[2] = (double)pf_rescan; po[3] = (double)pf_apply;
+      po[4] = (double)pf_nresc; po[5] = (double)pf_nlist; po[6] = (double)pf_rounds;
+    }
+#endif
   }
 }
 
@@ -251,13 +592,21 @@ __global__ void __launch_bounds__(AU_THREADS) auction_kernel(const float4* __res
 
 using namespace shwd;
 
-static size_t auction_smem(int N) {
-  return (size_t)N * (2 * sizeof(double) + sizeof(unsigned long long) + 2 * sizeof(float4) + 6 * sizeof(int));
+static size_t auction_smem(int N, int K, bool dense) {
+  return (size_t)N * ((dense ? 0 : sizeof(float4)) + 3 * sizeof(double) + sizeof(float) + 3 * sizeof(int) +
+                      (size_t)K * (sizeof(float) + sizeof(unsigned short))) +
+         AU_RC * (sizeof(double) + sizeof(int)) + 16;
+}
+constexpr size_t AU_SMEM_BUDGET = 226 * 1024;
+// list width: 16 candidates per person where they fit next to the points, 8 for the largest clouds
+static int auction_list_width(int N, bool dense) {
+  if (auction_smem(N, 16, dense) <= AU_SMEM_BUDGET) return 16;
+  return 8;
 }
 
 extern "C" int shwd_exact_assignment_max_points(void) {
   int n = 1;
-  while (auction_smem(n + 1) <= 220 * 1024) ++n;
+  while (n < AU_MAX_N && auction_smem(n + 1, 8, false) <= AU_SMEM_BUDGET) ++n;
   return n;
 }
 
@@ -267,8 +616,9 @@ extern "C" int shwd_exact_assignment(const float* x4, const float* y4, int B, in
     return SHWD_ERR_INVALID_ARGUMENT;
   if ((reinterpret_cast<uintptr_t>(x4) & 15) || (reinterpret_cast<uintptr_t>(y4) & 15)) return SHWD_ERR_INVALID_ARGUMENT;
   if (B == 0) return SHWD_OK;
-  const size_t smem = auction_smem(N);
-  if (smem > 220 * 1024) return SHWD_ERR_UNSUPPORTED;
+  if (N > shwd_exact_assignment_max_points()) return SHWD_ERR_UNSUPPORTED;
+  const int K = auction_list_width(N, false);
+  const size_t smem = auction_smem(N, K, false);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SHWD_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), s));
   const int fast = pick_fast(cost_kind, p, n_power);
@@ -279,7 +629,7 @@ extern "C" int shwd_exact_assignment(const float* x4, const float* y4, int B, in
   do {                                                                                                                      \
     if (smem > 32 * 1024) /* static + dynamic beyond 48 KB needs the opt-in */                                              \
       SHWD_CUDA_CHECK(cudaFuncSetAttribute(auction_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    auction_kernel<F><<<B, AU_THREADS, smem, s>>>(X, Y, nullptr, N, cp, sigma, prices, rounds, status);                     \
+    auction_kernel<F><<<B, AU_THREADS, smem, s>>>(X, Y, nullptr, N, K, cp, sigma, prices, rounds, status);                  \
   } while (0)
   switch (fast) {
     case FAST_GEO2: SHWD_LAUNCH_AUCTION(FAST_GEO2); break;
@@ -291,20 +641,21 @@ extern "C" int shwd_exact_assignment(const float* x4, const float* y4, int B, in
   return SHWD_OK;
 }
 
-// The same solve on an explicit cost matrix C (B, N, N) float32 (costs >= 0, as every cost of this path is): what
-// ot.emd2(a, b, M) receives at main_rotation.py:63-79 (POT_loss) and in the notebooks' W2 metric.  Uniform weights, square.
+// The same solve on an explicit cost matrix C (B, N, N) float32: what ot.emd2(a, b, M) receives at
+// main_rotation.py:63-79 (POT_loss) and in the notebooks' W2 metric.  Uniform weights, square.
 extern "C" int shwd_exact_assignment_dense(const float* C, int B, int N, int* sigma, double* prices, int* rounds, int* status,
                                            void* stream) {
   if (!C || !sigma || !status || B < 0 || N <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B == 0) return SHWD_OK;
-  const size_t smem = auction_smem(N);
-  if (smem > 220 * 1024) return SHWD_ERR_UNSUPPORTED;
+  if (N > shwd_exact_assignment_max_points()) return SHWD_ERR_UNSUPPORTED;
+  const int K = auction_list_width(N, true);
+  const size_t smem = auction_smem(N, K, true);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SHWD_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), s));
   const CostParams cp = make_cost_unit(SHWD_COST_SQEUCLID, 2.f, 1.f);  // unused by the dense functor
   if (smem > 32 * 1024)
     SHWD_CUDA_CHECK(cudaFuncSetAttribute(auction_kernel<AU_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  auction_kernel<AU_DENSE><<<B, AU_THREADS, smem, s>>>(nullptr, nullptr, C, N, cp, sigma, prices, rounds, status);
+  auction_kernel<AU_DENSE><<<B, AU_THREADS, smem, s>>>(nullptr, nullptr, C, N, K, cp, sigma, prices, rounds, status);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }

@@ -132,10 +132,14 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const float* __
 
 // gq_i = 2 g_i (q_i - r_{nn(i)})  +  sum_{j : nn_r(j) == i} 2 h_j (q_i - r_j), the second sum in ascending j
 // (deterministic; no float atomics).
+// UNIFORM (the fused loss node): every d_xy[b, :] has the same upstream gradient g[b * g_stride] * cx (d_yx: ... * cy) -- the
+// reductions of chamfer_distance folded into two scalars -- so no (B,N) / (B,M) gradient tensors exist.
+template <bool UNIFORM>
 __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int N,
                                                                  int M, int blocks_x, const int* __restrict__ idx_xy,
                                                                  const int* __restrict__ idx_yx, const float* __restrict__ gdx,
-                                                                 const float* __restrict__ gdy, float* __restrict__ gx,
+                                                                 const float* __restrict__ gdy, const float* __restrict__ g,
+                                                                 int g_stride, float cx, float cy, float* __restrict__ gx,
                                                                  float* __restrict__ gy) {
   __shared__ float4 tile[CH_TILE];  // (r_j, 2 h_j)
   __shared__ int tidx[CH_TILE];
@@ -147,8 +151,14 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const float* __
   const int nq = dir ? M : N, nr = dir ? N : M;
   const int* q_nn = dir ? idx_yx + (size_t)b * M : idx_xy + (size_t)b * N;  // nn of each query in r
   const int* r_nn = dir ? idx_xy + (size_t)b * N : idx_yx + (size_t)b * M;  // nn of each r point in q
-  const float* gq = dir ? gdy + (size_t)b * M : gdx + (size_t)b * N;
-  const float* gr = dir ? gdx + (size_t)b * N : gdy + (size_t)b * M;
+  const float* gq = UNIFORM ? nullptr : (dir ? gdy + (size_t)b * M : gdx + (size_t)b * N);
+  const float* gr = UNIFORM ? nullptr : (dir ? gdx + (size_t)b * N : gdy + (size_t)b * M);
+  float uq = 0.f, ur = 0.f;  // UNIFORM: 2 * upstream gradient of every query / every r point
+  if (UNIFORM) {
+    const float gb = __ldg(g + (size_t)b * g_stride);
+    uq = 2.f * (gb * (dir ? cy : cx));
+    ur = 2.f * (gb * (dir ? cx : cy));
+  }
   float* out = dir ? gy + (size_t)b * M * 3 : gx + (size_t)b * N * 3;
   const int i = qb * CH_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -159,7 +169,7 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const float* __
     ay = __ldg(q + 3 * i + 1);
     az = __ldg(q + 3 * i + 2);
     const int j = __ldg(q_nn + i);
-    const float g2 = 2.f * __ldg(gq + i);
+    const float g2 = UNIFORM ? uq : 2.f * __ldg(gq + i);
     ox = g2 * (ax - __ldg(r + 3 * j));
     oy = g2 * (ay - __ldg(r + 3 * j + 1));
     oz = g2 * (az - __ldg(r + 3 * j + 2));
@@ -171,7 +181,8 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const float* __
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       int k = -1;
       if (j < cnt) {
-        v = make_float4(__ldg(r + 3 * (t0 + j)), __ldg(r + 3 * (t0 + j) + 1), __ldg(r + 3 * (t0 + j) + 2), 2.f * __ldg(gr + t0 + j));
+        v = make_float4(__ldg(r + 3 * (t0 + j)), __ldg(r + 3 * (t0 + j) + 1), __ldg(r + 3 * (t0 + j) + 2),
+                        UNIFORM ? ur : 2.f * __ldg(gr + t0 + j));
         k = __ldg(r_nn + t0 + j);
       }
       tile[j] = v;
@@ -197,6 +208,53 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const float* __
     out[3 * i] = ox;
     out[3 * i + 1] = oy;
     out[3 * i + 2] = oz;
+  }
+}
+
+// The reductions of pytorch3d's chamfer_distance in one launch: CTA b sums d_xy[b, :] and d_yx[b, :] in a fixed order,
+// loss_b = sx * sum_i d_xy + sy * sum_j d_yx; with a batch reduction the last CTA to finish (ticket) adds the loss_b in
+// index order and scales -- deterministic, no float atomics.
+__device__ __forceinline__ float block_sum_fixed(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < CH_THREADS / 32; ++w) t += red[w];
+  return t;
+}
+__global__ void __launch_bounds__(CH_THREADS) chamfer_reduce_kernel(const float* __restrict__ d_xy, const float* __restrict__ d_yx,
+                                                                    int B, int N, int M, float sx, float sy, float sb,
+                                                                    int reduce_batch, float* __restrict__ per_pair,
+                                                                    unsigned* __restrict__ ticket, float* __restrict__ loss) {
+  __shared__ float red[CH_THREADS / 32];
+  __shared__ bool last;
+  const int b = blockIdx.x;
+  float a = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < N; i += CH_THREADS) a += __ldg(d_xy + (size_t)b * N + i);
+  if (sy != 0.f)
+    for (int j = threadIdx.x; j < M; j += CH_THREADS) c += __ldg(d_yx + (size_t)b * M + j);
+  a = block_sum_fixed(a, red);
+  c = block_sum_fixed(c, red);
+  const float lb = (sy != 0.f) ? sx * a + sy * c : sx * a;
+  if (!reduce_batch) {
+    if (threadIdx.x == 0) loss[b] = lb;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    per_pair[b] = lb;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == (unsigned)(B - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (int k = threadIdx.x; k < B; k += CH_THREADS) t += __ldcg(per_pair + k);
+  t = block_sum_fixed(t, red);
+  if (threadIdx.x == 0) {
+    loss[0] = t * sb;
+    *ticket = 0u;  // re-armed for the next call on this workspace
   }
 }
 
@@ -228,8 +286,40 @@ extern "C" int shwd_chamfer_bwd(const float* x, const float* y, int B, int N, in
   if (B == 0) return SHWD_OK;
   if (B > 65535) return SHWD_ERR_UNSUPPORTED;
   const int bx = (N + CH_THREADS - 1) / CH_THREADS, by = (M + CH_THREADS - 1) / CH_THREADS;
-  chamfer_bwd_kernel<<<dim3(bx + by, B), CH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, y, N, M, bx, idx_xy, idx_yx, gdx, gdy,
-                                                                                           gx, gy);
+  chamfer_bwd_kernel<false><<<dim3(bx + by, B), CH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, y, N, M, bx, idx_xy, idx_yx, gdx,
+                                                                                                  gdy, nullptr, 0, 0.f, 0.f, gx, gy);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+// chamfer_distance's reductions (pytorch3d semantics as the reference calls it, train_CD.py:123,161; main_rotation.py:203) on
+// the nearest-neighbour distances of shwd_chamfer_fwd:  loss_b = sx * sum_i d_xy[b,i] + sy * sum_j d_yx[b,j]  (sx = 1/N or 1,
+// sy = 1/M, 1 or 0 for single_directional);  reduce_batch != 0: loss[0] = sb * sum_b loss_b (sb = 1/B or 1), else loss[b].
+// ws: B floats + one zero-initialised unsigned (shwd_chamfer_reduce_workspace_bytes), re-armed by the kernel.
+extern "C" size_t shwd_chamfer_reduce_workspace_bytes(int B) { return (size_t)(B > 0 ? B : 1) * sizeof(float) + 16; }
+extern "C" int shwd_chamfer_reduce(const float* d_xy, const float* d_yx, int B, int N, int M, float sx, float sy, float sb,
+                                   int reduce_batch, void* ws, float* loss, void* stream) {
+  if (!d_xy || !d_yx || !loss || !ws || B < 0 || N <= 0 || M <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (B == 0) return SHWD_OK;
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws);
+  float* per_pair = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 16);
+  chamfer_reduce_kernel<<<B, CH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(d_xy, d_yx, B, N, M, sx, sy, sb, reduce_batch,
+                                                                               per_pair, ticket, loss);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+// Backward of the fused loss: d loss / d d_xy[b, :] = g[b * g_stride] * cx, d loss / d d_yx[b, :] = g[b * g_stride] * cy
+// (g: the upstream gradient on the device -- one scalar, or one per pair without a batch reduction).
+extern "C" int shwd_chamfer_bwd_uniform(const float* x, const float* y, int B, int N, int M, const int* idx_xy, const int* idx_yx,
+                                        const float* g, int g_stride, float cx, float cy, float* gx, float* gy, void* stream) {
+  if (!x || !y || !idx_xy || !idx_yx || !g || !gx || !gy || B < 0 || N <= 0 || M <= 0 || (g_stride != 0 && g_stride != 1))
+    return SHWD_ERR_INVALID_ARGUMENT;
+  if (B == 0) return SHWD_OK;
+  if (B > 65535) return SHWD_ERR_UNSUPPORTED;
+  const int bx = (N + CH_THREADS - 1) / CH_THREADS, by = (M + CH_THREADS - 1) / CH_THREADS;
+  chamfer_bwd_kernel<true><<<dim3(bx + by, B), CH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, y, N, M, bx, idx_xy, idx_yx, nullptr,
+                                                                                                 nullptr, g, g_stride, cx, cy, gx, gy);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }

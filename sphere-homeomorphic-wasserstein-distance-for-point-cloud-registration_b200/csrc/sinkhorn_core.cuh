@@ -101,7 +101,7 @@ struct SinkParams {
   // workspace
   int* done;    // (B)
   int* status;  // (1)
-  float* err;   // (iters, B)
+  unsigned long long* err;   // (iters, B) early-stop statistic in 2^-40 fixed point (integer sums: order-independent)
   int spin_ready;  // the host pre-filled the write-once planes with SPIN_SENTINEL
 };
 
@@ -117,7 +117,7 @@ struct SweepIO {
   float* out_pot;
   float* out_pot_lo;     // nullptr -> residual not kept
   const float* old_pot;  // for the early-stop statistic (nullptr -> 0)
-  float* err_out;        // nullptr -> not recorded
+  unsigned long long* err_out;  // nullptr -> not recorded
   // MODE_FINAL: the plan is evaluated in its column-normalised form P_ij = b * S^v,L_ij,
   //   S^v,L_ij = 2^(fl(M(alpha^L_i) + fl(beta^L_j + lo_j - lb2))) * 2^res_j,
   // i.e. with exactly the roundings of the last beta half-step, so P and the softmax factor it cancels against in the
@@ -284,9 +284,13 @@ __device__ __forceinline__ bool finalize_visit(const CostParams& cp, const Sweep
       }
     }
     if (MODE == MODE_LSE && ios[0].err_out) {
-      // early-stop statistic sum_i |u_new - u_old| (sinkhorn.py:42): one float atomic per warp (= per owner group)
+      // early-stop statistic sum_i |u_new - u_old| (sinkhorn.py:42): one atomic per warp (= per owner group), in 2^-40
+      // fixed point so that the sum does not depend on the order the CTAs arrive in (an iterate sitting exactly at the
+      // threshold is selected the same way in every run); a warp's share is clamped at 1024 -- astronomically above any
+      // threshold -- which keeps 2048 groups inside 64 bits
       errv = warp_sum(errv);
-      if (lane == 0 && threadIdx.x < ng * 32) atomicAdd(io.err_out, errv);
+      if (lane == 0 && threadIdx.x < ng * 32)
+        atomicAdd(io.err_out, (unsigned long long)((double)fminf(errv, 1024.f) * 1099511627776.0));
     }
   __syncthreads();
   return false;
@@ -1105,8 +1109,9 @@ __device__ void fwd_tail(const SinkParams& prm, int lse_done, float4* sS, float2
     if (threadIdx.x == 0) {
       int found = L;
       for (int l = 0; l < L; ++l) {
-        float s = 0.f;
-        for (int b = 0; b < prm.B; ++b) s += __ldcg(prm.err + (size_t)l * prm.B + b);
+        unsigned long long si = 0ull;
+        for (int b = 0; b < prm.B; ++b) si += __ldcg(prm.err + (size_t)l * prm.B + b);
+        const float s = (float)((double)si * 9.094947017729282e-13);
         // err is in alpha units (k u); the reference tests u
         if (s * prm.inv_k / prm.B < prm.thresh) {
           found = l + 1;
@@ -1330,7 +1335,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 struct Workspace {
   int* done;
   int* status;
-  float* err;
+  unsigned long long* err;
   float* abar;
   float* bbar;
   size_t head_bytes;  // counters + status + err (memset on every launch)
@@ -1345,8 +1350,8 @@ static Workspace carve(void* base, int B, int N, int M, int iters, int adj_plane
   off += 256;
   w.done = reinterpret_cast<int*>(p + off);
   off = align_up(off + sizeof(int) * (size_t)B, 256);
-  w.err = reinterpret_cast<float*>(p + off);
-  off = align_up(off + sizeof(float) * (size_t)B * (size_t)iters, 256);
+  w.err = reinterpret_cast<unsigned long long*>(p + off);
+  off = align_up(off + sizeof(unsigned long long) * (size_t)B * (size_t)iters, 256);
   w.head_bytes = off;
   w.abar = reinterpret_cast<float*>(p + off);
   off = align_up(off + sizeof(float) * (size_t)adj_planes * B * N, 256);

@@ -9,11 +9,46 @@
 // (x^0, x^1, x^2, 1/max(||x_c||,1e-8)) that the OT kernels stage into shared memory unchanged.
 // One CTA per cloud; the centroid is a warp-shuffle + shared-memory tree reduction.  HBM-bound:
 // 12 B read (x2 when centring: the second pass hits L1/L2) + 16 B written per point.
+// Few large clouds (a single pair of 16384 ... 65536 points: cfg4 / the top of cfg5) would leave the GPU to one or two SMs:
+// those launches use one thread-block CLUSTER of 8 CTAs per cloud -- every CTA owns a contiguous eighth of the points, the
+// per-CTA partial sums (centroid, regulariser, gradient mean) are exchanged through distributed shared memory and added in
+// rank order by every CTA (deterministic, no scratch memory, no second launch).
 #include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace shwd {
 
 constexpr int SM_THREADS = 256;
+constexpr int SM_CLUSTER = 8;  // CTAs per cloud on the cluster path
+
+// Sum of one float4 per CTA over the CTAs of this cluster, in rank order (a plain copy when the launch has no cluster).
+__device__ __forceinline__ float4 cluster_sum4(float4 mine, float4* slot) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned nb = cluster.num_blocks();
+  if (nb == 1) return mine;
+  __syncthreads();  // (slot may still be read by a previous call's tail in this CTA)
+  if (threadIdx.x == 0) *slot = mine;
+  cluster.sync();
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (unsigned r = 0; r < nb; ++r) {
+    const float4 v = *cluster.map_shared_rank(slot, r);
+    t.x += v.x;
+    t.y += v.y;
+    t.z += v.z;
+    t.w += v.w;
+  }
+  cluster.sync();  // nobody leaves (or overwrites its slot) while a peer still reads it
+  return t;
+}
+// this CTA's contiguous share [lo, hi) of `count` items
+__device__ __forceinline__ void cluster_range(int count, int& lo, int& hi) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int nb = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+  const int per = (count + nb - 1) / nb;
+  lo = min(r * per, count);
+  hi = min(lo + per, count);
+}
 
 struct P4 {
   float3 p[4];
@@ -68,16 +103,19 @@ template <bool VEC>
 __global__ void __launch_bounds__(SM_THREADS) sphere_map_fwd_kernel(const float* __restrict__ x, float4* __restrict__ xh4,
                                                                     float* __restrict__ reg_out, int N, int flags) {
   __shared__ float red[96];
-  const int b = blockIdx.x;
+  __shared__ float4 cslot;
+  const int b = blockIdx.x / (int)cg::this_cluster().num_blocks();
   const float* xb = x + (size_t)b * N * 3;
   float4* ob = xh4 + (size_t)b * N;
   const bool center = flags & SHWD_MAP_CENTER, normalize = flags & SHWD_MAP_NORMALIZE;
   float3 mean = make_float3(0.f, 0.f, 0.f);
   float reg = 0.f;
+  int lo, hi;  // this CTA's quads (VEC) or points
+  cluster_range(VEC ? N / 4 : N, lo, hi);
   if (center || reg_out) {
     float3 s = make_float3(0.f, 0.f, 0.f);
     if (VEC) {
-      for (int q = threadIdx.x; q < N / 4; q += SM_THREADS) {
+      for (int q = lo + threadIdx.x; q < hi; q += SM_THREADS) {
         P4 r = load4(xb, q);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -88,7 +126,7 @@ __global__ void __launch_bounds__(SM_THREADS) sphere_map_fwd_kernel(const float*
         }
       }
     } else {
-      for (int n = threadIdx.x; n < N; n += SM_THREADS) {
+      for (int n = lo + threadIdx.x; n < hi; n += SM_THREADS) {
         float3 p = make_float3(__ldg(xb + 3 * n), __ldg(xb + 3 * n + 1), __ldg(xb + 3 * n + 2));
         s.x += p.x;
         s.y += p.y;
@@ -97,11 +135,11 @@ __global__ void __launch_bounds__(SM_THREADS) sphere_map_fwd_kernel(const float*
       }
     }
     float3 tot = block_sum3(s, red);
-    if (center) mean = make_float3(tot.x / N, tot.y / N, tot.z / N);
-    if (reg_out) {
-      float3 rr = block_sum3(make_float3(reg, 0.f, 0.f), red);
-      if (threadIdx.x == 0) reg_out[b] = rr.x;
-    }
+    float rsum = 0.f;
+    if (reg_out) rsum = block_sum3(make_float3(reg, 0.f, 0.f), red).x;
+    const float4 all = cluster_sum4(make_float4(tot.x, tot.y, tot.z, rsum), &cslot);
+    if (center) mean = make_float3(all.x / N, all.y / N, all.z / N);
+    if (reg_out && threadIdx.x == 0 && cg::this_cluster().block_rank() == 0) reg_out[b] = all.w;
   }
   auto map = [&](float3 p) -> float4 {
     p.x -= mean.x;
@@ -118,13 +156,13 @@ __global__ void __launch_bounds__(SM_THREADS) sphere_map_fwd_kernel(const float*
     return make_float4(p.x, p.y, p.z, inv);
   };
   if (VEC) {
-    for (int q = threadIdx.x; q < N / 4; q += SM_THREADS) {
+    for (int q = lo + threadIdx.x; q < hi; q += SM_THREADS) {
       P4 r = load4(xb, q);
 #pragma unroll
       for (int e = 0; e < 4; ++e) ob[4 * q + e] = map(r.p[e]);
     }
   } else {
-    for (int n = threadIdx.x; n < N; n += SM_THREADS)
+    for (int n = lo + threadIdx.x; n < hi; n += SM_THREADS)
       ob[n] = map(make_float3(__ldg(xb + 3 * n), __ldg(xb + 3 * n + 1), __ldg(xb + 3 * n + 2)));
   }
 }
@@ -136,7 +174,11 @@ __global__ void __launch_bounds__(SM_THREADS) sphere_map_bwd_kernel(const float*
                                                                     const float4* __restrict__ g4, const float* __restrict__ greg,
                                                                     float* __restrict__ gx, int N, int flags) {
   __shared__ float red[96];
-  const int b = blockIdx.x;
+  __shared__ float4 cslot;
+  const int b = blockIdx.x / (int)cg::this_cluster().num_blocks();
+  int lo, hi;  // this CTA's quads (VEC) or points
+  cluster_range(VEC ? N / 4 : N, lo, hi);
+  const int plo = VEC ? 4 * lo : lo, phi = VEC ? 4 * hi : hi;
   const float* xb = x + (size_t)b * N * 3;
   const float4* hb = xh4 + (size_t)b * N;
   const float4* gb = g4 ? g4 + (size_t)b * N : nullptr;
@@ -171,17 +213,18 @@ __global__ void __launch_bounds__(SM_THREADS) sphere_map_bwd_kernel(const float*
   float3 mean = make_float3(0.f, 0.f, 0.f);
   if (center && gb) {
     float3 s = make_float3(0.f, 0.f, 0.f);
-    for (int n = threadIdx.x; n < N; n += SM_THREADS) {
+    for (int n = plo + threadIdx.x; n < phi; n += SM_THREADS) {
       float3 g = gc_of(n);
       s.x += g.x;
       s.y += g.y;
       s.z += g.z;
     }
     float3 tot = block_sum3(s, red);
-    mean = make_float3(tot.x / N, tot.y / N, tot.z / N);
+    const float4 all = cluster_sum4(make_float4(tot.x, tot.y, tot.z, 0.f), &cslot);
+    mean = make_float3(all.x / N, all.y / N, all.z / N);
   }
   if (VEC) {
-    for (int q = threadIdx.x; q < N / 4; q += SM_THREADS) {
+    for (int q = lo + threadIdx.x; q < hi; q += SM_THREADS) {
       P4 out;
       P4 raw;
       if (greg) raw = load4(xb, q);
@@ -202,7 +245,7 @@ __global__ void __launch_bounds__(SM_THREADS) sphere_map_bwd_kernel(const float*
       store4(ob, q, out);
     }
   } else {
-    for (int n = threadIdx.x; n < N; n += SM_THREADS) {
+    for (int n = lo + threadIdx.x; n < hi; n += SM_THREADS) {
       float3 g = gc_of(n);
       g.x -= mean.x;
       g.y -= mean.y;
@@ -225,15 +268,33 @@ __global__ void __launch_bounds__(SM_THREADS) sphere_map_bwd_kernel(const float*
 using namespace shwd;
 
 static bool vec_ok(const void* p, int N) { return (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0); }
+// a cluster of SM_CLUSTER CTAs per cloud when one CTA per cloud would leave most of the GPU idle on a large cloud
+static bool use_cluster(int B, int N) { return N >= 8192 && B * SM_CLUSTER <= 2 * sm_count(); }
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_map(void (*kernel)(KArgs...), int B, bool cluster, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster ? B * SM_CLUSTER : B);
+  cfg.blockDim = dim3(SM_THREADS);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster ? SM_CLUSTER : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 extern "C" int shwd_sphere_map_fwd(const float* x, float* xh4, float* reg_out, int B, int N, int flags, void* stream) {
   if (!x || !xh4 || B < 0 || N <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B == 0) return SHWD_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool cl = use_cluster(B, N);
   if (vec_ok(x, N))
-    sphere_map_fwd_kernel<true><<<B, SM_THREADS, 0, s>>>(x, reinterpret_cast<float4*>(xh4), reg_out, N, flags);
+    SHWD_CUDA_CHECK(launch_map(sphere_map_fwd_kernel<true>, B, cl, s, x, reinterpret_cast<float4*>(xh4), reg_out, N, flags));
   else
-    sphere_map_fwd_kernel<false><<<B, SM_THREADS, 0, s>>>(x, reinterpret_cast<float4*>(xh4), reg_out, N, flags);
+    SHWD_CUDA_CHECK(launch_map(sphere_map_fwd_kernel<false>, B, cl, s, x, reinterpret_cast<float4*>(xh4), reg_out, N, flags));
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }
@@ -243,12 +304,13 @@ extern "C" int shwd_sphere_map_bwd(const float* x, const float* xh4, const float
   if (!x || !xh4 || !gx || B < 0 || N <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B == 0) return SHWD_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool cl = use_cluster(B, N);
   if (vec_ok(x, N) && vec_ok(gx, N))
-    sphere_map_bwd_kernel<true><<<B, SM_THREADS, 0, s>>>(x, reinterpret_cast<const float4*>(xh4),
-                                                         reinterpret_cast<const float4*>(g4), greg, gx, N, flags);
+    SHWD_CUDA_CHECK(launch_map(sphere_map_bwd_kernel<true>, B, cl, s, x, reinterpret_cast<const float4*>(xh4),
+                               reinterpret_cast<const float4*>(g4), greg, gx, N, flags));
   else
-    sphere_map_bwd_kernel<false><<<B, SM_THREADS, 0, s>>>(x, reinterpret_cast<const float4*>(xh4),
-                                                          reinterpret_cast<const float4*>(g4), greg, gx, N, flags);
+    SHWD_CUDA_CHECK(launch_map(sphere_map_bwd_kernel<false>, B, cl, s, x, reinterpret_cast<const float4*>(xh4),
+                               reinterpret_cast<const float4*>(g4), greg, gx, N, flags));
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }

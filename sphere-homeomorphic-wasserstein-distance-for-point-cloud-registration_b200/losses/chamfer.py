@@ -16,20 +16,5 @@ def chamfer_distance(x, y, x_lengths=None, y_lengths=None, x_normals=None, y_nor
         raise ValueError('batch_reduction must be one of ["mean", "sum"] or None')
     if point_reduction not in ("mean", "sum"):
         raise ValueError('point_reduction must be one of ["mean", "sum"]')
-    d_xy, d_yx, _, _ = ops.chamfer_nn(x, y)
-    B, N = d_xy.shape
-    M = d_yx.shape[1]
-    cham_x = d_xy.sum(1)
-    cham_y = d_yx.sum(1)
-    if point_reduction == "mean":
-        cham_x = cham_x / N
-        cham_y = cham_y / M
-    if batch_reduction is not None:
-        cham_x = cham_x.sum()
-        cham_y = cham_y.sum()
-        if batch_reduction == "mean":
-            cham_x = cham_x / max(B, 1)
-            cham_y = cham_y / max(B, 1)
-    if single_directional:
-        return cham_x, None
-    return cham_x + cham_y, None
+    # one autograd node: nearest neighbours + every reduction below in two launches, backward in one (csrc/chamfer.cu)
+    return ops.chamfer_loss(x, y, point_reduction == "mean", batch_reduction, single_directional), None

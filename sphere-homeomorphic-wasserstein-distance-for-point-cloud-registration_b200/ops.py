@@ -250,6 +250,63 @@ class ChamferFn(torch.autograd.Function):
         return gx, gy
 
 
+class ChamferLossFn(torch.autograd.Function):
+    """chamfer_distance as ONE autograd node: nearest neighbours, the point / batch reductions (fixed order) and, backward,
+    one launch that reads the upstream scalar on the device -- no (B,N) gradient tensors, no ATen reduce / elementwise
+    kernels.  ``apply(x, y, sx, sy, sb, reduce_batch)`` -> loss () or (B,)  (pytorch3d semantics: train_CD.py:123,161)."""
+
+    @staticmethod
+    def forward(ctx, x, y, sx, sy, sb, reduce_batch):
+        lib = _lib.lib()
+        x = x.contiguous()
+        y = y.contiguous()
+        B, N, _ = x.shape
+        M = y.shape[1]
+        dev = x.device
+        d_xy = torch.empty(B, N, device=dev, dtype=torch.float32)
+        d_yx = torch.empty(B, M, device=dev, dtype=torch.float32)
+        i_xy = torch.empty(B, N, device=dev, dtype=torch.int32)
+        i_yx = torch.empty(B, M, device=dev, dtype=torch.int32)
+        loss = torch.zeros((1,) if reduce_batch else (B,), device=dev, dtype=torch.float32)
+        ws = torch.zeros(lib.shwd_chamfer_reduce_workspace_bytes(B), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            s = _stream()
+            _lib.check(lib.shwd_chamfer_fwd(_ptr(x), _ptr(y), B, N, M, _ptr(d_xy), _ptr(i_xy), _ptr(d_yx), _ptr(i_yx), s), "shwd_chamfer_fwd")
+            _lib.check(lib.shwd_chamfer_reduce(_ptr(d_xy), _ptr(d_yx), B, N, M, float(sx), float(sy), float(sb), int(reduce_batch),
+                                               _ptr(ws), _ptr(loss), s), "shwd_chamfer_reduce")
+        ctx.save_for_backward(x, y, i_xy, i_yx)
+        ctx.scales = (float(sx), float(sy), float(sb), bool(reduce_batch))
+        return loss.reshape(()) if reduce_batch else loss
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, i_xy, i_yx = ctx.saved_tensors
+        sx, sy, sb, reduce_batch = ctx.scales
+        B, N, _ = x.shape
+        M = y.shape[1]
+        g = g.contiguous().float()
+        gx = torch.empty_like(x)
+        gy = torch.empty_like(y)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().shwd_chamfer_bwd_uniform(_ptr(x), _ptr(y), B, N, M, _ptr(i_xy), _ptr(i_yx), _ptr(g),
+                                                           0 if reduce_batch else 1, sx * sb, sy * sb, _ptr(gx), _ptr(gy), _stream()),
+                       "shwd_chamfer_bwd_uniform")
+        return gx, gy, None, None, None, None
+
+
+def chamfer_loss(x, y, point_mean=True, batch_reduction="mean", single_directional=False):
+    """The fused chamfer_distance value (see ChamferLossFn)."""
+    xc, _ = _as_cloud(x, "x")
+    yc, _ = _as_cloud(y, "y")
+    if xc.shape[0] != yc.shape[0]:
+        raise ValueError("batch sizes differ: %d vs %d" % (xc.shape[0], yc.shape[0]))
+    B, N, M = xc.shape[0], xc.shape[1], yc.shape[1]
+    sx = 1.0 / N if point_mean else 1.0
+    sy = 0.0 if single_directional else (1.0 / M if point_mean else 1.0)
+    sb = 1.0 / max(B, 1) if batch_reduction == "mean" else 1.0
+    return ChamferLossFn.apply(xc, yc, sx, sy, sb, batch_reduction is not None)
+
+
 def chamfer_nn(x, y):
     """Nearest-neighbour squared distances and indices in both directions: (d_xy, d_yx, idx_xy, idx_yx)."""
     xc, _ = _as_cloud(x, "x")

@@ -45,7 +45,8 @@ def gold(name):
 
 
 # ----------------------------------------------------------------------------------------------------- sphere map ---
-@pytest.mark.parametrize("B,N", [(3, 64), (2, 50), (4, 1024), (1, 7)])
+# (1, 65536), (2, 8193), (3, 16384): few large clouds -> one thread-block cluster of 8 CTAs per cloud (partial sums through DSMEM)
+@pytest.mark.parametrize("B,N", [(3, 64), (2, 50), (4, 1024), (1, 7), (1, 65536), (2, 8193), (3, 16384)])
 @pytest.mark.parametrize("center", [True, False])
 @pytest.mark.parametrize("normalize", [True, False])
 def test_sphere_map_fwd_bwd(shwd, B, N, center, normalize):
@@ -435,6 +436,16 @@ def test_chamfer_matches_oracle(shwd, B, N, M, br, pr):
     d_xy, d_yx, i_xy, i_yx = shwd.chamfer_nn(x.to(dev()), y.to(dev()))
     assert torch.equal(d_xy.cpu(), d.min(2).values) and torch.equal(d_yx.cpu(), d.min(1).values)
     assert torch.equal(i_xy.cpu().long(), d.argmin(2)) and torch.equal(i_yx.cpu().long(), d.argmin(1))
+    # single_directional (pytorch3d: only the x -> y term), un-batched clouds, and a non-unit upstream gradient
+    xs = x[0].clone().to(dev()).requires_grad_(True)
+    ys = y[0].clone().to(dev()).requires_grad_(True)
+    one, _ = shwd.losses.chamfer_distance(xs, ys, batch_reduction=br, point_reduction=pr, single_directional=True)
+    (one.sum() * 3.0).backward()
+    xq, yq = x[0].clone().requires_grad_(True), y[0].clone().requires_grad_(True)
+    dq = ((xq.unsqueeze(1) - yq.unsqueeze(0)) ** 2).sum(-1).min(1).values
+    refq = dq.mean() if pr == "mean" else dq.sum()
+    (refq * 3.0).backward()
+    assert rel(one, refq) < 1e-6 and rel(xs.grad, xq.grad) < TOL and rel(ys.grad, yq.grad) < TOL
 
 
 # ---------------------------------------------------------------------------------------------------------- sort ----
