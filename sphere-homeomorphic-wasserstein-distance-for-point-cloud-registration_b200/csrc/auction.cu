@@ -160,15 +160,14 @@ __device__ __forceinline__ AuBest au_scan_top2(const CostParams& cp, const AuSha
 // object is known to be the best, it is skipped here and owns slot 0), tmin = smallest w NOT stored, cnt = how many
 // qualified; TRACK: also the exact best / second best over all objects (valid whenever cut >= the true second best).
 template <int FAST, bool TRACK>
-__device__ __forceinline__ void au_scan_collect(const CostParams& cp, const AuShared& S, const float4 o, const float* crow,
-                                                double cshift, int N, int K, int i, int lane, double cut, int j1k, int& cnt,
-                                                double& tmin, AuBest& best) {
-  unsigned short* li = S.lidx + (size_t)i * K;
-  float* lc = S.lcost + (size_t)i * K;
+__device__ __forceinline__ void au_scan_range(const CostParams& cp, const AuShared& S, const float4 o, const float* crow,
+                                              double cshift, int lo, int N, int K, unsigned short* li, float* lc, int lane,
+                                              double cut, int j1k, int cnt0, int& cnt, double& tmin, AuBest& best) {
+  // objects lo <= j < N; entries go to li / lc (capacity K), the first one at position cnt0
   const unsigned lt = (1u << lane) - 1u;
-  cnt = j1k >= 0 ? 1 : 0;
+  cnt = cnt0;
   tmin = INFINITY;
-  for (int j0 = lane; j0 < N + lane; j0 += 128) {  // (+ lane: every lane runs the same number of ballots)
+  for (int j0 = lo + lane; j0 < N + lane; j0 += 128) {  // (+ lane: every lane runs the same number of ballots)
     float c[4];
     double p[4];
 #pragma unroll
@@ -198,6 +197,13 @@ __device__ __forceinline__ void au_scan_collect(const CostParams& cp, const AuSh
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, s));
+}
+template <int FAST, bool TRACK>
+__device__ __forceinline__ void au_scan_collect(const CostParams& cp, const AuShared& S, const float4 o, const float* crow,
+                                                double cshift, int N, int K, int i, int lane, double cut, int j1k, int& cnt,
+                                                double& tmin, AuBest& best) {
+  au_scan_range<FAST, TRACK>(cp, S, o, crow, cshift, 0, N, K, S.lidx + (size_t)i * K, S.lcost + (size_t)i * K, lane, cut, j1k,
+                             j1k >= 0 ? 1 : 0, cnt, tmin, best);
 }
 // A rescan that also rebuilds the candidate list.  guess: an upper bound of the person's true second-best w (the second
 // best of its exhausted list), or non-finite when there is none: with a guess the list is cut at guess + delta_i and ONE
@@ -243,6 +249,122 @@ __device__ __forceinline__ AuBest au_rescan(const CostParams& cp, const AuShared
   return best;
 }
 
+// The same rescan by G = 2, 4, 8 or 16 warps per person (a Jacobi round with few persons -- the price wars of the small-eps
+// phases -- would otherwise leave most of the CTA idle behind one warp's 1024-object scan).  Warp `sub` of a group scans a
+// contiguous N / G slice into its own staging row; the per-warp (count, smallest unstored w, best / second best) meet in
+// shared memory, and every warp copies its staged entries to the list at the offset its predecessors' counts give (index
+// order again).  Up to three attempts with the cuts of au_rescan; every attempt is one scan + one __syncthreads, and every
+// warp of the CTA runs the same number of barriers.  build == false: best / second best only (one attempt, no list).
+struct AuPart {
+  AuBest best;
+  double tmin;
+  int cnt;
+};
+constexpr int AU_STAGE_K = 16;
+template <int FAST>
+__device__ __forceinline__ AuBest au_rescan_coop(const CostParams& cp, const AuShared& S, const float4* Xb, const float* Cb,
+                                                 double cshift, int N, int K, int c0, int nC, int G, bool build,
+                                                 AuPart (*part)[AU_WARPS], unsigned short (*stg_i)[AU_STAGE_K],
+                                                 float (*stg_c)[AU_STAGE_K], int warp, int lane) {
+  constexpr bool DENSE = FAST == AU_DENSE;
+  const int r = warp / G, sub = warp % G;
+  const bool active = r < nC;
+  const int i = active ? S.R[c0 + r] : 0;
+  const float4 o = (DENSE || !active) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(Xb + i);
+  const float* crow = DENSE ? Cb + (size_t)i * N : nullptr;
+  const int per = (N + G - 1) / G;
+  const int lo = min(sub * per, N), hi = min(lo + per, N);
+  float dl = active ? S.delta[i] : 0.f;
+  const double guess = active ? S.Tw[i] : 0.0;
+  const bool has_guess = build && guess > -INFINITY && guess < INFINITY;
+  AuBest best = {INFINITY, INFINITY, INT_MAX, 0.f};
+  bool done = !active;
+  const int natt = build ? 3 : 1;
+  for (int a = 0; a < natt; ++a) {
+    double cut = -INFINITY;
+    int j1k = -1;
+    if (!done) {
+      if (a == 0) {
+        if (has_guess) cut = guess + (double)dl;
+      } else {
+        cut = (a == 1) ? fmax(best.w1 + (double)dl, best.w2) : best.w2;
+        j1k = best.j1;
+      }
+      int cnt;
+      double tmin;
+      AuBest bp = {INFINITY, INFINITY, INT_MAX, 0.f};
+      if (a == 0)
+        au_scan_range<FAST, true>(cp, S, o, crow, cshift, lo, hi, K, stg_i[warp], stg_c[warp], lane, cut, j1k, 0, cnt, tmin, bp);
+      else
+        au_scan_range<FAST, false>(cp, S, o, crow, cshift, lo, hi, K, stg_i[warp], stg_c[warp], lane, cut, j1k, 0, cnt, tmin, bp);
+      if (a == 0) {  // (au_warp_merge without the index fix-up: an empty slice keeps INT_MAX and loses every merge)
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+          AuBest other;
+          other.w1 = __shfl_xor_sync(0xffffffffu, bp.w1, s);
+          other.w2 = __shfl_xor_sync(0xffffffffu, bp.w2, s);
+          other.j1 = __shfl_xor_sync(0xffffffffu, bp.j1, s);
+          other.c1 = __shfl_xor_sync(0xffffffffu, bp.c1, s);
+          bp = au_merge(bp, other);
+        }
+      }
+      if (lane == 0) {
+        part[a][warp].best = bp;
+        part[a][warp].tmin = tmin;
+        part[a][warp].cnt = cnt;
+      }
+    }
+    __syncthreads();
+    if (!done) {
+      int tot = j1k >= 0 ? 1 : 0, off = tot, mine = 0;
+      double tminG = INFINITY;
+      for (int t = 0; t < G; ++t) {
+        const AuPart& q = part[a][r * G + t];
+        if (t == sub) {
+          off = tot;
+          mine = q.cnt;
+        }
+        tot += q.cnt;
+        tminG = fmin(tminG, q.tmin);
+        if (a == 0) best = (t == 0) ? q.best : au_merge(best, q.best);
+      }
+      if (a == 0 && best.j1 == INT_MAX) best.j1 = 0;
+      bool ok;
+      if (a == 0) {
+        ok = has_guess && tot <= K && best.w2 <= cut;  // (prices may have risen past the guess since it was taken)
+        if (has_guess && tot > K) dl *= 0.125f;
+      } else if (a == 1) {
+        ok = tot <= K;
+        if (!ok) dl *= 0.125f;
+      } else {
+        ok = true;
+      }
+      if (ok && build) {
+        unsigned short* li = S.lidx + (size_t)i * K;
+        float* lc = S.lcost + (size_t)i * K;
+        for (int e = lane; e < min(mine, K); e += 32)
+          if (off + e < K) {
+            li[off + e] = stg_i[warp][e];
+            lc[off + e] = stg_c[warp][e];
+          }
+        if (sub == 0) {
+          for (int k = tot + lane; k < K; k += 32) li[k] = 0xFFFFu;
+          if (lane == 0) {
+            if (j1k >= 0) {
+              li[0] = (unsigned short)best.j1;
+              lc[0] = best.c1;
+            }
+            S.Tw[i] = tot > K ? fmin(tminG, best.w2) : tminG;  // (entries cut off by the capacity tie with the second best)
+            S.delta[i] = tot <= K / 2 ? dl * 2.f : dl;
+          }
+        }
+        done = true;
+      }
+    }
+  }
+  return best;
+}
+
 // Smallest and second-smallest of one non-negative double per lane (+inf: no entry), by integer min-reductions on the bit
 // patterns (non-negative doubles order like their bits).  l1 = lowest lane holding the smallest.
 __device__ __forceinline__ void au_top2(double w, int lane, double& w1, double& w2, int& l1) {
@@ -282,6 +404,9 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
   S.rj = S.R + N;
   S.lidx = reinterpret_cast<unsigned short*>(S.rj + AU_RC);
   __shared__ double s_red[AU_WARPS], s_red2[AU_WARPS];
+  __shared__ AuPart s_part[3][AU_WARPS];
+  __shared__ unsigned short s_stg_i[AU_WARPS][AU_STAGE_K];
+  __shared__ float s_stg_c[AU_WARPS][AU_STAGE_K];
   __shared__ int s_ctl[4];  // nR, queue head, queue count, failed
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -345,7 +470,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
   for (int i = tid; i < N; i += AU_THREADS) S.delta[i] = (float)(SHWD_AU_DELTA0 * cmax / N);
   const double eps_final = cmax * 9.094947017729282e-13;  // 2^-40
 #ifdef SHWD_AU_PROFILE
-  long long pf_start = 0, pf_gs = 0, pf_rescan = 0, pf_apply = 0, pf_nresc = 0, pf_nlist = 0, pf_rounds = 0;
+  long long pf_top2 = 0, pf_neval = 0, pf_start = 0, pf_gs = 0, pf_rescan = 0, pf_apply = 0, pf_nresc = 0, pf_nlist = 0, pf_rounds = 0;
 #endif
   long long bids = 0;  // (warp 0's count of list bids + every thread's view of the parallel rounds is not needed: info only)
   int failed = 0;
@@ -467,7 +592,12 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
           const double tw = S.Tw[i];
           double w1, w2;
           int l1;
+          AU_PROF_T(t_t2);
           au_top2(w, lane, w1, w2, l1);
+          AU_PROF_ADD(pf_top2, t_t2);
+#ifdef SHWD_AU_PROFILE
+          ++pf_neval;
+#endif
           if (!(w2 <= tw)) {  // list exhausted: the best or second best may be an unlisted object
             if (lane == 0) {
               S.R[nR] = i;
@@ -512,17 +642,30 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
       for (int c0 = 0; c0 < nRall; c0 += AU_RC) {
         const int nC = min(AU_RC, nRall - c0);
         AU_PROF_T(t_rs);
-        for (int r = warp; r < nC; r += AU_WARPS) {
-          const int i = S.R[c0 + r];
-          const float4 o = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(Xb + i);
-          const float* crow = DENSE ? Cb + (size_t)i * N : nullptr;
-          const AuBest best = lists ? au_rescan<FAST>(cp, S, o, crow, cshift, N, K, i, lane)
-                                    : au_scan_top2<FAST>(cp, S, o, crow, cshift, N, lane);
-          if (lane == 0) {
+        if (nC <= AU_WARPS / 2) {  // few persons: several warps share a person's scan
+          int G = AU_WARPS;
+          while (G * nC > AU_WARPS) G >>= 1;
+          const AuBest best = au_rescan_coop<FAST>(cp, S, Xb, Cb, cshift, N, K, c0, nC, G, lists, s_part, s_stg_i, s_stg_c, warp, lane);
+          const int r = warp / G;
+          if (r < nC && warp % G == 0 && lane == 0) {
             const double bid = S.price[best.j1] + (best.w2 - best.w1) + eps;
             S.rj[r] = best.j1;
             S.rbid[r] = bid;
             atomicMax(S.bidval + best.j1, ((unsigned long long)__double_as_longlong(bid) & ~0x1FFull) | (unsigned long long)(AU_RC - 1 - r));
+          }
+        } else {
+        for (int r = warp; r < nC; r += AU_WARPS) {
+            const int i = S.R[c0 + r];
+            const float4 o = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(Xb + i);
+            const float* crow = DENSE ? Cb + (size_t)i * N : nullptr;
+            const AuBest best = lists ? au_rescan<FAST>(cp, S, o, crow, cshift, N, K, i, lane)
+                                      : au_scan_top2<FAST>(cp, S, o, crow, cshift, N, lane);
+            if (lane == 0) {
+              const double bid = S.price[best.j1] + (best.w2 - best.w1) + eps;
+              S.rj[r] = best.j1;
+              S.rbid[r] = bid;
+              atomicMax(S.bidval + best.j1, ((unsigned long long)__double_as_longlong(bid) & ~0x1FFull) | (unsigned long long)(AU_RC - 1 - r));
+            }
           }
         }
         __syncthreads();
@@ -579,10 +722,10 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
     if (rounds_out) rounds_out[b] = (int)(bids > INT_MAX ? INT_MAX : bids);
     if (failed) atomicExch(status, 1);
 #ifdef SHWD_AU_PROFILE
-    if (price_out && N >= 8) {
+    if (price_out && N >= 9) {
       double* po = price_out + (size_t)b * N;
       po[0] = (double)pf_start; po[1] = (double)pf_gs; po[2] = (double)pf_rescan; po[3] = (double)pf_apply;
-      po[4] = (double)pf_nresc; po[5] = (double)pf_nlist; po[6] = (double)pf_rounds;
+      po[4] = (double)pf_nresc; po[5] = (double)pf_nlist; po[6] = (double)pf_rounds; po[7] = (double)pf_top2; po[8] = (double)pf_neval;
     }
 #endif
   }
@@ -597,7 +740,7 @@ static size_t auction_smem(int N, int K, bool dense) {
                       (size_t)K * (sizeof(float) + sizeof(unsigned short))) +
          AU_RC * (sizeof(double) + sizeof(int)) + 16;
 }
-constexpr size_t AU_SMEM_BUDGET = 226 * 1024;
+constexpr size_t AU_SMEM_BUDGET = 222 * 1024;  // + ~4.5 KB of static shared memory
 // list width: 16 candidates per person where they fit next to the points, 8 for the largest clouds
 static int auction_list_width(int N, bool dense) {
   if (auction_smem(N, 16, dense) <= AU_SMEM_BUDGET) return 16;
