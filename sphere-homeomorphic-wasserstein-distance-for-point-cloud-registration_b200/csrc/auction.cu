@@ -5,11 +5,14 @@
 // (POT's C++ network simplex on a float64 copy of C, one pair at a time on the CPU, with a GPU->CPU->GPU round trip).
 // For uniform weights and n == m the LP optimum is attained at a permutation, so emd2 = (1/n) * min-assignment cost.
 // POT is a third-party dependency that is not vendored (version un-pinned): this solves the same LP by a different exact
-// method, Bertsekas' forward auction with epsilon-scaling, in float64 on the float32 cost values:
+// method, Bertsekas' forward auction with epsilon-scaling, in 64-bit fixed point on the float32 cost values (every cost is
+// scaled by a power of two S with Cmax * S in [2^45, 2^46) and converted once -- exact for every cost >= Cmax * 2^-23, to
+// 2^-46 Cmax below that -- so prices, bids and comparisons are integer adds and compares: the first version ran them in
+// float64, whose dependent-op latency was what a bid and a scan spent their time on):
 //   * an unassigned person i bids for its best object j1 = argmin_j w_ij, w_ij = C_ij + price_j, the price
 //     price_j1 + (second best w - best w) + eps; the previous owner becomes unassigned; a phase ends when everybody is
 //     assigned;
-//   * eps starts at Cmax/4 and is divided by 5 per phase down to Cmax * 2^-40, prices are kept between phases.  At the
+//   * eps starts at Cmax/100 and is divided by 5 per phase down to Cmax * 2^-40, prices are kept between phases.  At the
 //     end the assignment is within n*eps of optimal -- far below one float32 ulp of the cost sum -- i.e. it is the
 //     optimum unless two assignments tie to ~1e-9 relative.
 //
@@ -22,7 +25,7 @@
 //     contains the person's best and second-best object overall, and a bid needs K shared-memory loads instead of N
 //     cost evaluations.  Lists are selected by a window [w1, max(w1 + delta_i, w2)] with a per-person adaptive delta_i.
 //   * GAUSS-SEIDEL BIDS IN ONE WARP.  Warp 0 pops unassigned persons from a ring buffer and serves them from their lists
-//     with warp-wide integer min-reductions (redux.sync on the bit patterns of the non-negative doubles w) -- no
+//     with warp-wide integer min-reductions (redux.sync on the two halves of the 64-bit w) -- no
 //     __syncthreads, ~0.15 us per bid.  A person whose list is exhausted is deferred to a rescan list R.
 //   * BATCHED RESCANS + ONE JACOBI ROUND.  When the queue is empty all 16 warps rescan the persons in R in parallel (one
 //     warp each: best / second best, new list, new Tw) against the same price vector, and those persons bid at once
@@ -50,6 +53,9 @@ constexpr long long AU_MAX_BIDS = 64ll << 20;  // safety net (a solve needs ~50 
 constexpr int AU_RC = 512;        // rescanned persons per Jacobi round (their slot index rides in the low 9 bits of the bid key)
 constexpr int AU_MAX_N = 2048;    // person index rides in the low 11 bits of the phase-start bid key
 constexpr int AU_PP = AU_MAX_N / AU_THREADS;  // persons per thread in the phase-start round
+#ifndef SHWD_AU_EPS0
+#define SHWD_AU_EPS0 0.01  // first epsilon as a fraction of Cmax (A/B on the training shape: 0.25 22 ms, 0.05 18, 0.01 16, 0.005 20)
+#endif
 #ifndef SHWD_AU_LIST_EPS
 #define SHWD_AU_LIST_EPS 2.5e-3  // candidate lists are built once eps <= this fraction of Cmax
 #endif
@@ -78,8 +84,15 @@ __device__ __forceinline__ float au_cost(const CostParams& cp, const float4 o, c
   }
 }
 
+typedef long long i64;
+constexpr i64 AU_INF = 0x7FFFFFFFFFFFFFFFll;   // "no entry"
+constexpr i64 AU_NONE = -AU_INF - 1;            // Tw of a person without a list
+struct AuFix {  // float32 cost -> fixed point: one multiply by a power of two (exact) and one round-to-nearest conversion
+  float scale;
+  __device__ __forceinline__ i64 operator()(float c) const { return __float2ll_rn(c * scale); }
+};
 struct AuBest {  // smallest and second-smallest w of a scan, the object and plain cost of the smallest
-  double w1, w2;
+  i64 w1, w2;
   int j1;
   float c1;
 };
@@ -90,28 +103,28 @@ __device__ __forceinline__ AuBest au_merge(const AuBest& a, const AuBest& b) {
     r.w1 = a.w1;
     r.j1 = a.j1;
     r.c1 = a.c1;
-    r.w2 = fmin(a.w2, b.w1);
+    r.w2 = min(a.w2, b.w1);
   } else {
     r.w1 = b.w1;
     r.j1 = b.j1;
     r.c1 = b.c1;
-    r.w2 = fmin(b.w2, a.w1);
+    r.w2 = min(b.w2, a.w1);
   }
   return r;
 }
 
 struct AuShared {
   float4* sY;                  // N   packed points of the object cloud (unused by the dense variant)
-  double* price;               // N
+  i64* price;                  // N
   unsigned long long* bidval;  // N   highest (bid bits | slot) per object in a Jacobi round (0: none)
-  double* Tw;                  // N   smallest w the person's last scan did NOT list (-inf: no list yet)
+  i64* Tw;                     // N   smallest w the person's last scan did NOT list (AU_NONE: no list yet)
   float* delta;                // N   the person's list window
   int* owner;                  // N   person holding object j (-1: free)
   int* queue;                  // N   ring buffer of unassigned persons with a (possibly) usable list
   int* R;                      // N   persons whose list is exhausted: to be rescanned
   unsigned short* lidx;        // N*K listed objects (0xFFFF: empty slot)
   float* lcost;                // N*K their plain costs
-  double* rbid;                // AU_RC  bid of a rescanned person
+  i64* rbid;                   // AU_RC  bid of a rescanned person
   int* rj;                     // AU_RC  its object
 };
 
@@ -129,9 +142,9 @@ __device__ __forceinline__ AuBest au_warp_merge(AuBest best) {
   if (best.j1 == INT_MAX) best.j1 = 0;  // (cannot happen for finite costs; keeps indices in range)
   return best;
 }
-__device__ __forceinline__ void au_top2_update(AuBest& best, double w, int j, float c) {
+__device__ __forceinline__ void au_top2_update(AuBest& best, i64 w, int j, float c) {
   const bool lt = w < best.w1;
-  best.w2 = fmin(best.w2, lt ? best.w1 : w);
+  best.w2 = min(best.w2, lt ? best.w1 : w);
   best.j1 = lt ? j : best.j1;
   best.c1 = lt ? c : best.c1;
   best.w1 = lt ? w : best.w1;
@@ -139,48 +152,54 @@ __device__ __forceinline__ void au_top2_update(AuBest& best, double w, int j, fl
 // best and second best only (the large-eps phases: every bid moves a price by more than a list window, lists are useless)
 template <int FAST>
 __device__ __forceinline__ AuBest au_scan_top2(const CostParams& cp, const AuShared& S, const float4 o, const float* crow,
-                                               double cshift, int N, int lane) {
-  AuBest best = {INFINITY, INFINITY, INT_MAX, 0.f};
+                                               AuFix fix, int N, int lane) {
+  // four independent (best, second best) accumulators: the update is a dependent compare / select chain
+  AuBest acc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u] = {AU_INF, AU_INF, INT_MAX, 0.f};
   for (int j0 = lane; j0 < N; j0 += 128) {
     float c[4];
-    double p[4];
+    i64 p[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = j0 + 32 * u;
       const bool ok = j < N;
       c[u] = ok ? au_cost<FAST>(cp, o, S.sY, crow, ok ? j : 0) : 0.f;
-      p[u] = ok ? S.price[j] : (double)INFINITY;
+      p[u] = ok ? S.price[j] : 0;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) au_top2_update(best, ((double)c[u] - cshift) + p[u], j0 + 32 * u, c[u]);
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u;
+      au_top2_update(acc[u], j < N ? fix(c[u]) + p[u] : AU_INF, j, c[u]);
+    }
   }
-  return au_warp_merge(best);
+  return au_warp_merge(au_merge(au_merge(acc[0], acc[1]), au_merge(acc[2], acc[3])));
 }
 // One collecting pass: every object with w <= cut goes into the person's list in index order (at most K; j1k >= 0: that
 // object is known to be the best, it is skipped here and owns slot 0), tmin = smallest w NOT stored, cnt = how many
 // qualified; TRACK: also the exact best / second best over all objects (valid whenever cut >= the true second best).
 template <int FAST, bool TRACK>
 __device__ __forceinline__ void au_scan_range(const CostParams& cp, const AuShared& S, const float4 o, const float* crow,
-                                              double cshift, int lo, int N, int K, unsigned short* li, float* lc, int lane,
-                                              double cut, int j1k, int cnt0, int& cnt, double& tmin, AuBest& best) {
+                                              AuFix fix, int lo, int N, int K, unsigned short* li, float* lc, int lane,
+                                              i64 cut, int j1k, int cnt0, int& cnt, i64& tmin, AuBest& best) {
   // objects lo <= j < N; entries go to li / lc (capacity K), the first one at position cnt0
   const unsigned lt = (1u << lane) - 1u;
   cnt = cnt0;
-  tmin = INFINITY;
+  tmin = AU_INF;
   for (int j0 = lo + lane; j0 < N + lane; j0 += 128) {  // (+ lane: every lane runs the same number of ballots)
     float c[4];
-    double p[4];
+    i64 p[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = j0 + 32 * u;
       const bool ok = j < N;
       c[u] = ok ? au_cost<FAST>(cp, o, S.sY, crow, ok ? j : 0) : 0.f;
-      p[u] = ok ? S.price[j] : (double)INFINITY;
+      p[u] = ok ? S.price[j] : 0;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = j0 + 32 * u;
-      const double w = ((double)c[u] - cshift) + p[u];
+      const i64 w = j < N ? fix(c[u]) + p[u] : AU_INF;
       if (TRACK) au_top2_update(best, w, j, c[u]);
       const bool other = j < N && j != j1k;
       const bool take = other && w <= cut;
@@ -191,18 +210,18 @@ __device__ __forceinline__ void au_scan_range(const CostParams& cp, const AuShar
         li[pos] = (unsigned short)j;
         lc[pos] = c[u];
       }
-      tmin = (other && !st) ? fmin(tmin, w) : tmin;
+      tmin = (other && !st) ? min(tmin, w) : tmin;
       cnt += __popc(b);
     }
   }
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, s));
+  for (int s = 16; s > 0; s >>= 1) tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, s));
 }
 template <int FAST, bool TRACK>
 __device__ __forceinline__ void au_scan_collect(const CostParams& cp, const AuShared& S, const float4 o, const float* crow,
-                                                double cshift, int N, int K, int i, int lane, double cut, int j1k, int& cnt,
-                                                double& tmin, AuBest& best) {
-  au_scan_range<FAST, TRACK>(cp, S, o, crow, cshift, 0, N, K, S.lidx + (size_t)i * K, S.lcost + (size_t)i * K, lane, cut, j1k,
+                                                AuFix fix, int N, int K, int i, int lane, i64 cut, int j1k, int& cnt,
+                                                i64& tmin, AuBest& best) {
+  au_scan_range<FAST, TRACK>(cp, S, o, crow, fix, 0, N, K, S.lidx + (size_t)i * K, S.lcost + (size_t)i * K, lane, cut, j1k,
                              j1k >= 0 ? 1 : 0, cnt, tmin, best);
 }
 // A rescan that also rebuilds the candidate list.  guess: an upper bound of the person's true second-best w (the second
@@ -211,29 +230,29 @@ __device__ __forceinline__ void au_scan_collect(const CostParams& cp, const AuSh
 // the exact values: max(w1 + delta_i, w2), then w2 itself.
 template <int FAST>
 __device__ __forceinline__ AuBest au_rescan(const CostParams& cp, const AuShared& S, const float4 o, const float* crow,
-                                            double cshift, int N, int K, int i, int lane) {
+                                            AuFix fix, int N, int K, int i, int lane) {
   float dl = S.delta[i];
-  const double guess = S.Tw[i];
-  AuBest best = {INFINITY, INFINITY, INT_MAX, 0.f};
+  const i64 guess = S.Tw[i];
+  AuBest best = {AU_INF, AU_INF, INT_MAX, 0.f};
   int cnt = 0;
-  double tmin = INFINITY;
+  i64 tmin = AU_INF;
   bool done = false;
-  if (guess > -INFINITY && guess < INFINITY) {
-    const double cut = guess + (double)dl;
-    au_scan_collect<FAST, true>(cp, S, o, crow, cshift, N, K, i, lane, cut, -1, cnt, tmin, best);
+  if (guess > AU_NONE && guess < AU_INF) {
+    const i64 cut = guess + (i64)dl;
+    au_scan_collect<FAST, true>(cp, S, o, crow, fix, N, K, i, lane, cut, -1, cnt, tmin, best);
     best = au_warp_merge(best);
     done = cnt <= K && best.w2 <= cut;  // (prices may have risen past the guess since it was taken)
-    if (!done) dl *= 0.125f;
+    if (cnt > K) dl *= 0.125f;
   } else {
-    best = au_scan_top2<FAST>(cp, S, o, crow, cshift, N, lane);
+    best = au_scan_top2<FAST>(cp, S, o, crow, fix, N, lane);
   }
   unsigned short* li = S.lidx + (size_t)i * K;
   if (!done) {
     AuBest dummy = best;
-    au_scan_collect<FAST, false>(cp, S, o, crow, cshift, N, K, i, lane, fmax(best.w1 + (double)dl, best.w2), best.j1, cnt, tmin, dummy);
+    au_scan_collect<FAST, false>(cp, S, o, crow, fix, N, K, i, lane, max(best.w1 + (i64)dl, best.w2), best.j1, cnt, tmin, dummy);
     if (cnt > K) {
       dl *= 0.125f;
-      au_scan_collect<FAST, false>(cp, S, o, crow, cshift, N, K, i, lane, best.w2, best.j1, cnt, tmin, dummy);
+      au_scan_collect<FAST, false>(cp, S, o, crow, fix, N, K, i, lane, best.w2, best.j1, cnt, tmin, dummy);
     }
     if (lane == 0) {
       li[0] = (unsigned short)best.j1;
@@ -257,13 +276,13 @@ __device__ __forceinline__ AuBest au_rescan(const CostParams& cp, const AuShared
 // warp of the CTA runs the same number of barriers.  build == false: best / second best only (one attempt, no list).
 struct AuPart {
   AuBest best;
-  double tmin;
+  i64 tmin;
   int cnt;
 };
 constexpr int AU_STAGE_K = 16;
 template <int FAST>
 __device__ __forceinline__ AuBest au_rescan_coop(const CostParams& cp, const AuShared& S, const float4* Xb, const float* Cb,
-                                                 double cshift, int N, int K, int c0, int nC, int G, bool build,
+                                                 AuFix fix, int N, int K, int c0, int nC, int G, bool build,
                                                  AuPart (*part)[AU_WARPS], unsigned short (*stg_i)[AU_STAGE_K],
                                                  float (*stg_c)[AU_STAGE_K], int warp, int lane) {
   constexpr bool DENSE = FAST == AU_DENSE;
@@ -275,28 +294,28 @@ __device__ __forceinline__ AuBest au_rescan_coop(const CostParams& cp, const AuS
   const int per = (N + G - 1) / G;
   const int lo = min(sub * per, N), hi = min(lo + per, N);
   float dl = active ? S.delta[i] : 0.f;
-  const double guess = active ? S.Tw[i] : 0.0;
-  const bool has_guess = build && guess > -INFINITY && guess < INFINITY;
-  AuBest best = {INFINITY, INFINITY, INT_MAX, 0.f};
+  const i64 guess = active ? S.Tw[i] : 0;
+  const bool has_guess = build && guess > AU_NONE && guess < AU_INF;
+  AuBest best = {AU_INF, AU_INF, INT_MAX, 0.f};
   bool done = !active;
   const int natt = build ? 3 : 1;
   for (int a = 0; a < natt; ++a) {
-    double cut = -INFINITY;
+    i64 cut = AU_NONE;
     int j1k = -1;
     if (!done) {
       if (a == 0) {
-        if (has_guess) cut = guess + (double)dl;
+        if (has_guess) cut = guess + (i64)dl;
       } else {
-        cut = (a == 1) ? fmax(best.w1 + (double)dl, best.w2) : best.w2;
+        cut = (a == 1) ? max(best.w1 + (i64)dl, best.w2) : best.w2;
         j1k = best.j1;
       }
       int cnt;
-      double tmin;
-      AuBest bp = {INFINITY, INFINITY, INT_MAX, 0.f};
+      i64 tmin;
+      AuBest bp = {AU_INF, AU_INF, INT_MAX, 0.f};
       if (a == 0)
-        au_scan_range<FAST, true>(cp, S, o, crow, cshift, lo, hi, K, stg_i[warp], stg_c[warp], lane, cut, j1k, 0, cnt, tmin, bp);
+        au_scan_range<FAST, true>(cp, S, o, crow, fix, lo, hi, K, stg_i[warp], stg_c[warp], lane, cut, j1k, 0, cnt, tmin, bp);
       else
-        au_scan_range<FAST, false>(cp, S, o, crow, cshift, lo, hi, K, stg_i[warp], stg_c[warp], lane, cut, j1k, 0, cnt, tmin, bp);
+        au_scan_range<FAST, false>(cp, S, o, crow, fix, lo, hi, K, stg_i[warp], stg_c[warp], lane, cut, j1k, 0, cnt, tmin, bp);
       if (a == 0) {  // (au_warp_merge without the index fix-up: an empty slice keeps INT_MAX and loses every merge)
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) {
@@ -317,7 +336,7 @@ __device__ __forceinline__ AuBest au_rescan_coop(const CostParams& cp, const AuS
     __syncthreads();
     if (!done) {
       int tot = j1k >= 0 ? 1 : 0, off = tot, mine = 0;
-      double tminG = INFINITY;
+      i64 tminG = AU_INF;
       for (int t = 0; t < G; ++t) {
         const AuPart& q = part[a][r * G + t];
         if (t == sub) {
@@ -325,7 +344,7 @@ __device__ __forceinline__ AuBest au_rescan_coop(const CostParams& cp, const AuS
           mine = q.cnt;
         }
         tot += q.cnt;
-        tminG = fmin(tminG, q.tmin);
+        tminG = min(tminG, q.tmin);
         if (a == 0) best = (t == 0) ? q.best : au_merge(best, q.best);
       }
       if (a == 0 && best.j1 == INT_MAX) best.j1 = 0;
@@ -354,7 +373,7 @@ __device__ __forceinline__ AuBest au_rescan_coop(const CostParams& cp, const AuS
               li[0] = (unsigned short)best.j1;
               lc[0] = best.c1;
             }
-            S.Tw[i] = tot > K ? fmin(tminG, best.w2) : tminG;  // (entries cut off by the capacity tie with the second best)
+            S.Tw[i] = tot > K ? min(tminG, best.w2) : tminG;  // (entries cut off by the capacity tie with the second best)
             S.delta[i] = tot <= K / 2 ? dl * 2.f : dl;
           }
         }
@@ -365,10 +384,10 @@ __device__ __forceinline__ AuBest au_rescan_coop(const CostParams& cp, const AuS
   return best;
 }
 
-// Smallest and second-smallest of one non-negative double per lane (+inf: no entry), by integer min-reductions on the bit
-// patterns (non-negative doubles order like their bits).  l1 = lowest lane holding the smallest.
-__device__ __forceinline__ void au_top2(double w, int lane, double& w1, double& w2, int& l1) {
-  const unsigned long long kb = (unsigned long long)__double_as_longlong(w);
+// Smallest and second-smallest of one 64-bit w per lane (AU_INF: no entry), by integer min-reductions on the two halves
+// of the sign-flipped value (order-preserving as unsigned).  l1 = lowest lane holding the smallest.
+__device__ __forceinline__ void au_top2(i64 w, int lane, i64& w1, i64& w2, int& l1) {
+  const unsigned long long kb = (unsigned long long)w ^ 0x8000000000000000ull;
   unsigned hi = (unsigned)(kb >> 32), lo = (unsigned)kb;
   const unsigned m1h = __reduce_min_sync(0xffffffffu, hi);
   const unsigned m1l = __reduce_min_sync(0xffffffffu, hi == m1h ? lo : 0xffffffffu);
@@ -379,8 +398,8 @@ __device__ __forceinline__ void au_top2(double w, int lane, double& w1, double& 
   }
   const unsigned m2h = __reduce_min_sync(0xffffffffu, hi);
   const unsigned m2l = __reduce_min_sync(0xffffffffu, hi == m2h ? lo : 0xffffffffu);
-  w1 = __longlong_as_double((long long)(((unsigned long long)m1h << 32) | m1l));
-  w2 = (m2h == 0xffffffffu) ? (double)INFINITY : __longlong_as_double((long long)(((unsigned long long)m2h << 32) | m2l));
+  w1 = (i64)((((unsigned long long)m1h << 32) | m1l) ^ 0x8000000000000000ull);
+  w2 = (i64)((((unsigned long long)m2h << 32) | m2l) ^ 0x8000000000000000ull);  // all ones = AU_INF: no second entry
 }
 
 template <int FAST>
@@ -392,9 +411,9 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
   extern __shared__ float4 au_smem[];  // carved in decreasing alignment: float4, 8-byte, 4-byte, 2-byte arrays
   AuShared S;
   S.sY = au_smem;
-  S.price = reinterpret_cast<double*>(S.sY + (DENSE ? 0 : N));
+  S.price = reinterpret_cast<i64*>(S.sY + (DENSE ? 0 : N));
   S.bidval = reinterpret_cast<unsigned long long*>(S.price + N);
-  S.Tw = reinterpret_cast<double*>(S.bidval + N);
+  S.Tw = reinterpret_cast<i64*>(S.bidval + N);
   S.rbid = S.Tw + N;
   S.delta = reinterpret_cast<float*>(S.rbid + AU_RC);
   S.lcost = S.delta + N;
@@ -414,14 +433,14 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
   const float* Cb = DENSE ? Cd + (size_t)b * N * N : nullptr;  // row i of this pair's matrix: Cb + i * N
   for (int i = tid; i < N; i += AU_THREADS) {
     if (!DENSE) S.sY[i] = __ldg(Y + (size_t)b * N + i);
-    S.price[i] = 0.0;
+    S.price[i] = 0;
     S.bidval[i] = 0ull;
-    S.Tw[i] = -INFINITY;
+    S.Tw[i] = AU_NONE;
     S.owner[i] = -1;
   }
   __syncthreads();
-  // Cmax = max_ij C_ij sets the epsilon schedule; Cmin < 0 (possible for a caller-supplied matrix only) is shifted away so
-  // that every w = C - shift + price is a non-negative double
+  // the cost range Cmax - min(Cmin, 0) sets the epsilon schedule and the fixed-point scale (Cmin < 0 is possible for a
+  // caller-supplied matrix only; signed 64-bit arithmetic needs no shift)
   float cm = 0.f, cn = 0.f;
   bool nonfinite = false;
   for (int i = warp; i < N; i += AU_WARPS) {
@@ -458,7 +477,13 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
     cshift = fmin(cshift, s_red2[w]);
   }
   cmax -= cshift;
-  if (!(cmax > 0.0)) cmax = 1.0;  // all costs equal: any assignment is optimal; run one trivial phase
+  if (!(cmax > 0.0)) cmax = 1.0;  // all costs zero: any assignment is optimal; run one trivial phase
+  int cexp;
+  frexp(cmax, &cexp);  // cmax = m * 2^cexp, m in [0.5, 1)
+  const double Sd = ldexp(1.0, min(46 - cexp, 126));  // cmax * S in [2^45, 2^46): prices may rise to 2^17 Cmax before 64 bits end
+  AuFix fix;
+  fix.scale = (float)Sd;
+  const double unit = 1.0 / Sd;
   if (N == 1) {
     if (tid == 0) {
       sigma[(size_t)b] = 0;
@@ -467,21 +492,23 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
     }
     return;
   }
-  for (int i = tid; i < N; i += AU_THREADS) S.delta[i] = (float)(SHWD_AU_DELTA0 * cmax / N);
-  const double eps_final = cmax * 9.094947017729282e-13;  // 2^-40
+  for (int i = tid; i < N; i += AU_THREADS) S.delta[i] = (float)(SHWD_AU_DELTA0 * cmax * Sd / N);
+  const i64 eps_final = max((i64)(cmax * Sd * 9.094947017729282e-13), (i64)1);  // 2^-40 Cmax: 32 .. 64 units
+  const i64 eps_list = (i64)(cmax * Sd * SHWD_AU_LIST_EPS);
 #ifdef SHWD_AU_PROFILE
+  long long pf_hist_c[10] = {0}, pf_hist_n[10] = {0}, pf_hist_p[10] = {0};
   long long pf_top2 = 0, pf_neval = 0, pf_start = 0, pf_gs = 0, pf_rescan = 0, pf_apply = 0, pf_nresc = 0, pf_nlist = 0, pf_rounds = 0;
 #endif
   long long bids = 0;  // (warp 0's count of list bids + every thread's view of the parallel rounds is not needed: info only)
   int failed = 0;
-  for (double eps = cmax * 0.25;; eps = fmax(eps * AU_EPS_FACTOR, eps_final)) {
-    const bool lists = eps <= cmax * SHWD_AU_LIST_EPS;  // larger eps: plain parallel rounds of full scans
+  for (i64 eps = (i64)(cmax * Sd * SHWD_AU_EPS0);; eps = max((i64)((double)eps * AU_EPS_FACTOR), eps_final)) {
+    const bool lists = eps <= eps_list;  // larger eps: plain parallel rounds of full scans
     // ================= phase start: everybody unassigned, prices and lists kept; one parallel round from the lists
     __syncthreads();
     AU_PROF_T(t_start);
     for (int i = tid; i < N; i += AU_THREADS) S.owner[i] = -1;
     int pj[AU_PP];
-    double pbid[AU_PP];
+    i64 pbid[AU_PP];
 #pragma unroll
     for (int q = 0; q < AU_PP; ++q) {
       const int i = tid + q * AU_THREADS;
@@ -489,15 +516,15 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
       if (i < N) {
         const unsigned short* li = S.lidx + (size_t)i * K;
         const float* lc = S.lcost + (size_t)i * K;
-        const double tw = S.Tw[i];
-        if (tw > -INFINITY) {
-          double w1 = INFINITY, w2 = INFINITY, p1 = 0.0;
+        const i64 tw = S.Tw[i];
+        if (tw > AU_NONE) {
+          i64 w1 = AU_INF, w2 = AU_INF, p1 = 0;
           int j1 = -1;
           for (int k = 0; k < K; ++k) {
             const int j = li[k];
             if (j == 0xFFFF) break;
-            const double p = S.price[j];
-            const double w = ((double)lc[k] - cshift) + p;
+            const i64 p = S.price[j];
+            const i64 w = fix(lc[k]) + p;
             if (w < w1) {
               w2 = w1;
               w1 = w;
@@ -521,7 +548,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
     for (int q = 0; q < AU_PP; ++q) {
       const int i = tid + q * AU_THREADS;
       if (pj[q] >= 0)
-        atomicMax(S.bidval + pj[q], ((unsigned long long)__double_as_longlong(pbid[q]) & ~0x7FFull) | (unsigned long long)(AU_MAX_N - 1 - i));
+        atomicMax(S.bidval + pj[q], ((unsigned long long)pbid[q] & ~0x7FFull) | (unsigned long long)(AU_MAX_N - 1 - i));
     }
     __syncthreads();
 #pragma unroll
@@ -582,15 +609,15 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
             j = S.lidx[(size_t)i * K + lane];
             c = S.lcost[(size_t)i * K + lane];
           }
-          double p = 0.0, w = INFINITY;
+          i64 p = 0, w = AU_INF;
           int own = -1;
           if (j != 0xFFFF) {
             p = S.price[j];
             own = S.owner[j];
-            w = ((double)c - cshift) + p;
+            w = fix(c) + p;
           }
-          const double tw = S.Tw[i];
-          double w1, w2;
+          const i64 tw = S.Tw[i];
+          i64 w1, w2;
           int l1;
           AU_PROF_T(t_t2);
           au_top2(w, lane, w1, w2, l1);
@@ -645,31 +672,39 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
         if (nC <= AU_WARPS / 2) {  // few persons: several warps share a person's scan
           int G = AU_WARPS;
           while (G * nC > AU_WARPS) G >>= 1;
-          const AuBest best = au_rescan_coop<FAST>(cp, S, Xb, Cb, cshift, N, K, c0, nC, G, lists, s_part, s_stg_i, s_stg_c, warp, lane);
+          const AuBest best = au_rescan_coop<FAST>(cp, S, Xb, Cb, fix, N, K, c0, nC, G, lists, s_part, s_stg_i, s_stg_c, warp, lane);
           const int r = warp / G;
           if (r < nC && warp % G == 0 && lane == 0) {
-            const double bid = S.price[best.j1] + (best.w2 - best.w1) + eps;
+            const i64 bid = S.price[best.j1] + (best.w2 - best.w1) + eps;
             S.rj[r] = best.j1;
             S.rbid[r] = bid;
-            atomicMax(S.bidval + best.j1, ((unsigned long long)__double_as_longlong(bid) & ~0x1FFull) | (unsigned long long)(AU_RC - 1 - r));
+            atomicMax(S.bidval + best.j1, ((unsigned long long)bid & ~0x1FFull) | (unsigned long long)(AU_RC - 1 - r));
           }
         } else {
         for (int r = warp; r < nC; r += AU_WARPS) {
             const int i = S.R[c0 + r];
             const float4 o = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(Xb + i);
             const float* crow = DENSE ? Cb + (size_t)i * N : nullptr;
-            const AuBest best = lists ? au_rescan<FAST>(cp, S, o, crow, cshift, N, K, i, lane)
-                                      : au_scan_top2<FAST>(cp, S, o, crow, cshift, N, lane);
+            const AuBest best = lists ? au_rescan<FAST>(cp, S, o, crow, fix, N, K, i, lane)
+                                      : au_scan_top2<FAST>(cp, S, o, crow, fix, N, lane);
             if (lane == 0) {
-              const double bid = S.price[best.j1] + (best.w2 - best.w1) + eps;
+              const i64 bid = S.price[best.j1] + (best.w2 - best.w1) + eps;
               S.rj[r] = best.j1;
               S.rbid[r] = bid;
-              atomicMax(S.bidval + best.j1, ((unsigned long long)__double_as_longlong(bid) & ~0x1FFull) | (unsigned long long)(AU_RC - 1 - r));
+              atomicMax(S.bidval + best.j1, ((unsigned long long)bid & ~0x1FFull) | (unsigned long long)(AU_RC - 1 - r));
             }
           }
         }
         __syncthreads();
         AU_PROF_ADD(pf_rescan, t_rs);
+#ifdef SHWD_AU_PROFILE
+        {
+          const int bk = (nC <= 8 ? 0 : nC <= 16 ? 1 : nC <= 64 ? 2 : nC < AU_RC ? 3 : 4) + (lists ? 5 : 0);
+          pf_hist_c[bk] += clock64() - t_rs;
+          pf_hist_n[bk] += 1;
+          pf_hist_p[bk] += nC;
+        }
+#endif
         AU_PROF_T(t_ap);
         if (warp == 0) {
           for (int base = 0; base < nC; base += 32) {
@@ -717,7 +752,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
     for (int j = tid; j < N; j += AU_THREADS) sigma[(size_t)b * N + S.owner[j]] = j;
   }
   for (int i = tid; i < N; i += AU_THREADS)
-    if (price_out) price_out[(size_t)b * N + i] = S.price[i];
+    if (price_out) price_out[(size_t)b * N + i] = (double)S.price[i] * unit;
   if (tid == 0) {
     if (rounds_out) rounds_out[b] = (int)(bids > INT_MAX ? INT_MAX : bids);
     if (failed) atomicExch(status, 1);
@@ -726,6 +761,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
       double* po = price_out + (size_t)b * N;
       po[0] = (double)pf_start; po[1] = (double)pf_gs; po[2] = (double)pf_rescan; po[3] = (double)pf_apply;
       po[4] = (double)pf_nresc; po[5] = (double)pf_nlist; po[6] = (double)pf_rounds; po[7] = (double)pf_top2; po[8] = (double)pf_neval;
+      if (N >= 40) for (int q = 0; q < 10; ++q) { po[10 + 3 * q] = (double)pf_hist_c[q]; po[11 + 3 * q] = (double)pf_hist_n[q]; po[12 + 3 * q] = (double)pf_hist_p[q]; }
     }
 #endif
   }
