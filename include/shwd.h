@@ -128,6 +128,12 @@ int shwd_project_circle_bwd(const float* x, const float* U, int B, int N, int P,
 /* Line projection (Flow_ellipsoid.ipynb:208-220): x (B,N,3), theta (P,3) -> keys (B,P,N). */
 int shwd_project_line(const float* x, const float* theta, int B, int N, int P, float* keys, void* stream);
 int shwd_project_line_bwd(const float* theta, int B, int N, int P, const float* gkeys, float* gx, void* stream);
+/* Both backward projections with the chain rule of the per-pair slice MEAN folded in: gx[b] = (gw[b] / P) * (...), gw (B,)
+ * on the device -- no elementwise scaling pass after the launch (ops.SlicedLossFn.backward). */
+int shwd_project_circle_bwd_scaled(const float* x, const float* U, int B, int N, int P, const float* gkeys, const float* gw,
+                                   float* gx, void* stream);
+int shwd_project_line_bwd_scaled(const float* theta, int B, int N, int P, const float* gkeys, const float* gw, float* gx,
+                                 void* stream);
 /* Stable segmented sort (torch.sort(stable=True) order, NaN last, -0 == +0): keys (segs,len) -> sorted (segs,len),
  * perm (segs,len) int64.  Replaces torch.sort at max_spherical_sliced_w.py:163-164,224-225,232,235.
  * Rows of up to 16384 keys are sorted in shared memory (workspace 0 bytes); longer rows need the global scratch. */

@@ -39,6 +39,8 @@ SIGNATURES = {
     "shwd_project_circle_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "shwd_project_line": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "shwd_project_line_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "shwd_project_circle_bwd_scaled": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "shwd_project_line_bwd_scaled": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "shwd_segmented_sort_workspace_bytes": (_sz, [_i, _i]),
     "shwd_segmented_sort": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "shwd_segmented_sort_i32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -69,7 +69,9 @@ constexpr int PB_TILE = 256;  // slices staged per tile
 
 __global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd_kernel(const float* __restrict__ x, const float* __restrict__ U,
                                                                         int N, int P, const float* __restrict__ gk,
-                                                                        float* __restrict__ gx) {
+                                                                        const float* __restrict__ gw, float* __restrict__ gx) {
+  // gw (nullable): per-pair upstream gradient of the slice MEAN -- the result is scaled by gw[b] / P here instead of by
+  // an elementwise pass afterwards (same two roundings: the division, then the product)
   __shared__ float sU[PB_TILE * 6];
   __shared__ float red[PB_WARPS][3][32];
   const int b = blockIdx.y;
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd_kernel(const fl
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < PB_WARPS; ++w) t += red[w][k][pt];
+      if (gw) t = t * (__ldg(gw + b) / (float)P);
       gx[((size_t)b * N + blockIdx.x * 32) * 3 + threadIdx.x] = t;
     }
   }
@@ -136,7 +139,8 @@ __global__ void __launch_bounds__(PJ_THREADS) project_line_kernel(const float* _
 }
 
 __global__ void __launch_bounds__(PJ_THREADS) project_line_bwd_kernel(const float* __restrict__ th, int N, int P,
-                                                                      const float* __restrict__ gk, float* __restrict__ gx) {
+                                                                      const float* __restrict__ gk, const float* __restrict__ gw,
+                                                                      float* __restrict__ gx) {
   __shared__ float sT[PB_TILE * 3];
   __shared__ float red[PB_WARPS][3][32];
   const int b = blockIdx.y;
@@ -168,6 +172,7 @@ __global__ void __launch_bounds__(PJ_THREADS) project_line_bwd_kernel(const floa
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < PB_WARPS; ++w) t += red[w][k][pt];
+      if (gw) t = t * (__ldg(gw + b) / (float)P);
       gx[((size_t)b * N + blockIdx.x * 32) * 3 + threadIdx.x] = t;
     }
   }
@@ -978,7 +983,7 @@ extern "C" int shwd_project_circle_bwd(const float* x, const float* U, int B, in
   if (!x || !U || !gkeys || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B > 65535) return SHWD_ERR_UNSUPPORTED;
   dim3 grid((N + 31) / 32, B);
-  project_circle_bwd_kernel<<<grid, PJ_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, U, N, P, gkeys, gx);
+  project_circle_bwd_kernel<<<grid, PJ_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, U, N, P, gkeys, nullptr, gx);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }
@@ -996,7 +1001,28 @@ extern "C" int shwd_project_line_bwd(const float* theta, int B, int N, int P, co
   if (!theta || !gkeys || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B > 65535) return SHWD_ERR_UNSUPPORTED;
   dim3 grid((N + 31) / 32, B);
-  project_line_bwd_kernel<<<grid, PJ_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(theta, N, P, gkeys, gx);
+  project_line_bwd_kernel<<<grid, PJ_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(theta, N, P, gkeys, nullptr, gx);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+
+// The same with the slice-mean's chain rule folded in: gx[b] = (gw[b] / P) * sum_p ...  (gw: (B,) upstream gradient of the
+// per-pair mean over the P slices, on the device) -- what ops.SlicedLossFn.backward launches.
+extern "C" int shwd_project_circle_bwd_scaled(const float* x, const float* U, int B, int N, int P, const float* gkeys,
+                                              const float* gw, float* gx, void* stream) {
+  if (!x || !U || !gkeys || !gw || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (B > 65535) return SHWD_ERR_UNSUPPORTED;
+  dim3 grid((N + 31) / 32, B);
+  project_circle_bwd_kernel<<<grid, PJ_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, U, N, P, gkeys, gw, gx);
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+extern "C" int shwd_project_line_bwd_scaled(const float* theta, int B, int N, int P, const float* gkeys, const float* gw,
+                                            float* gx, void* stream) {
+  if (!theta || !gkeys || !gw || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (B > 65535) return SHWD_ERR_UNSUPPORTED;
+  dim3 grid((N + 31) / 32, B);
+  project_line_bwd_kernel<<<grid, PJ_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(theta, N, P, gkeys, gw, gx);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }

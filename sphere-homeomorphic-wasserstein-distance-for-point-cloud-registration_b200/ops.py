@@ -727,7 +727,7 @@ class SlicedLossFn(torch.autograd.Function):
         B, n, _ = x.shape
         m = y.shape[1]
         P = frames.shape[0]
-        scale = (gw.reshape(B, 1, 1).float() / P)
+        gwc = gw.reshape(B).contiguous().float()  # the kernels scale by gw[b] / P themselves
         gx = gy = None
         with torch.cuda.device(x.device):
             st = _stream()
@@ -736,11 +736,11 @@ class SlicedLossFn(torch.autograd.Function):
                     continue
                 g = torch.empty_like(c)
                 if ctx.mode == "line":
-                    _lib.check(lib.shwd_project_line_bwd(_ptr(frames), B, cnt, P, _ptr(gk), _ptr(g), st), "shwd_project_line_bwd")
+                    _lib.check(lib.shwd_project_line_bwd_scaled(_ptr(frames), B, cnt, P, _ptr(gk), _ptr(gwc), _ptr(g), st),
+                               "shwd_project_line_bwd_scaled")
                 else:
-                    _lib.check(lib.shwd_project_circle_bwd(_ptr(c), _ptr(frames), B, cnt, P, _ptr(gk), _ptr(g), st),
-                               "shwd_project_circle_bwd")
-                g = g * scale
+                    _lib.check(lib.shwd_project_circle_bwd_scaled(_ptr(c), _ptr(frames), B, cnt, P, _ptr(gk), _ptr(gwc), _ptr(g), st),
+                               "shwd_project_circle_bwd_scaled")
                 if idx == 0:
                     gx = g
                 else:
