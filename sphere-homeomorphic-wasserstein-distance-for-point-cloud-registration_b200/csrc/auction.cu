@@ -402,6 +402,25 @@ __device__ __forceinline__ void au_top2(i64 w, int lane, i64& w1, i64& w2, int& 
   w2 = (i64)((((unsigned long long)m2h << 32) | m2l) ^ 0x8000000000000000ull);  // all ones = AU_INF: no second entry
 }
 
+// The same for TWO persons at once, one per 16-lane half of the warp (K <= 16): a shuffle butterfly over xor 8, 4, 2, 1 never
+// leaves a half.  Every lane of a half ends with that half's (smallest, second smallest, lane-in-half of the smallest).
+__device__ __forceinline__ void au_top2_half(i64 w, int hl, i64& w1, i64& w2, int& l1) {
+  unsigned long long a1 = (unsigned long long)w ^ 0x8000000000000000ull, a2 = 0xffffffffffffffffull;
+  int la = hl;
+#pragma unroll
+  for (int s = 8; s > 0; s >>= 1) {
+    const unsigned long long b1 = __shfl_xor_sync(0xffffffffu, a1, s), b2 = __shfl_xor_sync(0xffffffffu, a2, s);
+    const int lb = __shfl_xor_sync(0xffffffffu, la, s);
+    const bool take = b1 < a1 || (b1 == a1 && lb < la);
+    a2 = take ? min(a1, b2) : min(a2, b1);
+    la = take ? lb : la;
+    a1 = take ? b1 : a1;
+  }
+  w1 = (i64)(a1 ^ 0x8000000000000000ull);
+  w2 = (i64)(a2 ^ 0x8000000000000000ull);
+  l1 = la;
+}
+
 template <int FAST>
 __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __restrict__ X, const float4* __restrict__ Y,
                                                              const float* __restrict__ Cd, int N, int K, CostParams cp,
@@ -497,6 +516,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
   const i64 eps_list = (i64)(cmax * Sd * SHWD_AU_LIST_EPS);
 #ifdef SHWD_AU_PROFILE
   long long pf_hist_c[10] = {0}, pf_hist_n[10] = {0}, pf_hist_p[10] = {0};
+  long long pf_q2 = 0;
   long long pf_top2 = 0, pf_neval = 0, pf_start = 0, pf_gs = 0, pf_rescan = 0, pf_apply = 0, pf_nresc = 0, pf_nlist = 0, pf_rounds = 0;
 #endif
   long long bids = 0;  // (warp 0's count of list bids + every thread's view of the parallel rounds is not needed: info only)
@@ -595,6 +615,93 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
       if (warp == 0) {
         __syncwarp();
         while (qcount > 0) {
+          if (lists && qcount >= 2) {
+            // ---- two persons per pass, one per half-warp: A = queue head bids first (Gauss-Seidel order); B's evaluation is
+            // taken only if A's bid did not touch an object of B's list (otherwise B stays at the head of the queue)
+            const int half = lane >> 4, hl = lane & 15;
+            const int q1 = (qhead + 1 == N) ? 0 : qhead + 1;
+            const int i2 = S.queue[half ? q1 : qhead];
+            int j2 = 0xFFFF;
+            float c2 = 0.f;
+            if (hl < K) {
+              j2 = S.lidx[(size_t)i2 * K + hl];
+              c2 = S.lcost[(size_t)i2 * K + hl];
+            }
+            i64 p2 = 0, wv = AU_INF;
+            int own2 = -1;
+            if (j2 != 0xFFFF) {
+              p2 = S.price[j2];
+              own2 = S.owner[j2];
+              wv = fix(c2) + p2;
+            }
+            const i64 tw2 = S.Tw[i2];
+            i64 h1, h2;
+            int hb;
+            au_top2_half(wv, hl, h1, h2, hb);
+            const bool ok2 = h2 <= tw2;  // (uniform within a half)
+            const bool okA = __shfl_sync(0xffffffffu, (int)ok2, 0) != 0, okB = __shfl_sync(0xffffffffu, (int)ok2, 16) != 0;
+            const int lbA = __shfl_sync(0xffffffffu, hb, 0), lbB = 16 + __shfl_sync(0xffffffffu, hb, 16);
+            const int jA = __shfl_sync(0xffffffffu, j2, lbA);
+            const bool clash = okA && __ballot_sync(0xffffffffu, half == 1 && j2 == jA) != 0u;
+            const int iA = __shfl_sync(0xffffffffu, i2, 0), iB = __shfl_sync(0xffffffffu, i2, 16);
+#ifdef SHWD_AU_PROFILE
+            pf_neval += clash ? 1 : 2;
+#endif
+            // A
+            qhead = q1;
+            --qcount;
+            if (!okA) {
+              if (lane == 0) {
+                S.R[nR] = iA;
+                S.Tw[iA] = h2;
+              }
+              ++nR;
+            } else {
+              if (lane == lbA) {
+                S.price[j2] = p2 + (h2 - h1) + eps;
+                S.owner[j2] = iA;
+              }
+              const int oldA = __shfl_sync(0xffffffffu, own2, lbA);
+              if (oldA >= 0) {
+                int qt = qhead + qcount;
+                if (qt >= N) qt -= N;
+                if (lane == 0) S.queue[qt] = oldA;
+                ++qcount;
+              }
+              ++bids;
+            }
+            // B
+            if (!clash) {
+              qhead = (qhead + 1 == N) ? 0 : qhead + 1;
+              --qcount;
+              if (!okB) {
+                if (lane == 16) {
+                  S.R[nR] = iB;
+                  S.Tw[iB] = h2;
+                }
+                ++nR;
+              } else {
+                if (lane == lbB) {
+                  S.price[j2] = p2 + (h2 - h1) + eps;
+                  S.owner[j2] = iB;
+                }
+                const int oldB = __shfl_sync(0xffffffffu, own2, lbB);
+                if (oldB >= 0) {
+                  int qt = qhead + qcount;
+                  if (qt >= N) qt -= N;
+                  if (lane == 0) S.queue[qt] = oldB;
+                  ++qcount;
+                }
+                ++bids;
+              }
+            }
+            __syncwarp();
+            if (bids > AU_MAX_BIDS) {
+              failed = 1;
+              break;
+            }
+            continue;
+          }
           const int i = S.queue[qhead];
           qhead = (qhead + 1 == N) ? 0 : qhead + 1;
           --qcount;
@@ -619,6 +726,9 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
           const i64 tw = S.Tw[i];
           i64 w1, w2;
           int l1;
+#ifdef SHWD_AU_PROFILE
+          if (qcount >= 1) ++pf_q2;  // (another person was waiting in the queue when this one was popped)
+#endif
           AU_PROF_T(t_t2);
           au_top2(w, lane, w1, w2, l1);
           AU_PROF_ADD(pf_top2, t_t2);
@@ -760,7 +870,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) auction_kernel(const float4* __
     if (price_out && N >= 9) {
       double* po = price_out + (size_t)b * N;
       po[0] = (double)pf_start; po[1] = (double)pf_gs; po[2] = (double)pf_rescan; po[3] = (double)pf_apply;
-      po[4] = (double)pf_nresc; po[5] = (double)pf_nlist; po[6] = (double)pf_rounds; po[7] = (double)pf_top2; po[8] = (double)pf_neval;
+      po[4] = (double)pf_nresc; po[5] = (double)pf_nlist; po[6] = (double)pf_rounds; po[7] = (double)pf_top2; po[8] = (double)pf_neval; po[9] = (double)pf_q2;
       if (N >= 40) for (int q = 0; q < 10; ++q) { po[10 + 3 * q] = (double)pf_hist_c[q]; po[11 + 3 * q] = (double)pf_hist_n[q]; po[12 + 3 * q] = (double)pf_hist_p[q]; }
     }
 #endif

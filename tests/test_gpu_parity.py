@@ -1124,6 +1124,46 @@ def test_exact_assignment_is_the_lp_optimum(shwd, B, N, kind, p):
         assert np.array_equal(ours, ref) or abs(excess) <= 1e-13, (b, int(rounds[b]), "relative excess cost %.3e" % excess)
 
 
+def test_exact_assignment_edge_cases(shwd):
+    """The candidate-list auction on the inputs that stress it: the largest supported clouds (8-entry lists), clouds with
+    many duplicated points (exact ties: whole groups of persons see identical objects), a cost matrix with negative
+    entries and one whose entries are all equal."""
+    from scipy.optimize import linear_sum_assignment
+    lib = shwd._lib.lib()
+    N = lib.shwd_exact_assignment_max_points()
+    g = torch.Generator().manual_seed(5)
+    x, y = torch.randn(1, N, 3, generator=g), torch.randn(1, N, 3, generator=g) * 0.7 + 0.3
+    sig, _, _, status = shwd.ops.exact_assignment(x.to(dev()), y.to(dev()), "sqeuclid", 2.0, return_info=True)
+    C = oracle.cost_matrix(x, y, "sqeuclid", 2)[0].double().numpy()
+    ref = linear_sum_assignment(C)[1]
+    ours = sig[0].cpu().numpy()
+    assert int(status.item()) == 0 and sorted(ours.tolist()) == list(range(N))
+    assert np.array_equal(ours, ref) or abs(C[np.arange(N), ours].sum() - C[np.arange(N), ref].sum()) <= 1e-12 * C[np.arange(N), ref].sum()
+    # duplicated points: 40 distinct locations, each 8 times, in both clouds
+    n = 320
+    x = torch.randn(1, 40, 3, generator=g).repeat(1, 8, 1)
+    y = (torch.randn(1, 40, 3, generator=g) * 0.5).repeat(1, 8, 1)[:, torch.randperm(n, generator=g)]
+    for kind in ("sqeuclid", "geodesic"):
+        sig, _, _, status = shwd.ops.exact_assignment(x.to(dev()), y.to(dev()), kind, 2.0, return_info=True)
+        xn, yn = (F.normalize(x, dim=-1), F.normalize(y, dim=-1)) if kind == "geodesic" else (x, y)
+        C = oracle.cost_matrix(xn, yn, kind, 2)[0].double().numpy()
+        r, c = linear_sum_assignment(C)
+        ours = sig[0].cpu().numpy()
+        assert int(status.item()) == 0 and sorted(ours.tolist()) == list(range(n))
+        assert abs(C[np.arange(n), ours].sum() - C[r, c].sum()) <= 1e-9 * max(C[r, c].sum(), 1e-30), kind
+    # explicit matrices: negative entries (signed fixed point, no shift) and a constant matrix
+    M = torch.randn(2, 150, 150, generator=g)
+    v = shwd.exact_emd2_dense(M.to(dev()))
+    for b in range(2):
+        r, c = linear_sum_assignment(M[b].double().numpy())
+        ref_v = M[b].double()[r, c].sum().item() / 150
+        assert abs(v[b].item() - ref_v) <= 2e-6 * abs(ref_v) + 1e-7
+    const = torch.full((1, 33, 33), 2.5)
+    sig = shwd.exact_assignment_dense(const.to(dev()))
+    assert sorted(sig[0].cpu().tolist()) == list(range(33))
+    assert shwd.exact_emd2_dense(const.to(dev())).item() == pytest.approx(2.5)
+
+
 @pytest.mark.parametrize("kind", ["sqeuclid", "geodesic"])
 def test_exact_solver_value_and_gradient_follow_pot_semantics(shwd, kind):
     """Cos_disimilarity_W / Geodesic_distance_W with solver="exact": the value mean_b emd2_b^(1/p) and the gradient POT's
