@@ -34,14 +34,15 @@ def _uniform(w, n):
 
 
 def emd2(a, b, M, processes=1, numItermax=100000, log=False, return_matrix=False, center_dual=True, numThreads=1):
-    """Exact OT cost <G*, M> for uniform marginals ``a`` (n,), ``b`` (n,) and the cost matrix ``M`` (n,n) on a CUDA device."""
+    """Exact OT cost <G*, M> for uniform marginals ``a`` (n,), ``b`` (m,) and the cost matrix ``M`` (n,m) on a CUDA device."""
     if log or return_matrix:
         raise NotImplementedError("ot.emd2(log=True / return_matrix=True) is not used on the reference's path")
     if not isinstance(M, torch.Tensor):
         raise TypeError("this ot.emd2 takes torch tensors (the reference passes torch tensors)")
-    if M.dim() != 2 or M.shape[0] != M.shape[1]:
-        raise NotImplementedError("only square cost matrices (equally sized clouds) are solved on the GPU, got %s" % (tuple(M.shape),))
-    n = M.shape[0]
-    if not (_uniform(a, n) and _uniform(b, n)):
+    if M.dim() != 2:
+        raise NotImplementedError("ot.emd2 takes one (n, m) cost matrix, got %s" % (tuple(M.shape),))
+    n, m = M.shape
+    if not (_uniform(a, n) and _uniform(b, m)):
         raise NotImplementedError("only uniform weights are solved on the GPU (what the reference passes)")
+    # n != m: the assignment of lcm(n, m) copies (raises NotImplementedError beyond the kernel's size)
     return shwd.exact_emd2_dense(M)

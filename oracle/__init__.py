@@ -21,11 +21,11 @@ from .sinkhorn import log_sinkhorn, entropic_w
 from .sliced import (project_circle, emd1d_circle, sliced_wasserstein_sphere_p1, euclid_sliced_wasserstein,
                      binary_search_circle, sliced_wasserstein_sphere)
 from .chamfer import chamfer_distance
-from .emd import exact_emd2
+from .emd import exact_emd2, exact_emd2_lp
 from . import data
 
 __all__ = [
     "sphere_map", "flow_regularization", "cost_matrix", "COST_KINDS", "log_sinkhorn", "entropic_w",
     "project_circle", "emd1d_circle", "sliced_wasserstein_sphere_p1", "euclid_sliced_wasserstein",
-    "binary_search_circle", "sliced_wasserstein_sphere", "chamfer_distance", "exact_emd2", "data",
+    "binary_search_circle", "sliced_wasserstein_sphere", "chamfer_distance", "exact_emd2", "exact_emd2_lp", "data",
 ]

@@ -21,3 +21,22 @@ def exact_emd2(C):
     plan = np.zeros_like(Cn)
     plan[r, c] = 1.0 / n
     return float((plan * Cn).sum()), torch.from_numpy(plan)
+
+
+def exact_emd2_lp(C):
+    """C: (n,m) tensor, n != m allowed -> (value, plan): the transport LP with uniform marginals 1/n, 1/m solved by
+    scipy.optimize.linprog (HiGHS) on the float64 cost -- the general problem ``ot.emd2`` solves when the two clouds of
+    s2_wasserstein.py:39-50 have different sizes.  Small problems only (n * m variables)."""
+    from scipy.optimize import linprog
+    Cn = C.detach().double().cpu().numpy()
+    n, m = Cn.shape
+    A = np.zeros((n + m, n * m))
+    for i in range(n):
+        A[i, i * m:(i + 1) * m] = 1.0
+    for j in range(m):
+        A[n + j, j::m] = 1.0
+    rhs = np.concatenate([np.full(n, 1.0 / n), np.full(m, 1.0 / m)])
+    res = linprog(Cn.reshape(-1), A_eq=A[:-1], b_eq=rhs[:-1], bounds=(0, None), method="highs")  # (one constraint is redundant)
+    if res.status != 0:
+        raise RuntimeError("linprog failed: %s" % res.message)
+    return float(res.fun), torch.from_numpy(res.x.reshape(n, m))

@@ -47,11 +47,12 @@ class _EntropicW(nn.Module):
         if self.solver != "auto":
             return self.solver == "exact"
         from .. import _lib
-        ok = x.shape[-2] == y.shape[-2] and x.shape[-2] <= _lib.lib().shwd_exact_assignment_max_points()
+        n, m = x.shape[-2], y.shape[-2]
+        ok = (n <= _lib.lib().shwd_exact_assignment_max_points()) if n == m else (ops.exact_copies(n, m) is not None)
         if not ok and not _warned_fallback[0]:
             import warnings
             _warned_fallback[0] = True
-            warnings.warn("%s: clouds of %d and %d points are outside the exact assignment kernel (equal sizes up to %d); "
+            warnings.warn("%s: clouds of %d and %d points are outside the exact assignment kernel (lcm(n, m) up to %d); "
                           "using the entropic solver (eps=%g, %d iterations) instead of the reference's ot.emd2"
                           % (type(self).__name__, x.shape[-2], y.shape[-2], _lib.lib().shwd_exact_assignment_max_points(),
                              self.eps, self.max_iter))

@@ -556,10 +556,30 @@ def exact_assignment_dense(C, return_info=False):
     return sig
 
 
+def exact_copies(n, m):
+    """Uniform marginals 1/n and 1/m with n != m: the transport LP is the assignment problem between L/n copies of every
+    source point and L/m copies of every target point, L = lcm(n, m) (each copy carries mass 1/L; any optimal assignment of
+    the copies, merged back, is an optimal plan and vice versa).  Returns (L/n, L/m), or None when L exceeds what the
+    assignment kernel takes."""
+    import math
+    L = n * m // math.gcd(n, m)
+    if L > _lib.lib().shwd_exact_assignment_max_points():
+        return None
+    return L // n, L // m
+
+
 def exact_emd2_dense(M):
-    """``ot.emd2(a, b, M)`` for uniform ``a``, ``b`` and a square cost matrix M (N,N) [or (B,N,N) -> (B,)]: the value
+    """``ot.emd2(a, b, M)`` for uniform ``a``, ``b`` and a cost matrix M (N,N') [or (B,N,N') -> (B,)]: the value
     (1/n) sum_i M[i, sigma(i)] accumulated in float64 like POT, returned in M's dtype; through autograd on the n matched
-    entries the gradient w.r.t. M is the optimal plan -- what POT's torch backend attaches."""
+    entries the gradient w.r.t. M is the optimal plan -- what POT's torch backend attaches.  N != N': solved on the
+    lcm(N, N') copies of ``exact_copies`` (rows / columns repeated; the gradient sums back over the copies)."""
+    if M.shape[-2] != M.shape[-1]:
+        rc = exact_copies(M.shape[-2], M.shape[-1])
+        if rc is None:
+            raise NotImplementedError("exact emd2 between %d and %d points needs lcm = %d copies; the assignment kernel takes %d"
+                                      % (M.shape[-2], M.shape[-1], M.shape[-2] * M.shape[-1] // __import__("math").gcd(M.shape[-2], M.shape[-1]),
+                                         _lib.lib().shwd_exact_assignment_max_points()))
+        return exact_emd2_dense(M.repeat_interleave(rc[0], dim=-2).repeat_interleave(rc[1], dim=-1))
     sigma, _, _, status = exact_assignment_dense(M, return_info=True)
     Mb = M if M.dim() == 3 else M.unsqueeze(0)
     c = torch.gather(Mb, 2, sigma.unsqueeze(-1)).squeeze(-1)  # (B,N): M[b, i, sigma(i)]
@@ -590,6 +610,13 @@ def exact_emd2(x, y, kind="sqeuclid", p=2.0):
     entries -- exactly the gradient POT attaches (d emd2 / dC = optimal plan)."""
     xc, _ = _as_cloud(x, "x")
     yc, _ = _as_cloud(y, "y")
+    if xc.shape[1] != yc.shape[1]:  # n != m: the assignment of lcm(n, m) copies (exact_copies); gradients sum over the copies
+        rc = exact_copies(xc.shape[1], yc.shape[1])
+        if rc is None:
+            raise ValueError("exact emd2 between %d and %d points: lcm(n, m) exceeds the %d points the assignment kernel takes"
+                             % (xc.shape[1], yc.shape[1], _lib.lib().shwd_exact_assignment_max_points()))
+        xc = xc.repeat_interleave(rc[0], dim=1)
+        yc = yc.repeat_interleave(rc[1], dim=1)
     sigma, _, _, status = exact_assignment(xc, yc, kind, p, return_info=True)
     ys = torch.gather(yc, 1, sigma.unsqueeze(-1).expand(-1, -1, 3))
     c = _pair_cost(xc, ys, kind, p)

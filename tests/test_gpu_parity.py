@@ -1164,6 +1164,39 @@ def test_exact_assignment_edge_cases(shwd):
     assert shwd.exact_emd2_dense(const.to(dev())).item() == pytest.approx(2.5)
 
 
+@pytest.mark.parametrize("n,m", [(6, 4), (30, 20), (5, 7), (64, 32), (1, 3)])
+def test_exact_solver_rectangular_is_the_transport_lp_optimum(shwd, n, m):
+    """Clouds of different sizes (train_W_COS.py:292-293 exposes --source_p_n / --target_p_n; ot.emd2 takes any n, m): the
+    uniform transport LP, solved as the assignment of lcm(n, m) copies, against scipy's LP solver on the same cost -- through
+    the loss object (value and both gradients, POT semantics d emd2 / dC = plan) and through the ot.emd2 drop-in."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dropin_ot"))
+    import ot
+    g = torch.Generator().manual_seed(n * 100 + m)
+    x = torch.randn(2, n, 3, generator=g)
+    y = torch.randn(2, m, 3, generator=g) * 0.8 + 0.2
+    xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    C = oracle.cost_matrix(xr, yr, "sqeuclid", 2)
+    ref = 0
+    for b in range(2):
+        val, plan = oracle.exact_emd2_lp(C[b])
+        ref = ref + torch.pow((plan.float() * C[b]).sum(), 0.5)
+    ref = ref / 2
+    ref.backward()
+    xg, yg = x.clone().to(dev()).requires_grad_(True), y.clone().to(dev()).requires_grad_(True)
+    out = shwd.losses.Cos_disimilarity_W(dev(), p=2)(xg, yg)  # the reference-style constructor: exact solve
+    out.backward()
+    assert out.item() == pytest.approx(ref.item(), rel=5e-6)
+    # (the LP optimum is generically unique, so the plans -- hence the gradients -- agree)
+    assert rel(xg.grad, xr.grad) < 1e-4 and rel(yg.grad, yr.grad) < 1e-4
+    M = C[0].detach().float().to(dev()).requires_grad_(True)
+    v = ot.emd2(torch.full((n,), 1.0 / n, device=dev()), torch.full((m,), 1.0 / m, device=dev()), M)
+    val0, plan0 = oracle.exact_emd2_lp(C[0])
+    assert v.item() == pytest.approx(val0, rel=5e-6)
+    v.backward()
+    assert torch.allclose(M.grad.cpu().double(), plan0, atol=1e-6)
+
+
 @pytest.mark.parametrize("kind", ["sqeuclid", "geodesic"])
 def test_exact_solver_value_and_gradient_follow_pot_semantics(shwd, kind):
     """Cos_disimilarity_W / Geodesic_distance_W with solver="exact": the value mean_b emd2_b^(1/p) and the gradient POT's
@@ -1440,8 +1473,8 @@ def test_dense_emd2_dropin_is_the_lp_optimum(shwd, N, kind):
     Mb = torch.stack([M, M.t().contiguous()]).to(dev())
     vb = shwd.exact_emd2_dense(Mb)
     assert vb.shape == (2,) and abs(vb[0].item() - val.item()) < 1e-7 and abs(vb[1].item() - ref) <= 2e-6 * max(abs(ref), 1e-30) + 1e-12
-    with pytest.raises(NotImplementedError):
-        ot.emd2(w, w, torch.rand(N, N + 1, device=dev()))
+    with pytest.raises(NotImplementedError):  # rectangular beyond the kernel: lcm(n, m) copies would not fit
+        ot.emd2(torch.full((3000,), 1 / 3000, device=dev()), torch.full((7,), 1 / 7, device=dev()), torch.rand(3000, 7, device=dev()))
     if N > 1:
         w2 = w.clone()
         w2[0] *= 1.5

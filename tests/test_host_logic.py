@@ -252,6 +252,9 @@ def test_exact_solver_option_and_limits():
     assert L.Geodesic_distance_W("cpu", p=2, solver="exact").solver == "exact"
     from shwd_b200 import _lib
     assert _lib.lib().shwd_exact_assignment_max_points() >= 2048
+    # clouds of different sizes: the assignment of lcm(n, m) copies, when that fits the kernel
+    from shwd_b200 import ops
+    assert ops.exact_copies(512, 1024) == (2, 1) and ops.exact_copies(6, 4) == (2, 3) and ops.exact_copies(1000, 1024) is None
     assert list(inspect.signature(L.binary_search_circle).parameters) == [
         "u_values", "v_values", "u_weights", "v_weights", "p", "Lm", "Lp", "tm", "tp", "eps", "require_sort"]
 
