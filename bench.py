@@ -388,7 +388,7 @@ def main():
         units_local = B
         sk = L.log_Sinkhorn_Distance_Loss(eps=EPS, max_iter=ITERS, batch_reduction="sum", type_of_cost_norm="L2", dense_outputs=False)
         h_t, h_s, h_out = pinned(tmpl), pinned(src), torch.empty(2).pin_memory()
-        launches = 4  # chamfer fwd, 2 sphere-map (packing), OT fwd
+        launches = 5  # chamfer fwd + its reduction, 2 sphere-map (packing), OT fwd
         h2d, d2h = 2 * B * N * 12, 8
 
         def eval_pair(t, s):
@@ -418,7 +418,7 @@ def main():
         units_local = B
         h_x, h_y = pinned(xs), pinned(ys)
         h_gx, h_gy, h_loss = torch.empty_like(h_x).pin_memory(), torch.empty_like(h_y).pin_memory(), torch.empty(1).pin_memory()
-        launches = 7  # 2 project, 2 sort, circular_wp, 2 project-bwd
+        launches = 5  # 2 project+sort (the sort CTAs compute their own keys), circular_wp, 2 project-bwd
         h2d, d2h = 2 * B * N * 12, 2 * B * N * 12 + 4
 
         def step_resident():
