@@ -1164,6 +1164,17 @@ def test_exact_assignment_edge_cases(shwd):
     assert shwd.exact_emd2_dense(const.to(dev())).item() == pytest.approx(2.5)
 
 
+def test_exact_assignment_randomised_against_scipy(shwd):
+    """tools/fuzz_auction.py for ten seconds: random sizes, cost kinds, duplicated / clustered clouds, tied / negative
+    matrices -- the optimal VALUE against scipy's exact assignment (4459 cases ran clean when this was written)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_auction.py"), "10", "7"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("n,m", [(6, 4), (30, 20), (5, 7), (64, 32), (1, 3)])
 def test_exact_solver_rectangular_is_the_transport_lp_optimum(shwd, n, m):
     """Clouds of different sizes (train_W_COS.py:292-293 exposes --source_p_n / --target_p_n; ot.emd2 takes any n, m): the
