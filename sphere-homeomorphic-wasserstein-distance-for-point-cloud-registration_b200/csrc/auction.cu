@@ -333,19 +333,39 @@ __device__ __forceinline__ AuBest au_rescan_coop(const CostParams& cp, const AuS
         part[a][warp].cnt = cnt;
       }
     }
-    __syncthreads();
+    // (the barrier doubles as the vote "every group of the CTA is done": the remaining attempts are skipped by everybody)
+    if (__syncthreads_and(done ? 1 : 0)) break;
     if (!done) {
-      int tot = j1k >= 0 ? 1 : 0, off = tot, mine = 0;
-      i64 tminG = AU_INF;
-      for (int t = 0; t < G; ++t) {
-        const AuPart& q = part[a][r * G + t];
-        if (t == sub) {
-          off = tot;
-          mine = q.cnt;
+      // the G partials of this group, one per lane: totals by warp reductions, the (best, second best) by a butterfly
+      const int base = j1k >= 0 ? 1 : 0;
+      AuPart q = {{AU_INF, AU_INF, INT_MAX, 0.f}, AU_INF, 0};
+      if (lane < G) q = part[a][r * G + lane];
+      int tot = q.cnt, before = lane < sub ? q.cnt : 0;
+      i64 tminG = q.tmin;
+#pragma unroll
+      for (int sft = 8; sft > 0; sft >>= 1) {  // G <= 16 lanes hold data, the others the neutral element
+        tot += __shfl_xor_sync(0xffffffffu, tot, sft);
+        before += __shfl_xor_sync(0xffffffffu, before, sft);
+        tminG = min(tminG, __shfl_xor_sync(0xffffffffu, tminG, sft));
+      }
+      tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+      before += __shfl_xor_sync(0xffffffffu, before, 16);
+      tminG = min(tminG, __shfl_xor_sync(0xffffffffu, tminG, 16));
+      tot += base;
+      const int off = base + before;
+      const int mine = __shfl_sync(0xffffffffu, q.cnt, sub);
+      if (a == 0) {
+        AuBest bb = q.best;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+          AuBest other;
+          other.w1 = __shfl_xor_sync(0xffffffffu, bb.w1, sft);
+          other.w2 = __shfl_xor_sync(0xffffffffu, bb.w2, sft);
+          other.j1 = __shfl_xor_sync(0xffffffffu, bb.j1, sft);
+          other.c1 = __shfl_xor_sync(0xffffffffu, bb.c1, sft);
+          bb = au_merge(bb, other);
         }
-        tot += q.cnt;
-        tminG = min(tminG, q.tmin);
-        if (a == 0) best = (t == 0) ? q.best : au_merge(best, q.best);
+        best = bb;
       }
       if (a == 0 && best.j1 == INT_MAX) best.j1 = 0;
       bool ok;
