@@ -25,9 +25,14 @@
 //
 // Reference quirks kept: the arc bookkeeping of Cost (v_0 + 1 appended, index clips at n-1 / m), theta detached in
 // the final Cost (:207), the secant point only where |dCp(tm) - dCm(tp)| > 1e-3 (:196-197), `done` re-evaluated from
-// dCp * dCm <= 0 every round.  One batch-global quirk is NOT reproduced: "re-wrap negatives only if the whole batch
-// has both signs" (:41-42, :82-83) -- here negatives are always re-wrapped; the two differ only if every CDF entry of
-// every slice in the call is negative, which needs frac > v_cdf[m-1] ~ 1 in all slices at once.
+// dCp * dCm <= 0 every round.  The batch-global test "re-wrap the negative CDF entries only if the call holds both signs"
+// (:41-42, :82-83) differs from "always re-wrap" only when EVERY entry of EVERY slice of the call is negative in the same
+// evaluation, i.e. frac > v_cdf[m-1] in all slices at once.  v_cdf[m-1] = fl(m * fl(1/m)) >= 1 - 2^-24 and frac <= 1, so
+// that needs frac == 1.0 exactly: theta in [-2^-25, 0) (the rounded theta - floor(theta) is then 1.0) for a cloud size m
+// whose last CDF entry rounds below 1.  A call of ONE slice decides that locally and is reproduced (Shift::keep_neg: the
+// CDF stays negative and un-rolled, exactly the reference's arithmetic); in a call of several slices every slice would
+// have to sit in that 3e-8 window in the same round, and the kernel re-wraps like the reference does whenever at least one
+// slice has a non-negative entry.
 // The rounds of different slices are independent in the reference as well: every unfinished slice halves the same
 // dyadic bracket each round, so all of them reach the stopping width in the same round.
 #include "common.cuh"
@@ -42,6 +47,7 @@ struct Circle {
   const float* u;     // sorted u values (n)            -- shared memory
   const float* v;     // sorted v values (m)
   int n, m;
+  bool lone;     // the call holds a single slice (the batch-global "both signs present" test is then local, see make_shift)
   float p;
   float wu, wv;  // float32(1/n), float32(1/m): torch.full((len,), 1/len, dtype=float32)
 };
@@ -57,6 +63,8 @@ __device__ __forceinline__ float vcdf_at(const Circle& c, int j) { return __fmul
 struct Shift {
   float fl, flp1, frac, r0;
   int j0;
+  bool keep_neg;  // every entry negative in a call of ONE slice: the reference leaves the CDF un-wrapped (:41-42, :82-83)
+  bool allneg;
 };
 
 template <bool P2>
@@ -76,7 +84,7 @@ __device__ __forceinline__ float r_cdf(const Circle& c, const Shift& s, int t) {
   int j = t + s.j0;
   if (j >= c.m) j -= c.m;
   const float x = __fsub_rn(vcdf_at(c, j), s.frac);
-  return x < 0.f ? __fadd_rn(x, 1.f) : x;
+  return (x < 0.f && !s.keep_neg) ? __fadd_rn(x, 1.f) : x;
 }
 __device__ __forceinline__ float r_val_in(const Circle& c, const Shift& s, int t) {
   int j = t + s.j0;
@@ -99,17 +107,28 @@ __device__ __forceinline__ Shift make_shift(const Circle& c, float theta) {
   while (lo < c.m && __fsub_rn(vcdf_at(c, lo), s.frac) < 0.f) ++lo;
   while (lo > 0 && !(__fsub_rn(vcdf_at(c, lo - 1), s.frac) < 0.f)) --lo;
   s.j0 = (lo == c.m) ? 0 : lo;
+  s.allneg = (lo == c.m);
+  s.keep_neg = s.allneg && c.lone;
   s.r0 = 0.f;
   s.r0 = r_cdf(c, s, 0);
   return s;
 }
 
-// #{i : u_cdf[i] < x}  (torch.searchsorted(u_cdf, x), left), in [0, n]
+// #{i : u_cdf[i] < x}  (torch.searchsorted(u_cdf, x), left), in [0, n] -- two probes, no loop.  u_cdf[i] = fl((i+1) fl(1/n))
+// = (i+1)/n (1 + e), |e| < 2^-22, so entry i is surely below x when i+1 <= xn - 2^-7 and surely not when i+1 >= xn + 2^-7
+// (xn <= 2^15); fl(x * n) is within 2^-9 of xn, hence with g = floor(fl(x * n)) the count is g - 1, g or g + 1: entries
+// g - 1 and g (0-based) decide.
 __device__ __forceinline__ int u_count_lt(const Circle& c, float x) {
-  int i = min(max(__float2int_rd(x * (float)c.n), 0), c.n);
-  while (i < c.n && ucdf_at(c, i) < x) ++i;
-  while (i > 0 && ucdf_at(c, i - 1) >= x) --i;
-  return i;
+  const int g = __float2int_rd(x * (float)c.n);
+  const int b = min(max(g, 1) - 1, c.n);
+  return b + (int)(b < c.n && ucdf_at(c, b) < x) + (int)(b + 1 < c.n && ucdf_at(c, b + 1) < x);
+}
+// #{i : u_cdf^+[i] <= x} for u_cdf^+ = cat(u_cdf, u_cdf[0] + 1)  (searchsorted(..., right=True)), given iu = u_count_lt(x):
+// u_cdf is strictly increasing (steps of 1/n >> its rounding), so at most the entry at iu equals x.
+__device__ __forceinline__ int u_count_le(const Circle& c, float x, int iu, float ucdf_wrap) {
+  int ium = iu + (int)(iu < c.n && ucdf_at(c, iu) <= x);
+  if (ium == c.n && ucdf_wrap <= x) ++ium;
+  return ium;
 }
 // #{t : r_cdf[t] < x}, in [0, m]
 __device__ __forceinline__ int r_count_lt(const Circle& c, const Shift& s, float x) {
@@ -136,25 +155,105 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* wtot) {
   return t;
 }
 
-// dCost :25-65 -> (dCp, dCm): right / left derivative of the cost in theta
-template <bool P2, int T>
-__device__ float2 dcost(const Circle& c, float theta, float2* wtot) {
+// What a thread remembers of one dCost evaluation (kept for the two ends of the bisection bracket).
+//
+// dCost(theta) depends on theta only through (floor(theta), j0, which CDF entries are negative) and, per rolled entry t,
+// through the two search results iu_t = #{u_cdf < r_cdf[t]} and ium_t = #{u_cdf^+ <= r_cdf[t]}: the summands themselves are
+// built from values (u, v + integer), not from frac.  C(theta) is piecewise linear and the bisection spends its second half
+// inside one or two linear pieces, re-evaluating the very same sum (n = m = 4096: pieces are 2^-12 wide, the bracket ends at
+// 2^-24).  For theta between the bracket ends and sharing (floor, j0, all-negative) with an end E, every r_cdf[t] is a
+// monotone function of frac (a rounded subtraction, then possibly a rounded +1), so iu_t and ium_t are monotone in theta:
+// iu_t(theta) <= iu_t(tm), >= iu_t(tp), and therefore   sum_t iu_t(theta) == sum_t iu_t(E)  <=>  iu_t(theta) == iu_t(E) for
+// every t  (the same for ium).  A thread whose two sums over ITS entries equal the end's has exactly the end's summands in
+// the end's order: its partial sums are the end's, bit for bit, and it skips the powers, the value loads and the clipping.
+// The searches alone are ~1/4 of an entry's instructions.  Whether a round tries the searches first is decided from the share
+// of warps that could have skipped in the previous round (clouds of different sizes have their kinks spread out, and a warp
+// only skips if none of its 32 x m/T entries has one inside the bracket).
+// Equal cloud sizes that are a power of two never get there: their kinks sit on the dyadic grid the midpoints walk, so the
+// bisection stops on "dCp * dCm <= 0" at round log2(n) (cfg3: round 12 of 4096 points) -- those calls run MEMO = false, which
+// keeps the kernel at 40 registers and six CTAs per SM.
+struct DcMemo {
+  float fl;
+  int j0;       // with the all-negative flag in bit 30; -1: nothing remembered
+  int siu, sium;
+  float dcp, dcm;  // this thread's partial sums
+};
+
+template <int T>
+__device__ __forceinline__ float2 block_sum2_vote(float a, float b, bool warp_skipped, float2* wtot, int* wskip, int& n_skipped) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    wtot[threadIdx.x >> 5] = make_float2(a, b);
+    wskip[threadIdx.x >> 5] = warp_skipped ? 1 : 0;
+  }
+  __syncthreads();
+  float2 t = make_float2(0.f, 0.f);
+  int k = 0;
+#pragma unroll
+  for (int w = 0; w < T / 32; ++w) {
+    t.x += wtot[w].x;
+    t.y += wtot[w].y;
+    k += wskip[w];
+  }
+  n_skipped = k;
+  return t;
+}
+
+// dCost :25-65 -> (dCp, dCm): right / left derivative of the cost in theta.  lo / hi: the evaluations at the bracket ends
+// (tm / tp; tm <= theta <= tp); out: this evaluation.  searches_first: see DcMemo (uniform over the CTA; updated).
+template <bool P2, int T, bool MEMO>
+__device__ float2 dcost(const Circle& c, float theta, float2* wtot, int* wskip, const DcMemo& lo, const DcMemo& hi, DcMemo& out,
+                        bool& searches_first) {
   const Shift s = make_shift(c, theta);
   const float u_wrap = __fadd_rn(c.u[0], 1.f), ucdf_wrap = __fadd_rn(ucdf_at(c, 0), 1.f);
+  const int key = s.j0 | (s.allneg ? (1 << 30) : 0);
+  const bool near_lo = MEMO && lo.fl == s.fl && lo.j0 == key;
+  const bool near_hi = MEMO && hi.fl == s.fl && hi.j0 == key;
   float dcp = 0.f, dcm = 0.f;
-  for (int t = threadIdx.x; t < c.m; t += T) {
-    const float x = r_cdf(c, s, t);
-    const int iu = u_count_lt(c, x);                       // searchsorted(u_cdf, x)
-    const float ui = c.u[min(iu, c.n - 1)];
-    int ium = iu;                                          // searchsorted(cat(u_cdf, u_cdf_0 + 1), x, right=True)
-    while (ium < c.n && ucdf_at(c, ium) <= x) ++ium;
-    if (ium == c.n && ucdf_wrap <= x) ++ium;
-    const float uim = (ium < c.n) ? c.u[ium] : u_wrap;     // index clipped at n -> u_0 + 1
-    const float v0 = r_val_in(c, s, t), v1 = r_val(c, s, t + 1);
-    dcp += __fsub_rn(powp<P2>(__fsub_rn(ui, v1), c.p), powp<P2>(__fsub_rn(ui, v0), c.p));
-    dcm += __fsub_rn(powp<P2>(__fsub_rn(uim, v1), c.p), powp<P2>(__fsub_rn(uim, v0), c.p));
+  int siu = 0, sium = 0;
+  bool same = false;  // this thread's summands are those of a bracket end
+  if (MEMO && searches_first && (near_lo || near_hi)) {
+    for (int t = threadIdx.x; t < c.m; t += T) {
+      const float x = r_cdf(c, s, t);
+      const int iu = u_count_lt(c, x);
+      const int ium = u_count_le(c, x, iu, ucdf_wrap);
+      siu += iu;
+      sium += ium;
+    }
+    if (near_lo && siu == lo.siu && sium == lo.sium) {
+      same = true; dcp = lo.dcp; dcm = lo.dcm;
+    } else if (near_hi && siu == hi.siu && sium == hi.sium) {
+      same = true; dcp = hi.dcp; dcm = hi.dcm;
+    }
   }
-  return block_sum2<T>(dcp, dcm, wtot);
+  if (!same) {
+    siu = 0;
+    sium = 0;
+    for (int t = threadIdx.x; t < c.m; t += T) {
+      const float x = r_cdf(c, s, t);
+      const int iu = u_count_lt(c, x);                       // searchsorted(u_cdf, x)
+      const float ui = c.u[min(iu, c.n - 1)];
+      const int ium = u_count_le(c, x, iu, ucdf_wrap);       // searchsorted(cat(u_cdf, u_cdf_0 + 1), x, right=True)
+      const float uim = (ium < c.n) ? c.u[ium] : u_wrap;     // index clipped at n -> u_0 + 1
+      const float v0 = r_val_in(c, s, t), v1 = r_val(c, s, t + 1);
+      dcp += __fsub_rn(powp<P2>(__fsub_rn(ui, v1), c.p), powp<P2>(__fsub_rn(ui, v0), c.p));
+      dcm += __fsub_rn(powp<P2>(__fsub_rn(uim, v1), c.p), powp<P2>(__fsub_rn(uim, v0), c.p));
+      if (MEMO) {
+        siu += iu;
+        sium += ium;
+      }
+    }
+    // (would the searches alone have sufficed?  feeds the next round's decision)
+    same = (near_lo && siu == lo.siu && sium == lo.sium) || (near_hi && siu == hi.siu && sium == hi.sium);
+  }
+  if (!MEMO) return block_sum2<T>(dcp, dcm, wtot);
+  int n_skipped;
+  const float2 tot = block_sum2_vote<T>(dcp, dcm, __all_sync(0xffffffffu, same), wtot, wskip, n_skipped);
+  searches_first = 2 * n_skipped >= T / 32;
+  out.fl = s.fl; out.j0 = key; out.siu = siu; out.sium = sium; out.dcp = dcp; out.dcm = dcm;
+  return tot;
 }
 
 // Cost :68-113, pass U.  Returns the cost (broadcast); gu (nullable, global) receives d cost / d u_sorted.
@@ -239,7 +338,7 @@ __device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv
   }
 }
 
-template <bool P2, int T>
+template <bool P2, int T, bool MEMO>
 __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict__ us, const float* __restrict__ vs,
                                                                  const int32_t* __restrict__ pu, const int32_t* __restrict__ pv, int n,
                                                                  int m, float p, float tm0, float tp0, float tol,
@@ -248,6 +347,7 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
                                                                  float* __restrict__ theta_out) {
   extern __shared__ float cw_smem[];
   __shared__ float2 wtot[T / 32];
+  __shared__ int wskip[T / 32];
   float* su = cw_smem;
   float* sv = su + n;
   const size_t sl = blockIdx.x;
@@ -258,16 +358,21 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
     sv[j] = __ldg(vs + sl * m + j);
   }
   __syncthreads();
-  Circle c = {su, sv, n, m, p, (float)(1.0 / (double)n), (float)(1.0 / (double)m)};
+  Circle c = {su, sv, n, m, gridDim.x == 1, p, (float)(1.0 / (double)n), (float)(1.0 / (double)m)};
 
   // binary_search_circle :172-205 (every quantity is uniform over the CTA: the sums are broadcast)
   float tm = tm0, tp = tp0, tc = (tm0 + tp0) * 0.5f;
+  DcMemo at_tm, at_tp, at_tc;  // dCost at the bracket ends (invalid until an end has been a midpoint) and at tc
+  at_tm.j0 = -1;
+  at_tp.j0 = -1;
+  bool searches_first = false;
   for (int round = 0; round < CW_MAX_ROUNDS; ++round) {
-    const float2 dc = dcost<P2, T>(c, tc, wtot);
+    const float2 dc = dcost<P2, T, MEMO>(c, tc, wtot, wskip, at_tm, at_tp, at_tc, searches_first);
     if (dc.x * dc.y <= 0.f) break;  // done: the optimum is the kink at tc
     if (__fsub_rn(tp, tm) < tol) {
-      const float2 dtp = dcost<P2, T>(c, tp, wtot);
-      const float2 dtm = dcost<P2, T>(c, tm, wtot);
+      DcMemo unused;
+      const float2 dtp = dcost<P2, T, MEMO>(c, tp, wtot, wskip, at_tm, at_tp, unused, searches_first);
+      const float2 dtm = dcost<P2, T, MEMO>(c, tm, wtot, wskip, at_tm, at_tp, unused, searches_first);
       const float ctm = cost_pass_u<P2, T>(c, tm, nullptr, nullptr, wtot);
       const float ctp = cost_pass_u<P2, T>(c, tp, nullptr, nullptr, wtot);
       const float den = __fsub_rn(dtm.x, dtp.y);  // dCptm - dCmtp
@@ -275,7 +380,7 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
         tc = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(ctp, ctm), __fmul_rn(tm, dtm.x)), __fmul_rn(tp, dtp.y)), den);
       break;
     }
-    if (dc.x < 0.f) tm = tc; else tp = tc;
+    if (dc.x < 0.f) { tm = tc; if (MEMO) at_tm = at_tc; } else { tp = tc; if (MEMO) at_tp = at_tc; }
     tc = __fmul_rn(__fadd_rn(tm, tp), 0.5f);
   }
   const float w = cost_pass_u<P2, T>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot);
@@ -312,11 +417,18 @@ static int circular_wp_dispatch(const float* us, const float* vs, const int32_t*
   // slices run 1024 threads per CTA instead (cfg4 SSW p=2: see DESIGN.md 4.4); shorter rows keep the 256-thread CTAs
   // (and their summation order).
   const bool big = smem > 56 * 1024;
-#define SHWD_LAUNCH_WP(P2, T)                                                                                                      \
+  // equal power-of-two sizes: the bisection ends on a kink at round log2(n), nothing to remember (see DcMemo)
+  const bool memo = !(n == m && (n & (n - 1)) == 0);
+#define SHWD_LAUNCH_WP_M(P2, T, MEMO)                                                                                              \
   do {                                                                                                                             \
     if (smem > 32 * 1024) /* static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here) */                            \
-      SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<P2, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    circular_wp_kernel<P2, T><<<S, T, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta);                        \
+      SHWD_CUDA_CHECK(                                                                                                             \
+          cudaFuncSetAttribute(circular_wp_kernel<P2, T, MEMO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    circular_wp_kernel<P2, T, MEMO><<<S, T, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta);                  \
+  } while (0)
+#define SHWD_LAUNCH_WP(P2, T)                                                                                                      \
+  do {                                                                                                                             \
+    if (memo) SHWD_LAUNCH_WP_M(P2, T, true); else SHWD_LAUNCH_WP_M(P2, T, false);                                                  \
   } while (0)
   if (p == 2.f) {
     if (big) SHWD_LAUNCH_WP(true, 1024); else SHWD_LAUNCH_WP(true, CW_THREADS);
@@ -324,6 +436,7 @@ static int circular_wp_dispatch(const float* us, const float* vs, const int32_t*
     if (big) SHWD_LAUNCH_WP(false, 1024); else SHWD_LAUNCH_WP(false, CW_THREADS);
   }
 #undef SHWD_LAUNCH_WP
+#undef SHWD_LAUNCH_WP_M
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }

@@ -1386,6 +1386,54 @@ def test_circular_wp_degenerate_rows(shwd, p):
         assert (w.cpu() - wr).abs().max().item() <= 1e-5 * max(wr.abs().max().item(), 1e-3) + 1e-9
 
 
+def test_circular_wp_single_slice_all_negative_cdf(shwd):
+    """The batch-global sign test of dCost / Cost (max_spherical_sliced_w.py:41-42, :82-83) in the one place where it is
+    reachable: a call of ONE slice whose rotation makes every shifted CDF entry negative (frac rounds to 1.0 for theta in
+    [-2^-25, 0), and fl(m * fl(1/m)) < 1 for this m).  The reference then leaves the CDF un-wrapped and un-rolled; a call
+    of one slice reproduces that, value, rotation and gradients."""
+    import numpy as np
+    ms = [m for m in range(40, 400) if np.float32(m) * np.float32(1.0 / m) < np.float32(1.0)]
+    assert ms, "no cloud size with a last CDF entry below 1 in the range"
+    tm, tp = -2.0 ** -24, 0.0
+    hit = 0
+    for m in ms[:4]:
+        n = m + 7
+        u, v = _tie_free(1, n, 300 + m), _tie_free(1, m, 400 + m, lo=0.1, width=0.8)
+        # the oracle must really be in the all-negative state at the first midpoint, otherwise the test tests nothing
+        vc = torch.cumsum(torch.full((m,), 1 / m), -1)
+        th0 = torch.tensor((tm + tp) / 2, dtype=torch.float32)
+        hit += int(bool(((vc - (th0 - torch.floor(th0))) < 0).all()))
+        ur, vr = u.clone().requires_grad_(True), v.clone().requires_grad_(True)
+        wr, thr = oracle.sliced.binary_search_circle(ur, vr, p=2, tm=tm, tp=tp, return_theta=True)
+        wr.sum().backward()
+        ug, vg = u.clone().to(dev()).requires_grad_(True), v.clone().to(dev()).requires_grad_(True)
+        us, _ = shwd.ops.SegmentedSortFn.apply(ug)
+        vs, _ = shwd.ops.SegmentedSortFn.apply(vg)
+        w, th = shwd.ops.CircularWpFn.apply(us, vs, 2.0, tm, tp, 1e-7)
+        w.sum().backward()
+        print("single-slice all-negative CDF m=%d: w %.3e theta %.3e gu %.3e gv %.3e" % (
+            m, rel(w, wr), (th.cpu() - thr).abs().max().item(), rel(ug.grad, ur.grad), rel(vg.grad, vr.grad)))
+        assert rel(w, wr) < TOL and (th.cpu() - thr).abs().max().item() < 2e-6
+        assert rel(ug.grad, ur.grad) < 1e-4 and rel(vg.grad, vr.grad) < 1e-4
+    assert hit > 0
+
+
+def test_circular_wp_memoised_rounds_do_not_depend_on_the_company(shwd):
+    """The bisection reuses a thread's partial sums of dCost from a bracket end when its searches return the end's
+    results (csrc/circular_wp.cu, DcMemo): a slice must get the same bits whether it runs alone, first or last in a call,
+    and whatever its neighbours are (the reuse decision is per CTA)."""
+    for n, m in ((4096, 4096), (1500, 1333), (257, 4000)):
+        u, v = _tie_free(6, n, 31 + n).to(dev()), _tie_free(6, m, 32 + m, lo=0.15, width=0.6).to(dev())
+        us, vs = torch.sort(u, -1)[0].contiguous(), torch.sort(v, -1)[0].contiguous()
+        w, th = shwd.ops.CircularWpFn.apply(us, vs, 2.0, -1.0, 1.0, 1e-7)
+        for r in (0, 3, 5):
+            w1, th1 = shwd.ops.CircularWpFn.apply(us[r:r + 1].contiguous(), vs[r:r + 1].contiguous(), 2.0, -1.0, 1.0, 1e-7)
+            # a lone slice differs from a slice in company only through the all-negative-CDF rule, unreachable from [-1, 1]
+            assert torch.equal(w1, w[r:r + 1]) and torch.equal(th1, th[r:r + 1])
+        w2, th2 = shwd.ops.CircularWpFn.apply(us.flip(0).contiguous(), vs.flip(0).contiguous(), 2.0, -1.0, 1.0, 1e-7)
+        assert torch.equal(w2.flip(0), w) and torch.equal(th2.flip(0), th)
+
+
 # ------------------------------------------------------------------------------------------------- CUDA graphs ----
 def _graph_cases(shwd):
     g = torch.Generator().manual_seed(5)
