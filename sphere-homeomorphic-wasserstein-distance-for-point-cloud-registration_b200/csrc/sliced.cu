@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
   __shared__ float wf[2][CW1_WARPS];
   __shared__ float s_first[CW1_THREADS];  // first merged value of each thread's chunk
   __shared__ float s_lastF[CW1_THREADS];  // F at the last entry of each thread's chunk
-  __shared__ uint32_t s_kmin[CW1_WARPS];
+  __shared__ uint32_t s_sel[3][4];  // (sum, largest key <= mid, smallest key > mid) of a selection round, triple-buffered
   const int nm = n + m;
   float* su = cw1_smem;                 // n (padded)
   float* sv = su + cw1_pad(n - 1) + 1;  // m (padded)
@@ -751,6 +751,7 @@ __global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
   const float wu = 1.f / n, wv = 1.f / m;
   for (int i = tid; i < n; i += CW1_THREADS) su[cw1_pad(i)] = __ldg(us + s * n + i);
   for (int j = tid; j < m; j += CW1_THREADS) sv[cw1_pad(j)] = __ldg(vs + s * m + j);
+  if (tid < 12) s_sel[tid >> 2][tid & 3] = ((tid & 3) == 2) ? 0xFFFFFFFFu : 0u;
   __syncthreads();
   // ---- merge path: u goes first on ties (u_i lands at i + #{v < u_i}; v_j at j + #{u <= v_j})
   const int c = (nm + CW1_THREADS - 1) / CW1_THREADS;  // <= C
@@ -823,7 +824,7 @@ __global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
       if (q == cnt - 1) dl[q] = nxt - last;
   }
   float tot = 0.f;
-  uint32_t kmin = 0xFFFFFFFFu;
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
   {
     float run = base;
 #pragma unroll
@@ -834,46 +835,85 @@ __global__ void __launch_bounds__(CW1_THREADS, (C <= 16 ? 2 : 1))
         const uint32_t kq = float_sort_key(run);
         if (!RECOMPUTE) key[q] = kq;
         kmin = min(kmin, kq);
+        kmax = max(kmax, kq);
       }
       tot += dl[q];
     }
     s_lastF[tid] = run;
   }
-  __syncthreads();  // wf[0] read by everyone before block_sum_pp reuses it; publishes s_lastF
-  int phase = 1;
-  tot = block_sum_pp(tot, wf, phase);
+  // ---- level median = the smallest key K with  S(K) := sum_{key <= K} delta >= 1/2.  A search on the VALUES with both ends
+  // snapped to keys that exist: [lo, hi] always holds K, lo and hi are keys of the row; a round evaluates S at the key of
+  // the midpoint of the two VALUES and, in the same pass, the largest key <= mid (kb) and the smallest key > mid (ka);
+  // S(mid) >= 1/2 -> hi = kb (S(kb) = S(mid)), else lo = ka (every key below ka sums to less than 1/2).  The interval of
+  // values at least halves and loses a key per round, so the search ends after ~log2(#distinct F values) rounds -- F takes
+  // few distinct values (levels 1/n apart, plus the rounding spread inside a level): cfg3 rows end in ~10 rounds where the
+  // plain bisection of the 32-bit key needed 32.  After 24 rounds the midpoint is taken between the KEYS (at most 32 more).
+  // Partial sums: a thread adds its own deltas in float32 (fixed order), the CTA adds the threads' partials in 2^-31 fixed
+  // point -- integers, so one redux.sync per warp and one shared-memory atomic per warp replace the shuffle tree and the
+  // sixteen-way read-back, and the total does not depend on the order of arrival.
   uint32_t kmed;
-  if (tot - 0.5f >= 0.f) {
-    // smallest key K with sum_{key <= K} delta - 0.5 >= 0
-    uint32_t lo = 0u, hi = 0xFFFFFFFFu;
-    while (lo < hi) {
-      const uint32_t mid = lo + ((hi - lo) >> 1);
-      float part = 0.f;
-      if (RECOMPUTE) {
-        float run = base;  // dl[q] == 0 beyond cnt, so the surplus entries add nothing whatever their recomputed key
-#pragma unroll
-        for (int q = 0; q < C; ++q) {
-          run += ((from_u >> q) & 1u) ? wu : -wv;
-          part += (float_sort_key(run) <= mid) ? dl[q] : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < C; ++q) part += (key[q] <= mid) ? dl[q] : 0.f;
+  {
+    constexpr float FIX = 2147483648.f;  // 2^31
+    constexpr uint32_t HALF = 1u << 30;
+    int set = 0;
+    auto exchange = [&](float part, uint32_t kb, uint32_t ka, uint32_t& S, uint32_t& KB, uint32_t& KA) {
+      uint32_t ps = __reduce_add_sync(0xffffffffu, __float2uint_rn(part * FIX));
+      kb = __reduce_max_sync(0xffffffffu, kb);
+      ka = __reduce_min_sync(0xffffffffu, ka);
+      if (lane == 0) {
+        atomicAdd(&s_sel[set][0], ps);
+        atomicMax(&s_sel[set][1], kb);
+        atomicMin(&s_sel[set][2], ka);
       }
-      part = block_sum_pp(part, wf, phase);
-      if (part - 0.5f >= 0.f) hi = mid; else lo = mid + 1u;
-    }
-    kmed = lo;
-  } else {
-    // the cumulative sum never reaches 0.5 (all cw < 0 -> all inf -> argmin = 0): the smallest F
-    for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-    if (lane == 0) s_kmin[warp] = kmin;
-    __syncthreads();
-    kmed = s_kmin[0];
+      __syncthreads();
+      S = s_sel[set][0];
+      KB = s_sel[set][1];
+      KA = s_sel[set][2];
+      const int clr = set == 0 ? 2 : set - 1;  // read last in the previous round, used again two rounds from now
+      if (tid < 3) s_sel[clr][tid] = (tid == 2) ? 0xFFFFFFFFu : 0u;
+      set = set == 2 ? 0 : set + 1;
+    };
+    uint32_t S, lo, hi;
+    exchange(tot, kmax, kmin, S, hi, lo);  // the whole row: total, largest and smallest key
+    if (S >= HALF) {
+      for (int round = 0; lo < hi; ++round) {
+        uint32_t mid = (round < 24) ? float_sort_key(0.5f * float_from_sort_key(lo) + 0.5f * float_from_sort_key(hi))
+                                    : lo + ((hi - lo) >> 1);
+        mid = min(max(mid, lo), hi - 1u);
+        float part = 0.f;
+        uint32_t kb = 0u, ka = 0xFFFFFFFFu;
+        if (RECOMPUTE) {
+          // (rows of more than 20 entries per thread recompute their keys and have no registers to spare for the two
+          //  snapped ends: plain bisection of the key interval, with the integer exchange)
+          mid = lo + ((hi - lo) >> 1);
+          float run = base;  // dl[q] == 0 beyond cnt, so the surplus entries add nothing whatever their recomputed key
 #pragma unroll
-    for (int w = 1; w < CW1_WARPS; ++w) kmed = min(kmed, s_kmin[w]);
+          for (int q = 0; q < C; ++q) {
+            run += ((from_u >> q) & 1u) ? wu : -wv;
+            part += (float_sort_key(run) <= mid) ? dl[q] : 0.f;
+          }
+          kb = mid;
+          ka = mid + 1u;
+        } else {
+#pragma unroll
+          for (int q = 0; q < C; ++q) {
+            const bool le = key[q] <= mid;
+            part += le ? dl[q] : 0.f;
+            kb = max(kb, le ? key[q] : 0u);
+            ka = min(ka, le ? 0xFFFFFFFFu : key[q]);
+          }
+        }
+        uint32_t KB, KA;
+        exchange(part, kb, ka, S, KB, KA);
+        if (S >= HALF) hi = KB; else lo = KA;
+      }
+      kmed = lo;
+    } else {
+      kmed = lo;  // the cumulative sum never reaches 1/2 (all cw < 0 -> all inf -> argmin = 0): the smallest F
+    }
   }
   const float med = float_from_sort_key(kmed);
+  int phase = 1;
   // ---- W and dW/d(merged value), the latter parked in su / sv (dead since the merge) for a coalesced write-out
   const bool want_g = gus || gvs;
   float acc = 0.f;
