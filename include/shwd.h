@@ -149,6 +149,10 @@ int shwd_segmented_sort_i32(const float* keys, int segs, int len, float* sorted,
  * values (B*P,N) (rebuilt from the sort keys: -0.0 comes back as +0.0) and the int32 stable-sort permutation.  Same keys,
  * same permutation as shwd_project_* followed by shwd_segmented_sort_i32.  N <= shwd_sort_projected_max_points(). */
 int shwd_sort_projected_max_points(void);
+/* Rows of up to 8192 keys whose keys are spread out (finite, at most 48 per bucket of a 4096-bucket monotone map of the
+ * value) are sorted by one bucket pass + an in-bucket rank instead of the radix passes; same (key, index) order, i.e. the
+ * same bits.  shwd_sort_set_method: 0 automatic (default), 1 radix passes only (A/B timing, tests).  Process-wide. */
+int shwd_sort_set_method(int method);
 int shwd_sort_projected(const float* x, const float* frames, int B, int N, int P, int mode, float* sorted, int32_t* perm,
                         void* stream);
 /* Circular W1 by level median on sorted circle coordinates (emd1D_circle, max_spherical_sliced_w.py:230-247):

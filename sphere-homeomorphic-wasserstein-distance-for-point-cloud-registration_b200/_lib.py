@@ -45,6 +45,7 @@ SIGNATURES = {
     "shwd_segmented_sort": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "shwd_segmented_sort_i32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "shwd_sort_projected_max_points": (_i, []),
+    "shwd_sort_set_method": (_i, [_i]),
     "shwd_sort_projected": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "shwd_circular_w1_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "shwd_circular_wp_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -460,27 +460,117 @@ __device__ __forceinline__ void radix_pass_trim(const RecBuf<true>& a, const Rec
   __syncthreads();
 }
 
+// ---- one-pass bucket sort for rows whose keys are spread out (what projections of a cloud are) -------------------------
+// torch.sort(stable=True) orders a row by the pair (key, input index), a total order: any method that realises it is "the
+// stable sort".  The keys of a slice are ~evenly spread over their range, so a MONOTONE map of the value onto SORT_NB buckets,
+//     bucket(t) = min(floor((t - tmin) * SORT_NB / (tmax - tmin)), SORT_NB - 1)        (float32 ops are monotone),
+// leaves about one record per bucket: count (shared-memory atomics on 16-bit halves), scan, scatter into the bucket's range
+// in ARRIVAL order (atomicAdd returning the slot), then every record counts the records of its own bucket that precede it
+// in (key, index) order -- a loop of the bucket's length, ~2 on average -- and moves to its final place.  Four light sweeps
+// over the row instead of three ranking passes of nine ballots each (cfg3: 280 -> see DESIGN.md 4.4).  Rows with a non-finite
+// key or a bucket above SORT_BUCKET_CAP records (ties, clustered keys) take the radix passes below; the decision is made
+// before anything is moved.
+constexpr int SORT_NB = 2 * SORT_WARPS * (1 << SORT_TRIM_MAXW) / 2;  // 4096 buckets: the radix counters' 8 KB as 16-bit halves
+constexpr int SORT_BUCKET_CAP = 48;
+constexpr int SORT_BUCKET_MIN_LEN = 128;
+
+__device__ __forceinline__ uint32_t sort_bucket(uint32_t key, float tmin, float scale) {
+  const float t = float_from_sort_key(key);
+  return min(__float2uint_rz(__fmul_rn(__fsub_rn(t, tmin), scale)), (uint32_t)(SORT_NB - 1));
+}
+
+// Returns false (CTA-uniform, nothing moved) if the row must take the radix passes; true: the row's outputs are written
+// (straight from the rank step: a record's final slot lies within a bucket's length of the slot it is read from, so a
+// warp's stores still fall into the same few 128-byte lines).  COUNTED: the caller filled the histogram while it produced
+// the keys (circle coordinates: the map of [0, 1) is known beforehand -- tmin = 0, scale = SORT_NB).
+template <bool COUNTED>
+__device__ __forceinline__ bool bucket_sort_row(const RecBuf<true>& a, const RecBuf<true>& b, int len, uint32_t kmin, uint32_t kmax,
+                                                uint32_t* hist32, uint32_t* wt, float* __restrict__ sorted_row,
+                                                int32_t* __restrict__ perm_row) {
+  constexpr int WORDS = SORT_NB / 2;
+  constexpr int WPT = WORDS / SORT_THREADS;  // counter words per thread in the scan
+  if (len < SORT_BUCKET_MIN_LEN || kmax >= 0xFF800000u || kmin <= 0x007FFFFFu) return false;  // short row / +-inf / NaN
+  float tmin = 0.f, scale = (float)SORT_NB;
+  if (!COUNTED) {
+    tmin = float_from_sort_key(kmin);
+    scale = __fdiv_rn((float)SORT_NB, __fsub_rn(float_from_sort_key(kmax), tmin));
+    if (!(scale < 3.0e38f)) return false;  // range below ~1e-35: every key would land in the two end buckets anyway
+    for (int i = threadIdx.x; i < WORDS; i += SORT_THREADS) hist32[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < len; i += SORT_THREADS) {
+      const uint32_t bk = sort_bucket(rec_ld_key<true>(a, i), tmin, scale);
+      atomicAdd(hist32 + (bk >> 1), 1u << ((bk & 1u) * 16u));
+    }
+    __syncthreads();
+  } else if (kmin < 0x80000000u) {
+    return false;  // a negative key: not circle coordinates after all
+  }
+  const uint32_t hs = (uint32_t)__cvta_generic_to_shared(hist32);
+  uint32_t c[WPT];
+  uint32_t tot = 0, mx = 0;
+#pragma unroll
+  for (int w = 0; w < WPT; ++w) {
+    c[w] = hist32[threadIdx.x * WPT + w];
+    tot += (c[w] & 0xffffu) + (c[w] >> 16);
+    mx = max(mx, max(c[w] & 0xffffu, c[w] >> 16));
+  }
+  if (__syncthreads_or(mx > (uint32_t)SORT_BUCKET_CAP)) return false;
+  uint32_t run = block_exscan_u32(tot, wt);
+#pragma unroll
+  for (int w = 0; w < WPT; ++w) {  // counters -> first slot of each bucket (the scatter advances them to the bucket's end)
+    const uint32_t lo = run, hi = run + (c[w] & 0xffffu);
+    hist32[threadIdx.x * WPT + w] = lo | (hi << 16);
+    run = hi + (c[w] >> 16);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < len; i += SORT_THREADS) {
+    const uint2 rec = rec_ld<true>(a, i);
+    const uint32_t bk = sort_bucket(rec.x, tmin, scale);
+    const uint32_t old = atomicAdd(hist32 + (bk >> 1), 1u << ((bk & 1u) * 16u));
+    rec_st<true>(b, (int)((old >> ((bk & 1u) * 16u)) & 0xffffu), rec);
+  }
+  __syncthreads();
+  for (int sl = threadIdx.x; sl < len; sl += SORT_THREADS) {
+    const uint2 rec = rec_ld<true>(b, sl);
+    const uint32_t bk = sort_bucket(rec.x, tmin, scale);
+    uint32_t end, beg = 0u;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(end) : "r"(hs + 2u * bk));
+    if (bk > 0u) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(beg) : "r"(hs + 2u * (bk - 1u)));
+    uint32_t r = beg;
+    for (uint32_t j = beg; j < end; ++j) {
+      const uint2 o = rec_ld<true>(b, (int)j);
+      r += (o.x < rec.x || (o.x == rec.x && o.y < rec.y)) ? 1u : 0u;
+    }
+    if (sorted_row) sorted_row[r] = float_from_sort_key(rec.x);
+    if (perm_row) perm_row[r] = (int32_t)rec.y;
+  }
+  return true;
+}
+
 // KEYS: 0 = keys read from `keys` (B*P rows of len), 1 = circle keys of cloud x through frames fr (P,3,2), 2 = line keys
 // through directions fr (P,3).  seg = b * P + p.
-template <int KEYS>
+template <int KEYS, bool BUCKETS>
 __global__ void __launch_bounds__(SORT_THREADS) segmented_sort_trim_kernel(const float* __restrict__ keys, const float* __restrict__ x,
                                                                            const float* __restrict__ fr, int P, int len,
                                                                            float* __restrict__ sorted, int32_t* __restrict__ perm32) {
   extern __shared__ uint2 sbuf[];
   __shared__ uint32_t hist32[SORT_WARPS * (1 << SORT_TRIM_MAXW) / 2];
   __shared__ uint32_t wt[SORT_WARPS];
-  __shared__ uint32_t s_or[SORT_WARPS], s_and[SORT_WARPS];
+  __shared__ uint32_t s_or[SORT_WARPS], s_and[SORT_WARPS], s_min[SORT_WARPS], s_max[SORT_WARPS];
   __shared__ float s_fr[6];
   const size_t seg = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RecBuf<true> a = make_recbuf<true>(sbuf), b = make_recbuf<true>(sbuf + len);
+  constexpr bool COUNTED = BUCKETS && KEYS == 1;  // circle coordinates: the bucket histogram is filled as the keys are made
   if (KEYS != 0) {
     const int p = (int)(seg % P);
     const int nf = KEYS == 1 ? 6 : 3;
     if (threadIdx.x < nf) s_fr[threadIdx.x] = __ldg(fr + (size_t)p * nf + threadIdx.x);
+    if (COUNTED)
+      for (int i = threadIdx.x; i < SORT_NB / 2; i += SORT_THREADS) hist32[i] = 0;
     __syncthreads();
   }
-  uint32_t vor = 0u, vand = 0xffffffffu;
+  uint32_t vor = 0u, vand = 0xffffffffu, kmin = 0xffffffffu, kmax = 0u;
   for (int i = threadIdx.x; i < len; i += SORT_THREADS) {
     float kf;
     if (KEYS == 0) {
@@ -493,16 +583,23 @@ __global__ void __launch_bounds__(SORT_THREADS) segmented_sort_trim_kernel(const
     const uint32_t k = float_sort_key(kf);
     vor |= k;
     vand &= k;
+    kmin = min(kmin, k);
+    kmax = max(kmax, k);
     rec_st<true>(a, i, make_uint2(k, (uint32_t)i));
+    if (COUNTED && len >= SORT_BUCKET_MIN_LEN) {
+      const uint32_t bk = sort_bucket(k, 0.f, (float)SORT_NB);
+      atomicAdd(hist32 + (bk >> 1), 1u << ((bk & 1u) * 16u));
+    }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    vor |= __shfl_xor_sync(0xffffffffu, vor, o);
-    vand &= __shfl_xor_sync(0xffffffffu, vand, o);
-  }
+  vor = __reduce_or_sync(0xffffffffu, vor);
+  vand = __reduce_and_sync(0xffffffffu, vand);
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
   if (lane == 0) {
     s_or[warp] = vor;
     s_and[warp] = vand;
+    s_min[warp] = kmin;
+    s_max[warp] = kmax;
   }
   __syncthreads();
   vor = 0u;
@@ -511,8 +608,14 @@ __global__ void __launch_bounds__(SORT_THREADS) segmented_sort_trim_kernel(const
   for (int w = 0; w < SORT_WARPS; ++w) {
     vor |= s_or[w];
     vand &= s_and[w];
+    kmin = min(kmin, s_min[w]);
+    kmax = max(kmax, s_max[w]);
   }
   const uint32_t varying = vor ^ vand;  // (CTA-uniform) bits in which the row's keys differ
+  if (BUCKETS && varying != 0u &&
+      bucket_sort_row<COUNTED>(a, b, len, kmin, kmax, hist32, wt, sorted ? sorted + seg * len : nullptr,
+                               perm32 ? perm32 + seg * len : nullptr))
+    return;
   if (varying != 0u) {
     const int lo = __ffs(varying) - 1, nbits = 32 - __clz(varying) - lo;
     const int passes = (nbits + SORT_TRIM_MAXW - 1) / SORT_TRIM_MAXW;
@@ -1104,14 +1207,29 @@ static int launch_sort_compact(const float* keys, int segs, int len, float* sort
   return SHWD_OK;
 }
 
+static int g_sort_method = 0;  // shwd_sort_set_method
+extern "C" int shwd_sort_set_method(int method) {
+  if (method < 0 || method > 1) return SHWD_ERR_INVALID_ARGUMENT;
+  g_sort_method = method;
+  return SHWD_OK;
+}
+
 // the trimmed-digit kernel (int32 permutation, values rebuilt from the keys): rows the uint2 layout is best for
 template <int KEYS>
 static int launch_sort_trim(const float* keys, const float* x, const float* fr, int P, int segs, int len, float* sorted, int32_t* perm32,
                             cudaStream_t s) {
   const size_t smem = 2 * (size_t)len * sizeof(uint2);
-  if (smem > 32 * 1024)
-    SHWD_CUDA_CHECK(cudaFuncSetAttribute(segmented_sort_trim_kernel<KEYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  segmented_sort_trim_kernel<KEYS><<<segs, SORT_THREADS, smem, s>>>(keys, x, fr, P, len, sorted, perm32);
+  if (g_sort_method == 1) {
+    if (smem > 32 * 1024)
+      SHWD_CUDA_CHECK(
+          cudaFuncSetAttribute(segmented_sort_trim_kernel<KEYS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    segmented_sort_trim_kernel<KEYS, false><<<segs, SORT_THREADS, smem, s>>>(keys, x, fr, P, len, sorted, perm32);
+  } else {
+    if (smem > 32 * 1024)
+      SHWD_CUDA_CHECK(
+          cudaFuncSetAttribute(segmented_sort_trim_kernel<KEYS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    segmented_sort_trim_kernel<KEYS, true><<<segs, SORT_THREADS, smem, s>>>(keys, x, fr, P, len, sorted, perm32);
+  }
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }

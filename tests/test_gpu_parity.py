@@ -469,9 +469,11 @@ def test_segmented_sort_is_bit_exact_stable(shwd, segs, length):
     assert torch.equal(v.cpu().view(torch.int32), ref_v.view(torch.int32))  # same bits, incl. signed zeros / NaN payloads
 
 
-@pytest.mark.parametrize("kind", ["circle", "signed", "ties", "constant", "tiny_range", "specials", "denormal_span"])
-@pytest.mark.parametrize("segs,length", [(5, 1), (7, 33), (3, 1000), (4, 4096), (2, 4224)])
-def test_trimmed_digit_sort_is_bit_exact_stable(shwd, kind, segs, length):
+@pytest.mark.parametrize("method", [0, 1])  # 0: bucket pass where the row allows it, 1: radix passes only
+@pytest.mark.parametrize("kind", ["circle", "signed", "ties", "constant", "tiny_range", "specials", "denormal_span", "clustered",
+                                  "few_ties_spread", "one_outlier"])
+@pytest.mark.parametrize("segs,length", [(5, 1), (7, 33), (3, 1000), (4, 4096), (2, 4224), (3, 8192)])
+def test_trimmed_digit_sort_is_bit_exact_stable(shwd, kind, segs, length, method):
     """The sliced losses' own sort (digits trimmed to the bits in which a row's keys differ, csrc/sliced.cu): the int32
     permutation equals torch.sort(stable=True) bit for bit on rows that differ in 27 bits (circle coordinates: 3 passes),
     32 bits (signed), a handful of bits, none at all, with NaN / +-inf / +-0, and across the denormal boundary."""
@@ -493,10 +495,23 @@ def test_trimmed_digit_sort_is_bit_exact_stable(shwd, kind, segs, length):
         k[:, 2::11] = -float("inf")
         k[:, 3::13] = 0.0
         k[:, 4::17] = -0.0
+    elif kind == "clustered":  # half of the keys inside 1e-4 of the range: some buckets overflow, some rows may not
+        k = torch.rand(segs, length, generator=g)
+        k[:, ::2] = 0.3 + 1e-4 * torch.rand(segs, (length + 1) // 2, generator=g)
+    elif kind == "few_ties_spread":  # spread keys with duplicated values: equal keys share a bucket, the index decides
+        k = torch.rand(segs, length, generator=g)
+        k[:, 1::3] = k[:, ::3][:, :k[:, 1::3].shape[1]]
+    elif kind == "one_outlier":  # the range is set by one key; everything else falls into a few buckets
+        k = torch.rand(segs, length, generator=g) * 1e-3
+        k[:, 0] = 1e6
     else:
         k = torch.rand(segs, length, generator=g) * 1e-37 * torch.randint(0, 3, (segs, length), generator=g).float() * 1e-3
     kd = k.to(dev())
-    so, pe = shwd.ops._sort_i32(kd)
+    assert shwd._lib.lib().shwd_sort_set_method(method) == 0
+    try:
+        so, pe = shwd.ops._sort_i32(kd)
+    finally:
+        shwd._lib.lib().shwd_sort_set_method(0)
     ref_v, ref_p = torch.sort(kd, dim=-1, stable=True)
     assert torch.equal(pe.long(), ref_p)
     assert torch.equal(so.isnan(), ref_v.isnan()) and torch.equal(so[~so.isnan()], ref_v[~ref_v.isnan()])  # (-0.0 == +0.0)
