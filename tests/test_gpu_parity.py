@@ -780,6 +780,30 @@ def test_project_circle_keys(shwd):
         assert d.max().item() < 1e-6, d.max().item()
 
 
+def test_project_circle_keys_special_points(shwd):
+    """The circle coordinate at the points where atan2 is decided by sign bits or is undefined: projections on the axes of
+    the frame (exact zeros of either sign), the zero vector (normalize -> (0, 0) -> atan2(-0, -0) = -pi -> 0), NaN and inf
+    coordinates (NaN).  Against the reference's own chain (max_spherical_sliced_w.py:270-279) in torch on the device, and the
+    achieved distance on ordinary points."""
+    U = torch.zeros(1, 3, 2)
+    U[0, 0, 0] = 1.0
+    U[0, 1, 1] = 1.0  # frame = (e_x, e_y): a = x, c = y
+    pts = [[1.0, 0.0, 0.3], [-1.0, 0.0, 0.3], [0.0, 1.0, 0.3], [0.0, -1.0, 0.3], [1.0, -0.0, 0.0], [-2.0, -0.0, 0.0],
+           [-0.0, 3.0, 0.0], [0.0, 0.0, 1.0], [-0.0, 0.0, 1.0], [0.0, -0.0, 1.0], [-0.0, -0.0, 1.0], [1e-30, 1e-30, 0.0],
+           [1e-20, -3e-20, 0.0], [float("nan"), 1.0, 0.0], [1.0, float("inf"), 0.0], [0.5, 0.5, 0.0], [-0.5, 0.5, 0.0]]
+    g = torch.Generator().manual_seed(3)
+    X = torch.cat([torch.tensor(pts), torch.randn(4000, 3, generator=g)]).unsqueeze(0).to(dev())
+    keys = shwd.ops.ProjectCircleFn.apply(X, U.to(dev()))[0, 0]
+    q = F.normalize(torch.matmul(U.to(dev()).transpose(-1, -2)[0], X[0].T).T, p=2, dim=-1)
+    ref = (torch.atan2(-q[:, 1], -q[:, 0]) + torch.pi) / (2 * torch.pi)
+    assert torch.equal(keys.isnan(), ref.isnan()) and int(ref.isnan().sum()) == 2
+    ok = ~ref.isnan()
+    d = (keys[ok] - ref[ok]).abs()
+    print("circle coordinate vs torch's chain on the device: max %.3e (%d special points, 4000 random)" % (d.max().item(), len(pts)))
+    assert d.max().item() < 2.5e-7  # both sit within ~1e-7 of the exact value (tools/fit_circle_key.py)
+    assert torch.equal(keys[:len(pts)][ok[:len(pts)]].round(decimals=4), ref[:len(pts)][ok[:len(pts)]].round(decimals=4))
+
+
 @pytest.mark.parametrize("p", [1, 2, 3])
 def test_euclid_sliced_w_matches_oracle(shwd, p):
     g = torch.Generator().manual_seed(p)
