@@ -171,6 +171,14 @@ size_t shwd_circular_wp_workspace_bytes(int S, int n, int m);
 int shwd_circular_wp(const float* us, const float* vs, int S, int n, int m, float p, float tm, float tp, float tol,
                      float* w, float* gus, float* gvs, float* theta, void* workspace, size_t workspace_bytes,
                      void* stream);
+/* The same with the reference's u_weights / v_weights (binary_search_circle, max_spherical_sliced_w.py:117,156-170): ucdf
+ * (S,n) / vcdf (S,m) are the per-slice CDF tables cumsum(weights[..., sorter], -1) the reference forms (non-decreasing);
+ * the closed-form searches of the uniform kernel become bisections on the tables.  gcu (S,n) / gcv (S,m) (nullable; need
+ * gus and gvs) receive d w / d ucdf, d w / d vcdf -- the path by which the reference's autograd reaches the weights (the
+ * merged CDF axis of the final Cost, :93-95).  n + m <= 28160. */
+int shwd_circular_wp_weighted(const float* us, const float* vs, const float* ucdf, const float* vcdf, int S, int n, int m,
+                              float p, float tm, float tp, float tol, float* w, float* gus, float* gvs, float* gcu, float* gcv,
+                              float* theta, void* stream);
 /* Euclidean sliced W on sorted projections (Flow_ellipsoid.ipynb:217-219): xs, ys (S,n) sorted -> acc (S) =
  * sum_n |xs-ys|^p ; gxs/gys (nullable) receive d acc / d(sorted values). */
 int shwd_euclid_sw(const float* xs, const float* ys, int S, int n, float p, float* acc, float* gxs, float* gys,

@@ -126,15 +126,19 @@ def _cost(theta, u_values, v_values, u_cdf, v_cdf, p):
     return torch.sum(delta * torch.abs(u_icdf - v_icdf) ** p, dim=-1)
 
 
-def binary_search_circle(u_values, v_values, p=2, Lm=10, Lp=10, tm=-1.0, tp=1.0, eps=1e-6, return_theta=False):
-    """``binary_search_circle`` :117-207 with uniform weights and ``require_sort=True``.  (P,n),(P,m) -> (P,)."""
+def binary_search_circle(u_values, v_values, p=2, Lm=10, Lp=10, tm=-1.0, tp=1.0, eps=1e-6, return_theta=False,
+                         u_weights=None, v_weights=None):
+    """``binary_search_circle`` :117-207 with ``require_sort=True``; uniform weights unless ``u_weights`` (n,) /
+    ``v_weights`` (m,) are given (:156-170: gathered through the sort permutations, then cumsum).  (P,n),(P,m) -> (P,)."""
     n, m = u_values.shape[-1], v_values.shape[-1]
     dt = u_values.dtype
     rows = u_values.shape[0]
-    u_values, _ = torch.sort(u_values, -1)
-    v_values, _ = torch.sort(v_values, -1)
-    u_cdf = torch.cumsum(torch.full((n,), 1 / n, dtype=dt).expand(rows, n), -1)
-    v_cdf = torch.cumsum(torch.full((m,), 1 / m, dtype=dt).expand(rows, m), -1)
+    uw = torch.full((n,), 1 / n, dtype=dt) if u_weights is None else u_weights
+    vw = torch.full((m,), 1 / m, dtype=dt) if v_weights is None else v_weights
+    u_values, u_perm = torch.sort(u_values, -1)
+    v_values, v_perm = torch.sort(v_values, -1)
+    u_cdf = torch.cumsum(uw[..., u_perm], -1)
+    v_cdf = torch.cumsum(vw[..., v_perm], -1)
     L = max(Lm, Lp)
     tm = torch.full((rows, m), tm, dtype=dt)
     tp = torch.full((rows, m), tp, dtype=dt)
@@ -163,10 +167,13 @@ def binary_search_circle(u_values, v_values, p=2, Lm=10, Lp=10, tm=-1.0, tp=1.0,
     return (w, tc[:, 0].detach()) if return_theta else w
 
 
-def sliced_wasserstein_sphere(Xs, Xt, U, p=2):
+def sliced_wasserstein_sphere(Xs, Xt, U, p=2, u_weights=None, v_weights=None):
     """``sliced_cost`` :251-286 for any p with an explicit frame tensor ``U``: mean over slices of W1 (p == 1) or
     of W_p^p (p != 1; no root is taken, :284-286)."""
     a = project_circle(Xs, U)
     b = project_circle(Xt, U)
-    w = emd1d_circle(a, b) if p == 1 else binary_search_circle(a, b, p=p)
+    if p == 1:
+        w = emd1d_circle(a, b, u_weights=u_weights, v_weights=v_weights)
+    else:
+        w = binary_search_circle(a, b, p=p, u_weights=u_weights, v_weights=v_weights)
     return torch.mean(w)

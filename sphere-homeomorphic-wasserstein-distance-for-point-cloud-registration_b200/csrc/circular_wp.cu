@@ -50,6 +50,8 @@ struct Circle {
   bool lone;     // the call holds a single slice (the batch-global "both signs present" test is then local, see make_shift)
   float p;
   float wu, wv;  // float32(1/n), float32(1/m): torch.full((len,), 1/len, dtype=float32)
+  const float* ucdf;  // W (caller-supplied weights) only: the slice's CDF tables cumsum(weights[sorter]) -- shared memory
+  const float* vcdf;
 };
 
 // u_cdf[i] = cumsum(full(1/n))[i] the way torch's CPU kernel forms it -- a double accumulator, every prefix rounded to
@@ -57,8 +59,12 @@ struct Circle {
 // double partial sum is exact ((i+1) * w needs < 40 bits) and its float32 rounding is the single rounding of the exact
 // product, i.e. __fmul_rn(float(i+1), w).  Two ALU instructions instead of a shared-memory load on the hottest path of the
 // bisection (dcost was bound by shared-memory wavefronts: ~12 loads per CDF entry, 7 of them from the two CDF tables).
-__device__ __forceinline__ float ucdf_at(const Circle& c, int i) { return __fmul_rn(__int2float_rn(i + 1), c.wu); }
-__device__ __forceinline__ float vcdf_at(const Circle& c, int j) { return __fmul_rn(__int2float_rn(j + 1), c.wv); }
+// W: non-uniform weights (u_weights / v_weights of the reference, :156-170) -- the CDFs are tables, every closed-form guess
+// below becomes a binary search; the structure of the passes is unchanged (they only need the CDFs to be non-decreasing).
+template <bool W>
+__device__ __forceinline__ float ucdf_at(const Circle& c, int i) { return W ? c.ucdf[i] : __fmul_rn(__int2float_rn(i + 1), c.wu); }
+template <bool W>
+__device__ __forceinline__ float vcdf_at(const Circle& c, int j) { return W ? c.vcdf[j] : __fmul_rn(__int2float_rn(j + 1), c.wv); }
 
 struct Shift {
   float fl, flp1, frac, r0;
@@ -80,37 +86,50 @@ __device__ __forceinline__ float dpowp(float d, float p) {
   return copysignf(p * powf(a, p - 1.f), d);
 }
 
+template <bool W>
 __device__ __forceinline__ float r_cdf(const Circle& c, const Shift& s, int t) {
   int j = t + s.j0;
   if (j >= c.m) j -= c.m;
-  const float x = __fsub_rn(vcdf_at(c, j), s.frac);
+  const float x = __fsub_rn(vcdf_at<W>(c, j), s.frac);
   return (x < 0.f && !s.keep_neg) ? __fadd_rn(x, 1.f) : x;
 }
+template <bool W>
 __device__ __forceinline__ float r_val_in(const Circle& c, const Shift& s, int t) {
   int j = t + s.j0;
   if (j >= c.m) j -= c.m;
-  const float x = __fsub_rn(vcdf_at(c, j), s.frac);
+  const float x = __fsub_rn(vcdf_at<W>(c, j), s.frac);
   return __fadd_rn(c.v[j], x < 0.f ? s.flp1 : s.fl);
 }
 // t in [0, m]: r_val[m] = r_val[0] + 1
+template <bool W>
 __device__ __forceinline__ float r_val(const Circle& c, const Shift& s, int t) {
-  return t >= c.m ? __fadd_rn(r_val_in(c, s, 0), 1.f) : r_val_in(c, s, t);
+  return t >= c.m ? __fadd_rn(r_val_in<W>(c, s, 0), 1.f) : r_val_in<W>(c, s, t);
 }
 
+template <bool W>
 __device__ __forceinline__ Shift make_shift(const Circle& c, float theta) {
   Shift s;
   s.fl = floorf(theta);
   s.flp1 = __fadd_rn(s.fl, 1.f);
   s.frac = __fsub_rn(theta, s.fl);
-  // first j with v_cdf_j - frac >= 0 (v_cdf is increasing): closed-form guess, then a local walk
-  int lo = min(max(__float2int_rd(s.frac * (float)c.m), 0), c.m);
-  while (lo < c.m && __fsub_rn(vcdf_at(c, lo), s.frac) < 0.f) ++lo;
-  while (lo > 0 && !(__fsub_rn(vcdf_at(c, lo - 1), s.frac) < 0.f)) --lo;
+  // first j with v_cdf_j - frac >= 0 (v_cdf is increasing): closed-form guess, then a local walk (W: bisection)
+  int lo;
+  if (W) {
+    lo = 0;
+    for (int hi = c.m; lo < hi;) {
+      const int mid = (lo + hi) >> 1;
+      if (__fsub_rn(c.vcdf[mid], s.frac) < 0.f) lo = mid + 1; else hi = mid;
+    }
+  } else {
+    lo = min(max(__float2int_rd(s.frac * (float)c.m), 0), c.m);
+    while (lo < c.m && __fsub_rn(vcdf_at<W>(c, lo), s.frac) < 0.f) ++lo;
+    while (lo > 0 && !(__fsub_rn(vcdf_at<W>(c, lo - 1), s.frac) < 0.f)) --lo;
+  }
   s.j0 = (lo == c.m) ? 0 : lo;
   s.allneg = (lo == c.m);
   s.keep_neg = s.allneg && c.lone;
   s.r0 = 0.f;
-  s.r0 = r_cdf(c, s, 0);
+  s.r0 = r_cdf<W>(c, s, 0);
   return s;
 }
 
@@ -118,23 +137,45 @@ __device__ __forceinline__ Shift make_shift(const Circle& c, float theta) {
 // = (i+1)/n (1 + e), |e| < 2^-22, so entry i is surely below x when i+1 <= xn - 2^-7 and surely not when i+1 >= xn + 2^-7
 // (xn <= 2^15); fl(x * n) is within 2^-9 of xn, hence with g = floor(fl(x * n)) the count is g - 1, g or g + 1: entries
 // g - 1 and g (0-based) decide.
+template <bool W>
 __device__ __forceinline__ int u_count_lt(const Circle& c, float x) {
+  if (W) {
+    int lo = 0;
+    for (int hi = c.n; lo < hi;) {
+      const int mid = (lo + hi) >> 1;
+      if (c.ucdf[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
   const int g = __float2int_rd(x * (float)c.n);
   const int b = min(max(g, 1) - 1, c.n);
-  return b + (int)(b < c.n && ucdf_at(c, b) < x) + (int)(b + 1 < c.n && ucdf_at(c, b + 1) < x);
+  return b + (int)(b < c.n && ucdf_at<W>(c, b) < x) + (int)(b + 1 < c.n && ucdf_at<W>(c, b + 1) < x);
 }
 // #{i : u_cdf^+[i] <= x} for u_cdf^+ = cat(u_cdf, u_cdf[0] + 1)  (searchsorted(..., right=True)), given iu = u_count_lt(x):
 // u_cdf is strictly increasing (steps of 1/n >> its rounding), so at most the entry at iu equals x.
+template <bool W>
 __device__ __forceinline__ int u_count_le(const Circle& c, float x, int iu, float ucdf_wrap) {
-  int ium = iu + (int)(iu < c.n && ucdf_at(c, iu) <= x);
+  int ium = iu + (int)(iu < c.n && ucdf_at<W>(c, iu) <= x);
+  if (W) {  // equal CDF entries (zero weights) are possible: walk over all of them
+    while (ium > iu && ium < c.n && c.ucdf[ium] <= x) ++ium;
+  }
   if (ium == c.n && ucdf_wrap <= x) ++ium;
   return ium;
 }
 // #{t : r_cdf[t] < x}, in [0, m]
+template <bool W>
 __device__ __forceinline__ int r_count_lt(const Circle& c, const Shift& s, float x) {
+  if (W) {
+    int lo = 0;
+    for (int hi = c.m; lo < hi;) {
+      const int mid = (lo + hi) >> 1;
+      if (r_cdf<W>(c, s, mid) < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
   int t = min(max(__float2int_rd((x - s.r0) * (float)c.m) + 1, 0), c.m);
-  while (t < c.m && r_cdf(c, s, t) < x) ++t;
-  while (t > 0 && r_cdf(c, s, t - 1) >= x) --t;
+  while (t < c.m && r_cdf<W>(c, s, t) < x) ++t;
+  while (t > 0 && r_cdf<W>(c, s, t - 1) >= x) --t;
   return t;
 }
 
@@ -203,11 +244,11 @@ __device__ __forceinline__ float2 block_sum2_vote(float a, float b, bool warp_sk
 
 // dCost :25-65 -> (dCp, dCm): right / left derivative of the cost in theta.  lo / hi: the evaluations at the bracket ends
 // (tm / tp; tm <= theta <= tp); out: this evaluation.  searches_first: see DcMemo (uniform over the CTA; updated).
-template <bool P2, int T, bool MEMO>
+template <bool P2, int T, bool MEMO, bool W>
 __device__ float2 dcost(const Circle& c, float theta, float2* wtot, int* wskip, const DcMemo& lo, const DcMemo& hi, DcMemo& out,
                         bool& searches_first) {
-  const Shift s = make_shift(c, theta);
-  const float u_wrap = __fadd_rn(c.u[0], 1.f), ucdf_wrap = __fadd_rn(ucdf_at(c, 0), 1.f);
+  const Shift s = make_shift<W>(c, theta);
+  const float u_wrap = __fadd_rn(c.u[0], 1.f), ucdf_wrap = __fadd_rn(ucdf_at<W>(c, 0), 1.f);
   const int key = s.j0 | (s.allneg ? (1 << 30) : 0);
   const bool near_lo = MEMO && lo.fl == s.fl && lo.j0 == key;
   const bool near_hi = MEMO && hi.fl == s.fl && hi.j0 == key;
@@ -216,9 +257,9 @@ __device__ float2 dcost(const Circle& c, float theta, float2* wtot, int* wskip, 
   bool same = false;  // this thread's summands are those of a bracket end
   if (MEMO && searches_first && (near_lo || near_hi)) {
     for (int t = threadIdx.x; t < c.m; t += T) {
-      const float x = r_cdf(c, s, t);
-      const int iu = u_count_lt(c, x);
-      const int ium = u_count_le(c, x, iu, ucdf_wrap);
+      const float x = r_cdf<W>(c, s, t);
+      const int iu = u_count_lt<W>(c, x);
+      const int ium = u_count_le<W>(c, x, iu, ucdf_wrap);
       siu += iu;
       sium += ium;
     }
@@ -232,12 +273,12 @@ __device__ float2 dcost(const Circle& c, float theta, float2* wtot, int* wskip, 
     siu = 0;
     sium = 0;
     for (int t = threadIdx.x; t < c.m; t += T) {
-      const float x = r_cdf(c, s, t);
-      const int iu = u_count_lt(c, x);                       // searchsorted(u_cdf, x)
+      const float x = r_cdf<W>(c, s, t);
+      const int iu = u_count_lt<W>(c, x);                       // searchsorted(u_cdf, x)
       const float ui = c.u[min(iu, c.n - 1)];
-      const int ium = u_count_le(c, x, iu, ucdf_wrap);       // searchsorted(cat(u_cdf, u_cdf_0 + 1), x, right=True)
+      const int ium = u_count_le<W>(c, x, iu, ucdf_wrap);       // searchsorted(cat(u_cdf, u_cdf_0 + 1), x, right=True)
       const float uim = (ium < c.n) ? c.u[ium] : u_wrap;     // index clipped at n -> u_0 + 1
-      const float v0 = r_val_in(c, s, t), v1 = r_val(c, s, t + 1);
+      const float v0 = r_val_in<W>(c, s, t), v1 = r_val<W>(c, s, t + 1);
       dcp += __fsub_rn(powp<P2>(__fsub_rn(ui, v1), c.p), powp<P2>(__fsub_rn(ui, v0), c.p));
       dcm += __fsub_rn(powp<P2>(__fsub_rn(uim, v1), c.p), powp<P2>(__fsub_rn(uim, v0), c.p));
       if (MEMO) {
@@ -257,36 +298,61 @@ __device__ float2 dcost(const Circle& c, float theta, float2* wtot, int* wskip, 
 }
 
 // Cost :68-113, pass U.  Returns the cost (broadcast); gu (nullable, global) receives d cost / d u_sorted.
-template <bool P2, int T>
-__device__ float cost_pass_u(const Circle& c, float theta, float* __restrict__ gu, const int32_t* __restrict__ pu, float2* wtot) {
-  const Shift s = make_shift(c, theta);
+// gcu (W only, nullable): d cost / d u_cdf[k].  The cost is sum_a delta_a h_a over the merged axis (delta_a = a - previous
+// entry, h_a = |u_icdf - v_icdf|^p at a), so d cost / d a = h_a - h_next(a): the entry's own h minus that of the entry
+// that follows it on the axis (the searches are not differentiated, like torch.searchsorted).
+template <bool P2, int T, bool W>
+__device__ float cost_pass_u(const Circle& c, float theta, float* __restrict__ gu, const int32_t* __restrict__ pu, float2* wtot,
+                             float* __restrict__ gcu = nullptr) {
+  const Shift s = make_shift<W>(c, theta);
   float acc = 0.f;
   for (int k = threadIdx.x; k < c.n; k += T) {
-    float prev = (k > 0) ? ucdf_at(c, k - 1) : 0.f;
-    const float xk = ucdf_at(c, k);
+    float prev = (k > 0) ? ucdf_at<W>(c, k - 1) : 0.f;
+    const float xk = ucdf_at<W>(c, k);
     const float U = c.u[k];
-    int t = (k > 0) ? r_count_lt(c, s, prev) : 0;
+    int t = (k > 0) ? r_count_lt<W>(c, s, prev) : 0;
     float g = 0.f;
     // v entries below u_cdf[k]: v-index t, u-index k
     while (t < c.m) {
-      const float rt = r_cdf(c, s, t);
+      const float rt = r_cdf<W>(c, s, t);
       if (rt >= xk) break;
-      const float delta = __fsub_rn(rt, prev), d = __fsub_rn(U, r_val_in(c, s, t));
+      const float delta = __fsub_rn(rt, prev), d = __fsub_rn(U, r_val_in<W>(c, s, t));
       acc = fmaf(delta, powp<P2>(d, c.p), acc);
       g = fmaf(delta, dpowp<P2>(d, c.p), g);
       prev = rt;
       ++t;
     }
     {  // the u entry itself: v-index = #{r < u_cdf[k]} = t (clipped at m)
-      const float delta = __fsub_rn(xk, prev), d = __fsub_rn(U, r_val(c, s, t));
-      acc = fmaf(delta, powp<P2>(d, c.p), acc);
+      const float delta = __fsub_rn(xk, prev), d = __fsub_rn(U, r_val<W>(c, s, t));
+      const float h = powp<P2>(d, c.p);
+      acc = fmaf(delta, h, acc);
       g = fmaf(delta, dpowp<P2>(d, c.p), g);
       prev = xk;
+      if (W && gcu) {
+        // the entry after u_cdf[k]: the next rolled v entry r[t] (>= u_cdf[k]) if it lies below u_cdf[k+1] (equal values: the u
+        // entry sorts first), else the u entry k + 1, else nothing.  Equal CDF entries (zero weights): searchsorted returns
+        // the FIRST index of the group, so every member of it reads the group's first value (kk).
+        int kk = k;
+        while (kk > 0 && ucdf_at<W>(c, kk - 1) == xk) --kk;
+        const float h0 = (kk == k) ? h : powp<P2>(__fsub_rn(c.u[kk], r_val<W>(c, s, t)), c.p);
+        float hn = 0.f;
+        const bool last = (k == c.n - 1);
+        const float rt = (t < c.m) ? r_cdf<W>(c, s, t) : 0.f;
+        if (t < c.m && (last || rt < ucdf_at<W>(c, k + 1))) {
+          const int iu = min((rt > xk) ? k + 1 : kk, c.n - 1);  // #{u_cdf < r[t]}
+          int tt = t;                                             // #{r < r[t]}
+          while (tt > 0 && r_cdf<W>(c, s, tt - 1) == rt) --tt;
+          hn = powp<P2>(__fsub_rn(c.u[iu], r_val_in<W>(c, s, tt)), c.p);
+        } else if (!last) {
+          hn = powp<P2>(__fsub_rn(c.u[(ucdf_at<W>(c, k + 1) == xk) ? kk : k + 1], r_val<W>(c, s, t)), c.p);
+        }
+        gcu[k] = h0 - hn;
+      }
     }
     if (k == c.n - 1) {  // axis entries above u_cdf[n-1]: u-index clipped to n-1
       while (t < c.m) {
-        const float rt = r_cdf(c, s, t);
-        const float delta = __fsub_rn(rt, prev), d = __fsub_rn(U, r_val_in(c, s, t));
+        const float rt = r_cdf<W>(c, s, t);
+        const float delta = __fsub_rn(rt, prev), d = __fsub_rn(U, r_val_in<W>(c, s, t));
         acc = fmaf(delta, powp<P2>(d, c.p), acc);
         g = fmaf(delta, dpowp<P2>(d, c.p), g);
         prev = rt;
@@ -298,22 +364,24 @@ __device__ float cost_pass_u(const Circle& c, float theta, float* __restrict__ g
   return block_sum2<T>(acc, 0.f, wtot).x;
 }
 
-// Cost, pass V: gv (global, indexed by sorted v position) receives d cost / d v_sorted.
-template <bool P2, int T>
-__device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv, const int32_t* __restrict__ pv) {
-  const Shift s = make_shift(c, theta);
+// Cost, pass V: gv (global, indexed by sorted v position) receives d cost / d v_sorted; gcv (W only, nullable)
+// d cost / d v_cdf[j] (see cost_pass_u; d v_cdf_theta / d v_cdf = 1, theta is detached).
+template <bool P2, int T, bool W>
+__device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv, const int32_t* __restrict__ pv,
+                            float* __restrict__ gcv = nullptr) {
+  const Shift s = make_shift<W>(c, theta);
   for (int t = threadIdx.x; t < c.m; t += T) {
-    float prev = (t > 0) ? r_cdf(c, s, t - 1) : 0.f;
-    const float xt = r_cdf(c, s, t);
-    const float V = r_val_in(c, s, t);
+    float prev = (t > 0) ? r_cdf<W>(c, s, t - 1) : 0.f;
+    const float xt = r_cdf<W>(c, s, t);
+    const float V = r_val_in<W>(c, s, t);
     int i = 0;
     if (t > 0) {  // first u entry above r_cdf[t-1]
-      i = u_count_lt(c, prev);
-      while (i < c.n && ucdf_at(c, i) <= prev) ++i;
+      i = u_count_lt<W>(c, prev);
+      while (i < c.n && ucdf_at<W>(c, i) <= prev) ++i;
     }
     float g = 0.f;
-    while (i < c.n && ucdf_at(c, i) < xt) {  // u entries inside (r[t-1], r[t]): v-index t
-      const float a = ucdf_at(c, i);
+    while (i < c.n && ucdf_at<W>(c, i) < xt) {  // u entries inside (r[t-1], r[t]): v-index t
+      const float a = ucdf_at<W>(c, i);
       g = fmaf(__fsub_rn(a, prev), dpowp<P2>(__fsub_rn(c.u[i], V), c.p), g);
       prev = a;
       ++i;
@@ -323,11 +391,11 @@ __device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv
     if (t == 0) {
       // the wrap-around partner r_val[m] = r_val[0] + 1 serves the u entries above r_cdf[m-1]
       const float Vw = __fadd_rn(V, 1.f);
-      float pw = r_cdf(c, s, c.m - 1);
-      int iw = u_count_lt(c, pw);
-      while (iw < c.n && ucdf_at(c, iw) <= pw) ++iw;
+      float pw = r_cdf<W>(c, s, c.m - 1);
+      int iw = u_count_lt<W>(c, pw);
+      while (iw < c.n && ucdf_at<W>(c, iw) <= pw) ++iw;
       for (; iw < c.n; ++iw) {
-        const float a = ucdf_at(c, iw);
+        const float a = ucdf_at<W>(c, iw);
         g = fmaf(__fsub_rn(a, pw), dpowp<P2>(__fsub_rn(c.u[iw], Vw), c.p), g);
         pw = a;
       }
@@ -335,16 +403,39 @@ __device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv
     int j = t + s.j0;
     if (j >= c.m) j -= c.m;
     gv[pv ? __ldg(pv + j) : j] = -g;
+    if (W && gcv) {
+      // own entry: u-index #{u_cdf < r[t]} = i, v-index #{r < r[t]} = the first member of r[t]'s group of equal entries (tt)
+      int tt = t;
+      while (tt > 0 && r_cdf<W>(c, s, tt - 1) == xt) --tt;
+      const float h = powp<P2>(__fsub_rn(c.u[min(i, c.n - 1)], r_val_in<W>(c, s, tt)), c.p);
+      // the entry after r[t]: the first u entry above it (index i2) if it does not exceed r[t+1] (equal values: u first), else
+      // the v entry t + 1, else nothing
+      int i2 = i;
+      while (i2 < c.n && ucdf_at<W>(c, i2) <= xt) ++i2;
+      const bool lastv = (t == c.m - 1);
+      const float rn = lastv ? 0.f : r_cdf<W>(c, s, t + 1);
+      float hn = 0.f;
+      if (i2 < c.n && (lastv || ucdf_at<W>(c, i2) <= rn)) {
+        hn = powp<P2>(__fsub_rn(c.u[i2], r_val<W>(c, s, t + 1)), c.p);  // v-index #{r < u_cdf[i2]} = t + 1 (m: the wrap entry)
+      } else if (!lastv) {
+        const bool tie = (rn == xt);
+        hn = powp<P2>(__fsub_rn(c.u[min(tie ? i : i2, c.n - 1)], r_val_in<W>(c, s, tie ? tt : t + 1)), c.p);
+      }
+      gcv[j] = h - hn;
+    }
   }
 }
 
-template <bool P2, int T, bool MEMO>
+template <bool P2, int T, bool MEMO, bool W = false>
 __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict__ us, const float* __restrict__ vs,
                                                                  const int32_t* __restrict__ pu, const int32_t* __restrict__ pv, int n,
                                                                  int m, float p, float tm0, float tp0, float tol,
                                                                  float* __restrict__ w_out,
                                                                  float* __restrict__ gus, float* __restrict__ gvs,
-                                                                 float* __restrict__ theta_out) {
+                                                                 float* __restrict__ theta_out,
+                                                                 const float* __restrict__ ucdfs = nullptr,
+                                                                 const float* __restrict__ vcdfs = nullptr,
+                                                                 float* __restrict__ gcus = nullptr, float* __restrict__ gcvs = nullptr) {
   extern __shared__ float cw_smem[];
   __shared__ float2 wtot[T / 32];
   __shared__ int wskip[T / 32];
@@ -357,8 +448,15 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
   for (int j = threadIdx.x; j < m; j += T) {
     sv[j] = __ldg(vs + sl * m + j);
   }
+  float* scu = sv + m;
+  float* scv = scu + n;
+  if (W) {
+    for (int i = threadIdx.x; i < n; i += T) scu[i] = __ldg(ucdfs + sl * n + i);
+    for (int j = threadIdx.x; j < m; j += T) scv[j] = __ldg(vcdfs + sl * m + j);
+  }
   __syncthreads();
-  Circle c = {su, sv, n, m, gridDim.x == 1, p, (float)(1.0 / (double)n), (float)(1.0 / (double)m)};
+  Circle c = {su, sv, n, m, gridDim.x == 1, p, (float)(1.0 / (double)n), (float)(1.0 / (double)m), W ? scu : nullptr,
+              W ? scv : nullptr};
 
   // binary_search_circle :172-205 (every quantity is uniform over the CTA: the sums are broadcast)
   float tm = tm0, tp = tp0, tc = (tm0 + tp0) * 0.5f;
@@ -367,14 +465,14 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
   at_tp.j0 = -1;
   bool searches_first = false;
   for (int round = 0; round < CW_MAX_ROUNDS; ++round) {
-    const float2 dc = dcost<P2, T, MEMO>(c, tc, wtot, wskip, at_tm, at_tp, at_tc, searches_first);
+    const float2 dc = dcost<P2, T, MEMO, W>(c, tc, wtot, wskip, at_tm, at_tp, at_tc, searches_first);
     if (dc.x * dc.y <= 0.f) break;  // done: the optimum is the kink at tc
     if (__fsub_rn(tp, tm) < tol) {
       DcMemo unused;
-      const float2 dtp = dcost<P2, T, MEMO>(c, tp, wtot, wskip, at_tm, at_tp, unused, searches_first);
-      const float2 dtm = dcost<P2, T, MEMO>(c, tm, wtot, wskip, at_tm, at_tp, unused, searches_first);
-      const float ctm = cost_pass_u<P2, T>(c, tm, nullptr, nullptr, wtot);
-      const float ctp = cost_pass_u<P2, T>(c, tp, nullptr, nullptr, wtot);
+      const float2 dtp = dcost<P2, T, MEMO, W>(c, tp, wtot, wskip, at_tm, at_tp, unused, searches_first);
+      const float2 dtm = dcost<P2, T, MEMO, W>(c, tm, wtot, wskip, at_tm, at_tp, unused, searches_first);
+      const float ctm = cost_pass_u<P2, T, W>(c, tm, nullptr, nullptr, wtot);
+      const float ctp = cost_pass_u<P2, T, W>(c, tp, nullptr, nullptr, wtot);
       const float den = __fsub_rn(dtm.x, dtp.y);  // dCptm - dCmtp
       if (fabsf(den) > 0.001f)
         tc = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(ctp, ctm), __fmul_rn(tm, dtm.x)), __fmul_rn(tp, dtp.y)), den);
@@ -383,8 +481,9 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
     if (dc.x < 0.f) { tm = tc; if (MEMO) at_tm = at_tc; } else { tp = tc; if (MEMO) at_tp = at_tc; }
     tc = __fmul_rn(__fadd_rn(tm, tp), 0.5f);
   }
-  const float w = cost_pass_u<P2, T>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot);
-  if (gvs) cost_pass_v<P2, T>(c, tc, gvs + sl * m, pv ? pv + sl * m : nullptr);
+  const float w = cost_pass_u<P2, T, W>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot,
+                                        (W && gcus) ? gcus + sl * n : nullptr);
+  if (gvs) cost_pass_v<P2, T, W>(c, tc, gvs + sl * m, pv ? pv + sl * m : nullptr, (W && gcvs) ? gcvs + sl * m : nullptr);
   if (threadIdx.x == 0) {
     w_out[sl] = w;
     if (theta_out) theta_out[sl] = tc;
@@ -404,12 +503,14 @@ extern "C" size_t shwd_circular_wp_workspace_bytes(int S, int n, int m) {
 
 static int circular_wp_dispatch(const float* us, const float* vs, const int32_t* pu, const int32_t* pv, int S, int n, int m, float p,
                                 float tm, float tp, float tol, float* w, float* gus, float* gvs, float* theta, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                size_t workspace_bytes, void* stream, const float* ucdf = nullptr, const float* vcdf = nullptr,
+                                float* gcu = nullptr, float* gcv = nullptr) {
   if (!us || !vs || !w || S < 0 || n <= 0 || m <= 0 || !(p > 0.f) || !(tm < tp)) return SHWD_ERR_INVALID_ARGUMENT;
   if (S == 0) return SHWD_OK;
   (void)workspace;
   (void)workspace_bytes;
-  const size_t smem = ((size_t)n + m) * sizeof(float);
+  const bool weighted = ucdf != nullptr;
+  const size_t smem = ((size_t)n + m) * sizeof(float) * (weighted ? 2 : 1);
   if (n > 32768 || m > 32768) return SHWD_ERR_UNSUPPORTED;  // exactness argument of ucdf_at: at most 2^15 weights per CDF
   if (smem > 220 * 1024) return SHWD_ERR_UNSUPPORTED;        // n + m <= 56320 per slice
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -418,7 +519,7 @@ static int circular_wp_dispatch(const float* us, const float* vs, const int32_t*
   // (and their summation order).
   const bool big = smem > 56 * 1024;
   // equal power-of-two sizes: the bisection ends on a kink at round log2(n), nothing to remember (see DcMemo)
-  const bool memo = !(n == m && (n & (n - 1)) == 0);
+  const bool memo = !(n == m && (n & (n - 1)) == 0) && !weighted;
 #define SHWD_LAUNCH_WP_M(P2, T, MEMO)                                                                                              \
   do {                                                                                                                             \
     if (smem > 32 * 1024) /* static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here) */                            \
@@ -426,9 +527,17 @@ static int circular_wp_dispatch(const float* us, const float* vs, const int32_t*
           cudaFuncSetAttribute(circular_wp_kernel<P2, T, MEMO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
     circular_wp_kernel<P2, T, MEMO><<<S, T, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta);                  \
   } while (0)
+#define SHWD_LAUNCH_WP_W(P2, T)                                                                                                    \
+  do {                                                                                                                             \
+    if (smem > 32 * 1024)                                                                                                          \
+      SHWD_CUDA_CHECK(cudaFuncSetAttribute(circular_wp_kernel<P2, T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                           (int)smem));                                                                           \
+    circular_wp_kernel<P2, T, false, true><<<S, T, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta, ucdf,     \
+                                                               vcdf, gcu, gcv);                                                   \
+  } while (0)
 #define SHWD_LAUNCH_WP(P2, T)                                                                                                      \
   do {                                                                                                                             \
-    if (memo) SHWD_LAUNCH_WP_M(P2, T, true); else SHWD_LAUNCH_WP_M(P2, T, false);                                                  \
+    if (weighted) SHWD_LAUNCH_WP_W(P2, T); else if (memo) SHWD_LAUNCH_WP_M(P2, T, true); else SHWD_LAUNCH_WP_M(P2, T, false);      \
   } while (0)
   if (p == 2.f) {
     if (big) SHWD_LAUNCH_WP(true, 1024); else SHWD_LAUNCH_WP(true, CW_THREADS);
@@ -436,6 +545,7 @@ static int circular_wp_dispatch(const float* us, const float* vs, const int32_t*
     if (big) SHWD_LAUNCH_WP(false, 1024); else SHWD_LAUNCH_WP(false, CW_THREADS);
   }
 #undef SHWD_LAUNCH_WP
+#undef SHWD_LAUNCH_WP_W
 #undef SHWD_LAUNCH_WP_M
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
@@ -454,4 +564,16 @@ extern "C" int shwd_circular_wp_scatter(const float* us, const float* vs, const 
   if (!perm_u || !perm_v || !gku || !gkv) return SHWD_ERR_INVALID_ARGUMENT;
   return circular_wp_dispatch(us, vs, perm_u, perm_v, S, n, m, p, tm, tp, tol, w, gku, gkv, theta, workspace, workspace_bytes,
                               stream);
+}
+
+// binary_search_circle with u_weights / v_weights (max_spherical_sliced_w.py:156-170): ucdf (S,n) / vcdf (S,m) are the per-slice
+// CDF tables cumsum(weights[..., sorter], -1) the reference forms; gcu / gcv (nullable) receive d W / d ucdf, d W / d vcdf (the
+// reference's autograd reaches the weights through the merged CDF axis of the final Cost, :93-95).  n + m <= 28160.
+extern "C" int shwd_circular_wp_weighted(const float* us, const float* vs, const float* ucdf, const float* vcdf, int S, int n, int m,
+                                         float p, float tm, float tp, float tol, float* w, float* gus, float* gvs, float* gcu,
+                                         float* gcv, float* theta, void* stream) {
+  if (!ucdf || !vcdf) return SHWD_ERR_INVALID_ARGUMENT;
+  if ((gcu || gcv) && !(gus && gvs)) return SHWD_ERR_INVALID_ARGUMENT;  // the CDF gradients ride on the gradient passes
+  return circular_wp_dispatch(us, vs, nullptr, nullptr, S, n, m, p, tm, tp, tol, w, gus, gvs, theta, nullptr, 0, stream, ucdf, vcdf,
+                              gcu, gcv);
 }

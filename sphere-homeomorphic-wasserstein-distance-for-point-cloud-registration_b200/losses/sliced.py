@@ -37,14 +37,21 @@ def emd1D_circle(u_values, v_values, u_weights=None, v_weights=None, p=1, requir
 def binary_search_circle(u_values, v_values, u_weights=None, v_weights=None, p=1, Lm=10, Lp=10, tm=-1, tp=1, eps=1e-6,
                          require_sort=True):
     """Circular W_p^p per row by bisection on the rotation: (S,n),(S,m) -> (S,)  (max_spherical_sliced_w.py:117-207).
-    Uniform weights.  Every round of the reference's host-synchronised loop runs inside one kernel launch."""
-    if u_weights is not None or v_weights is not None:
-        raise NotImplementedError("binary_search_circle with non-uniform weights: the bisection kernel evaluates the uniform "
-                                  "CDFs in closed form; no caller in the reference passes weights (sliced_cost is always "
-                                  "called with u_weights=v_weights=None, max_spherical_sliced_w.py:518-533)")
+    Every round of the reference's host-synchronised loop runs inside one kernel launch.  With ``u_weights`` / ``v_weights``
+    ((n,) or (S,n); gathered through the sort permutations, :166-170) the kernel searches per-slice CDF tables instead of the
+    closed-form uniform CDFs; the weights receive gradients through the final cost, like the reference's autograd."""
+    pu = pv = None
     if require_sort:
-        u_values, _ = ops.SegmentedSortFn.apply(u_values.contiguous().float())
-        v_values, _ = ops.SegmentedSortFn.apply(v_values.contiguous().float())
+        u_values, pu = ops.SegmentedSortFn.apply(u_values.contiguous().float())
+        v_values, pv = ops.SegmentedSortFn.apply(v_values.contiguous().float())
+    if u_weights is not None or v_weights is not None:
+        S, n = u_values.shape
+        m = v_values.shape[-1]
+        ucdf = ops.weight_cdf(u_weights, pu, S, n, u_values.device)
+        vcdf = ops.weight_cdf(v_weights, pv, S, m, u_values.device)
+        w, _ = ops.CircularWpWeightedFn.apply(u_values.contiguous(), v_values.contiguous(), ucdf, vcdf, float(p), float(tm),
+                                              float(tp), eps / max(Lm, Lp))
+        return w
     w, _ = ops.CircularWpFn.apply(u_values.contiguous(), v_values.contiguous(), float(p), float(tm), float(tp),
                                   eps / max(Lm, Lp))
     return w
@@ -53,14 +60,16 @@ def binary_search_circle(u_values, v_values, u_weights=None, v_weights=None, p=1
 def sliced_cost(Xs, Xt, Us, p=2, u_weights=None, v_weights=None):
     """(n,3),(m,3) clouds and (P,3,2) frames -> mean over slices of the circular W (max_spherical_sliced_w.py:251-286)."""
     if u_weights is not None or v_weights is not None:
-        if p != 1:
-            raise NotImplementedError("sliced_cost with non-uniform weights is supported for p == 1 (see binary_search_circle)")
         xs, unb = ops._as_cloud(Xs, "Xs")
         xt, _ = ops._as_cloud(Xt, "Xt")
         ks = ops.ProjectCircleFn.apply(xs, Us.to(device=xs.device, dtype=torch.float32))  # (B,P,n)
         kt = ops.ProjectCircleFn.apply(xt, Us.to(device=xs.device, dtype=torch.float32))
         B, P, n = ks.shape
-        w = emd1D_circle(ks.reshape(B * P, n), kt.reshape(B * P, -1), u_weights, v_weights, p=1).reshape(B, P).mean(1)
+        if p == 1:
+            w = emd1D_circle(ks.reshape(B * P, n), kt.reshape(B * P, -1), u_weights, v_weights, p=1)
+        else:
+            w = binary_search_circle(ks.reshape(B * P, n), kt.reshape(B * P, -1), u_weights, v_weights, p=p)
+        w = w.reshape(B, P).mean(1)
         return w.reshape(()) if unb else w
     w = ops.spherical_sliced_w1(Xs, Xt, Us) if p == 1 else ops.spherical_sliced_wp(Xs, Xt, Us, float(p))
     return w.reshape(()) if Xs.dim() == 2 else w

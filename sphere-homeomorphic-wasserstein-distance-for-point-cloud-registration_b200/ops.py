@@ -469,6 +469,51 @@ class CircularWpFn(torch.autograd.Function):
         return gus * g, gvs * g, None, None, None, None
 
 
+class CircularWpWeightedFn(torch.autograd.Function):
+    """binary_search_circle with u_weights / v_weights (max_spherical_sliced_w.py:117,156-170): sorted coordinates us (S,n),
+    vs (S,m) and the per-slice CDF tables ucdf = cumsum(u_weights[..., sorter]), vcdf -> W_p^p per slice.  Gradients w.r.t. the
+    sorted values and w.r.t. the CDF tables (the path by which the reference's autograd reaches the weights: the merged CDF
+    axis of the final Cost, :93-95; theta is detached, :207)."""
+
+    @staticmethod
+    def forward(ctx, us, vs, ucdf, vcdf, p, tm, tp, tol):
+        us, vs, ucdf, vcdf = (t.contiguous().float() for t in (us, vs, ucdf, vcdf))
+        S, n = us.shape
+        m = vs.shape[1]
+        if ucdf.shape != us.shape or vcdf.shape != vs.shape:
+            raise ValueError("CDF tables must have the shapes of the value rows")
+        w = torch.empty(S, device=us.device, dtype=torch.float32)
+        theta = torch.empty(S, device=us.device, dtype=torch.float32)
+        gus, gvs, gcu, gcv = (torch.empty_like(t) for t in (us, vs, ucdf, vcdf))
+        with torch.cuda.device(us.device):
+            _lib.check(_lib.lib().shwd_circular_wp_weighted(_ptr(us), _ptr(vs), _ptr(ucdf), _ptr(vcdf), S, n, m, float(p), float(tm),
+                                                            float(tp), float(tol), _ptr(w), _ptr(gus), _ptr(gvs), _ptr(gcu),
+                                                            _ptr(gcv), _ptr(theta), _stream()), "shwd_circular_wp_weighted")
+        ctx.save_for_backward(gus, gvs, gcu, gcv)
+        ctx.mark_non_differentiable(theta)
+        return w, theta
+
+    @staticmethod
+    def backward(ctx, gw, _gt):
+        gus, gvs, gcu, gcv = ctx.saved_tensors
+        g = gw.contiguous().unsqueeze(1)
+        return gus * g, gvs * g, gcu * g, gcv * g, None, None, None, None
+
+
+def weight_cdf(weights, perm, S, length, device):
+    """cumsum(weights[..., sorter], -1) per slice (max_spherical_sliced_w.py:166-170), or the uniform 1/len weights when
+    ``weights`` is None.  The reference accumulates on the CPU, where torch.cumsum carries a float64 accumulator and rounds
+    every prefix to float32; the device scan is run in float64 for the same prefixes."""
+    if weights is None:
+        ws = torch.full((S, length), 1 / length, dtype=torch.float32, device=device)
+    else:
+        ws = weights.to(device=device, dtype=torch.float32)
+        if perm is not None:  # (n,) weights: the reference's ``weights[..., sorter]``; per-slice rows are gathered row by row
+            ws = ws[perm.long()] if ws.dim() == 1 else torch.gather(ws.expand(S, length), -1, perm.long())
+        ws = ws.expand(S, length)
+    return torch.cumsum(ws.double(), -1).float()
+
+
 class EuclidSWFn(torch.autograd.Function):
     """Sorted projections xs, ys (S,n) -> sum_n |xs-ys|^p per slice (S)  (Flow_ellipsoid.ipynb:217-219)."""
 

@@ -195,6 +195,7 @@ def main():
     make_wrapper_fixtures(ref_losses)
     make_notebook_fixture()
     make_weighted_circle_fixture()
+    make_weighted_wp_fixture()
 
 
 def _flat_state(prefix, sd):
@@ -278,6 +279,41 @@ def make_weighted_circle_fixture():
     print("weighted emd1D_circle", w.detach().numpy()[:3])
 
 
+def make_weighted_wp_fixture():
+    """binary_search_circle with non-uniform weights (max_spherical_sliced_w.py:117-207; weights gathered through the sorts and
+    accumulated, :156-170), p = 2 and p = 3: value, gradients w.r.t. the coordinates and w.r.t. the weights; and one
+    sliced_cost(p=2, u_weights, v_weights) call (:251-286)."""
+    ssw = _load(os.path.join(REF, "Point_Cloud_Resistration/losses/max_spherical_sliced_w.py"), "ref_ssw_wp")
+    g = torch.Generator().manual_seed(78)
+    out = {}
+    for p in (2, 3):
+        u = torch.rand(5, 83, generator=g).requires_grad_(True)
+        v = torch.rand(5, 61, generator=g).requires_grad_(True)
+        uw = torch.rand(83, generator=g) + 0.1
+        uw = (uw / uw.sum()).requires_grad_(True)
+        vw = torch.rand(61, generator=g) + 0.1
+        vw = (vw / vw.sum()).requires_grad_(True)
+        w = ssw.binary_search_circle(u, v, u_weights=uw, v_weights=vw, p=p)
+        gu, gv, guw, gvw = torch.autograd.grad(w.sum(), (u, v, uw, vw))
+        out.update({f"u_p{p}": u.detach().numpy(), f"v_p{p}": v.detach().numpy(), f"uw_p{p}": uw.detach().numpy(),
+                    f"vw_p{p}": vw.detach().numpy(), f"w_p{p}": w.detach().numpy(), f"gu_p{p}": gu.numpy(), f"gv_p{p}": gv.numpy(),
+                    f"guw_p{p}": guw.numpy(), f"gvw_p{p}": gvw.numpy()})
+        print("weighted binary_search_circle p=%d" % p, w.detach().numpy()[:3])
+    Xs = F.normalize(torch.randn(140, 3, generator=g), dim=-1).requires_grad_(True)
+    Xt = F.normalize(torch.randn(110, 3, generator=g) + 0.4, dim=-1).requires_grad_(True)
+    U, _ = torch.linalg.qr(torch.randn(11, 3, 2, generator=g))
+    uw = torch.rand(140, generator=g) + 0.2
+    uw = uw / uw.sum()
+    vw = torch.rand(110, generator=g) + 0.2
+    vw = vw / vw.sum()
+    loss = ssw.sliced_cost(Xs, Xt, U, p=2, u_weights=uw, v_weights=vw)
+    gx, gy = torch.autograd.grad(loss, (Xs, Xt))
+    out.update(dict(Xs=Xs.detach().numpy(), Xt=Xt.detach().numpy(), U=U.numpy(), sc_uw=uw.numpy(), sc_vw=vw.numpy(),
+                    sc_loss=np.float64(loss.item()), sc_gx=gx.numpy(), sc_gy=gy.numpy()))
+    print("weighted sliced_cost p=2", loss.item())
+    np.savez(os.path.join(HERE, "binary_search_circle_weighted.npz"), **out)
+
+
 def make_notebook_fixture():
     """Row a11: the Euclidean sliced Wasserstein distance of the flow notebooks, by executing the SOURCE of cell 5 of
     Wasserstein_flow_problem/Flow_ellipsoid.ipynb (``rand_projections`` / ``sliced_wasserstein_distance``, raw JSON lines
@@ -315,5 +351,9 @@ if __name__ == "__main__":
         make_wrapper_fixtures(_ref_losses)
         make_notebook_fixture()
         make_weighted_circle_fixture()
+    elif "--weighted-wp-only" in sys.argv:  # the fixture added last in round 2
+        _install_shims()
+        torch.set_num_threads(8)
+        make_weighted_wp_fixture()
     else:
         main()

@@ -252,3 +252,23 @@ def test_oracle_weighted_emd1d_circle_matches_reference():
     assert rel(w.detach().numpy(), d["w"]) < 2e-6
     for got, want in ((gu, "gu"), (gv, "gv"), (guw, "guw"), (gvw, "gvw")):
         assert rel(got.numpy(), d[want]) < 2e-5
+
+
+def test_oracle_weighted_binary_search_circle_matches_reference():
+    """binary_search_circle / sliced_cost with non-uniform weights (max_spherical_sliced_w.py:117-207, 251-286): the oracle
+    against the unmodified reference's frozen value and gradients (coordinates and weights)."""
+    d = load("binary_search_circle_weighted")
+    for p in (2, 3):
+        t = {k: torch.from_numpy(d[f"{k}_p{p}"]).requires_grad_(True) for k in ("u", "v", "uw", "vw")}
+        w = oracle.sliced.binary_search_circle(t["u"], t["v"], p=p, u_weights=t["uw"], v_weights=t["vw"])
+        grads = torch.autograd.grad(w.sum(), (t["u"], t["v"], t["uw"], t["vw"]))
+        assert rel(w.detach().numpy(), d[f"w_p{p}"]) < 2e-6
+        for got, name in zip(grads, ("gu", "gv", "guw", "gvw")):
+            assert rel(got.numpy(), d[f"{name}_p{p}"]) < 2e-5, (p, name)
+    Xs = torch.from_numpy(d["Xs"]).requires_grad_(True)
+    Xt = torch.from_numpy(d["Xt"]).requires_grad_(True)
+    loss = oracle.sliced.sliced_wasserstein_sphere(Xs, Xt, torch.from_numpy(d["U"]), p=2, u_weights=torch.from_numpy(d["sc_uw"]),
+                                                   v_weights=torch.from_numpy(d["sc_vw"]))
+    gx, gy = torch.autograd.grad(loss, (Xs, Xt))
+    assert abs(loss.item() - float(d["sc_loss"])) / float(d["sc_loss"]) < 2e-6
+    assert rel(gx.numpy(), d["sc_gx"]) < 2e-5 and rel(gy.numpy(), d["sc_gy"]) < 2e-5
