@@ -426,6 +426,89 @@ __device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv
   }
 }
 
+// ---- equal power-of-two cloud sizes, rotation on the 1/n grid -------------------------------------------------------------
+// n == m == 2^k with uniform weights: u_cdf[i] = v_cdf[i] = (i+1) / n EXACTLY (1/n is a power of two), and the bisection's
+// midpoints are dyadic: as long as theta is a multiple of 1/n -- every round up to round k, where those calls end on a kink (see
+// DcMemo) -- the shifted CDF r_cdf[t] is an exact multiple of 1/n as well, q = frac * n being an integer:
+//     q >= 1:  r_cdf[t] = t / n          q == 0:  r_cdf[t] = (t + 1) / n          (t = 0 .. m-1, after the roll by j0 = max(q-1, 0))
+// so every search has a closed form:  #{u_cdf < r_cdf[t]} = max(t-1, 0) | t,  #{u_cdf^+ <= r_cdf[t]} = t | t+1,
+// #{r_cdf < u_cdf[k]} = k+1 | k, and the merged axis of Cost consists of coincident (u, v) pairs: the entries the walks of the
+// generic passes visit besides the owner's own carry delta == 0 exactly (fmaf(0, h, acc) == acc) and are skipped.  The
+// summands, their operands and their order per thread are those of the generic code, so the results are the same bits
+// (shwd_circular_wp_set_dyadic(0) switches the shortcut off: the tests compare the two).  ~25 instead of ~100 instructions
+// per CDF entry and round.
+template <bool P2, int T>
+__device__ float2 dcost_dyadic(const Circle& c, float theta, float2* wtot) {
+  const Shift s = make_shift<false>(c, theta);
+  const bool q0 = (s.frac == 0.f);
+  const float u_wrap = __fadd_rn(c.u[0], 1.f);
+  const float v_wrap = __fadd_rn(__fadd_rn(c.v[s.j0], s.fl), 1.f);  // r_val[m] = r_val[0] + 1 (entry j0 is never negative)
+  float dcp = 0.f, dcm = 0.f;
+  for (int t = threadIdx.x; t < c.m; t += T) {
+    int j = t + s.j0;
+    const bool wr = j >= c.m;  // wrapped <=> its shifted CDF entry was negative
+    if (wr) j -= c.m;
+    const float v0 = __fadd_rn(c.v[j], wr ? s.flp1 : s.fl);
+    float v1 = v_wrap;
+    if (t + 1 < c.m) {
+      int j1 = t + 1 + s.j0;
+      const bool wr1 = j1 >= c.m;
+      if (wr1) j1 -= c.m;
+      v1 = __fadd_rn(c.v[j1], wr1 ? s.flp1 : s.fl);
+    }
+    const int iu = q0 ? t : max(t - 1, 0), ium = q0 ? t + 1 : t;
+    const float ui = c.u[min(iu, c.n - 1)];
+    const float uim = (ium < c.n) ? c.u[ium] : u_wrap;
+    dcp += __fsub_rn(powp<P2>(__fsub_rn(ui, v1), c.p), powp<P2>(__fsub_rn(ui, v0), c.p));
+    dcm += __fsub_rn(powp<P2>(__fsub_rn(uim, v1), c.p), powp<P2>(__fsub_rn(uim, v0), c.p));
+  }
+  return block_sum2<T>(dcp, dcm, wtot);
+}
+
+template <bool P2, int T>
+__device__ float cost_pass_u_dyadic(const Circle& c, float theta, float* __restrict__ gu, const int32_t* __restrict__ pu, float2* wtot) {
+  const Shift s = make_shift<false>(c, theta);
+  const bool q0 = (s.frac == 0.f);
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < c.n; k += T) {
+    const float prev = (k > 0) ? ucdf_at<false>(c, k - 1) : 0.f;
+    const float xk = ucdf_at<false>(c, k);
+    const int t = q0 ? k : k + 1;  // #{r_cdf < u_cdf[k]}; m: the wrap entry
+    const float delta = __fsub_rn(xk, prev), d = __fsub_rn(c.u[k], r_val<false>(c, s, t));
+    acc = fmaf(delta, powp<P2>(d, c.p), acc);
+    if (gu) gu[pu ? __ldg(pu + k) : k] = fmaf(delta, dpowp<P2>(d, c.p), 0.f);
+  }
+  return block_sum2<T>(acc, 0.f, wtot).x;
+}
+
+template <bool P2, int T>
+__device__ void cost_pass_v_dyadic(const Circle& c, float theta, float* __restrict__ gv, const int32_t* __restrict__ pv) {
+  const Shift s = make_shift<false>(c, theta);
+  const bool q0 = (s.frac == 0.f);
+  for (int t = threadIdx.x; t < c.m; t += T) {
+    const float prev = (t > 0) ? r_cdf<false>(c, s, t - 1) : 0.f;
+    const float xt = r_cdf<false>(c, s, t);
+    const float V = r_val_in<false>(c, s, t);
+    const int i = q0 ? t : max(t - 1, 0);  // #{u_cdf < r_cdf[t]}
+    float g = fmaf(__fsub_rn(xt, prev), dpowp<P2>(__fsub_rn(c.u[min(i, c.n - 1)], V), c.p), 0.f);
+    if (t == 0 && !q0) {
+      // the wrap-around partner r_val[m] = r_val[0] + 1 serves the one u entry above r_cdf[m-1] = (m-1)/n: u_cdf[n-1] = 1
+      const float pw = r_cdf<false>(c, s, c.m - 1);
+      g = fmaf(__fsub_rn(ucdf_at<false>(c, c.n - 1), pw), dpowp<P2>(__fsub_rn(c.u[c.n - 1], __fadd_rn(V, 1.f)), c.p), g);
+    }
+    int j = t + s.j0;
+    if (j >= c.m) j -= c.m;
+    gv[pv ? __ldg(pv + j) : j] = -g;
+  }
+}
+
+// theta on the 1/n grid (n a power of two: the product is exact)
+__device__ __forceinline__ bool on_grid(float theta, int n) {
+  const float fr = __fsub_rn(theta, floorf(theta));  // (a rotation in [-2^-25, 0) rounds to 1.0: not a grid point)
+  const float fq = fr * (float)n;
+  return fr < 1.f && fq == floorf(fq);
+}
+
 template <bool P2, int T, bool MEMO, bool W = false>
 __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict__ us, const float* __restrict__ vs,
                                                                  const int32_t* __restrict__ pu, const int32_t* __restrict__ pv, int n,
@@ -435,7 +518,8 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
                                                                  float* __restrict__ theta_out,
                                                                  const float* __restrict__ ucdfs = nullptr,
                                                                  const float* __restrict__ vcdfs = nullptr,
-                                                                 float* __restrict__ gcus = nullptr, float* __restrict__ gcvs = nullptr) {
+                                                                 float* __restrict__ gcus = nullptr, float* __restrict__ gcvs = nullptr,
+                                                                 int dyadic = 0) {
   extern __shared__ float cw_smem[];
   __shared__ float2 wtot[T / 32];
   __shared__ int wskip[T / 32];
@@ -464,8 +548,12 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
   at_tm.j0 = -1;
   at_tp.j0 = -1;
   bool searches_first = false;
+  // equal power-of-two sizes (the launcher passes dyadic = 1 only for those, they run MEMO = false): closed-form searches while
+  // the rotation sits on the 1/n grid
+  const bool dy = !MEMO && !W && dyadic != 0;
   for (int round = 0; round < CW_MAX_ROUNDS; ++round) {
-    const float2 dc = dcost<P2, T, MEMO, W>(c, tc, wtot, wskip, at_tm, at_tp, at_tc, searches_first);
+    const float2 dc = (dy && on_grid(tc, n)) ? dcost_dyadic<P2, T>(c, tc, wtot)
+                                             : dcost<P2, T, MEMO, W>(c, tc, wtot, wskip, at_tm, at_tp, at_tc, searches_first);
     if (dc.x * dc.y <= 0.f) break;  // done: the optimum is the kink at tc
     if (__fsub_rn(tp, tm) < tol) {
       DcMemo unused;
@@ -481,9 +569,15 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
     if (dc.x < 0.f) { tm = tc; if (MEMO) at_tm = at_tc; } else { tp = tc; if (MEMO) at_tp = at_tc; }
     tc = __fmul_rn(__fadd_rn(tm, tp), 0.5f);
   }
-  const float w = cost_pass_u<P2, T, W>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot,
-                                        (W && gcus) ? gcus + sl * n : nullptr);
-  if (gvs) cost_pass_v<P2, T, W>(c, tc, gvs + sl * m, pv ? pv + sl * m : nullptr, (W && gcvs) ? gcvs + sl * m : nullptr);
+  float w;
+  if (dy && on_grid(tc, n)) {
+    w = cost_pass_u_dyadic<P2, T>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot);
+    if (gvs) cost_pass_v_dyadic<P2, T>(c, tc, gvs + sl * m, pv ? pv + sl * m : nullptr);
+  } else {
+    w = cost_pass_u<P2, T, W>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot,
+                              (W && gcus) ? gcus + sl * n : nullptr);
+    if (gvs) cost_pass_v<P2, T, W>(c, tc, gvs + sl * m, pv ? pv + sl * m : nullptr, (W && gcvs) ? gcvs + sl * m : nullptr);
+  }
   if (threadIdx.x == 0) {
     w_out[sl] = w;
     if (theta_out) theta_out[sl] = tc;
@@ -499,6 +593,12 @@ extern "C" size_t shwd_circular_wp_workspace_bytes(int S, int n, int m) {
   (void)n;
   (void)m;
   return 0;  // the uniform CDFs are evaluated in registers (ucdf_at / vcdf_at); kept for ABI stability
+}
+
+static int g_wp_dyadic = 1;  // shwd_circular_wp_set_dyadic
+extern "C" int shwd_circular_wp_set_dyadic(int on) {
+  g_wp_dyadic = on ? 1 : 0;
+  return SHWD_OK;
 }
 
 static int circular_wp_dispatch(const float* us, const float* vs, const int32_t* pu, const int32_t* pv, int S, int n, int m, float p,
@@ -525,7 +625,8 @@ static int circular_wp_dispatch(const float* us, const float* vs, const int32_t*
     if (smem > 32 * 1024) /* static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here) */                            \
       SHWD_CUDA_CHECK(                                                                                                             \
           cudaFuncSetAttribute(circular_wp_kernel<P2, T, MEMO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-    circular_wp_kernel<P2, T, MEMO><<<S, T, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta);                  \
+    circular_wp_kernel<P2, T, MEMO><<<S, T, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta, nullptr, nullptr, \
+                                                       nullptr, nullptr, (!(MEMO) && !weighted && g_wp_dyadic) ? 1 : 0);           \
   } while (0)
 #define SHWD_LAUNCH_WP_W(P2, T)                                                                                                    \
   do {                                                                                                                             \

@@ -810,6 +810,40 @@ def test_weighted_circular_wp_matches_oracle(shwd, S, n, m, p, zeros):
     assert max(errs[1:]) < bound, (errs, floor)
 
 
+@pytest.mark.parametrize("S,n,p", [(7, 1, 2), (7, 2, 2), (6, 64, 2), (5, 1024, 2), (4, 1024, 3), (3, 4096, 2), (2, 16384, 2)])
+def test_circular_wp_dyadic_shortcut_is_bit_identical(shwd, S, n, p):
+    """Equal power-of-two sizes: the closed-form searches on the 1/n grid (dcost_dyadic, cost_pass_*_dyadic) against the generic
+    searches of the same kernel -- value, rotation and both gradients must be the same bits; also through the fused sliced node."""
+    u, v = _tie_free(S, n, 500 + n), _tie_free(S, n, 600 + n, lo=0.3, width=0.6)
+    lib = shwd._lib.lib()
+    out = []
+    try:
+        for on in (1, 0):
+            assert lib.shwd_circular_wp_set_dyadic(on) == 0
+            ug, vg = u.clone().to(dev()).requires_grad_(True), v.clone().to(dev()).requires_grad_(True)
+            us, _ = shwd.ops.SegmentedSortFn.apply(ug)
+            vs, _ = shwd.ops.SegmentedSortFn.apply(vg)
+            w, th = shwd.ops.CircularWpFn.apply(us, vs, float(p), -1.0, 1.0, 1e-7)
+            w.sum().backward()
+            res = [w.detach().clone(), th.clone(), ug.grad.clone(), vg.grad.clone()]
+            if n >= 64:
+                g = torch.Generator().manual_seed(n)
+                Xs = F.normalize(torch.randn(2, n, 3, generator=g), dim=-1).to(dev()).requires_grad_(True)
+                Xt = F.normalize(torch.randn(2, n, 3, generator=g) + 0.3, dim=-1).to(dev()).requires_grad_(True)
+                U, _ = torch.linalg.qr(torch.randn(5, 3, 2, generator=g))
+                loss = shwd.ops.spherical_sliced_wp(Xs, Xt, U.to(dev()), float(p))
+                loss.sum().backward()
+                res += [loss.detach().clone(), Xs.grad.clone(), Xt.grad.clone()]
+            out.append(res)
+    finally:
+        lib.shwd_circular_wp_set_dyadic(1)
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+    # and the rotation found is on the grid for most rows (the shortcut was actually exercised)
+    th = out[0][1]
+    assert ((th * n) == torch.floor(th * n)).float().mean().item() > 0.5 or n <= 2
+
+
 def test_circular_wp_full_size_properties(shwd):
     """BASELINE config 3 (N=4096, 512 slices), p=2: properties that need no CPU reference.  (i) a common rotation of
     both clouds on the circle leaves W unchanged; (ii) W(u,u) = 0; (iii) W(u,v) = W(v,u); (iv) the input order of the
