@@ -125,6 +125,10 @@ int shwd_chamfer_bwd_uniform(const float* x, const float* y, int B, int N, int M
 int shwd_project_circle(const float* x, const float* U, int B, int N, int P, float* keys, void* stream);
 int shwd_project_circle_bwd(const float* x, const float* U, int B, int N, int P, const float* gkeys, float* gx,
                             void* stream);
+/* Projection backward: rows with N % 4 == 0 (and 16-byte aligned buffers, a grid of at least one CTA per SM) are read four
+ * points per lane (512 contiguous bytes per warp and row) -- same bits as the one-point-per-lane kernel.
+ * shwd_project_bwd_set_wide: 1 on (default), 0 off (A/B timing, tests).  Process-wide. */
+int shwd_project_bwd_set_wide(int on);
 /* Line projection (Flow_ellipsoid.ipynb:208-220): x (B,N,3), theta (P,3) -> keys (B,P,N). */
 int shwd_project_line(const float* x, const float* theta, int B, int N, int P, float* keys, void* stream);
 int shwd_project_line_bwd(const float* theta, int B, int N, int P, const float* gkeys, float* gx, void* stream);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "shwd_circular_w1": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "shwd_circular_wp_workspace_bytes": (_sz, [_i, _i, _i]),
     "shwd_circular_wp_set_dyadic": (_i, [_i]),
+    "shwd_project_bwd_set_wide": (_i, [_i]),
     "shwd_circular_wp_weighted": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "shwd_circular_wp": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "shwd_euclid_sw": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),

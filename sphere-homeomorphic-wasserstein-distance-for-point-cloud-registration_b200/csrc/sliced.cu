@@ -146,6 +146,77 @@ __global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd_kernel(const fl
   }
 }
 
+// The same with FOUR consecutive points per lane (N % 4 == 0): a warp reads 512 contiguous bytes of a gradient row instead of
+// 128 (one LDG.128 per lane), a CTA owns 128 points.  The rows are N * 4 bytes apart, so the narrow version's requests were
+// isolated 128-byte lines -- DRAM pages opened for one line each: 0.96 TB/s at cfg3 (67 MB per cloud in 70 us).  Per point the
+// slices are visited by the same warp in the same order and the eight partial sums are added in the same warp order, so the
+// result is the narrow kernel's, bit for bit.
+__global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd4_kernel(const float* __restrict__ x, const float* __restrict__ U,
+                                                                         int N, int P, const float* __restrict__ gk,
+                                                                         const float* __restrict__ gw, float* __restrict__ gx) {
+  __shared__ float sU[PB_TILE * 6];
+  __shared__ float red[PB_WARPS][3][128];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n4 = (blockIdx.x * 32 + lane) * 4;
+  const bool ok = n4 < N;  // N % 4 == 0: a lane's four points are all inside or all outside
+  float X[4][3];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) X[e][0] = X[e][1] = X[e][2] = 0.f;
+  if (ok) {
+    const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)b * N + n4) * 3);
+    const float4 A = __ldg(xp), Bv = __ldg(xp + 1), C = __ldg(xp + 2);
+    X[0][0] = A.x; X[0][1] = A.y; X[0][2] = A.z;
+    X[1][0] = A.w; X[1][1] = Bv.x; X[1][2] = Bv.y;
+    X[2][0] = Bv.z; X[2][1] = Bv.w; X[2][2] = C.x;
+    X[3][0] = C.y; X[3][1] = C.z; X[3][2] = C.w;
+  }
+  const float* gkb = gk + (size_t)b * P * N + (ok ? n4 : 0);
+  float G[4][3];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) G[e][0] = G[e][1] = G[e][2] = 0.f;
+  for (int p0 = 0; p0 < P; p0 += PB_TILE) {
+    const int pc = min(PB_TILE, P - p0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < pc * 6; i += PJ_THREADS) sU[i] = __ldg(U + (size_t)p0 * 6 + i);
+    __syncthreads();
+#pragma unroll 4
+    for (int p = warp; p < pc; p += PB_WARPS) {
+      const float* u = sU + p * 6;
+      const float4 gk4 = ok ? __ldg(reinterpret_cast<const float4*>(gkb + (size_t)(p0 + p) * N)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float gkv[4] = {gk4.x, gk4.y, gk4.z, gk4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a = fmaf(u[4], X[e][2], fmaf(u[2], X[e][1], u[0] * X[e][0]));
+        float c = fmaf(u[5], X[e][2], fmaf(u[3], X[e][1], u[1] * X[e][0]));
+        float r2 = fmaxf(fmaf(c, c, a * a), 1e-24f);
+        float g = gkv[e] / (TWO_PI_F * r2);
+        float ta = -c * g, tc = a * g;
+        G[e][0] = fmaf(ta, u[0], fmaf(tc, u[1], G[e][0]));
+        G[e][1] = fmaf(ta, u[2], fmaf(tc, u[3], G[e][1]));
+        G[e][2] = fmaf(ta, u[4], fmaf(tc, u[5], G[e][2]));
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    red[warp][0][lane * 4 + e] = G[e][0];
+    red[warp][1][lane * 4 + e] = G[e][1];
+    red[warp][2][lane * 4 + e] = G[e][2];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 384; o += PJ_THREADS) {  // output element (point pt, component k) of this CTA's contiguous span
+    const int pt = o / 3, k = o - pt * 3;
+    if (blockIdx.x * 128 + pt < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < PB_WARPS; ++w) t += red[w][k][pt];
+      if (gw) t = t * (__ldg(gw + b) / (float)P);
+      gx[((size_t)b * N + blockIdx.x * 128) * 3 + o] = t;
+    }
+  }
+}
+
 // keys[b,p,n] = <x_n, theta_p>                                              (Flow_ellipsoid.ipynb:214-216)
 __global__ void __launch_bounds__(PJ_THREADS) project_line_kernel(const float* __restrict__ x, const float* __restrict__ th, int N,
                                                                   int P, float* __restrict__ keys) {
@@ -1136,6 +1207,24 @@ __global__ void __launch_bounds__(SORT_THREADS) euclid_sw_kernel(const float* __
 
 using namespace shwd;
 
+static int g_project_bwd_wide = 1;  // shwd_project_bwd_set_wide (A/B, tests)
+extern "C" int shwd_project_bwd_set_wide(int on) {
+  g_project_bwd_wide = on ? 1 : 0;
+  return SHWD_OK;
+}
+static void launch_project_circle_bwd(const float* x, const float* U, int B, int N, int P, const float* gkeys, const float* gw,
+                                      float* gx, cudaStream_t s) {
+  // four points per lane when the rows allow vector loads and the grid still fills the SMs
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gkeys)) & 15) == 0;
+  if (g_project_bwd_wide && (N % 4) == 0 && al && (long long)B * ((N + 127) / 128) >= 148) {
+    dim3 grid((N + 127) / 128, B);
+    project_circle_bwd4_kernel<<<grid, PJ_THREADS, 0, s>>>(x, U, N, P, gkeys, gw, gx);
+  } else {
+    dim3 grid((N + 31) / 32, B);
+    project_circle_bwd_kernel<<<grid, PJ_THREADS, 0, s>>>(x, U, N, P, gkeys, gw, gx);
+  }
+}
+
 extern "C" int shwd_project_circle(const float* x, const float* U, int B, int N, int P, float* keys, void* stream) {
   if (!x || !U || !keys || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B > 65535 || (P + 31) / 32 > 65535) return SHWD_ERR_UNSUPPORTED;
@@ -1149,8 +1238,7 @@ extern "C" int shwd_project_circle_bwd(const float* x, const float* U, int B, in
                                        void* stream) {
   if (!x || !U || !gkeys || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B > 65535) return SHWD_ERR_UNSUPPORTED;
-  dim3 grid((N + 31) / 32, B);
-  project_circle_bwd_kernel<<<grid, PJ_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, U, N, P, gkeys, nullptr, gx);
+  launch_project_circle_bwd(x, U, B, N, P, gkeys, nullptr, gx, static_cast<cudaStream_t>(stream));
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }
@@ -1179,8 +1267,7 @@ extern "C" int shwd_project_circle_bwd_scaled(const float* x, const float* U, in
                                               const float* gw, float* gx, void* stream) {
   if (!x || !U || !gkeys || !gw || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B > 65535) return SHWD_ERR_UNSUPPORTED;
-  dim3 grid((N + 31) / 32, B);
-  project_circle_bwd_kernel<<<grid, PJ_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, U, N, P, gkeys, gw, gx);
+  launch_project_circle_bwd(x, U, B, N, P, gkeys, gw, gx, static_cast<cudaStream_t>(stream));
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }

@@ -844,6 +844,26 @@ def test_circular_wp_dyadic_shortcut_is_bit_identical(shwd, S, n, p):
     assert ((th * n) == torch.floor(th * n)).float().mean().item() > 0.5 or n <= 2
 
 
+@pytest.mark.parametrize("B,N,P", [(8, 4096, 64), (2, 16384, 40), (40, 512, 300), (5, 4100, 33)])
+def test_project_circle_bwd_wide_rows_are_bit_identical(shwd, B, N, P):
+    """project_circle_bwd4_kernel (four points per lane, N % 4 == 0) against the one-point-per-lane kernel: same bits."""
+    g = torch.Generator().manual_seed(B * N + P)
+    x = F.normalize(torch.randn(B, N, 3, generator=g), dim=-1).to(dev())
+    U, _ = torch.linalg.qr(torch.randn(P, 3, 2, generator=g))
+    gk = torch.randn(B, P, N, generator=g).to(dev())
+    lib = shwd._lib.lib()
+    out = []
+    try:
+        for on in (1, 0):
+            assert lib.shwd_project_bwd_set_wide(on) == 0
+            xg = x.clone().requires_grad_(True)
+            shwd.ops.ProjectCircleFn.apply(xg, U.to(dev())).backward(gk)
+            out.append(xg.grad.clone())
+    finally:
+        lib.shwd_project_bwd_set_wide(1)
+    assert torch.equal(out[0], out[1])
+
+
 def test_circular_wp_full_size_properties(shwd):
     """BASELINE config 3 (N=4096, 512 slices), p=2: properties that need no CPU reference.  (i) a common rotation of
     both clouds on the circle leaves W unchanged; (ii) W(u,u) = 0; (iii) W(u,v) = W(v,u); (iv) the input order of the
