@@ -180,21 +180,32 @@ __global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd4_kernel(const f
     __syncthreads();
     for (int i = threadIdx.x; i < pc * 6; i += PJ_THREADS) sU[i] = __ldg(U + (size_t)p0 * 6 + i);
     __syncthreads();
-#pragma unroll 4
-    for (int p = warp; p < pc; p += PB_WARPS) {
-      const float* u = sU + p * 6;
-      const float4 gk4 = ok ? __ldg(reinterpret_cast<const float4*>(gkb + (size_t)(p0 + p) * N)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float gkv[4] = {gk4.x, gk4.y, gk4.z, gk4.w};
+    // eight rows in flight per lane (the loads first, then the arithmetic): the kernel is bound by load latency at 1.7 CTAs per SM
+    for (int pb = warp; pb < pc; pb += 8 * PB_WARPS) {
+      float4 gq[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float a = fmaf(u[4], X[e][2], fmaf(u[2], X[e][1], u[0] * X[e][0]));
-        float c = fmaf(u[5], X[e][2], fmaf(u[3], X[e][1], u[1] * X[e][0]));
-        float r2 = fmaxf(fmaf(c, c, a * a), 1e-24f);
-        float g = gkv[e] / (TWO_PI_F * r2);
-        float ta = -c * g, tc = a * g;
-        G[e][0] = fmaf(ta, u[0], fmaf(tc, u[1], G[e][0]));
-        G[e][1] = fmaf(ta, u[2], fmaf(tc, u[3], G[e][1]));
-        G[e][2] = fmaf(ta, u[4], fmaf(tc, u[5], G[e][2]));
+      for (int q = 0; q < 8; ++q) {
+        const int p = pb + q * PB_WARPS;
+        gq[q] = (ok && p < pc) ? __ldg(reinterpret_cast<const float4*>(gkb + (size_t)(p0 + p) * N)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int p = pb + q * PB_WARPS;
+        if (p < pc) {
+          const float* u = sU + p * 6;
+          const float gkv[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = fmaf(u[4], X[e][2], fmaf(u[2], X[e][1], u[0] * X[e][0]));
+            float c = fmaf(u[5], X[e][2], fmaf(u[3], X[e][1], u[1] * X[e][0]));
+            float r2 = fmaxf(fmaf(c, c, a * a), 1e-24f);
+            float g = gkv[e] / (TWO_PI_F * r2);
+            float ta = -c * g, tc = a * g;
+            G[e][0] = fmaf(ta, u[0], fmaf(tc, u[1], G[e][0]));
+            G[e][1] = fmaf(ta, u[2], fmaf(tc, u[3], G[e][1]));
+            G[e][2] = fmaf(ta, u[4], fmaf(tc, u[5], G[e][2]));
+          }
+        }
       }
     }
   }
