@@ -774,14 +774,19 @@ __device__ __forceinline__ void sts_u16_if(uint32_t a, uint32_t v, bool pred) {
   asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.u16 [%0], %1; }" ::"r"(a), "h"((uint16_t)v), "r"((int)pred) : "memory");
 }
 
+// nb > 0: try the one-pass bucket sort first (bucket_sort_row's method on this layout: nb buckets of 16-bit counters behind the
+// arrays -- the launcher sizes the counter area for max(radix counters, nb) -- keys scattered from keyA into (keyB, idxB) in
+// arrival order, then ranked inside their bucket by (key, index)); rows it does not take (a non-finite key, a bucket above
+// SORT_BUCKET_CAP, fewer than SORT_BUCKET_MIN_LEN keys) run the four radix passes as before, nothing having been moved.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) segmented_sort_compact_kernel(const float* __restrict__ keys, int len,
                                                                             float* __restrict__ sorted, int64_t* __restrict__ perm,
-                                                                            int32_t* __restrict__ perm32) {
+                                                                            int32_t* __restrict__ perm32, int nb) {
   constexpr int THREADS = WARPS * 32;
   static_assert(THREADS >= 256, "one thread per digit in the offset scan");
   extern __shared__ __align__(16) unsigned char csm[];
   __shared__ uint32_t wt[WARPS];
+  __shared__ uint32_t s_kmin[WARPS], s_kmax[WARPS];
   // keyA[len] keyB[len] (u32) | idxA[len] idxB[len] (u16) | hist[WARPS][256] (u16)
   uint32_t ka = (uint32_t)__cvta_generic_to_shared(csm), kb = ka + 4u * len;
   uint32_t ia = kb + 4u * len, ib = ia + 2u * len;
@@ -790,9 +795,92 @@ __global__ void __launch_bounds__(WARPS * 32) segmented_sort_compact_kernel(cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t seg = blockIdx.x;
   const float* k = keys + seg * len;
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
   for (int i = tid; i < len; i += THREADS) {
-    sts_u32(ka + 4u * i, float_sort_key(__ldg(k + i)));
+    const uint32_t key = float_sort_key(__ldg(k + i));
+    kmin = min(kmin, key);
+    kmax = max(kmax, key);
+    sts_u32(ka + 4u * i, key);
     sts_u16(ia + 2u * i, (uint32_t)i);
+  }
+  if (nb > 0 && len >= SORT_BUCKET_MIN_LEN) {
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) {
+      s_kmin[warp] = kmin;
+      s_kmax[warp] = kmax;
+    }
+    __syncthreads();  // (also the key stores above)
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      kmin = min(kmin, s_kmin[w]);
+      kmax = max(kmax, s_kmax[w]);
+    }
+    // finite keys only (+-inf / NaN rows take the radix passes), and a range the map can resolve
+    bool ok = kmax < 0xFF800000u && kmin > 0x007FFFFFu && kmax > kmin;
+    const float tmin = float_from_sort_key(kmin);
+    const float scale = ok ? __fdiv_rn((float)nb, __fsub_rn(float_from_sort_key(kmax), tmin)) : 0.f;
+    ok = ok && scale < 3.0e38f;
+    if (ok) {  // CTA-uniform
+      const int words = nb >> 1, wpt = words / THREADS;  // nb is a multiple of 2 * THREADS (launcher)
+      const uint32_t nbm1 = (uint32_t)nb - 1u;
+      auto bucket = [&](uint32_t key) { return min(__float2uint_rz(__fmul_rn(__fsub_rn(float_from_sort_key(key), tmin), scale)), nbm1); };
+      for (int i = tid; i < words; i += THREADS) hist32[i] = 0u;
+      __syncthreads();
+      for (int i = tid; i < len; i += THREADS) {
+        const uint32_t bk = bucket(lds_u32(ka + 4u * i));
+        atomicAdd(hist32 + (bk >> 1), 1u << ((bk & 1u) * 16u));
+      }
+      __syncthreads();
+      uint32_t tot = 0, mx = 0;
+      for (int w = 0; w < wpt; ++w) {
+        const uint32_t c = hist32[tid * wpt + w];
+        tot += (c & 0xffffu) + (c >> 16);
+        mx = max(mx, max(c & 0xffffu, c >> 16));
+      }
+      if (!__syncthreads_or(mx > (uint32_t)SORT_BUCKET_CAP)) {
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (lane == 31) wt[warp] = inc;
+        __syncthreads();
+        uint32_t run = inc - tot;
+        for (int w = 0; w < warp; ++w) run += wt[w];
+        for (int w = 0; w < wpt; ++w) {  // counters -> first slot of each bucket (the scatter advances them to the bucket's end)
+          const uint32_t c = hist32[tid * wpt + w];
+          const uint32_t lo = run, hi = run + (c & 0xffffu);
+          hist32[tid * wpt + w] = lo | (hi << 16);
+          run = hi + (c >> 16);
+        }
+        __syncthreads();
+        for (int i = tid; i < len; i += THREADS) {
+          const uint32_t key = lds_u32(ka + 4u * i);
+          const uint32_t bk = bucket(key);
+          const uint32_t old = atomicAdd(hist32 + (bk >> 1), 1u << ((bk & 1u) * 16u));
+          const uint32_t slot = (old >> ((bk & 1u) * 16u)) & 0xffffu;
+          sts_u32(kb + 4u * slot, key);
+          sts_u16(ib + 2u * slot, (uint32_t)i);
+        }
+        __syncthreads();
+        for (int sl = tid; sl < len; sl += THREADS) {
+          const uint32_t key = lds_u32(kb + 4u * sl), idx = lds_u16(ib + 2u * sl);
+          const uint32_t bk = bucket(key);
+          const uint32_t end = lds_u16(hs + 2u * bk), beg = bk ? lds_u16(hs + 2u * (bk - 1u)) : 0u;
+          uint32_t r = beg;
+          for (uint32_t j = beg; j < end; ++j) {
+            const uint32_t ok2 = lds_u32(kb + 4u * j), oi = lds_u16(ib + 2u * j);
+            r += (ok2 < key || (ok2 == key && oi < idx)) ? 1u : 0u;
+          }
+          if (sorted) sorted[seg * len + r] = __ldg(k + idx);  // the original value (keeps -0.0)
+          if (perm) perm[seg * len + r] = (int64_t)idx;
+          if (perm32) perm32[seg * len + r] = (int32_t)idx;
+        }
+        return;
+      }
+    }
   }
   const int chunk = (((len + WARPS - 1) / WARPS) + 31) & ~31;
   const int beg = min(len, warp * chunk), end = min(len, beg + chunk);
@@ -1319,17 +1407,21 @@ extern "C" size_t shwd_segmented_sort_workspace_bytes(int segs, int len) {
   return (size_t)segs * 2 * (size_t)len * sizeof(uint2);
 }
 
+static int g_sort_method = 0;  // shwd_sort_set_method
 template <int WARPS>
 static int launch_sort_compact(const float* keys, int segs, int len, float* sorted, int64_t* perm, int32_t* perm32, cudaStream_t s) {
-  const size_t smem = 12 * (size_t)len + (size_t)WARPS * 512;
+  // bucket counters: ~2 keys per bucket (8192 buckets beyond 8192 keys, where one CTA per SM fits anyway; 4096 below, which
+  // keeps two CTAs of 8192 keys on an SM); 0 = radix passes only (shwd_sort_set_method(1))
+  const int nb = g_sort_method == 1 ? 0 : (len > 8192 ? 8192 : 4096);
+  const size_t hist = (size_t)WARPS * 512 > (size_t)nb * 2 ? (size_t)WARPS * 512 : (size_t)nb * 2;
+  const size_t smem = 12 * (size_t)len + hist;
   if (smem > 32 * 1024)
     SHWD_CUDA_CHECK(cudaFuncSetAttribute(segmented_sort_compact_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  segmented_sort_compact_kernel<WARPS><<<segs, WARPS * 32, smem, s>>>(keys, len, sorted, perm, perm32);
+  segmented_sort_compact_kernel<WARPS><<<segs, WARPS * 32, smem, s>>>(keys, len, sorted, perm, perm32, nb);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }
 
-static int g_sort_method = 0;  // shwd_sort_set_method
 extern "C" int shwd_sort_set_method(int method) {
   if (method < 0 || method > 1) return SHWD_ERR_INVALID_ARGUMENT;
   g_sort_method = method;
@@ -1385,6 +1477,10 @@ static int launch_segmented_sort(const float* keys, int segs, int len, float* so
   if (sort_use_compact(len)) {
     static const int warps_env = sort_env("SHWD_SORT_WARPS", "8", 8, "16", 16, 0);
     const int warps = warps_env ? warps_env : 16;  // (32 warps for the one-CTA-per-SM rows: 34.1 vs 33.7 Gkeys/s at 16384, slower below)
+    // rows beyond 8192 keys are alone on their SM: 32 warps (bucket pass 0.158 -> 0.141 ms at 512 x 16384, 0.106 -> 0.083 at
+    // 512 x 10000; the radix passes do not care: 0.250 -> 0.242).  SHWD_SORT_BIG32=0 keeps 16 (A/B).
+    static const int big32 = sort_env("SHWD_SORT_BIG32", "1", 1, "0", 2, 1);
+    if (big32 == 1 && len > 8192) return launch_sort_compact<32>(keys, segs, len, sorted, perm, perm32, s);
     return warps == 16 ? launch_sort_compact<16>(keys, segs, len, sorted, perm, perm32, s)
                        : launch_sort_compact<8>(keys, segs, len, sorted, perm, perm32, s);
   }

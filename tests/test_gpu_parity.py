@@ -472,7 +472,7 @@ def test_segmented_sort_is_bit_exact_stable(shwd, segs, length):
 @pytest.mark.parametrize("method", [0, 1])  # 0: bucket pass where the row allows it, 1: radix passes only
 @pytest.mark.parametrize("kind", ["circle", "signed", "ties", "constant", "tiny_range", "specials", "denormal_span", "clustered",
                                   "few_ties_spread", "one_outlier"])
-@pytest.mark.parametrize("segs,length", [(5, 1), (7, 33), (3, 1000), (4, 4096), (2, 4224), (3, 8192)])
+@pytest.mark.parametrize("segs,length", [(5, 1), (7, 33), (3, 1000), (4, 4096), (2, 4224), (3, 5000), (3, 8192), (2, 10000), (2, 16384)])
 def test_trimmed_digit_sort_is_bit_exact_stable(shwd, kind, segs, length, method):
     """The sliced losses' own sort (digits trimmed to the bits in which a row's keys differ, csrc/sliced.cu): the int32
     permutation equals torch.sort(stable=True) bit for bit on rows that differ in 27 bits (circle coordinates: 3 passes),
