@@ -116,18 +116,29 @@ __global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd_kernel(const fl
     __syncthreads();
     for (int i = threadIdx.x; i < pc * 6; i += PJ_THREADS) sU[i] = __ldg(U + (size_t)p0 * 6 + i);
     __syncthreads();
-#pragma unroll 8
-    for (int p = warp; p < pc; p += PB_WARPS) {
-      const float* u = sU + p * 6;
-      const float gkv = ok ? __ldg(gkb + (size_t)(p0 + p) * N) : 0.f;
-      float a = fmaf(u[4], x2, fmaf(u[2], x1, u[0] * x0));
-      float c = fmaf(u[5], x2, fmaf(u[3], x1, u[1] * x0));
-      float r2 = fmaxf(fmaf(c, c, a * a), 1e-24f);
-      float g = gkv / (TWO_PI_F * r2);
-      float ta = -c * g, tc = a * g;
-      g0 = fmaf(ta, u[0], fmaf(tc, u[1], g0));
-      g1 = fmaf(ta, u[2], fmaf(tc, u[3], g1));
-      g2 = fmaf(ta, u[4], fmaf(tc, u[5], g2));
+    // sixteen rows in flight per lane, the loads before the arithmetic (same accumulation order)
+    for (int pb = warp; pb < pc; pb += 16 * PB_WARPS) {
+      float gq[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int p = pb + q * PB_WARPS;
+        gq[q] = (ok && p < pc) ? __ldg(gkb + (size_t)(p0 + p) * N) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int p = pb + q * PB_WARPS;
+        if (p < pc) {
+          const float* u = sU + p * 6;
+          float a = fmaf(u[4], x2, fmaf(u[2], x1, u[0] * x0));
+          float c = fmaf(u[5], x2, fmaf(u[3], x1, u[1] * x0));
+          float r2 = fmaxf(fmaf(c, c, a * a), 1e-24f);
+          float g = gq[q] / (TWO_PI_F * r2);
+          float ta = -c * g, tc = a * g;
+          g0 = fmaf(ta, u[0], fmaf(tc, u[1], g0));
+          g1 = fmaf(ta, u[2], fmaf(tc, u[3], g1));
+          g2 = fmaf(ta, u[4], fmaf(tc, u[5], g2));
+        }
+      }
     }
   }
   red[warp][0][lane] = g0;

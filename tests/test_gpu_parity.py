@@ -1122,6 +1122,31 @@ def test_fused_residual_flow_matches_eager_modules(shwd, n_flow_layer, shape):
     assert all(torch.equal(a, prm.grad) for a, (_, prm) in zip(g1, live))
 
 
+def test_optuna_flow_class_takes_the_fused_kernel_at_the_standard_shape(shwd):
+    """Norm_Flow_structure_optuna (s2_wasserstein.py:171-201) with the width / depth Norm_Flow_structure itself builds runs the
+    fused kernel -- same values and gradients as its eager modules; any other width / depth stays eager."""
+    torch.manual_seed(3)
+    phi = shwd.losses.Norm_Flow_structure_optuna(flow_name="Residual", n_flow_layer=2, Residual_hidden_units=8,
+                                                 Residual_hidden_layers=7).to(dev())
+    from shwd_b200.losses import flows
+    assert flows.is_standard_residual_stack(phi.net)
+    x = (torch.randn(3, 200, 3) * 0.8).to(dev())
+    xe, xf = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ye = xe
+    for f in phi.net:
+        ye = f(ye)
+    ye.square().sum().backward()
+    ge = [q.grad.clone() for q in phi.parameters() if q.grad is not None]
+    phi.zero_grad()
+    yf = phi(xf)
+    yf.square().sum().backward()
+    gf = [q.grad.clone() for q in phi.parameters() if q.grad is not None]
+    assert rel(yf, ye) < TOL and rel(xf.grad, xe.grad) < TOL and len(ge) == len(gf)
+    assert all((a - b).norm().item() <= TOL * max(b.norm().item(), 1e-3) for a, b in zip(gf, ge))
+    other = shwd.losses.Norm_Flow_structure_optuna(flow_name="Residual", n_flow_layer=2, Residual_hidden_units=4).to(dev())
+    assert not flows.is_standard_residual_stack(other.net) and other(x).shape == x.shape
+
+
 def _state(d, prefix):
     return {k[len(prefix):].replace("__", "."): torch.from_numpy(v) for k, v in d.items() if k.startswith(prefix)}
 
