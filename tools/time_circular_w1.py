@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn.functional as F
 import shwd
 dev = torch.device("cuda:0")
-for S, n, m in ((4096, 4096, 4096), (4096, 4000, 3500), (4096, 1024, 1024), (512, 16384, 16384), (1024, 5000, 5000), (4096, 300, 250)):
+for S, n, m in ((4096, 4096, 4096), (4096, 4000, 3500), (4096, 1024, 1024), (512, 16384, 16384), (1024, 5000, 5000), (1024, 6000, 6000), (1024, 8192, 8192), (4096, 300, 250)):
     g = torch.Generator().manual_seed(11)
     us = torch.sort(torch.rand(S, n, generator=g), -1)[0].to(dev)
     vs = torch.sort((torch.rand(S, m, generator=g) * 0.8 + 0.15) % 1.0, -1)[0].to(dev)
