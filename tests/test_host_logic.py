@@ -314,3 +314,22 @@ def test_bench_reference_arm_and_meta_describe_the_same_workload():
         assert cfg in bench.CPU_SAMPLE
     assert bench.workload_meta("cfg2", "strong", 8)["config"]["global_batch"] == 32
     assert bench.workload_meta("cfg2", "weak", 8)["config"]["global_batch"] == 256
+
+
+def test_weight_cdf_equals_the_reference_cumsum_bit_for_bit():
+    """ops.weight_cdf (the per-slice CDF tables of the weighted circular W_p) against the reference's own expression
+    ``torch.cumsum(weights[..., sorter], -1)`` on the CPU (max_spherical_sliced_w.py:166-170): the same float32 bits, for (n,)
+    weights gathered through a (S,n) sorter and for the uniform default."""
+    g = torch.Generator().manual_seed(4)
+    S, n = 7, 1531
+    w = torch.rand(n, generator=g) + 0.01
+    w = w / w.sum()
+    perm = torch.argsort(torch.rand(S, n, generator=g), dim=-1)
+    got = shwd.ops.weight_cdf(w, perm.int(), S, n, torch.device("cpu"))
+    want = torch.cumsum(w[..., perm], -1)
+    assert got.dtype == torch.float32 and torch.equal(got, want)
+    uni = shwd.ops.weight_cdf(None, None, S, n, torch.device("cpu"))
+    assert torch.equal(uni, torch.cumsum(torch.full((n,), 1 / n, dtype=torch.float32), -1).expand(S, n))
+    # and the closed form the uniform kernel evaluates in registers: fl((i + 1) * fl(1 / n))
+    closed = (torch.arange(1, n + 1, dtype=torch.float64) * float(torch.tensor(1 / n, dtype=torch.float32))).float()
+    assert torch.equal(uni[0], closed)
