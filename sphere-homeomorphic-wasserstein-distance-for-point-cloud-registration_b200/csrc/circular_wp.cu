@@ -437,8 +437,9 @@ __device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv
 // summands, their operands and their order per thread are those of the generic code, so the results are the same bits
 // (shwd_circular_wp_set_dyadic(0) switches the shortcut off: the tests compare the two).  ~25 instead of ~100 instructions
 // per CDF entry and round.
+// between: the off-grid form of equal sizes (see between_safe below) -- #{u_cdf < r_cdf[t]} = #{u_cdf^+ <= r_cdf[t]} = t.
 template <bool P2, int T>
-__device__ float2 dcost_dyadic(const Circle& c, float theta, float2* wtot) {
+__device__ float2 dcost_dyadic(const Circle& c, float theta, float2* wtot, bool between = false) {
   const Shift s = make_shift<false>(c, theta);
   const bool q0 = (s.frac == 0.f);
   const float u_wrap = __fadd_rn(c.u[0], 1.f);
@@ -456,7 +457,7 @@ __device__ float2 dcost_dyadic(const Circle& c, float theta, float2* wtot) {
       if (wr1) j1 -= c.m;
       v1 = __fadd_rn(c.v[j1], wr1 ? s.flp1 : s.fl);
     }
-    const int iu = q0 ? t : max(t - 1, 0), ium = q0 ? t + 1 : t;
+    const int iu = (q0 || between) ? t : max(t - 1, 0), ium = (q0 && !between) ? t + 1 : t;
     const float ui = c.u[min(iu, c.n - 1)];
     const float uim = (ium < c.n) ? c.u[ium] : u_wrap;
     dcp += __fsub_rn(powp<P2>(__fsub_rn(ui, v1), c.p), powp<P2>(__fsub_rn(ui, v0), c.p));
@@ -493,6 +494,69 @@ __device__ void cost_pass_v_dyadic(const Circle& c, float theta, float* __restri
     float g = fmaf(__fsub_rn(xt, prev), dpowp<P2>(__fsub_rn(c.u[min(i, c.n - 1)], V), c.p), 0.f);
     if (t == 0 && !q0) {
       // the wrap-around partner r_val[m] = r_val[0] + 1 serves the one u entry above r_cdf[m-1] = (m-1)/n: u_cdf[n-1] = 1
+      const float pw = r_cdf<false>(c, s, c.m - 1);
+      g = fmaf(__fsub_rn(ucdf_at<false>(c, c.n - 1), pw), dpowp<P2>(__fsub_rn(c.u[c.n - 1], __fadd_rn(V, 1.f)), c.p), g);
+    }
+    int j = t + s.j0;
+    if (j >= c.m) j -= c.m;
+    gv[pv ? __ldg(pv + j) : j] = -g;
+  }
+}
+
+// ---- equal cloud sizes of ANY length, rotation safely OFF the 1/n grid ---------------------------------------------------------
+// n == m, uniform weights: u_cdf[i] = v_cdf[i] = fl((i+1) w), w = fl(1/n).  With F = frac / w and phi = F - floor(F), the shifted
+// entry is r_cdf[t] = (t + 1 - phi) / n up to rounding: comparing it with a u_cdf entry compares an integer with F, perturbed by
+// at most n (2^-22 + 2^-25) index units (the roundings of the two CDF entries, of the subtraction and of the re-wrap).  So when
+// phi and 1 - phi exceed n 2^-20 -- four times that bound -- every r_cdf[t] lies STRICTLY between u_cdf[t-1] and u_cdf[t]:
+//     j0 = floor(F),   #{u_cdf < r_cdf[t]} = #{u_cdf^+ <= r_cdf[t]} = t,   #{r_cdf < u_cdf[k]} = k + 1,
+// the merged axis of Cost is r_0 u_0 r_1 u_1 ... r_{n-1} u_{n-1}, and the searches of the generic code are known without being
+// run -- same summands, same order, same bits (the A/B test switches this off with shwd_circular_wp_set_dyadic(0)).  This is
+// what the rounds of a bisection look like once the bracket is narrower than 1/n, and almost every earlier round of sizes that
+// are not a power of two; rotations within the margin of the grid (the first rounds; n = 1000: multiples of 1/8) run the
+// generic searches.
+__device__ __forceinline__ bool between_safe(const Circle& c, const Shift& s) {
+  if (s.allneg) return false;
+  const double F = (double)s.frac / (double)c.wu;
+  const double fl = floor(F), phi = F - fl;
+  const double margin = (double)c.n * 9.5367431640625e-07;  // n 2^-20
+  return phi > margin && 1.0 - phi > margin && (int)fl == s.j0;
+}
+
+template <bool P2, int T>
+__device__ float cost_pass_u_between(const Circle& c, float theta, float* __restrict__ gu, const int32_t* __restrict__ pu, float2* wtot) {
+  const Shift s = make_shift<false>(c, theta);
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < c.n; k += T) {
+    const float prev = (k > 0) ? ucdf_at<false>(c, k - 1) : 0.f;
+    const float xk = ucdf_at<false>(c, k);
+    const float U = c.u[k];
+    const float rk = r_cdf<false>(c, s, k);  // the one v entry inside (u_cdf[k-1], u_cdf[k]): v-index k, u-index k
+    const float d1 = __fsub_rn(U, r_val_in<false>(c, s, k)), e1 = __fsub_rn(rk, prev);
+    acc = fmaf(e1, powp<P2>(d1, c.p), acc);
+    float g = fmaf(e1, dpowp<P2>(d1, c.p), 0.f);
+    const float d2 = __fsub_rn(U, r_val<false>(c, s, k + 1)), e2 = __fsub_rn(xk, rk);  // the u entry: v-index k + 1 (m: the wrap entry)
+    acc = fmaf(e2, powp<P2>(d2, c.p), acc);
+    g = fmaf(e2, dpowp<P2>(d2, c.p), g);
+    if (gu) gu[pu ? __ldg(pu + k) : k] = g;
+  }
+  return block_sum2<T>(acc, 0.f, wtot).x;
+}
+
+template <bool P2, int T>
+__device__ void cost_pass_v_between(const Circle& c, float theta, float* __restrict__ gv, const int32_t* __restrict__ pv) {
+  const Shift s = make_shift<false>(c, theta);
+  for (int t = threadIdx.x; t < c.m; t += T) {
+    float prev = (t > 0) ? r_cdf<false>(c, s, t - 1) : 0.f;
+    const float xt = r_cdf<false>(c, s, t);
+    const float V = r_val_in<false>(c, s, t);
+    float g = 0.f;
+    if (t > 0) {  // the one u entry inside (r[t-1], r[t]): u_cdf[t-1], v-index t
+      const float a = ucdf_at<false>(c, t - 1);
+      g = fmaf(__fsub_rn(a, prev), dpowp<P2>(__fsub_rn(c.u[t - 1], V), c.p), g);
+      prev = a;
+    }
+    g = fmaf(__fsub_rn(xt, prev), dpowp<P2>(__fsub_rn(c.u[min(t, c.n - 1)], V), c.p), g);  // the v entry: u-index t
+    if (t == 0) {  // the wrap-around partner r_val[m] = r_val[0] + 1 serves the one u entry above r_cdf[m-1]: u_cdf[n-1]
       const float pw = r_cdf<false>(c, s, c.m - 1);
       g = fmaf(__fsub_rn(ucdf_at<false>(c, c.n - 1), pw), dpowp<P2>(__fsub_rn(c.u[c.n - 1], __fadd_rn(V, 1.f)), c.p), g);
     }
@@ -548,19 +612,37 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
   at_tm.j0 = -1;
   at_tp.j0 = -1;
   bool searches_first = false;
-  // equal power-of-two sizes (the launcher passes dyadic = 1 only for those, they run MEMO = false): closed-form searches while
-  // the rotation sits on the 1/n grid
-  const bool dy = !MEMO && !W && dyadic != 0;
+  // closed-form searches (uniform weights, n == m; `dyadic` bit 0: equal power-of-two sizes while the rotation sits on the 1/n
+  // grid, bit 1: any equal sizes while it is safely off the grid): mode 1 / 2, else 0 = the generic searches
+  const bool dy = !W && (dyadic & 1) != 0, bt = !W && (dyadic & 2) != 0;
+  auto mode_of = [&](float th) -> int {
+    if (dy && on_grid(th, n)) return 1;
+    if (bt && between_safe(c, make_shift<false>(c, th))) return 2;
+    return 0;
+  };
+  auto eval = [&](float th, DcMemo& out) -> float2 {
+    const int md = mode_of(th);
+    if (md != 0) {
+      out.j0 = -1;  // nothing for the memo of the generic rounds
+      return dcost_dyadic<P2, T>(c, th, wtot, md == 2);
+    }
+    return dcost<P2, T, MEMO, W>(c, th, wtot, wskip, at_tm, at_tp, out, searches_first);
+  };
+  auto cost_at = [&](float th) -> float {
+    const int md = mode_of(th);
+    if (md == 1) return cost_pass_u_dyadic<P2, T>(c, th, nullptr, nullptr, wtot);
+    if (md == 2) return cost_pass_u_between<P2, T>(c, th, nullptr, nullptr, wtot);
+    return cost_pass_u<P2, T, W>(c, th, nullptr, nullptr, wtot);
+  };
   for (int round = 0; round < CW_MAX_ROUNDS; ++round) {
-    const float2 dc = (dy && on_grid(tc, n)) ? dcost_dyadic<P2, T>(c, tc, wtot)
-                                             : dcost<P2, T, MEMO, W>(c, tc, wtot, wskip, at_tm, at_tp, at_tc, searches_first);
+    const float2 dc = eval(tc, at_tc);
     if (dc.x * dc.y <= 0.f) break;  // done: the optimum is the kink at tc
     if (__fsub_rn(tp, tm) < tol) {
       DcMemo unused;
-      const float2 dtp = dcost<P2, T, MEMO, W>(c, tp, wtot, wskip, at_tm, at_tp, unused, searches_first);
-      const float2 dtm = dcost<P2, T, MEMO, W>(c, tm, wtot, wskip, at_tm, at_tp, unused, searches_first);
-      const float ctm = cost_pass_u<P2, T, W>(c, tm, nullptr, nullptr, wtot);
-      const float ctp = cost_pass_u<P2, T, W>(c, tp, nullptr, nullptr, wtot);
+      const float2 dtp = eval(tp, unused);
+      const float2 dtm = eval(tm, unused);
+      const float ctm = cost_at(tm);
+      const float ctp = cost_at(tp);
       const float den = __fsub_rn(dtm.x, dtp.y);  // dCptm - dCmtp
       if (fabsf(den) > 0.001f)
         tc = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(ctp, ctm), __fmul_rn(tm, dtm.x)), __fmul_rn(tp, dtp.y)), den);
@@ -570,9 +652,13 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
     tc = __fmul_rn(__fadd_rn(tm, tp), 0.5f);
   }
   float w;
-  if (dy && on_grid(tc, n)) {
+  const int mdf = mode_of(tc);
+  if (mdf == 1) {
     w = cost_pass_u_dyadic<P2, T>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot);
     if (gvs) cost_pass_v_dyadic<P2, T>(c, tc, gvs + sl * m, pv ? pv + sl * m : nullptr);
+  } else if (mdf == 2) {
+    w = cost_pass_u_between<P2, T>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot);
+    if (gvs) cost_pass_v_between<P2, T>(c, tc, gvs + sl * m, pv ? pv + sl * m : nullptr);
   } else {
     w = cost_pass_u<P2, T, W>(c, tc, gus ? gus + sl * n : nullptr, pu ? pu + sl * n : nullptr, wtot,
                               (W && gcus) ? gcus + sl * n : nullptr);
@@ -620,13 +706,15 @@ static int circular_wp_dispatch(const float* us, const float* vs, const int32_t*
   const bool big = smem > 56 * 1024;
   // equal power-of-two sizes: the bisection ends on a kink at round log2(n), nothing to remember (see DcMemo)
   const bool memo = !(n == m && (n & (n - 1)) == 0) && !weighted;
+  // closed-form searches: bit 0 on the 1/n grid (equal power-of-two sizes), bit 1 safely off it (any equal sizes)
+  const int wp_shortcuts = (!weighted && g_wp_dyadic && n == m) ? (((n & (n - 1)) == 0 ? 1 : 0) | 2) : 0;
 #define SHWD_LAUNCH_WP_M(P2, T, MEMO)                                                                                              \
   do {                                                                                                                             \
     if (smem > 32 * 1024) /* static + dynamic beyond 48 KB needs the opt-in (static is < 16 KB here) */                            \
       SHWD_CUDA_CHECK(                                                                                                             \
           cudaFuncSetAttribute(circular_wp_kernel<P2, T, MEMO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
     circular_wp_kernel<P2, T, MEMO><<<S, T, smem, s>>>(us, vs, pu, pv, n, m, p, tm, tp, tol, w, gus, gvs, theta, nullptr, nullptr, \
-                                                       nullptr, nullptr, (!(MEMO) && !weighted && g_wp_dyadic) ? 1 : 0);           \
+                                                       nullptr, nullptr, wp_shortcuts);                                            \
   } while (0)
 #define SHWD_LAUNCH_WP_W(P2, T)                                                                                                    \
   do {                                                                                                                             \

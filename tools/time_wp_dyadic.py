@@ -19,7 +19,7 @@ def timed(fn, reps=10):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-for n in (1024, 4096, 16384):
+for n in (1024, 4096, 16384, 1000, 4000):
     S = 4096 if n <= 4096 else 512
     g = torch.Generator().manual_seed(11)
     B = 8 if n <= 4096 else 1
