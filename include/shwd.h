@@ -175,8 +175,9 @@ size_t shwd_circular_wp_workspace_bytes(int S, int n, int m);
 int shwd_circular_wp(const float* us, const float* vs, int S, int n, int m, float p, float tm, float tp, float tol,
                      float* w, float* gus, float* gvs, float* theta, void* workspace, size_t workspace_bytes,
                      void* stream);
-/* Equal power-of-two cloud sizes take closed-form searches while the rotation sits on the 1/n grid (same bits, ~4x fewer
- * instructions per round; circular_wp.cu).  shwd_circular_wp_set_dyadic: 1 on (default), 0 off (A/B timing, tests).  Process-wide. */
+/* Equal cloud sizes take closed-form searches while the rotation sits on the 1/n grid (powers of two) or safely off it (any
+ * length) -- same bits, ~4x fewer instructions per round; circular_wp.cu.  shwd_circular_wp_set_dyadic: 1 on (default), 0 off
+ * (A/B timing, tests).  Process-wide. */
 int shwd_circular_wp_set_dyadic(int on);
 /* The same with the reference's u_weights / v_weights (binary_search_circle, max_spherical_sliced_w.py:117,156-170): ucdf
  * (S,n) / vcdf (S,m) are the per-slice CDF tables cumsum(weights[..., sorter], -1) the reference forms (non-decreasing);

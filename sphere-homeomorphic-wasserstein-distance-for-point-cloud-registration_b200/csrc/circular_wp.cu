@@ -439,8 +439,9 @@ __device__ void cost_pass_v(const Circle& c, float theta, float* __restrict__ gv
 // per CDF entry and round.
 // between: the off-grid form of equal sizes (see between_safe below) -- #{u_cdf < r_cdf[t]} = #{u_cdf^+ <= r_cdf[t]} = t.
 template <bool P2, int T>
-__device__ float2 dcost_dyadic(const Circle& c, float theta, float2* wtot, bool between = false) {
+__device__ float2 dcost_dyadic(const Circle& c, float theta, float2* wtot, bool between = false, DcMemo* memo = nullptr) {
   const Shift s = make_shift<false>(c, theta);
+  int siu = 0, sium = 0;
   const bool q0 = (s.frac == 0.f);
   const float u_wrap = __fadd_rn(c.u[0], 1.f);
   const float v_wrap = __fadd_rn(__fadd_rn(c.v[s.j0], s.fl), 1.f);  // r_val[m] = r_val[0] + 1 (entry j0 is never negative)
@@ -462,6 +463,16 @@ __device__ float2 dcost_dyadic(const Circle& c, float theta, float2* wtot, bool 
     const float uim = (ium < c.n) ? c.u[ium] : u_wrap;
     dcp += __fsub_rn(powp<P2>(__fsub_rn(ui, v1), c.p), powp<P2>(__fsub_rn(ui, v0), c.p));
     dcm += __fsub_rn(powp<P2>(__fsub_rn(uim, v1), c.p), powp<P2>(__fsub_rn(uim, v0), c.p));
+    siu += iu;
+    sium += ium;
+  }
+  if (memo) {  // what the generic evaluation would remember of this rotation (see DcMemo): the two search results are the counts
+    memo->fl = s.fl;
+    memo->j0 = s.j0 | (s.allneg ? (1 << 30) : 0);
+    memo->siu = siu;
+    memo->sium = sium;
+    memo->dcp = dcp;
+    memo->dcm = dcm;
   }
   return block_sum2<T>(dcp, dcm, wtot);
 }
@@ -623,8 +634,9 @@ __global__ void __launch_bounds__(T) circular_wp_kernel(const float* __restrict_
   auto eval = [&](float th, DcMemo& out) -> float2 {
     const int md = mode_of(th);
     if (md != 0) {
-      out.j0 = -1;  // nothing for the memo of the generic rounds
-      return dcost_dyadic<P2, T>(c, th, wtot, md == 2);
+      // (fills the memo of the generic rounds; a generic round that follows tries the searches first: the bracket is narrow by then)
+      if (MEMO && md == 2) searches_first = true;
+      return dcost_dyadic<P2, T>(c, th, wtot, md == 2, MEMO ? &out : nullptr);
     }
     return dcost<P2, T, MEMO, W>(c, th, wtot, wskip, at_tm, at_tp, out, searches_first);
   };
