@@ -126,9 +126,11 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.mark_at = index, None, [], None
 
     def start(self):
+        if os.environ.get("SHWD_BENCH_NO_CLOCKS") == "1":  # (diagnostic: is an outlier step the sampler's doing?)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -141,6 +143,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_first(self, timeout=5.0):
+        """Block until the first sample has arrived: nvidia-smi's own start-up (driver attach, hundreds of ms) then lies before
+        the warm-up instead of inside a 260 ms timed region -- one in four runs showed a 0.6 ms/step outlier on either leg."""
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -150,7 +159,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        for ln in self.lines[self.mark_at or 0:]:  # samples from the start of the first timed region on
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -357,8 +366,10 @@ def main():
             tmpl, src = registration_pairs(B, N, 1234 + rank, dev)
         units_local = B
         crit = L.Geodesic_distance_W(device=dev, p=int(P_COST), eps=EPS, max_iter=ITERS)
-        h_t, h_s = pinned(tmpl), pinned(src)
-        h_gx, h_gy, h_loss = torch.empty_like(h_t).pin_memory(), torch.empty_like(h_s).pin_memory(), torch.empty(1).pin_memory()
+        # end-to-end staging: both clouds travel as ONE pinned buffer / one H2D copy, both gradients and the loss come back as ONE
+        # D2H copy (five separate DMA operations per step left the leg exposed to per-copy latency on a busy box)
+        h_in = pinned(torch.stack([tmpl, src]))
+        h_back = torch.empty(2 * B * N * 3 + 1).pin_memory()
         launches = 6  # 2 sphere-map fwd, OT fwd, OT bwd, 2 sphere-map bwd
         h2d, d2h = 2 * B * N * 12, 2 * B * N * 12 + 4
 
@@ -371,17 +382,15 @@ def main():
             return loss
 
         def step_e2e():
-            x = h_t.to(dev, non_blocking=True)
-            y = h_s.to(dev, non_blocking=True)
+            xy = h_in.to(dev, non_blocking=True)
+            x, y = xy[0], xy[1]
             x = x - x.mean(dim=1, keepdim=True)  # centring in the training loop, train_W_COS.py:167-168
             y = y - y.mean(dim=1, keepdim=True)
             x.requires_grad_(True)
             y.requires_grad_(True)
             loss = crit(x, y)
             loss.backward()
-            h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-            h_gx.copy_(x.grad, non_blocking=True)
-            h_gy.copy_(y.grad, non_blocking=True)
+            h_back.copy_(torch.cat([x.grad.reshape(-1), y.grad.reshape(-1), loss.detach().reshape(1)]), non_blocking=True)
             return loss
     elif cfg == "cfg1":
         B, N = B_PER_GPU, N_PTS
@@ -477,6 +486,8 @@ def main():
         for _ in range(warmup):
             fn()
         barrier()
+        if rank == 0 and sampler.mark_at is None:
+            sampler.mark_at = len(sampler.lines)
         evs = []
         for _ in range(steps):
             flush.fill_(1)  # L2 flush, outside the timed events
@@ -491,16 +502,19 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), out
 
+    # clocks: started BEFORE the warm-up and killed AFTER both timed legs (B200_PROFILING.md: "start before, kill after") -- the
+    # sampler's start-up and exit are process events on the same GPU and must not fall into a timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
     ms_total, out = timed(step_resident, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
     loss_val = out.detach().clone().reshape(())
     if world > 1:
         dist.all_reduce(loss_val, op=dist.ReduceOp.SUM)  # the DDP loss all-reduce (after the timed region)
         loss_val /= world
     ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
     status_ok = True
 
     # ---- roofline of the dominant kernel + live peaks (rank 0) -------------------------------------------------------
