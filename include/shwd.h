@@ -221,6 +221,24 @@ int shwd_resflow_fwd(const float* x, int npts, const float* params, const float*
 int shwd_resflow_bwd(const float* x, const float* gy, int npts, const float* params, const float* uv, int n_layers,
                      float coeff, float* gx, float* gparams, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the learned sphere map phi, Planar variant: a stack of planar flows z <- z + u^ tanh(lin + b), fused -------------
+ * Replaces Norm_Flow_structure.forward ("Planar", s2_wasserstein.py:140-143,160-163; normflows_ishikawa/flows/planar.py:49-60:
+ * u^ = u + (log(1 + exp(<w,u>)) - 1 - <w,u>) w / |w|^2, act = tanh) and its autograd; the log-determinant is discarded by
+ * the caller and not computed.  params: n_layers x shwd_planar_params_per_layer() RAW parameters [u 3 | w 3 | b 1] per flow
+ * layer, n_layers <= shwd_planar_max_layers().  `lin` is the reference's sum over dim 1 of w * z:
+ *   clouds == 0: x, y, gy, gx are (npts,3) and lin_n = <w, z_n>                       (the un-batched branch);
+ *   clouds  > 0: they are (clouds,npts,3) and lin_bc = w_c sum_n z_bnc               (what batched clouds yield in the
+ *                reference: dim 1 is the point axis); colsum (clouds,3), float64, receives the per-cloud column sums
+ *                of x in the forward and is handed back to the backward (x itself is not read again there).
+ * gparams: gradient w.r.t. the raw parameters (same layout), reduced in a fixed order (bit-reproducible). */
+int shwd_planar_max_layers(void);
+int shwd_planar_params_per_layer(void);
+size_t shwd_planar_workspace_bytes(int clouds, int npts, int n_layers);
+int shwd_planar_fwd(const float* x, int clouds, int npts, const float* params, int n_layers, float* y, double* colsum,
+                    void* stream);
+int shwd_planar_bwd(const float* x, const float* gy, const double* colsum, int clouds, int npts, const float* params,
+                    int n_layers, float* gx, float* gparams, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- exact optimal assignment (uniform weights, n == m): the exact solve behind ot.emd2 on the W_COS path ------------
  * Replaces the per-pair CPU solve `ot.emd2(a_i, b_i, C_i)` (s2_wasserstein.py:39-50, 99-110; main_rotation.py:63-79) by a
  * float64 forward auction with epsilon-scaling on the on-the-fly cost, one CTA per pair.  x4, y4: packed points (B,N,4)

@@ -64,6 +64,11 @@ SIGNATURES = {
     "shwd_resflow_uv_per_layer": (_i, []),
     "shwd_resflow_fwd": (_i, [_vp, _i, _vp, _vp, _i, _f, _vp, _vp]),
     "shwd_resflow_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "shwd_planar_max_layers": (_i, []),
+    "shwd_planar_params_per_layer": (_i, []),
+    "shwd_planar_workspace_bytes": (_sz, [_i, _i, _i]),
+    "shwd_planar_fwd": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "shwd_planar_bwd": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "shwd_exact_assignment_max_points": (_i, []),
     "shwd_exact_assignment": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "shwd_exact_assignment_dense": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),

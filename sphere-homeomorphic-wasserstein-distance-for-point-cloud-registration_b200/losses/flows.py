@@ -5,8 +5,9 @@ flows ``Norm_Flow_structure`` builds from the vendored normflows 1.7.2 copy
 Only the forward map is kept -- the reference discards the log-determinant (``x, _ = flow(x)``,
 s2_wasserstein.py:160-163).  The modules below own the parameters and define the map; on CUDA inputs a stack of
 standard Residual flows (hidden 8, 7 layers -- what ``Norm_Flow_structure`` builds) runs as ONE fused kernel per direction
-(``csrc/resflow.cu``, ``fused_residual_stack``) instead of ~45 eager kernels per flow layer; anything else (Planar, other
-widths, CPU tensors) runs the eager modules.
+(``csrc/resflow.cu``, ``fused_residual_stack``) instead of ~45 eager kernels per flow layer, and a stack of Planar flows
+on (N,3) or (B,N,3) inputs likewise (``csrc/planar.cu``, ``fused_planar_stack``); anything else (other widths, CPU tensors)
+runs the eager modules.
 """
 import math
 
@@ -177,3 +178,18 @@ def fused_residual_stack(flows, x, uv=None):
         params += _raw_params(f)
     coeff = list(flows[0].net)[1].coeff
     return ops.ResidualFlowStackFn.apply(x, uv.to(x.device), len(flows), coeff, *params).reshape(x.shape)
+
+
+def is_planar_stack(flows):
+    """True when every flow is a 3-D PlanarFlow and the stack is no deeper than the fused kernel's limit (8)."""
+    return 0 < len(flows) <= 8 and all(isinstance(f, PlanarFlow) and tuple(f.w.shape) == (1, 3) for f in flows)
+
+
+def fused_planar_stack(flows, x):
+    """phi(x) for a Planar stack through the fused CUDA kernels (x: (N,3) or (B,N,3) CUDA tensor)."""
+    from .. import ops
+    params = []
+    for f in flows:
+        params += [f.u, f.w, f.b]
+    return ops.PlanarFlowStackFn.apply(x, len(flows), *params)
+

@@ -717,6 +717,58 @@ class ResidualFlowStackFn(torch.autograd.Function):
         return (gx, None, None, None) + tuple(grads)
 
 
+class PlanarFlowStackFn(torch.autograd.Function):
+    """y = phi(x) for a stack of Planar flows, one fused launch per direction (csrc/planar.cu).
+    ``apply(x, n_layers, *params)``: ``params`` are the modules' raw tensors, per flow u (1,3), w (1,3), b (1,).  ``x`` is
+    (N,3) -- lin = <w, z_n> -- or (B,N,3) -- lin = w_c sum_n z_bnc, what the reference's sum over dim 1 yields for batched
+    clouds (flows/planar.py:49-60 as called from s2_wasserstein.py:160-163)."""
+
+    @staticmethod
+    def forward(ctx, x, n_layers, *params):
+        lib = _lib.lib()
+        if not x.is_cuda:
+            raise RuntimeError("phi inputs must live on a CUDA device: no CPU fallback")
+        if x.dim() not in (2, 3) or x.shape[-1] != 3:
+            raise ValueError("fused Planar stack: x must be (N,3) or (B,N,3)")
+        xc = x.contiguous().float()
+        flat = torch.cat([p.reshape(-1) for p in params]).float()
+        if flat.numel() != n_layers * lib.shwd_planar_params_per_layer() or not 0 < n_layers <= lib.shwd_planar_max_layers():
+            raise ValueError("parameter list does not match the fused Planar-flow layout")
+        clouds, npts = (xc.shape[0], xc.shape[1]) if xc.dim() == 3 else (0, xc.shape[0])
+        y = torch.empty_like(xc)
+        colsum = torch.empty((max(clouds, 1), 3), device=xc.device, dtype=torch.float64)
+        if xc.numel():
+            with torch.cuda.device(xc.device):
+                _lib.check(lib.shwd_planar_fwd(_ptr(xc), clouds, npts, _ptr(flat), int(n_layers), _ptr(y), _ptr(colsum), _stream()),
+                           "shwd_planar_fwd")
+        ctx.save_for_backward(xc, flat, colsum)
+        ctx.n_layers, ctx.clouds, ctx.npts = int(n_layers), clouds, npts
+        ctx.shapes = [p.shape for p in params]
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, flat, colsum = ctx.saved_tensors
+        lib = _lib.lib()
+        gy = gy.contiguous().float()
+        gx = torch.empty_like(xc)
+        gp = torch.zeros_like(flat)
+        if xc.numel():
+            wsb = lib.shwd_planar_workspace_bytes(ctx.clouds, ctx.npts, ctx.n_layers)
+            ws = torch.empty(max(wsb, 8), device=xc.device, dtype=torch.uint8)
+            with torch.cuda.device(xc.device):
+                _lib.check(lib.shwd_planar_bwd(_ptr(xc), _ptr(gy), _ptr(colsum), ctx.clouds, ctx.npts, _ptr(flat), ctx.n_layers,
+                                               _ptr(gx), _ptr(gp), _ptr(ws), wsb, _stream()), "shwd_planar_bwd")
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = 1
+            for d in shp:
+                n *= d
+            grads.append(gp[off:off + n].view(shp))
+            off += n
+        return (gx, None) + tuple(grads)
+
+
 def _sort_i32(keys2d):
     """(S,len) float32 keys -> (sorted values, int32 stable-sort permutation); device-side only."""
     lib = _lib.lib()

@@ -1157,7 +1157,7 @@ def _state(d, prefix):
 
 @pytest.mark.parametrize("name", ["Residual", "Planar"])
 def test_phi_matches_vendored_normflows_fixture(shwd, name):
-    """Norm_Flow_structure on the GPU (Residual: the fused resflow kernels; Planar: eager) loaded with the REFERENCE's
+    """Norm_Flow_structure on the GPU (Residual: the fused resflow kernels; Planar: the fused planar kernels) loaded with the REFERENCE's
     state_dict -- same keys, shapes and order as train_W_COS.py:204 saves -- against outputs and autograd gradients frozen
     from the vendored normflows 1.7.2 (tests/golden/make_golden.py section 7): batched clouds and the (N,3) branch."""
     d = gold("flow_" + name.lower())
@@ -1168,6 +1168,7 @@ def test_phi_matches_vendored_normflows_fixture(shwd, name):
     for tag in ("b", "u"):
         x = torch.from_numpy(d["x_" + tag]).to(dev()).requires_grad_(True)
         y = phi(x)
+        assert name != "Planar" or type(y.grad_fn).__name__ == "PlanarFlowStackFnBackward"
         named = [(n, q) for n, q in phi.named_parameters() if q.dtype == torch.float32 and q.dim() > 0]
         gs = torch.autograd.grad((y * torch.from_numpy(d["w_" + tag]).to(dev())).sum(), [x] + [q for _, q in named], allow_unused=True)
         ey, egx = rel(y, torch.from_numpy(d["y_" + tag])), rel(gs[0], torch.from_numpy(d["gx_" + tag]))
@@ -1186,6 +1187,91 @@ def test_phi_matches_vendored_normflows_fixture(shwd, name):
         phi.load_state_dict(sd)
         x = torch.from_numpy(d["x_b"]).to(dev())
         assert rel(phi(x), phi.forward_eager(x)) < TOL
+
+
+@pytest.mark.parametrize("shape,layers", [((32, 1024, 3), 3), ((3, 1000, 3), 8), ((4, 16, 3), 8), ((1, 7, 3), 1), ((2, 1, 3), 2), ((1, 20000, 3), 5),
+                                          ((5000, 3), 3), ((1, 3), 1), ((257, 3), 8), ((70001, 3), 2)])
+def test_fused_planar_stack_matches_eager_modules(shwd, shape, layers):
+    """csrc/planar.cu against the eager PlanarFlow modules (pinned to the vendored normflows by the fixture test above) in
+    float64: batched clouds (lin = w_c sum_n z_bnc, the reference's sum over dim 1) and the (N,3) branch, every stack depth
+    the kernel templates cover, sizes that do not fill a CTA; value, d/dx, d/d(u, w, b); bit-reproducible."""
+    torch.manual_seed(shape[-2] + layers)
+    phi = shwd.losses.Norm_Flow_structure(flow_name="Planar", n_flow_layer=layers)
+    with torch.no_grad():
+        for q in phi.parameters():
+            q.add_(0.2 * torch.randn_like(q))
+        if len(shape) == 3 and shape[1] >= 100:
+            # Batched clouds: every layer translates the cloud by d = u^ tanh(w S + b) and the column sum S moves by N d, so a
+            # perturbation of S grows by 1 + N u^ w (1 - tanh^2) per layer.  With |u^| ~ 1 that is ~N: the float32 result of the
+            # reference itself is then decided by the rounding of its sum.  For a comparison that means something, pick
+            # parameters with u^ = eps w + (small vector orthogonal to w), eps ~ 1 / N: u = alpha w + q with alpha solving
+            # alpha + (softplus(alpha |w|^2) - 1 - alpha |w|^2) / |w|^2 = eps (monotone in alpha -> bisection).
+            N = shape[1]
+            for f in phi.net:
+                f.w.mul_(2.0 / N ** 0.5)  # w S stays inside tanh's active range: S ~ 0.7 sqrt(N)
+                w = f.w.double().reshape(3)
+                ww = (w * w).sum()
+                eps = (2.0 * torch.rand(()).item() - 1.0) * 2.0 / (N * ww.item() ** 0.5)
+                lo_a, hi_a = -1e4, 1e4
+                for _ in range(200):
+                    mid = 0.5 * (lo_a + hi_a)
+                    val = mid + (F.softplus(mid * ww) - 1 - mid * ww) / ww - eps
+                    lo_a, hi_a = (mid, hi_a) if val < 0 else (lo_a, mid)
+                q = torch.randn(3, dtype=torch.float64) / N
+                q = q - (q * w).sum() / ww * w
+                f.u.copy_((0.5 * (lo_a + hi_a) * w + q).float().reshape(1, 3))
+    x = torch.randn(*shape) * 0.7
+    wgt = torch.randn(*shape)
+    phi64 = shwd.losses.Norm_Flow_structure(flow_name="Planar", n_flow_layer=layers).double()
+    phi64.load_state_dict({k: v.double() for k, v in phi.state_dict().items()})
+    x64 = x.double().requires_grad_(True)
+    y64 = phi64.forward_eager(x64)
+    g64 = torch.autograd.grad((y64 * wgt.double()).sum(), [x64] + list(phi64.parameters()))
+    phi32 = shwd.losses.Norm_Flow_structure(flow_name="Planar", n_flow_layer=layers)
+    phi32.load_state_dict(phi.state_dict())
+    x32 = x.clone().requires_grad_(True)
+    y32 = phi32.forward_eager(x32)
+    g32 = torch.autograd.grad((y32 * wgt).sum(), [x32] + list(phi32.parameters()))
+    scale = max(b.norm().item() for b in g64[1:])
+
+    def relc(a, b):  # saturated layers have exactly-zero float32 gradients against 1e-100 in float64: clamp the denominator
+        return (a.detach().double().cpu() - b).norm().item() / max(b.norm().item(), 1e-3 * scale)
+
+    # eager float32 against float64: the reference's own rounding
+    floor_y, floor = rel(y32, y64), max(relc(a, b) for a, b in zip(g32, g64))
+    phi = phi.to(dev())
+    xg = x.to(dev()).requires_grad_(True)
+    y = phi(xg)
+    assert type(y.grad_fn).__name__ == "PlanarFlowStackFnBackward"
+    g = torch.autograd.grad((y * wgt.to(dev())).sum(), [xg] + list(phi.parameters()))
+    ey = rel(y, y64)
+    eg = [relc(a, b) for a, b in zip(g, g64)]
+    print("planar %s x%d: y %.2e d/dx %.2e worst d/dparam %.2e (eager f32 floor: y %.2e grads %.2e)"
+          % (shape, layers, ey, eg[0], max(eg[1:]), floor_y, floor))
+    assert ey < max(TOL, 8 * floor_y) and eg[0] < max(TOL, 8 * floor) and max(eg[1:]) < max(TOL, 16 * floor)
+    y2 = phi(xg)
+    g2 = torch.autograd.grad((y2 * wgt.to(dev())).sum(), [xg] + list(phi.parameters()))
+    assert torch.equal(y, y2) and all(torch.equal(a, b) for a, b in zip(g, g2))
+    with torch.no_grad():
+        assert torch.equal(phi(xg), y)
+
+
+def test_fused_planar_stack_guards(shwd):
+    """Empty clouds, the optuna structure and deeper-than-eight stacks (eager), argument errors through the C ABI."""
+    phi = shwd.losses.Norm_Flow_structure(flow_name="Planar", n_flow_layer=3).to(dev())
+    for shape in ((0, 3), (4, 0, 3), (0, 16, 3)):
+        x = torch.zeros(*shape, device=dev(), requires_grad=True)
+        y = phi(x)
+        assert y.shape == x.shape
+        (y.sum() + sum(q.sum() for q in phi.parameters()) * 0).backward()
+    opt = shwd.losses.Norm_Flow_structure_optuna(flow_name="Planar", n_flow_layer=2).to(dev())
+    x = torch.randn(4, 50, 3, device=dev())
+    assert type(opt(x.requires_grad_(True)).grad_fn).__name__ == "PlanarFlowStackFnBackward"
+    deep = shwd.losses.Norm_Flow_structure(flow_name="Planar", n_flow_layer=9).to(dev())
+    assert type(deep(x).grad_fn).__name__ != "PlanarFlowStackFnBackward" and deep(x).shape == x.shape
+    lib = shwd._lib.lib()
+    assert lib.shwd_planar_max_layers() == 8 and lib.shwd_planar_params_per_layer() == 7
+    assert lib.shwd_planar_fwd(None, 0, 4, None, 1, None, None, None) == -1  # SHWD_ERR_INVALID_ARGUMENT
 
 
 def test_euclid_sliced_w_matches_notebook_fixture(shwd):
@@ -1212,22 +1298,38 @@ def test_max_wrapper_step_matches_reference_fixture(shwd, name):
     'test' branch."""
     d = gold("max_wrapper_" + name.lower())
     L = shwd.losses
-    phi = L.Norm_Flow_structure(flow_name=name, n_flow_layer=int(d["n_flow_layer"]))
-    phi.load_state_dict(_state(d, "sd0__"))
-    phi = phi.to(dev())
-    op = torch.optim.SGD(list(phi.parameters()), lr=float(d["lr"]))
-    csw = L.Cos_disimilarity_W(dev(), p=2)
-    assert csw.solver == "auto"
-    crit = L.max_cos_disimilarity_wassersten_distance(phi=phi, CSW=csw, device=dev(), phi_op=op, max_iter=int(d["max_iter"]),
-                                                       lam=float(d["lam"]))
-    second = torch.from_numpy(d["second"]).to(dev()).requires_grad_(True)
-    first = torch.from_numpy(d["first"]).to(dev())
-    cswd, ft, st = crit(first, second, "train")
-    (g2,) = torch.autograd.grad(cswd, second)
-    e = (abs(cswd.item() - float(d["cswd"])) / float(d["cswd"]), rel(ft, torch.from_numpy(d["first_t"])),
-         rel(st, torch.from_numpy(d["second_t"])), rel(g2, torch.from_numpy(d["g_second"])))
+
+    def run(eager):
+        phi = L.Norm_Flow_structure(flow_name=name, n_flow_layer=int(d["n_flow_layer"]))
+        phi.load_state_dict(_state(d, "sd0__"))
+        phi = phi.to(dev())
+        if eager:
+            phi.forward = phi.forward_eager
+        op = torch.optim.SGD(list(phi.parameters()), lr=float(d["lr"]))
+        csw = L.Cos_disimilarity_W(dev(), p=2)
+        assert csw.solver == "auto"
+        crit = L.max_cos_disimilarity_wassersten_distance(phi=phi, CSW=csw, device=dev(), phi_op=op, max_iter=int(d["max_iter"]),
+                                                           lam=float(d["lam"]))
+        second = torch.from_numpy(d["second"]).to(dev()).requires_grad_(True)
+        first = torch.from_numpy(d["first"]).to(dev())
+        cswd, ft, st = crit(first, second, "train")
+        (g2,) = torch.autograd.grad(cswd, second)
+        e = (abs(cswd.item() - float(d["cswd"])) / float(d["cswd"]), rel(ft, torch.from_numpy(d["first_t"])),
+             rel(st, torch.from_numpy(d["second_t"])), rel(g2, torch.from_numpy(d["g_second"])))
+        return e, phi, crit, first, second
+
+    e, phi, crit, first, second = run(False)
     print("max wrapper %s: cswd %.2e first_t %.2e second_t %.2e d/dsecond %.2e" % ((name,) + e))
-    assert e[0] < TOL and e[1] < TOL and e[2] < TOL and e[3] < 5e-5
+    slack = 1.0
+    if name == "Planar":
+        # The fixture's first cloud is centred: its column sums -- the ONLY input of the reference's batched Planar layers
+        # (planar.py:52 sums over dim 1 = the points) -- are float32 rounding residue (~1e-7), amplified by ~N u^ w per layer.
+        # How far torch's own CUDA kernels land from the CPU-generated fixture is therefore the yardstick, measured here.
+        ee = run(True)[0]
+        print("   (eager torch modules on the same GPU: cswd %.2e first_t %.2e second_t %.2e d/dsecond %.2e)" % ee)
+        slack = 2.0
+        assert all(a < max(b * 3, t) for a, b, t in zip(e, ee, (TOL, TOL, TOL, 5e-5)))
+    assert e[0] < TOL and e[1] < TOL and e[2] < TOL and e[3] < 5e-5 * slack
     for k, v in _state(d, "sd1__").items():
         if v.dtype == torch.float32 and v.dim() > 0 and "last_" not in k and not k.endswith("scale"):
             got = phi.state_dict()[k].cpu()
