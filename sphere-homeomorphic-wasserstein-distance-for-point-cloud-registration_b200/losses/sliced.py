@@ -2,11 +2,15 @@
 
   sliced_wasserstein_sphere / sliced_cost / emd1D_circle   Point_Cloud_Resistration/losses/max_spherical_sliced_w.py:210-310
   sliced_wasserstein_distance                               Wasserstein_flow_problem/Flow_ellipsoid.ipynb:203-220 (cell 5)
+  transform_to_sphere / max_spherical_wassersten_distance   max_spherical_sliced_w.py:334-350, 498-536 (SURVEY.md 8f #4 tail)
 
 The frames / directions are drawn with torch exactly as the reference draws them (``qr(randn(P,d,2))``,
 row-normalised ``randn(P,d)``); projection, sort and the 1-D reductions run in CUDA.
 """
+import math
+
 import torch
+from torch import nn
 
 from .. import ops
 
@@ -113,3 +117,66 @@ def sliced_wasserstein_distance(first_samples, second_samples, num_projection=10
         projections = rand_projections(second_samples.size(-1), num_projection, device=device)
     w = ops.euclid_sliced_w(first_samples.to(device), second_samples.to(device), projections, float(p))
     return w.reshape(()) if first_samples.dim() == 2 else w
+
+
+class transform_to_sphere(nn.Module):
+    """max_spherical_sliced_w.py:334-350 -- the small sphere map of the max-SSW wrapper: an MLP 3 -> 16 -> 4 -> 2 (tanh) read as
+    two angles, ``theta_1 = pi (tanh(.)/2 + 1/2)``, ``theta_2 = pi tanh(.)``, mapped to a point of S^2.  Same module tree
+    (``net.0``, ``net.2``, ``net.4``) as the reference, so its ``state_dict`` loads unchanged."""
+
+    def __init__(self):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(3, 16), nn.Tanh(), nn.Linear(16, 4), nn.Tanh(), nn.Linear(4, 2))
+
+    def forward(self, x):
+        a = self.net(x)
+        t1 = math.pi * (torch.tanh(a[:, :, 0]) / 2 + 0.5)
+        t2 = math.pi * torch.tanh(a[:, :, 1])
+        return torch.stack([torch.sin(t1) * torch.cos(t2), torch.sin(t1) * torch.sin(t2), torch.cos(t1)], dim=2)
+
+
+class max_spherical_wassersten_distance(nn.Module):
+    """max_spherical_sliced_w.py:498-536 -- gradient ascent of ``phi`` on the summed sliced cost of the detached clouds
+    (``max_iter`` optimiser steps), then the outer sum over the batch; returns ``(ssw, phi(first), phi(second))``.
+
+    ``SSW`` is called the reference's way, once per pair: ``SSW(first_t[i], second_t[i], num_projections, device, p=p)``
+    (pass ``losses.sliced_wasserstein_sphere``); every such call is one fused project + sort + reduce launch sequence
+    (``ops.SlicedLossFn``).  ``shared_frames=True`` (an extension, off by default) draws ONE set of frames per evaluation and
+    sends the whole batch through a single fused call instead of B calls -- same expectation per pair, but the pairs then
+    share their slices, which the reference's per-pair draws (:307-308) do not."""
+
+    def __init__(self, num_projections, phi, SSW, phi_op, p=2, max_iter=10, device="cuda", shared_frames=False, verbose=True):
+        super().__init__()
+        self.num_projections = num_projections
+        self.phi = phi
+        self.SSW = SSW
+        self.phi_op = phi_op
+        self.p = p
+        self.max_iter = max_iter
+        self.device = device
+        self.shared_frames = shared_frames
+        self.verbose = verbose
+
+    def _sum_over_pairs(self, a, b):
+        if self.shared_frames:
+            Z = torch.randn((self.num_projections, a.shape[-1], 2), device=a.device)
+            return sliced_cost(a, b, stiefel_frames(Z), p=self.p).sum()
+        ssw = 0
+        for i in range(len(a)):
+            ssw = ssw + self.SSW(a[i], b[i], self.num_projections, self.device, p=self.p)
+        return ssw
+
+    def forward(self, first_samples, second_samples, train_or_test="train"):
+        if train_or_test == "train":
+            f0, s0 = first_samples.detach(), second_samples.detach()
+            for _ in range(self.max_iter):
+                ssw = self._sum_over_pairs(self.phi(f0), self.phi(s0))
+                loss = -ssw  # gradient ascent
+                self.phi_op.zero_grad()
+                loss.backward(retain_graph=True)
+                self.phi_op.step()
+                if self.verbose:
+                    print(ssw.item())  # (:524)
+        first_t = self.phi(first_samples)
+        second_t = self.phi(second_samples)
+        return self._sum_over_pairs(first_t, second_t), first_t, second_t

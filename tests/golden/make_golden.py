@@ -196,6 +196,7 @@ def main():
     make_notebook_fixture()
     make_weighted_circle_fixture()
     make_weighted_wp_fixture()
+    make_max_ssw_fixture()
 
 
 def _flat_state(prefix, sd):
@@ -343,8 +344,56 @@ def make_notebook_fixture():
     np.savez(os.path.join(HERE, "notebook_sliced_wasserstein.npz"), **out)
 
 
+class FixedFramesSSW:
+    """An ``SSW`` callable with the signature the max-SSW wrapper calls (max_spherical_sliced_w.py:518,532) that replaces the
+    random frames of sliced_wasserstein_sphere (:307-308) by a fixed cycle of frames, so a wrapper run is a function of its
+    inputs.  ``sliced_cost`` is the reference's (fixture generation) or the drop-in's (the GPU test)."""
+
+    def __init__(self, sliced_cost, Us):
+        self.sliced_cost, self.Us, self.k = sliced_cost, Us, 0
+
+    def __call__(self, Xs, Xt, num_projections, device, p=2):
+        U = self.Us[self.k % len(self.Us)]
+        self.k += 1
+        return self.sliced_cost(Xs, Xt, U.to(Xs.device), p=p)
+
+
+def make_max_ssw_fixture():
+    """SURVEY.md 8f #4 tail: one training call of max_spherical_wassersten_distance (max_spherical_sliced_w.py:498-536) with
+    the reference's own sphere map transform_to_sphere (:334-350), from the UNMODIFIED reference: two SGD ascent steps on
+    phi over detached inputs, then the outer sum over the batch of per-pair sliced costs; p = 2 and p = 1."""
+    ssw = _load(os.path.join(REF, "Point_Cloud_Resistration/losses/max_spherical_sliced_w.py"), "ref_ssw_max")
+    out = {}
+    for p in (2, 1):
+        torch.manual_seed(600 + p)
+        phi = ssw.transform_to_sphere()
+        phi_op = torch.optim.SGD(phi.parameters(), lr=0.05)
+        g = torch.Generator().manual_seed(60 + p)
+        Us = torch.linalg.qr(torch.randn(5, 24, 3, 2, generator=g)).Q
+        first = torch.randn(3, 40, 3, generator=g)
+        second = (first[:, torch.randperm(40, generator=g)][:, :33] * 0.8 + 0.1 * torch.randn(3, 33, 3, generator=g)).requires_grad_(True)
+        crit = ssw.max_spherical_wassersten_distance(24, phi, FixedFramesSSW(ssw.sliced_cost, Us), phi_op, p=p, max_iter=2, device="cpu")
+        sd0 = {k: v.clone() for k, v in phi.state_dict().items()}
+        val, ft, st = crit(first, second, "train")
+        (g_second,) = torch.autograd.grad(val, second)
+        sd1 = {k: v.clone() for k, v in phi.state_dict().items()}
+        val_test, _, _ = crit(first, second.detach(), "test")
+        out.update({f"first_p{p}": first.numpy(), f"second_p{p}": second.detach().numpy(), f"Us_p{p}": Us.numpy(),
+                    f"ssw_p{p}": np.float64(val.item()), f"first_t_p{p}": ft.detach().numpy(), f"second_t_p{p}": st.detach().numpy(),
+                    f"g_second_p{p}": g_second.numpy(), f"ssw_test_p{p}": np.float64(val_test.item())})
+        out.update(_flat_state(f"sd0_p{p}__", sd0))
+        out.update(_flat_state(f"sd1_p{p}__", sd1))
+        print("max SSW wrapper p=%d" % p, val.item(), "test", val_test.item())
+    out.update(lr=np.float64(0.05), max_iter=np.int64(2), num_projections=np.int64(24))
+    np.savez(os.path.join(HERE, "max_ssw_wrapper.npz"), **out)
+
+
 if __name__ == "__main__":
-    if "--wrappers-only" in sys.argv:  # regenerate only the fixtures added in round 2 (the older ones are unchanged)
+    if "--max-ssw-only" in sys.argv:  # the fixture added in the last session of round 2
+        _install_shims()
+        torch.set_num_threads(8)
+        make_max_ssw_fixture()
+    elif "--wrappers-only" in sys.argv:  # regenerate only the fixtures added in round 2 (the older ones are unchanged)
         _install_shims()
         torch.set_num_threads(8)
         import losses as _ref_losses

@@ -1338,6 +1338,57 @@ def test_max_wrapper_step_matches_reference_fixture(shwd, name):
     assert ctest.item() == pytest.approx(float(d["cswd_test"]), rel=TOL)
 
 
+class _FixedFramesSSW:
+    """The SSW callable of tests/golden/make_golden.py (fixed cycle of frames instead of random ones), on the drop-in's sliced_cost."""
+
+    def __init__(self, sliced_cost, Us):
+        self.sliced_cost, self.Us, self.k = sliced_cost, Us, 0
+
+    def __call__(self, Xs, Xt, num_projections, device, p=2):
+        U = self.Us[self.k % len(self.Us)]
+        self.k += 1
+        return self.sliced_cost(Xs, Xt, U.to(Xs.device), p=p)
+
+
+@pytest.mark.parametrize("p", [2, 1])
+def test_max_ssw_wrapper_step_matches_reference_fixture(shwd, p, capsys):
+    """One training call of max_spherical_wassersten_distance with transform_to_sphere (max_spherical_sliced_w.py:334-350,
+    498-536; SURVEY.md 8f #4 tail) against the frozen run of the unmodified reference: two SGD ascent steps, the outer sum of
+    per-pair sliced costs (33 against 40 points), both transformed clouds, the gradient reaching the second cloud, phi after the
+    ascent and the 'test' branch."""
+    d = gold("max_ssw_wrapper")
+    L = shwd.losses
+    phi = L.transform_to_sphere()
+    phi.load_state_dict(_state(d, "sd0_p%d__" % p))
+    phi = phi.to(dev())
+    op = torch.optim.SGD(phi.parameters(), lr=float(d["lr"]))
+    Us = torch.from_numpy(d["Us_p%d" % p]).to(dev())
+    crit = L.max_spherical_wassersten_distance(int(d["num_projections"]), phi, _FixedFramesSSW(L.sliced_cost, Us), op, p=p,
+                                               max_iter=int(d["max_iter"]), device=dev())
+    first = torch.from_numpy(d["first_p%d" % p]).to(dev())
+    second = torch.from_numpy(d["second_p%d" % p]).to(dev()).requires_grad_(True)
+    val, ft, st = crit(first, second, "train")
+    (g2,) = torch.autograd.grad(val, second)
+    want = float(d["ssw_p%d" % p])
+    e = (abs(val.item() - want) / want, rel(ft, torch.from_numpy(d["first_t_p%d" % p])), rel(st, torch.from_numpy(d["second_t_p%d" % p])),
+         rel(g2, torch.from_numpy(d["g_second_p%d" % p])))
+    with capsys.disabled():
+        print("max SSW wrapper p=%d: ssw %.2e first_t %.2e second_t %.2e d/dsecond %.2e" % ((p,) + e))
+    assert max(e) < TOL
+    for k, v in _state(d, "sd1_p%d__" % p).items():
+        got = phi.state_dict()[k].cpu()
+        assert torch.allclose(got, v, rtol=2e-4, atol=2e-6), (k, (got - v).abs().max().item())
+    vt, _, _ = crit(first, second.detach(), "test")
+    assert vt.item() == pytest.approx(float(d["ssw_test_p%d" % p]), rel=TOL)
+    # the one-call extension: same estimator, frames shared by the pairs of one evaluation
+    torch.manual_seed(0)
+    shared = L.max_spherical_wassersten_distance(256, phi, None, op, p=p, max_iter=0, device=dev(), shared_frames=True)
+    vs, _, _ = shared(first, second.detach(), "test")
+    per_pair = L.max_spherical_wassersten_distance(256, phi, L.sliced_wasserstein_sphere, op, p=p, max_iter=0, device=dev())
+    vp, _, _ = per_pair(first, second.detach(), "test")
+    assert vs.item() == pytest.approx(vp.item(), rel=0.25)  # two Monte-Carlo estimates of the same quantity
+
+
 def test_max_wrapper_with_fused_phi_runs_the_reference_step(shwd):
     """One training step of max_cos_disimilarity_wassersten_distance (s2_wasserstein.py:234-262) with the fused phi:
     the inner ascent changes phi's parameters, the outer loss back-propagates to the cloud."""

@@ -333,3 +333,18 @@ def test_weight_cdf_equals_the_reference_cumsum_bit_for_bit():
     # and the closed form the uniform kernel evaluates in registers: fl((i + 1) * fl(1 / n))
     closed = (torch.arange(1, n + 1, dtype=torch.float64) * float(torch.tensor(1 / n, dtype=torch.float32))).float()
     assert torch.equal(uni[0], closed)
+
+
+def test_transform_to_sphere_is_the_reference_module():
+    """max_spherical_sliced_w.py:334-350: same state_dict keys / shapes, and -- loaded with the weights the unmodified reference
+    ended its ascent with -- the same points on the sphere (fixture of tests/golden/make_golden.py::make_max_ssw_fixture)."""
+    import numpy as np
+    d = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "max_ssw_wrapper.npz")))
+    phi = L.transform_to_sphere()
+    sd = {k[len("sd1_p2__"):].replace("__", "."): torch.from_numpy(v) for k, v in d.items() if k.startswith("sd1_p2__")}
+    assert list(phi.state_dict().keys()) == list(sd.keys()) == ["net.0.weight", "net.0.bias", "net.2.weight", "net.2.bias",
+                                                               "net.4.weight", "net.4.bias"]
+    phi.load_state_dict(sd)
+    y = phi(torch.from_numpy(d["first_p2"]))
+    assert torch.allclose(y, torch.from_numpy(d["first_t_p2"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(y.norm(dim=-1), torch.ones(3, 40), atol=1e-6)
