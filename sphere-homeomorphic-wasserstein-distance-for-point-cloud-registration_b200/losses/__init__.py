@@ -12,7 +12,9 @@ from .s2_wasserstein import (Cos_disimilarity_W, Geodesic_distance_W, Norm_Flow_
 from .sinkhorn import (Sinkhorn_Distance_Loss, log_Sinkhorn_Distance_Loss, log_N_Sinkhorn_Distance_Loss,
                        log_Sinkhorn_Distance_Loss_fixed)
 from .sliced import (sliced_wasserstein_sphere, sliced_cost, emd1D_circle, binary_search_circle,
-                     sliced_wasserstein_distance, transform_to_sphere, max_spherical_wassersten_distance)
+                     sliced_wasserstein_distance, transform_to_sphere, max_spherical_wassersten_distance,
+                     sliced_cost_fast, sliced_wasserstein_sphere_fast, transform_to_sphere_fast,
+                     max_spherical_wassersten_distance_fast)
 from .chamfer import chamfer_distance
 
 __all__ = [
@@ -21,4 +23,5 @@ __all__ = [
     "Sinkhorn_Distance_Loss", "log_Sinkhorn_Distance_Loss", "log_N_Sinkhorn_Distance_Loss",
     "log_Sinkhorn_Distance_Loss_fixed", "sliced_wasserstein_sphere", "sliced_cost", "emd1D_circle", "binary_search_circle",
     "sliced_wasserstein_distance", "chamfer_distance", "transform_to_sphere", "max_spherical_wassersten_distance",
+    "sliced_cost_fast", "sliced_wasserstein_sphere_fast", "transform_to_sphere_fast", "max_spherical_wassersten_distance_fast",
 ]

@@ -180,3 +180,34 @@ class max_spherical_wassersten_distance(nn.Module):
         first_t = self.phi(first_samples)
         second_t = self.phi(second_samples)
         return self._sum_over_pairs(first_t, second_t), first_t, second_t
+
+
+def sliced_cost_fast(Xs, Xt, Us, p=2, u_weights=None, v_weights=None):
+    """max_spherical_sliced_w_fast.py:258-295 (there named ``sliced_cost``) -- batched clouds (B,n,3), (B,m,3) with PER-PAIR
+    frames ``Us`` (B,P,3,2); returns the SUM over the pairs of the per-pair mean over slices, shape (1,), as the reference's
+    loop ``w1 += mean(binary_search_circle(Xps[i], Xpt[i]))`` does.  Each pair is one fused sliced call.  (The reference's
+    p == 1 branch fails on batched keys -- its ``gather`` index is flattened, :250 -- the same sum is returned here.)"""
+    if Us.dim() != 4 or Us.shape[0] != Xs.shape[0]:
+        raise ValueError("Us must be (batch, num_projections, d, 2) with one frame set per pair")
+    w1 = torch.zeros((1,), device=Xs.device)
+    for i in range(Xs.shape[0]):
+        w1 = w1 + sliced_cost(Xs[i], Xt[i], Us[i], p=p, u_weights=u_weights, v_weights=v_weights)
+    return w1
+
+
+def sliced_wasserstein_sphere_fast(Xs, Xt, num_projections, device, u_weights=None, v_weights=None, p=2):
+    """max_spherical_sliced_w_fast.py:298-319 -- one frame draw ``qr(randn(B,P,d,2))`` for the whole batch, then sliced_cost_fast."""
+    Z = torch.randn((Xs.shape[0], num_projections, Xs.shape[2], 2), device=device)
+    return sliced_cost_fast(Xs, Xt, stiefel_frames(Z), p=p, u_weights=u_weights, v_weights=v_weights)
+
+
+class transform_to_sphere_fast(transform_to_sphere):
+    """max_spherical_sliced_w_fast.py:323-340 -- the same module as transform_to_sphere."""
+
+
+class max_spherical_wassersten_distance_fast(max_spherical_wassersten_distance):
+    """max_spherical_sliced_w_fast.py:346-382 -- as max_spherical_wassersten_distance, with ``SSW`` called ONCE per evaluation on
+    the whole batch: ``SSW(phi(first), phi(second), num_projections, device, p=p)`` (pass sliced_wasserstein_sphere_fast)."""
+
+    def _sum_over_pairs(self, a, b):
+        return self.SSW(a, b, self.num_projections, self.device, p=self.p)

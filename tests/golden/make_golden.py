@@ -197,6 +197,7 @@ def main():
     make_weighted_circle_fixture()
     make_weighted_wp_fixture()
     make_max_ssw_fixture()
+    make_ssw_fast_fixture()
 
 
 def _flat_state(prefix, sd):
@@ -388,11 +389,58 @@ def make_max_ssw_fixture():
     np.savez(os.path.join(HERE, "max_ssw_wrapper.npz"), **out)
 
 
+def make_ssw_fast_fixture():
+    """The batched variant max_spherical_sliced_w_fast.py:258-295 (`sliced_cost` with per-pair frames (B,P,3,2): projection by
+    one broadcast matmul, then a loop over the batch of mean_P binary_search_circle; returns the SUM over the pairs, shape (1,))
+    and one training call of max_spherical_wassersten_distance_fast (:346-382) on it, from the unmodified reference."""
+    fast = _load(os.path.join(REF, "Point_Cloud_Resistration/losses/max_spherical_sliced_w_fast.py"), "ref_ssw_fast")
+    g = torch.Generator().manual_seed(91)
+    out = {}
+    for p in (2, 3):
+        Us = torch.linalg.qr(torch.randn(3, 16, 3, 2, generator=g)).Q
+        x = F.normalize(torch.randn(3, 40, 3, generator=g), dim=-1).requires_grad_(True)
+        y = F.normalize(torch.randn(3, 33, 3, generator=g), dim=-1).requires_grad_(True)
+        w = fast.sliced_cost(x, y, Us, p=p)
+        gx, gy = torch.autograd.grad(w.sum(), (x, y))
+        out.update({f"Us_p{p}": Us.numpy(), f"x_p{p}": x.detach().numpy(), f"y_p{p}": y.detach().numpy(), f"w_p{p}": w.detach().numpy(),
+                    f"gx_p{p}": gx.numpy(), f"gy_p{p}": gy.numpy()})
+        print("ssw fast p=%d" % p, w.detach().numpy())
+    # the wrapper, with the frames of every SSW call fixed (one (B,P,3,2) set per call, cycled)
+    torch.manual_seed(92)
+    phi = fast.transform_to_sphere_fast()
+    phi_op = torch.optim.SGD(phi.parameters(), lr=0.05)
+    Uc = torch.linalg.qr(torch.randn(4, 3, 16, 3, 2, generator=g)).Q
+    first = torch.randn(3, 40, 3, generator=g)
+    second = (first[:, :33] * 0.8 + 0.1 * torch.randn(3, 33, 3, generator=g)).requires_grad_(True)
+    crit = fast.max_spherical_wassersten_distance_fast(16, phi, FixedFramesSSW(fast.sliced_cost, Uc), phi_op, p=2, max_iter=2, device="cpu")
+    sd0 = {k: v.clone() for k, v in phi.state_dict().items()}
+    val, ft, st = crit(first, second, "train")
+    (g_second,) = torch.autograd.grad(val.sum(), second)
+    out.update(Uc=Uc.numpy(), first=first.numpy(), second=second.detach().numpy(), ssw=val.detach().numpy(), first_t=ft.detach().numpy(),
+               second_t=st.detach().numpy(), g_second=g_second.numpy())
+    out.update(_flat_state("sd0__", sd0))
+    out.update(_flat_state("sd1__", phi.state_dict()))
+    # the same call in float64 (same code, same weights): how far the reference's float32 gradient is from its own exact value
+    phi64 = fast.transform_to_sphere_fast().double()
+    phi64.load_state_dict({k: v.double() for k, v in sd0.items()})
+    op64 = torch.optim.SGD(phi64.parameters(), lr=0.05)
+    crit64 = fast.max_spherical_wassersten_distance_fast(16, phi64, FixedFramesSSW(fast.sliced_cost, Uc.double()), op64, p=2, max_iter=2,
+                                                         device="cpu")
+    second64 = second.detach().double().requires_grad_(True)
+    val64, _, _ = crit64(first.double(), second64, "train")
+    (g64,) = torch.autograd.grad(val64.sum(), second64)
+    out.update(g_second_f64=g64.numpy(), ssw_f64=val64.detach().double().numpy())
+    print("max SSW fast wrapper", val.detach().numpy(), "float32 vs float64 reference: d/dsecond",
+          float((g_second.double() - g64).norm() / g64.norm()))
+    np.savez(os.path.join(HERE, "ssw_fast.npz"), **out)
+
+
 if __name__ == "__main__":
-    if "--max-ssw-only" in sys.argv:  # the fixture added in the last session of round 2
+    if "--max-ssw-only" in sys.argv:  # the fixtures added in the last session of round 2
         _install_shims()
         torch.set_num_threads(8)
         make_max_ssw_fixture()
+        make_ssw_fast_fixture()
     elif "--wrappers-only" in sys.argv:  # regenerate only the fixtures added in round 2 (the older ones are unchanged)
         _install_shims()
         torch.set_num_threads(8)
