@@ -159,6 +159,13 @@ int shwd_sort_projected_max_points(void);
 int shwd_sort_set_method(int method);
 int shwd_sort_projected(const float* x, const float* frames, int B, int N, int P, int mode, float* sorted, int32_t* perm,
                         void* stream);
+/* The same three entry points with ONE FRAME SET PER PAIR, U / frames (B,P,3,2): the batched variant
+ * max_spherical_sliced_w_fast.py:258-319 (`Z = randn(B,P,d,2)`, `Us[b]` applied to pair b), circle keys only (mode 1). */
+int shwd_project_circle_pp(const float* x, const float* U, int B, int N, int P, float* keys, void* stream);
+int shwd_project_circle_bwd_scaled_pp(const float* x, const float* U, int B, int N, int P, const float* gkeys, const float* gw,
+                                      float* gx, void* stream);
+int shwd_sort_projected_pp(const float* x, const float* frames, int B, int N, int P, int mode, float* sorted, int32_t* perm,
+                           void* stream);
 /* Circular W1 by level median on sorted circle coordinates (emd1D_circle, max_spherical_sliced_w.py:230-247):
  * us (S,n), vs (S,m) sorted ascending, n + m <= 32768 -> w (S); gus/gvs (nullable) receive dW/d(sorted values). */
 size_t shwd_circular_w1_workspace_bytes(int S, int n, int m);

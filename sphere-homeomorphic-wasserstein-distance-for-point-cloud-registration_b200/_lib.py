@@ -36,10 +36,12 @@ SIGNATURES = {
     "shwd_chamfer_reduce": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp]),
     "shwd_chamfer_bwd_uniform": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp]),
     "shwd_project_circle": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "shwd_project_circle_pp": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "shwd_project_circle_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "shwd_project_line": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "shwd_project_line_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "shwd_project_circle_bwd_scaled": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "shwd_project_circle_bwd_scaled_pp": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "shwd_project_line_bwd_scaled": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "shwd_segmented_sort_workspace_bytes": (_sz, [_i, _i]),
     "shwd_segmented_sort": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -47,6 +49,7 @@ SIGNATURES = {
     "shwd_sort_projected_max_points": (_i, []),
     "shwd_sort_set_method": (_i, [_i]),
     "shwd_sort_projected": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "shwd_sort_projected_pp": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "shwd_circular_w1_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "shwd_circular_wp_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "shwd_euclid_sw_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),

@@ -68,11 +68,13 @@ __device__ __forceinline__ float line_key(const float* t /* theta[p][d] */, floa
 
 // keys[b,p,n] = (atan2(-q1, -q0) + pi) / (2 pi), q = normalize(U_p^T x_n)            (sliced_cost :270-279)
 __global__ void __launch_bounds__(PJ_THREADS) project_circle_kernel(const float* __restrict__ x, const float* __restrict__ U,
-                                                                    int N, int P, float* __restrict__ keys) {
+                                                                    int N, int P, float* __restrict__ keys, int pp) {
+  // pp: U holds one frame set PER PAIR, (B,P,3,2) (max_spherical_sliced_w_fast.py:298-319), instead of one (P,3,2) for all
   extern __shared__ float sU[];  // P_TILE * 6
   const int b = blockIdx.z;
   const int p0 = blockIdx.y * 32;
   const int pc = min(32, P - p0);
+  if (pp) U += (size_t)b * P * 6;
   for (int i = threadIdx.x; i < pc * 6; i += PJ_THREADS) sU[i] = __ldg(U + (size_t)p0 * 6 + i);
   __syncthreads();
   const int n = blockIdx.x * PJ_THREADS + threadIdx.x;
@@ -93,12 +95,13 @@ constexpr int PB_TILE = 256;  // slices staged per tile
 
 __global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd_kernel(const float* __restrict__ x, const float* __restrict__ U,
                                                                         int N, int P, const float* __restrict__ gk,
-                                                                        const float* __restrict__ gw, float* __restrict__ gx) {
+                                                                        const float* __restrict__ gw, float* __restrict__ gx, int pp) {
   // gw (nullable): per-pair upstream gradient of the slice MEAN -- the result is scaled by gw[b] / P here instead of by
   // an elementwise pass afterwards (same two roundings: the division, then the product)
   __shared__ float sU[PB_TILE * 6];
   __shared__ float red[PB_WARPS][3][32];
   const int b = blockIdx.y;
+  if (pp) U += (size_t)b * P * 6;  // one frame set per pair
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + lane;
   const bool ok = n < N;
@@ -164,10 +167,11 @@ __global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd_kernel(const fl
 // result is the narrow kernel's, bit for bit.
 __global__ void __launch_bounds__(PJ_THREADS) project_circle_bwd4_kernel(const float* __restrict__ x, const float* __restrict__ U,
                                                                          int N, int P, const float* __restrict__ gk,
-                                                                         const float* __restrict__ gw, float* __restrict__ gx) {
+                                                                         const float* __restrict__ gw, float* __restrict__ gx, int pp) {
   __shared__ float sU[PB_TILE * 6];
   __shared__ float red[PB_WARPS][3][128];
   const int b = blockIdx.y;
+  if (pp) U += (size_t)b * P * 6;  // one frame set per pair
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n4 = (blockIdx.x * 32 + lane) * 4;
   const bool ok = n4 < N;  // N % 4 == 0: a lane's four points are all inside or all outside
@@ -669,7 +673,8 @@ __device__ __forceinline__ bool bucket_sort_row(const RecBuf<true>& a, const Rec
 template <int KEYS, bool BUCKETS>
 __global__ void __launch_bounds__(SORT_THREADS) segmented_sort_trim_kernel(const float* __restrict__ keys, const float* __restrict__ x,
                                                                            const float* __restrict__ fr, int P, int len,
-                                                                           float* __restrict__ sorted, int32_t* __restrict__ perm32) {
+                                                                           float* __restrict__ sorted, int32_t* __restrict__ perm32,
+                                                                           int pp) {
   extern __shared__ uint2 sbuf[];
   __shared__ uint32_t hist32[SORT_WARPS * (1 << SORT_TRIM_MAXW) / 2];
   __shared__ uint32_t wt[SORT_WARPS];
@@ -680,9 +685,9 @@ __global__ void __launch_bounds__(SORT_THREADS) segmented_sort_trim_kernel(const
   RecBuf<true> a = make_recbuf<true>(sbuf), b = make_recbuf<true>(sbuf + len);
   constexpr bool COUNTED = BUCKETS && KEYS == 1;  // circle coordinates: the bucket histogram is filled as the keys are made
   if (KEYS != 0) {
-    const int p = (int)(seg % P);
+    const size_t p = pp ? seg : seg % P;  // pp: one frame set per pair, fr is (B,P,...)
     const int nf = KEYS == 1 ? 6 : 3;
-    if (threadIdx.x < nf) s_fr[threadIdx.x] = __ldg(fr + (size_t)p * nf + threadIdx.x);
+    if (threadIdx.x < nf) s_fr[threadIdx.x] = __ldg(fr + p * nf + threadIdx.x);
     if (COUNTED)
       for (int i = threadIdx.x; i < SORT_NB / 2; i += SORT_THREADS) hist32[i] = 0;
     __syncthreads();
@@ -1323,25 +1328,31 @@ extern "C" int shwd_project_bwd_set_wide(int on) {
   return SHWD_OK;
 }
 static void launch_project_circle_bwd(const float* x, const float* U, int B, int N, int P, const float* gkeys, const float* gw,
-                                      float* gx, cudaStream_t s) {
+                                      float* gx, cudaStream_t s, int pp = 0) {
   // four points per lane when the rows allow vector loads and the grid still fills the SMs
   const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gkeys)) & 15) == 0;
   if (g_project_bwd_wide && (N % 4) == 0 && al && (long long)B * ((N + 127) / 128) >= 148) {
     dim3 grid((N + 127) / 128, B);
-    project_circle_bwd4_kernel<<<grid, PJ_THREADS, 0, s>>>(x, U, N, P, gkeys, gw, gx);
+    project_circle_bwd4_kernel<<<grid, PJ_THREADS, 0, s>>>(x, U, N, P, gkeys, gw, gx, pp);
   } else {
     dim3 grid((N + 31) / 32, B);
-    project_circle_bwd_kernel<<<grid, PJ_THREADS, 0, s>>>(x, U, N, P, gkeys, gw, gx);
+    project_circle_bwd_kernel<<<grid, PJ_THREADS, 0, s>>>(x, U, N, P, gkeys, gw, gx, pp);
   }
 }
 
-extern "C" int shwd_project_circle(const float* x, const float* U, int B, int N, int P, float* keys, void* stream) {
+static int project_circle_any(const float* x, const float* U, int B, int N, int P, float* keys, void* stream, int pp) {
   if (!x || !U || !keys || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B > 65535 || (P + 31) / 32 > 65535) return SHWD_ERR_UNSUPPORTED;
   dim3 grid((N + PJ_THREADS - 1) / PJ_THREADS, (P + 31) / 32, B);
-  project_circle_kernel<<<grid, PJ_THREADS, 32 * 6 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(x, U, N, P, keys);
+  project_circle_kernel<<<grid, PJ_THREADS, 32 * 6 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(x, U, N, P, keys, pp);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
+}
+extern "C" int shwd_project_circle(const float* x, const float* U, int B, int N, int P, float* keys, void* stream) {
+  return project_circle_any(x, U, B, N, P, keys, stream, 0);
+}
+extern "C" int shwd_project_circle_pp(const float* x, const float* U, int B, int N, int P, float* keys, void* stream) {
+  return project_circle_any(x, U, B, N, P, keys, stream, 1);
 }
 
 extern "C" int shwd_project_circle_bwd(const float* x, const float* U, int B, int N, int P, const float* gkeys, float* gx,
@@ -1378,6 +1389,14 @@ extern "C" int shwd_project_circle_bwd_scaled(const float* x, const float* U, in
   if (!x || !U || !gkeys || !gw || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
   if (B > 65535) return SHWD_ERR_UNSUPPORTED;
   launch_project_circle_bwd(x, U, B, N, P, gkeys, gw, gx, static_cast<cudaStream_t>(stream));
+  SHWD_CUDA_CHECK(cudaGetLastError());
+  return SHWD_OK;
+}
+extern "C" int shwd_project_circle_bwd_scaled_pp(const float* x, const float* U, int B, int N, int P, const float* gkeys,
+                                                 const float* gw, float* gx, void* stream) {
+  if (!x || !U || !gkeys || !gw || !gx || B <= 0 || N <= 0 || P <= 0) return SHWD_ERR_INVALID_ARGUMENT;
+  if (B > 65535) return SHWD_ERR_UNSUPPORTED;
+  launch_project_circle_bwd(x, U, B, N, P, gkeys, gw, gx, static_cast<cudaStream_t>(stream), 1);
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
 }
@@ -1442,18 +1461,18 @@ extern "C" int shwd_sort_set_method(int method) {
 // the trimmed-digit kernel (int32 permutation, values rebuilt from the keys): rows the uint2 layout is best for
 template <int KEYS>
 static int launch_sort_trim(const float* keys, const float* x, const float* fr, int P, int segs, int len, float* sorted, int32_t* perm32,
-                            cudaStream_t s) {
+                            cudaStream_t s, int pp = 0) {
   const size_t smem = 2 * (size_t)len * sizeof(uint2);
   if (g_sort_method == 1) {
     if (smem > 32 * 1024)
       SHWD_CUDA_CHECK(
           cudaFuncSetAttribute(segmented_sort_trim_kernel<KEYS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    segmented_sort_trim_kernel<KEYS, false><<<segs, SORT_THREADS, smem, s>>>(keys, x, fr, P, len, sorted, perm32);
+    segmented_sort_trim_kernel<KEYS, false><<<segs, SORT_THREADS, smem, s>>>(keys, x, fr, P, len, sorted, perm32, pp);
   } else {
     if (smem > 32 * 1024)
       SHWD_CUDA_CHECK(
           cudaFuncSetAttribute(segmented_sort_trim_kernel<KEYS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    segmented_sort_trim_kernel<KEYS, true><<<segs, SORT_THREADS, smem, s>>>(keys, x, fr, P, len, sorted, perm32);
+    segmented_sort_trim_kernel<KEYS, true><<<segs, SORT_THREADS, smem, s>>>(keys, x, fr, P, len, sorted, perm32, pp);
   }
   SHWD_CUDA_CHECK(cudaGetLastError());
   return SHWD_OK;
@@ -1469,14 +1488,22 @@ extern "C" int shwd_sort_projected_max_points(void) {
   return forced == 1 ? 0 : SORT_WIDE_BEST_MAX;
 }
 
-extern "C" int shwd_sort_projected(const float* x, const float* frames, int B, int N, int P, int mode, float* sorted, int32_t* perm,
-                                   void* stream) {
+static int sort_projected_any(const float* x, const float* frames, int B, int N, int P, int mode, float* sorted, int32_t* perm,
+                              void* stream, int pp) {
   if (!x || !frames || B < 0 || N <= 0 || P <= 0 || (mode != 1 && mode != 2) || (!sorted && !perm)) return SHWD_ERR_INVALID_ARGUMENT;
   if (N > shwd_sort_projected_max_points()) return SHWD_ERR_UNSUPPORTED;
   if (B == 0) return SHWD_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return mode == 1 ? launch_sort_trim<1>(nullptr, x, frames, P, B * P, N, sorted, perm, s)
-                   : launch_sort_trim<2>(nullptr, x, frames, P, B * P, N, sorted, perm, s);
+  return mode == 1 ? launch_sort_trim<1>(nullptr, x, frames, P, B * P, N, sorted, perm, s, pp)
+                   : launch_sort_trim<2>(nullptr, x, frames, P, B * P, N, sorted, perm, s, pp);
+}
+extern "C" int shwd_sort_projected(const float* x, const float* frames, int B, int N, int P, int mode, float* sorted, int32_t* perm,
+                                   void* stream) {
+  return sort_projected_any(x, frames, B, N, P, mode, sorted, perm, stream, 0);
+}
+extern "C" int shwd_sort_projected_pp(const float* x, const float* frames, int B, int N, int P, int mode, float* sorted, int32_t* perm,
+                                      void* stream) {
+  return sort_projected_any(x, frames, B, N, P, mode, sorted, perm, stream, 1);
 }
 
 static int launch_segmented_sort(const float* keys, int segs, int len, float* sorted, int64_t* perm, int32_t* perm32,

@@ -140,8 +140,9 @@ class max_spherical_wassersten_distance(nn.Module):
     (``max_iter`` optimiser steps), then the outer sum over the batch; returns ``(ssw, phi(first), phi(second))``.
 
     ``SSW`` is called the reference's way, once per pair: ``SSW(first_t[i], second_t[i], num_projections, device, p=p)``
-    (pass ``losses.sliced_wasserstein_sphere``); every such call is one fused project + sort + reduce launch sequence
-    (``ops.SlicedLossFn``).  ``shared_frames=True`` (an extension, off by default) draws ONE set of frames per evaluation and
+    (any callable); every such call is one fused project + sort + reduce launch sequence (``ops.SlicedLossFn``).  When
+    ``SSW`` is this package's ``sliced_wasserstein_sphere`` the B independent frame draws are made as one (B,P,d,2) tensor
+    and the batch goes through ONE fused call with per-pair frames (same distribution).  ``shared_frames=True`` (an extension, off by default) draws ONE set of frames per evaluation and
     sends the whole batch through a single fused call instead of B calls -- same expectation per pair, but the pairs then
     share their slices, which the reference's per-pair draws (:307-308) do not."""
 
@@ -161,6 +162,11 @@ class max_spherical_wassersten_distance(nn.Module):
         if self.shared_frames:
             Z = torch.randn((self.num_projections, a.shape[-1], 2), device=a.device)
             return sliced_cost(a, b, stiefel_frames(Z), p=self.p).sum()
+        if self.SSW is sliced_wasserstein_sphere and a.dim() == 3 and a.shape[1] + b.shape[1] <= ops.CIRCULAR_W1_MAX:
+            # the reference's B calls draw B independent frame sets; drawing them as one (B,P,d,2) tensor is the same
+            # distribution, and the kernels take one frame set per pair -- one fused call instead of B
+            Z = torch.randn((a.shape[0], self.num_projections, a.shape[-1], 2), device=a.device)
+            return sliced_cost_fast(a, b, stiefel_frames(Z), p=self.p).reshape(())
         ssw = 0
         for i in range(len(a)):
             ssw = ssw + self.SSW(a[i], b[i], self.num_projections, self.device, p=self.p)
@@ -185,10 +191,14 @@ class max_spherical_wassersten_distance(nn.Module):
 def sliced_cost_fast(Xs, Xt, Us, p=2, u_weights=None, v_weights=None):
     """max_spherical_sliced_w_fast.py:258-295 (there named ``sliced_cost``) -- batched clouds (B,n,3), (B,m,3) with PER-PAIR
     frames ``Us`` (B,P,3,2); returns the SUM over the pairs of the per-pair mean over slices, shape (1,), as the reference's
-    loop ``w1 += mean(binary_search_circle(Xps[i], Xpt[i]))`` does.  Each pair is one fused sliced call.  (The reference's
+    loop ``w1 += mean(binary_search_circle(Xps[i], Xpt[i]))`` does.  One fused sliced call for the whole batch (per pair when weights are given).  (The reference's
     p == 1 branch fails on batched keys -- its ``gather`` index is flattened, :250 -- the same sum is returned here.)"""
     if Us.dim() != 4 or Us.shape[0] != Xs.shape[0]:
         raise ValueError("Us must be (batch, num_projections, d, 2) with one frame set per pair")
+    if u_weights is None and v_weights is None and Xs.shape[1] + Xt.shape[1] <= ops.CIRCULAR_W1_MAX:
+        # the whole batch in ONE fused call: the kernels index the frames by pair (shwd_*_pp, include/shwd.h)
+        w = ops.spherical_sliced_w1(Xs, Xt, Us) if p == 1 else ops.spherical_sliced_wp(Xs, Xt, Us, float(p))
+        return w.sum().reshape(1)
     w1 = torch.zeros((1,), device=Xs.device)
     for i in range(Xs.shape[0]):
         w1 = w1 + sliced_cost(Xs[i], Xt[i], Us[i], p=p, u_weights=u_weights, v_weights=v_weights)

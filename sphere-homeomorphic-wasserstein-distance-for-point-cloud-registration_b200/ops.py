@@ -801,7 +801,13 @@ class SlicedLossFn(torch.autograd.Function):
         frames = frames.contiguous()
         B, n, _ = x.shape
         m = y.shape[1]
-        P = frames.shape[0]
+        # frames (P,3,2) / (P,3): one set for every pair; (B,P,3,2): one set PER PAIR (max_spherical_sliced_w_fast.py:298-319)
+        pp = frames.dim() == 4
+        if pp and (mode == "line" or frames.shape[0] != B):
+            raise ValueError("per-pair frames must be (B,P,3,2) and are for the circle modes")
+        P = frames.shape[1] if pp else frames.shape[0]
+        sort_projected = lib.shwd_sort_projected_pp if pp else lib.shwd_sort_projected
+        project_circle = lib.shwd_project_circle_pp if pp else lib.shwd_project_circle
         S = B * P
         dev = x.device
         ku = torch.empty(S, n, device=dev, dtype=torch.float32)
@@ -815,14 +821,14 @@ class SlicedLossFn(torch.autograd.Function):
                 if cnt <= fused_max:  # the sort CTAs compute their own keys: no key array, no projection launch
                     so = torch.empty(S, cnt, device=dev, dtype=torch.float32)
                     pe = torch.empty(S, cnt, device=dev, dtype=torch.int32)
-                    _lib.check(lib.shwd_sort_projected(_ptr(c), _ptr(frames), B, cnt, P, 2 if mode == "line" else 1, _ptr(so), _ptr(pe), st),
+                    _lib.check(sort_projected(_ptr(c), _ptr(frames), B, cnt, P, 2 if mode == "line" else 1, _ptr(so), _ptr(pe), st),
                                "shwd_sort_projected")
                     sorted_perm.append((so, pe))
                 else:
                     if mode == "line":
                         _lib.check(lib.shwd_project_line(_ptr(c), _ptr(frames), B, cnt, P, _ptr(kbuf), st), "shwd_project_line")
                     else:
-                        _lib.check(lib.shwd_project_circle(_ptr(c), _ptr(frames), B, cnt, P, _ptr(kbuf), st), "shwd_project_circle")
+                        _lib.check(project_circle(_ptr(c), _ptr(frames), B, cnt, P, _ptr(kbuf), st), "shwd_project_circle")
                     sorted_perm.append(_sort_i32(kbuf))
             (su, pu), (sv, pv) = sorted_perm
             gku, gkv = ku, kv  # (dead once sorted / never filled): these buffers receive d w / d keys
@@ -841,7 +847,7 @@ class SlicedLossFn(torch.autograd.Function):
             else:
                 raise ValueError("unknown sliced mode %r" % (mode,))
         ctx.save_for_backward(x, y, frames, gku, gkv)
-        ctx.mode = mode
+        ctx.mode, ctx.pp = mode, pp
         return w.view(B, P).mean(dim=1)
 
     @staticmethod
@@ -850,7 +856,8 @@ class SlicedLossFn(torch.autograd.Function):
         lib = _lib.lib()
         B, n, _ = x.shape
         m = y.shape[1]
-        P = frames.shape[0]
+        P = frames.shape[1] if ctx.pp else frames.shape[0]
+        circle_bwd = lib.shwd_project_circle_bwd_scaled_pp if ctx.pp else lib.shwd_project_circle_bwd_scaled
         gwc = gw.reshape(B).contiguous().float()  # the kernels scale by gw[b] / P themselves
         gx = gy = None
         with torch.cuda.device(x.device):
@@ -863,7 +870,7 @@ class SlicedLossFn(torch.autograd.Function):
                     _lib.check(lib.shwd_project_line_bwd_scaled(_ptr(frames), B, cnt, P, _ptr(gk), _ptr(gwc), _ptr(g), st),
                                "shwd_project_line_bwd_scaled")
                 else:
-                    _lib.check(lib.shwd_project_circle_bwd_scaled(_ptr(c), _ptr(frames), B, cnt, P, _ptr(gk), _ptr(gwc), _ptr(g), st),
+                    _lib.check(circle_bwd(_ptr(c), _ptr(frames), B, cnt, P, _ptr(gk), _ptr(gwc), _ptr(g), st),
                                "shwd_project_circle_bwd_scaled")
                 if idx == 0:
                     gx = g
@@ -902,12 +909,15 @@ def circular_w1_large(us, vs, uw=None, vw=None):
 
 
 def spherical_sliced_w1(Xs, Xt, U):
-    """mean_P circular-W1 of the great-circle projections (sliced_cost with p == 1, explicit frames U (P,3,2))."""
+    """mean_P circular-W1 of the great-circle projections (sliced_cost with p == 1, explicit frames U (P,3,2), or one set per
+    pair (B,P,3,2))."""
     xs, _ = _as_cloud(Xs, "Xs")
     xt, _ = _as_cloud(Xt, "Xt")
     U = U.to(device=xs.device, dtype=torch.float32)
     if xs.shape[1] + xt.shape[1] <= CIRCULAR_W1_MAX:
         return SlicedLossFn.apply(xs, xt, U, "circle_w1", 1.0, 0.0, 0.0, 0.0)  # (B,)
+    if U.dim() == 4:
+        raise ValueError("per-pair frames (B,P,3,2) are supported up to n + m = %d points per pair" % CIRCULAR_W1_MAX)
     ks = ProjectCircleFn.apply(xs, U)  # (B,P,n)
     kt = ProjectCircleFn.apply(xt, U)
     B, P, n = ks.shape

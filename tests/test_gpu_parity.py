@@ -1440,6 +1440,33 @@ def test_batched_fast_variant_matches_reference_fixture(shwd, capsys):
         sys.path.pop(0)
 
 
+@pytest.mark.parametrize("B,n,m,P", [(3, 40, 33, 16), (8, 4096, 4096, 24), (5, 1000, 1024, 40), (2, 5000, 4500, 8)])
+@pytest.mark.parametrize("p", [1, 2])
+def test_per_pair_frames_fused_call_equals_the_per_pair_calls(shwd, B, n, m, P, p, capsys):
+    """Frames (B,P,3,2), one set per pair (max_spherical_sliced_w_fast.py:298-319): ONE fused call through the shwd_*_pp entry
+    points against B single-pair calls with the pair's own frames (the fixture-pinned path): values and both gradients, on the
+    fused-key sort, the wide projection backward and the project-then-sort path of long rows."""
+    g = torch.Generator().manual_seed(B * n + p)
+    x = F.normalize(torch.randn(B, n, 3, generator=g), dim=-1).to(dev())
+    y = F.normalize(torch.randn(B, m, 3, generator=g), dim=-1).to(dev())
+    Us = shwd.losses.sliced.stiefel_frames(torch.randn(B, P, 3, 2, generator=g)).to(dev())
+    wgt = torch.rand(B, generator=g).to(dev()) + 0.5
+    xa, ya = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    wa = shwd.ops.spherical_sliced_w1(xa, ya, Us) if p == 1 else shwd.ops.spherical_sliced_wp(xa, ya, Us, float(p))
+    ga = torch.autograd.grad((wa * wgt).sum(), (xa, ya))
+    xb, yb = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    wb = torch.stack([shwd.losses.sliced_cost(xb[i], yb[i], Us[i], p=p) for i in range(B)])
+    gb = torch.autograd.grad((wb * wgt).sum(), (xb, yb))
+    e = (rel(wa, wb), rel(ga[0], gb[0]), rel(ga[1], gb[1]))
+    with capsys.disabled():
+        print("per-pair frames B=%d n=%d m=%d P=%d p=%d: w %.1e gx %.1e gy %.1e%s" % (
+            B, n, m, P, p, e[0], e[1], e[2], "  (bit-identical)" if torch.equal(wa, wb) and torch.equal(ga[0], gb[0]) else ""))
+    assert torch.equal(wa, wb) and torch.equal(ga[0], gb[0]) and torch.equal(ga[1], gb[1])  # same kernels, same bits
+    assert shwd.losses.sliced_cost_fast(x, y, Us, p=p).item() == pytest.approx(wb.sum().item(), rel=1e-6)
+    with pytest.raises(ValueError):
+        shwd.ops.spherical_sliced_wp(x, y, Us[:-1], 2.0) if B > 1 else shwd.ops.spherical_sliced_wp(x, y, Us.repeat(2, 1, 1, 1), 2.0)
+
+
 def test_max_wrapper_with_fused_phi_runs_the_reference_step(shwd):
     """One training step of max_cos_disimilarity_wassersten_distance (s2_wasserstein.py:234-262) with the fused phi:
     the inner ascent changes phi's parameters, the outer loss back-propagates to the cloud."""
