@@ -11,3 +11,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 B3="python bench.py --config cfg3 --steps 2 --warmup 3 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${TAG:-r02i}_launches_bench_cfg3.csv $B3 > $O/ncu_l3.log 2>&1; echo launches3 rc=$?
 python tools/time_ot_kernels.py > $O/${TAG:-r02i}_ot_kernels.md 2>&1; tail -12 $O/${TAG:-r02i}_ot_kernels.md
+python tools/time_planar.py > $O/${TAG:-r02i}_planar.md 2>&1; tail -4 $O/${TAG:-r02i}_planar.md
+python tools/time_max_ssw.py > $O/${TAG:-r02i}_max_ssw.md 2>&1; cat $O/${TAG:-r02i}_max_ssw.md
