@@ -272,3 +272,27 @@ def test_oracle_weighted_binary_search_circle_matches_reference():
     gx, gy = torch.autograd.grad(loss, (Xs, Xt))
     assert abs(loss.item() - float(d["sc_loss"])) / float(d["sc_loss"]) < 2e-6
     assert rel(gx.numpy(), d["sc_gx"]) < 2e-5 and rel(gy.numpy(), d["sc_gy"]) < 2e-5
+
+
+@pytest.mark.parametrize("p", [2, 1])
+def test_oracle_sliced_path_reproduces_the_max_ssw_wrapper_fixture(p):
+    """The outer value of the frozen max_spherical_wassersten_distance call (max_spherical_sliced_w.py:528-533) is a sum of
+    per-pair sliced costs of the transformed clouds (40 against 33 points) with the fixture's frame cycle: calls 0-5 are the two
+    ascent steps over three pairs, calls 6-8 the outer evaluation.  The oracle's sliced path must reproduce it."""
+    d = load("max_ssw_wrapper")
+    ft, st, Us = (torch.from_numpy(d[k % p]) for k in ("first_t_p%d", "second_t_p%d", "Us_p%d"))
+    total = sum(oracle.sliced_wasserstein_sphere(ft[i], st[i], Us[(6 + i) % len(Us)], p=p) for i in range(len(ft)))
+    assert float(total.detach()) == pytest.approx(float(d["ssw_p%d" % p]), rel=2e-6)
+
+
+def test_oracle_sliced_path_reproduces_the_batched_fast_fixture():
+    """max_spherical_sliced_w_fast.py:258-295: per-pair frames, value = sum over the pairs, p = 2 and 3, with gradients."""
+    d = load("ssw_fast")
+    for p in (2, 3):
+        x = torch.from_numpy(d["x_p%d" % p]).requires_grad_(True)
+        y = torch.from_numpy(d["y_p%d" % p]).requires_grad_(True)
+        Us = torch.from_numpy(d["Us_p%d" % p])
+        total = sum(oracle.sliced_wasserstein_sphere(x[i], y[i], Us[i], p=p) for i in range(len(x)))
+        gx, gy = torch.autograd.grad(total, (x, y))
+        assert total.item() == pytest.approx(float(d["w_p%d" % p][0]), rel=2e-6)
+        assert rel(gx.numpy(), d["gx_p%d" % p]) < 1e-5 and rel(gy.numpy(), d["gy_p%d" % p]) < 1e-5
