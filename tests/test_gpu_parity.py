@@ -414,6 +414,31 @@ def test_max_wrapper_trains_phi_and_returns_reference_tuple(shwd):
     assert torch.isfinite(v)
 
 
+@pytest.mark.parametrize("mode", ["max", "mean", "softmax"])
+@pytest.mark.parametrize("solver", ["exact", "sinkhorn"])
+def test_pseudo_max_wrapper_one_launch_equals_one_call_per_flow(shwd, mode, solver, capsys):
+    """pseudo_max_cos_disimilarity_wassersten_distance (s2_wasserstein.py:272-344): all phi_num x B pairs through ONE solver
+    launch (the default here) against the reference's order -- one criterion call per flow, `if cswd > max_cswd` on the host."""
+    L = shwd.losses
+    torch.manual_seed(5)
+    csw = L.Cos_disimilarity_W(dev(), p=2) if solver == "exact" else L.Geodesic_distance_W(dev(), p=2, eps=0.05, max_iter=30)
+    pm = L.pseudo_max_cos_disimilarity_wassersten_distance(csw, dev(), phi_num=5, n_flow_layer=2, flow_name="Residual",
+                                                           mean_or_max_or_softmax=mode)
+    a = F.normalize(torch.randn(6, 128, 3), dim=-1).to(dev())
+    b = (F.normalize(torch.randn(6, 128, 3), dim=-1) * 1.05).to(dev())
+    v1, fa, fb = pm(a, b)
+    pm.batched = False
+    per_flow = [csw(phi(a), phi(b)) for phi in pm.phi_list]  # the reference's loop, spelled out
+    want = {"max": max(per_flow), "mean": sum(per_flow) / 5,
+            "softmax": (F.softmax(torch.stack(per_flow), 0) * torch.stack(per_flow)).sum()}[mode]
+    v0, ga, gb = pm(a, b)
+    e = (abs(v1.item() - want.item()) / want.item(), abs(v0.item() - want.item()) / want.item())
+    with capsys.disabled():
+        print("pseudo-max %s / %s: one launch %.1e, per-flow calls %.1e from the spelled-out loop" % ((mode, solver) + e))
+    assert e[0] < 1e-6 and e[1] < 1e-6 and torch.equal(fa, ga) and torch.equal(fb, gb)
+    assert torch.equal(fa, pm.phi_list[-1](a))  # the LAST flow's clouds are what the reference returns
+
+
 # ------------------------------------------------------------------------------------------------------- Chamfer ----
 @pytest.mark.parametrize("B,N,M", [(2, 40, 33), (3, 1024, 1024), (1, 2500, 300)])
 @pytest.mark.parametrize("br,pr", [("mean", "mean"), ("sum", "mean"), (None, "sum")])

@@ -13,3 +13,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-fil
 python tools/time_ot_kernels.py > $O/${TAG:-r02i}_ot_kernels.md 2>&1; tail -12 $O/${TAG:-r02i}_ot_kernels.md
 python tools/time_planar.py > $O/${TAG:-r02i}_planar.md 2>&1; tail -4 $O/${TAG:-r02i}_planar.md
 python tools/time_max_ssw.py > $O/${TAG:-r02i}_max_ssw.md 2>&1; cat $O/${TAG:-r02i}_max_ssw.md
+python tools/time_pseudo_max.py > $O/${TAG:-r02i}_pseudo_max.md 2>&1; cat $O/${TAG:-r02i}_pseudo_max.md
