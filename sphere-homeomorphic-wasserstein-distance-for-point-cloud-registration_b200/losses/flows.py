@@ -122,16 +122,35 @@ class ResidualFlow(nn.Module):
     """x + LipschitzMLP(x) (flows/residual.py:12-68 with reverse=False); module tree as in the reference:
     ``iresblock.nnet.net.{2i}`` = Swish, ``.{2i+1}`` = the spectrally normalised linear layer."""
 
-    def __init__(self, dim=3, hidden_units=8, hidden_layers=7, lipschitz_const=0.95):
+    def __init__(self, dim=3, hidden_units=8, hidden_layers=7, lipschitz_const=0.95, reverse=False):
         super().__init__()
         channels = [dim] + [hidden_units] * (hidden_layers - 1) + [dim]
         self.iresblock = _IResBlock(LipschitzMLP(channels, lipschitz_const))
+        # reverse=True is normflows' constructor default (flows/residual.py:21,63-65): ``forward`` then applies the INVERSE of
+        # x + g(x); s2_wasserstein.py:152 passes reverse=False, mini_batch_Residual_MSSW.py:381 keeps the default
+        self.reverse = reverse
 
     @property
     def net(self):
         return self.iresblock.nnet.net
 
+    def _inverse_fixed_point(self, y, atol=1e-5, rtol=1e-5):
+        """x with x + g(x) = y by the iteration x <- y - g(x) until every entry moved by less than the tolerance (at most 1000
+        rounds), differentiated through its iterations like the reference's (flows/residual.py:133-142)."""
+        g = self.iresblock.nnet
+        x, x_prev = y - g(y), y
+        i = 0
+        tol = atol + y.abs() * rtol
+        while not torch.all((x - x_prev) ** 2 / tol < 1):
+            x, x_prev = y - g(x), x
+            i += 1
+            if i > 1000:
+                break
+        return x
+
     def forward(self, x):
+        if self.reverse:
+            return self._inverse_fixed_point(x)
         return self.iresblock(x)
 
 
@@ -158,7 +177,7 @@ def _uv_buffer(flows):
 def is_standard_residual_stack(flows):
     """True when every flow is a ResidualFlow with channels [3, 8 x6, 3] -- the shape the fused kernel implements."""
     for f in flows:
-        if not isinstance(f, ResidualFlow):
+        if not isinstance(f, ResidualFlow) or f.reverse:
             return False
         lins = list(f.net)[1::2]
         shapes = [tuple(l.weight.shape) for l in lins]

@@ -198,6 +198,7 @@ def main():
     make_weighted_wp_fixture()
     make_max_ssw_fixture()
     make_ssw_fast_fixture()
+    make_mini_batch_mssw_fixture()
 
 
 def _flat_state(prefix, sd):
@@ -435,8 +436,64 @@ def make_ssw_fast_fixture():
     np.savez(os.path.join(HERE, "ssw_fast.npz"), **out)
 
 
+def make_mini_batch_mssw_fixture():
+    """mini_batch_Residual_MSSW.py from the UNMODIFIED reference: (A) its sphere map transform_to_sphere (:327-408: MLP -> flows on
+    R^2 -> angles -> S^2) for both flow kinds -- the first forward runs ActNorm's data-dependent initialisation, the second one is
+    differentiated; (B) one training call of max_spherical_wassersten_distance_Residual (:413-452) with a Planar map, the
+    mini-batches drawn by np.random.choice after np.random.seed(12), the frames of every SSW call fixed."""
+    mb = _load(os.path.join(REF, "Point_Cloud_Resistration/losses/mini_batch_Residual_MSSW.py"), "ref_mini_batch_mssw")
+    out = {}
+    for fl in ("Planar", "Residual"):
+        torch.manual_seed(700 if fl == "Planar" else 701)
+        np.random.seed(7)
+        phi = mb.transform_to_sphere(fl, n_flow_layer=2)
+        with torch.no_grad():
+            for prm in phi.parameters():
+                if prm.dim() > 0 and prm.dtype == torch.float32:
+                    prm.add_(0.2 * torch.randn_like(prm))
+        phi.train()
+        sd0 = {k: v.clone() for k, v in phi.state_dict().items()}
+        g = torch.Generator().manual_seed(70)
+        x1 = torch.randn(4, 30, 3, generator=g)
+        y1 = phi(x1)
+        x2 = torch.randn(4, 30, 3, generator=g).requires_grad_(True)
+        w = torch.randn(4, 30, 3, generator=g)
+        y2 = phi(x2)
+        named = [(n, q) for n, q in phi.named_parameters() if q.dtype == torch.float32 and q.dim() > 0]
+        gs = torch.autograd.grad((y2 * w).sum(), [x2] + [q for _, q in named], allow_unused=True)
+        out.update({f"{fl}_x1": x1.numpy(), f"{fl}_y1": y1.detach().numpy(), f"{fl}_x2": x2.detach().numpy(), f"{fl}_w": w.numpy(),
+                    f"{fl}_y2": y2.detach().numpy(), f"{fl}_gx": gs[0].numpy()})
+        for (n, q), gq in zip(named, gs[1:]):
+            out[f"{fl}_gp__" + n.replace(".", "__")] = (torch.zeros_like(q) if gq is None else gq).numpy()
+        out.update(_flat_state(f"{fl}_sd0__", sd0))
+        print("mini-batch MSSW sphere map", fl, "|y2|", float(y2.norm()), "|gx|", float(gs[0].norm()))
+    torch.manual_seed(702)
+    phi = mb.transform_to_sphere("Planar", n_flow_layer=2)
+    phi_op = torch.optim.SGD(phi.parameters(), lr=0.05)
+    g = torch.Generator().manual_seed(71)
+    Us = torch.linalg.qr(torch.randn(5, 24, 3, 2, generator=g)).Q
+    first = torch.randn(4, 40, 3, generator=g)
+    second = (first[:, :33] * 0.8 + 0.1 * torch.randn(4, 33, 3, generator=g)).requires_grad_(True)
+    crit = mb.max_spherical_wassersten_distance_Residual(24, phi, phi_op, SSW=FixedFramesSSW(mb.sliced_cost, Us), p=2, max_iter=2,
+                                                         psi_minibatch_size=2, device="cpu")
+    sd0 = {k: v.clone() for k, v in phi.state_dict().items()}
+    np.random.seed(12)
+    val, ft, st = crit(first, second, "train")
+    (g_second,) = torch.autograd.grad(val, second)
+    out.update(Us=Us.numpy(), first=first.numpy(), second=second.detach().numpy(), ssw=np.float64(val.item()), first_t=ft.detach().numpy(),
+               second_t=st.detach().numpy(), g_second=g_second.numpy())
+    out.update(_flat_state("w_sd0__", sd0))
+    out.update(_flat_state("w_sd1__", phi.state_dict()))
+    print("mini-batch MSSW wrapper", val.item())
+    np.savez(os.path.join(HERE, "mini_batch_mssw.npz"), **out)
+
+
 if __name__ == "__main__":
-    if "--max-ssw-only" in sys.argv:  # the fixtures added in the last session of round 2
+    if "--mini-batch-only" in sys.argv:
+        _install_shims()
+        torch.set_num_threads(8)
+        make_mini_batch_mssw_fixture()
+    elif "--max-ssw-only" in sys.argv:  # the fixtures added in the last session of round 2
         _install_shims()
         torch.set_num_threads(8)
         make_max_ssw_fixture()

@@ -1492,6 +1492,44 @@ def test_per_pair_frames_fused_call_equals_the_per_pair_calls(shwd, B, n, m, P, 
         shwd.ops.spherical_sliced_wp(x, y, Us[:-1], 2.0) if B > 1 else shwd.ops.spherical_sliced_wp(x, y, Us.repeat(2, 1, 1, 1), 2.0)
 
 
+def test_mini_batch_mssw_wrapper_matches_reference_fixture(shwd, capsys):
+    """One training call of max_spherical_wassersten_distance_Residual (mini_batch_Residual_MSSW.py:413-452) with its own sphere
+    map (Planar flows on R^2), the mini-batches drawn by np.random.choice after np.random.seed(12) as in the frozen run of the
+    unmodified reference, the frames of every SSW call fixed; then the one-fused-call route with the package's own SSW."""
+    from shwd_b200.losses import mini_batch_mssw as M
+    d = gold("mini_batch_mssw")
+    phi = M.transform_to_sphere("Planar", n_flow_layer=2)
+    phi.load_state_dict(_state(d, "w_sd0__"))
+    phi = phi.to(dev())
+    op = torch.optim.SGD(phi.parameters(), lr=0.05)
+    crit = M.max_spherical_wassersten_distance_Residual(24, phi, op, SSW=_FixedFramesSSW(shwd.losses.sliced_cost, torch.from_numpy(d["Us"]).to(dev())),
+                                                        p=2, max_iter=2, psi_minibatch_size=2, device=dev(), verbose=False)
+    first = torch.from_numpy(d["first"]).to(dev())
+    second = torch.from_numpy(d["second"]).to(dev()).requires_grad_(True)
+    np.random.seed(12)
+    val, ft, st = crit(first, second, "train")
+    (g2,) = torch.autograd.grad(val, second)
+    want = float(d["ssw"])
+    e = (abs(val.item() - want) / want, rel(ft, torch.from_numpy(d["first_t"])), rel(st, torch.from_numpy(d["second_t"])),
+         rel(g2, torch.from_numpy(d["g_second"])))
+    with capsys.disabled():
+        print("mini-batch max-SSW wrapper: ssw %.2e first_t %.2e second_t %.2e d/dsecond %.2e" % e)
+    # measured: value 1.6e-5, clouds 6.8e-6 / 6.3e-6, gradient 9.7e-4 -- the value is 2.4e-5 = a mean of squared differences of
+    # ~5e-3 between nearly coinciding clouds, so its gradient is a sum of cancelling float32 terms in the reference as well
+    assert e[0] < 1e-4 and e[1] < TOL and e[2] < TOL and e[3] < 4e-3
+    # phi after the two ascent steps: the steps themselves are small here (lr x a gradient of nearly coinciding clouds), so the
+    # comparison is on the UPDATE, relative to the largest one
+    sd0, sd1 = _state(d, "w_sd0__"), _state(d, "w_sd1__")
+    upd = max((sd1[k] - sd0[k]).abs().max().item() for k in sd1)
+    worst = max((phi.state_dict()[k].cpu() - sd1[k]).abs().max().item() for k in sd1)
+    with capsys.disabled():
+        print("   phi after the ascent: largest update %.2e, largest deviation from the reference's %.2e" % (upd, worst))
+    assert worst < 0.05 * upd + 2e-6
+    fused = M.max_spherical_wassersten_distance_Residual(64, phi, op, p=2, max_iter=1, psi_minibatch_size=3, device=dev(), verbose=False)
+    v2, _, _ = fused(first, second.detach(), "train")
+    assert v2.dim() == 0 and torch.isfinite(v2) and v2.item() > 0
+
+
 def test_max_wrapper_with_fused_phi_runs_the_reference_step(shwd):
     """One training step of max_cos_disimilarity_wassersten_distance (s2_wasserstein.py:234-262) with the fused phi:
     the inner ascent changes phi's parameters, the outer loss back-propagates to the cloud."""

@@ -348,3 +348,34 @@ def test_transform_to_sphere_is_the_reference_module():
     y = phi(torch.from_numpy(d["first_p2"]))
     assert torch.allclose(y, torch.from_numpy(d["first_t_p2"]), rtol=1e-5, atol=1e-6)
     assert torch.allclose(y.norm(dim=-1), torch.ones(3, 40), atol=1e-6)
+
+
+@pytest.mark.parametrize("fl", ["Planar", "Residual"])
+def test_mini_batch_mssw_sphere_map_matches_the_reference_fixture(fl):
+    """mini_batch_Residual_MSSW.py:327-408 (MLP -> flows on R^2, incl. ActNorm's data-dependent first-batch initialisation ->
+    angles -> S^2): loaded with the reference's own state_dict, the first forward (initialising) and a second, differentiated
+    one against outputs and autograd gradients frozen from the unmodified reference (make_golden.py::make_mini_batch_mssw_fixture)."""
+    import numpy as np
+    from shwd_b200.losses import mini_batch_mssw as M
+    d = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mini_batch_mssw.npz")))
+    pre = fl + "_sd0__"
+    sd = {k[len(pre):].replace("__", "."): torch.from_numpy(v) for k, v in d.items() if k.startswith(pre)}
+    phi = M.transform_to_sphere(fl, n_flow_layer=2)
+    res = phi.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    phi.train()
+    y1 = phi(torch.from_numpy(d[fl + "_x1"]))
+    x2 = torch.from_numpy(d[fl + "_x2"]).requires_grad_(True)
+    y2 = phi(x2)
+    named = [(n, q) for n, q in phi.named_parameters() if q.dtype == torch.float32 and q.dim() > 0]
+    gs = torch.autograd.grad((y2 * torch.from_numpy(d[fl + "_w"])).sum(), [x2] + [q for _, q in named], allow_unused=True)
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-3)).item()
+
+    assert rel(y1.detach(), torch.from_numpy(d[fl + "_y1"])) < 1e-6 and rel(y2.detach(), torch.from_numpy(d[fl + "_y2"])) < 1e-6
+    assert rel(gs[0], torch.from_numpy(d[fl + "_gx"])) < 1e-5
+    for (n, q), g in zip(named, gs[1:]):
+        want = torch.from_numpy(d[fl + "_gp__" + n.replace(".", "__")])
+        got = torch.zeros_like(want) if g is None else g
+        assert got.shape == want.shape and rel(got, want) < 2e-5, n
