@@ -9,6 +9,12 @@ Import shims, created in a temp dir, never inside the ref
   * ``normflows``          -> alias of the vendored ``losses/normflows_ishikawa`` package.
   * ``matplotlib.pyplot``  -> empty stub (imported, never used, by max_spherical_sliced_w.py:4).
 The Sinkhorn files are loaded stand-alone by path.  Outputs: ``*.npz`` with inputs, outputs and autograd gradients.
+
+Subsets (each regenerates its files bit for bit; the full run writes everything):
+    --wrappers-only      flow_{residual,planar}, max_wrapper_{residual,planar}, notebook_sliced_wasserstein, emd1d_circle_weighted
+    --weighted-wp-only   binary_search_circle_weighted
+    --max-ssw-only       max_ssw_wrapper, ssw_fast        (max_spherical_sliced_w.py:498-536, max_spherical_sliced_w_fast.py)
+    --mini-batch-only    mini_batch_mssw                  (mini_batch_Residual_MSSW.py)
 """
 import importlib.util
 import os
