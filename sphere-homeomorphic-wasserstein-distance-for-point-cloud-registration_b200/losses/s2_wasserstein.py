@@ -148,7 +148,7 @@ class Norm_Flow_structure(nn.Module):
             if uv is None or uv.device != x.device:
                 uv = self._uv_cache = _uv_buffer(self.net).to(x.device)
             return fused_residual_stack(self.net, x, uv)  # one kernel per direction (csrc/resflow.cu)
-        if x.is_cuda and x.shape[-1] == 3 and x.dim() in (2, 3) and is_planar_stack(self.net):
+        if x.is_cuda and x.dtype == torch.float32 and x.shape[-1] == 3 and x.dim() in (2, 3) and is_planar_stack(self.net):
             return fused_planar_stack(self.net, x)  # one kernel per direction (csrc/planar.cu)
         for flow in self.net:
             x = flow(x)
@@ -184,7 +184,7 @@ class Norm_Flow_structure_optuna(nn.Module):
         # are gathered per call (2 * sum(dims) floats), so there is no cache to invalidate
         if x.is_cuda and x.shape[-1] == 3 and is_standard_residual_stack(self.net):
             return fused_residual_stack(self.net, x)
-        if x.is_cuda and x.shape[-1] == 3 and x.dim() in (2, 3) and is_planar_stack(self.net):
+        if x.is_cuda and x.dtype == torch.float32 and x.shape[-1] == 3 and x.dim() in (2, 3) and is_planar_stack(self.net):
             return fused_planar_stack(self.net, x)
         for flow in self.net:
             x = flow(x)
